@@ -1,0 +1,86 @@
+"""Generate the committed golden fixtures (build container only; needs /root/reference).
+
+    python tests/golden/make_golden.py
+
+For each of the reference's two primary known-answer sets:
+  * c1_<set>_batch.npz     the hot path's INPUT as one scaffold batch: position-major event arrays produced by
+                           oracle/pileup_emul.py from the bundled BAM + the stored Rdic.json (sR2M), reference
+                           base codes, split table (inStrain/profile/fasta.py:56-73, window 10000)
+  * c1_<set>_expected.npz  the reference's OWN stored outputs: raw_snp_table.csv.gz / raw_linkage_table.csv.gz of
+                           `...forRC.IS/raw_data/` (inStrain v1.7.0, pysam 0.16.0.1), re-encoded as arrays
+                           (random columns r2_normalized / d_prime_normalized dropped, as the reference's tests do)
+and null_lut_fdr1e-06.npz = generate_snp_model(NullModel.txt, 1e-6) (snv_utilities.py:14-38) as an int LUT.
+"""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import bamio, pileup_emul, ref_harness, restate  # noqa: E402
+from oracle.validate_against_reference import load_set  # noqa: E402
+
+CLS = {n: i for i, n in enumerate(restate.CLASS_NAMES)}
+B = {b: i for i, b in enumerate("ACTG")}
+
+
+def make_batch(which, window=10000):
+    refs, by_tid, seqs, rdic, raw = load_set(which)
+    names, lens, offs = [], [], []
+    ref_codes, ev_pos, ev_base, ev_qual, ev_rid, pair_mm, splits = [], [], [], [], [], [], []
+    off, pair_off = 0, 0
+    for tid, (name, length) in enumerate(refs):
+        if name not in rdic:
+            continue
+        seq = seqs[name]
+        ev = restate.sort_events(pileup_emul.scaffold_events(by_tid.get(tid, []), rdic[name]))
+        names.append(name)
+        lens.append(len(seq))
+        offs.append(off)
+        ref_codes.append(restate.encode_ref(seq))
+        ev_pos.append(ev["ref_pos"] + off)
+        ev_base.append(ev["base"])
+        ev_qual.append(ev["qual"])
+        ev_rid.append(ev["read_id"] + pair_off)
+        pair_mm.append(ev["pair_mm"])
+        splits.extend([(s + off, e + off) for s, e in bamio.iterate_splits(len(seq), window)])
+        off += len(seq)
+        pair_off += len(ev["pair_mm"])
+    cat = np.concatenate
+    batch = dict(scaffold_names=np.array(names), scaffold_len=np.array(lens, np.int32),
+                 scaffold_off=np.array(offs, np.int32), ref_codes=cat(ref_codes),
+                 ref_pos=cat(ev_pos).astype(np.int32), base=cat(ev_base), qual=cat(ev_qual),
+                 read_id=cat(ev_rid).astype(np.int32), pair_mm=cat(pair_mm).astype(np.int32),
+                 splits=np.array(splits, np.int32))
+    name2off = dict(zip(names, offs))
+    snp = pd.read_csv(os.path.join(raw, "raw_snp_table.csv.gz"))
+    ld = pd.read_csv(os.path.join(raw, "raw_linkage_table.csv.gz"))
+    soff = snp["scaffold"].map(name2off).values
+    loff = ld["scaffold"].map(name2off).values
+    exp = dict(
+        snv_pos=(snp["position"].values + soff).astype(np.int32), snv_mm=snp["mm"].values.astype(np.int32),
+        snv_cnt=snp[["A", "C", "T", "G"]].values.astype(np.int32),
+        snv_con=snp["con_base"].map(B).values.astype(np.uint8), snv_var=snp["var_base"].map(B).values.astype(np.uint8),
+        snv_allele_count=snp["allele_count"].values.astype(np.uint8),
+        snv_cls=snp["class"].map(CLS).values.astype(np.uint8), snv_cryptic=snp["cryptic"].values.astype(np.uint8),
+        ld_pos_a=(ld["position_A"].values + loff).astype(np.int32),
+        ld_pos_b=(ld["position_B"].values + loff).astype(np.int32), ld_mm=ld["mm"].values.astype(np.int32),
+        ld_counts=ld[["countAB", "countAb", "countaB", "countab"]].values.astype(np.int32),
+        ld_alleles=np.stack([ld[c].map(B).values for c in ("allele_A", "allele_a", "allele_B", "allele_b")], 1).astype(np.uint8),
+        ld_r2=ld["r2"].values.astype(np.float64), ld_d_prime=ld["d_prime"].values.astype(np.float64))
+    return batch, exp
+
+
+if __name__ == "__main__":
+    model = ref_harness.null_model(1e-6)
+    lut, dflt = restate.lut_from_model(model)
+    np.savez_compressed(os.path.join(HERE, "null_lut_fdr1e-06.npz"), lut=lut, default=np.int32(dflt))
+    for which in ("G1", "G2"):
+        batch, exp = make_batch(which)
+        np.savez_compressed(os.path.join(HERE, "c1_%s_batch.npz" % which), **batch)
+        np.savez_compressed(os.path.join(HERE, "c1_%s_expected.npz" % which), **exp)
+        print(which, "events", len(batch["ref_pos"]), "pairs", len(batch["pair_mm"]), "L", len(batch["ref_codes"]),
+              "snv rows", len(exp["snv_pos"]), "ld rows", len(exp["ld_pos_a"]))

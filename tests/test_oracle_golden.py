@@ -1,0 +1,47 @@
+"""Pin the oracle (oracle/oracle.c via oracle/restate.py) against the reference's golden vectors.
+
+The expected arrays are the reference's OWN stored outputs (`raw_snp_table`, `raw_linkage_table` of the two
+`forRC.IS` profile directories, inStrain v1.7.0) -- see tests/golden/make_golden.py.  This mirrors the reference's
+exact-match regression test (test/tests/test_profile.py:831-1206) for the hot path's two tables.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from oracle import restate
+
+
+def expected_rows(exp, ref_codes):
+    snv = np.zeros(len(exp["snv_pos"]), dtype=restate.SNV_DT)
+    snv["pos"], snv["mm"], snv["cnt"] = exp["snv_pos"], exp["snv_mm"], exp["snv_cnt"]
+    snv["ref"] = ref_codes[exp["snv_pos"]]
+    snv["con"], snv["var"] = exp["snv_con"], exp["snv_var"]
+    snv["allele_count"], snv["cls"], snv["cryptic"] = exp["snv_allele_count"], exp["snv_cls"], exp["snv_cryptic"]
+    ld = np.zeros(len(exp["ld_pos_a"]), dtype=restate.LD_DT)
+    ld["pos_a"], ld["pos_b"], ld["mm"] = exp["ld_pos_a"], exp["ld_pos_b"], exp["ld_mm"]
+    for i, f in enumerate(("c_AB", "c_Ab", "c_aB", "c_ab")):
+        ld[f] = exp["ld_counts"][:, i]
+    for i, f in enumerate(("allele_A", "allele_a", "allele_B", "allele_b")):
+        ld[f] = exp["ld_alleles"][:, i]
+    ld["r2"], ld["d_prime"] = exp["ld_r2"], exp["ld_d_prime"]
+    return snv, ld
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_oracle_reproduces_reference_goldens(which, null_lut):
+    batch, exp = load_batch(which)
+    lut, dflt = null_lut
+    out = restate.profile_events(batch, batch["ref_codes"], lut, dflt, batch["splits"])
+    snv, ld = expected_rows(exp, batch["ref_codes"])
+    assert_snv_equal(out["snv"], snv)
+    assert_ld_equal(out["ld"], ld, tol=1e-9)
+    # test_profile_13 (test/tests/test_profile.py:726-750): position_coverage == sum covT[mm' <= mm][pos]
+    cov_cum = np.cumsum(out["covT"], axis=1)
+    assert np.array_equal(cov_cum[out["snv"]["pos"], out["snv"]["mm"]], out["snv"]["cnt"].sum(1))
+
+
+def test_null_lut_shape(null_lut):
+    lut, dflt = null_lut
+    assert dflt == 17 and lut[0] == -1 and lut[5] == 2 and len(lut) == 10000
