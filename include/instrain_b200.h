@@ -1,0 +1,179 @@
+/* instrain_b200.h -- C ABI of libinstrain_b200.so: the B200 (sm_100a) implementation of the
+ * `inStrain profile` hot path (pileup counts -> per-site SNV call -> pairwise SNV linkage).
+ *
+ * The reference has no FFI: its seam is the Python call
+ *     inStrain.profile.profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs)      inStrain/profile/__init__.py:7-18
+ * and, one level lower, per split
+ *     profile_split(samfile, scaffold, start, end, split_number, seq, R2M, null_model, **kwargs)
+ *                                                                          inStrain/profile/profile_utilities.py:115-216
+ * This library replaces the body of profile_split (every function listed below) for a whole *batch* of
+ * scaffolds/splits at once; the Python shim `instrain_b200.profile` binds it with ctypes.
+ *
+ * Data model (one "batch" = any number of scaffolds concatenated into one int32 coordinate space):
+ *   events   columnar, POSITION-MAJOR (sorted by ref_pos; within a position = pileup column order = BAM order):
+ *              ref_pos int32, base uint8 (0..3 = A,C,T,G  -- inStrain's order, profile_utilities.py:34-35;
+ *              4 = any other in-alignment base), qual uint8 (after htslib's mate-overlap tweak),
+ *              read_id int32 (index of the read PAIR = the reference's `query_name` key of R2M)
+ *   pair_mm  uint8[n_pairs]   R2M value (summed NM of the pair, filter_reads.py:917-928); 0 in set mode
+ *   ref      uint8[L]         reference base codes (0..3, 4 = not A/C/G/T), upper-cased sequence (fasta.py:25-27)
+ *   splits   int32[n_splits][2]  (start,end) inclusive, ascending, disjoint, in batch coordinates (fasta.py:56-73);
+ *                             linkage never crosses a split (profile_utilities.py:165,184-185)
+ * Only reads whose name is in R2M are packed (others are never counted: profile_utilities.py:277-283).
+ *
+ * Every pointer argument may be a HOST pointer or a DEVICE pointer (detected with cudaPointerGetAttributes);
+ * host buffers are staged through context-owned device buffers.  No torch types cross this boundary.
+ * All functions return 0 on success or a negative ISB_ERR_* code; isb_last_error() gives the message.
+ * One context per GPU; a context is not thread-safe.  There is NO CPU fallback: without a CUDA device
+ * isb_create() fails.
+ */
+#ifndef INSTRAIN_B200_H
+#define INSTRAIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISB_ABI_VERSION 1
+
+#define ISB_OK 0
+#define ISB_ERR_CUDA (-1)        /* CUDA runtime error (message has the cudaError string) */
+#define ISB_ERR_ARG (-2)         /* invalid argument (M out of range, null pointer, misaligned pointer ...) */
+#define ISB_ERR_CAPACITY (-3)    /* an output row buffer is too small; n_* hold the required sizes */
+#define ISB_ERR_ORDER (-4)       /* events are not position-major */
+#define ISB_ERR_UNSUPPORTED (-5) /* input outside the supported envelope (e.g. a pair with >2 reads on one site) */
+
+#define ISB_MAX_MM 64            /* mm levels M = max(pair_mm)+1 must be <= 64 */
+
+/* site_flags byte written by isb_call_snvs: low nibble = the reference's `bases` set (bit b = base b was con/var
+ * of a multi-allelic call at some mm), 0x10 = anySNP (snv_utilities.py:84-140): the site takes part in linkage. */
+#define ISB_SITE_ANYSNP 0x10
+
+/* class codes of isb_snv_row.cls (calc_snp_class, snv_utilities.py:198-223) */
+enum { ISB_CLS_AMBIGUOUS_REFERENCE = 0, ISB_CLS_DIVERGENT_SITE = 1, ISB_CLS_SNS = 2, ISB_CLS_SNV = 3,
+       ISB_CLS_CON_SNV = 4, ISB_CLS_POP_SNV = 5 };
+
+/* One row of the reference's raw_snp_table (Stable, snv_utilities.py:119-130).  32 bytes. */
+typedef struct {
+    int32_t pos;          /* batch coordinate */
+    int32_t cnt[4];       /* A,C,T,G counts cumulative over mm' <= mm (mm_counts_to_counts, profile_utilities.py:297-312) */
+    int32_t mm;
+    uint8_t ref;          /* reference base code */
+    uint8_t con;          /* con_base */
+    uint8_t var;          /* var_base */
+    uint8_t allele_count; /* "morphia" */
+    uint8_t cls;          /* ISB_CLS_* */
+    uint8_t cryptic;      /* p2c[pos] (snv_utilities.py:137-144) */
+    uint8_t pad[2];
+} isb_snv_row;
+
+/* One row of the reference's raw_linkage_table (_calc_ld_single, linkage.py:138-240; without the two
+ * unseeded-random "normalized" columns).  48 bytes. */
+typedef struct {
+    int32_t pos_a, pos_b; /* batch coordinates, pos_a <= pos_b */
+    int32_t mm;
+    int32_t c_AB, c_Ab, c_aB, c_ab;
+    uint8_t allele_A, allele_a, allele_B, allele_b;
+    double r2, d_prime;   /* NaN where the reference yields np.nan */
+} isb_ld_row;
+
+typedef struct isb_ctx isb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* null_lut[t] = minimum alt count at coverage t, or -1 where the reference's model dict has no key t;
+ * lut_default = model[-1]  (generate_snp_model, snv_utilities.py:14-38; lookup at :173-176). */
+isb_ctx *isb_create(int device, const int32_t *null_lut, int n_lut, int lut_default);
+void isb_destroy(isb_ctx *ctx);
+const char *isb_last_error(const isb_ctx *ctx);   /* ctx may be NULL: error of the last failed isb_create */
+int isb_abi_version(void);
+/* Run on `stream` (a cudaStream_t) instead of the context's own stream; 0 restores the own stream. */
+int isb_set_stream(isb_ctx *ctx, void *stream);
+int isb_synchronize(isb_ctx *ctx);
+
+/* ---- stage K1: pileup counts ------------------------------------------------------------------------------- */
+/* Replaces pysam's column iteration + get_base_counts_mm (profile_utilities.py:268-286):
+ *   counts[p-start][mm][base] += 1  for every event with qual >= min_qual and base < 4
+ *   nmask[p-start] |= 1<<mm         for every event with qual >= min_qual and base == 4  (the mm key that the
+ *                                   reference's defaultdict creates before P2C[...] raises, :280-281)
+ * counts is int32[L][M][4] and is overwritten (not accumulated); nmask is uint64[L] (may be NULL).
+ * Events must be position-major unless ISB_K1_ANY_ORDER is set in `flags` (slower global-atomic path). */
+#define ISB_K1_ANY_ORDER 0x1
+int isb_pileup_counts(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const uint8_t *base,
+                      const uint8_t *qual, const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm,
+                      int32_t start, int32_t L, int M, int min_qual, uint32_t flags,
+                      int32_t *counts, uint64_t *nmask);
+
+/* ---- stage K2: SNV calling ----------------------------------------------------------------------------------- */
+/* Replaces update_covT (profile_utilities.py:288-295), update_snp_table / call_snv_site / calc_snp_class /
+ * calculate_clonality (snv_utilities.py:40-231) and is_present (readComparer.py:307-316) for L positions.
+ *   covT[p][m]   = exact-mm coverage (int32)           clonT[p][m] = clonality of cumulative counts (float32, NaN = unset)
+ *   site_flags[p] see ISB_SITE_ANYSNP                   rows: unordered; *n_rows = number produced (also when > cap)
+ * clonTR (rarefied, unseeded RNG in the reference, snv_utilities.py:233-247) is not produced. */
+int isb_call_snvs(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const uint64_t *nmask, const uint8_t *ref,
+                  int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT, uint8_t *site_flags,
+                  isb_snv_row *rows, int64_t cap, int64_t *n_rows);
+
+/* ---- stage K3: linkage --------------------------------------------------------------------------------------- */
+/* Replaces update_linked_reads, calc_mm_SNV_linkage_network, calculate_ld, _iterator_ld_sites,
+ * major_minor_allele and the deterministic part of _calc_ld_single (linkage.py:14-198, 254-283).
+ * Needs the position-major events again plus K1/K2 outputs.  rows unordered; *n_rows as above. */
+int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                int min_qual, const int32_t *counts, const uint64_t *nmask, const uint8_t *site_flags,
+                int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap, int64_t *n_rows);
+
+/* ---- whole path for one batch (what the profile_bam shim calls) ------------------------------------------------ */
+typedef struct {
+    int64_t n_events;
+    const int32_t *ref_pos;
+    const uint8_t *base;
+    const uint8_t *qual;
+    const int32_t *read_id;
+    int64_t n_pairs;
+    const uint8_t *pair_mm;
+    int32_t start;            /* coordinate of position row 0 */
+    int32_t L;
+    const uint8_t *ref;
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+} isb_batch;
+
+typedef struct {
+    int32_t min_cov;          /* -c/--min_cov 5          (argumentParser.py:107) */
+    int32_t min_snp;          /* --min_snp 20            (argumentParser.py:157) */
+    int32_t min_qual;         /* min_base_quality=30     (profile_utilities.py:152) */
+    uint32_t flags;           /* ISB_SKIP_LINKAGE ... */
+    double min_freq;          /* -f/--min_freq 0.05      (argumentParser.py:109) */
+} isb_params;
+#define ISB_SKIP_LINKAGE 0x2   /* K1+K2 only (BASELINE config 2) */
+#define ISB_NO_SYNC 0x4        /* all-device buffers only: enqueue and return; row counts valid after isb_synchronize */
+
+typedef struct {
+    /* outputs (host or device); any may be NULL to skip the copy-out (the kernels still run) */
+    int32_t *counts;          /* [L][M][4] */
+    uint64_t *nmask;          /* [L] */
+    int32_t *covT;            /* [L][M] */
+    float *clonT;             /* [L][M] */
+    uint8_t *site_flags;      /* [L] */
+    isb_snv_row *snv;
+    int64_t snv_cap;
+    isb_ld_row *ld;
+    int64_t ld_cap;
+    /* filled by the call */
+    int64_t n_snv;
+    int64_t n_ld;
+    int64_t n_sites;          /* linkage-eligible (anySNP) sites */
+    int64_t n_site_pairs;     /* site pairs evaluated by the linkage kernel */
+} isb_result;
+
+int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out);
+
+/* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
+int64_t isb_launch_count(const isb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTRAIN_B200_H */

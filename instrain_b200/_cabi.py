@@ -1,0 +1,113 @@
+"""ctypes binding of libinstrain_b200.so (include/instrain_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is visible, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libinstrain_b200.so")
+
+ISB_OK = 0
+ISB_ERR_CUDA, ISB_ERR_ARG, ISB_ERR_CAPACITY, ISB_ERR_ORDER, ISB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+ISB_K1_ANY_ORDER = 0x1
+ISB_SKIP_LINKAGE = 0x2
+ISB_NO_SYNC = 0x4
+ISB_SITE_ANYSNP = 0x10
+ISB_MAX_MM = 64
+
+SNV_DT = np.dtype([("pos", "<i4"), ("cnt", "<i4", (4,)), ("mm", "<i4"), ("ref", "u1"), ("con", "u1"),
+                   ("var", "u1"), ("allele_count", "u1"), ("cls", "u1"), ("cryptic", "u1"), ("pad", "u1", (2,))])
+LD_DT = np.dtype([("pos_a", "<i4"), ("pos_b", "<i4"), ("mm", "<i4"), ("c_AB", "<i4"), ("c_Ab", "<i4"),
+                  ("c_aB", "<i4"), ("c_ab", "<i4"), ("allele_A", "u1"), ("allele_a", "u1"), ("allele_B", "u1"),
+                  ("allele_b", "u1"), ("r2", "<f8"), ("d_prime", "<f8")])
+assert SNV_DT.itemsize == 32 and LD_DT.itemsize == 48
+
+CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "pop_SNV"]
+
+# every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
+EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
+           "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_launch_count"]
+
+
+class IsbBatch(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("ref_pos", C.c_void_p), ("base", C.c_void_p), ("qual", C.c_void_p),
+                ("read_id", C.c_void_p), ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
+                ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
+                ("M", C.c_int32)]
+
+
+class IsbParams(C.Structure):
+    _fields_ = [("min_cov", C.c_int32), ("min_snp", C.c_int32), ("min_qual", C.c_int32), ("flags", C.c_uint32),
+                ("min_freq", C.c_double)]
+
+
+class IsbResult(C.Structure):
+    _fields_ = [("counts", C.c_void_p), ("nmask", C.c_void_p), ("covT", C.c_void_p), ("clonT", C.c_void_p),
+                ("site_flags", C.c_void_p), ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("ld", C.c_void_p),
+                ("ld_cap", C.c_int64), ("n_snv", C.c_int64), ("n_ld", C.c_int64), ("n_sites", C.c_int64),
+                ("n_site_pairs", C.c_int64)]
+
+
+class IsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libinstrain_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and declare prototypes.  Raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libinstrain_b200.so is not built (%s). Run `python -m instrain_b200.build` (needs nvcc); "
+                          "instrain_b200 has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double
+    L.isb_create.restype = vp
+    L.isb_create.argtypes = [C.c_int, vp, C.c_int, C.c_int]
+    L.isb_destroy.restype = None
+    L.isb_destroy.argtypes = [vp]
+    L.isb_last_error.restype = C.c_char_p
+    L.isb_last_error.argtypes = [vp]
+    L.isb_abi_version.restype = C.c_int
+    L.isb_set_stream.restype = C.c_int
+    L.isb_set_stream.argtypes = [vp, vp]
+    L.isb_synchronize.restype = C.c_int
+    L.isb_synchronize.argtypes = [vp]
+    L.isb_launch_count.restype = i64
+    L.isb_launch_count.argtypes = [vp]
+    L.isb_pileup_counts.restype = C.c_int
+    L.isb_pileup_counts.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, C.c_int, C.c_int, u32, vp, vp]
+    L.isb_call_snvs.restype = C.c_int
+    L.isb_call_snvs.argtypes = [vp, i32, C.c_int, vp, vp, vp, i32, C.c_int, dbl, vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.isb_linkage.restype = C.c_int
+    L.isb_linkage.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, C.c_int, C.c_int, vp, vp, vp, i32, vp,
+                              C.c_int, vp, i64, C.POINTER(i64)]
+    L.isb_profile_batch.restype = C.c_int
+    L.isb_profile_batch.argtypes = [vp, C.POINTER(IsbBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    _lib = L
+    return L
+
+
+def ptr(a):
+    """Host numpy array / torch tensor (host or CUDA) / int / None -> c_void_p value."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr()
+    raise TypeError("unsupported buffer type %r" % type(a))

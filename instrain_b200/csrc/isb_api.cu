@@ -1,0 +1,342 @@
+// isb_api.cu -- context, host<->device staging and the extern "C" entry points of libinstrain_b200.so.
+// See include/instrain_b200.h for the contract; each entry point cites the reference code it replaces there.
+#include "isb_common.cuh"
+
+static char g_create_err[512] = "";
+
+int isb_ensure(isb_ctx *ctx, int slot, size_t bytes)
+{
+    isb_devbuf &b = ctx->buf[slot];
+    if (bytes <= b.cap) return ISB_OK;
+    if (b.p) ISB_CUDA(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;     // a little slack so slowly growing batches do not reallocate each time
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes;
+        ISB_CUDA(cudaMalloc(&b.p, want));
+    }
+    b.cap = want;
+    return ISB_OK;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// host pointer -> staged device copy in `slot`; device pointer -> itself
+template <class T>
+static int stage_in(isb_ctx *ctx, int slot, const T *p, size_t count, const T **out)
+{
+    if (!p) { *out = nullptr; return ISB_OK; }
+    if (is_device_ptr(p)) { *out = p; return ISB_OK; }
+    if (count == 0) { *out = nullptr; return ISB_OK; }
+    int rc = isb_ensure(ctx, slot, count * sizeof(T) + 16);
+    if (rc) return rc;
+    ISB_CUDA(cudaMemcpyAsync(ctx->buf[slot].p, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const T *)ctx->buf[slot].p;
+    return ISB_OK;
+}
+
+// output: device pointer -> itself; host pointer or NULL -> scratch in `slot` (copied back by finish_out if host)
+template <class T>
+static int stage_out(isb_ctx *ctx, int slot, T *p, size_t count, T **out)
+{
+    if (p && is_device_ptr(p)) { *out = p; return ISB_OK; }
+    int rc = isb_ensure(ctx, slot, count * sizeof(T) + 16);
+    if (rc) return rc;
+    *out = (T *)ctx->buf[slot].p;
+    return ISB_OK;
+}
+
+template <class T>
+static int finish_out(isb_ctx *ctx, T *host, const T *dev, size_t count)
+{
+    if (!host || (const T *)host == dev || count == 0) return ISB_OK;
+    ISB_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return ISB_OK;
+}
+
+static int check_dev_err(isb_ctx *ctx)
+{
+    const unsigned e = *ctx->h_err;
+    if (!e) return ISB_OK;
+    if (e & ISB_DEV_ERR_ORDER) return isb_fail(ctx, ISB_ERR_ORDER, "events are not position-major (an event lies outside its position tile)");
+    if (e & ISB_DEV_ERR_MM) return isb_fail(ctx, ISB_ERR_ARG, "pair_mm value >= M");
+    if (e & ISB_DEV_ERR_MULT) return isb_fail(ctx, ISB_ERR_UNSUPPORTED, "a read pair has more than 2 qualifying events on one site");
+    return isb_fail(ctx, ISB_ERR_CUDA, "device-side error flag set");
+}
+
+static int fetch_status(isb_ctx *ctx)
+{
+    ISB_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    ISB_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ISB_OK;
+}
+
+extern "C" {
+
+int isb_abi_version(void) { return ISB_ABI_VERSION; }
+
+const char *isb_last_error(const isb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+isb_ctx *isb_create(int device, const int32_t *null_lut, int n_lut, int lut_default)
+{
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "isb_create: no CUDA device (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n_dev || !null_lut || n_lut <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "isb_create: bad device index %d (of %d) or null model", device, n_dev);
+        return nullptr;
+    }
+    isb_ctx *ctx = new isb_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+#define CREATE_CHECK(call)                                                                                     \
+    do {                                                                                                       \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            snprintf(g_create_err, sizeof(g_create_err), "isb_create: %s: %s", #call, cudaGetErrorString(_e)); \
+            delete ctx;                                                                                        \
+            return nullptr;                                                                                    \
+        }                                                                                                      \
+    } while (0)
+    CREATE_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CHECK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CREATE_CHECK(cudaMalloc(&ctx->d_lut, sizeof(int32_t) * (size_t)n_lut));
+    CREATE_CHECK(cudaMemcpy(ctx->d_lut, null_lut, sizeof(int32_t) * (size_t)n_lut, cudaMemcpyHostToDevice));
+    ctx->n_lut = n_lut;
+    ctx->lut_default = lut_default;
+    CREATE_CHECK(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_err, sizeof(unsigned int)));
+    CREATE_CHECK(cudaMemset(ctx->d_err, 0, sizeof(unsigned int)));
+    CREATE_CHECK(cudaMallocHost(&ctx->h_counters, 8 * sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMallocHost(&ctx->h_err, sizeof(unsigned int)));
+    memset(ctx->h_counters, 0, 8 * sizeof(unsigned long long));
+    *ctx->h_err = 0;
+#undef CREATE_CHECK
+    return ctx;
+}
+
+void isb_destroy(isb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < SL_COUNT; ++i)
+        if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int isb_set_stream(isb_ctx *ctx, void *stream)
+{
+    if (!ctx) return ISB_ERR_ARG;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return ISB_OK;
+}
+
+int isb_synchronize(isb_ctx *ctx)
+{
+    if (!ctx) return ISB_ERR_ARG;
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fetch_status(ctx);
+    if (rc) return rc;
+    return check_dev_err(ctx);
+}
+
+int64_t isb_launch_count(const isb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int check_common(isb_ctx *ctx, int32_t L, int M)
+{
+    if (!ctx) return ISB_ERR_ARG;
+    if (M < 1 || M > ISB_MAX_MM) return isb_fail(ctx, ISB_ERR_ARG, "M (mm levels) must be in [1, 64]");
+    if (L < 0) return isb_fail(ctx, ISB_ERR_ARG, "L < 0");
+    return ISB_OK;
+}
+
+int isb_pileup_counts(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                      const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                      int min_qual, uint32_t flags, int32_t *counts, uint64_t *nmask)
+{
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!counts || (n_events > 0 && (!ref_pos || !base || !qual)) || (M > 1 && n_events > 0 && (!read_id || !pair_mm)))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_pileup_counts: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int32_t *d_pos; const uint8_t *d_base, *d_qual, *d_mm; const int32_t *d_rid;
+    if ((rc = stage_in(ctx, SL_REF_POS, ref_pos, (size_t)n_events, &d_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_BASE, base, (size_t)n_events, &d_base))) return rc;
+    if ((rc = stage_in(ctx, SL_QUAL, qual, (size_t)n_events, &d_qual))) return rc;
+    if ((rc = stage_in(ctx, SL_READ_ID, M > 1 ? read_id : nullptr, (size_t)n_events, &d_rid))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, M > 1 ? pair_mm : nullptr, (size_t)n_pairs, &d_mm))) return rc;
+    int32_t *d_counts; uint64_t *d_nmask = nullptr;
+    if ((rc = stage_out(ctx, SL_COUNTS, counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if (nmask && (rc = stage_out(ctx, SL_NMASK, nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = isb_k1_launch(ctx, n_events, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, min_qual, flags, d_counts,
+                            (unsigned long long *)d_nmask))) return rc;
+    if ((rc = finish_out(ctx, counts, d_counts, (size_t)L * M * 4))) return rc;
+    if ((rc = finish_out(ctx, nmask, d_nmask, (size_t)L))) return rc;
+    if ((rc = fetch_status(ctx))) return rc;
+    return check_dev_err(ctx);
+}
+
+int isb_call_snvs(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const uint64_t *nmask, const uint8_t *ref,
+                  int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT, uint8_t *site_flags,
+                  isb_snv_row *rows, int64_t cap, int64_t *n_rows)
+{
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!counts || !ref || !n_rows || (cap > 0 && !rows)) return isb_fail(ctx, ISB_ERR_ARG, "isb_call_snvs: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int32_t *d_counts; const uint64_t *d_nmask; const uint8_t *d_ref;
+    if ((rc = stage_in(ctx, SL_COUNTS, counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if ((rc = stage_in(ctx, SL_NMASK, nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, ref, (size_t)L, &d_ref))) return rc;
+    int32_t *d_covT; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_rows;
+    if ((rc = stage_out(ctx, SL_COVT, covT, (size_t)L * M, &d_covT))) return rc;
+    if ((rc = stage_out(ctx, SL_CLONT, clonT, (size_t)L * M, &d_clonT))) return rc;
+    if ((rc = stage_out(ctx, SL_FLAGS, site_flags, (size_t)L, &d_flags))) return rc;
+    if ((rc = stage_out(ctx, SL_SNV, rows, (size_t)(cap > 0 ? cap : 1), &d_rows))) return rc;
+    if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, min_cov, min_freq,
+                            d_covT, d_clonT, d_flags, d_rows, cap))) return rc;
+    if ((rc = finish_out(ctx, covT, d_covT, (size_t)L * M))) return rc;
+    if ((rc = finish_out(ctx, clonT, d_clonT, (size_t)L * M))) return rc;
+    if ((rc = finish_out(ctx, site_flags, d_flags, (size_t)L))) return rc;
+    if ((rc = fetch_status(ctx))) return rc;
+    *n_rows = (int64_t)ctx->h_counters[0];
+    const int64_t n_copy = *n_rows < cap ? *n_rows : cap;
+    if ((rc = finish_out(ctx, rows, d_rows, (size_t)n_copy))) return rc;
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = check_dev_err(ctx))) return rc;
+    if (*n_rows > cap) return isb_fail(ctx, ISB_ERR_CAPACITY, "isb_call_snvs: row buffer too small");
+    return ISB_OK;
+}
+
+int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                int min_qual, const int32_t *counts, const uint64_t *nmask, const uint8_t *site_flags,
+                int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap, int64_t *n_rows)
+{
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!counts || !site_flags || !n_rows || (cap > 0 && !rows) || (n_splits > 0 && !splits) ||
+        (n_events > 0 && (!ref_pos || !base || !qual || !read_id)) || (M > 1 && !pair_mm))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_linkage: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int32_t *d_pos, *d_rid, *d_counts, *d_splits; const uint8_t *d_base, *d_qual, *d_mm, *d_flags; const uint64_t *d_nmask;
+    if ((rc = stage_in(ctx, SL_REF_POS, ref_pos, (size_t)n_events, &d_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_BASE, base, (size_t)n_events, &d_base))) return rc;
+    if ((rc = stage_in(ctx, SL_QUAL, qual, (size_t)n_events, &d_qual))) return rc;
+    if ((rc = stage_in(ctx, SL_READ_ID, read_id, (size_t)n_events, &d_rid))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, pair_mm, (size_t)n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_COUNTS, counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if ((rc = stage_in(ctx, SL_NMASK, nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = stage_in(ctx, SL_FLAGS, site_flags, (size_t)L, &d_flags))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, splits, (size_t)n_splits * 2, &d_splits))) return rc;
+    isb_ld_row *d_rows;
+    if ((rc = stage_out(ctx, SL_LD, rows, (size_t)(cap > 0 ? cap : 1), &d_rows))) return rc;
+    if ((rc = isb_k3_launch(ctx, n_events, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, min_qual, d_counts,
+                            (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits, min_snp, d_rows, cap))) return rc;
+    if ((rc = fetch_status(ctx))) return rc;
+    *n_rows = (int64_t)ctx->h_counters[1];
+    const int64_t n_copy = *n_rows < cap ? *n_rows : cap;
+    if ((rc = finish_out(ctx, rows, d_rows, (size_t)n_copy))) return rc;
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = check_dev_err(ctx))) return rc;
+    if (*n_rows > cap) return isb_fail(ctx, ISB_ERR_CAPACITY, "isb_linkage: row buffer too small");
+    return ISB_OK;
+}
+
+int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    const int64_t n = in->n_events;
+    if (!in->ref || (n > 0 && (!in->ref_pos || !in->base || !in->qual || !in->read_id)) || (M > 1 && !in->pair_mm) ||
+        (in->n_splits > 0 && !in->splits))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_batch: null input pointer");
+    const bool do_ld = !(prm->flags & ISB_SKIP_LINKAGE);
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int32_t *d_pos, *d_rid, *d_splits; const uint8_t *d_base, *d_qual, *d_mm, *d_ref;
+    if ((rc = stage_in(ctx, SL_REF_POS, in->ref_pos, (size_t)n, &d_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_BASE, in->base, (size_t)n, &d_base))) return rc;
+    if ((rc = stage_in(ctx, SL_QUAL, in->qual, (size_t)n, &d_qual))) return rc;
+    if ((rc = stage_in(ctx, SL_READ_ID, in->read_id, (size_t)n, &d_rid))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    int32_t *d_counts, *d_covT; uint64_t *d_nmask; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_snv; isb_ld_row *d_ld;
+    if ((rc = stage_out(ctx, SL_COUNTS, out->counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if ((rc = stage_out(ctx, SL_NMASK, out->nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = stage_out(ctx, SL_COVT, out->covT, (size_t)L * M, &d_covT))) return rc;
+    if ((rc = stage_out(ctx, SL_CLONT, out->clonT, (size_t)L * M, &d_clonT))) return rc;
+    if ((rc = stage_out(ctx, SL_FLAGS, out->site_flags, (size_t)L, &d_flags))) return rc;
+    const int64_t snv_cap = out->snv ? out->snv_cap : 0, ld_cap = out->ld ? out->ld_cap : 0;
+    if ((rc = stage_out(ctx, SL_SNV, out->snv, (size_t)(snv_cap > 0 ? snv_cap : 1), &d_snv))) return rc;
+    if ((rc = stage_out(ctx, SL_LD, out->ld, (size_t)(ld_cap > 0 ? ld_cap : 1), &d_ld))) return rc;
+
+    if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, in->start, L, M, prm->min_qual, 0, d_counts,
+                            (unsigned long long *)d_nmask))) return rc;
+    if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, in->start, prm->min_cov,
+                            prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
+    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M,
+                                     prm->min_qual, d_counts, (const unsigned long long *)d_nmask, d_flags,
+                                     in->n_splits, d_splits, prm->min_snp, d_ld, ld_cap))) return rc;
+    if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
+    if ((rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
+    if ((rc = finish_out(ctx, out->covT, d_covT, (size_t)L * M))) return rc;
+    if ((rc = finish_out(ctx, out->clonT, d_clonT, (size_t)L * M))) return rc;
+    if ((rc = finish_out(ctx, out->site_flags, d_flags, (size_t)L))) return rc;
+    if (prm->flags & ISB_NO_SYNC) {
+        out->n_snv = out->n_ld = out->n_sites = out->n_site_pairs = -1;
+        return ISB_OK;
+    }
+    if ((rc = fetch_status(ctx))) return rc;
+    out->n_snv = (int64_t)ctx->h_counters[0];
+    out->n_ld = (int64_t)ctx->h_counters[1];
+    out->n_sites = (int64_t)ctx->h_counters[2];
+    out->n_site_pairs = (int64_t)ctx->h_counters[3];
+    if ((rc = finish_out(ctx, out->snv, d_snv, (size_t)(out->n_snv < snv_cap ? out->n_snv : snv_cap)))) return rc;
+    if ((rc = finish_out(ctx, out->ld, d_ld, (size_t)(out->n_ld < ld_cap ? out->n_ld : ld_cap)))) return rc;
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = check_dev_err(ctx))) return rc;
+    if ((out->snv && out->n_snv > snv_cap) || (out->ld && do_ld && out->n_ld > ld_cap))
+        return isb_fail(ctx, ISB_ERR_CAPACITY, "isb_profile_batch: row buffer too small (see n_snv / n_ld)");
+    return ISB_OK;
+}
+
+}  // extern "C"

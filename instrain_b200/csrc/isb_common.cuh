@@ -1,0 +1,100 @@
+// isb_common.cuh -- shared declarations for libinstrain_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/instrain_b200.h"
+
+#define ISB_WARP 32
+#define ISB_FULL 0xffffffffu
+
+// device-side error bits (ctx->d_err)
+#define ISB_DEV_ERR_ORDER 0x1u        // event outside its position tile: input not position-major
+#define ISB_DEV_ERR_MM 0x2u           // pair_mm >= M
+#define ISB_DEV_ERR_MULT 0x4u         // a read pair has > 2 qualifying events on one site
+#define ISB_DEV_ERR_ROWBUF 0x8u       // linkage bit-row scratch too small (host grows it and re-runs K3)
+
+enum {  // scratch buffer slots of a context (grow-only device allocations)
+    SL_REF_POS = 0, SL_BASE, SL_QUAL, SL_READ_ID, SL_PAIR_MM, SL_REF, SL_SPLITS,   // staged inputs
+    SL_COUNTS, SL_NMASK, SL_COVT, SL_CLONT, SL_FLAGS, SL_SNV, SL_LD,              // staged outputs
+    SL_TILE_OFF,                                                                   // K1 tile event offsets
+    SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
+    SL_COUNT
+};
+
+struct isb_devbuf {
+    void *p;
+    size_t cap;
+};
+
+struct isb_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    int32_t *d_lut;
+    int n_lut;
+    int lut_default;
+    unsigned long long *d_counters;   // [0]=n_snv rows [1]=n_ld rows [2]=n_sites [3]=n_site_pairs [4]=total row words
+    unsigned int *d_err;
+    unsigned long long *h_counters;   // pinned mirror
+    unsigned int *h_err;
+    int64_t launches;
+    isb_devbuf buf[SL_COUNT];
+    char err[512];
+};
+
+struct isb_site_meta {   // one linkage-eligible site (16 bytes)
+    int32_t ev_lo_rel;   // first event of the site, relative to the site's tile (unused; kept for alignment)
+    int32_t wlo;         // first 32-bit word of the pair-id window
+    int32_t nw;          // words in the window (0: no qualifying event)
+    int32_t split;       // split index, -1 if the position is in no split
+};
+
+#define ISB_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,       \
+                     cudaGetErrorString(_e));                                                      \
+            return ISB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define ISB_LAUNCH_CHECK()                                                                         \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        ISB_CUDA(cudaGetLastError());                                                              \
+    } while (0)
+
+static inline int isb_fail(isb_ctx *ctx, int code, const char *msg)
+{
+    snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return code;
+}
+
+// ---- launchers implemented in the kernel translation units -------------------------------------------------
+int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                  const int32_t *read_id, const uint8_t *pair_mm, int32_t start, int32_t L, int M, int min_qual,
+                  uint32_t flags, int32_t *counts, unsigned long long *nmask);
+int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                  const uint8_t *ref, int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT,
+                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap);
+int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                  const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                  int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
+                  int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap);
+int isb_ensure(isb_ctx *ctx, int slot, size_t bytes);
+
+// ---- small device helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t isb_lower_bound(const int32_t *__restrict__ a, int64_t lo, int64_t hi, int64_t key)
+{
+    // first index in [lo, hi) with a[idx] >= key
+    while (lo < hi) {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if ((int64_t)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}

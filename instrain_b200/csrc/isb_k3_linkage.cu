@@ -1,0 +1,484 @@
+// isb_k3_linkage.cu -- K3: pairwise SNV linkage (r^2, D') from allele co-occurrence on shared read pairs, sm_100a.
+//
+// Replaces update_linked_reads (inStrain/profile/linkage.py:254-283), calc_mm_SNV_linkage_network (:14-44),
+// calculate_ld / _iterator_ld_sites (:46-131), major_minor_allele (:133-136) and the deterministic part of
+// _calc_ld_single (:138-198).  Integer popcount work, no tensor cores.
+//
+// Formulation.  For a linkage-eligible site s (anySNP, allele set `bases`) and allele b, let n_s,b(r) in {0,1,2} be
+// the number of qualifying events of read pair r showing b at s.  The reference's combo count of an edge is
+//      K[b1,b2](s,t; mm<=m) = sum_{r: mm(r)<=m} n_s,b1(r) * n_t,b2(r)              (s < t, same split)
+// because read_to_snvs[mm][name] lists every (site, base) entry of the pair and itertools.combinations pairs them.
+// Pair ids are assigned in BAM order, so the pairs covering a site fall in a narrow id window; per site we keep
+// bit rows over that window only:   any | ge1[b] for b in bases | ge2[b] for b in bases   (n>=1, n>=2 planes).
+// Then K = popc(ge1 & ge1 & mask_m) (+ the ge2 cross terms when a site has a double entry), where mask_m marks the
+// pairs with mm <= m.  A row is emitted for level m only if some pair with mm == m links the two sites
+// (sorted(mm2combo2counts.items()), linkage.py:93).  Self edges (a pair entered twice on ONE site, which htslib's
+// overlap quirk can produce) are handled by a slow exact path.
+#include "isb_common.cuh"
+#include "isb_scan.cuh"
+#include <math_constants.h>
+
+#define K3_THREADS 256
+
+struct k3_args {
+    // events
+    int64_t n;
+    const int32_t *ref_pos;
+    const uint8_t *base;
+    const uint8_t *qual;
+    const int32_t *read_id;
+    int64_t n_pairs;
+    const uint8_t *pair_mm;
+    int32_t start, L;
+    int M, min_qual, min_snp;
+    const int32_t *counts;
+    const unsigned long long *nmask;
+    const uint8_t *site_flags;
+    int32_t n_splits;
+    const int32_t *splits;
+    // sites
+    int64_t S;
+    const int32_t *site_pos;       // relative position index
+    int64_t *site_ev;              // [2S] event range of the site
+    isb_site_meta *meta;
+    int32_t *site_words;
+    const int64_t *row_off;
+    uint32_t *rows;
+    uint8_t *has2;
+    const uint32_t *mle;           // [M][nwp] pairs with mm <= m (M > 1 only)
+    int64_t nwp;
+    // output
+    isb_ld_row *out;
+    int64_t cap;
+    unsigned long long *n_ld;
+    unsigned long long *n_site_pairs;
+    unsigned int *d_err;
+};
+
+struct FlagFn {
+    const uint8_t *flags;
+    __device__ int operator()(int64_t i) const { return (flags[i] & ISB_SITE_ANYSNP) ? 1 : 0; }
+};
+struct SitePosSink {
+    int32_t *site_pos;
+    __device__ void operator()(int64_t i, int64_t prefix, int v) const { if (v) site_pos[prefix] = (int32_t)i; }
+};
+struct WordsFn {
+    const int32_t *w;
+    __device__ int operator()(int64_t i) const { return w[i]; }
+};
+struct RowOffSink {
+    int64_t *row_off;
+    __device__ void operator()(int64_t i, int64_t prefix, int) const { row_off[i] = prefix; }
+};
+
+__device__ __forceinline__ bool k3_qualifies(const k3_args &a, int64_t e, unsigned bases)
+{
+    const int b = a.base[e];
+    return a.qual[e] >= a.min_qual && b < 4 && ((bases >> b) & 1u);
+}
+
+// ---- per-site event range, pair-id window, split ----------------------------------------------------------------
+__global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    for (int64_t k = warp0; k < a.S; k += n_warps) {
+        const int32_t p = a.site_pos[k];
+        const int64_t abs_pos = (int64_t)p + a.start;
+        const int64_t lo = isb_lower_bound(a.ref_pos, 0, a.n, abs_pos);
+        const int64_t hi = isb_lower_bound(a.ref_pos, lo, a.n, abs_pos + 1);
+        const unsigned bases = a.site_flags[p] & 0xF;
+        int idmin = INT_MAX, idmax = -1;
+        for (int64_t e = lo + lane; e < hi; e += 32)
+            if (k3_qualifies(a, e, bases)) {
+                const int id = a.read_id[e];
+                idmin = min(idmin, id);
+                idmax = max(idmax, id);
+            }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            idmin = min(idmin, __shfl_xor_sync(ISB_FULL, idmin, d));
+            idmax = max(idmax, __shfl_xor_sync(ISB_FULL, idmax, d));
+        }
+        if (lane == 0) {
+            // split = last split whose start <= abs_pos, if abs_pos <= its end
+            int s_lo = 0, s_hi = a.n_splits;
+            while (s_lo < s_hi) {
+                const int mid = (s_lo + s_hi) >> 1;
+                if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
+            }
+            int split = s_lo - 1;
+            if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
+            isb_site_meta m;
+            m.ev_lo_rel = 0;
+            m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
+            m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
+            m.split = split;
+            a.meta[k] = m;
+            a.site_ev[2 * k] = lo;
+            a.site_ev[2 * k + 1] = hi;
+            a.site_words[k] = (1 + 2 * __popc(bases)) * m.nw;
+            a.has2[k] = 0;
+        }
+    }
+}
+
+// ---- bit rows ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K3_THREADS) k3_build_rows(k3_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    for (int64_t k = warp0; k < a.S; k += n_warps) {
+        const isb_site_meta m = a.meta[k];
+        if (m.nw == 0) continue;
+        const int32_t p = a.site_pos[k];
+        const unsigned bases = a.site_flags[p] & 0xF;
+        const int na = __popc(bases);
+        uint32_t *any = a.rows + a.row_off[k];
+        const int64_t lo = a.site_ev[2 * k], hi = a.site_ev[2 * k + 1];
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            if (!k3_qualifies(a, e, bases)) continue;
+            const int b = a.base[e];
+            const int id = a.read_id[e];
+            const int w = (id >> 5) - m.wlo;
+            const uint32_t bit = 1u << (id & 31);
+            const int r = __popc(bases & ((1u << b) - 1u));
+            if (atomicOr(any + w, bit) & bit) a.has2[k] = 1;          // second entry of this pair on this site
+            uint32_t *ge1 = any + (size_t)(1 + r) * m.nw;
+            if (atomicOr(ge1 + w, bit) & bit) {
+                uint32_t *ge2 = any + (size_t)(1 + na + r) * m.nw;
+                if (atomicOr(ge2 + w, bit) & bit) atomicOr(a.d_err, ISB_DEV_ERR_MULT);
+            }
+        }
+    }
+}
+
+// mle[m][w] = bit i set iff pair (32 w + i) has mm <= m
+__global__ void __launch_bounds__(256) k3_mm_masks(const uint8_t *__restrict__ pair_mm, int64_t n_pairs, int M,
+                                                   int64_t nwp, uint32_t *__restrict__ mle)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwp) return;
+    for (int m = 0; m < M; ++m) {
+        uint32_t word = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int64_t id = (w << 5) + i;
+            if (id < n_pairs && pair_mm[id] <= m) word |= 1u << i;
+        }
+        mle[(size_t)m * nwp + w] = word;
+    }
+}
+
+// ---- LD statistics ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void k3_major_minor(const int *c, int &maj, int &mnr)
+{
+    // sorted(d, key=d.get, reverse=True)[:2]: stable, ties keep A,C,T,G order (linkage.py:133-136)
+    int idx[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int x = 1; x < 4; ++x) {
+        const int v = idx[x];
+        int k = x - 1;
+        while (k >= 0 && c[idx[k]] < c[v]) { idx[k + 1] = idx[k]; --k; }
+        idx[k + 1] = v;
+    }
+    maj = idx[0];
+    mnr = idx[1];
+}
+
+__device__ __forceinline__ void k3_emit(const k3_args &a, int32_t p1, int32_t p2, int m, int A, int al, int B, int bl,
+                                        int cAB, int cAb, int caB, int cab)
+{
+    const int total = cAB + cAb + caB + cab;
+    if (!(total > a.min_snp)) return;                                  // strict (linkage.py:165)
+    const double tot = (double)total;
+    const double fAB = __ddiv_rn((double)cAB, tot), fAb = __ddiv_rn((double)cAb, tot);
+    const double faB = __ddiv_rn((double)caB, tot), fab = __ddiv_rn((double)cab, tot);
+    const double fA = __dadd_rn(fAB, fAb), fa = __dadd_rn(fab, faB);
+    const double fB = __dadd_rn(fAB, faB), fb = __dadd_rn(fab, fAb);
+    const double linkD = __dsub_rn(fAB, __dmul_rn(fA, fB));
+    double r2 = CUDART_NAN, dp = CUDART_NAN;
+    if (!(fa == 0.0 || fA == 0.0 || fB == 0.0 || fb == 0.0))
+        r2 = __ddiv_rn(__dmul_rn(linkD, linkD), __dmul_rn(__dmul_rn(__dmul_rn(fA, fa), fB), fb));
+    const double linkd = __dsub_rn(fab, __dmul_rn(fa, fb));
+    if (linkd < 0.0) {
+        const double d1 = __dmul_rn(-fA, fB), d2 = __dmul_rn(-fa, fb);
+        dp = __ddiv_rn(linkd, d1 > d2 ? d1 : d2);
+    } else if (linkD > 0.0) {
+        const double d1 = __dmul_rn(fA, fb), d2 = __dmul_rn(fa, fB);
+        dp = __ddiv_rn(linkd, d1 < d2 ? d1 : d2);
+    }
+    const unsigned long long slot = atomicAdd(a.n_ld, 1ull);
+    if ((int64_t)slot < a.cap) {
+        isb_ld_row r;
+        r.pos_a = p1 + a.start; r.pos_b = p2 + a.start; r.mm = m;
+        r.c_AB = cAB; r.c_Ab = cAb; r.c_aB = caB; r.c_ab = cab;
+        r.allele_A = (uint8_t)A; r.allele_a = (uint8_t)al; r.allele_B = (uint8_t)B; r.allele_b = (uint8_t)bl;
+        r.r2 = r2; r.d_prime = dp;
+        a.out[slot] = r;
+    }
+}
+
+struct k3_site {
+    int32_t p;
+    int wlo, nw, na, has2;
+    unsigned bases;
+    const uint32_t *rows;   // `any` row; ge1[r] at rows + (1+r)*nw; ge2[r] at rows + (1+na+r)*nw
+};
+
+__device__ __forceinline__ k3_site k3_load_site(const k3_args &a, int64_t k)
+{
+    k3_site s;
+    const isb_site_meta m = a.meta[k];
+    s.p = a.site_pos[k];
+    s.wlo = m.wlo; s.nw = m.nw;
+    s.bases = a.site_flags[s.p] & 0xF;
+    s.na = __popc(s.bases);
+    s.has2 = a.has2[k];
+    s.rows = a.rows + a.row_off[k];
+    return s;
+}
+
+__device__ __forceinline__ int k3_rank(unsigned bases, int b)
+{
+    return ((bases >> b) & 1u) ? __popc(bases & ((1u << b) - 1u)) : -1;
+}
+
+// K[b1,b2] over absolute pair-id words [lo, hi), optionally masked (mask indexed by absolute word)
+__device__ __forceinline__ int k3_pair_count(const k3_site &si, int ra, const k3_site &sj, int rb, int lo, int hi,
+                                             const uint32_t *__restrict__ mask)
+{
+    if (ra < 0 || rb < 0) return 0;
+    const uint32_t *a1 = si.rows + (size_t)(1 + ra) * si.nw - si.wlo;
+    const uint32_t *b1 = sj.rows + (size_t)(1 + rb) * sj.nw - sj.wlo;
+    int c = 0;
+    if (!(si.has2 | sj.has2)) {
+        for (int w = lo; w < hi; ++w) {
+            uint32_t x = a1[w] & b1[w];
+            if (mask) x &= __ldg(mask + w);
+            c += __popc(x);
+        }
+    } else {
+        const uint32_t *a2 = si.rows + (size_t)(1 + si.na + ra) * si.nw - si.wlo;
+        const uint32_t *b2 = sj.rows + (size_t)(1 + sj.na + rb) * sj.nw - sj.wlo;
+        for (int w = lo; w < hi; ++w) {
+            const uint32_t mk = mask ? __ldg(mask + w) : 0xffffffffu;
+            const uint32_t x1 = a1[w] & mk, x2 = a2[w] & mk, y1 = b1[w], y2 = b2[w];
+            c += __popc(x1 & y1) + __popc(x2 & y1) + __popc(x1 & y2) + __popc(x2 & y2);   // (g1+g2)*(g1+g2)
+        }
+    }
+    return c;
+}
+
+__device__ __forceinline__ bool k3_level_present(const k3_args &a, int32_t p, int m, const int4 &E)
+{
+    if (E.x + E.y + E.z + E.w > 0) return true;
+    return a.nmask && ((a.nmask[p] >> m) & 1ull);
+}
+
+__device__ void k3_process_pair(const k3_args &a, const k3_site &si, const k3_site &sj, unsigned long long &n_pairs_local)
+{
+    const int lo = max(si.wlo, sj.wlo), hi = min(si.wlo + si.nw, sj.wlo + sj.nw);
+    if (lo >= hi) return;
+    const uint32_t *any_i = si.rows - si.wlo, *any_j = sj.rows - sj.wlo;
+    unsigned long long pm = 0;                                         // mm levels having >= 1 linking pair
+    if (a.M == 1) {
+        for (int w = lo; w < hi; ++w)
+            if (any_i[w] & any_j[w]) { pm = 1ull; break; }
+    } else {
+        for (int w = lo; w < hi; ++w) {
+            uint32_t x = any_i[w] & any_j[w];
+            while (x) {
+                const int b = __ffs(x) - 1;
+                x &= x - 1;
+                pm |= 1ull << __ldg(a.pair_mm + (((int64_t)w << 5) + b));
+            }
+        }
+    }
+    if (!pm) return;
+    ++n_pairs_local;
+    int C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
+    const int m_last = 63 - __clzll(pm);
+    for (int m = 0; m <= m_last; ++m) {
+        const int4 E1 = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)si.p * a.M + m);
+        const int4 E2 = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)sj.p * a.M + m);
+        C1[0] += E1.x; C1[1] += E1.y; C1[2] += E1.z; C1[3] += E1.w;
+        C2[0] += E2.x; C2[1] += E2.y; C2[2] += E2.z; C2[3] += E2.w;
+        if (!((pm >> m) & 1ull)) continue;
+        if (!(k3_level_present(a, si.p, m, E1) && k3_level_present(a, sj.p, m, E2))) continue;   // updateMMs
+        const int s1 = C1[0] + C1[1] + C1[2] + C1[3], s2 = C2[0] + C2[1] + C2[2] + C2[3];
+        if (s1 + s2 < a.min_snp) continue;
+        int A, al, B, bl;
+        k3_major_minor(C1, A, al);
+        k3_major_minor(C2, B, bl);
+        if (C1[A] == 0 || C1[al] == 0 || C2[B] == 0 || C2[bl] == 0) continue;
+        const uint32_t *mask = a.M > 1 ? a.mle + (size_t)m * a.nwp : nullptr;
+        const int rA = k3_rank(si.bases, A), ra = k3_rank(si.bases, al);
+        const int rB = k3_rank(sj.bases, B), rb = k3_rank(sj.bases, bl);
+        const int cAB = k3_pair_count(si, rA, sj, rB, lo, hi, mask);
+        const int cAb = k3_pair_count(si, rA, sj, rb, lo, hi, mask);
+        const int caB = k3_pair_count(si, ra, sj, rB, lo, hi, mask);
+        const int cab = k3_pair_count(si, ra, sj, rb, lo, hi, mask);
+        k3_emit(a, si.p, sj.p, m, A, al, B, bl, cAB, cAb, caB, cab);
+    }
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_pairs(k3_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    unsigned long long n_pairs_local = 0;
+    for (int64_t k = warp0; k < a.S; k += n_warps) {
+        const k3_site si = k3_load_site(a, k);
+        const int split = a.meta[k].split;
+        if (split < 0 || si.nw == 0) continue;
+        for (int64_t jb = k + 1;; jb += 32) {
+            const int64_t j = jb + lane;
+            const bool cand = j < a.S && a.meta[j].split == split;
+            if (!__any_sync(ISB_FULL, cand)) break;
+            if (cand) {
+                const k3_site sj = k3_load_site(a, j);
+                if (sj.nw > 0) k3_process_pair(a, si, sj, n_pairs_local);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n_pairs_local += __shfl_xor_sync(ISB_FULL, n_pairs_local, d);
+    if (lane == 0 && n_pairs_local) atomicAdd(a.n_site_pairs, n_pairs_local);
+}
+
+// Self edges: a pair with two entries (first, second in column order) on ONE site gives the combo
+// "b_first:b_second" on the edge (p, p) (itertools.combinations over the pair's entry list).  Rare: one thread per
+// flagged site, exact and slow.
+__global__ void __launch_bounds__(128) k3_self_edges(k3_args a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.S; k += stride) {
+        if (!a.has2[k] || a.meta[k].split < 0) continue;
+        const int32_t p = a.site_pos[k];
+        const unsigned bases = a.site_flags[p] & 0xF;
+        const int64_t lo = a.site_ev[2 * k], hi = a.site_ev[2 * k + 1];
+        int K[16];
+        for (int i = 0; i < 16; ++i) K[i] = 0;
+        int C[4] = {0, 0, 0, 0};
+        for (int m = 0; m < a.M; ++m) {
+            const int4 E = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)p * a.M + m);
+            C[0] += E.x; C[1] += E.y; C[2] += E.z; C[3] += E.w;
+            bool added = false;
+            for (int64_t e2 = lo; e2 < hi; ++e2) {
+                if (!k3_qualifies(a, e2, bases)) continue;
+                const int rid = a.read_id[e2];
+                if ((a.M > 1 ? a.pair_mm[rid] : 0) != m) continue;
+                for (int64_t e1 = lo; e1 < e2; ++e1)
+                    if (a.read_id[e1] == rid && k3_qualifies(a, e1, bases)) {
+                        K[a.base[e1] * 4 + a.base[e2]] += 1;
+                        added = true;
+                    }
+            }
+            if (!added) continue;
+            if (!k3_level_present(a, p, m, E)) continue;
+            const int s1 = C[0] + C[1] + C[2] + C[3];
+            if (s1 + s1 < a.min_snp) continue;
+            int A, al;
+            k3_major_minor(C, A, al);
+            if (C[A] == 0 || C[al] == 0) continue;
+            k3_emit(a, p, p, m, A, al, A, al, K[A * 4 + A], K[A * 4 + al], K[al * 4 + A], K[al * 4 + al]);
+        }
+    }
+}
+
+int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                  const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                  int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
+                  int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap)
+{
+    cudaStream_t st = ctx->stream;
+    int rc;
+    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), st));
+    if (L <= 0 || n <= 0) return ISB_OK;
+
+    // 1. ordered list of linkage-eligible sites
+    const int nb = (int)(((int64_t)L + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)nb))) return rc;
+    int64_t *block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
+    FlagFn ff{site_flags};
+    scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(ff, (int64_t)L, block_sums);
+    ISB_LAUNCH_CHECK();
+    scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nb, ctx->d_counters + 2);
+    ISB_LAUNCH_CHECK();
+    ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ISB_CUDA(cudaStreamSynchronize(st));
+    const int64_t S = (int64_t)ctx->h_counters[2];
+    if (S == 0) return ISB_OK;
+    if ((rc = isb_ensure(ctx, SL_SITE_POS, sizeof(int32_t) * (size_t)S))) return rc;
+    if ((rc = isb_ensure(ctx, SL_SITE_META, (sizeof(isb_site_meta) + 2 * sizeof(int64_t)) * (size_t)S))) return rc;
+    if ((rc = isb_ensure(ctx, SL_SITE_WORDS, sizeof(int32_t) * (size_t)S))) return rc;
+    if ((rc = isb_ensure(ctx, SL_ROW_OFF, sizeof(int64_t) * (size_t)S))) return rc;
+    if ((rc = isb_ensure(ctx, SL_HAS2, (size_t)S))) return rc;
+    int32_t *site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
+    SitePosSink sps{site_pos};
+    scan_scatter<<<nb, SCAN_THREADS, 0, st>>>(ff, (int64_t)L, block_sums, sps);
+    ISB_LAUNCH_CHECK();
+
+    k3_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.ref_pos = ref_pos; a.base = base; a.qual = qual; a.read_id = read_id;
+    a.n_pairs = n_pairs; a.pair_mm = pair_mm; a.start = start; a.L = L; a.M = M; a.min_qual = min_qual;
+    a.min_snp = min_snp; a.counts = counts; a.nmask = nmask; a.site_flags = site_flags;
+    a.n_splits = n_splits; a.splits = splits;
+    a.S = S; a.site_pos = site_pos;
+    a.site_ev = (int64_t *)ctx->buf[SL_SITE_META].p;
+    a.meta = (isb_site_meta *)((int64_t *)ctx->buf[SL_SITE_META].p + 2 * S);
+    a.site_words = (int32_t *)ctx->buf[SL_SITE_WORDS].p;
+    a.row_off = (int64_t *)ctx->buf[SL_ROW_OFF].p;
+    a.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;
+    a.out = rows; a.cap = cap;
+    a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
+
+    // 2. per-site event range + pair-id window
+    const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;
+    const int grid_sites = (int)(site_warps_blocks < (int64_t)ctx->sm_count * 32 ? site_warps_blocks : (int64_t)ctx->sm_count * 32);
+    k3_site_windows<<<grid_sites, K3_THREADS, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+
+    // 3. bit-row storage offsets
+    const int nbs = (int)((S + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)(nb > nbs ? nb : nbs)))) return rc;
+    block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
+    WordsFn wf{a.site_words};
+    scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums);
+    ISB_LAUNCH_CHECK();
+    scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nbs, ctx->d_counters + 4);
+    ISB_LAUNCH_CHECK();
+    RowOffSink ros{(int64_t *)ctx->buf[SL_ROW_OFF].p};
+    scan_scatter<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums, ros);
+    ISB_LAUNCH_CHECK();
+    ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ISB_CUDA(cudaStreamSynchronize(st));
+    const size_t total_words = (size_t)ctx->h_counters[4];
+    if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (total_words + 4)))) return rc;
+    a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
+    ISB_CUDA(cudaMemsetAsync(a.rows, 0, sizeof(uint32_t) * (total_words + 4), st));
+
+    // 4. mm <= m masks
+    if (M > 1) {
+        a.nwp = (n_pairs + 31) / 32;
+        if ((rc = isb_ensure(ctx, SL_MM_MASK, sizeof(uint32_t) * (size_t)a.nwp * M))) return rc;
+        k3_mm_masks<<<(int)((a.nwp + 255) / 256), 256, 0, st>>>(pair_mm, n_pairs, M, a.nwp, (uint32_t *)ctx->buf[SL_MM_MASK].p);
+        ISB_LAUNCH_CHECK();
+        a.mle = (const uint32_t *)ctx->buf[SL_MM_MASK].p;
+    }
+
+    // 5. rows, pairs, self edges
+    k3_build_rows<<<grid_sites, K3_THREADS, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    k3_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    const int grid_self = (int)((S + 127) / 128 < (int64_t)ctx->sm_count * 8 ? (S + 127) / 128 : (int64_t)ctx->sm_count * 8);
+    k3_self_edges<<<grid_self, 128, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}

@@ -1,0 +1,174 @@
+"""Thin Python face of the C-ABI: one `Engine` per GPU.
+
+Everything here goes through libinstrain_b200.so (instrain_b200/_cabi.py); there is no other compute path.
+Buffers may be numpy arrays (host; staged by the library) or CUDA torch tensors (used in place).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .null_model import load_lut
+
+
+def _is_cuda(a):
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _pair_mm_u8(pair_mm):
+    """The ABI takes uint8 mm values (ISB_MAX_MM = 64); host arrays of another integer dtype are narrowed."""
+    if pair_mm is None or not isinstance(pair_mm, np.ndarray) or pair_mm.dtype == np.uint8:
+        return pair_mm
+    if len(pair_mm) and (pair_mm.min() < 0 or pair_mm.max() > 255):
+        raise ValueError("pair_mm outside [0, 255]")
+    return np.ascontiguousarray(pair_mm, dtype=np.uint8)
+
+
+class Engine:
+    """Owns an isb_ctx (device context + scratch).  Mirrors the per-worker state of the reference's
+    split_profile_worker (inStrain/profile/profile_utilities.py:37-90): null model + open handle."""
+
+    def __init__(self, device=0, null_lut=None, lut_default=None, model_file=None, fdr=1e-6):
+        self.lib = _cabi.load()
+        if null_lut is None:
+            null_lut, lut_default = load_lut(model_file, fdr)
+        null_lut = np.ascontiguousarray(null_lut, dtype=np.int32)
+        self.device = device
+        self.ctx = self.lib.isb_create(device, null_lut.ctypes.data, len(null_lut), int(lut_default))
+        if not self.ctx:
+            raise _cabi.IsbError(_cabi.ISB_ERR_CUDA, self.lib.isb_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.isb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != 0 and rc not in allow:
+            raise _cabi.IsbError(rc, self.lib.isb_last_error(self.ctx).decode())
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.isb_set_stream(self.ctx, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._check(self.lib.isb_synchronize(self.ctx))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.isb_launch_count(self.ctx))
+
+    # ---- stage K1 ----------------------------------------------------------------------------------------------
+    def pileup_counts(self, ev, start, L, M, min_qual=30, any_order=False, counts=None, nmask=None):
+        """ev: dict(ref_pos, base, qual, read_id, pair_mm). Returns (counts[L,M,4] int32, nmask[L] uint64)."""
+        n = len(ev["ref_pos"])
+        pair_mm = _pair_mm_u8(ev.get("pair_mm"))
+        if counts is None:
+            counts = np.empty((L, M, 4), dtype=np.int32)
+        if nmask is None:
+            nmask = np.empty(L, dtype=np.uint64)
+        p = _cabi.ptr
+        self._check(self.lib.isb_pileup_counts(
+            self.ctx, n, p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev.get("read_id")),
+            0 if pair_mm is None else len(pair_mm), p(pair_mm), start, L, M, min_qual,
+            _cabi.ISB_K1_ANY_ORDER if any_order else 0, p(counts), p(nmask)))
+        return counts, nmask
+
+    # ---- stage K2 ----------------------------------------------------------------------------------------------
+    def call_snvs(self, counts, nmask, ref_codes, start=0, min_cov=5, min_freq=0.05, cap=None):
+        L, M = counts.shape[0], counts.shape[1]
+        covT = np.empty((L, M), dtype=np.int32)
+        clonT = np.empty((L, M), dtype=np.float32)
+        flags = np.empty(L, dtype=np.uint8)
+        cap = max(1024, L // 8) if cap is None else cap
+        p = _cabi.ptr
+        while True:
+            rows = np.empty(cap, dtype=_cabi.SNV_DT)
+            n = C.c_int64(0)
+            rc = self._check(self.lib.isb_call_snvs(self.ctx, L, M, p(counts), p(nmask), p(ref_codes), start, min_cov,
+                                                    float(min_freq), p(covT), p(clonT), p(flags), p(rows), cap,
+                                                    C.byref(n)), allow=(_cabi.ISB_ERR_CAPACITY,))
+            if rc == 0:
+                return covT, clonT, flags, rows[:n.value].copy()
+            cap = int(n.value)
+
+    # ---- stage K3 ----------------------------------------------------------------------------------------------
+    def linkage(self, ev, counts, nmask, flags, splits, start=0, min_snp=20, min_qual=30, cap=None):
+        L, M = counts.shape[0], counts.shape[1]
+        splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
+        pair_mm = _pair_mm_u8(ev.get("pair_mm"))
+        cap = 1 << 16 if cap is None else cap
+        p = _cabi.ptr
+        while True:
+            rows = np.empty(cap, dtype=_cabi.LD_DT)
+            n = C.c_int64(0)
+            rc = self._check(self.lib.isb_linkage(
+                self.ctx, len(ev["ref_pos"]), p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev["read_id"]),
+                0 if pair_mm is None else len(pair_mm), p(pair_mm), start, L, M, min_qual, p(counts), p(nmask),
+                p(flags), len(splits), p(splits), min_snp, p(rows), cap, C.byref(n)),
+                allow=(_cabi.ISB_ERR_CAPACITY,))
+            if rc == 0:
+                return rows[:n.value].copy()
+            cap = int(n.value)
+
+    # ---- whole path --------------------------------------------------------------------------------------------
+    def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
+                      min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
+                      snv_cap=None, ld_cap=None):
+        """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
+
+        `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
+        """
+        L = len(ref_codes)
+        pair_mm = _pair_mm_u8(ev["pair_mm"])
+        if M is None:
+            M = int(pair_mm.max()) + 1 if len(pair_mm) else 1
+        if M > _cabi.ISB_MAX_MM:
+            raise ValueError("mm levels M=%d exceeds ISB_MAX_MM=%d" % (M, _cabi.ISB_MAX_MM))
+        splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
+        p = _cabi.ptr
+        batch = _cabi.IsbBatch(len(ev["ref_pos"]), p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev["read_id"]),
+                               len(pair_mm), p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M)
+        prm = _cabi.IsbParams(min_cov, min_snp, min_qual, _cabi.ISB_SKIP_LINKAGE if skip_linkage else 0,
+                              float(min_freq))
+        out = {}
+        if "counts" in want:
+            out["counts"] = np.empty((L, M, 4), dtype=np.int32)
+        if "nmask" in want:
+            out["nmask"] = np.empty(L, dtype=np.uint64)
+        if "covT" in want:
+            out["covT"] = np.empty((L, M), dtype=np.int32)
+        if "clonT" in want:
+            out["clonT"] = np.empty((L, M), dtype=np.float32)
+        if "site_flags" in want:
+            out["site_flags"] = np.empty(L, dtype=np.uint8)
+        snv_cap = max(1024, L // 8) if snv_cap is None else snv_cap
+        ld_cap = (1 << 16) if ld_cap is None else ld_cap
+        while True:
+            snv = np.empty(snv_cap, dtype=_cabi.SNV_DT) if "snv" in want else None
+            ld = np.empty(ld_cap, dtype=_cabi.LD_DT) if ("ld" in want and not skip_linkage) else None
+            res = _cabi.IsbResult(p(out.get("counts")), p(out.get("nmask")), p(out.get("covT")), p(out.get("clonT")),
+                                  p(out.get("site_flags")), p(snv), snv_cap if snv is not None else 0, p(ld),
+                                  ld_cap if ld is not None else 0, 0, 0, 0, 0)
+            rc = self._check(self.lib.isb_profile_batch(self.ctx, C.byref(batch), C.byref(prm), C.byref(res)),
+                             allow=(_cabi.ISB_ERR_CAPACITY,))
+            if rc == 0:
+                break
+            snv_cap = max(snv_cap, int(res.n_snv))
+            ld_cap = max(ld_cap, int(res.n_ld))
+        if snv is not None:
+            out["snv"] = snv[:res.n_snv].copy()
+        if ld is not None:
+            out["ld"] = ld[:res.n_ld].copy()
+        elif "ld" in want:
+            out["ld"] = np.zeros(0, dtype=_cabi.LD_DT)
+        out["n_snv"], out["n_ld"], out["n_sites"], out["n_site_pairs"] = (int(res.n_snv), int(res.n_ld),
+                                                                          int(res.n_sites), int(res.n_site_pairs))
+        out["M"] = M
+        return out

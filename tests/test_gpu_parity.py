@@ -1,0 +1,218 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, instrain_b200.engine.Engine) against the oracle
+(oracle/restate.py -> oracle/oracle.c) on identical inputs, and against the reference's golden tables.
+
+Bar (BASELINE.json north_star): per-position counts and SNV calls bit-exact; r2 / d_prime within 1e-6
+(the comparisons below use 1e-9; the integer fields of linkage rows are compared exactly).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from oracle import restate, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(null_lut):
+    from instrain_b200.engine import Engine
+    e = Engine(0, null_lut[0], null_lut[1])
+    yield e
+    e.close()
+
+
+def oracle_all(batch, null_lut, **kw):
+    return restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"], **kw)
+
+
+def check_batch(eng, batch, null_lut, tol=1e-9, **kw):
+    exp = oracle_all(batch, null_lut, **kw)
+    M = exp["counts"].shape[1]
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M,
+                            want=("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld"), **kw)
+    assert np.array_equal(got["counts"], exp["counts"])
+    assert np.array_equal(got["nmask"], exp["nmask"])
+    assert np.array_equal(got["covT"], exp["covT"])
+    # clonality: float32 bit patterns identical (NaN = unset)
+    assert np.array_equal(got["clonT"].view(np.uint32) == 0x7FC00000, np.isnan(exp["clonT"])) or \
+        np.array_equal(np.isnan(got["clonT"]), np.isnan(exp["clonT"]))
+    ok = ~np.isnan(exp["clonT"])
+    assert np.array_equal(got["clonT"][ok].view(np.uint32), exp["clonT"][ok].view(np.uint32))
+    assert np.array_equal(got["site_flags"], exp["site_flags"])
+    assert_snv_equal(got["snv"], exp["snv"])
+    assert_ld_equal(got["ld"], exp["ld"], tol=tol)
+    return got, exp
+
+
+# ---- golden vectors of the reference -------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_golden_tables_through_cabi(eng, which, null_lut):
+    """The CUDA path reproduces the reference's stored raw_snp_table / raw_linkage_table (inStrain v1.7.0)."""
+    from test_oracle_golden import expected_rows
+    batch, exp = load_batch(which)
+    got, _ = check_batch(eng, batch, null_lut)
+    snv, ld = expected_rows(exp, batch["ref_codes"])
+    assert_snv_equal(got["snv"], snv)
+    assert_ld_equal(got["ld"], ld, tol=1e-6)
+    # test_profile_13 (reference test/tests/test_profile.py:726-750)
+    cov_cum = np.cumsum(got["covT"], axis=1)
+    assert np.array_equal(cov_cum[got["snv"]["pos"], got["snv"]["mm"]], got["snv"]["cnt"].sum(1))
+
+
+# ---- stage entry points ----------------------------------------------------------------------------------------------
+def test_stage_entry_points(eng, null_lut):
+    batch, _ = load_batch("G1")
+    exp = oracle_all(batch, null_lut)
+    L, M = exp["counts"].shape[:2]
+    counts, nmask = eng.pileup_counts(batch, 0, L, M)
+    assert np.array_equal(counts, exp["counts"]) and np.array_equal(nmask, exp["nmask"])
+    covT, clonT, flags, snv = eng.call_snvs(counts, nmask, batch["ref_codes"], cap=16)   # forces the capacity retry
+    assert np.array_equal(covT, exp["covT"]) and np.array_equal(flags, exp["site_flags"])
+    assert_snv_equal(snv, exp["snv"])
+    ld = eng.linkage(batch, counts, nmask, flags, batch["splits"], cap=16)
+    assert_ld_equal(ld, exp["ld"], tol=1e-9)
+
+
+def test_any_order_counts(eng, null_lut):
+    """ISB_K1_ANY_ORDER: BAM-order (unsorted) events give the same counts through the atomic path."""
+    batch, _ = load_batch("G1")
+    exp = oracle_all(batch, null_lut, do_linkage=False)
+    L, M = exp["counts"].shape[:2]
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(len(batch["ref_pos"]))
+    ev = {k: np.ascontiguousarray(batch[k][perm]) for k in ("ref_pos", "base", "qual", "read_id")}
+    ev["pair_mm"] = batch["pair_mm"]
+    counts, nmask = eng.pileup_counts(ev, 0, L, M, any_order=True)
+    assert np.array_equal(counts, exp["counts"]) and np.array_equal(nmask, exp["nmask"])
+
+
+def test_unsorted_events_rejected(eng):
+    from instrain_b200 import _cabi
+    batch, _ = load_batch("G1")
+    ev = {k: batch[k].copy() for k in ("ref_pos", "base", "qual", "read_id", "pair_mm")}
+    ev["ref_pos"][1000:200000] = ev["ref_pos"][1000:200000][::-1].copy()
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.pileup_counts(ev, 0, len(batch["ref_codes"]), int(batch["pair_mm"].max()) + 1)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+
+
+def test_argument_errors(eng):
+    from instrain_b200 import _cabi
+    ev = dict(ref_pos=np.zeros(4, np.int32), base=np.zeros(4, np.uint8), qual=np.full(4, 40, np.uint8),
+              read_id=np.zeros(4, np.int32), pair_mm=np.array([70], np.uint8))
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.pileup_counts(ev, 0, 8, 65)
+    assert ei.value.code == _cabi.ISB_ERR_ARG
+    with pytest.raises(_cabi.IsbError) as ei:            # mm value >= M
+        eng.pileup_counts(ev, 0, 8, 3)
+    assert ei.value.code == _cabi.ISB_ERR_ARG
+
+
+# ---- synthetic configs -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,cov,dens,nsc,skip_mm,n_frac,seed", [
+    (30000, 50, 0.01, 2, False, 0.0, 20260102),     # config-2 shaped, M ~ 12
+    (30000, 50, 0.01, 1, True, 0.0, 20260102),      # --skip_mm_profiling, M = 1
+    (12000, 100, 0.05, 1, False, 0.002, 20260105),  # LD-stress shaped + non-ACGT read bases (nmask)
+    (700, 30, 0.02, 3, False, 0.0, 7),              # tiny scaffolds (test_profile_18), one split each
+    (25000, 8, 0.01, 1, False, 0.0, 11),            # low coverage around min_cov
+])
+def test_synthetic_parity(eng, null_lut, L, cov, dens, nsc, skip_mm, n_frac, seed):
+    batch = synth.make_batch(L, cov, dens, seed, n_scaffolds=nsc, skip_mm=skip_mm, n_frac=n_frac)
+    got, exp = check_batch(eng, batch, null_lut)
+    assert len(exp["snv"]) > 0
+
+
+def test_thresholds_are_parameters(eng, null_lut):
+    batch = synth.make_batch(20000, 40, 0.02, 3)
+    check_batch(eng, batch, null_lut, min_cov=10, min_freq=0.1, min_snp=5)
+    check_batch(eng, batch, null_lut, min_cov=1, min_freq=0.01, min_snp=50)
+
+
+def test_ambiguous_reference_and_empty_regions(eng, null_lut):
+    """N in the reference (test_special_2), zero-coverage stretches, events outside [start, start+L)."""
+    batch = synth.make_batch(20000, 40, 0.02, 5)
+    batch["ref_codes"] = batch["ref_codes"].copy()
+    batch["ref_codes"][::37] = 4
+    keep = (batch["ref_pos"] < 5000) | (batch["ref_pos"] > 9000)          # a coverage hole
+    for k in ("ref_pos", "base", "qual", "read_id"):
+        batch[k] = np.ascontiguousarray(batch[k][keep])
+    got, exp = check_batch(eng, batch, null_lut)
+    assert (exp["snv"]["cls"] == 0).any()
+
+
+def test_empty_batch(eng, null_lut):
+    L = 1000
+    ev = dict(ref_pos=np.zeros(0, np.int32), base=np.zeros(0, np.uint8), qual=np.zeros(0, np.uint8),
+              read_id=np.zeros(0, np.int32), pair_mm=np.zeros(0, np.uint8))
+    got = eng.profile_batch(ev, np.zeros(L, np.uint8), [(0, L - 1)], M=1, want=("counts", "covT", "clonT", "snv", "ld"))
+    assert got["counts"].sum() == 0 and got["covT"].sum() == 0 and np.isnan(got["clonT"]).all()
+    assert len(got["snv"]) == 0 and len(got["ld"]) == 0
+
+
+def test_double_entries_and_self_edges(eng, null_lut):
+    """Both mates of a pair counted on one site (htslib's overlap quirk produces this): multiplicity-2 combos and
+    self edges (p, p) must match the reference's itertools.combinations semantics."""
+    batch = synth.make_batch(6000, 120, 0.03, 9, skip_mm=False)
+    exp0 = oracle_all(batch, null_lut)
+    sites = np.nonzero(exp0["site_flags"] & 0x10)[0]
+    rng = np.random.default_rng(3)
+    pos = batch["ref_pos"]
+    dup_idx = []
+    for p in sites[::3]:
+        lo, hi = np.searchsorted(pos, p), np.searchsorted(pos, p + 1)
+        cand = np.arange(lo, hi)[batch["qual"][lo:hi] >= 30]
+        dup_idx.extend(rng.choice(cand, size=min(len(cand), 40), replace=False).tolist())
+    dup_idx = np.array(sorted(dup_idx))
+    new = {k: np.concatenate([batch[k], batch[k][dup_idx]]) for k in ("ref_pos", "base", "qual", "read_id")}
+    # half of the duplicated entries show a different base than the original mate
+    flip = rng.random(len(dup_idx)) < 0.5
+    nb = new["base"][len(pos):]
+    nb[flip] = (nb[flip] + 1) % 4
+    order = np.argsort(new["ref_pos"], kind="stable")
+    for k in new:
+        batch[k] = np.ascontiguousarray(new[k][order])
+    got, exp = check_batch(eng, batch, null_lut, min_snp=10)
+    assert (exp["ld"]["pos_a"] == exp["ld"]["pos_b"]).any(), "test did not produce a self edge"
+
+
+def test_triple_entry_is_reported(eng, null_lut):
+    from instrain_b200 import _cabi
+    batch = synth.make_batch(3000, 60, 0.03, 4, skip_mm=True)
+    exp0 = oracle_all(batch, null_lut)
+    p = int(np.nonzero(exp0["site_flags"] & 0x10)[0][0])
+    pos = batch["ref_pos"]
+    lo, hi = np.searchsorted(pos, p), np.searchsorted(pos, p + 1)
+    e = lo + int(np.nonzero((batch["qual"][lo:hi] >= 30) & ((exp0["site_flags"][p] >> batch["base"][lo:hi]) & 1 > 0))[0][0])
+    for k in ("ref_pos", "base", "qual", "read_id"):
+        batch[k] = np.ascontiguousarray(np.insert(batch[k], [e, e], [batch[k][e], batch[k][e]]))
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1)
+    assert ei.value.code == _cabi.ISB_ERR_UNSUPPORTED
+
+
+# ---- size-independent properties at larger size (no oracle) -----------------------------------------------------------
+def test_properties_large(eng, null_lut):
+    batch = synth.make_batch(400000, 60, 0.01, 20260103, skip_mm=True)
+    L = len(batch["ref_codes"])
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, want=("counts", "covT", "snv", "ld"))
+    qual_ok = (batch["qual"] >= 30) & (batch["base"] < 4)
+    assert got["counts"].sum() == qual_ok.sum()                                    # checksum of checksums
+    assert np.array_equal(got["counts"].sum((1, 2)), np.bincount(batch["ref_pos"][qual_ok], minlength=L))
+    assert np.array_equal(got["covT"][:, 0], got["counts"].sum((1, 2)))
+    # linearity: counts(evA + evB) == counts(evA) + counts(evB)
+    half = (batch["read_id"] % 2) == 0
+    sub = lambda m: {**{k: np.ascontiguousarray(batch[k][m]) for k in ("ref_pos", "base", "qual", "read_id")},
+                     "pair_mm": batch["pair_mm"]}
+    ca, _ = eng.pileup_counts(sub(half), 0, L, 1)
+    cb, _ = eng.pileup_counts(sub(~half), 0, L, 1)
+    assert np.array_equal(ca + cb, got["counts"])
+    # idempotence / determinism of the whole path
+    again = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, want=("snv", "ld"))
+    assert_snv_equal(again["snv"], got["snv"])
+    assert_ld_equal(again["ld"], got["ld"], tol=0)
+    # every linkage row: pos_a <= pos_b, same split, total > min_snp
+    ld = got["ld"]
+    assert (ld["pos_a"] <= ld["pos_b"]).all()
+    sp = np.searchsorted(batch["splits"][:, 0], ld["pos_a"], side="right")
+    assert np.array_equal(sp, np.searchsorted(batch["splits"][:, 0], ld["pos_b"], side="right"))
+    assert ((ld["c_AB"] + ld["c_Ab"] + ld["c_aB"] + ld["c_ab"]) > 20).all()
