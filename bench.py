@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- genome positions profiled / second (pileup + SNV + linkage) on B200, CPU reference beside.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[2] / north_star): synthetic metagenome, `--scaffolds` x `--L` bp at `--cov` x coverage,
+1 % SNV density, min_cov 5, min_freq 0.05, min_snp 20, window_length 10000, --skip_mm_profiling (M = 1) unless --mm.
+Defaults: 100 x 1 Mb x 100x = the full 100 Mb configuration (1e10 aligned bases = 100 GB of event columns in HBM);
+it is generated on the device (instrain_b200/synth.py) because it cannot be produced on, or shipped from, the host
+in bench time.  A "step" = one full pass of the hot path (isb_profile_batch: K1 pileup -> K2 SNV -> K3 linkage) over the
+whole resident data set.  Inputs are ~100 GB >> the 126 MB L2, so no L2 flush is needed between steps.
+
+Multi-GPU: scaffolds are independent, so every rank profiles its own 100-scaffold shard (weak scaling, no data-path
+collective) and the final SNV / linkage tables are gathered to rank 0 over NCCL inside the timed step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genome positions profiled/sec (pileup+SNV+LD)"
+UNIT = "positions/s"
+SEED = 20260103
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaffolds", type=int, default=100)
+    ap.add_argument("--L", type=int, default=1000000)
+    ap.add_argument("--cov", type=int, default=100)
+    ap.add_argument("--dens", type=float, default=0.01)
+    ap.add_argument("--mm", action="store_true", help="keep per-pair mm levels (M ~ 12-15) instead of M = 1")
+    ap.add_argument("--e2e-scaffolds", type=int, default=4, help="scaffolds in the bounded host-buffer (e2e) slice")
+    ap.add_argument("--cpu-scaffolds", type=int, default=1, help="scaffolds in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_pass(host_batch, lut, dflt, threads):
+    """One pass of the reference algorithm (oracle port, C) over a host batch, split-aligned chunks on `threads` threads.
+    Returns (#snv rows, #ld rows)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import restate
+    pos = host_batch["ref_pos"]
+    splits = host_batch["splits"]
+    per = max(1, (len(splits) + threads * 4 - 1) // (threads * 4))
+    tasks = [splits[i:i + per] for i in range(0, len(splits), per)]
+    pair_mm = host_batch["pair_mm"].astype(np.int32)
+
+    def run(sp):
+        lo, hi = int(sp[0, 0]), int(sp[-1, 1]) + 1
+        e_lo, e_hi = np.searchsorted(pos, lo), np.searchsorted(pos, hi)
+        ev = dict(ref_pos=pos[e_lo:e_hi], base=host_batch["base"][e_lo:e_hi], qual=host_batch["qual"][e_lo:e_hi],
+                  read_id=host_batch["read_id"][e_lo:e_hi], pair_mm=pair_mm)
+        out = restate.profile_events(ev, host_batch["ref_codes"][lo:hi], lut, dflt, sp, start=lo,
+                                     M=int(pair_mm.max()) + 1 if len(pair_mm) else 1)
+        return len(out["snv"]), len(out["ld"])
+
+    if threads <= 1:
+        res = [run(t) for t in tasks]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(run, tasks))
+    return sum(r[0] for r in res), sum(r[1] for r in res)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if world > 1 and args.impl != "reference":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    from instrain_b200 import _cabi, synth
+    from instrain_b200.null_model import load_lut
+    lut, dflt = load_lut()
+    M_label = "per-pair mm levels" if args.mm else "M=1 (--skip_mm_profiling)"
+    workload = "synthetic metagenome %d x %d bp, %dx coverage, %.3g SNV density, %s, full profile (K1+K2+K3)" % (
+        args.scaffolds, args.L, args.cov, args.dens, M_label)
+    config = {"workload": workload, "scaffolds_per_gpu": args.scaffolds, "scaffold_len": args.L, "coverage": args.cov,
+              "snv_density": args.dens, "min_cov": 5, "min_freq": 0.05, "min_snp": 20, "window_length": 10000,
+              "sharding": "scaffolds per rank (weak), NCCL gather of SNV/linkage rows to rank 0" if world > 1 else "single GPU",
+              "l2": "inputs (%.0f GB) larger than L2; no flush needed" % (args.scaffolds * args.L * args.cov * 10 / 1e9)}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        n_sc = max(1, min(args.scaffolds, 2))
+        d = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED, skip_mm=not args.mm)
+        hb = synth.to_host_batch(d, 0, n_sc)
+        del d
+        torch.cuda.empty_cache()
+        cores = os.cpu_count() or 1
+        for _ in range(args.warmup):
+            cpu_oracle_pass(hb, lut, dflt, cores)
+        t0 = time.time()
+        for _ in range(args.steps):
+            rows = cpu_oracle_pass(hb, lut, dflt, cores)
+        dt = (time.time() - t0) / max(1, args.steps)
+        val = n_sc * args.L / dt
+        sample = "%d scaffold(s) x %d bp at %dx (%d events) of the same workload per step" % (n_sc, args.L, args.cov, len(hb["ref_pos"]))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 counts / f64 statistics", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference algorithm = oracle/oracle.c (C restatement pinned on the reference's goldens); the "
+                    "reference itself is pure Python + pysam and cannot run on this box", "rows": list(rows)}))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------ B200 arm
+    from instrain_b200.engine import Engine
+    t_gen = time.time()
+    d = synth.generate(local_rank, args.L, args.scaffolds, args.cov, args.dens, SEED + rank, skip_mm=not args.mm)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    n, npairs, Ltot = d["ref_pos"].numel(), d["pair_mm"].numel(), args.L * args.scaffolds
+    M = int(d["pair_mm"].max().item()) + 1 if npairs else 1
+    eng = Engine(local_rank, lut, dflt)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    lib, ctx, p = eng.lib, eng.ctx, _cabi.ptr
+
+    counts = torch.empty((Ltot, M, 4), dtype=torch.int32, device=dev)
+    nmask = torch.empty(Ltot, dtype=torch.int64, device=dev)
+    covT = torch.empty((Ltot, M), dtype=torch.int32, device=dev)
+    clonT = torch.empty((Ltot, M), dtype=torch.float32, device=dev)
+    flags = torch.empty(Ltot, dtype=torch.uint8, device=dev)
+    snv_cap, ld_cap = max(1 << 16, Ltot // 16), max(1 << 18, Ltot // 2)
+    res = None
+
+    def alloc_rows():
+        nonlocal snv, ld, res
+        snv = torch.empty(snv_cap * 32, dtype=torch.uint8, device=dev)
+        ld = torch.empty(ld_cap * 48, dtype=torch.uint8, device=dev)
+        res = _cabi.IsbResult(p(counts), p(nmask), p(covT), p(clonT), p(flags), p(snv), snv_cap, p(ld), ld_cap, 0, 0, 0, 0)
+
+    snv = ld = None
+    alloc_rows()
+    batch = _cabi.IsbBatch(n, p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), npairs, p(d["pair_mm"]), 0,
+                           Ltot, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M)
+    prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
+
+    def gather_tables():
+        """NCCL gather of the final SNV / linkage rows to rank 0 (the only collective of the job)."""
+        if world == 1:
+            return
+        mine = torch.tensor([res.n_snv, res.n_ld], dtype=torch.int64, device=dev)
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        mx = torch.stack(allc).max(0).values.tolist()
+        for buf, rowb, m in ((snv, 32, mx[0]), (ld, 48, mx[1])):
+            view = buf[:m * rowb]
+            dst = [torch.empty_like(view) for _ in range(world)] if rank == 0 else None
+            dist.gather(view, dst, dst=0)
+
+    def step():
+        nonlocal snv_cap, ld_cap
+        rc = lib.isb_profile_batch(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+        if rc == _cabi.ISB_ERR_CAPACITY:
+            snv_cap, ld_cap = max(snv_cap, int(res.n_snv) + 1024), max(ld_cap, int(res.n_ld) + 1024)
+            alloc_rows()
+            rc = lib.isb_profile_batch(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(lib.isb_last_error(ctx).decode())
+        gather_tables()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    eng.enable_timing(True)
+    eng.stage_times()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    stage_ms, stage_calls = eng.stage_times()
+    eng.enable_timing(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(w0, w1) if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * Ltot / (ms_step / 1e3)
+
+    # -------------------------------------------------------------------------------- roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    k1_ms = stage_ms[0] / max(1, stage_calls[0])
+    ev_bytes = 10 if M > 1 else 6                     # at M = 1 K1 does not need (and does not read) read_id
+    alg_bytes = n * ev_bytes + 16 * M * Ltot + 8 * Ltot
+    alg_bytes_survey = n * 10 + 16 * M * Ltot         # 10*c + 16*M B/position
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        key = "M1" if M == 1 else "Mgt1"
+        traffic = tj[key]["dram_bytes_per_event"] * n
+    except Exception:
+        pass
+    roofline = {"kernel": "k1_pileup_tiles_tma<M=1>" if M == 1 else "k1_pileup_tiles<M>1>", "bound": "hbm",
+                "achieved": alg_bytes / k1_ms / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / k1_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_def": "%d B/event (ref_pos i32 + base u8 + qual u8%s) + 16*M B/position counts + 8 B/position nmask"
+                             % (ev_bytes, " + read_id i32" if M > 1 else "; read_id not needed at M=1"),
+                "achieved_survey_def": alg_bytes_survey / k1_ms / 1e6, "launch_ms": k1_ms,
+                "stage_ms_per_step": {"k1_pileup": stage_ms[0] / args.steps, "k2_snv": stage_ms[1] / args.steps,
+                                      "k3_linkage": stage_ms[2] / args.steps}}
+
+    # -------------------------------------------------------------------------------- e2e: host buffers through the C-ABI
+    e2e = None
+    if rank == 0:
+        n_sc = max(1, min(args.e2e_scaffolds, args.scaffolds))
+        hb = synth.to_host_batch(d, 0, n_sc)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h = {k: pin(hb[k]) for k in ("ref_pos", "base", "qual", "read_id", "pair_mm", "ref_codes", "splits")}
+        Ls = n_sc * args.L
+        Ms = int(hb["pair_mm"].max()) + 1 if len(hb["pair_mm"]) else 1
+        o = dict(covT=torch.empty((Ls, Ms), dtype=torch.int32).pin_memory(),
+                 clonT=torch.empty((Ls, Ms), dtype=torch.float32).pin_memory(),
+                 flags=torch.empty(Ls, dtype=torch.uint8).pin_memory(),
+                 snv=torch.empty(max(1 << 16, Ls // 16) * 32, dtype=torch.uint8).pin_memory(),
+                 ld=torch.empty(max(1 << 18, Ls // 2) * 48, dtype=torch.uint8).pin_memory())
+        hbatch = _cabi.IsbBatch(len(hb["ref_pos"]), p(h["ref_pos"]), p(h["base"]), p(h["qual"]), p(h["read_id"]),
+                                len(hb["pair_mm"]), p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]),
+                                p(h["splits"]), Ms)
+        hres = _cabi.IsbResult(None, None, p(o["covT"]), p(o["clonT"]), p(o["flags"]), p(o["snv"]),
+                               o["snv"].numel() // 32, p(o["ld"]), o["ld"].numel() // 48, 0, 0, 0, 0)
+        ts = []
+        for it in range(2 + 3):
+            torch.cuda.synchronize()
+            a = time.time()
+            rc = lib.isb_profile_batch(ctx, C.byref(hbatch), C.byref(prm), C.byref(hres))
+            torch.cuda.synchronize()
+            if rc != 0:
+                raise RuntimeError(lib.isb_last_error(ctx).decode())
+            if it >= 2:
+                ts.append(time.time() - a)
+        dt = float(np.median(ts))
+        h2d = len(hb["ref_pos"]) * 10 + len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
+        d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
+        e2e = {"value": Ls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3,
+               "slice": "%d of the %d scaffolds per step, pinned host buffers -> isb_profile_batch -> pinned host results" % (n_sc, args.scaffolds)}
+
+    # -------------------------------------------------------------------------------- CPU baseline (oracle port) beside
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_sc = max(1, min(args.cpu_scaffolds, args.scaffolds))
+        hb = synth.to_host_batch(d, 0, n_sc)
+        a = time.time()
+        cpu_oracle_pass(hb, lut, dflt, 1)
+        dt = time.time() - a
+        cpu = {"value": n_sc * args.L / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d scaffold(s) x %d bp at %dx (%d events) of the same workload, one pass, 1 thread of oracle/oracle.c"
+                         % (n_sc, args.L, args.cov, len(hb["ref_pos"]))}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 counts / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "rows": {"n_events_per_gpu": n, "n_pairs_per_gpu": npairs, "M": M, "n_snv": int(res.n_snv), "n_ld": int(res.n_ld),
+                     "n_sites": int(res.n_sites), "n_site_pairs": int(res.n_site_pairs)},
+            "setup_s": round(t_gen, 1)}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

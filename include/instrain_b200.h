@@ -173,6 +173,12 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 int64_t isb_launch_count(const isb_ctx *ctx);
 
+/* Measurement hooks (bench.py's roofline leg): when enabled, isb_profile_batch brackets K1 / K2 / K3 with CUDA
+ * events on the context's stream.  isb_stage_times synchronises, returns the summed device milliseconds and call
+ * counts per stage (index 0 = K1 pileup, 1 = K2 SNV, 2 = K3 linkage) since the last call, and resets them. */
+int isb_enable_timing(isb_ctx *ctx, int on);
+int isb_stage_times(isb_ctx *ctx, double ms[3], int64_t calls[3]);
+
 #ifdef __cplusplus
 }
 #endif

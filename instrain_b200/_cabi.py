@@ -29,7 +29,8 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
-           "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_launch_count"]
+           "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_launch_count",
+           "isb_enable_timing", "isb_stage_times"]
 
 
 class IsbBatch(C.Structure):
@@ -90,6 +91,10 @@ def load():
     L.isb_linkage.restype = C.c_int
     L.isb_linkage.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, C.c_int, C.c_int, vp, vp, vp, i32, vp,
                               C.c_int, vp, i64, C.POINTER(i64)]
+    L.isb_enable_timing.restype = C.c_int
+    L.isb_enable_timing.argtypes = [vp, C.c_int]
+    L.isb_stage_times.restype = C.c_int
+    L.isb_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.isb_profile_batch.restype = C.c_int
     L.isb_profile_batch.argtypes = [vp, C.POINTER(IsbBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     _lib = L

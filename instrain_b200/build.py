@@ -11,6 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libinstrain_b200.so")
+CSRC_SYNTH = os.path.join(HERE, "csrc_synth")
+LIB_SYNTH = os.path.join(LIB_DIR, "libisb_synth.so")     # bench/test support: device-side synthetic data generator
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -23,21 +25,22 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _stale(lib, srcs):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    t = os.path.getmtime(lib)
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB]
-    subprocess.check_call(cmd)
+    synth_src = sorted(glob.glob(os.path.join(CSRC_SYNTH, "*.cu")))
+    for lib, srcs in ((LIB, sources()), (LIB_SYNTH, synth_src)):
+        if force or _stale(lib, srcs):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", lib] + (["-lz"] if lib == LIB else [])
+            subprocess.check_call(cmd)
     return LIB
 
 

@@ -1,6 +1,7 @@
 // isb_api.cu -- context, host<->device staging and the extern "C" entry points of libinstrain_b200.so.
 // See include/instrain_b200.h for the contract; each entry point cites the reference code it replaces there.
 #include "isb_common.cuh"
+#include <stdlib.h>
 
 static char g_create_err[512] = "";
 
@@ -20,6 +21,28 @@ int isb_ensure(isb_ctx *ctx, int slot, size_t bytes)
     }
     b.cap = want;
     return ISB_OK;
+}
+
+int isb_time_begin(isb_ctx *ctx, int stage)
+{
+    if (!ctx->timing) return -1;
+    if (ctx->n_tev == ctx->cap_tev) {
+        const int cap = ctx->cap_tev ? ctx->cap_tev * 2 : 64;
+        isb_tev *t = (isb_tev *)realloc(ctx->tev, sizeof(isb_tev) * cap);
+        if (!t) return -1;
+        ctx->tev = t;
+        ctx->cap_tev = cap;
+    }
+    isb_tev &t = ctx->tev[ctx->n_tev];
+    t.stage = stage;
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return -1;
+    cudaEventRecord(t.a, ctx->stream);
+    return ctx->n_tev++;
+}
+
+void isb_time_end(isb_ctx *ctx, int slot)
+{
+    if (slot >= 0) cudaEventRecord(ctx->tev[slot].b, ctx->stream);
 }
 
 static bool is_device_ptr(const void *p)
@@ -151,6 +174,8 @@ void isb_destroy(isb_ctx *ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (int i = 0; i < ctx->n_tev; ++i) { cudaEventDestroy(ctx->tev[i].a); cudaEventDestroy(ctx->tev[i].b); }
+    free(ctx->tev);
     delete ctx;
 }
 
@@ -171,6 +196,33 @@ int isb_synchronize(isb_ctx *ctx)
 }
 
 int64_t isb_launch_count(const isb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int isb_enable_timing(isb_ctx *ctx, int on)
+{
+    if (!ctx) return ISB_ERR_ARG;
+    ctx->timing = on ? 1 : 0;
+    return ISB_OK;
+}
+
+int isb_stage_times(isb_ctx *ctx, double ms[3], int64_t calls[3])
+{
+    if (!ctx || !ms || !calls) return ISB_ERR_ARG;
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) { ms[i] = 0.0; calls[i] = 0; }
+    for (int i = 0; i < ctx->n_tev; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->tev[i].a, ctx->tev[i].b) == cudaSuccess) {
+            ms[ctx->tev[i].stage] += t;
+            calls[ctx->tev[i].stage] += 1;
+        }
+        cudaEventDestroy(ctx->tev[i].a);
+        cudaEventDestroy(ctx->tev[i].b);
+    }
+    (void)cudaGetLastError();
+    ctx->n_tev = 0;
+    return ISB_OK;
+}
 
 static int check_common(isb_ctx *ctx, int32_t L, int M)
 {
@@ -308,14 +360,20 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
     if ((rc = stage_out(ctx, SL_SNV, out->snv, (size_t)(snv_cap > 0 ? snv_cap : 1), &d_snv))) return rc;
     if ((rc = stage_out(ctx, SL_LD, out->ld, (size_t)(ld_cap > 0 ? ld_cap : 1), &d_ld))) return rc;
 
+    int ts = isb_time_begin(ctx, 0);
     if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, in->start, L, M, prm->min_qual, 0, d_counts,
                             (unsigned long long *)d_nmask))) return rc;
+    isb_time_end(ctx, ts);
+    ts = isb_time_begin(ctx, 1);
     if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, in->start, prm->min_cov,
                             prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
+    isb_time_end(ctx, ts);
     ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    ts = do_ld ? isb_time_begin(ctx, 2) : -1;
     if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M,
                                      prm->min_qual, d_counts, (const unsigned long long *)d_nmask, d_flags,
                                      in->n_splits, d_splits, prm->min_snp, d_ld, ld_cap))) return rc;
+    isb_time_end(ctx, ts);
     if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
     if ((rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
     if ((rc = finish_out(ctx, out->covT, d_covT, (size_t)L * M))) return rc;

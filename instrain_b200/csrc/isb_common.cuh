@@ -44,7 +44,20 @@ struct isb_ctx {
     int64_t launches;
     isb_devbuf buf[SL_COUNT];
     char err[512];
+    // optional per-stage device timing (isb_enable_timing): CUDA events recorded on ctx->stream around K1 / K2 / K3
+    int timing;
+    int n_tev;
+    int cap_tev;
+    struct isb_tev *tev;
 };
+
+struct isb_tev {
+    int stage;               // 0 = K1, 1 = K2, 2 = K3
+    cudaEvent_t a, b;
+};
+
+int isb_time_begin(isb_ctx *ctx, int stage);   // returns slot index or -1 (timing off)
+void isb_time_end(isb_ctx *ctx, int slot);
 
 struct isb_site_meta {   // one linkage-eligible site (16 bytes)
     int32_t ev_lo_rel;   // first event of the site, relative to the site's tile (unused; kept for alignment)

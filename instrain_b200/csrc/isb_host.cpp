@@ -1,0 +1,401 @@
+// isb_host.cpp -- host side of the drop-in boundary: BAM -> position-major event columns (C++; no GPU involved).
+//
+// Replaces what the reference delegates to pysam/htslib for this path:
+//   pysam.AlignmentFile(bam)                              inStrain/profile/profile_utilities.py:56
+//   samfile.pileup(..., stepper='nofilter', ignore_overlaps=True, min_base_quality=30, ...)
+//                                                         inStrain/profile/profile_utilities.py:150-153
+// i.e. BGZF inflate + BAM record decode (SAM/BAM spec 4.2), htslib's mate-overlap quality tweak
+// (bam_plp overlap_push / tweak_overlap_quality / cigar_iref2iseq_set,next of htslib 1.10, including the in-block
+// counter behaviour the reference's goldens pin -- SURVEY.md Appendix A), CIGAR expansion of M/=/X bases and a stable
+// counting sort into position-major order (= pileup column order).  Only reads whose name is in R2M are packed
+// (others can never be counted: profile_utilities.py:277-283); the quality threshold itself is applied by the K1 kernel.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/instrain_b200.h"
+
+namespace {
+
+struct BamRec {
+    int32_t tid, pos, mtid, mpos, isize, l_seq;
+    uint16_t flag, n_cigar;
+    uint32_t cig_off;     // into cigar pool
+    uint64_t seq_off;     // into seq/qual pools (one byte per base)
+    int32_t name_idx;     // index into the caller's name list
+};
+
+struct Bam {
+    FILE *fp = nullptr;
+    std::vector<uint8_t> buf;     // decompressed bytes not yet consumed
+    size_t off = 0;
+    bool eof = false;
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    char err[256] = "";
+    // look-ahead record (raw bytes) of the next scaffold
+    std::vector<uint8_t> pending;
+    bool has_pending = false;
+};
+
+struct Events {
+    std::vector<int32_t> ref_pos, read_id;
+    std::vector<uint8_t> base, qual, pair_mm;
+    int64_t n_reads_seen = 0, n_reads_packed = 0;
+};
+
+bool read_block(Bam *b)
+{
+    uint8_t h[18];
+    size_t got = fread(h, 1, 18, b->fp);
+    if (got == 0) { b->eof = true; return false; }
+    if (got != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
+        snprintf(b->err, sizeof(b->err), "not a BGZF block");
+        b->eof = true;
+        return false;
+    }
+    const int xlen = h[10] | (h[11] << 8);
+    std::vector<uint8_t> extra(xlen);
+    memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, b->fp) != (size_t)(xlen - 6)) { b->eof = true; return false; }
+    int bsize = -1;
+    for (int i = 0; i + 4 <= xlen;) {
+        const int slen = extra[i + 2] | (extra[i + 3] << 8);
+        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+        i += 4 + slen;
+    }
+    if (bsize < 0) { snprintf(b->err, sizeof(b->err), "BGZF block without BC field"); b->eof = true; return false; }
+    const int clen = bsize - xlen - 19;           // compressed payload
+    std::vector<uint8_t> comp(clen + 8);
+    if (fread(comp.data(), 1, clen + 8, b->fp) != (size_t)(clen + 8)) { b->eof = true; return false; }
+    const uint32_t isize = comp[clen + 4] | (comp[clen + 5] << 8) | (comp[clen + 6] << 16) | ((uint32_t)comp[clen + 7] << 24);
+    if (isize == 0) return true;                  // empty block (EOF marker)
+    // compact the buffer before appending
+    if (b->off > (1u << 20)) { b->buf.erase(b->buf.begin(), b->buf.begin() + b->off); b->off = 0; }
+    const size_t old = b->buf.size();
+    b->buf.resize(old + isize);
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) { b->eof = true; return false; }
+    zs.next_in = comp.data(); zs.avail_in = clen;
+    zs.next_out = b->buf.data() + old; zs.avail_out = isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) { snprintf(b->err, sizeof(b->err), "inflate failed (%d)", rc); b->eof = true; return false; }
+    return true;
+}
+
+// make at least `need` unread bytes available; false at EOF
+bool ensure(Bam *b, size_t need)
+{
+    while (b->buf.size() - b->off < need) {
+        if (b->eof) return false;
+        if (!read_block(b) && b->eof) return b->buf.size() - b->off >= need;
+    }
+    return true;
+}
+
+bool read_exact(Bam *b, void *dst, size_t n)
+{
+    if (!ensure(b, n)) return false;
+    memcpy(dst, b->buf.data() + b->off, n);
+    b->off += n;
+    return true;
+}
+
+// ---- htslib overlap tweak (restated; see oracle/pileup_emul.py for the Python twin used by the tests) ---------------
+enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
+inline bool is_match(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
+
+struct Walker {
+    const uint32_t *cig;
+    int n, ci = 0;
+    int64_t icig = 0, iseq = 0, iref = 0;
+    int set(int64_t pos)
+    {
+        if (pos < 0) return -1;
+        icig = iseq = iref = 0;
+        while (ci < n) {
+            const int op = cig[ci] & 0xf;
+            const int64_t len = cig[ci] >> 4;
+            if (op == OP_S || op == OP_I) { ++ci; iseq += len; icig = 0; }
+            else if (op == OP_H || op == OP_P) { ++ci; icig = 0; }
+            else if (is_match(op)) {
+                pos -= len;
+                if (pos < 0) { icig = len + pos; iseq += icig; iref += icig; return 0; }
+                ++ci; iseq += len; icig = 0; iref += len;
+            } else if (op == OP_D || op == OP_N) {
+                pos -= len;
+                if (pos < 0) pos = 0;
+                ++ci; iref += len; icig = 0;
+            } else return -2;
+        }
+        iseq = -1;
+        return -1;
+    }
+    int next()
+    {
+        while (ci < n) {
+            const int op = cig[ci] & 0xf;
+            const int64_t len = cig[ci] >> 4;
+            if (is_match(op)) {
+                if (icig >= len - 1) { icig = 0; ++ci; continue; }
+                ++iseq; ++icig; ++iref;
+                return 0;
+            }
+            if (op == OP_D || op == OP_N) { ++ci; iref += len; icig = 0; }
+            else if (op == OP_I || op == OP_S) { ++ci; iseq += len; icig = 0; }
+            else if (op == OP_H || op == OP_P) { ++ci; icig = 0; }
+            else return -2;
+        }
+        iseq = -1; iref = -1;
+        return -1;
+    }
+};
+
+void tweak_overlap(const BamRec &a, const BamRec &b, const uint32_t *cigs, const uint8_t *seq, uint8_t *qual)
+{
+    Walker wa{cigs + a.cig_off, a.n_cigar}, wb{cigs + b.cig_off, b.n_cigar};
+    int64_t iref = b.pos;
+    int ar = wa.set(iref - a.pos);
+    if (ar < 0) return;
+    int br = wb.set(iref - b.pos);
+    if (br < 0) return;
+    const uint8_t *sa = seq + a.seq_off, *sb = seq + b.seq_off;
+    uint8_t *qa = qual + a.seq_off, *qb = qual + b.seq_off;
+    for (;;) {
+        while (ar >= 0 && wa.iref >= 0 && wa.iref < iref - a.pos) ar = wa.next();
+        if (ar < 0) return;
+        if (iref < wa.iref + a.pos) iref = wa.iref + a.pos;
+        while (br >= 0 && wb.iref >= 0 && wb.iref < iref - b.pos) br = wb.next();
+        if (br < 0) return;
+        if (iref < wb.iref + b.pos) iref = wb.iref + b.pos;
+        ++iref;
+        if (wa.iref + a.pos != wb.iref + b.pos) continue;
+        const int64_t ia = wa.iseq, ib = wb.iseq;
+        if (sa[ia] == sb[ib]) {
+            const int q = (int)qa[ia] + (int)qb[ib];
+            qa[ia] = (uint8_t)(q > 200 ? 200 : q);
+            qb[ib] = 0;
+        } else if (qa[ia] >= qb[ib]) {
+            qa[ia] = (uint8_t)(0.8 * qa[ia]);
+            qb[ib] = 0;
+        } else {
+            qb[ib] = (uint8_t)(0.8 * qb[ib]);
+            qa[ia] = 0;
+        }
+    }
+}
+
+int64_t ref_len_of(const uint32_t *cig, int n)
+{
+    int64_t l = 0;
+    for (int i = 0; i < n; ++i) {
+        const int op = cig[i] & 0xf;
+        if (op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X) l += cig[i] >> 4;
+    }
+    return l;
+}
+
+// nt16 code (=ACMGRSVTWYHKDBN) -> inStrain base code (A,C,T,G = 0..3; 4 otherwise)
+const uint8_t NT16_TO_CODE[16] = {4, 0, 1, 4, 3, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4};
+
+}  // namespace
+
+extern "C" {
+
+void *isb_bam_open(const char *path)
+{
+    Bam *b = new Bam();
+    b->fp = fopen(path, "rb");
+    if (!b->fp) { delete b; return nullptr; }
+    char magic[4];
+    int32_t l_text = 0, n_ref = 0;
+    if (!read_exact(b, magic, 4) || memcmp(magic, "BAM\1", 4) != 0 || !read_exact(b, &l_text, 4)) goto fail;
+    if (!ensure(b, (size_t)l_text)) goto fail;
+    b->off += l_text;
+    if (!read_exact(b, &n_ref, 4)) goto fail;
+    for (int i = 0; i < n_ref; ++i) {
+        int32_t l_name = 0, l_ref = 0;
+        if (!read_exact(b, &l_name, 4) || !ensure(b, (size_t)l_name)) goto fail;
+        b->ref_names.emplace_back((const char *)b->buf.data() + b->off, l_name > 0 ? l_name - 1 : 0);
+        b->off += l_name;
+        if (!read_exact(b, &l_ref, 4)) goto fail;
+        b->ref_lens.push_back(l_ref);
+    }
+    return b;
+fail:
+    fclose(b->fp);
+    delete b;
+    return nullptr;
+}
+
+void isb_bam_close(void *h)
+{
+    Bam *b = (Bam *)h;
+    if (!b) return;
+    if (b->fp) fclose(b->fp);
+    delete b;
+}
+
+int isb_bam_n_refs(void *h) { return (int)((Bam *)h)->ref_names.size(); }
+const char *isb_bam_ref_name(void *h, int tid) { return ((Bam *)h)->ref_names[tid].c_str(); }
+int64_t isb_bam_ref_len(void *h, int tid) { return ((Bam *)h)->ref_lens[tid]; }
+const char *isb_bam_error(void *h) { return ((Bam *)h)->err; }
+
+// tid of the next alignment record in the (coordinate-sorted) file: >= 0, -1 = unmapped tail, -2 = end of file
+int isb_bam_peek_tid(void *h)
+{
+    Bam *b = (Bam *)h;
+    if (!b->has_pending) {
+        int32_t block_size = 0;
+        if (!read_exact(b, &block_size, 4)) return -2;
+        b->pending.resize(block_size);
+        if (!read_exact(b, b->pending.data(), block_size)) return -2;
+        b->has_pending = true;
+    }
+    int32_t tid;
+    memcpy(&tid, b->pending.data(), 4);
+    return tid < 0 ? -1 : tid;
+}
+
+// Consume every record of scaffold `tid` (the file is coordinate-sorted, so they are contiguous) and pack the reads
+// whose name is in the given list.  names: n_names NUL-free strings concatenated in names_blob, name_off[n_names+1];
+// name_mm[i] = R2M value (0 in set mode).  Coordinates are shifted by pos_offset, pair ids start at pair_id_offset
+// and follow BAM order of first appearance.  Returns an opaque result (isb_events_*), or NULL on error.
+void *isb_pack_scaffold(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                        const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset)
+{
+    Bam *b = (Bam *)h;
+    std::unordered_map<std::string, int32_t> name2idx;
+    name2idx.reserve((size_t)n_names * 2 + 16);
+    for (int64_t i = 0; i < n_names; ++i)
+        name2idx.emplace(std::string(names_blob + name_off[i], (size_t)(name_off[i + 1] - name_off[i])), (int32_t)i);
+
+    std::vector<BamRec> recs;
+    std::vector<uint32_t> cigs;
+    std::vector<uint8_t> seq, qual;
+    Events *ev = new Events();
+    for (;;) {
+        const int t = isb_bam_peek_tid(h);
+        if (t != tid) break;
+        const uint8_t *p = b->pending.data();
+        b->has_pending = false;
+        ev->n_reads_seen++;
+        int32_t core[8];
+        memcpy(core, p, 32);
+        BamRec r;
+        r.tid = core[0]; r.pos = core[1];
+        const uint32_t bmq = (uint32_t)core[2];
+        const int l_read_name = bmq & 0xff;
+        const uint32_t fnc = (uint32_t)core[3];
+        r.n_cigar = fnc & 0xffff; r.flag = fnc >> 16;
+        r.l_seq = core[4]; r.mtid = core[5]; r.mpos = core[6]; r.isize = core[7];
+        if (r.flag & 0x4) continue;                                  // unmapped
+        const char *name = (const char *)p + 32;
+        auto it = name2idx.find(std::string(name, l_read_name > 0 ? l_read_name - 1 : 0));
+        if (it == name2idx.end()) continue;                          // not in R2M: can never be counted
+        r.name_idx = it->second;
+        const uint8_t *q = p + 32 + l_read_name;
+        r.cig_off = (uint32_t)cigs.size();
+        cigs.resize(cigs.size() + r.n_cigar);
+        memcpy(cigs.data() + r.cig_off, q, 4u * r.n_cigar);
+        q += 4u * r.n_cigar;
+        r.seq_off = seq.size();
+        seq.resize(seq.size() + r.l_seq);
+        qual.resize(qual.size() + r.l_seq);
+        for (int i = 0; i < r.l_seq; ++i) seq[r.seq_off + i] = (q[i >> 1] >> ((~i & 1) << 2)) & 0xf;
+        q += (r.l_seq + 1) >> 1;
+        memcpy(qual.data() + r.seq_off, q, r.l_seq);
+        recs.push_back(r);
+    }
+    // mate-overlap handling in file order (bam_plp overlap_push with ignore_overlaps=True)
+    {
+        std::unordered_map<int32_t, int32_t> pending;                // name idx -> first mate record
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const BamRec &r = recs[i];
+            if ((r.flag & 0x8) || !(r.flag & 0x2)) continue;
+            const int64_t end = r.pos + ref_len_of(cigs.data() + r.cig_off, r.n_cigar);
+            const int64_t aisize = r.isize < 0 ? -(int64_t)r.isize : r.isize;
+            if ((r.mtid >= 0 && r.tid != r.mtid) || (aisize >= 2 * (int64_t)r.l_seq && r.mpos >= end)) continue;
+            auto it = pending.find(r.name_idx);
+            if (it == pending.end()) {
+                if (r.mpos >= r.pos) pending.emplace(r.name_idx, (int32_t)i);
+            } else {
+                tweak_overlap(recs[it->second], r, cigs.data(), seq.data(), qual.data());
+                pending.erase(it);
+            }
+        }
+    }
+    // expand M/=/X bases in file order, then stable counting sort by position
+    const int64_t L = tid >= 0 && tid < (int)b->ref_lens.size() ? b->ref_lens[tid] : 0;
+    std::vector<int32_t> pair_of_name((size_t)n_names, -1);
+    std::vector<int64_t> cnt((size_t)L + 1, 0);
+    int32_t next_pair = 0;
+    for (const BamRec &r : recs) {                                   // pass 1: coverage histogram + pair ids
+        if (pair_of_name[r.name_idx] < 0) {
+            pair_of_name[r.name_idx] = next_pair++;
+            ev->pair_mm.push_back(name_mm ? name_mm[r.name_idx] : 0);
+        }
+        int64_t pos = r.pos;
+        for (int c = 0; c < r.n_cigar; ++c) {
+            const int op = cigs[r.cig_off + c] & 0xf;
+            const int64_t len = cigs[r.cig_off + c] >> 4;
+            if (is_match(op)) {
+                for (int64_t k = 0; k < len; ++k)
+                    if (pos + k >= 0 && pos + k < L) cnt[pos + k]++;
+                pos += len;
+            } else if (op == OP_D || op == OP_N) pos += len;
+        }
+        ev->n_reads_packed++;
+    }
+    int64_t total = 0;
+    for (int64_t i = 0; i <= L; ++i) { const int64_t c = cnt[i]; cnt[i] = total; total += c; }
+    ev->ref_pos.resize(total); ev->read_id.resize(total); ev->base.resize(total); ev->qual.resize(total);
+    for (const BamRec &r : recs) {                                   // pass 2: scatter (file order => stable)
+        int64_t pos = r.pos, qp = 0;
+        const int32_t pid = pair_of_name[r.name_idx] + pair_id_offset;
+        for (int c = 0; c < r.n_cigar; ++c) {
+            const int op = cigs[r.cig_off + c] & 0xf;
+            const int64_t len = cigs[r.cig_off + c] >> 4;
+            if (is_match(op)) {
+                for (int64_t k = 0; k < len; ++k) {
+                    if (pos + k < 0 || pos + k >= L) continue;
+                    const int64_t w = cnt[pos + k]++;
+                    ev->ref_pos[w] = (int32_t)(pos + k) + pos_offset;
+                    ev->read_id[w] = pid;
+                    ev->base[w] = NT16_TO_CODE[seq[r.seq_off + qp + k]];
+                    ev->qual[w] = qual[r.seq_off + qp + k];
+                }
+                pos += len; qp += len;
+            } else if (op == OP_I || op == OP_S) qp += len;
+            else if (op == OP_D || op == OP_N) pos += len;
+        }
+    }
+    return ev;
+}
+
+int64_t isb_events_count(void *e) { return (int64_t)((Events *)e)->ref_pos.size(); }
+int64_t isb_events_pairs(void *e) { return (int64_t)((Events *)e)->pair_mm.size(); }
+int64_t isb_events_reads_seen(void *e) { return ((Events *)e)->n_reads_seen; }
+int64_t isb_events_reads_packed(void *e) { return ((Events *)e)->n_reads_packed; }
+// copy the columns out (any pointer may be NULL)
+void isb_events_copy(void *e, int32_t *ref_pos, uint8_t *base, uint8_t *qual, int32_t *read_id, uint8_t *pair_mm)
+{
+    Events *ev = (Events *)e;
+    const size_t n = ev->ref_pos.size();
+    if (ref_pos) memcpy(ref_pos, ev->ref_pos.data(), n * 4);
+    if (base) memcpy(base, ev->base.data(), n);
+    if (qual) memcpy(qual, ev->qual.data(), n);
+    if (read_id) memcpy(read_id, ev->read_id.data(), n * 4);
+    if (pair_mm) memcpy(pair_mm, ev->pair_mm.data(), ev->pair_mm.size());
+}
+void isb_events_free(void *e) { delete (Events *)e; }
+
+}  // extern "C"

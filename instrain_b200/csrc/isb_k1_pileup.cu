@@ -7,11 +7,11 @@
 // Main kernel (position-major events): one CTA owns a tile of TP consecutive positions.  Because events are
 // sorted by position, the tile's events are ONE contiguous slice [tile_off[t], tile_off[t+1]) of every column,
 // so every event byte is read exactly once, fully coalesced with 128-bit loads, and the tile's counters live in
-// shared memory.  Equal (position, mm, base) keys inside a warp are merged with __match_any_sync before ONE
-// shared-memory atomic per distinct key (a position's ~c events agree on 1-2 bases, so a 32-event slot
-// collapses to a handful of atomics).  The finished tile is written back with 128-bit stores: global counters are
-// never touched by atomics.
+// shared memory.  The finished tile is written back with 128-bit stores: global counters are never touched by
+// atomics.  Two implementations of the tile kernel follow: v0 (warp-cooperative, __match_any_sync merge; kept as the
+// fallback for unaligned columns and for A/B measurements) and v2 (TMA-staged, lane-serial; the production path).
 #include "isb_common.cuh"
+#include <stdlib.h>
 
 #define K1_THREADS 256
 
@@ -101,6 +101,237 @@ k1_pileup_tiles(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__
     for (int i = threadIdx.x; i < n_cnt4; i += K1_THREADS) dst[i] = reinterpret_cast<const int4 *>(s_cnt)[i];
 }
 
+// ---- v2: TMA-staged, lane-serial kernel (the production path) -----------------------------------------------------
+// ncu on the warp-cooperative kernels above showed them ISSUE-bound (78 % issue-active, ~250 warp instructions per 128
+// events, DRAM at 31 %): every lane spends ~60 instructions per event on unpacking, validation and warp reductions.
+// v2 turns the work around (used for M = 1, the --skip_mm_profiling / headline configuration; with per-pair mm levels the
+// (position, mm) cell changes almost every event, lane-local accumulation does not pay and v0 stays the default):
+//   * one elected thread streams the tile's event slice into shared memory with 1-D TMA bulk copies
+//     (cp.async.bulk.shared.global + mbarrier complete_tx), a 3-stage ring, no register staging;
+//   * every thread then walks a CONTIGUOUS run of E events of the stage (E = 20 at M = 1: the 80-byte / 20-byte thread
+//     strides are bank-conflict-free for the 128-bit position loads and 32-bit base/qual loads).  Position-major order
+//     means a run covers 1-2 positions, so the thread counts 4 events at a time with byte-SIMD logic + POPC into four
+//     registers and touches shared memory only when the position changes (~2 atomics per 20 events);
+//   * the finished tile is written out with 128-bit stores as before.
+#define K1V2_STAGES 3
+
+__device__ __forceinline__ uint32_t k1_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k1_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k1_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k1_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k1_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k1_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(k1_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k1_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k1_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const uint32_t addr = k1_smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <bool kM1> struct k1v2_cfg;
+template <> struct k1v2_cfg<true> { static constexpr int E = 20; };    // events per thread per stage
+template <> struct k1v2_cfg<false> { static constexpr int E = 12; };
+
+template <bool kM1>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__ base,
+                    const uint8_t *__restrict__ qual, const int32_t *__restrict__ read_id,
+                    const uint8_t *__restrict__ pair_mm, const int64_t *__restrict__ tile_off, int64_t n,
+                    int32_t start, int32_t L, int M, int TP, int min_qual, int32_t *__restrict__ counts,
+                    unsigned long long *__restrict__ nmask, unsigned int *__restrict__ d_err)
+{
+    constexpr int E = k1v2_cfg<kM1>::E;
+    constexpr int CH = E * K1_THREADS;                               // events per stage (multiple of 16)
+    constexpr int STAGE_BYTES = CH * (kM1 ? 6 : 10);
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    // layout: [stages][ pos CH*4 | rid CH*4 (M>1) | base CH | qual CH ] | counters TP*M*16 | mbarriers
+    unsigned char *s_stage = s_raw;
+    int32_t *s_cnt = reinterpret_cast<int32_t *>(s_raw + K1V2_STAGES * STAGE_BYTES);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_raw + K1V2_STAGES * STAGE_BYTES + (size_t)TP * M * 16);
+
+    const int tile = blockIdx.x;
+    const int p0 = tile * TP;
+    const int np = min(TP, L - p0);
+    const int n_cnt4 = np * M;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_cnt4; i += K1_THREADS) reinterpret_cast<int4 *>(s_cnt)[i] = make_int4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int s = 0; s < K1V2_STAGES; ++s) k1_mbar_init(s_bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t e_lo = tile_off[tile], e_hi = tile_off[tile + 1];
+    const int64_t A = e_lo & ~(int64_t)15;                           // slice start, 16-event aligned for the bulk copies
+    const int64_t n_bulk = n & ~(int64_t)15;                         // events that may be fetched with 16-byte granules
+    const int n_chunks = (int)((e_hi - A + CH - 1) / CH);
+    const int32_t rel0 = start + p0;
+
+    auto issue = [&](int c) {                                        // thread 0 only
+        const int st = c % K1V2_STAGES;
+        const int64_t c_lo = A + (int64_t)c * CH;
+        int64_t c_hi = min(c_lo + CH, (e_hi + 15) & ~(int64_t)15);
+        c_hi = min(c_hi, n_bulk);
+        const unsigned ne = c_hi > c_lo ? (unsigned)(c_hi - c_lo) : 0u;
+        unsigned char *sp = s_stage + (size_t)st * STAGE_BYTES;
+        k1_mbar_expect_tx(s_bar + st, ne * (kM1 ? 6u : 10u));
+        if (ne) {
+            k1_bulk_g2s(sp, ref_pos + c_lo, ne * 4u, s_bar + st);
+            if (!kM1) k1_bulk_g2s(sp + CH * 4, read_id + c_lo, ne * 4u, s_bar + st);
+            k1_bulk_g2s(sp + CH * (kM1 ? 4 : 8), base + c_lo, ne, s_bar + st);
+            k1_bulk_g2s(sp + CH * (kM1 ? 5 : 9), qual + c_lo, ne, s_bar + st);
+        }
+    };
+    if (tid == 0)
+        for (int c = 0; c < K1V2_STAGES - 1 && c < n_chunks; ++c) issue(c);
+
+    // byte-SIMD quality test: high bit of byte j set iff q_j >= min_qual (valid for 1 <= min_qual <= 128)
+    const uint32_t q_add = 0x80808080u - 0x01010101u * (uint32_t)min(max(min_qual, 1), 128);
+    const bool q_simd = min_qual >= 1 && min_qual <= 128;
+
+    for (int c = 0; c < n_chunks; ++c) {
+        const int st = c % K1V2_STAGES;
+        if (tid == 0 && c + K1V2_STAGES - 1 < n_chunks) issue(c + K1V2_STAGES - 1);
+        unsigned char *sp = s_stage + (size_t)st * STAGE_BYTES;
+        const int32_t *s_pos = reinterpret_cast<const int32_t *>(sp);
+        const int32_t *s_rid = reinterpret_cast<const int32_t *>(sp + CH * 4);
+        const unsigned char *s_base = sp + CH * (kM1 ? 4 : 8);
+        const unsigned char *s_qual = sp + CH * (kM1 ? 5 : 9);
+        const int64_t c_lo = A + (int64_t)c * CH;
+        // the (< 16) events past the last 16-aligned boundary of the whole array cannot be bulk-copied: plain copies
+        if (c_lo + CH > n_bulk && n_bulk < n) {
+            const int64_t t_lo = max(c_lo, n_bulk), t_hi = min(c_lo + CH, n);
+            for (int64_t e = t_lo + tid; e < t_hi; e += K1_THREADS) {
+                const int i = (int)(e - c_lo);
+                const_cast<int32_t *>(s_pos)[i] = ref_pos[e];
+                if (!kM1) const_cast<int32_t *>(s_rid)[i] = read_id[e];
+                const_cast<unsigned char *>(s_base)[i] = base[e];
+                const_cast<unsigned char *>(s_qual)[i] = qual[e];
+            }
+            __syncthreads();
+        }
+        k1_mbar_wait(s_bar + st, (unsigned)((c / K1V2_STAGES) & 1));
+
+        const int i0 = tid * E;                                       // this thread's run inside the stage
+        // valid events of the run: chunk-relative index in [v_lo, v_hi)
+        const int v_lo = (int)max((int64_t)0, e_lo - c_lo), v_hi = (int)min((int64_t)CH, e_hi - c_lo);
+        if (kM1) {
+            // Lane-serial run of E events.  Position-major order => a 4-event vector holds a leading segment equal to
+            // its first position and (rarely, ~4/c per lane) a trailing segment; both are counted with byte-SIMD masks
+            // + POPC, so the only divergent work at a position change is the 4-counter flush.
+            int cur_p = 0x7fffffff;
+            unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            auto flush = [&]() {
+                const unsigned pr = (unsigned)(cur_p - rel0);
+                if (pr < (unsigned)np) {
+                    int32_t *d = s_cnt + (pr << 2);
+                    if (a0) atomicAdd(d + 0, (int)a0);
+                    if (a1) atomicAdd(d + 1, (int)a1);
+                    if (a2) atomicAdd(d + 2, (int)a2);
+                    if (a3) atomicAdd(d + 3, (int)a3);
+                } else if ((a0 | a1 | a2 | a3) && cur_p != 0x7fffffff) atomicOr(d_err, ISB_DEV_ERR_ORDER);
+                a0 = a1 = a2 = a3 = 0;
+            };
+            const bool interior = (i0 >= v_lo) && (i0 + E <= v_hi);
+#pragma unroll
+            for (int v = 0; v < E / 4; ++v) {
+                const int i = i0 + 4 * v;
+                if (!interior && (i + 4 <= v_lo || i >= v_hi)) continue;
+                const int4 pv = *reinterpret_cast<const int4 *>(s_pos + i);
+                const uint32_t b4 = *reinterpret_cast<const uint32_t *>(s_base + i);
+                const uint32_t q4 = *reinterpret_cast<const uint32_t *>(s_qual + i);
+                uint32_t ok;
+                if (q_simd) ok = ((((q4 & 0x7f7f7f7fu) + q_add) | q4) >> 7) & 0x01010101u;
+                else ok = ((q4 & 0xff) >= (unsigned)min_qual) | (((q4 >> 8) & 0xff) >= (unsigned)min_qual) << 8 |
+                          (((q4 >> 16) & 0xff) >= (unsigned)min_qual) << 16 | ((q4 >> 24) >= (unsigned)min_qual) << 24;
+                if (!interior) {                                         // clip to the tile's slice [v_lo, v_hi)
+                    const int lo_k = max(v_lo - i, 0), hi_k = min(v_hi - i, 4);
+                    ok &= (0xffffffffu << (8 * lo_k)) & (hi_k >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * hi_k)));
+                }
+                if (b4 & 0xfcfcfcfcu) {                                  // non-ACGT base(s): rare, exact per-event path
+                    const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (((b4 >> (8 * j)) & 0xfc) && ((ok >> (8 * j)) & 1)) {
+                            const unsigned pr = (unsigned)(ps[j] - rel0);
+                            if (pr < (unsigned)np) { if (nmask) atomicOr(nmask + p0 + pr, 1ull); }
+                            else atomicOr(d_err, ISB_DEV_ERR_ORDER);
+                            ok &= ~(1u << (8 * j));
+                        }
+                }
+                const uint32_t lo = b4 & 0x01010101u, hi = (b4 >> 1) & 0x01010101u;
+                const int same = (pv.y == pv.x) + (pv.z == pv.x) + (pv.w == pv.x);      // leading segment = 1 + same events
+                const uint32_t mA = 0x01010101u >> (8 * (3 - same));
+                if (pv.x != cur_p) { flush(); cur_p = pv.x; }
+                const uint32_t okA = ok & mA;
+                a0 += __popc(okA & ~hi & ~lo);
+                a1 += __popc(okA & ~hi & lo);
+                a2 += __popc(okA & hi & ~lo);
+                a3 += __popc(okA & hi & lo);
+                if (same != 3) {
+                    const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
+                    const int pn = same == 0 ? pv.y : (same == 1 ? pv.z : pv.w);          // first event after the segment
+                    if (pn == pv.w) {                                    // exactly two positions in the vector
+                        flush();
+                        cur_p = pv.w;
+                        const uint32_t okB = ok & ~mA;
+                        a0 = __popc(okB & ~hi & ~lo);
+                        a1 = __popc(okB & ~hi & lo);
+                        a2 = __popc(okB & hi & ~lo);
+                        a3 = __popc(okB & hi & lo);
+                    } else {                                             // >= 3 positions in 4 events (coverage < ~3)
+                        for (int j = same + 1; j < 4; ++j) {
+                            if (ps[j] != cur_p) { flush(); cur_p = ps[j]; }
+                            if ((ok >> (8 * j)) & 1) {
+                                const int b = (b4 >> (8 * j)) & 3;
+                                a0 += (b == 0); a1 += (b == 1); a2 += (b == 2); a3 += (b == 3);
+                            }
+                        }
+                    }
+                }
+            }
+            flush();
+        } else {
+#pragma unroll
+            for (int v = 0; v < E / 4; ++v) {
+                const int i = i0 + 4 * v;
+                if (i + 4 <= v_lo || i >= v_hi) continue;
+                const int4 pv = *reinterpret_cast<const int4 *>(s_pos + i);
+                const int4 rv = *reinterpret_cast<const int4 *>(s_rid + i);
+                const uint32_t b4 = *reinterpret_cast<const uint32_t *>(s_base + i);
+                const uint32_t q4 = *reinterpret_cast<const uint32_t *>(s_qual + i);
+                const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
+                const int32_t rs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int b = (b4 >> (8 * j)) & 0xff, q = (q4 >> (8 * j)) & 0xff;
+                    if (i + j < v_lo || i + j >= v_hi || q < min_qual) continue;
+                    const unsigned pr = (unsigned)(ps[j] - rel0);
+                    if (pr >= (unsigned)np) { atomicOr(d_err, ISB_DEV_ERR_ORDER); continue; }
+                    const int mm = __ldg(pair_mm + rs[j]);
+                    if (mm >= M) { atomicOr(d_err, ISB_DEV_ERR_MM); continue; }
+                    if (b >= 4) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mm); continue; }
+                    atomicAdd(s_cnt + (((int)pr * M + mm) << 2) + b, 1);
+                }
+            }
+        }
+        __syncthreads();                                               // stage consumed: thread 0 may refill it
+    }
+    int4 *dst = reinterpret_cast<int4 *>(counts) + (size_t)p0 * M;
+    for (int i = tid; i < n_cnt4; i += K1_THREADS) dst[i] = reinterpret_cast<const int4 *>(s_cnt)[i];
+}
+
 // Any-order fallback: one global atomic per qualifying event (the baseline the tiled kernel is measured against).
 __global__ void __launch_bounds__(256)
 k1_pileup_atomic(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__ base, const uint8_t *__restrict__ qual,
@@ -159,12 +390,29 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     k1_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(ref_pos, n, start, L, TP, n_tiles, tile_off);
     ISB_LAUNCH_CHECK();
     const size_t smem = (size_t)TP * M * 16;
-    if (M == 1)
-        k1_pileup_tiles<true><<<n_tiles, K1_THREADS, smem, st>>>(ref_pos, base, qual, read_id, pair_mm, tile_off, n,
-                                                                 start, L, M, TP, min_qual, counts, nmask, ctx->d_err);
-    else
-        k1_pileup_tiles<false><<<n_tiles, K1_THREADS, smem, st>>>(ref_pos, base, qual, read_id, pair_mm, tile_off, n,
-                                                                  start, L, M, TP, min_qual, counts, nmask, ctx->d_err);
+    static int variant = -1;                        // ISB_K1_VARIANT=0: warp-cooperative match_any kernel (A/B + fallback)
+    if (variant < 0) {
+        const char *v = getenv("ISB_K1_VARIANT");
+        variant = v ? atoi(v) : 2;
+    }
+    const bool aligned16 = ((((uintptr_t)ref_pos | (uintptr_t)base | (uintptr_t)qual) & 15) == 0) &&
+                           (M == 1 || (((uintptr_t)read_id) & 15) == 0);
+#define K1_ARGS ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, M, TP, min_qual, counts, nmask, ctx->d_err
+    if (variant == 0 || !aligned16 || (M > 1 && variant != 3)) {
+        if (M == 1) k1_pileup_tiles<true><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
+        else k1_pileup_tiles<false><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
+    } else {
+        const size_t stage = (size_t)K1_THREADS * (M == 1 ? k1v2_cfg<true>::E * 6 : k1v2_cfg<false>::E * 10);
+        const size_t smem2 = K1V2_STAGES * stage + smem + K1V2_STAGES * sizeof(uint64_t);
+        if (M == 1) {
+            ISB_CUDA(cudaFuncSetAttribute(k1_pileup_tiles_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k1_pileup_tiles_tma<true><<<n_tiles, K1_THREADS, smem2, st>>>(K1_ARGS);
+        } else {
+            ISB_CUDA(cudaFuncSetAttribute(k1_pileup_tiles_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k1_pileup_tiles_tma<false><<<n_tiles, K1_THREADS, smem2, st>>>(K1_ARGS);
+        }
+    }
+#undef K1_ARGS
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

@@ -64,6 +64,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.isb_launch_count(self.ctx))
 
+    def enable_timing(self, on=True):
+        self._check(self.lib.isb_enable_timing(self.ctx, 1 if on else 0))
+
+    def stage_times(self):
+        """(ms[3], calls[3]) of K1 / K2 / K3 device time since the last call (CUDA events on the context stream)."""
+        ms = (C.c_double * 3)()
+        calls = (C.c_int64 * 3)()
+        self._check(self.lib.isb_stage_times(self.ctx, ms, calls))
+        return list(ms), list(calls)
+
     # ---- stage K1 ----------------------------------------------------------------------------------------------
     def pileup_counts(self, ev, start, L, M, min_qual=30, any_order=False, counts=None, nmask=None):
         """ev: dict(ref_pos, base, qual, read_id, pair_mm). Returns (counts[L,M,4] int32, nmask[L] uint64)."""

@@ -1,0 +1,98 @@
+"""Host packer: BAM -> position-major event columns (ctypes face of instrain_b200/csrc/isb_host.cpp).
+
+Replaces the reference's pysam.AlignmentFile + samfile.pileup(...) (inStrain/profile/profile_utilities.py:56,150-153)
+for the hot path: decodes the BAM once, applies htslib's mate-overlap quality tweak, expands CIGARs and emits the
+columnar (ref_pos, base, qual, read_id) arrays + pair_mm that the kernels consume.  Host-only C++; no GPU needed.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+
+
+def _lib():
+    L = _cabi.load()
+    if not getattr(L, "_packer_ready", False):
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        L.isb_bam_open.restype = vp
+        L.isb_bam_open.argtypes = [C.c_char_p]
+        L.isb_bam_close.argtypes = [vp]
+        L.isb_bam_n_refs.restype = C.c_int
+        L.isb_bam_n_refs.argtypes = [vp]
+        L.isb_bam_ref_name.restype = C.c_char_p
+        L.isb_bam_ref_name.argtypes = [vp, C.c_int]
+        L.isb_bam_ref_len.restype = i64
+        L.isb_bam_ref_len.argtypes = [vp, C.c_int]
+        L.isb_bam_error.restype = C.c_char_p
+        L.isb_bam_error.argtypes = [vp]
+        L.isb_bam_peek_tid.restype = C.c_int
+        L.isb_bam_peek_tid.argtypes = [vp]
+        L.isb_pack_scaffold.restype = vp
+        L.isb_pack_scaffold.argtypes = [vp, C.c_int, i64, C.c_char_p, vp, vp, i32, i32]
+        for f in ("isb_events_count", "isb_events_pairs", "isb_events_reads_seen", "isb_events_reads_packed"):
+            getattr(L, f).restype = i64
+            getattr(L, f).argtypes = [vp]
+        L.isb_events_copy.argtypes = [vp] * 6
+        L.isb_events_free.argtypes = [vp]
+        L._packer_ready = True
+    return L
+
+
+class BamPacker:
+    """Streams a coordinate-sorted BAM scaffold by scaffold."""
+
+    def __init__(self, path):
+        self.lib = _lib()
+        self.h = self.lib.isb_bam_open(path.encode())
+        if not self.h:
+            raise IOError("cannot open BAM %s" % path)
+        n = self.lib.isb_bam_n_refs(self.h)
+        self.ref_names = [self.lib.isb_bam_ref_name(self.h, i).decode() for i in range(n)]
+        self.ref_lens = [int(self.lib.isb_bam_ref_len(self.h, i)) for i in range(n)]
+
+    def close(self):
+        if self.h:
+            self.lib.isb_bam_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def peek_tid(self):
+        """tid of the next record: >= 0; -1 unmapped tail; -2 end of file."""
+        return int(self.lib.isb_bam_peek_tid(self.h))
+
+    def pack_scaffold(self, tid, r2m, pos_offset=0, pair_id_offset=0):
+        """Consume the records of scaffold `tid`; r2m is the reference's sR2M[scaffold]: dict name -> mm, or a set."""
+        names = list(r2m.keys()) if isinstance(r2m, dict) else list(r2m)
+        enc = [s.encode() for s in names]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            off[1:] = np.cumsum([len(b) for b in enc])
+        blob = b"".join(enc)
+        if isinstance(r2m, dict):
+            mm = np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names))
+            if len(mm) and (mm.min() < 0 or mm.max() >= _cabi.ISB_MAX_MM):
+                raise ValueError("R2M mismatch count outside [0, %d)" % _cabi.ISB_MAX_MM)
+            mm = mm.astype(np.uint8)
+        else:
+            mm = np.zeros(len(names), dtype=np.uint8)
+        e = self.lib.isb_pack_scaffold(self.h, tid, len(names), blob, off.ctypes.data, mm.ctypes.data, pos_offset,
+                                       pair_id_offset)
+        if not e:
+            raise IOError("isb_pack_scaffold failed: " + self.lib.isb_bam_error(self.h).decode())
+        try:
+            n, npairs = int(self.lib.isb_events_count(e)), int(self.lib.isb_events_pairs(e))
+            out = dict(ref_pos=np.empty(n, np.int32), base=np.empty(n, np.uint8), qual=np.empty(n, np.uint8),
+                       read_id=np.empty(n, np.int32), pair_mm=np.empty(npairs, np.uint8))
+            self.lib.isb_events_copy(e, out["ref_pos"].ctypes.data, out["base"].ctypes.data, out["qual"].ctypes.data,
+                                     out["read_id"].ctypes.data, out["pair_mm"].ctypes.data)
+            out["reads_seen"] = int(self.lib.isb_events_reads_seen(e))
+            out["reads_packed"] = int(self.lib.isb_events_reads_packed(e))
+        finally:
+            self.lib.isb_events_free(e)
+        return out

@@ -1,0 +1,100 @@
+"""Device-side synthetic metagenome (bench / test support; ctypes face of lib/libisb_synth.so).
+
+Generates BASELINE.json's synthetic configurations directly in HBM as position-major event columns
+(instrain_b200/csrc_synth/isb_synth.cu).  Not part of the hot path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libisb_synth.so")
+
+
+class _Params(C.Structure):
+    _fields_ = [("L", C.c_int64), ("n_scaffolds", C.c_int32), ("coverage", C.c_int32), ("snv_density", C.c_double),
+                ("seed", C.c_uint64), ("skip_mm", C.c_int32), ("pad", C.c_int32)]
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libisb_synth.so is not built; run `python -m instrain_b200.build`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.isbs_last_error.restype = C.c_char_p
+        _lib.isbs_plan.restype = C.c_int
+        _lib.isbs_plan.argtypes = [C.c_int, C.POINTER(_Params), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        _lib.isbs_fill.restype = C.c_int
+        _lib.isbs_fill.argtypes = [C.c_void_p] * 6
+    return _lib
+
+
+def iterate_splits(s_len, window_len=10000):
+    """Split geometry of the reference (inStrain/profile/fasta.py:56-73): 0-based, double-inclusive."""
+    n_chunks = s_len // window_len + 1
+    chunk_len = int(s_len / n_chunks)
+    out, start, end = [], 0, 0
+    for i in range(n_chunks):
+        if i + 1 == n_chunks:
+            out.append((start, s_len - 1))
+        else:
+            end += chunk_len
+            out.append((start, end - 1))
+            start += chunk_len
+    return out
+
+
+def batch_splits(L, n_scaffolds, window_len=10000):
+    one = np.array(iterate_splits(L, window_len), dtype=np.int64)
+    return np.concatenate([one + s * L for s in range(n_scaffolds)]).astype(np.int32)
+
+
+def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, window_len=10000):
+    """Returns a dict of CUDA torch tensors (ref_pos, base, qual, read_id, pair_mm, ref_codes) + splits (CUDA int32)."""
+    import torch
+    lib = _load()
+    prm = _Params(L, n_scaffolds, coverage, float(snv_density), seed, 1 if skip_mm else 0, 0)
+    n_ev, n_pairs = C.c_int64(0), C.c_int64(0)
+    if lib.isbs_plan(device, C.byref(prm), C.byref(n_ev), C.byref(n_pairs)) != 0:
+        raise RuntimeError("isbs_plan: " + lib.isbs_last_error().decode())
+    dev = torch.device("cuda", device)
+    n, npairs, Ltot = n_ev.value, n_pairs.value, L * n_scaffolds
+    pad = 16                                    # keep every column readable in whole 16-byte granules
+    out = dict(
+        ref_pos=torch.empty(n + pad, dtype=torch.int32, device=dev)[:n],
+        base=torch.empty(n + pad, dtype=torch.uint8, device=dev)[:n],
+        qual=torch.empty(n + pad, dtype=torch.uint8, device=dev)[:n],
+        read_id=torch.empty(n + pad, dtype=torch.int32, device=dev)[:n],
+        pair_mm=torch.empty(max(npairs, 1), dtype=torch.uint8, device=dev)[:npairs],
+        ref_codes=torch.empty(Ltot, dtype=torch.uint8, device=dev),
+    )
+    if lib.isbs_fill(out["ref_pos"].data_ptr(), out["base"].data_ptr(), out["qual"].data_ptr(),
+                     out["read_id"].data_ptr(), out["pair_mm"].data_ptr(), out["ref_codes"].data_ptr()) != 0:
+        raise RuntimeError("isbs_fill: " + lib.isbs_last_error().decode())
+    out["splits"] = torch.from_numpy(batch_splits(L, n_scaffolds, window_len)).to(dev)
+    out["L"], out["n_scaffolds"] = L, n_scaffolds
+    return out
+
+
+def to_host_batch(d, lo_scaffold=0, n_scaffolds=1):
+    """Cut scaffolds [lo, lo+n) out of a generated data set as a self-contained host (numpy) batch with coordinates and
+    pair ids re-based to 0 -- the form the oracle and the host-buffer (e2e) path take."""
+    import torch
+    L = d["L"]
+    p_lo, p_hi = lo_scaffold * L, (lo_scaffold + n_scaffolds) * L
+    bounds = torch.searchsorted(d["ref_pos"], torch.tensor([p_lo, p_hi], dtype=torch.int32, device=d["ref_pos"].device))
+    e_lo, e_hi = int(bounds[0]), int(bounds[1])
+    rid = d["read_id"][e_lo:e_hi]
+    id_lo, id_hi = (int(rid.min()), int(rid.max()) + 1) if e_hi > e_lo else (0, 0)
+    spl = d["splits"]
+    sel = (spl[:, 0] >= p_lo) & (spl[:, 0] < p_hi)
+    return dict(
+        ref_pos=(d["ref_pos"][e_lo:e_hi] - p_lo).cpu().numpy(), base=d["base"][e_lo:e_hi].cpu().numpy(),
+        qual=d["qual"][e_lo:e_hi].cpu().numpy(), read_id=(rid - id_lo).cpu().numpy(),
+        pair_mm=d["pair_mm"][id_lo:id_hi].cpu().numpy(), ref_codes=d["ref_codes"][p_lo:p_hi].cpu().numpy(),
+        splits=(spl[sel] - p_lo).cpu().numpy())

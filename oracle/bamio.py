@@ -138,3 +138,49 @@ def iterate_splits(s_len, window_len):
             out.append((start, end - 1))
             start += chunk_len
     return out
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def write_bam(path, refs, reads):
+    """Minimal BGZF/BAM writer for test fixtures: refs = [(name, length)], reads = iterable of Read (file order kept)."""
+    import zlib
+    out = bytearray()
+    out += b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", len(refs))
+    for name, length in refs:
+        nb = name.encode() + b"\0"
+        out += struct.pack("<i", len(nb)) + nb + struct.pack("<i", length)
+    code = {c: i for i, c in enumerate(SEQ_NT16)}
+    for r in reads:
+        nb = r.name.encode() + b"\0"
+        rl = sum(n for op, n in r.cigar if op in (0, 2, 3, 7, 8)) or 1
+        cig = b"".join(struct.pack("<I", (n << 4) | op) for op, n in r.cigar)
+        l_seq = len(r.seq)
+        nib = [code[c] for c in r.seq] + [0]
+        seq = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, l_seq, 2))
+        tags = b"" if r.nm is None else b"NMC" + struct.pack("<B", min(int(r.nm), 255))
+        body = struct.pack("<iiBBHHHiiii", r.tid, r.pos, len(nb), r.mapq, _reg2bin(r.pos, r.pos + rl), len(r.cigar),
+                           r.flag, l_seq, r.mtid, r.mpos, r.isize) + nb + cig + seq + bytes(r.qual) + tags
+        out += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as fh:
+        data = bytes(out)
+        for i in range(0, max(len(data), 1), 0xff00):
+            chunk = data[i:i + 0xff00]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp
+                     + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))

@@ -74,7 +74,37 @@ def make_batch(which, window=10000):
     return batch, exp
 
 
+def make_subset_bam(which="G1", n_scaffolds=6):
+    """A small coordinate-sorted BAM + its sR2M for the host-packer test: scaffolds whose mates hit htslib's
+    overlap-walker quirk plus the most SNV-rich ones; ALL reads of those scaffolds are kept
+    (also the ones the read filter dropped), re-numbered to a compact reference list."""
+    import json
+    refs, by_tid, seqs, rdic, raw = load_set(which)
+    snp = pd.read_csv(os.path.join(raw, "raw_snp_table.csv.gz"))
+    rich = snp.groupby("scaffold").size().sort_values(ascending=False).index.tolist()
+    want = ["N5_271_010G1_scaffold_62", "N5_271_010G1_scaffold_649"] + rich
+    names = []
+    for nme in want:
+        if nme in rdic and nme not in names:
+            names.append(nme)
+        if len(names) == n_scaffolds:
+            break
+    tids = sorted(t for t, (nme, _) in enumerate(refs) if nme in names)
+    new_tid = {t: i for i, t in enumerate(tids)}
+    new_refs = [refs[t] for t in tids]
+    reads = []
+    for t in tids:
+        for r in by_tid.get(t, []):
+            mt = new_tid.get(r.mtid, -1) if r.mtid >= 0 else -1
+            reads.append(r._replace(tid=new_tid[t], mtid=mt))
+    bamio.write_bam(os.path.join(HERE, "c1_%s_subset.bam" % which), new_refs, reads)
+    with open(os.path.join(HERE, "c1_%s_subset_r2m.json" % which), "w") as fh:
+        json.dump({refs[t][0]: rdic[refs[t][0]] for t in tids}, fh)
+    print(which, "subset BAM:", len(new_refs), "scaffolds", len(reads), "reads")
+
+
 if __name__ == "__main__":
+    make_subset_bam("G1")
     model = ref_harness.null_model(1e-6)
     lut, dflt = restate.lut_from_model(model)
     np.savez_compressed(os.path.join(HERE, "null_lut_fdr1e-06.npz"), lut=lut, default=np.int32(dflt))

@@ -216,3 +216,30 @@ def test_properties_large(eng, null_lut):
     sp = np.searchsorted(batch["splits"][:, 0], ld["pos_a"], side="right")
     assert np.array_equal(sp, np.searchsorted(batch["splits"][:, 0], ld["pos_b"], side="right"))
     assert ((ld["c_AB"] + ld["c_Ab"] + ld["c_aB"] + ld["c_ab"]) > 20).all()
+
+
+# ---- device-generated data (the bench's generator) ---------------------------------------------------------------------
+@pytest.mark.parametrize("skip_mm", [True, False])
+def test_device_generated_batch_parity(eng, null_lut, skip_mm):
+    """instrain_b200.synth (bench data generator): columns are position-major, and sampled scaffolds of it give the
+    same answer on the CUDA path and the oracle ('sampled splits vs oracle')."""
+    import torch
+    from instrain_b200 import synth as dsynth
+    d = dsynth.generate(0, 60000, 3, 60, 0.01, 20260103, skip_mm=skip_mm)
+    pos = d["ref_pos"].cpu().numpy()
+    assert (np.diff(pos) >= 0).all() and pos.min() >= 0 and pos.max() < 180000
+    cov = len(pos) / 180000.0
+    assert 45 < cov < 66, cov
+    hb = dsynth.to_host_batch(d, 1, 2)                      # scaffolds 1..2 as a self-contained host batch
+    assert hb["ref_pos"].min() >= 0 and hb["read_id"].min() == 0
+    got, exp = check_batch(eng, hb, null_lut)
+    assert len(exp["snv"]) > 100 and len(exp["ld"]) > 10
+    # whole device-resident data set through device pointers == per-slice host results
+    M = int(d["pair_mm"].max().item()) + 1 if d["pair_mm"].numel() else 1
+    full = eng.profile_batch(dict(ref_pos=d["ref_pos"], base=d["base"], qual=d["qual"], read_id=d["read_id"],
+                                  pair_mm=d["pair_mm"].cpu().numpy()), d["ref_codes"].cpu().numpy(),
+                             d["splits"].cpu().numpy(), M=M, want=("snv", "ld"))
+    sel = full["snv"][full["snv"]["pos"] >= 60000].copy()
+    sel["pos"] -= 60000
+    if M == got["M"]:
+        assert_snv_equal(sel, got["snv"])
