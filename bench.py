@@ -104,31 +104,18 @@ class ClockSampler:
 
 
 def cpu_oracle_pass(host_batch, lut, dflt, threads):
-    """One pass of the reference algorithm (oracle port, C) over a host batch, split-aligned chunks on `threads` threads.
-    Returns (#snv rows, #ld rows)."""
-    from concurrent.futures import ThreadPoolExecutor
+    """One pass of the reference algorithm (oracle port: oracle/oracle.c) over a host batch.  Chunks of 4 splits are
+    farmed to `threads` OpenMP threads inside the C library, the way the reference farms splits to worker processes
+    (inStrain/profile/profile_controller.py:243-271).  Returns (#snv rows, #ld rows)."""
     from oracle import restate
-    pos = host_batch["ref_pos"]
-    splits = host_batch["splits"]
-    per = max(1, (len(splits) + threads * 4 - 1) // (threads * 4))
-    tasks = [splits[i:i + per] for i in range(0, len(splits), per)]
-    pair_mm = host_batch["pair_mm"].astype(np.int32)
+    return restate.profile_mt(host_batch, host_batch["ref_codes"], lut, dflt, host_batch["splits"], n_threads=threads)
 
-    def run(sp):
-        lo, hi = int(sp[0, 0]), int(sp[-1, 1]) + 1
-        e_lo, e_hi = np.searchsorted(pos, lo), np.searchsorted(pos, hi)
-        ev = dict(ref_pos=pos[e_lo:e_hi], base=host_batch["base"][e_lo:e_hi], qual=host_batch["qual"][e_lo:e_hi],
-                  read_id=host_batch["read_id"][e_lo:e_hi], pair_mm=pair_mm)
-        out = restate.profile_events(ev, host_batch["ref_codes"][lo:hi], lut, dflt, sp, start=lo,
-                                     M=int(pair_mm.max()) + 1 if len(pair_mm) else 1)
-        return len(out["snv"]), len(out["ld"])
 
-    if threads <= 1:
-        res = [run(t) for t in tasks]
-    else:
-        with ThreadPoolExecutor(threads) as ex:
-            res = list(ex.map(run, tasks))
-    return sum(r[0] for r in res), sum(r[1] for r in res)
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def main():
@@ -164,7 +151,7 @@ def main():
         hb = synth.to_host_batch(d, 0, n_sc)
         del d
         torch.cuda.empty_cache()
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         for _ in range(args.warmup):
             cpu_oracle_pass(hb, lut, dflt, cores)
         t0 = time.time()
@@ -338,7 +325,7 @@ def main():
         cpu_oracle_pass(hb, lut, dflt, 1)
         dt = time.time() - a
         cpu = {"value": n_sc * args.L / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d scaffold(s) x %d bp at %dx (%d events) of the same workload, one pass, 1 thread of oracle/oracle.c"
+               "sample": "%d scaffold(s) x %d bp at %dx (%d events) of the same workload, one pass, 1 thread of oracle/oracle.c (orc_profile_mt)"
                          % (n_sc, args.L, args.cov, len(hb["ref_pos"]))}
 
     if rank == 0:

@@ -109,7 +109,7 @@ bool read_exact(Bam *b, void *dst, size_t n)
     return true;
 }
 
-// ---- htslib overlap tweak (restated; see oracle/pileup_emul.py for the Python twin used by the tests) ---------------
+// ---- htslib overlap tweak (restated from htslib 1.10 sam.c; the parity tests hold a Python twin) ---------------
 enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
 inline bool is_match(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
 

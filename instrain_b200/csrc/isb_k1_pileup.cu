@@ -113,8 +113,6 @@ k1_pileup_tiles(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__
 //     means a run covers 1-2 positions, so the thread counts 4 events at a time with byte-SIMD logic + POPC into four
 //     registers and touches shared memory only when the position changes (~2 atomics per 20 events);
 //   * the finished tile is written out with 128-bit stores as before.
-#define K1V2_STAGES 3
-
 __device__ __forceinline__ uint32_t k1_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void k1_mbar_init(uint64_t *bar, unsigned count)
 {
@@ -139,35 +137,131 @@ __device__ __forceinline__ void k1_mbar_wait(uint64_t *bar, unsigned parity)
     } while (!ok);
 }
 
-template <bool kM1> struct k1v2_cfg;
-template <> struct k1v2_cfg<true> { static constexpr int E = 20; };    // events per thread per stage
-template <> struct k1v2_cfg<false> { static constexpr int E = 12; };
+// Per-thread state of the lane-serial M = 1 walk: current position and its four base counters.
+struct k1_run {
+    int cur_p;
+    unsigned a0, a1, a2, a3;
+};
 
-template <bool kM1>
-__global__ void __launch_bounds__(K1_THREADS)
+// Flush the counters of position `p` to the tile histogram when `doit`; straight-line predicated code (no
+// branch/reconvergence overhead): out-of-tile positions are clamped to a dummy row at index np and reported.
+// Flush the counters of position `p` to the tile histogram when `doit`.  ONE branch per flush with four unconditional
+// reductions inside: ptxas turns every conditional shared-memory atomic into its own branch + BSSY/BSYNC region
+// (29 % of the executed instructions in the previous version), so the per-counter "if (a_k)" tests are gone.
+// Out-of-tile positions are clamped to a dummy row at index np and reported.
+__device__ __forceinline__ void k1_red(uint32_t smem_addr, unsigned val)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr), "r"(val) : "memory");
+}
+
+__device__ __forceinline__ void k1_flush(int32_t *s_cnt, int p, int rel0, int np, bool doit, unsigned a0, unsigned a1,
+                                         unsigned a2, unsigned a3, unsigned &bad)
+{
+    if (doit) {
+        const unsigned pr = (unsigned)(p - rel0);
+        bad |= ((a0 | a1 | a2 | a3) && pr >= (unsigned)np && p != 0x7fffffff) ? 1u : 0u;
+        const uint32_t d = k1_smem_u32(s_cnt) + (min(pr, (unsigned)np) << 4);
+        k1_red(d + 0, a0);
+        k1_red(d + 4, a1);
+        k1_red(d + 8, a2);
+        k1_red(d + 12, a3);
+    }
+}
+
+// One 4-event vector of the run.  Position-major order => a leading segment A (events equal to the first position)
+// and at most one trailing segment B in the common case; both are counted with byte masks + POPC.
+template <bool kInterior>
+__device__ __forceinline__ void k1_vec4(k1_run &r, const int4 pv, const uint32_t b4, const uint32_t q4, uint32_t q_add,
+                                        bool q_simd, int min_qual, int i, int v_lo, int v_hi, int32_t *s_cnt, int rel0,
+                                        int np, int p0, unsigned long long *nmask, unsigned &bad)
+{
+    uint32_t ok;
+    if (q_simd) ok = ((((q4 & 0x7f7f7f7fu) + q_add) | q4) >> 7) & 0x01010101u;
+    else ok = ((q4 & 0xff) >= (unsigned)min_qual) | (((q4 >> 8) & 0xff) >= (unsigned)min_qual) << 8 |
+              (((q4 >> 16) & 0xff) >= (unsigned)min_qual) << 16 | ((q4 >> 24) >= (unsigned)min_qual) << 24;
+    if (!kInterior) {                                                // clip to the tile's slice [v_lo, v_hi)
+        const int lo_k = min(max(v_lo - i, 0), 4), hi_k = min(max(v_hi - i, 0), 4);
+        const uint32_t m_lo = lo_k >= 4 ? 0u : (0xffffffffu << (8 * lo_k));
+        const uint32_t m_hi = hi_k >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * hi_k));
+        ok &= m_lo & m_hi;
+    }
+    const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
+    if (b4 & 0xfcfcfcfcu) {                                          // non-ACGT base(s): rare, exact per-event path
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (((b4 >> (8 * j)) & 0xfc) && ((ok >> (8 * j)) & 1)) {
+                const unsigned pr = (unsigned)(ps[j] - rel0);
+                if (pr < (unsigned)np) { if (nmask) atomicOr(nmask + p0 + pr, 1ull); }
+                else bad |= 1u;
+                ok &= ~(1u << (8 * j));
+            }
+    }
+    const uint32_t lo = b4 & 0x01010101u, hi = (b4 >> 1) & 0x01010101u;
+    const int same = (pv.y == pv.x) + (pv.z == pv.x) + (pv.w == pv.x);
+    const bool multi = (same == 0 && pv.y != pv.w) || (same == 1 && pv.z != pv.w);     // >= 3 positions in 4 events
+    if (!multi) {
+        const uint32_t mA = 0x01010101u >> (8 * (3 - same));
+        const uint32_t okA = ok & mA, okB = ok & ~mA;
+        const bool f1 = pv.x != r.cur_p;                               // the run's position ends before this vector
+        k1_flush(s_cnt, r.cur_p, rel0, np, f1, r.a0, r.a1, r.a2, r.a3, bad);
+        const unsigned keep = f1 ? 0u : 0xffffffffu;
+        r.a0 = (r.a0 & keep) + __popc(okA & ~hi & ~lo);
+        r.a1 = (r.a1 & keep) + __popc(okA & ~hi & lo);
+        r.a2 = (r.a2 & keep) + __popc(okA & hi & ~lo);
+        r.a3 = (r.a3 & keep) + __popc(okA & hi & lo);
+        const bool f2 = same != 3;                                     // a second position starts inside the vector
+        k1_flush(s_cnt, pv.x, rel0, np, f2, r.a0, r.a1, r.a2, r.a3, bad);
+        const unsigned b0 = __popc(okB & ~hi & ~lo), b1 = __popc(okB & ~hi & lo);
+        const unsigned b2 = __popc(okB & hi & ~lo), b3 = __popc(okB & hi & lo);
+        r.a0 = f2 ? b0 : r.a0;
+        r.a1 = f2 ? b1 : r.a1;
+        r.a2 = f2 ? b2 : r.a2;
+        r.a3 = f2 ? b3 : r.a3;
+        r.cur_p = pv.w;
+    } else {                                                           // coverage < ~3: event by event
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool f = ps[j] != r.cur_p;
+            k1_flush(s_cnt, r.cur_p, rel0, np, f, r.a0, r.a1, r.a2, r.a3, bad);
+            const unsigned keep = f ? 0u : 0xffffffffu;
+            const unsigned one = (ok >> (8 * j)) & 1u;
+            const int b = (b4 >> (8 * j)) & 3;
+            r.a0 = (r.a0 & keep) + (b == 0 ? one : 0u);
+            r.a1 = (r.a1 & keep) + (b == 1 ? one : 0u);
+            r.a2 = (r.a2 & keep) + (b == 2 ? one : 0u);
+            r.a3 = (r.a3 & keep) + (b == 3 ? one : 0u);
+            r.cur_p = ps[j];
+        }
+    }
+}
+
+// kE events per thread per stage (kE*4 and kE bytes thread strides must be bank-conflict-free: kE = 12, 20, 28 ...),
+// kT threads, kS stages.
+template <bool kM1, int kT, int kE, int kS>
+__global__ void __launch_bounds__(kT)
 k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__ base,
                     const uint8_t *__restrict__ qual, const int32_t *__restrict__ read_id,
                     const uint8_t *__restrict__ pair_mm, const int64_t *__restrict__ tile_off, int64_t n,
                     int32_t start, int32_t L, int M, int TP, int min_qual, int32_t *__restrict__ counts,
                     unsigned long long *__restrict__ nmask, unsigned int *__restrict__ d_err)
 {
-    constexpr int E = k1v2_cfg<kM1>::E;
-    constexpr int CH = E * K1_THREADS;                               // events per stage (multiple of 16)
+    constexpr int CH = kE * kT;                                      // events per stage (multiple of 16)
     constexpr int STAGE_BYTES = CH * (kM1 ? 6 : 10);
+    static_assert(CH % 16 == 0 && STAGE_BYTES % 128 == 0, "stage geometry");
     extern __shared__ __align__(128) unsigned char s_raw[];
-    // layout: [stages][ pos CH*4 | rid CH*4 (M>1) | base CH | qual CH ] | counters TP*M*16 | mbarriers
+    // layout: [stages][ pos CH*4 | rid CH*4 (M>1) | base CH | qual CH ] | counters (TP+1)*M*16 | mbarriers
     unsigned char *s_stage = s_raw;
-    int32_t *s_cnt = reinterpret_cast<int32_t *>(s_raw + K1V2_STAGES * STAGE_BYTES);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_raw + K1V2_STAGES * STAGE_BYTES + (size_t)TP * M * 16);
+    int32_t *s_cnt = reinterpret_cast<int32_t *>(s_raw + kS * STAGE_BYTES);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_raw + kS * STAGE_BYTES + (size_t)(TP + 1) * M * 16);
 
     const int tile = blockIdx.x;
     const int p0 = tile * TP;
     const int np = min(TP, L - p0);
     const int n_cnt4 = np * M;
     const int tid = threadIdx.x;
-    for (int i = tid; i < n_cnt4; i += K1_THREADS) reinterpret_cast<int4 *>(s_cnt)[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i < n_cnt4 + M; i += kT) reinterpret_cast<int4 *>(s_cnt)[i] = make_int4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int s = 0; s < K1V2_STAGES; ++s) k1_mbar_init(s_bar + s, 1);
+        for (int s = 0; s < kS; ++s) k1_mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -177,9 +271,10 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
     const int64_t n_bulk = n & ~(int64_t)15;                         // events that may be fetched with 16-byte granules
     const int n_chunks = (int)((e_hi - A + CH - 1) / CH);
     const int32_t rel0 = start + p0;
+    unsigned bad = 0;
 
     auto issue = [&](int c) {                                        // thread 0 only
-        const int st = c % K1V2_STAGES;
+        const int st = c % kS;
         const int64_t c_lo = A + (int64_t)c * CH;
         int64_t c_hi = min(c_lo + CH, (e_hi + 15) & ~(int64_t)15);
         c_hi = min(c_hi, n_bulk);
@@ -194,15 +289,15 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         }
     };
     if (tid == 0)
-        for (int c = 0; c < K1V2_STAGES - 1 && c < n_chunks; ++c) issue(c);
+        for (int c = 0; c < kS - 1 && c < n_chunks; ++c) issue(c);
 
     // byte-SIMD quality test: high bit of byte j set iff q_j >= min_qual (valid for 1 <= min_qual <= 128)
     const uint32_t q_add = 0x80808080u - 0x01010101u * (uint32_t)min(max(min_qual, 1), 128);
     const bool q_simd = min_qual >= 1 && min_qual <= 128;
 
     for (int c = 0; c < n_chunks; ++c) {
-        const int st = c % K1V2_STAGES;
-        if (tid == 0 && c + K1V2_STAGES - 1 < n_chunks) issue(c + K1V2_STAGES - 1);
+        const int st = c % kS;
+        if (tid == 0 && c + kS - 1 < n_chunks) issue(c + kS - 1);
         unsigned char *sp = s_stage + (size_t)st * STAGE_BYTES;
         const int32_t *s_pos = reinterpret_cast<const int32_t *>(sp);
         const int32_t *s_rid = reinterpret_cast<const int32_t *>(sp + CH * 4);
@@ -212,7 +307,7 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         // the (< 16) events past the last 16-aligned boundary of the whole array cannot be bulk-copied: plain copies
         if (c_lo + CH > n_bulk && n_bulk < n) {
             const int64_t t_lo = max(c_lo, n_bulk), t_hi = min(c_lo + CH, n);
-            for (int64_t e = t_lo + tid; e < t_hi; e += K1_THREADS) {
+            for (int64_t e = t_lo + tid; e < t_hi; e += kT) {
                 const int i = (int)(e - c_lo);
                 const_cast<int32_t *>(s_pos)[i] = ref_pos[e];
                 if (!kM1) const_cast<int32_t *>(s_rid)[i] = read_id[e];
@@ -221,90 +316,37 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
             }
             __syncthreads();
         }
-        k1_mbar_wait(s_bar + st, (unsigned)((c / K1V2_STAGES) & 1));
+        k1_mbar_wait(s_bar + st, (unsigned)((c / kS) & 1));
 
-        const int i0 = tid * E;                                       // this thread's run inside the stage
-        // valid events of the run: chunk-relative index in [v_lo, v_hi)
+        const int i0 = tid * kE;                                      // this thread's run inside the stage
+        // valid events of the stage: chunk-relative index in [v_lo, v_hi)
         const int v_lo = (int)max((int64_t)0, e_lo - c_lo), v_hi = (int)min((int64_t)CH, e_hi - c_lo);
         if (kM1) {
-            // Lane-serial run of E events.  Position-major order => a 4-event vector holds a leading segment equal to
-            // its first position and (rarely, ~4/c per lane) a trailing segment; both are counted with byte-SIMD masks
-            // + POPC, so the only divergent work at a position change is the 4-counter flush.
-            int cur_p = 0x7fffffff;
-            unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            auto flush = [&]() {
-                const unsigned pr = (unsigned)(cur_p - rel0);
-                if (pr < (unsigned)np) {
-                    int32_t *d = s_cnt + (pr << 2);
-                    if (a0) atomicAdd(d + 0, (int)a0);
-                    if (a1) atomicAdd(d + 1, (int)a1);
-                    if (a2) atomicAdd(d + 2, (int)a2);
-                    if (a3) atomicAdd(d + 3, (int)a3);
-                } else if ((a0 | a1 | a2 | a3) && cur_p != 0x7fffffff) atomicOr(d_err, ISB_DEV_ERR_ORDER);
-                a0 = a1 = a2 = a3 = 0;
-            };
-            const bool interior = (i0 >= v_lo) && (i0 + E <= v_hi);
-#pragma unroll
-            for (int v = 0; v < E / 4; ++v) {
-                const int i = i0 + 4 * v;
-                if (!interior && (i + 4 <= v_lo || i >= v_hi)) continue;
-                const int4 pv = *reinterpret_cast<const int4 *>(s_pos + i);
-                const uint32_t b4 = *reinterpret_cast<const uint32_t *>(s_base + i);
-                const uint32_t q4 = *reinterpret_cast<const uint32_t *>(s_qual + i);
-                uint32_t ok;
-                if (q_simd) ok = ((((q4 & 0x7f7f7f7fu) + q_add) | q4) >> 7) & 0x01010101u;
-                else ok = ((q4 & 0xff) >= (unsigned)min_qual) | (((q4 >> 8) & 0xff) >= (unsigned)min_qual) << 8 |
-                          (((q4 >> 16) & 0xff) >= (unsigned)min_qual) << 16 | ((q4 >> 24) >= (unsigned)min_qual) << 24;
-                if (!interior) {                                         // clip to the tile's slice [v_lo, v_hi)
-                    const int lo_k = max(v_lo - i, 0), hi_k = min(v_hi - i, 4);
-                    ok &= (0xffffffffu << (8 * lo_k)) & (hi_k >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * hi_k)));
+            k1_run r = {0x7fffffff, 0u, 0u, 0u, 0u};
+            if (v_lo == 0 && v_hi == CH) {                           // interior chunk (all but the tile's two ends)
+#pragma unroll 1
+                for (int v = 0; v < kE / 4; ++v) {
+                    const int i = i0 + 4 * v;
+                    k1_vec4<true>(r, *reinterpret_cast<const int4 *>(s_pos + i),
+                                  *reinterpret_cast<const uint32_t *>(s_base + i),
+                                  *reinterpret_cast<const uint32_t *>(s_qual + i), q_add, q_simd, min_qual, i, v_lo, v_hi,
+                                  s_cnt, rel0, np, p0, nmask, bad);
                 }
-                if (b4 & 0xfcfcfcfcu) {                                  // non-ACGT base(s): rare, exact per-event path
-                    const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (((b4 >> (8 * j)) & 0xfc) && ((ok >> (8 * j)) & 1)) {
-                            const unsigned pr = (unsigned)(ps[j] - rel0);
-                            if (pr < (unsigned)np) { if (nmask) atomicOr(nmask + p0 + pr, 1ull); }
-                            else atomicOr(d_err, ISB_DEV_ERR_ORDER);
-                            ok &= ~(1u << (8 * j));
-                        }
-                }
-                const uint32_t lo = b4 & 0x01010101u, hi = (b4 >> 1) & 0x01010101u;
-                const int same = (pv.y == pv.x) + (pv.z == pv.x) + (pv.w == pv.x);      // leading segment = 1 + same events
-                const uint32_t mA = 0x01010101u >> (8 * (3 - same));
-                if (pv.x != cur_p) { flush(); cur_p = pv.x; }
-                const uint32_t okA = ok & mA;
-                a0 += __popc(okA & ~hi & ~lo);
-                a1 += __popc(okA & ~hi & lo);
-                a2 += __popc(okA & hi & ~lo);
-                a3 += __popc(okA & hi & lo);
-                if (same != 3) {
-                    const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
-                    const int pn = same == 0 ? pv.y : (same == 1 ? pv.z : pv.w);          // first event after the segment
-                    if (pn == pv.w) {                                    // exactly two positions in the vector
-                        flush();
-                        cur_p = pv.w;
-                        const uint32_t okB = ok & ~mA;
-                        a0 = __popc(okB & ~hi & ~lo);
-                        a1 = __popc(okB & ~hi & lo);
-                        a2 = __popc(okB & hi & ~lo);
-                        a3 = __popc(okB & hi & lo);
-                    } else {                                             // >= 3 positions in 4 events (coverage < ~3)
-                        for (int j = same + 1; j < 4; ++j) {
-                            if (ps[j] != cur_p) { flush(); cur_p = ps[j]; }
-                            if ((ok >> (8 * j)) & 1) {
-                                const int b = (b4 >> (8 * j)) & 3;
-                                a0 += (b == 0); a1 += (b == 1); a2 += (b == 2); a3 += (b == 3);
-                            }
-                        }
-                    }
+            } else {
+#pragma unroll 1
+                for (int v = 0; v < kE / 4; ++v) {
+                    const int i = i0 + 4 * v;
+                    if (i + 4 <= v_lo || i >= v_hi) continue;
+                    k1_vec4<false>(r, *reinterpret_cast<const int4 *>(s_pos + i),
+                                   *reinterpret_cast<const uint32_t *>(s_base + i),
+                                   *reinterpret_cast<const uint32_t *>(s_qual + i), q_add, q_simd, min_qual, i, v_lo, v_hi,
+                                   s_cnt, rel0, np, p0, nmask, bad);
                 }
             }
-            flush();
+            k1_flush(s_cnt, r.cur_p, rel0, np, true, r.a0, r.a1, r.a2, r.a3, bad);
         } else {
-#pragma unroll
-            for (int v = 0; v < E / 4; ++v) {
+#pragma unroll 1
+            for (int v = 0; v < kE / 4; ++v) {
                 const int i = i0 + 4 * v;
                 if (i + 4 <= v_lo || i >= v_hi) continue;
                 const int4 pv = *reinterpret_cast<const int4 *>(s_pos + i);
@@ -318,7 +360,7 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
                     const int b = (b4 >> (8 * j)) & 0xff, q = (q4 >> (8 * j)) & 0xff;
                     if (i + j < v_lo || i + j >= v_hi || q < min_qual) continue;
                     const unsigned pr = (unsigned)(ps[j] - rel0);
-                    if (pr >= (unsigned)np) { atomicOr(d_err, ISB_DEV_ERR_ORDER); continue; }
+                    if (pr >= (unsigned)np) { bad |= 1u; continue; }
                     const int mm = __ldg(pair_mm + rs[j]);
                     if (mm >= M) { atomicOr(d_err, ISB_DEV_ERR_MM); continue; }
                     if (b >= 4) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mm); continue; }
@@ -328,8 +370,23 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         }
         __syncthreads();                                               // stage consumed: thread 0 may refill it
     }
+    if (bad) atomicOr(d_err, ISB_DEV_ERR_ORDER);
     int4 *dst = reinterpret_cast<int4 *>(counts) + (size_t)p0 * M;
-    for (int i = tid; i < n_cnt4; i += K1_THREADS) dst[i] = reinterpret_cast<const int4 *>(s_cnt)[i];
+    for (int i = tid; i < n_cnt4; i += kT) dst[i] = reinterpret_cast<const int4 *>(s_cnt)[i];
+}
+
+template <bool kM1, int kT, int kE, int kS>
+static int k1_launch_tma(isb_ctx *ctx, int n_tiles, size_t cnt_bytes, int M, const int32_t *ref_pos, const uint8_t *base,
+                         const uint8_t *qual, const int32_t *read_id, const uint8_t *pair_mm, const int64_t *tile_off,
+                         int64_t n, int32_t start, int32_t L, int TP, int min_qual, int32_t *counts,
+                         unsigned long long *nmask)
+{
+    const size_t smem = (size_t)kS * kE * kT * (kM1 ? 6 : 10) + cnt_bytes + (size_t)M * 16 + kS * sizeof(uint64_t);
+    auto kern = k1_pileup_tiles_tma<kM1, kT, kE, kS>;
+    ISB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_tiles, kT, smem, ctx->stream>>>(ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, M, TP, min_qual,
+                                            counts, nmask, ctx->d_err);
+    return ISB_OK;
 }
 
 // Any-order fallback: one global atomic per qualifying event (the baseline the tiled kernel is measured against).
@@ -390,29 +447,33 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     k1_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(ref_pos, n, start, L, TP, n_tiles, tile_off);
     ISB_LAUNCH_CHECK();
     const size_t smem = (size_t)TP * M * 16;
-    static int variant = -1;                        // ISB_K1_VARIANT=0: warp-cooperative match_any kernel (A/B + fallback)
+    static int variant = -1, cfg = 0;               // ISB_K1_VARIANT=0: warp-cooperative kernel (A/B + fallback)
     if (variant < 0) {
         const char *v = getenv("ISB_K1_VARIANT");
         variant = v ? atoi(v) : 2;
+        const char *c = getenv("ISB_K1_CFG");           // tile-kernel geometry, see k1_launch_tma instantiations below
+        cfg = c ? atoi(c) : 0;
     }
     const bool aligned16 = ((((uintptr_t)ref_pos | (uintptr_t)base | (uintptr_t)qual) & 15) == 0) &&
                            (M == 1 || (((uintptr_t)read_id) & 15) == 0);
 #define K1_ARGS ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, M, TP, min_qual, counts, nmask, ctx->d_err
+#define K1_TMA_ARGS ctx, n_tiles, smem, M, ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, TP, min_qual, counts, nmask
     if (variant == 0 || !aligned16 || (M > 1 && variant != 3)) {
         if (M == 1) k1_pileup_tiles<true><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
         else k1_pileup_tiles<false><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
+    } else if (M == 1) {
+        int rc2;
+        if (cfg == 1) rc2 = k1_launch_tma<true, 512, 12, 2>(K1_TMA_ARGS);        // 2 CTAs x 16 warps / SM
+        else if (cfg == 2) rc2 = k1_launch_tma<true, 256, 12, 3>(K1_TMA_ARGS);   // 3 CTAs x 8 warps / SM
+        else if (cfg == 3) rc2 = k1_launch_tma<true, 256, 20, 2>(K1_TMA_ARGS);   // 2 stages
+        else rc2 = k1_launch_tma<true, 256, 20, 3>(K1_TMA_ARGS);                 // 2 CTAs x 8 warps / SM
+        if (rc2) return rc2;
     } else {
-        const size_t stage = (size_t)K1_THREADS * (M == 1 ? k1v2_cfg<true>::E * 6 : k1v2_cfg<false>::E * 10);
-        const size_t smem2 = K1V2_STAGES * stage + smem + K1V2_STAGES * sizeof(uint64_t);
-        if (M == 1) {
-            ISB_CUDA(cudaFuncSetAttribute(k1_pileup_tiles_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k1_pileup_tiles_tma<true><<<n_tiles, K1_THREADS, smem2, st>>>(K1_ARGS);
-        } else {
-            ISB_CUDA(cudaFuncSetAttribute(k1_pileup_tiles_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k1_pileup_tiles_tma<false><<<n_tiles, K1_THREADS, smem2, st>>>(K1_ARGS);
-        }
+        int rc2 = k1_launch_tma<false, 256, 12, 3>(K1_TMA_ARGS);
+        if (rc2) return rc2;
     }
 #undef K1_ARGS
+#undef K1_TMA_ARGS
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

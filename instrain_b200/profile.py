@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference's profiling entry points for the hot path.
+
+    profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs)          <- inStrain.profile.profile_bam   (profile/__init__.py:7-18)
+
+Same arguments and keyword names as the reference (`kwargs` = vars(args) + s2s + s2p, controller.py:337-343).
+Where the reference farms (scaffold, split) commands to worker processes (profile_controller.py:243-271) and each worker
+runs profile_split's per-column Python loop (profile_utilities.py:115-266), this shim
+  1. streams the BAM once through the C++ host packer (instrain_b200/packer.py),
+  2. concatenates scaffolds into batches (one int32 coordinate space per batch),
+  3. runs K1 -> K2 -> K3 for the whole batch through the C-ABI (Engine.profile_batch),
+  4. turns the row arrays into the reference's per-scaffold tables (instrain_b200/tables.py).
+There is no CPU fallback: without the CUDA library / a GPU this raises.
+"""
+import logging
+import time
+
+import numpy as np
+import pandas as pd
+
+from . import tables
+from .engine import Engine
+from .packer import BamPacker
+from .synth import iterate_splits
+
+_REF_LUT = np.full(256, 4, dtype=np.uint8)
+for _i, _b in enumerate("ACTG"):
+    _REF_LUT[ord(_b)] = _i
+
+
+def encode_reference(seq):
+    """Upper-cased reference string (fasta.py:25-27) -> base codes 0..3 (A,C,T,G), 4 = anything else."""
+    return _REF_LUT[np.frombuffer(seq.encode(), dtype=np.uint8)]
+
+
+class ScaffoldProfile:
+    """What the reference's merged ScaffoldSplitObject carries for one scaffold (profile_utilities.py:719-820):
+    raw_snp_table, raw_linkage_table, covT, clonT (+ length).  clonTR is not produced (unseeded RNG in the reference)."""
+
+    def __init__(self, scaffold, length):
+        self.scaffold, self.length = scaffold, length
+        self.raw_snp_table = self.raw_linkage_table = None
+        self.covT, self.clonT, self.clonTR = {}, {}, {}
+
+
+class ProfileResult:
+    """Container returned by profile_bam when inStrain.SNVprofile is not importable: same attribute names the
+    reference stores (profile_utilities.py:670-715)."""
+
+    def __init__(self):
+        self.scaffold_list = []
+        self.scaffolds = {}
+        self.raw_snp_table = self.raw_linkage_table = None
+        self.timing = {}
+
+    def get(self, name):
+        return getattr(self, name)
+
+
+def _fdb_splits(Fdb, scaffold, length, window_length):
+    """Split table of one scaffold: from the reference's Fdb (fasta.py:30-52) when given, else the same geometry."""
+    if Fdb is not None:
+        db = Fdb[Fdb["scaffold"] == scaffold].sort_values("start")
+        return [(int(s), int(e)) for s, e in zip(db["start"], db["end"])]
+    return iterate_splits(length, window_length)
+
+
+def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch_events=400_000_000, **kwargs):
+    """Profile every scaffold of `sR2M` found in the BAM.  Returns (ProfileResult, engine).
+
+    kwargs (reference names and defaults, argumentParser.py:107-173): min_cov 5, min_freq 0.05, min_snp 20,
+    window_length 10000, skip_mm_profiling False (then sR2M values are sets), model_file/fdr for the null model.
+    """
+    min_cov = int(kwargs.get("min_cov", 5))
+    min_freq = float(kwargs.get("min_freq", 0.05))
+    min_snp = int(kwargs.get("min_snp", 20))
+    window_length = int(kwargs.get("window_length", 10000))
+    fdr = float(kwargs.get("fdr", 1e-6)) or 1e-6                      # 0 -> 1e-6 (controller.py:207-208)
+    own = engine is None
+    if own:
+        engine = Engine(device, model_file=kwargs.get("model_file"), fdr=fdr)
+    res = ProfileResult()
+    t0 = time.time()
+    snp_tabs, ld_tabs = [], []
+
+    def flush(batch):
+        if not batch["names"]:
+            return
+        cat = np.concatenate
+        ev = dict(ref_pos=cat(batch["ref_pos"]), base=cat(batch["base"]), qual=cat(batch["qual"]),
+                  read_id=cat(batch["read_id"]), pair_mm=cat(batch["pair_mm"]))
+        ref_codes = cat(batch["ref"])
+        offs = np.array(batch["off"], dtype=np.int64)
+        out = engine.profile_batch(ev, ref_codes, np.array(batch["splits"], np.int32), min_cov=min_cov, min_freq=min_freq,
+                                   min_snp=min_snp, want=("covT", "clonT", "snv", "ld"))
+        seqs = {n: s2s[n] for n in batch["names"]}
+        snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs))
+        ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
+        for name, off in zip(batch["names"], offs):
+            sp = ScaffoldProfile(name, len(s2s[name]))
+            sl = slice(int(off), int(off) + len(s2s[name]))
+            sp.covT = tables.basewise(out["covT"][sl], "coverage")
+            sp.clonT = tables.basewise(out["clonT"][sl], "clonality")
+            res.scaffolds[name] = sp
+            res.scaffold_list.append(name)
+
+    new_batch = lambda: dict(names=[], off=[], ref=[], splits=[], ref_pos=[], base=[], qual=[], read_id=[], pair_mm=[],
+                             n_events=0, L=0, n_pairs=0)
+    batch = new_batch()
+    with BamPacker(bam) as bp:
+        while True:
+            tid = bp.peek_tid()
+            if tid < 0:
+                break
+            name = bp.ref_names[tid]
+            if name not in sR2M or name not in s2s:
+                bp.pack_scaffold(tid, {})                                  # consume and drop
+                continue
+            L = len(s2s[name])
+            if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
+                flush(batch)
+                batch = new_batch()
+            ev = bp.pack_scaffold(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
+            batch["names"].append(name)
+            batch["off"].append(batch["L"])
+            batch["ref"].append(encode_reference(s2s[name]))
+            batch["splits"].extend((s + batch["L"], e + batch["L"]) for s, e in _fdb_splits(Fdb, name, L, window_length))
+            for k in ("ref_pos", "base", "qual", "read_id", "pair_mm"):
+                batch[k].append(ev[k])
+            batch["n_events"] += len(ev["ref_pos"])
+            batch["L"] += L
+            batch["n_pairs"] += len(ev["pair_mm"])
+    flush(batch)
+    res.raw_snp_table = pd.concat(snp_tabs, ignore_index=True) if snp_tabs else pd.DataFrame(columns=tables.SNV_COLUMNS)
+    res.raw_linkage_table = pd.concat(ld_tabs, ignore_index=True) if ld_tabs else pd.DataFrame(columns=tables.LD_COLUMNS)
+    for name, sp in res.scaffolds.items():
+        sp.raw_snp_table = res.raw_snp_table[res.raw_snp_table["scaffold"] == name]
+        sp.raw_linkage_table = res.raw_linkage_table[res.raw_linkage_table["scaffold"] == name]
+    res.timing["profile_scaffolds_s"] = time.time() - t0
+    logging.debug("instrain_b200: profiled %d scaffolds in %.2fs", len(res.scaffold_list), res.timing["profile_scaffolds_s"])
+    if own:
+        engine.close()
+    return res
+
+
+def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
+    """Drop-in for inStrain.profile.profile_bam (profile/__init__.py:7-18).  Returns an inStrain SNVprofile stored at
+    ISP_loc when the reference package (with its h5py dependency) is importable, else the ProfileResult itself."""
+    s2s = kwargs.pop("s2s", None)
+    if s2s is None:
+        raise ValueError("profile_bam needs kwargs['s2s'] (scaffold -> sequence), as ProfileController.run_profile passes it")
+    res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
+    try:
+        import inStrain.SNVprofile
+    except Exception:
+        return res
+    Sprofile = inStrain.SNVprofile.SNVprofile(ISP_loc)
+    Sprofile.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
+    Sprofile.store("bam_loc", bam, "value", "Location of .bam file")
+    Sprofile.store("scaffold_list", res.scaffold_list, "list", "1d list of scaffolds, in same order as counts_table")
+    Sprofile.store("raw_linkage_table", res.raw_linkage_table, "pandas", "Contains raw linkage information")
+    Sprofile.store("raw_snp_table", res.raw_snp_table, "pandas", "Contains raw SNP information on a mm level")
+    Sprofile.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
+    Sprofile.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
+    return Sprofile

@@ -1,0 +1,70 @@
+"""Row arrays from the kernels -> the reference's pandas tables (host glue, no compute).
+
+Column names / order follow what the reference stores:
+  raw_snp_table      generate_snp_table              inStrain/profile/snv_utilities.py:274-290 (+ position shift :181)
+  raw_linkage_table  _calc_ld_single / _update_r2    inStrain/profile/linkage.py:138-252
+  covT / clonT       shrink_basewise                 inStrain/profile/profile_utilities.py:337-350
+The reference's unseeded-random columns (r2_normalized, d_prime_normalized, clonTR) are emitted as NaN / omitted.
+"""
+import numpy as np
+import pandas as pd
+
+from ._cabi import CLASS_NAMES
+
+BASES = np.array(list("ACTG"))
+SNV_COLUMNS = ["scaffold", "position", "ref_base", "A", "C", "T", "G", "con_base", "var_base", "mm", "allele_count",
+               "class", "cryptic", "position_coverage"]
+LD_COLUMNS = ["r2", "d_prime", "r2_normalized", "d_prime_normalized", "total", "countAB", "countAb", "countaB", "countab",
+              "allele_A", "allele_a", "allele_B", "allele_b", "distance", "position_A", "position_B", "mm", "scaffold"]
+
+
+def _locate(pos, scaffold_off):
+    """batch coordinate -> (scaffold index, scaffold-relative position)."""
+    idx = np.searchsorted(scaffold_off, pos, side="right") - 1
+    return idx, pos - np.asarray(scaffold_off)[idx]
+
+
+def snv_table(rows, scaffold_names, scaffold_off, seqs):
+    """isb_snv_row[] -> raw_snp_table DataFrame (sorted by scaffold order, position, mm)."""
+    rows = rows[np.lexsort((rows["mm"], rows["pos"]))]
+    names = np.asarray(scaffold_names, dtype=object)
+    sidx, rel = _locate(rows["pos"].astype(np.int64), scaffold_off)
+    ref_base = np.empty(len(rows), dtype=object)
+    for i in np.unique(sidx):
+        m = sidx == i
+        seq = np.frombuffer(seqs[names[i]].encode(), dtype="S1")
+        ref_base[m] = seq[rel[m]].astype(str)
+    cnt = rows["cnt"].astype(np.int64)
+    return pd.DataFrame({
+        "scaffold": names[sidx], "position": rel.astype(np.int64), "ref_base": ref_base,
+        "A": cnt[:, 0], "C": cnt[:, 1], "T": cnt[:, 2], "G": cnt[:, 3],
+        "con_base": BASES[rows["con"]], "var_base": BASES[rows["var"]], "mm": rows["mm"].astype(np.int64),
+        "allele_count": rows["allele_count"].astype(np.int64), "class": np.array(CLASS_NAMES, dtype=object)[rows["cls"]],
+        "cryptic": rows["cryptic"].astype(bool), "position_coverage": cnt.sum(1)}, columns=SNV_COLUMNS)
+
+
+def linkage_table(rows, scaffold_names, scaffold_off):
+    rows = rows[np.lexsort((rows["mm"], rows["pos_b"], rows["pos_a"]))]
+    names = np.asarray(scaffold_names, dtype=object)
+    sidx, rel_a = _locate(rows["pos_a"].astype(np.int64), scaffold_off)
+    rel_b = rows["pos_b"].astype(np.int64) - np.asarray(scaffold_off)[sidx]
+    c = [rows[k].astype(np.int64) for k in ("c_AB", "c_Ab", "c_aB", "c_ab")]
+    nan = np.full(len(rows), np.nan)
+    return pd.DataFrame({
+        "r2": rows["r2"], "d_prime": rows["d_prime"], "r2_normalized": nan, "d_prime_normalized": nan,
+        "total": c[0] + c[1] + c[2] + c[3], "countAB": c[0], "countAb": c[1], "countaB": c[2], "countab": c[3],
+        "allele_A": BASES[rows["allele_A"]], "allele_a": BASES[rows["allele_a"]], "allele_B": BASES[rows["allele_B"]],
+        "allele_b": BASES[rows["allele_b"]], "distance": rel_b - rel_a, "position_A": rel_a, "position_B": rel_b,
+        "mm": rows["mm"].astype(np.int64), "scaffold": names[sidx]}, columns=LD_COLUMNS)
+
+
+def basewise(dense, kind):
+    """Dense [L, M] array of one scaffold -> {mm: pd.Series} like shrink_basewise: coverage keeps values > 0 (int32),
+    clonality drops NaN (float32).  A level appears iff it has at least one retained position."""
+    out = {}
+    for mm in range(dense.shape[1]):
+        col = dense[:, mm]
+        keep = np.nonzero(col > 0)[0] if kind == "coverage" else np.nonzero(~np.isnan(col) & (col > 0))[0]
+        if len(keep):
+            out[mm] = pd.Series(col[keep].astype("int32" if kind == "coverage" else "float32"), index=keep)
+    return out

@@ -12,8 +12,8 @@ def build(force=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c99",
-                           src, "-o", LIB, "-lm"])
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+                           "-std=c99", src, "-o", LIB, "-lm"])
     return LIB
 
 

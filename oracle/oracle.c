@@ -306,3 +306,61 @@ int64_t orc_linkage(int64_t n, const int32_t *ref_pos, const uint8_t *base, cons
     free(head); free(tail); free(touched); free(ent); free(ent_next); free(cmb);
     return n_rows <= cap ? n_rows : -n_rows;
 }
+
+/* ---------------------------------------------------------------- multi-threaded driver (CPU baseline only) */
+/* Runs the three stages over chunks of `chunk_splits` consecutive splits on `n_threads` OpenMP threads and returns the
+ * number of SNV / linkage rows.  Used by bench.py's cpu_baseline / --impl reference legs: the reference farms splits to
+ * worker processes the same way (profile_controller.py:243-271); rows are counted, not kept. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static int64_t lower_bound_i32(const int32_t *a, int64_t n, int64_t key)
+{
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if ((int64_t)a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+int orc_profile_mt(int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual, const int32_t *read_id,
+                   const int32_t *pair_mm, int64_t n_pairs, int M, int min_qual, const uint8_t *ref, int32_t ref_start,
+                   const int32_t *lut, int n_lut, int lut_default, int min_cov, double min_freq, int n_splits,
+                   const int32_t *splits, int min_snp, int chunk_splits, int n_threads, int64_t *n_snv, int64_t *n_ld)
+{
+    int64_t tot_snv = 0, tot_ld = 0;
+    int failed = 0;
+    const int n_chunks = (n_splits + chunk_splits - 1) / chunk_splits;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_snv, tot_ld) reduction(| : failed)
+    for (int c = 0; c < n_chunks; ++c) {
+        const int s0 = c * chunk_splits, s1 = (s0 + chunk_splits < n_splits) ? s0 + chunk_splits : n_splits;
+        const int32_t lo = splits[2 * s0], hi = splits[2 * (s1 - 1) + 1];
+        const int32_t L = hi - lo + 1;
+        const int64_t e0 = lower_bound_i32(ref_pos, n, lo), e1 = lower_bound_i32(ref_pos, n, (int64_t)hi + 1);
+        int32_t *counts = (int32_t *)malloc(sizeof(int32_t) * (size_t)L * M * 4);
+        uint64_t *nmask = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)L);
+        int32_t *covT = (int32_t *)malloc(sizeof(int32_t) * (size_t)L * M);
+        float *clonT = (float *)malloc(sizeof(float) * (size_t)L * M);
+        uint8_t *flags = (uint8_t *)malloc((size_t)L);
+        int64_t cap_s = (int64_t)L * 2 + 1024, cap_l = (int64_t)L * 8 + 65536;
+        orc_snv_row *srows = (orc_snv_row *)malloc(sizeof(orc_snv_row) * (size_t)cap_s);
+        orc_ld_row *lrows = (orc_ld_row *)malloc(sizeof(orc_ld_row) * (size_t)cap_l);
+        if (!counts || !nmask || !covT || !clonT || !flags || !srows || !lrows) failed |= 1;
+        else {
+            if (orc_pileup_counts(e1 - e0, ref_pos + e0, base + e0, qual + e0, read_id + e0, pair_mm, lo, L, M, min_qual,
+                                  counts, nmask)) failed |= 2;
+            int64_t a = orc_call_snvs(L, M, counts, nmask, ref + (lo - ref_start), lut, n_lut, lut_default, min_cov, min_freq,
+                                      lo, covT, clonT, flags, srows, cap_s);
+            int64_t b = orc_linkage(e1 - e0, ref_pos + e0, base + e0, qual + e0, read_id + e0, pair_mm, n_pairs, lo, L, M,
+                                    min_qual, counts, nmask, flags, s1 - s0, splits + 2 * s0, min_snp, lrows, cap_l);
+            tot_snv += a < 0 ? -a : a;
+            tot_ld += b < 0 ? -b : b;
+        }
+        free(counts); free(nmask); free(covT); free(clonT); free(flags); free(srows); free(lrows);
+    }
+    *n_snv = tot_snv;
+    *n_ld = tot_ld;
+    return failed;
+}

@@ -112,6 +112,26 @@ def linkage(ev, counts, nmask, flags, splits, start=0, min_snp=20, min_qual=30):
         cap = -n
 
 
+def profile_mt(ev, ref_codes, lut, lut_default, splits, M=None, ref_start=0, min_cov=5, min_freq=0.05, min_snp=20,
+               min_qual=30, chunk_splits=4, n_threads=0):
+    """All three stages over split chunks on `n_threads` OpenMP threads (CPU-baseline driver): returns (#snv, #ld)."""
+    pair_mm = np.ascontiguousarray(ev["pair_mm"], dtype=np.int32)
+    if M is None:
+        M = int(pair_mm.max()) + 1 if len(pair_mm) else 1
+    splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
+    L = lib()
+    L.orc_profile_mt.restype = C.c_int
+    n_snv, n_ld = C.c_int64(0), C.c_int64(0)
+    rc = L.orc_profile_mt(C.c_int64(len(ev["ref_pos"])), _p(ev["ref_pos"]), _p(ev["base"]), _p(ev["qual"]),
+                          _p(ev["read_id"]), _p(pair_mm), C.c_int64(len(pair_mm)), C.c_int(M), C.c_int(min_qual),
+                          _p(ref_codes), C.c_int32(ref_start), _p(lut), C.c_int(len(lut)), C.c_int(lut_default),
+                          C.c_int(min_cov), C.c_double(min_freq), C.c_int(len(splits)), _p(splits), C.c_int(min_snp),
+                          C.c_int(chunk_splits), C.c_int(n_threads), C.byref(n_snv), C.byref(n_ld))
+    if rc:
+        raise RuntimeError("orc_profile_mt failed (%d)" % rc)
+    return n_snv.value, n_ld.value
+
+
 def profile_events(ev, ref_codes, lut, lut_default, splits, start=0, M=None, min_cov=5, min_freq=0.05,
                    min_snp=20, min_qual=30, do_linkage=True):
     """Whole hot path on one coordinate space. `ev` must be position-major (see sort_events)."""

@@ -100,6 +100,8 @@ def make_subset_bam(which="G1", n_scaffolds=6):
     bamio.write_bam(os.path.join(HERE, "c1_%s_subset.bam" % which), new_refs, reads)
     with open(os.path.join(HERE, "c1_%s_subset_r2m.json" % which), "w") as fh:
         json.dump({refs[t][0]: rdic[refs[t][0]] for t in tids}, fh)
+    with open(os.path.join(HERE, "c1_%s_subset_seqs.json" % which), "w") as fh:
+        json.dump({refs[t][0]: seqs[refs[t][0]] for t in tids}, fh)
     print(which, "subset BAM:", len(new_refs), "scaffolds", len(reads), "reads")
 
 

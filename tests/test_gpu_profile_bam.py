@@ -1,0 +1,68 @@
+"""profile_bam shim end to end on a real BAM: host packer -> K1/K2/K3 -> reference-shaped tables, against the reference's
+stored raw_snp_table / raw_linkage_table rows of the same scaffolds (golden fixtures)."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, load_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_tables(names):
+    from instrain_b200._cabi import CLASS_NAMES
+    batch, exp = load_batch("G1")
+    sn = list(batch["scaffold_names"])
+    off = batch["scaffold_off"].astype(np.int64)
+    sidx = np.searchsorted(off, exp["snv_pos"], side="right") - 1
+    snv = pd.DataFrame({"scaffold": np.array(sn, dtype=object)[sidx], "position": exp["snv_pos"] - off[sidx],
+                        "mm": exp["snv_mm"], "A": exp["snv_cnt"][:, 0], "C": exp["snv_cnt"][:, 1],
+                        "T": exp["snv_cnt"][:, 2], "G": exp["snv_cnt"][:, 3],
+                        "con_base": np.array(list("ACTG"))[exp["snv_con"]], "var_base": np.array(list("ACTG"))[exp["snv_var"]],
+                        "allele_count": exp["snv_allele_count"], "class": np.array(CLASS_NAMES, dtype=object)[exp["snv_cls"]],
+                        "cryptic": exp["snv_cryptic"].astype(bool)})
+    lidx = np.searchsorted(off, exp["ld_pos_a"], side="right") - 1
+    ld = pd.DataFrame({"scaffold": np.array(sn, dtype=object)[lidx], "position_A": exp["ld_pos_a"] - off[lidx],
+                       "position_B": exp["ld_pos_b"] - off[lidx], "mm": exp["ld_mm"], "countAB": exp["ld_counts"][:, 0],
+                       "countAb": exp["ld_counts"][:, 1], "countaB": exp["ld_counts"][:, 2], "countab": exp["ld_counts"][:, 3],
+                       "r2": exp["ld_r2"], "d_prime": exp["ld_d_prime"]})
+    return snv[snv["scaffold"].isin(names)], ld[ld["scaffold"].isin(names)]
+
+
+def test_profile_bam_matches_reference_goldens():
+    from instrain_b200.profile import profile_bam
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    res = profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, rdic, "unused.IS", s2s=seqs,
+                      min_cov=5, min_freq=0.05, min_snp=20, window_length=10000)
+    assert sorted(res.scaffold_list) == sorted(rdic)
+    g_snv, g_ld = golden_tables(set(rdic))
+    key = ["scaffold", "position", "mm"]
+    a = res.raw_snp_table.sort_values(key).reset_index(drop=True)
+    b = g_snv.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) and len(a) > 1000
+    for c in ["scaffold", "position", "mm", "A", "C", "T", "G", "con_base", "var_base", "allele_count", "class", "cryptic"]:
+        assert (a[c].values == b[c].values).all(), c
+    assert (a["position_coverage"] == a[["A", "C", "T", "G"]].sum(1)).all()
+    for s in seqs:                                             # ref_base column comes from the FASTA
+        m = a["scaffold"] == s
+        assert all(seqs[s][p] == r for p, r in zip(a["position"][m], a["ref_base"][m]))
+    key = ["scaffold", "position_A", "position_B", "mm"]
+    a = res.raw_linkage_table.sort_values(key).reset_index(drop=True)
+    b = g_ld.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) and len(a) > 1000
+    for c in key + ["countAB", "countAb", "countaB", "countab"]:
+        assert (a[c].values == b[c].values).all(), c
+    assert (a["distance"] == a["position_B"] - a["position_A"]).all()
+    for c in ("r2", "d_prime"):
+        assert np.allclose(a[c].values, b[c].values, rtol=0, atol=1e-6, equal_nan=True), c
+    # per-scaffold basewise tables: test_profile_13 -- position_coverage == sum of covT[mm' <= mm][pos]
+    for s, sp in res.scaffolds.items():
+        t = sp.raw_snp_table
+        for pos, mm, cov in zip(t["position"], t["mm"], t["position_coverage"]):
+            tot = sum(int(sp.covT[m].get(pos, 0)) for m in sp.covT if m <= mm)
+            assert tot == cov
+        break
