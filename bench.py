@@ -281,14 +281,20 @@ def main():
                                       "k3_linkage": stage_ms[2] / args.steps}}
 
     # -------------------------------------------------------------------------------- e2e: host buffers through the C-ABI
+    # Public call a user makes: pinned HOST buffers in (the host packer's packed transfer format, ~1 B/event),
+    # isb_profile_batch_packed (H2D + K0 expand + K1 + K2 + K3 + D2H of every result table), pinned HOST tables out.
+    # Also measured with the 10 B/event columnar host buffers (isb_profile_batch) for comparison.
     e2e = None
     if rank == 0:
+        from instrain_b200.packed import encode_packed
         n_sc = max(1, min(args.e2e_scaffolds, args.scaffolds))
         hb = synth.to_host_batch(d, 0, n_sc)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h = {k: pin(hb[k]) for k in ("ref_pos", "base", "qual", "read_id", "pair_mm", "ref_codes", "splits")}
         Ls = n_sc * args.L
         Ms = int(hb["pair_mm"].max()) + 1 if len(hb["pair_mm"]) else 1
+        pk = encode_packed(hb, 0, Ls, 30)
+        h = {k: pin(hb[k]) for k in ("ref_pos", "base", "qual", "read_id", "pair_mm", "ref_codes", "splits")}
+        hp = {k: pin(pk[k]) for k in ("pos_off", "id_base", "bqd", "esc_evt", "esc_id")}
         o = dict(covT=torch.empty((Ls, Ms), dtype=torch.int32).pin_memory(),
                  clonT=torch.empty((Ls, Ms), dtype=torch.float32).pin_memory(),
                  flags=torch.empty(Ls, dtype=torch.uint8).pin_memory(),
@@ -297,24 +303,35 @@ def main():
         hbatch = _cabi.IsbBatch(len(hb["ref_pos"]), p(h["ref_pos"]), p(h["base"]), p(h["qual"]), p(h["read_id"]),
                                 len(hb["pair_mm"]), p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]),
                                 p(h["splits"]), Ms)
+        pbatch = _cabi.IsbPackedBatch(pk["n_events"], p(hp["pos_off"]), p(hp["id_base"]), p(hp["bqd"]), len(pk["esc_evt"]),
+                                      p(hp["esc_evt"]), p(hp["esc_id"]), len(hb["pair_mm"]), p(h["pair_mm"]), 0, Ls,
+                                      p(h["ref_codes"]), len(hb["splits"]), p(h["splits"]), Ms, 30)
         hres = _cabi.IsbResult(None, None, p(o["covT"]), p(o["clonT"]), p(o["flags"]), p(o["snv"]),
                                o["snv"].numel() // 32, p(o["ld"]), o["ld"].numel() // 48, 0, 0, 0, 0)
-        ts = []
-        for it in range(2 + 3):
-            torch.cuda.synchronize()
-            a = time.time()
-            rc = lib.isb_profile_batch(ctx, C.byref(hbatch), C.byref(prm), C.byref(hres))
-            torch.cuda.synchronize()
-            if rc != 0:
-                raise RuntimeError(lib.isb_last_error(ctx).decode())
-            if it >= 2:
-                ts.append(time.time() - a)
-        dt = float(np.median(ts))
-        h2d = len(hb["ref_pos"]) * 10 + len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
+
+        def time_call(fn, b):
+            ts = []
+            for it in range(2 + 3):
+                torch.cuda.synchronize()
+                a = time.time()
+                rc = fn(ctx, C.byref(b), C.byref(prm), C.byref(hres))
+                torch.cuda.synchronize()
+                if rc != 0:
+                    raise RuntimeError(lib.isb_last_error(ctx).decode())
+                if it >= 2:
+                    ts.append(time.time() - a)
+            return float(np.median(ts))
+
+        dt_col = time_call(lib.isb_profile_batch, hbatch)
+        dt = time_call(lib.isb_profile_batch_packed, pbatch)
+        common = len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
+        h2d = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
         e2e = {"value": Ls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3,
-               "slice": "%d of the %d scaffolds per step, pinned host buffers -> isb_profile_batch -> pinned host results" % (n_sc, args.scaffolds)}
+               "ms_per_step": dt * 1e3, "api": "isb_profile_batch_packed (packed transfer format, K0 expands on the device)",
+               "slice": "%d of the %d scaffolds per step, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, args.scaffolds),
+               "columnar_host_buffers": {"value": Ls / dt_col, "ms_per_step": dt_col * 1e3,
+                                         "h2d_bytes_per_step": int(len(hb["ref_pos"]) * 10 + common)}}
 
     # -------------------------------------------------------------------------------- CPU baseline (oracle port) beside
     cpu = None

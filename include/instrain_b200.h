@@ -170,6 +170,32 @@ typedef struct {
 
 int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out);
 
+/* Same path fed with the PACKED transfer format (~1 B per event + 12 B per position instead of 10 B per event): the
+ * host packer's compact form of the same event columns, expanded on the device by kernel K0 into the canonical
+ * columns, then K1 -> K2 -> K3 unchanged.  This is what the end-to-end (host buffers in, host tables out) path uses,
+ * because PCIe, not the kernels, bounds it.  Events of a position are sorted by pair id (stable w.r.t. BAM order, so
+ * results are identical to the BAM-order columns).  See instrain_b200/csrc/isb_k0_expand.cu for the byte layout. */
+typedef struct {
+    int64_t n_events;
+    const int64_t *pos_off;   /* [L+1] CSR offsets of the positions */
+    const int32_t *id_base;   /* [L]   pair id of the first event of each position */
+    const uint8_t *bqd;       /* [n]   bit7 = qual >= min_qual, bits 4-6 = base code, bits 0-3 = pair-id delta (15 = escape) */
+    int64_t n_esc;
+    const int64_t *esc_evt;   /* [n_esc] ascending event indices whose delta is > 14 */
+    const int32_t *esc_id;    /* [n_esc] their absolute pair ids */
+    int64_t n_pairs;
+    const uint8_t *pair_mm;
+    int32_t start;
+    int32_t L;
+    const uint8_t *ref;
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+    int32_t min_qual;         /* the threshold the quality bit was computed with; must equal isb_params.min_qual */
+} isb_packed_batch;
+
+int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb_params *prm, isb_result *out);
+
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 int64_t isb_launch_count(const isb_ctx *ctx);
 
@@ -178,6 +204,31 @@ int64_t isb_launch_count(const isb_ctx *ctx);
  * counts per stage (index 0 = K1 pileup, 1 = K2 SNV, 2 = K3 linkage) since the last call, and resets them. */
 int isb_enable_timing(isb_ctx *ctx, int on);
 int isb_stage_times(isb_ctx *ctx, double ms[3], int64_t calls[3]);
+
+/* ---- host packer (C++, no GPU): BAM -> position-major event columns ------------------------------------------------ */
+/* Replaces pysam.AlignmentFile(bam) (profile_utilities.py:56) and the htslib pileup engine behind
+ * samfile.pileup(..., stepper='nofilter', ignore_overlaps=True, ...) (profile_utilities.py:150-153): BGZF inflate, BAM
+ * record decode, htslib 1.10's mate-overlap quality tweak (overlap_push / tweak_overlap_quality, including the
+ * cigar_iref2iseq_next in-block counter behaviour the reference's goldens pin), CIGAR expansion of M/=/X bases and a
+ * stable counting sort into position-major order.  The BAM must be coordinate-sorted (as inStrain requires). */
+void *isb_bam_open(const char *path);                      /* NULL on failure */
+void isb_bam_close(void *bam);
+int isb_bam_n_refs(void *bam);
+const char *isb_bam_ref_name(void *bam, int tid);
+int64_t isb_bam_ref_len(void *bam, int tid);
+const char *isb_bam_error(void *bam);
+int isb_bam_peek_tid(void *bam);                           /* next record's tid; -1 unmapped tail; -2 end of file */
+/* Consume all records of scaffold `tid`; pack the reads whose name is in the list (names_blob + name_off[n_names+1];
+ * name_mm[i] = R2M value, 0 in set mode).  Positions are shifted by pos_offset, pair ids start at pair_id_offset and
+ * follow BAM order of first appearance.  Returns an events handle (NULL on error). */
+void *isb_pack_scaffold(void *bam, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                        const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset);
+int64_t isb_events_count(void *events);
+int64_t isb_events_pairs(void *events);
+int64_t isb_events_reads_seen(void *events);
+int64_t isb_events_reads_packed(void *events);
+void isb_events_copy(void *events, int32_t *ref_pos, uint8_t *base, uint8_t *qual, int32_t *read_id, uint8_t *pair_mm);
+void isb_events_free(void *events);
 
 #ifdef __cplusplus
 }

@@ -29,8 +29,12 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
-           "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_launch_count",
-           "isb_enable_timing", "isb_stage_times"]
+           "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
+           "isb_launch_count",
+           "isb_enable_timing", "isb_stage_times",
+           "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
+           "isb_bam_peek_tid", "isb_pack_scaffold", "isb_events_count", "isb_events_pairs", "isb_events_reads_seen",
+           "isb_events_reads_packed", "isb_events_copy", "isb_events_free"]
 
 
 class IsbBatch(C.Structure):
@@ -38,6 +42,13 @@ class IsbBatch(C.Structure):
                 ("read_id", C.c_void_p), ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
                 ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
                 ("M", C.c_int32)]
+
+
+class IsbPackedBatch(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("pos_off", C.c_void_p), ("id_base", C.c_void_p), ("bqd", C.c_void_p),
+                ("n_esc", C.c_int64), ("esc_evt", C.c_void_p), ("esc_id", C.c_void_p), ("n_pairs", C.c_int64),
+                ("pair_mm", C.c_void_p), ("start", C.c_int32), ("L", C.c_int32), ("ref", C.c_void_p),
+                ("n_splits", C.c_int32), ("splits", C.c_void_p), ("M", C.c_int32), ("min_qual", C.c_int32)]
 
 
 class IsbParams(C.Structure):
@@ -97,6 +108,8 @@ def load():
     L.isb_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.isb_profile_batch.restype = C.c_int
     L.isb_profile_batch.argtypes = [vp, C.POINTER(IsbBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    L.isb_profile_batch_packed.restype = C.c_int
+    L.isb_profile_batch_packed.argtypes = [vp, C.POINTER(IsbPackedBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     _lib = L
     return L
 

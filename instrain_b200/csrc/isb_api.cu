@@ -328,28 +328,14 @@ int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const ui
     return ISB_OK;
 }
 
-int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out)
+// K1 -> K2 -> K3 on device-resident inputs; outputs staged / copied as requested by `out`.
+static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const uint8_t *d_base, const uint8_t *d_qual,
+                          const int32_t *d_rid, int64_t n_pairs, const uint8_t *d_mm, int32_t start, int32_t L, int M,
+                          const uint8_t *d_ref, int32_t n_splits, const int32_t *d_splits, const isb_params *prm,
+                          isb_result *out)
 {
-    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
-    const int32_t L = in->L;
-    const int M = in->M;
-    int rc = check_common(ctx, L, M);
-    if (rc) return rc;
-    const int64_t n = in->n_events;
-    if (!in->ref || (n > 0 && (!in->ref_pos || !in->base || !in->qual || !in->read_id)) || (M > 1 && !in->pair_mm) ||
-        (in->n_splits > 0 && !in->splits))
-        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_batch: null input pointer");
+    int rc;
     const bool do_ld = !(prm->flags & ISB_SKIP_LINKAGE);
-    ISB_CUDA(cudaSetDevice(ctx->device));
-    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
-    const int32_t *d_pos, *d_rid, *d_splits; const uint8_t *d_base, *d_qual, *d_mm, *d_ref;
-    if ((rc = stage_in(ctx, SL_REF_POS, in->ref_pos, (size_t)n, &d_pos))) return rc;
-    if ((rc = stage_in(ctx, SL_BASE, in->base, (size_t)n, &d_base))) return rc;
-    if ((rc = stage_in(ctx, SL_QUAL, in->qual, (size_t)n, &d_qual))) return rc;
-    if ((rc = stage_in(ctx, SL_READ_ID, in->read_id, (size_t)n, &d_rid))) return rc;
-    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
-    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
-    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
     int32_t *d_counts, *d_covT; uint64_t *d_nmask; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_snv; isb_ld_row *d_ld;
     if ((rc = stage_out(ctx, SL_COUNTS, out->counts, (size_t)L * M * 4, &d_counts))) return rc;
     if ((rc = stage_out(ctx, SL_NMASK, out->nmask, (size_t)L, &d_nmask))) return rc;
@@ -361,18 +347,18 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
     if ((rc = stage_out(ctx, SL_LD, out->ld, (size_t)(ld_cap > 0 ? ld_cap : 1), &d_ld))) return rc;
 
     int ts = isb_time_begin(ctx, 0);
-    if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, in->start, L, M, prm->min_qual, 0, d_counts,
+    if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
                             (unsigned long long *)d_nmask))) return rc;
     isb_time_end(ctx, ts);
     ts = isb_time_begin(ctx, 1);
-    if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, in->start, prm->min_cov,
+    if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
                             prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
     isb_time_end(ctx, ts);
     ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
     ts = do_ld ? isb_time_begin(ctx, 2) : -1;
-    if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M,
-                                     prm->min_qual, d_counts, (const unsigned long long *)d_nmask, d_flags,
-                                     in->n_splits, d_splits, prm->min_snp, d_ld, ld_cap))) return rc;
+    if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
+                                     d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
+                                     prm->min_snp, d_ld, ld_cap))) return rc;
     isb_time_end(ctx, ts);
     if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
     if ((rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
@@ -395,6 +381,69 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
     if ((out->snv && out->n_snv > snv_cap) || (out->ld && do_ld && out->n_ld > ld_cap))
         return isb_fail(ctx, ISB_ERR_CAPACITY, "isb_profile_batch: row buffer too small (see n_snv / n_ld)");
     return ISB_OK;
+}
+
+int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    const int64_t n = in->n_events;
+    if (!in->ref || (n > 0 && (!in->ref_pos || !in->base || !in->qual || !in->read_id)) || (M > 1 && !in->pair_mm) ||
+        (in->n_splits > 0 && !in->splits))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_batch: null input pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int32_t *d_pos, *d_rid, *d_splits; const uint8_t *d_base, *d_qual, *d_mm, *d_ref;
+    if ((rc = stage_in(ctx, SL_REF_POS, in->ref_pos, (size_t)n, &d_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_BASE, in->base, (size_t)n, &d_base))) return rc;
+    if ((rc = stage_in(ctx, SL_QUAL, in->qual, (size_t)n, &d_qual))) return rc;
+    if ((rc = stage_in(ctx, SL_READ_ID, in->read_id, (size_t)n, &d_rid))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    return profile_device(ctx, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+                          d_splits, prm, out);
+}
+
+int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    const int64_t n = in->n_events;
+    if (!in->ref || !in->pos_off || (L > 0 && !in->id_base) || (n > 0 && !in->bqd) || (M > 1 && !in->pair_mm) ||
+        (in->n_splits > 0 && !in->splits) || (in->n_esc > 0 && (!in->esc_evt || !in->esc_id)))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_batch_packed: null input pointer");
+    if (in->min_qual != prm->min_qual)
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_batch_packed: the quality bit was packed with a different min_qual");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    const int64_t *d_off, *d_esce; const int32_t *d_idb, *d_esci, *d_splits; const uint8_t *d_bqd, *d_mm, *d_ref;
+    if ((rc = stage_in(ctx, SL_PK_OFF, in->pos_off, (size_t)L + 1, &d_off))) return rc;
+    if ((rc = stage_in(ctx, SL_PK_IDBASE, in->id_base, (size_t)L, &d_idb))) return rc;
+    if ((rc = stage_in(ctx, SL_PK_BQD, in->bqd, (size_t)n, &d_bqd))) return rc;
+    if ((rc = stage_in(ctx, SL_PK_ESC_EVT, in->esc_evt, (size_t)in->n_esc, &d_esce))) return rc;
+    if ((rc = stage_in(ctx, SL_PK_ESC_ID, in->esc_id, (size_t)in->n_esc, &d_esci))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    // canonical columns in context-owned HBM (16 spare events so every column is readable in whole 16-byte granules)
+    if ((rc = isb_ensure(ctx, SL_REF_POS, sizeof(int32_t) * ((size_t)n + 16)))) return rc;
+    if ((rc = isb_ensure(ctx, SL_READ_ID, sizeof(int32_t) * ((size_t)n + 16)))) return rc;
+    if ((rc = isb_ensure(ctx, SL_BASE, (size_t)n + 16))) return rc;
+    if ((rc = isb_ensure(ctx, SL_QUAL, (size_t)n + 16))) return rc;
+    int32_t *c_pos = (int32_t *)ctx->buf[SL_REF_POS].p, *c_rid = (int32_t *)ctx->buf[SL_READ_ID].p;
+    uint8_t *c_base = (uint8_t *)ctx->buf[SL_BASE].p, *c_qual = (uint8_t *)ctx->buf[SL_QUAL].p;
+    int qpass = prm->min_qual < 1 ? 1 : (prm->min_qual > 255 ? 255 : prm->min_qual);
+    if ((rc = isb_k0_launch(ctx, n, d_off, d_idb, d_bqd, in->n_esc, d_esce, d_esci, in->start, L, qpass, c_pos, c_base,
+                            c_qual, c_rid))) return rc;
+    return profile_device(ctx, n, c_pos, c_base, c_qual, c_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+                          d_splits, prm, out);
 }
 
 }  // extern "C"

@@ -318,29 +318,38 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         }
         k1_mbar_wait(s_bar + st, (unsigned)((c / kS) & 1));
 
-        const int i0 = tid * kE;                                      // this thread's run inside the stage
+        // Run -> thread mapping.  Lanes of one warp take runs that are kT/32 (an ODD number of) runs apart: neighbouring
+        // lanes then sit on different positions, so the flush atomics of one warp instruction do not collide on an
+        // address (49.8 M bank conflicts with the contiguous mapping), and the odd stride keeps the 128-bit position
+        // loads and 32-bit base/qual loads bank-conflict-free.
+        constexpr int kW = kT / 32;
+        static_assert(kW % 2 == 1 || !kM1, "interleaved mapping needs an odd warp count");
+        const int i0 = kM1 ? ((tid & 31) * kW + (tid >> 5)) * kE : tid * kE;
         // valid events of the stage: chunk-relative index in [v_lo, v_hi)
         const int v_lo = (int)max((int64_t)0, e_lo - c_lo), v_hi = (int)min((int64_t)CH, e_hi - c_lo);
         if (kM1) {
+            constexpr int NV = kE / 4;
+            int4 pv[NV];
+            uint32_t b4[NV], q4[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {                           // all loads of the run first: hides the LDS latency
+                pv[v] = *reinterpret_cast<const int4 *>(s_pos + i0 + 4 * v);
+                b4[v] = *reinterpret_cast<const uint32_t *>(s_base + i0 + 4 * v);
+                q4[v] = *reinterpret_cast<const uint32_t *>(s_qual + i0 + 4 * v);
+            }
             k1_run r = {0x7fffffff, 0u, 0u, 0u, 0u};
             if (v_lo == 0 && v_hi == CH) {                           // interior chunk (all but the tile's two ends)
-#pragma unroll 1
-                for (int v = 0; v < kE / 4; ++v) {
-                    const int i = i0 + 4 * v;
-                    k1_vec4<true>(r, *reinterpret_cast<const int4 *>(s_pos + i),
-                                  *reinterpret_cast<const uint32_t *>(s_base + i),
-                                  *reinterpret_cast<const uint32_t *>(s_qual + i), q_add, q_simd, min_qual, i, v_lo, v_hi,
-                                  s_cnt, rel0, np, p0, nmask, bad);
-                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    k1_vec4<true>(r, pv[v], b4[v], q4[v], q_add, q_simd, min_qual, i0 + 4 * v, v_lo, v_hi, s_cnt, rel0, np,
+                                  p0, nmask, bad);
             } else {
-#pragma unroll 1
-                for (int v = 0; v < kE / 4; ++v) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
                     const int i = i0 + 4 * v;
                     if (i + 4 <= v_lo || i >= v_hi) continue;
-                    k1_vec4<false>(r, *reinterpret_cast<const int4 *>(s_pos + i),
-                                   *reinterpret_cast<const uint32_t *>(s_base + i),
-                                   *reinterpret_cast<const uint32_t *>(s_qual + i), q_add, q_simd, min_qual, i, v_lo, v_hi,
-                                   s_cnt, rel0, np, p0, nmask, bad);
+                    k1_vec4<false>(r, pv[v], b4[v], q4[v], q_add, q_simd, min_qual, i, v_lo, v_hi, s_cnt, rel0, np, p0,
+                                   nmask, bad);
                 }
             }
             k1_flush(s_cnt, r.cur_p, rel0, np, true, r.a0, r.a1, r.a2, r.a3, bad);
@@ -463,10 +472,11 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
         else k1_pileup_tiles<false><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
     } else if (M == 1) {
         int rc2;
-        if (cfg == 1) rc2 = k1_launch_tma<true, 512, 12, 2>(K1_TMA_ARGS);        // 2 CTAs x 16 warps / SM
-        else if (cfg == 2) rc2 = k1_launch_tma<true, 256, 12, 3>(K1_TMA_ARGS);   // 3 CTAs x 8 warps / SM
-        else if (cfg == 3) rc2 = k1_launch_tma<true, 256, 20, 2>(K1_TMA_ARGS);   // 2 stages
-        else rc2 = k1_launch_tma<true, 256, 20, 3>(K1_TMA_ARGS);                 // 2 CTAs x 8 warps / SM
+        if (cfg == 1) rc2 = k1_launch_tma<true, 416, 12, 3>(K1_TMA_ARGS);        // 2 CTAs x 13 warps / SM
+        else if (cfg == 2) rc2 = k1_launch_tma<true, 224, 20, 3>(K1_TMA_ARGS);   // 2 CTAs x 7 warps / SM
+        else if (cfg == 3) rc2 = k1_launch_tma<true, 160, 28, 3>(K1_TMA_ARGS);   // 2 CTAs x 5 warps / SM
+        else if (cfg == 4) rc2 = k1_launch_tma<true, 352, 12, 3>(K1_TMA_ARGS);   // 2 CTAs x 11 warps / SM
+        else rc2 = k1_launch_tma<true, 288, 12, 3>(K1_TMA_ARGS);                 // 2 CTAs x 9 warps / SM
         if (rc2) return rc2;
     } else {
         int rc2 = k1_launch_tma<false, 256, 12, 3>(K1_TMA_ARGS);

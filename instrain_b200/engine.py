@@ -130,7 +130,7 @@ class Engine:
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
-                      snv_cap=None, ld_cap=None):
+                      snv_cap=None, ld_cap=None, packed=None):
         """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
 
         `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
@@ -143,8 +143,17 @@ class Engine:
             raise ValueError("mm levels M=%d exceeds ISB_MAX_MM=%d" % (M, _cabi.ISB_MAX_MM))
         splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
         p = _cabi.ptr
-        batch = _cabi.IsbBatch(len(ev["ref_pos"]), p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev["read_id"]),
-                               len(pair_mm), p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M)
+        if packed is not None:                     # packed transfer format (instrain_b200.packed.encode_packed)
+            if packed["min_qual"] != min_qual:
+                raise ValueError("packed batch was encoded with min_qual=%d" % packed["min_qual"])
+            batch = _cabi.IsbPackedBatch(packed["n_events"], p(packed["pos_off"]), p(packed["id_base"]), p(packed["bqd"]),
+                                         len(packed["esc_evt"]), p(packed["esc_evt"]), p(packed["esc_id"]), len(pair_mm),
+                                         p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M, min_qual)
+            entry = self.lib.isb_profile_batch_packed
+        else:
+            batch = _cabi.IsbBatch(len(ev["ref_pos"]), p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev["read_id"]),
+                                   len(pair_mm), p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M)
+            entry = self.lib.isb_profile_batch
         prm = _cabi.IsbParams(min_cov, min_snp, min_qual, _cabi.ISB_SKIP_LINKAGE if skip_linkage else 0,
                               float(min_freq))
         out = {}
@@ -166,7 +175,7 @@ class Engine:
             res = _cabi.IsbResult(p(out.get("counts")), p(out.get("nmask")), p(out.get("covT")), p(out.get("clonT")),
                                   p(out.get("site_flags")), p(snv), snv_cap if snv is not None else 0, p(ld),
                                   ld_cap if ld is not None else 0, 0, 0, 0, 0)
-            rc = self._check(self.lib.isb_profile_batch(self.ctx, C.byref(batch), C.byref(prm), C.byref(res)),
+            rc = self._check(entry(self.ctx, C.byref(batch), C.byref(prm), C.byref(res)),
                              allow=(_cabi.ISB_ERR_CAPACITY,))
             if rc == 0:
                 break

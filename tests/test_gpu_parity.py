@@ -243,3 +243,32 @@ def test_device_generated_batch_parity(eng, null_lut, skip_mm):
     sel["pos"] -= 60000
     if M == got["M"]:
         assert_snv_equal(sel, got["snv"])
+
+
+# ---- packed transfer format (K0 expansion) -------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["G1", "synthetic_mm", "escapes_and_N"])
+def test_packed_transfer_format_parity(eng, null_lut, case):
+    """isb_profile_batch_packed (compact host->device format, expanded by K0) gives the same tables as the columnar
+    entry point and the oracle -- including pair-id jumps > 14 (escape path) and non-ACGT bases."""
+    from instrain_b200.packed import encode_packed
+    if case == "G1":
+        batch, _ = load_batch("G1")
+    elif case == "synthetic_mm":
+        batch = synth.make_batch(30000, 60, 0.02, 77)
+    else:
+        batch = synth.make_batch(20000, 40, 0.02, 78, n_frac=0.003)
+        keep = (batch["read_id"] % 23) < 2                     # thin the pairs: large id deltas inside positions
+        for k in ("ref_pos", "base", "qual", "read_id"):
+            batch[k] = np.ascontiguousarray(batch[k][keep])
+    L = len(batch["ref_codes"])
+    pk = encode_packed(batch, 0, L, 30)
+    if case == "escapes_and_N":
+        assert len(pk["esc_evt"]) > 100
+    exp = oracle_all(batch, null_lut)
+    M = exp["counts"].shape[1]
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, packed=pk,
+                            want=("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld"))
+    assert np.array_equal(got["counts"], exp["counts"]) and np.array_equal(got["nmask"], exp["nmask"])
+    assert np.array_equal(got["covT"], exp["covT"]) and np.array_equal(got["site_flags"], exp["site_flags"])
+    assert_snv_equal(got["snv"], exp["snv"])
+    assert_ld_equal(got["ld"], exp["ld"], tol=1e-9)
