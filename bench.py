@@ -298,8 +298,8 @@ def main():
         o = dict(covT=torch.empty((Ls, Ms), dtype=torch.int32).pin_memory(),
                  clonT=torch.empty((Ls, Ms), dtype=torch.float32).pin_memory(),
                  flags=torch.empty(Ls, dtype=torch.uint8).pin_memory(),
-                 snv=torch.empty(max(1 << 16, Ls // 16) * 32, dtype=torch.uint8).pin_memory(),
-                 ld=torch.empty(max(1 << 18, Ls // 2) * 48, dtype=torch.uint8).pin_memory())
+                 snv=torch.empty(max(1 << 16, (Ls // 16) * (1 if Ms == 1 else 16)) * 32, dtype=torch.uint8).pin_memory(),
+                 ld=torch.empty(max(1 << 18, (Ls // 2) * (1 if Ms == 1 else 8)) * 48, dtype=torch.uint8).pin_memory())
         hbatch = _cabi.IsbBatch(len(hb["ref_pos"]), p(h["ref_pos"]), p(h["base"]), p(h["qual"]), p(h["read_id"]),
                                 len(hb["pair_mm"]), p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]),
                                 p(h["splits"]), Ms)

@@ -54,8 +54,9 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
         const bool counted = present && T >= min_cov;
         if (counted && !kWrite) {                                     // calculate_clonality, double, A,C,T,G order
             const double s = (double)T;
-            const double f0 = __ddiv_rn((double)C[0], s), f1 = __ddiv_rn((double)C[1], s);
-            const double f2 = __ddiv_rn((double)C[2], s), f3 = __ddiv_rn((double)C[3], s);
+            // 0/s == +0.0 exactly, so absent bases skip the (expensive) IEEE double division
+            const double f0 = C[0] ? __ddiv_rn((double)C[0], s) : 0.0, f1 = C[1] ? __ddiv_rn((double)C[1], s) : 0.0;
+            const double f2 = C[2] ? __ddiv_rn((double)C[2], s) : 0.0, f3 = C[3] ? __ddiv_rn((double)C[3], s) : 0.0;
             double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
             prob = __dadd_rn(prob, __dmul_rn(f2, f2));
             prob = __dadd_rn(prob, __dmul_rn(f3, f3));

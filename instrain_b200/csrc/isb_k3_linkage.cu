@@ -47,6 +47,10 @@ struct k3_args {
     uint8_t *has2;
     const uint32_t *mle;           // [M][nwp] pairs with mm <= m (M > 1 only)
     int64_t nwp;
+    const int64_t *tile_off;       // event offsets of position tiles of tile_tp positions (bounds the per-site search)
+    int tile_tp;
+    int32_t *pair_i, *pair_j;      // linked site pairs (site indices), filled by k3_enum_pairs
+    int64_t pair_cap;
     // output
     isb_ld_row *out;
     int64_t cap;
@@ -78,7 +82,35 @@ __device__ __forceinline__ bool k3_qualifies(const k3_args &a, int64_t e, unsign
     return a.qual[e] >= a.min_qual && b < 4 && ((bases >> b) & 1u);
 }
 
-// ---- per-site event range, pair-id window, split ----------------------------------------------------------------
+// ---- per-site event range, split --------------------------------------------------------------------------------
+// One THREAD per site: the two lower bounds are scalar binary searches bounded by the site's position tile
+// (tile_off from a k1_tile_offsets launch: ~1e5 events => 17 steps).  The searches are pure latency (dependent
+// scattered loads), so what matters is how many are in flight: the first version ran them one site per WARP over the
+// whole 1e10-event column (34 steps, 1 site in flight per warp) and took 180 us for 1e5 sites.
+__global__ void __launch_bounds__(256) k3_site_ranges(k3_args a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.S) return;
+    const int32_t p = a.site_pos[k];
+    const int64_t abs_pos = (int64_t)p + a.start;
+    const int t = p / a.tile_tp;
+    const int64_t t_lo = a.tile_off[t], t_hi = a.tile_off[t + 1];
+    const int64_t lo = isb_lower_bound(a.ref_pos, t_lo, t_hi, abs_pos);
+    const int64_t hi = isb_lower_bound(a.ref_pos, lo, t_hi, abs_pos + 1);
+    a.site_ev[2 * k] = lo;
+    a.site_ev[2 * k + 1] = hi;
+    // split = last split whose start <= abs_pos, if abs_pos <= its end
+    int s_lo = 0, s_hi = a.n_splits;
+    while (s_lo < s_hi) {
+        const int mid = (s_lo + s_hi) >> 1;
+        if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
+    }
+    int split = s_lo - 1;
+    if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
+    a.meta[k].split = split;
+}
+
+// ---- per-site pair-id window (warp per site, coalesced) -----------------------------------------------------------
 __global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
 {
     const int lane = threadIdx.x & 31;
@@ -86,9 +118,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
     const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     for (int64_t k = warp0; k < a.S; k += n_warps) {
         const int32_t p = a.site_pos[k];
-        const int64_t abs_pos = (int64_t)p + a.start;
-        const int64_t lo = isb_lower_bound(a.ref_pos, 0, a.n, abs_pos);
-        const int64_t hi = isb_lower_bound(a.ref_pos, lo, a.n, abs_pos + 1);
+        const int64_t lo = a.site_ev[2 * k], hi = a.site_ev[2 * k + 1];
         const unsigned bases = a.site_flags[p] & 0xF;
         int idmin = INT_MAX, idmax = -1;
         for (int64_t e = lo + lane; e < hi; e += 32)
@@ -103,22 +133,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
             idmax = max(idmax, __shfl_xor_sync(ISB_FULL, idmax, d));
         }
         if (lane == 0) {
-            // split = last split whose start <= abs_pos, if abs_pos <= its end
-            int s_lo = 0, s_hi = a.n_splits;
-            while (s_lo < s_hi) {
-                const int mid = (s_lo + s_hi) >> 1;
-                if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
-            }
-            int split = s_lo - 1;
-            if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
-            isb_site_meta m;
+            isb_site_meta m = a.meta[k];
             m.ev_lo_rel = 0;
             m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
             m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
-            m.split = split;
             a.meta[k] = m;
-            a.site_ev[2 * k] = lo;
-            a.site_ev[2 * k + 1] = hi;
             a.site_words[k] = (1 + 2 * __popc(bases)) * m.nw;
             a.has2[k] = 0;
         }
@@ -278,16 +297,59 @@ __device__ __forceinline__ bool k3_level_present(const k3_args &a, int32_t p, in
     return a.nmask && ((a.nmask[p] >> m) & 1ull);
 }
 
-__device__ void k3_process_pair(const k3_args &a, const k3_site &si, const k3_site &sj, unsigned long long &n_pairs_local)
+// Linked site pairs are first ENUMERATED (warp per site, lanes over the partner sites of the same split: window overlap
+// + one AND over the `any` rows), then evaluated one THREAD per pair.  The evaluation is a chain of dependent global
+// loads (rows, counts, masks); with one pair per lane of a site-warp only ~3.7 linked pairs per site kept the machine
+// busy (300 us for 3.7e5 pairs), one thread per pair puts every pair in flight at once.
+__global__ void __launch_bounds__(K3_THREADS) k3_enum_pairs(k3_args a)
 {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    for (int64_t k = warp0; k < a.S; k += n_warps) {
+        const isb_site_meta mi = a.meta[k];
+        if (mi.split < 0 || mi.nw == 0) continue;
+        const uint32_t *any_i = a.rows + a.row_off[k] - mi.wlo;
+        for (int64_t jb = k + 1;; jb += 32) {
+            const int64_t j = jb + lane;
+            isb_site_meta mj;
+            mj.ev_lo_rel = 0; mj.nw = 0; mj.wlo = 0; mj.split = -2;
+            if (j < a.S) mj = a.meta[j];
+            const bool cand = j < a.S && mj.split == mi.split;
+            if (!__any_sync(ISB_FULL, cand)) break;
+            bool linked = false;
+            if (cand && mj.nw > 0) {
+                const int lo = max(mi.wlo, mj.wlo), hi = min(mi.wlo + mi.nw, mj.wlo + mj.nw);
+                if (lo < hi) {
+                    const uint32_t *any_j = a.rows + a.row_off[j] - mj.wlo;
+                    for (int w = lo; w < hi; ++w)
+                        if (any_i[w] & any_j[w]) { linked = true; break; }
+                }
+            }
+            const unsigned m = __ballot_sync(ISB_FULL, linked);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.n_site_pairs, (unsigned long long)__popc(m));
+                base = __shfl_sync(ISB_FULL, base, 0);
+                if (linked) {
+                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                    if ((int64_t)slot < a.pair_cap) { a.pair_i[slot] = (int32_t)k; a.pair_j[slot] = (int32_t)j; }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k3_pair_stats(k3_args a, int64_t n_pairs_listed)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs_listed) return;
+    const k3_site si = k3_load_site(a, a.pair_i[t]), sj = k3_load_site(a, a.pair_j[t]);
     const int lo = max(si.wlo, sj.wlo), hi = min(si.wlo + si.nw, sj.wlo + sj.nw);
-    if (lo >= hi) return;
-    const uint32_t *any_i = si.rows - si.wlo, *any_j = sj.rows - sj.wlo;
-    unsigned long long pm = 0;                                         // mm levels having >= 1 linking pair
-    if (a.M == 1) {
-        for (int w = lo; w < hi; ++w)
-            if (any_i[w] & any_j[w]) { pm = 1ull; break; }
-    } else {
+    unsigned long long pm = 1ull;                                      // mm levels having >= 1 linking pair
+    if (a.M > 1) {
+        const uint32_t *any_i = si.rows - si.wlo, *any_j = sj.rows - sj.wlo;
+        pm = 0;
         for (int w = lo; w < hi; ++w) {
             uint32_t x = any_i[w] & any_j[w];
             while (x) {
@@ -296,9 +358,8 @@ __device__ void k3_process_pair(const k3_args &a, const k3_site &si, const k3_si
                 pm |= 1ull << __ldg(a.pair_mm + (((int64_t)w << 5) + b));
             }
         }
+        if (!pm) return;
     }
-    if (!pm) return;
-    ++n_pairs_local;
     int C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
     const int m_last = 63 - __clzll(pm);
     for (int m = 0; m <= m_last; ++m) {
@@ -323,31 +384,6 @@ __device__ void k3_process_pair(const k3_args &a, const k3_site &si, const k3_si
         const int cab = k3_pair_count(si, ra, sj, rb, lo, hi, mask);
         k3_emit(a, si.p, sj.p, m, A, al, B, bl, cAB, cAb, caB, cab);
     }
-}
-
-__global__ void __launch_bounds__(K3_THREADS) k3_pairs(k3_args a)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
-    unsigned long long n_pairs_local = 0;
-    for (int64_t k = warp0; k < a.S; k += n_warps) {
-        const k3_site si = k3_load_site(a, k);
-        const int split = a.meta[k].split;
-        if (split < 0 || si.nw == 0) continue;
-        for (int64_t jb = k + 1;; jb += 32) {
-            const int64_t j = jb + lane;
-            const bool cand = j < a.S && a.meta[j].split == split;
-            if (!__any_sync(ISB_FULL, cand)) break;
-            if (cand) {
-                const k3_site sj = k3_load_site(a, j);
-                if (sj.nw > 0) k3_process_pair(a, si, sj, n_pairs_local);
-            }
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n_pairs_local += __shfl_xor_sync(ISB_FULL, n_pairs_local, d);
-    if (lane == 0 && n_pairs_local) atomicAdd(a.n_site_pairs, n_pairs_local);
 }
 
 // Self edges: a pair with two entries (first, second in column order) on ONE site gives the combo
@@ -438,9 +474,18 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     a.out = rows; a.cap = cap;
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
 
-    // 2. per-site event range + pair-id window
+    // 2. per-site event range + pair-id window (searches bounded by position-tile event offsets)
+    {
+        const int tp = 1024;
+        const int n_tiles = (L + tp - 1) / tp;
+        if ((rc = isb_tile_offsets(ctx, ref_pos, n, start, L, tp, n_tiles))) return rc;
+        a.tile_off = (const int64_t *)ctx->buf[SL_K3_TILE_OFF].p;
+        a.tile_tp = tp;
+    }
     const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;
     const int grid_sites = (int)(site_warps_blocks < (int64_t)ctx->sm_count * 32 ? site_warps_blocks : (int64_t)ctx->sm_count * 32);
+    k3_site_ranges<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
     k3_site_windows<<<grid_sites, K3_THREADS, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
 
@@ -475,8 +520,30 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     // 5. rows, pairs, self edges
     k3_build_rows<<<grid_sites, K3_THREADS, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
-    k3_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
-    ISB_LAUNCH_CHECK();
+    for (int attempt = 0; attempt < 2; ++attempt) {                    // linked-pair list, then one thread per pair
+        int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
+        if (cap_pairs < 8 * S) {
+            if ((rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(8 * S)))) return rc;
+            cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
+        }
+        a.pair_cap = cap_pairs;
+        a.pair_i = (int32_t *)ctx->buf[SL_PAIRS].p;
+        a.pair_j = a.pair_i + cap_pairs;
+        ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(unsigned long long), st));
+        k3_enum_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
+        ISB_LAUNCH_CHECK();
+        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaStreamSynchronize(st));
+        const int64_t n_listed = (int64_t)ctx->h_counters[3];
+        if (n_listed <= cap_pairs) {
+            if (n_listed > 0) {
+                k3_pair_stats<<<(int)((n_listed + 255) / 256), 256, 0, st>>>(a, n_listed);
+                ISB_LAUNCH_CHECK();
+            }
+            break;
+        }
+        if ((rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(n_listed + n_listed / 8)))) return rc;
+    }
     const int grid_self = (int)((S + 127) / 128 < (int64_t)ctx->sm_count * 8 ? (S + 127) / 128 : (int64_t)ctx->sm_count * 8);
     k3_self_edges<<<grid_self, 128, 0, st>>>(a);
     ISB_LAUNCH_CHECK();

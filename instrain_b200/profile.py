@@ -6,8 +6,9 @@ Same arguments and keyword names as the reference (`kwargs` = vars(args) + s2s +
 Where the reference farms (scaffold, split) commands to worker processes (profile_controller.py:243-271) and each worker
 runs profile_split's per-column Python loop (profile_utilities.py:115-266), this shim
   1. streams the BAM once through the C++ host packer (instrain_b200/packer.py),
-  2. concatenates scaffolds into batches (one int32 coordinate space per batch),
-  3. runs K1 -> K2 -> K3 for the whole batch through the C-ABI (Engine.profile_batch),
+  2. concatenates scaffolds into batches (one int32 coordinate space per batch) and encodes each batch in the packed
+     host->device transfer format (instrain_b200/packed.py),
+  3. runs K0 (expand) -> K1 -> K2 -> K3 for the whole batch through the C-ABI (isb_profile_batch_packed),
   4. turns the row arrays into the reference's per-scaffold tables (instrain_b200/tables.py).
 There is no CPU fallback: without the CUDA library / a GPU this raises.
 """
@@ -19,6 +20,7 @@ import pandas as pd
 
 from . import tables
 from .engine import Engine
+from .packed import encode_packed
 from .packer import BamPacker
 from .synth import iterate_splits
 
@@ -90,8 +92,10 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
                   read_id=cat(batch["read_id"]), pair_mm=cat(batch["pair_mm"]))
         ref_codes = cat(batch["ref"])
         offs = np.array(batch["off"], dtype=np.int64)
+        # host -> device in the packed transfer format (~1 B/event); kernel K0 expands it to the event columns in HBM
+        pk = encode_packed(ev, 0, len(ref_codes), 30)
         out = engine.profile_batch(ev, ref_codes, np.array(batch["splits"], np.int32), min_cov=min_cov, min_freq=min_freq,
-                                   min_snp=min_snp, want=("covT", "clonT", "snv", "ld"))
+                                   min_snp=min_snp, want=("covT", "clonT", "snv", "ld"), packed=pk)
         seqs = {n: s2s[n] for n in batch["names"]}
         snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs))
         ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
