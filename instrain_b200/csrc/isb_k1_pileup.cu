@@ -323,8 +323,8 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         // address (49.8 M bank conflicts with the contiguous mapping), and the odd stride keeps the 128-bit position
         // loads and 32-bit base/qual loads bank-conflict-free.
         constexpr int kW = kT / 32;
-        static_assert(kW % 2 == 1 || !kM1, "interleaved mapping needs an odd warp count");
-        const int i0 = kM1 ? ((tid & 31) * kW + (tid >> 5)) * kE : tid * kE;
+        static_assert(kW % 2 == 1, "interleaved mapping needs an odd warp count");
+        const int i0 = ((tid & 31) * kW + (tid >> 5)) * kE;
         // valid events of the stage: chunk-relative index in [v_lo, v_hi)
         const int v_lo = (int)max((int64_t)0, e_lo - c_lo), v_hi = (int)min((int64_t)CH, e_hi - c_lo);
         if (kM1) {
@@ -354,32 +354,52 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
             }
             k1_flush(s_cnt, r.cur_p, rel0, np, true, r.a0, r.a1, r.a2, r.a3, bad);
         } else {
-#pragma unroll 1
-            for (int v = 0; v < kE / 4; ++v) {
+            // M > 1: the (position, mm) cell changes almost every event, so each event goes straight to the tile
+            // histogram with ONE unconditional shared-memory reduction (value 0 when the event does not count; clamped
+            // index) -- no per-event branches.  The interleaved run mapping keeps the 32 addresses of a warp
+            // instruction on different positions.
+            constexpr int NV = kE / 4;
+            int4 pv[NV], rv[NV];
+            uint32_t b4[NV], q4[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                pv[v] = *reinterpret_cast<const int4 *>(s_pos + i0 + 4 * v);
+                rv[v] = *reinterpret_cast<const int4 *>(s_rid + i0 + 4 * v);
+                b4[v] = *reinterpret_cast<const uint32_t *>(s_base + i0 + 4 * v);
+                q4[v] = *reinterpret_cast<const uint32_t *>(s_qual + i0 + 4 * v);
+            }
+            const uint32_t s_cnt_u32 = k1_smem_u32(s_cnt);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
                 const int i = i0 + 4 * v;
-                if (i + 4 <= v_lo || i >= v_hi) continue;
-                const int4 pv = *reinterpret_cast<const int4 *>(s_pos + i);
-                const int4 rv = *reinterpret_cast<const int4 *>(s_rid + i);
-                const uint32_t b4 = *reinterpret_cast<const uint32_t *>(s_base + i);
-                const uint32_t q4 = *reinterpret_cast<const uint32_t *>(s_qual + i);
-                const int32_t ps[4] = {pv.x, pv.y, pv.z, pv.w};
-                const int32_t rs[4] = {rv.x, rv.y, rv.z, rv.w};
+                const int32_t ps[4] = {pv[v].x, pv[v].y, pv[v].z, pv[v].w};
+                const int32_t rs[4] = {rv[v].x, rv[v].y, rv[v].z, rv[v].w};
+                int mmv[4];
+                bool okv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                         // the four mm gathers are issued back to back
+                    const int q = (q4[v] >> (8 * j)) & 0xff;
+                    okv[j] = (i + j >= v_lo) && (i + j < v_hi) && (q >= min_qual);
+                    mmv[j] = okv[j] ? (int)__ldg(pair_mm + rs[j]) : 0;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int b = (b4 >> (8 * j)) & 0xff, q = (q4 >> (8 * j)) & 0xff;
-                    if (i + j < v_lo || i + j >= v_hi || q < min_qual) continue;
+                    const int b = (b4[v] >> (8 * j)) & 0xff;
                     const unsigned pr = (unsigned)(ps[j] - rel0);
-                    if (pr >= (unsigned)np) { bad |= 1u; continue; }
-                    const int mm = __ldg(pair_mm + rs[j]);
-                    if (mm >= M) { atomicOr(d_err, ISB_DEV_ERR_MM); continue; }
-                    if (b >= 4) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mm); continue; }
-                    atomicAdd(s_cnt + (((int)pr * M + mm) << 2) + b, 1);
+                    const bool inb = pr < (unsigned)np, mm_ok = mmv[j] < M;
+                    bad |= (okv[j] && !inb) ? 1u : 0u;
+                    bad |= (okv[j] && !mm_ok) ? 2u : 0u;
+                    const bool count = okv[j] && inb && mm_ok;
+                    if (count && b >= 4) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mmv[j]); }   // rare
+                    const unsigned cell = min(pr, (unsigned)np) * (unsigned)M + (unsigned)min(mmv[j], M - 1);
+                    k1_red(s_cnt_u32 + (((cell << 2) + (unsigned)(b & 3)) << 2), (count && b < 4) ? 1u : 0u);
                 }
             }
         }
         __syncthreads();                                               // stage consumed: thread 0 may refill it
     }
-    if (bad) atomicOr(d_err, ISB_DEV_ERR_ORDER);
+    if (bad & 1u) atomicOr(d_err, ISB_DEV_ERR_ORDER);
+    if (bad & 2u) atomicOr(d_err, ISB_DEV_ERR_MM);
     int4 *dst = reinterpret_cast<int4 *>(counts) + (size_t)p0 * M;
     for (int i = tid; i < n_cnt4; i += kT) dst[i] = reinterpret_cast<const int4 *>(s_cnt)[i];
 }
@@ -478,7 +498,7 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                            (M == 1 || (((uintptr_t)read_id) & 15) == 0);
 #define K1_ARGS ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, M, TP, min_qual, counts, nmask, ctx->d_err
 #define K1_TMA_ARGS ctx, n_tiles, smem, M, ref_pos, base, qual, read_id, pair_mm, tile_off, n, start, L, TP, min_qual, counts, nmask
-    if (variant == 0 || !aligned16 || (M > 1 && variant != 3)) {
+    if (variant == 0 || !aligned16 || (M > 1 && variant == 1)) {
         if (M == 1) k1_pileup_tiles<true><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
         else k1_pileup_tiles<false><<<n_tiles, K1_THREADS, smem, st>>>(K1_ARGS);
     } else if (M == 1) {
@@ -491,7 +511,7 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
         else rc2 = k1_launch_tma<true, 352, 12, 3>(K1_TMA_ARGS);                 // default: 2 CTAs x 11 warps / SM
         if (rc2) return rc2;
     } else {
-        int rc2 = k1_launch_tma<false, 256, 12, 3>(K1_TMA_ARGS);
+        int rc2 = k1_launch_tma<false, 224, 12, 3>(K1_TMA_ARGS);                 // 2 CTAs x 7 warps / SM at M ~ 15
         if (rc2) return rc2;
     }
 #undef K1_ARGS

@@ -145,9 +145,15 @@ __global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
 }
 
 // ---- bit rows ---------------------------------------------------------------------------------------------------
+// Warp per site.  Rows of a site that fit in the warp's 64-word shared-memory scratch (the common case: 1 + 2*|bases|
+// rows x <= 12 words) are assembled there with shared-memory atomics and stored once, coalesced; larger windows fall
+// back to global atomics on the (pre-zeroed) row storage.
+#define K3_ROW_SCRATCH 64
 __global__ void __launch_bounds__(K3_THREADS) k3_build_rows(k3_args a)
 {
+    __shared__ uint32_t s_rows[K3_THREADS / 32][K3_ROW_SCRATCH];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     for (int64_t k = warp0; k < a.S; k += n_warps) {
@@ -156,8 +162,16 @@ __global__ void __launch_bounds__(K3_THREADS) k3_build_rows(k3_args a)
         const int32_t p = a.site_pos[k];
         const unsigned bases = a.site_flags[p] & 0xF;
         const int na = __popc(bases);
-        uint32_t *any = a.rows + a.row_off[k];
+        const int n_words = (1 + 2 * na) * m.nw;
+        const bool in_smem = n_words <= K3_ROW_SCRATCH;
+        uint32_t *g_any = a.rows + a.row_off[k];
+        uint32_t *any = in_smem ? s_rows[wib] : g_any;
+        if (in_smem) {
+            for (int i = lane; i < n_words; i += 32) any[i] = 0u;
+            __syncwarp();
+        }
         const int64_t lo = a.site_ev[2 * k], hi = a.site_ev[2 * k + 1];
+        bool dbl = false;
         for (int64_t e = lo + lane; e < hi; e += 32) {
             if (!k3_qualifies(a, e, bases)) continue;
             const int b = a.base[e];
@@ -165,12 +179,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_build_rows(k3_args a)
             const int w = (id >> 5) - m.wlo;
             const uint32_t bit = 1u << (id & 31);
             const int r = __popc(bases & ((1u << b) - 1u));
-            if (atomicOr(any + w, bit) & bit) a.has2[k] = 1;          // second entry of this pair on this site
+            if (atomicOr(any + w, bit) & bit) dbl = true;             // second entry of this pair on this site
             uint32_t *ge1 = any + (size_t)(1 + r) * m.nw;
             if (atomicOr(ge1 + w, bit) & bit) {
                 uint32_t *ge2 = any + (size_t)(1 + na + r) * m.nw;
                 if (atomicOr(ge2 + w, bit) & bit) atomicOr(a.d_err, ISB_DEV_ERR_MULT);
             }
+        }
+        if (__any_sync(ISB_FULL, dbl) && lane == 0) a.has2[k] = 1;
+        if (in_smem) {
+            __syncwarp();
+            for (int i = lane; i < n_words; i += 32) g_any[i] = any[i];
+            __syncwarp();
         }
     }
 }

@@ -71,6 +71,14 @@ def make_batch(which, window=10000):
         ld_counts=ld[["countAB", "countAb", "countaB", "countab"]].values.astype(np.int32),
         ld_alleles=np.stack([ld[c].map(B).values for c in ("allele_A", "allele_a", "allele_B", "allele_b")], 1).astype(np.uint8),
         ld_r2=ld["r2"].values.astype(np.float64), ld_d_prime=ld["d_prime"].values.astype(np.float64))
+    # merge-stage summary: the reference's stored cumulative_scaffold_table, non-random columns
+    from oracle.summary import COLUMNS
+    cst = pd.read_csv(os.path.join(raw, "cumulative_scaffold_table.csv.gz"))
+    name2idx = {n: i for i, n in enumerate(names)}
+    cst = cst.assign(sidx=cst["scaffold"].map(name2idx)).sort_values(["sidx", "mm"])
+    exp["sum_scaffold"] = cst["sidx"].values.astype(np.int32)
+    exp["sum_columns"] = np.array(COLUMNS)
+    exp["sum_values"] = cst[COLUMNS].values.astype(np.float64)
     return batch, exp
 
 

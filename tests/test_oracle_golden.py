@@ -45,3 +45,25 @@ def test_oracle_reproduces_reference_goldens(which, null_lut):
 def test_null_lut_shape(null_lut):
     lut, dflt = null_lut
     assert dflt == 17 and lut[0] == -1 and lut[5] == 2 and len(lut) == 10000
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_summary_restatement_reproduces_cumulative_scaffold_table(which, null_lut):
+    """oracle/summary.py (make_coverage_table restated) vs the reference's stored cumulative_scaffold_table
+    (non-random columns), cf. the reference's test_profile_3 / test_profile_16."""
+    from oracle import summary
+    batch, exp = load_batch(which)
+    lut, dflt = null_lut
+    out = restate.profile_events(batch, batch["ref_codes"], lut, dflt, batch["splits"], do_linkage=False)
+    rows, sidx = [], []
+    for i in range(len(batch["scaffold_names"])):
+        lo = int(batch["scaffold_off"][i])
+        hi = lo + int(batch["scaffold_len"][i])
+        sn = out["snv"][(out["snv"]["pos"] >= lo) & (out["snv"]["pos"] < hi)]
+        for r in summary.scaffold_summary(out["covT"][lo:hi], out["clonT"][lo:hi], out["nmask"][lo:hi], sn, lo):
+            rows.append([float(r[c]) for c in summary.COLUMNS])
+            sidx.append(i)
+    got = np.array(rows)
+    assert list(exp["sum_columns"]) == summary.COLUMNS
+    assert np.array_equal(np.array(sidx), exp["sum_scaffold"])
+    assert np.allclose(got, exp["sum_values"], rtol=0, atol=1e-9, equal_nan=True)
