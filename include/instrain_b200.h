@@ -196,6 +196,28 @@ typedef struct {
 
 int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb_params *prm, isb_result *out);
 
+/* ---- stage K4: merge-stage summary reductions (the row after the hot path) ----------------------------- */
+/* Numeric core of make_coverage_table (profile_utilities.py:425-506) with mm_counts_to_counts_shrunk (:508-532) and
+ * get_basewise_clons (:534-546): per scaffold s (positions [scaffold_off[s], scaffold_off[s+1]) of covT / clonT) and mm
+ * level m, over cumulative coverage c_m(p) = sum_{m'<=m} covT[p][m'] and the clonality of the highest level <= m at
+ * which clonT is set.  out[s*M + m]; the host derives breadth, mean, std, SEM, nucl_diversity, ANI from these exact
+ * sums (instrain_b200/summary.py).  Medians are exact order statistics (4-pass radix select). */
+typedef struct {
+    int64_t length;        /* positions of the scaffold */
+    int64_t nonzero;       /* positions with c_m > 0                         -> breadth */
+    int64_t sum_cov;       /* sum of c_m                                      -> coverage (mean) */
+    uint64_t sum_cov2;     /* sum of c_m^2                                    -> coverage_std / coverage_SEM */
+    int64_t counted;       /* positions with a clonality value                -> breadth_minCov, ANI denominators */
+    double sum_clon;       /* sum of those clonalities                        -> nucl_diversity = 1 - mean */
+    int32_t cov_med_lo, cov_med_hi;   /* the two middle order statistics of c_m (equal when length is odd) */
+    float clon_med_lo, clon_med_hi;   /* same for the clonality values (NaN when counted == 0) */
+    int32_t present;       /* level m is a key of the scaffold's covT (the table has a row for it) */
+    int32_t pad;
+} isb_summary_row;
+
+int isb_scaffold_summary(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const uint64_t *nmask,
+                         int32_t n_scaffolds, const int32_t *scaffold_off, isb_summary_row *out);
+
 /* number of kernels this library has launched on the context since creation (bench.py's gpu_launches) */
 int64_t isb_launch_count(const isb_ctx *ctx);
 

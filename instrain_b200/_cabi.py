@@ -25,12 +25,17 @@ LD_DT = np.dtype([("pos_a", "<i4"), ("pos_b", "<i4"), ("mm", "<i4"), ("c_AB", "<
                   ("allele_b", "u1"), ("r2", "<f8"), ("d_prime", "<f8")])
 assert SNV_DT.itemsize == 32 and LD_DT.itemsize == 48
 
+SUMMARY_DT = np.dtype([("length", "<i8"), ("nonzero", "<i8"), ("sum_cov", "<i8"), ("sum_cov2", "<u8"), ("counted", "<i8"),
+                       ("sum_clon", "<f8"), ("cov_med_lo", "<i4"), ("cov_med_hi", "<i4"), ("clon_med_lo", "<f4"),
+                       ("clon_med_hi", "<f4"), ("present", "<i4"), ("pad", "<i4")])
+assert SUMMARY_DT.itemsize == 72
+
 CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "pop_SNV"]
 
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
-           "isb_launch_count",
+           "isb_scaffold_summary", "isb_launch_count",
            "isb_enable_timing", "isb_stage_times",
            "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
            "isb_bam_peek_tid", "isb_pack_scaffold", "isb_events_count", "isb_events_pairs", "isb_events_reads_seen",
@@ -106,6 +111,8 @@ def load():
     L.isb_enable_timing.argtypes = [vp, C.c_int]
     L.isb_stage_times.restype = C.c_int
     L.isb_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.isb_scaffold_summary.restype = C.c_int
+    L.isb_scaffold_summary.argtypes = [vp, i32, C.c_int, vp, vp, vp, i32, vp, vp]
     L.isb_profile_batch.restype = C.c_int
     L.isb_profile_batch.argtypes = [vp, C.POINTER(IsbBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     L.isb_profile_batch_packed.restype = C.c_int

@@ -169,6 +169,7 @@ void isb_destroy(isb_ctx *ctx)
     for (int i = 0; i < SL_COUNT; ++i)
         if (ctx->buf[i].p) cudaFree(ctx->buf[i].p);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_thr2) cudaFree(ctx->d_thr2);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -325,6 +326,28 @@ int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const ui
     ISB_CUDA(cudaStreamSynchronize(ctx->stream));
     if ((rc = check_dev_err(ctx))) return rc;
     if (*n_rows > cap) return isb_fail(ctx, ISB_ERR_CAPACITY, "isb_linkage: row buffer too small");
+    return ISB_OK;
+}
+
+int isb_scaffold_summary(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const uint64_t *nmask,
+                         int32_t n_scaffolds, const int32_t *scaffold_off, isb_summary_row *out)
+{
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!covT || !clonT || !scaffold_off || !out || n_scaffolds < 0)
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_scaffold_summary: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    const int32_t *d_cov, *d_off; const float *d_clon; const uint64_t *d_nm;
+    // covT / clonT / nmask may still sit in the context's output staging slots (host callers pass host copies)
+    if ((rc = stage_in(ctx, SL_COVT, covT, (size_t)L * M, &d_cov))) return rc;
+    if ((rc = stage_in(ctx, SL_CLONT, clonT, (size_t)L * M, &d_clon))) return rc;
+    if ((rc = stage_in(ctx, SL_NMASK, nmask, (size_t)L, &d_nm))) return rc;
+    if ((rc = stage_in(ctx, SL_K4_OFF, scaffold_off, (size_t)n_scaffolds + 1, &d_off))) return rc;
+    isb_summary_row *d_out;
+    if ((rc = stage_out(ctx, SL_K4_OUT, out, (size_t)n_scaffolds * M, &d_out))) return rc;
+    if ((rc = isb_k4_launch(ctx, L, M, d_cov, d_clon, (const unsigned long long *)d_nm, n_scaffolds, d_off, d_out))) return rc;
+    if ((rc = finish_out(ctx, out, d_out, (size_t)n_scaffolds * M))) return rc;
+    ISB_CUDA(cudaStreamSynchronize(ctx->stream));
     return ISB_OK;
 }
 

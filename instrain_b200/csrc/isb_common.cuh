@@ -22,6 +22,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_TILE_OFF,                                                                   // K1 tile event offsets
     SL_PK_OFF, SL_PK_IDBASE, SL_PK_BQD, SL_PK_ESC_EVT, SL_PK_ESC_ID,                  // packed transfer format (K0 inputs)
     SL_K3_TILE_OFF, SL_PAIRS,
+    SL_K4_CUM, SL_K4_CLON, SL_K4_STATE, SL_K4_HIST, SL_K4_OFF, SL_K4_OUT,
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
     SL_COUNT
 };
@@ -39,6 +40,8 @@ struct isb_ctx {
     int32_t *d_lut;
     int n_lut;
     int lut_default;
+    int32_t *d_thr2;                  // K2: max(null-model threshold, min count passing min_freq) per coverage
+    double thr2_min_freq;
     unsigned long long *d_counters;   // [0]=n_snv rows [1]=n_ld rows [2]=n_sites [3]=n_site_pairs [4]=total row words
     unsigned int *d_err;
     unsigned long long *h_counters;   // pinned mirror
@@ -102,6 +105,8 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
                   int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap);
 int isb_ensure(isb_ctx *ctx, int slot, size_t bytes);
+int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const unsigned long long *nmask,
+                  int n_seg, const int32_t *seg_off, isb_summary_row *out);
 int isb_tile_offsets(isb_ctx *ctx, const int32_t *ref_pos, int64_t n, int32_t start, int32_t L, int tp, int n_tiles);
 int isb_k0_launch(isb_ctx *ctx, int64_t n, const int64_t *pos_off, const int32_t *id_base, const uint8_t *bqd,
                   int64_t n_esc, const int64_t *esc_evt, const int32_t *esc_id, int32_t start, int32_t L, int qpass,

@@ -13,6 +13,24 @@
 
 #define K2_THREADS 256
 
+// thr2[T] = max(null-model threshold, smallest c with (double)c / (double)T >= min_freq): with it the reference's per-base
+// test "c >= model[T] and float(c)/T >= min_freq" (snv_utilities.py:173-180) is ONE integer compare, bit-exact because
+// IEEE division is monotone in c.  Built once per (context, min_freq); coverages >= n_lut keep the division.
+__global__ void k2_build_thr2(const int32_t *__restrict__ lut, int n_lut, int lut_default, double min_freq,
+                              int32_t *__restrict__ thr2)
+{
+    const int T = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T >= n_lut) return;
+    const int thr = __ldg(lut + T) >= 0 ? __ldg(lut + T) : lut_default;
+    int lo = 0, hi = T + 1;                                  // smallest c in [0, T+1] passing the frequency test
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool ok = T > 0 && __ddiv_rn((double)mid, (double)T) >= min_freq;
+        if (ok) hi = mid; else lo = mid + 1;
+    }
+    thr2[T] = max(thr, lo);
+}
+
 struct k2_site_state {
     int n_rows;
     int cryptic;
@@ -33,7 +51,7 @@ __device__ __forceinline__ int k2_argmax4(const int *c)
 template <bool kWrite>
 __device__ __forceinline__ k2_site_state
 k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long long nm, int ref,
-             const int32_t *__restrict__ lut, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
+             const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
              int32_t *__restrict__ covT, float *__restrict__ clonT, isb_snv_row *__restrict__ rows, int64_t slot,
              int64_t cap, int cryptic_final)
 {
@@ -64,11 +82,17 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
         }
         if (!kWrite) clonT[(size_t)p * M + m] = clon;
         if (!counted) continue;                                       // call_snv_site -> (None, 0)
-        const int thr = (T < n_lut && __ldg(lut + T) >= 0) ? __ldg(lut + T) : lut_default;
-        int i = 0;
+        int thr, i = 0;
+        if (T < n_lut) {                                              // integer form of the two-part presence test
+            thr = __ldg(thr2 + T);
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (C[b] >= thr && __ddiv_rn((double)C[b], (double)T) >= min_freq) ++i;
+            for (int b = 0; b < 4; ++b) i += (C[b] >= thr);
+        } else {
+            thr = lut_default;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (C[b] >= thr && __ddiv_rn((double)C[b], (double)T) >= min_freq) ++i;
+        }
         const int con = k2_argmax4(C);
         const bool is_row = (i > 1) || (i == 1 && con != ref) || (i == 0);
         if (!is_row) {                                                // snp == -1
@@ -87,7 +111,8 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
             else if (ref == var) cls = ISB_CLS_CON_SNV;
             else {
                 const int cr = C[ref];                                // is_present(counts[ref], total, model, min_freq)
-                cls = (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq) ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
+                const bool pres = T < n_lut ? (cr >= thr) : (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq);
+                cls = pres ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
             }
             const int64_t r = slot + st.n_rows;
             if (r < cap) {
@@ -109,7 +134,7 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
 
 __global__ void __launch_bounds__(K2_THREADS)
 k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigned long long *__restrict__ nmask,
-             const uint8_t *__restrict__ ref, const int32_t *__restrict__ lut, int n_lut, int lut_default,
+             const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
              int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
              uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
              unsigned long long *__restrict__ n_rows)
@@ -123,7 +148,7 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
     if (active) {
         nm = nmask ? nmask[p] : 0ull;
         r = ref[p];
-        st = k2_site_loop<false>(p, M, counts, nm, r, lut, n_lut, lut_default, start, min_cov, min_freq, covT, clonT,
+        st = k2_site_loop<false>(p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, covT, clonT,
                                  nullptr, 0, 0, 0);
         site_flags[p] = (uint8_t)(st.bases | (st.any_snp ? ISB_SITE_ANYSNP : 0));
     }
@@ -140,7 +165,7 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
     if (lane == 0) base_slot = atomicAdd(n_rows, (unsigned long long)total);
     base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
     if (st.n_rows > 0)
-        k2_site_loop<true>(p, M, counts, nm, r, lut, n_lut, lut_default, start, min_cov, min_freq, covT, clonT, rows,
+        k2_site_loop<true>(p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, covT, clonT, rows,
                            (int64_t)base_slot + incl - st.n_rows, cap, st.cryptic);
 }
 
@@ -151,8 +176,14 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
     cudaStream_t st = ctx->stream;
     ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 0, 0, sizeof(unsigned long long), st));
     if (L <= 0) return ISB_OK;
+    if (!ctx->d_thr2 || ctx->thr2_min_freq != min_freq) {             // (re)build the merged integer threshold table
+        if (!ctx->d_thr2) ISB_CUDA(cudaMalloc(&ctx->d_thr2, sizeof(int32_t) * (size_t)ctx->n_lut));
+        k2_build_thr2<<<(ctx->n_lut + 255) / 256, 256, 0, st>>>(ctx->d_lut, ctx->n_lut, ctx->lut_default, min_freq, ctx->d_thr2);
+        ISB_LAUNCH_CHECK();
+        ctx->thr2_min_freq = min_freq;
+    }
     k2_call_snvs<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
-        L, M, counts, nmask, ref, ctx->d_lut, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
+        L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
         site_flags, rows, cap, ctx->d_counters + 0);
     ISB_LAUNCH_CHECK();
     return ISB_OK;

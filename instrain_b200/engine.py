@@ -127,6 +127,19 @@ class Engine:
                 return rows[:n.value].copy()
             cap = int(n.value)
 
+    # ---- stage K4 (merge-stage summary reductions) -----------------------------------------------------------------
+    def scaffold_summary(self, covT, clonT, nmask, scaffold_off):
+        """covT int32[L,M], clonT float32[L,M], nmask uint64[L] or None, scaffold_off int32[n+1] -> SUMMARY_DT[n*M]."""
+        L, M = covT.shape
+        off = np.ascontiguousarray(scaffold_off, dtype=np.int32)
+        n_sc = len(off) - 1
+        if off[0] != 0 or off[-1] != L:
+            raise ValueError("scaffold_off must start at 0 and end at L")
+        rows = np.zeros(n_sc * M, dtype=_cabi.SUMMARY_DT)
+        p = _cabi.ptr
+        self._check(self.lib.isb_scaffold_summary(self.ctx, L, M, p(covT), p(clonT), p(nmask), n_sc, p(off), p(rows)))
+        return rows
+
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),

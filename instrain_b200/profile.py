@@ -18,7 +18,7 @@ import time
 import numpy as np
 import pandas as pd
 
-from . import tables
+from . import summary, tables
 from .engine import Engine
 from .packed import encode_packed
 from .packer import BamPacker
@@ -51,8 +51,9 @@ class ProfileResult:
     def __init__(self):
         self.scaffold_list = []
         self.scaffolds = {}
-        self.raw_snp_table = self.raw_linkage_table = None
+        self.raw_snp_table = self.raw_linkage_table = self.cumulative_scaffold_table = None
         self.timing = {}
+        self.failures = []
 
     def get(self, name):
         return getattr(self, name)
@@ -82,11 +83,23 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         engine = Engine(device, model_file=kwargs.get("model_file"), fdr=fdr)
     res = ProfileResult()
     t0 = time.time()
-    snp_tabs, ld_tabs = [], []
+    snp_tabs, ld_tabs, sum_tabs = [], [], []
 
     def flush(batch):
+        """Profile one batch; a failing batch is logged in the reference's format and skipped, the run continues
+        (split_profile_wrapper_groups, profile_utilities.py:92-112)."""
         if not batch["names"]:
             return
+        try:
+            _flush(batch)
+        except Exception as e:                                            # noqa: BLE001 - mirror of the reference's catch-all
+            t = time.strftime("%m-%d %H:%M")
+            for name in batch["names"]:
+                msg = "\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(name, t, 0)
+                logging.error(msg + str(e))
+                res.failures.append(name)
+
+    def _flush(batch):
         cat = np.concatenate
         ev = dict(ref_pos=cat(batch["ref_pos"]), base=cat(batch["base"]), qual=cat(batch["qual"]),
                   read_id=cat(batch["read_id"]), pair_mm=cat(batch["pair_mm"]))
@@ -95,7 +108,11 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         # host -> device in the packed transfer format (~1 B/event); kernel K0 expands it to the event columns in HBM
         pk = encode_packed(ev, 0, len(ref_codes), 30)
         out = engine.profile_batch(ev, ref_codes, np.array(batch["splits"], np.int32), min_cov=min_cov, min_freq=min_freq,
-                                   min_snp=min_snp, want=("covT", "clonT", "snv", "ld"), packed=pk)
+                                   min_snp=min_snp, want=("covT", "clonT", "nmask", "snv", "ld"), packed=pk)
+        # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
+        bounds = np.append(offs, len(ref_codes)).astype(np.int32)
+        k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
+        sum_tabs.append(summary.summary_table(k4, out["snv"], batch["names"], offs, out["M"]))
         seqs = {n: s2s[n] for n in batch["names"]}
         snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs))
         ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
@@ -119,6 +136,13 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             if name not in sR2M or name not in s2s:
                 bp.pack_scaffold(tid, {})                                  # consume and drop
                 continue
+            if name == "FailureScaffoldHeaderTesting" and kwargs.get("debug", False):
+                # the reference's fault-injection hook (profile_utilities.py:137-139, test_profile_17): the scaffold fails,
+                # the failure is logged, the run survives
+                bp.pack_scaffold(tid, {})
+                logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(name, time.strftime("%m-%d %H:%M"), 1))
+                res.failures.append(name)
+                continue
             L = len(s2s[name])
             if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
                 flush(batch)
@@ -136,6 +160,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     flush(batch)
     res.raw_snp_table = pd.concat(snp_tabs, ignore_index=True) if snp_tabs else pd.DataFrame(columns=tables.SNV_COLUMNS)
     res.raw_linkage_table = pd.concat(ld_tabs, ignore_index=True) if ld_tabs else pd.DataFrame(columns=tables.LD_COLUMNS)
+    res.cumulative_scaffold_table = (pd.concat(sum_tabs, ignore_index=True) if sum_tabs
+                                     else pd.DataFrame(columns=summary.COLUMNS))
     for name, sp in res.scaffolds.items():
         sp.raw_snp_table = res.raw_snp_table[res.raw_snp_table["scaffold"] == name]
         sp.raw_linkage_table = res.raw_linkage_table[res.raw_linkage_table["scaffold"] == name]
@@ -163,6 +189,8 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     Sprofile.store("scaffold_list", res.scaffold_list, "list", "1d list of scaffolds, in same order as counts_table")
     Sprofile.store("raw_linkage_table", res.raw_linkage_table, "pandas", "Contains raw linkage information")
     Sprofile.store("raw_snp_table", res.raw_snp_table, "pandas", "Contains raw SNP information on a mm level")
+    Sprofile.store("cumulative_scaffold_table", res.cumulative_scaffold_table, "pandas",
+                   "Cumulative coverage on mm level. Formerly scaffoldTable.csv")
     Sprofile.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
     Sprofile.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
     return Sprofile

@@ -272,3 +272,48 @@ def test_packed_transfer_format_parity(eng, null_lut, case):
     assert np.array_equal(got["covT"], exp["covT"]) and np.array_equal(got["site_flags"], exp["site_flags"])
     assert_snv_equal(got["snv"], exp["snv"])
     assert_ld_equal(got["ld"], exp["ld"], tol=1e-9)
+
+
+# ---- K4: merge-stage summary -------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_scaffold_summary_matches_golden_cumulative_scaffold_table(eng, null_lut, which):
+    """isb_scaffold_summary + instrain_b200.summary vs the reference's stored cumulative_scaffold_table (non-random
+    columns; 1e-9) and vs the oracle's numpy restatement."""
+    from instrain_b200 import summary as psum
+    from oracle import summary as osum
+    batch, exp = load_batch(which)
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], want=("covT", "clonT", "nmask", "snv"),
+                            skip_linkage=True)
+    bounds = np.append(batch["scaffold_off"], len(batch["ref_codes"])).astype(np.int32)
+    rows = eng.scaffold_summary(got["covT"], got["clonT"], got["nmask"], bounds)
+    names = list(batch["scaffold_names"])
+    tab = psum.summary_table(rows, got["snv"], names, batch["scaffold_off"], got["M"])
+    assert np.array_equal(tab["scaffold"].map({n: i for i, n in enumerate(names)}).values, exp["sum_scaffold"])
+    cols = list(exp["sum_columns"])
+    assert np.allclose(tab[cols].values.astype(float), exp["sum_values"], rtol=0, atol=1e-9, equal_nan=True)
+    # raw reductions are exact integers: compare with numpy on the same arrays
+    M = got["M"]
+    r = rows.reshape(len(names), M)
+    s = 7
+    lo, hi = int(bounds[s]), int(bounds[s + 1])
+    cum = np.cumsum(got["covT"][lo:hi].astype(np.int64), axis=1)
+    assert np.array_equal(r[s]["sum_cov"], cum.sum(0)) and np.array_equal(r[s]["sum_cov2"].astype(np.int64), (cum * cum).sum(0))
+    assert np.array_equal(r[s]["nonzero"], (cum > 0).sum(0))
+
+
+def test_scaffold_summary_synthetic(eng, null_lut):
+    from instrain_b200 import summary as psum
+    from oracle import summary as osum
+    batch = synth.make_batch(7001, 45, 0.02, 5, n_scaffolds=3)          # odd length: single middle element
+    exp = oracle_all(batch, null_lut, do_linkage=False)
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], want=("covT", "clonT", "nmask", "snv"), skip_linkage=True)
+    bounds = np.array([0, 7001, 14002, 21003], np.int32)
+    rows = eng.scaffold_summary(got["covT"], got["clonT"], got["nmask"], bounds)
+    tab = psum.summary_table(rows, got["snv"], ["a", "b", "c"], bounds[:-1], got["M"])
+    ref = []
+    for i in range(3):
+        lo, hi = int(bounds[i]), int(bounds[i + 1])
+        sn = exp["snv"][(exp["snv"]["pos"] >= lo) & (exp["snv"]["pos"] < hi)]
+        for r in osum.scaffold_summary(exp["covT"][lo:hi], exp["clonT"][lo:hi], exp["nmask"][lo:hi], sn, lo):
+            ref.append([float(r[c]) for c in osum.COLUMNS])
+    assert np.allclose(tab[osum.COLUMNS].values.astype(float), np.array(ref), rtol=0, atol=1e-9, equal_nan=True)

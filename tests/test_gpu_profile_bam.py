@@ -46,7 +46,7 @@ def test_profile_bam_matches_reference_goldens():
     assert len(a) == len(b) and len(a) > 1000
     for c in ["scaffold", "position", "mm", "A", "C", "T", "G", "con_base", "var_base", "allele_count", "class", "cryptic"]:
         assert (a[c].values == b[c].values).all(), c
-    assert (a["position_coverage"] == a[["A", "C", "T", "G"]].sum(1)).all()
+    assert (a["position_coverage"] == a[["A", "C", "T", "G"]].sum(axis=1)).all()
     for s in seqs:                                             # ref_base column comes from the FASTA
         m = a["scaffold"] == s
         assert all(seqs[s][p] == r for p, r in zip(a["position"][m], a["ref_base"][m]))
