@@ -324,11 +324,45 @@ def main():
 
         dt_col = time_call(lib.isb_profile_batch, hbatch)
         dt = time_call(lib.isb_profile_batch_packed, pbatch)
+
+        # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
+        # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
+        dt_pipe = None
+        try:
+            eng2 = Engine(local_rank, lut, dflt)
+            o2 = {k: torch.empty_like(v).pin_memory() for k, v in o.items()}
+            hres2 = _cabi.IsbResult(None, None, p(o2["covT"]), p(o2["clonT"]), p(o2["flags"]), p(o2["snv"]),
+                                    o2["snv"].numel() // 32, p(o2["ld"]), o2["ld"].numel() // 48, 0, 0, 0, 0)
+            n_it = 4
+            errs = []
+
+            def worker(c, r):
+                for _ in range(n_it):
+                    if lib.isb_profile_batch_packed(c, C.byref(pbatch), C.byref(prm), C.byref(r)) != 0:
+                        errs.append(lib.isb_last_error(c).decode())
+
+            for rep in range(2):                         # first repetition warms the second context's scratch buffers
+                torch.cuda.synchronize()
+                t_a = time.time()
+                ths = [threading.Thread(target=worker, args=(ctx, hres)), threading.Thread(target=worker, args=(eng2.ctx, hres2))]
+                [t.start() for t in ths]
+                [t.join() for t in ths]
+                torch.cuda.synchronize()
+                dt_pipe = (time.time() - t_a) / (2 * n_it)
+            if errs:
+                raise RuntimeError(errs[0])
+            eng2.close()
+        except Exception as ex:                          # noqa: BLE001 - the pipelined figure is optional
+            dt_pipe = None
+            print("e2e pipelined leg skipped: %r" % (ex,), file=sys.stderr)
         common = len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
         h2d = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
-        e2e = {"value": Ls / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt * 1e3, "api": "isb_profile_batch_packed (packed transfer format, K0 expands on the device)",
+        best = min(dt, dt_pipe) if dt_pipe else dt
+        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": best * 1e3, "api": "isb_profile_batch_packed (packed transfer format, K0 expands on the device)",
+               "single_context": {"value": Ls / dt, "ms_per_step": dt * 1e3},
+               "two_contexts_pipelined": ({"value": Ls / dt_pipe, "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),
                "slice": "%d of the %d scaffolds per step, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, args.scaffolds),
                "columnar_host_buffers": {"value": Ls / dt_col, "ms_per_step": dt_col * 1e3,
                                          "h2d_bytes_per_step": int(len(hb["ref_pos"]) * 10 + common)}}

@@ -17,10 +17,18 @@ def encode_packed(ev, start, L, min_qual=30):
     if n and (pos.min() < 0 or pos.max() >= L):
         raise ValueError("events outside [start, start+L)")
     rid = np.asarray(ev["read_id"], dtype=np.int64)
-    order = np.lexsort((rid, pos))                               # by position, then pair id; stable
-    pos, rid = pos[order], rid[order]
-    base = np.minimum(np.asarray(ev["base"])[order], 4).astype(np.uint8)
-    ok = (np.asarray(ev["qual"])[order] >= min_qual)
+    base, qual = np.asarray(ev["base"]), np.asarray(ev["qual"])
+    if n > 1:
+        d_pos, d_rid = np.diff(pos), np.diff(rid)
+        in_order = bool(np.all((d_pos > 0) | ((d_pos == 0) & (d_rid >= 0))))
+        del d_pos, d_rid
+    else:
+        in_order = True
+    if not in_order:                                             # by position, then pair id; stable
+        order = np.lexsort((rid, pos))
+        pos, rid, base, qual = pos[order], rid[order], base[order], qual[order]
+    base = np.minimum(base, 4).astype(np.uint8)
+    ok = qual >= min_qual
     pos_off = np.searchsorted(pos, np.arange(L + 1, dtype=np.int64)).astype(np.int64)
     first = np.zeros(n, dtype=bool)
     nonempty = pos_off[:-1] < pos_off[1:]
