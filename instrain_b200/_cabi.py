@@ -15,6 +15,7 @@ ISB_ERR_CUDA, ISB_ERR_ARG, ISB_ERR_CAPACITY, ISB_ERR_ORDER, ISB_ERR_UNSUPPORTED 
 ISB_K1_ANY_ORDER = 0x1
 ISB_SKIP_LINKAGE = 0x2
 ISB_NO_SYNC = 0x4
+ISB_PIPELINE = 0x8
 ISB_SITE_ANYSNP = 0x10
 ISB_MAX_MM = 64
 

@@ -3,6 +3,8 @@
 #include "isb_common.cuh"
 #include <stdlib.h>
 
+#include <vector>
+
 static char g_create_err[512] = "";
 
 int isb_ensure(isb_ctx *ctx, int slot, size_t bytes)
@@ -145,6 +147,11 @@ isb_ctx *isb_create(int device, const int32_t *null_lut, int n_lut, int lut_defa
     ctx->sm_count = prop.multiProcessorCount;
     CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CREATE_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CREATE_CHECK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CREATE_CHECK(cudaMalloc(&ctx->d_lut, sizeof(int32_t) * (size_t)n_lut));
     CREATE_CHECK(cudaMemcpy(ctx->d_lut, null_lut, sizeof(int32_t) * (size_t)n_lut, cudaMemcpyHostToDevice));
     ctx->n_lut = n_lut;
@@ -175,6 +182,7 @@ void isb_destroy(isb_ctx *ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (int i = 0; i < ctx->n_tev; ++i) { cudaEventDestroy(ctx->tev[i].a); cudaEventDestroy(ctx->tev[i].b); }
     free(ctx->tev);
     delete ctx;
@@ -359,6 +367,7 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
 {
     int rc;
     const bool do_ld = !(prm->flags & ISB_SKIP_LINKAGE);
+    int64_t pipe_sites = -1, pipe_pairs = -1;
     int32_t *d_counts, *d_covT; uint64_t *d_nmask; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_snv; isb_ld_row *d_ld;
     if ((rc = stage_out(ctx, SL_COUNTS, out->counts, (size_t)L * M * 4, &d_counts))) return rc;
     if ((rc = stage_out(ctx, SL_NMASK, out->nmask, (size_t)L, &d_nmask))) return rc;
@@ -369,20 +378,94 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
     if ((rc = stage_out(ctx, SL_SNV, out->snv, (size_t)(snv_cap > 0 ? snv_cap : 1), &d_snv))) return rc;
     if ((rc = stage_out(ctx, SL_LD, out->ld, (size_t)(ld_cap > 0 ? ld_cap : 1), &d_ld))) return rc;
 
-    int ts = isb_time_begin(ctx, 0);
-    if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
-                            (unsigned long long *)d_nmask))) return rc;
-    isb_time_end(ctx, ts);
-    ts = isb_time_begin(ctx, 1);
-    if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
-                            prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
-    isb_time_end(ctx, ts);
-    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    ts = do_ld ? isb_time_begin(ctx, 2) : -1;
-    if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
-                                     d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
-                                     prm->min_snp, d_ld, ld_cap))) return rc;
-    isb_time_end(ctx, ts);
+    // ---- chunk pipeline ------------------------------------------------------------------------------------------
+    // (opt-in, ISB_PIPELINE) K1 is HBM-bound, K2 / K3 are latency-bound kernels with little DRAM traffic.  Large batches can be cut at
+    // split boundaries into a few chunks: the K1 launches run back to back on the main stream, and K2 + K3 of chunk c
+    // run on a second (higher-priority) stream as soon as K1(c) is done, i.e. underneath K1(c+1).  Results are
+    // identical (linkage never crosses a split; rows are appended through the same atomic counters).
+    std::vector<int32_t> hs;
+    std::vector<int> cut;                                    // chunk c = splits [cut[c], cut[c+1])
+    const bool want_pipe = (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
+    if (want_pipe) {
+        hs.resize((size_t)n_splits * 2);
+        ISB_CUDA(cudaMemcpyAsync(hs.data(), d_splits, sizeof(int32_t) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        ISB_CUDA(cudaStreamSynchronize(ctx->stream));
+        bool tiling = hs[0] == start && hs[hs.size() - 1] == start + L - 1;
+        for (int i = 0; tiling && i + 1 < n_splits; ++i) tiling = hs[2 * (i + 1)] == hs[2 * i + 1] + 1;
+        if (tiling) {                                        // splits tile [start, start+L): cut into <= 8 chunks
+            const int n_chunks = 8;
+            cut.push_back(0);
+            for (int c = 1; c < n_chunks; ++c) {
+                const int64_t target = start + (int64_t)L * c / n_chunks;
+                int i = cut.back();
+                while (i < n_splits && hs[2 * i] < target) ++i;
+                if (i > cut.back() && i < n_splits) cut.push_back(i);
+            }
+            cut.push_back(n_splits);
+        }
+    }
+    if (cut.size() >= 3) {
+        const int n_chunks = (int)cut.size() - 1;
+        cudaStream_t main_st = ctx->stream, aux = ctx->aux_stream;
+        std::vector<cudaEvent_t> ev(n_chunks + 1);
+        for (auto &e : ev) ISB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), main_st));
+        int ts = isb_time_begin(ctx, 0);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int32_t c_lo = hs[2 * cut[c]], c_len = hs[2 * (cut[c + 1] - 1) + 1] - c_lo + 1;
+            const size_t off = (size_t)(c_lo - start);
+            if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, c_lo, c_len, M, prm->min_qual, 0,
+                                    d_counts + off * M * 4, (unsigned long long *)d_nmask + off))) return rc;
+            ISB_CUDA(cudaEventRecord(ev[c], main_st));
+        }
+        isb_time_end(ctx, ts);
+        ctx->keep_counters = 1;
+        ctx->stream = aux;
+        int64_t acc_sites = 0, acc_pairs = 0;
+        rc = ISB_OK;
+        for (int c = 0; c < n_chunks && rc == ISB_OK; ++c) {
+            const int32_t c_lo = hs[2 * cut[c]], c_len = hs[2 * (cut[c + 1] - 1) + 1] - c_lo + 1;
+            const size_t off = (size_t)(c_lo - start);
+            cudaStreamWaitEvent(aux, ev[c], 0);
+            int t2 = isb_time_begin(ctx, 1);
+            rc = isb_k2_launch(ctx, c_len, M, d_counts + off * M * 4, (const unsigned long long *)d_nmask + off, d_ref + off,
+                               c_lo, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off,
+                               d_snv, snv_cap);
+            isb_time_end(ctx, t2);
+            if (rc == ISB_OK && do_ld) {
+                int t3 = isb_time_begin(ctx, 2);
+                rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, c_lo, c_len, M, prm->min_qual,
+                                   d_counts + off * M * 4, (const unsigned long long *)d_nmask + off, d_flags + off,
+                                   cut[c + 1] - cut[c], d_splits + 2 * cut[c], prm->min_snp, d_ld, ld_cap);
+                isb_time_end(ctx, t3);
+                acc_sites += (int64_t)ctx->h_counters[2];
+                acc_pairs += (int64_t)ctx->h_counters[3];
+            }
+        }
+        cudaEventRecord(ev[n_chunks], aux);
+        ctx->stream = main_st;
+        ctx->keep_counters = 0;
+        cudaStreamWaitEvent(main_st, ev[n_chunks], 0);
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (rc) return rc;
+        pipe_sites = acc_sites;
+        pipe_pairs = acc_pairs;
+    } else {
+        int ts = isb_time_begin(ctx, 0);
+        if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
+                                (unsigned long long *)d_nmask))) return rc;
+        isb_time_end(ctx, ts);
+        ts = isb_time_begin(ctx, 1);
+        if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
+                                prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
+        isb_time_end(ctx, ts);
+        ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        ts = do_ld ? isb_time_begin(ctx, 2) : -1;
+        if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
+                                         d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
+                                         prm->min_snp, d_ld, ld_cap))) return rc;
+        isb_time_end(ctx, ts);
+    }
     if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
     if ((rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
     if ((rc = finish_out(ctx, out->covT, d_covT, (size_t)L * M))) return rc;
@@ -395,8 +478,8 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
     if ((rc = fetch_status(ctx))) return rc;
     out->n_snv = (int64_t)ctx->h_counters[0];
     out->n_ld = (int64_t)ctx->h_counters[1];
-    out->n_sites = (int64_t)ctx->h_counters[2];
-    out->n_site_pairs = (int64_t)ctx->h_counters[3];
+    out->n_sites = pipe_sites >= 0 ? pipe_sites : (int64_t)ctx->h_counters[2];
+    out->n_site_pairs = pipe_pairs >= 0 ? pipe_pairs : (int64_t)ctx->h_counters[3];
     if ((rc = finish_out(ctx, out->snv, d_snv, (size_t)(out->n_snv < snv_cap ? out->n_snv : snv_cap)))) return rc;
     if ((rc = finish_out(ctx, out->ld, d_ld, (size_t)(out->n_ld < ld_cap ? out->n_ld : ld_cap)))) return rc;
     ISB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -42,6 +42,8 @@ struct isb_ctx {
     int lut_default;
     int32_t *d_thr2;                  // K2: max(null-model threshold, min count passing min_freq) per coverage
     double thr2_min_freq;
+    cudaStream_t aux_stream;          // chunk pipeline: K2 / K3 of chunk c run here while K1 of chunk c+1 runs on `stream`
+    int keep_counters;                // set inside the chunk pipeline: K2 / K3 append to the row counters instead of resetting
     unsigned long long *d_counters;   // [0]=n_snv rows [1]=n_ld rows [2]=n_sites [3]=n_site_pairs [4]=total row words
     unsigned int *d_err;
     unsigned long long *h_counters;   // pinned mirror

@@ -174,7 +174,7 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
                   uint8_t *site_flags, isb_snv_row *rows, int64_t cap)
 {
     cudaStream_t st = ctx->stream;
-    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 0, 0, sizeof(unsigned long long), st));
+    if (!ctx->keep_counters) ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 0, 0, sizeof(unsigned long long), st));
     if (L <= 0) return ISB_OK;
     if (!ctx->d_thr2 || ctx->thr2_min_freq != min_freq) {             // (re)build the merged integer threshold table
         if (!ctx->d_thr2) ISB_CUDA(cudaMalloc(&ctx->d_thr2, sizeof(int32_t) * (size_t)ctx->n_lut));

@@ -453,7 +453,10 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
 {
     cudaStream_t st = ctx->stream;
     int rc;
-    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), st));
+    // [1] = linkage rows (appended across the chunks of a pipelined batch), [2] sites, [3] linked pairs, [4] row words
+    if (ctx->keep_counters) ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
+    else ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), st));
+    ctx->h_counters[2] = ctx->h_counters[3] = 0;
     if (L <= 0 || n <= 0) return ISB_OK;
 
     // 1. ordered list of linkage-eligible sites

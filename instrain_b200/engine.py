@@ -143,7 +143,7 @@ class Engine:
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
-                      snv_cap=None, ld_cap=None, packed=None):
+                      snv_cap=None, ld_cap=None, packed=None, pipeline=False):
         """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
 
         `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
@@ -167,8 +167,8 @@ class Engine:
             batch = _cabi.IsbBatch(len(ev["ref_pos"]), p(ev["ref_pos"]), p(ev["base"]), p(ev["qual"]), p(ev["read_id"]),
                                    len(pair_mm), p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M)
             entry = self.lib.isb_profile_batch
-        prm = _cabi.IsbParams(min_cov, min_snp, min_qual, _cabi.ISB_SKIP_LINKAGE if skip_linkage else 0,
-                              float(min_freq))
+        prm = _cabi.IsbParams(min_cov, min_snp, min_qual, (_cabi.ISB_SKIP_LINKAGE if skip_linkage else 0) |
+                              (_cabi.ISB_PIPELINE if pipeline else 0), float(min_freq))
         out = {}
         if "counts" in want:
             out["counts"] = np.empty((L, M, 4), dtype=np.int32)

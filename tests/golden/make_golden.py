@@ -113,7 +113,43 @@ def make_subset_bam(which="G1", n_scaffolds=6):
     print(which, "subset BAM:", len(new_refs), "scaffolds", len(reads), "reads")
 
 
+def make_small_scaffold():
+    """Tiny-scaffold case (the reference's test_profile_18 input: SmallScaffold.fa + its BAM, one 126 bp scaffold).
+    No stored answer exists for it, so the expected tables come from the reference's OWN functions
+    (oracle/ref_harness.py) on the emulated pileup; R2M = every name seen exactly twice with mm = summed NM
+    (what get_paired_reads + paired_only yield before the ANI filter, inStrain/filter_reads.py:885-956,503-505)."""
+    import json
+    import shutil
+    src_bam = os.path.join(TD_DIR, "SmallScaffold.fa.sorted.bam")
+    refs, reads = bamio.read_bam(src_bam)
+    seqs = bamio.read_fasta(os.path.join(TD_DIR, "SmallScaffold.fa"))
+    name = refs[0][0]
+    cnt, nm = {}, {}
+    for r in reads:
+        if r.tid == 0 and not (r.flag & 4):
+            cnt[r.name] = cnt.get(r.name, 0) + 1
+            nm[r.name] = nm.get(r.name, 0) + int(r.nm or 0)
+    r2m = {k: int(nm[k]) for k, v in cnt.items() if v == 2 and nm[k] < 12}
+    ev = pileup_emul.scaffold_events([r for r in reads if r.tid == 0], r2m)
+    model = ref_harness.null_model(1e-6)
+    out = ref_harness.run_split(ev, seqs[name], 0, len(seqs[name]) - 1, r2m, model, scaffold=name)
+    shutil.copyfile(src_bam, os.path.join(HERE, "small_scaffold.bam"))
+    snp = pd.DataFrame(out["snp"])
+    ld = pd.DataFrame(out["ld"])
+    with open(os.path.join(HERE, "small_scaffold.json"), "w") as fh:
+        json.dump(dict(scaffold=name, seq=seqs[name], r2m=r2m,
+                       snp=snp.drop(columns=["scaffold"]).to_dict("list") if len(snp) else {},
+                       ld=ld[["position_A", "position_B", "mm", "countAB", "countAb", "countaB", "countab", "r2", "d_prime",
+                              "allele_A", "allele_a", "allele_B", "allele_b"]].to_dict("list") if len(ld) else {},
+                       covT={str(k): np.asarray(v).tolist() for k, v in out["covT"].items()}), fh)
+    print("small scaffold:", name, len(seqs[name]), "bp,", len(r2m), "pairs,", len(snp), "snv rows,", len(ld), "ld rows")
+
+
+TD_DIR = os.path.join(ref_harness.REFERENCE_ROOT, "test", "test_data")
+
+
 if __name__ == "__main__":
+    make_small_scaffold()
     make_subset_bam("G1")
     model = ref_harness.null_model(1e-6)
     lut, dflt = restate.lut_from_model(model)

@@ -317,3 +317,25 @@ def test_scaffold_summary_synthetic(eng, null_lut):
         for r in osum.scaffold_summary(exp["covT"][lo:hi], exp["clonT"][lo:hi], exp["nmask"][lo:hi], sn, lo):
             ref.append([float(r[c]) for c in osum.COLUMNS])
     assert np.allclose(tab[osum.COLUMNS].values.astype(float), np.array(ref), rtol=0, atol=1e-9, equal_nan=True)
+
+
+# ---- chunk pipeline (K1 of chunk c+1 overlapping K2/K3 of chunk c) -----------------------------------------------------
+@pytest.mark.parametrize("skip_mm", [True, False])
+def test_chunk_pipeline_equals_single_pass(eng, skip_mm):
+    """With ISB_PIPELINE, batches >= 2^22 positions are cut at split boundaries and pipelined over two streams; the tables
+    must equal the single-pass ones exactly."""
+    from instrain_b200 import synth as dsynth
+    d = dsynth.generate(0, 300000, 15, 12, 0.01, 99, skip_mm=skip_mm)            # 4.5e6 positions, ~5e7 events
+    ev = dict(ref_pos=d["ref_pos"], base=d["base"], qual=d["qual"], read_id=d["read_id"], pair_mm=d["pair_mm"].cpu().numpy())
+    ref, spl = d["ref_codes"].cpu().numpy(), d["splits"].cpu().numpy()
+    M = int(ev["pair_mm"].max()) + 1 if len(ev["pair_mm"]) else 1
+    want = ("counts", "covT", "clonT", "site_flags", "snv", "ld")
+    a = eng.profile_batch(ev, ref, spl, M=M, want=want, min_cov=3, min_snp=3)
+    b = eng.profile_batch(ev, ref, spl, M=M, want=want, min_cov=3, min_snp=3, pipeline=True)
+    assert len(a["snv"]) > 1000 and len(a["ld"]) > 100
+    for k in ("counts", "covT", "site_flags"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
+    assert_snv_equal(a["snv"], b["snv"])
+    assert_ld_equal(a["ld"], b["ld"], tol=0)
+    assert (a["n_sites"], a["n_site_pairs"]) == (b["n_sites"], b["n_site_pairs"])

@@ -66,3 +66,36 @@ def test_profile_bam_matches_reference_goldens():
             tot = sum(int(sp.covT[m].get(pos, 0)) for m in sp.covT if m <= mm)
             assert tot == cov
         break
+
+
+def test_profile_bam_tiny_scaffold_vs_reference_functions():
+    """The reference's test_profile_18 input (one 126 bp scaffold).  Expected tables were produced by the reference's OWN
+    process_bam_sites / calculate_ld (oracle/ref_harness.py) on the emulated pileup -- tests/golden/make_golden.py."""
+    from instrain_b200.profile import profile_bam
+    fx = json.load(open(os.path.join(GOLDEN, "small_scaffold.json")))
+    name = fx["scaffold"]
+    res = profile_bam(os.path.join(GOLDEN, "small_scaffold.bam"), None, {name: fx["r2m"]}, "unused.IS",
+                      s2s={name: fx["seq"]}, min_cov=5, min_freq=0.05, min_snp=20)
+    assert res.scaffold_list == [name] and not res.failures
+    exp = pd.DataFrame(fx["snp"]).sort_values(["position", "mm"]).reset_index(drop=True)
+    got = res.raw_snp_table.sort_values(["position", "mm"]).reset_index(drop=True)
+    assert len(got) == len(exp) == 48
+    for c in ["position", "mm", "ref_base", "A", "C", "T", "G", "con_base", "var_base", "allele_count", "class", "cryptic"]:
+        assert (got[c].values == exp[c].values).all(), c
+    key = ["position_A", "position_B", "mm"]
+    exp = pd.DataFrame(fx["ld"]).sort_values(key).reset_index(drop=True)
+    got = res.raw_linkage_table.sort_values(key).reset_index(drop=True)
+    assert len(got) == len(exp) == 39
+    for c in key + ["countAB", "countAb", "countaB", "countab", "allele_A", "allele_a", "allele_B", "allele_b"]:
+        assert (got[c].values == exp[c].values).all(), c
+    for c in ("r2", "d_prime"):
+        assert np.allclose(got[c].values.astype(float), exp[c].values.astype(float), rtol=0, atol=1e-6, equal_nan=True), c
+    sp = res.scaffolds[name]
+    for mm, dense in fx["covT"].items():                       # exact-mm coverage arrays of the reference (pre-shrink)
+        dense = np.asarray(dense)
+        s = sp.covT.get(int(mm))
+        mine = np.zeros(len(dense), dtype=np.int64)
+        if s is not None:
+            mine[s.index.values] = s.values
+        assert np.array_equal(mine, dense), mm
+    assert len(res.cumulative_scaffold_table) == len([m for m in fx["covT"] if np.asarray(fx["covT"][m]).sum() > 0])
