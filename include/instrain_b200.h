@@ -255,6 +255,23 @@ int64_t isb_events_reads_packed(void *events);
 void isb_events_copy(void *events, int32_t *ref_pos, uint8_t *base, uint8_t *qual, int32_t *read_id, uint8_t *pair_mm);
 void isb_events_free(void *events);
 
+/* ---- host read filter (C++, no GPU): BAM -> sR2M --------------------------------------------------------------------- */
+/* Default configuration of the reference's read filter: get_paired_reads (filter_reads.py:885-956),
+ * paired_read_filter with pairing_filter='paired_only' (:471-532), filter_scaff2pair2info / evaluate_pair (:201-300,
+ * :387-426).  isb_filter_open makes one pass over the BAM; isb_filter_apply applies the thresholds (reference defaults:
+ * min_read_ani 0.95, min_mapq -1, max_insert_relative 3, min_insert 50); the kept pairs of a scaffold (names in file
+ * order + summed NM) are what isb_pack_scaffold takes as R2M.  tally[6] = pass_pairing_filter, pass_min_read_ani,
+ * pass_max_insert, pass_min_insert, pass_min_mapq, filtered_pairs (the mapping_info columns). */
+void *isb_filter_open(const char *bam_path);
+int64_t isb_filter_apply(void *filter, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert);
+int isb_filter_n_refs(void *filter);
+double isb_filter_max_insert(void *filter);
+void isb_filter_tally(void *filter, int tid, int64_t tally[6]);
+int64_t isb_filter_n_pairs(void *filter, int tid);
+int64_t isb_filter_names_bytes(void *filter, int tid);
+void isb_filter_copy(void *filter, int tid, char *names_blob, int64_t *name_off, int32_t *mm);
+void isb_filter_free(void *filter);
+
 #ifdef __cplusplus
 }
 #endif

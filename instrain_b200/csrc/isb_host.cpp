@@ -15,6 +15,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -397,5 +398,199 @@ void isb_events_copy(void *e, int32_t *ref_pos, uint8_t *base, uint8_t *qual, in
     if (pair_mm) memcpy(pair_mm, ev->pair_mm.data(), ev->pair_mm.size());
 }
 void isb_events_free(void *e) { delete (Events *)e; }
+
+}  // extern "C"
+
+// ---- read filter: BAM -> sR2M (the hot path's input) ---------------------------------------------------------------
+// C++ restatement of the reference's default read filter:
+//   get_paired_reads        inStrain/filter_reads.py:885-956   per scaffold, name -> (NM sum, insert, max mapq, length, #reads)
+//   paired_read_filter      inStrain/filter_reads.py:471-532   pairing_filter = 'paired_only' (exactly two reads of the name on
+//                                                              the scaffold), no priority reads
+//   filter_scaff2pair2info  inStrain/filter_reads.py:201-300   max_insert = max_insert_relative * median insert over ALL pairs
+//   evaluate_pair           inStrain/filter_reads.py:387-426   1 - nm/length > min_read_ani, mapq > min_mapq,
+//                                                              min_insert < insert < max_insert
+// One sequential pass over the BAM (it shares the BGZF reader with the packer, so a second pysam pass disappears).
+namespace {
+
+struct PairInfo {
+    int64_t nm = 0, insert = -1, mapq = 0, length = 0;
+    int32_t reads = 0;
+    int32_t first = 0, last = 0;       // aligned span of the first read
+    uint8_t keep = 0;
+};
+
+struct ScaffoldPairs {
+    std::vector<std::string> names;                  // insertion (file) order
+    std::vector<PairInfo> info;
+    std::unordered_map<std::string, int32_t> index;
+    int64_t tally[6] = {0, 0, 0, 0, 0, 0};           // pass_pairing_filter, pass_min_read_ani, pass_max_insert, pass_min_insert, pass_min_mapq, filtered_pairs
+};
+
+struct Filter {
+    std::vector<std::string> ref_names;
+    std::vector<ScaffoldPairs> sc;
+    double max_insert = 0.0;
+    char err[256] = "";
+};
+
+int nm_tag(const uint8_t *p, const uint8_t *end)
+{
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        int64_t val = 0;
+        size_t size = 0;
+        switch (ty) {
+            case 'A': size = 1; break;
+            case 'c': size = 1; val = (int8_t)p[0]; break;
+            case 'C': size = 1; val = p[0]; break;
+            case 's': size = 2; { int16_t v; memcpy(&v, p, 2); val = v; } break;
+            case 'S': size = 2; { uint16_t v; memcpy(&v, p, 2); val = v; } break;
+            case 'i': size = 4; { int32_t v; memcpy(&v, p, 4); val = v; } break;
+            case 'I': size = 4; { uint32_t v; memcpy(&v, p, 4); val = v; } break;
+            case 'f': size = 4; break;
+            case 'Z': case 'H': { const uint8_t *q = p; while (q < end && *q) ++q; size = (size_t)(q - p) + 1; } break;
+            case 'B': {
+                const char sub = (char)p[0];
+                int32_t n; memcpy(&n, p + 1, 4);
+                const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                size = 5 + (size_t)n * w;
+            } break;
+            default: return 0;
+        }
+        if (t0 == 'N' && t1 == 'M') return (int)val;
+        p += size;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Pass over the whole BAM; returns a filter handle (NULL on failure).
+void *isb_filter_open(const char *bam_path)
+{
+    Bam *b = (Bam *)isb_bam_open(bam_path);
+    if (!b) return nullptr;
+    Filter *f = new Filter();
+    f->ref_names = b->ref_names;
+    f->sc.resize(b->ref_names.size());
+    for (;;) {
+        const int t = isb_bam_peek_tid(b);
+        if (t < 0) break;
+        const uint8_t *p = b->pending.data();
+        const uint8_t *end = p + b->pending.size();
+        b->has_pending = false;
+        int32_t core[8];
+        memcpy(core, p, 32);
+        const int l_read_name = (uint32_t)core[2] & 0xff;
+        const int mapq = ((uint32_t)core[2] >> 8) & 0xff;
+        const int n_cigar = (uint32_t)core[3] & 0xffff, flag = (uint32_t)core[3] >> 16;
+        const int l_seq = core[4];
+        if (flag & 0x4 || n_cigar == 0) continue;
+        const uint8_t *q = p + 32 + l_read_name;
+        int64_t pos = core[1], first = -1, last = -1, qlen = 0;
+        for (int c = 0; c < n_cigar; ++c) {
+            uint32_t cg; memcpy(&cg, q + 4 * c, 4);
+            const int op = cg & 0xf;
+            const int64_t len = cg >> 4;
+            if (is_match(op)) { if (first < 0) first = pos; last = pos + len - 1; pos += len; qlen += len; }
+            else if (op == OP_D || op == OP_N) pos += len;
+            else if (op == OP_I || op == OP_S) qlen += len;
+        }
+        if (first < 0) continue;                                      // get_reference_positions() == []
+        const uint8_t *tags = q + 4 * n_cigar + ((l_seq + 1) >> 1) + l_seq;
+        const int nm = nm_tag(tags, end);
+        ScaffoldPairs &sp = f->sc[t];
+        std::string name((const char *)p + 32, l_read_name > 0 ? l_read_name - 1 : 0);
+        auto it = sp.index.find(name);
+        if (it == sp.index.end()) {
+            PairInfo pi;
+            pi.nm = nm; pi.insert = -1; pi.mapq = mapq; pi.length = qlen; pi.reads = 1;
+            pi.first = (int32_t)first; pi.last = (int32_t)last;
+            sp.index.emplace(name, (int32_t)sp.info.size());
+            sp.names.push_back(std::move(name));
+            sp.info.push_back(pi);
+        } else {
+            PairInfo &pi = sp.info[it->second];
+            pi.nm += nm;
+            pi.reads += 1;
+            pi.length += qlen;
+            if (mapq > pi.mapq) pi.mapq = mapq;
+            if (pi.reads == 2) pi.insert = last > pi.first ? last - pi.first : (int64_t)pi.last - first;
+            else pi.insert = -1;
+            pi.first = pi.last = 0;
+        }
+    }
+    isb_bam_close(b);
+    return f;
+}
+
+// Apply the thresholds (reference defaults: 0.95, -1, 3, 50).  Returns the number of kept pairs.
+int64_t isb_filter_apply(void *h, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert)
+{
+    Filter *f = (Filter *)h;
+    std::vector<int64_t> ins;
+    for (auto &sp : f->sc)
+        for (auto &pi : sp.info)
+            if (pi.reads == 2) ins.push_back(pi.insert);
+    double median = 0.0;
+    if (!ins.empty()) {                                               // np.median
+        std::vector<int64_t> v = ins;
+        const size_t n = v.size(), k = n / 2;
+        std::nth_element(v.begin(), v.begin() + k, v.end());
+        median = (double)v[k];
+        if (n % 2 == 0) {
+            const int64_t lo = *std::max_element(v.begin(), v.begin() + k);
+            median = ((double)lo + (double)v[k]) / 2.0;
+        }
+    }
+    f->max_insert = median * max_insert_relative;
+    int64_t kept = 0;
+    for (auto &sp : f->sc) {
+        for (int i = 0; i < 6; ++i) sp.tally[i] = 0;
+        for (auto &pi : sp.info) {
+            pi.keep = 0;
+            if (pi.reads != 2) continue;                              // paired_only
+            sp.tally[0]++;
+            const bool f_ani = (1.0 - (double)pi.nm / (double)pi.length) > min_read_ani;
+            const bool f_mapq = pi.mapq > min_mapq;
+            bool f_min = true, f_max = true;
+            if (pi.insert != -1) { f_min = pi.insert > min_insert; f_max = (double)pi.insert < f->max_insert; }
+            sp.tally[1] += f_ani; sp.tally[2] += f_max; sp.tally[3] += f_min; sp.tally[4] += f_mapq;
+            if (f_ani && f_mapq && f_min && f_max) { pi.keep = 1; sp.tally[5]++; ++kept; }
+        }
+    }
+    return kept;
+}
+
+int isb_filter_n_refs(void *h) { return (int)((Filter *)h)->sc.size(); }
+double isb_filter_max_insert(void *h) { return ((Filter *)h)->max_insert; }
+void isb_filter_tally(void *h, int tid, int64_t out[6]) { memcpy(out, ((Filter *)h)->sc[tid].tally, sizeof(int64_t) * 6); }
+int64_t isb_filter_n_pairs(void *h, int tid) { return ((Filter *)h)->sc[tid].tally[5]; }
+int64_t isb_filter_names_bytes(void *h, int tid)
+{
+    const ScaffoldPairs &sp = ((Filter *)h)->sc[tid];
+    int64_t n = 0;
+    for (size_t i = 0; i < sp.info.size(); ++i) if (sp.info[i].keep) n += (int64_t)sp.names[i].size();
+    return n;
+}
+// kept pairs of scaffold tid in file order: concatenated names, offsets [n+1], summed NM
+void isb_filter_copy(void *h, int tid, char *names_blob, int64_t *name_off, int32_t *mm)
+{
+    const ScaffoldPairs &sp = ((Filter *)h)->sc[tid];
+    int64_t off = 0, k = 0;
+    for (size_t i = 0; i < sp.info.size(); ++i) {
+        if (!sp.info[i].keep) continue;
+        name_off[k] = off;
+        memcpy(names_blob + off, sp.names[i].data(), sp.names[i].size());
+        off += (int64_t)sp.names[i].size();
+        mm[k] = (int32_t)sp.info[i].nm;
+        ++k;
+    }
+    name_off[k] = off;
+}
+void isb_filter_free(void *h) { delete (Filter *)h; }
 
 }  // extern "C"

@@ -178,6 +178,16 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     s2s = kwargs.pop("s2s", None)
     if s2s is None:
         raise ValueError("profile_bam needs kwargs['s2s'] (scaffold -> sequence), as ProfileController.run_profile passes it")
+    if sR2M is None:
+        # no Rdic from the caller: run the reference's default read filter ourselves (C++ host filter, one BAM pass)
+        from .packer import BamPacker as _BP
+        from .read_filter import filter_reads
+        with _BP(bam) as bp:
+            names = bp.ref_names
+        sR2M, _, _ = filter_reads(bam, names, **{k: kwargs[k] for k in ("min_read_ani", "min_mapq", "max_insert_relative",
+                                                                       "min_insert") if k in kwargs})
+        if kwargs.get("skip_mm_profiling"):
+            sR2M = {s: set(d) for s, d in sR2M.items()}
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
     try:
         import inStrain.SNVprofile

@@ -74,3 +74,58 @@ def test_packer_matches_emulation_on_reference_bam():
     rdic = json.load(open(os.path.join(td, "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.forRC.IS/raw_data/Rdic.json")))
     n = compare_bam(os.path.join(td, "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.sorted.bam"), rdic)
     assert n == 1876216
+
+
+# ---- read filter: BAM -> sR2M -----------------------------------------------------------------------------
+def _oracle_filter(bam_path):
+    from oracle import read_filter as orf
+    refs, reads = bamio.read_bam(bam_path)
+    by = {}
+    for r in reads:
+        if r.tid >= 0:
+            by.setdefault(refs[r.tid][0], []).append(r)
+    return [n for n, _ in refs], orf.filter_pairs({s: orf.pair2info(rs) for s, rs in by.items()})
+
+
+def test_read_filter_matches_restatement_on_fixture_bam():
+    from instrain_b200 import build
+    build.build()
+    from instrain_b200.read_filter import filter_reads
+    path = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    names, (exp, exp_tal, exp_max) = _oracle_filter(path)
+    got, tal, mx = filter_reads(path, names)
+    assert mx == exp_max
+    assert got == {s: d for s, d in exp.items() if d}
+    for s, t in exp_tal.items():
+        if t["pass_pairing_filter"]:
+            assert tal[s] == t, s
+    # non-default thresholds
+    from oracle import read_filter as orf
+    refs, reads = bamio.read_bam(path)
+    by = {}
+    for r in reads:
+        by.setdefault(refs[r.tid][0], []).append(r)
+    exp3, _, _ = orf.filter_pairs({s: orf.pair2info(rs) for s, rs in by.items()}, 0.98, 20, 2, 100)
+    got3, _, _ = filter_reads(path, names, 0.98, 20, 2, 100)
+    assert got3 == {s: d for s, d in exp3.items() if d}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/test_data"), reason="reference tree not present")
+def test_read_filter_reproduces_reference_rdic():
+    """The reference's stored Rdic.json (sR2M) and mapping_info tallies for the bundled BAM, default thresholds."""
+    import pandas as pd
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.read_filter import filter_reads
+    td = "/root/reference/test/test_data"
+    isd = os.path.join(td, "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.forRC.IS/raw_data")
+    bam = os.path.join(td, "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.sorted.bam")
+    with BamPacker(bam) as bp:
+        names = bp.ref_names
+    got, tal, mx = filter_reads(bam, names)
+    rdic = json.load(open(os.path.join(isd, "Rdic.json")))
+    assert got == rdic and sum(len(v) for v in got.values()) == 7179 and mx == 960.0
+    mi = pd.read_csv(os.path.join(isd, "mapping_info.csv.gz"))
+    mi = mi[mi.scaffold != "all_scaffolds"].set_index("scaffold")
+    for s in mi.index:
+        if s in tal:
+            assert all(int(mi.loc[s, c]) == tal[s][c] for c in tal[s]), s

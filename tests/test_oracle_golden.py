@@ -67,3 +67,26 @@ def test_summary_restatement_reproduces_cumulative_scaffold_table(which, null_lu
     assert list(exp["sum_columns"]) == summary.COLUMNS
     assert np.array_equal(np.array(sidx), exp["sum_scaffold"])
     assert np.allclose(got, exp["sum_values"], rtol=0, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/test_data"), reason="reference tree not present")
+@pytest.mark.parametrize("which,n_pairs", [("G1", 7179), ("G2", 9435)])
+def test_read_filter_restatement_reproduces_rdic(which, n_pairs):
+    """oracle/read_filter.py vs the reference's stored Rdic.json (sR2M) and mapping_info tallies."""
+    import json
+    import pandas as pd
+    from oracle import bamio, read_filter
+    td = "/root/reference/test/test_data/"
+    bam = td + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010%s.sorted.bam" % which
+    isd = td + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010%s.forRC.IS/raw_data/" % which
+    refs, reads = bamio.read_bam(bam)
+    by = {}
+    for r in reads:
+        if r.tid >= 0:
+            by.setdefault(refs[r.tid][0], []).append(r)
+    out, tal, _ = read_filter.filter_pairs({s: read_filter.pair2info(rs) for s, rs in by.items()})
+    rdic = json.load(open(isd + "Rdic.json"))
+    assert {s: d for s, d in out.items() if d} == rdic and sum(len(v) for v in rdic.values()) == n_pairs
+    mi = pd.read_csv(isd + "mapping_info.csv.gz")
+    mi = mi[mi.scaffold != "all_scaffolds"].set_index("scaffold")
+    assert all(int(mi.loc[s, c]) == tal[s][c] for s in mi.index if s in tal for c in tal[s])
