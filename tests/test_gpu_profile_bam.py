@@ -99,3 +99,34 @@ def test_profile_bam_tiny_scaffold_vs_reference_functions():
             mine[s.index.values] = s.values
         assert np.array_equal(mine, dense), mm
     assert len(res.cumulative_scaffold_table) == len([m for m in fx["covT"] if np.asarray(fx["covT"][m]).sum() > 0])
+
+
+def test_polymorpher_extract_snvs_from_bam(null_lut):
+    """extract_SNVS_from_bam (second caller of the pileup primitive) against the oracle's counts summed over
+    mm, and against the reference's stored SNV rows where the row's mm is the scaffold's top level."""
+    from instrain_b200.polymorpher import extract_SNVS_from_bam
+    from oracle import bamio, pileup_emul, restate
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    refs, reads = bamio.read_bam(bam)
+    tid = 2
+    name = refs[tid][0]
+    ev = restate.sort_events(pileup_emul.scaffold_events([r for r in reads if r.tid == tid], rdic[name]))
+    L = refs[tid][1]
+    counts, _ = restate.pileup_counts(ev, 0, L, int(ev["pair_mm"].max()) + 1)
+    total = counts.sum(1)
+    g_snv, _ = golden_tables({name})
+    positions = sorted(set(int(p) for p in g_snv["position"]))[:200] + [0, L - 1]
+    got = extract_SNVS_from_bam(bam, rdic[name], positions, name)
+    assert set(got) == set(positions)
+    for p in positions:
+        assert np.array_equal(got[p], total[p]), p
+    top = g_snv[g_snv["mm"] == g_snv.groupby("position")["mm"].transform("max")]
+    n_chk = 0
+    for _, r in top.iterrows():
+        p = int(r["position"])
+        if p in got and counts[p, int(r["mm"]) + 1:].sum() == 0:
+            assert list(got[p]) == [r["A"], r["C"], r["T"], r["G"]]
+            n_chk += 1
+    assert n_chk > 20
+    assert extract_SNVS_from_bam(bam, rdic[name], [], name) == {}
