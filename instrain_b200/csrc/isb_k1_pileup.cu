@@ -369,30 +369,52 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
                 q4[v] = *reinterpret_cast<const uint32_t *>(s_qual + i0 + 4 * v);
             }
             const uint32_t s_cnt_u32 = k1_smem_u32(s_cnt);
+            const bool interior = v_lo == 0 && v_hi == CH;
+            // quality mask of each vector (byte-SIMD), clipped to the tile's slice on boundary chunks; then ALL mm gathers
+            // of the run are issued before any of them is used
+            uint32_t okm[NV];
+            int mmv[NV][4];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const int i = i0 + 4 * v;
-                const int32_t ps[4] = {pv[v].x, pv[v].y, pv[v].z, pv[v].w};
+                uint32_t ok;
+                if (q_simd) ok = ((((q4[v] & 0x7f7f7f7fu) + q_add) | q4[v]) >> 7) & 0x01010101u;
+                else ok = ((q4[v] & 0xff) >= (unsigned)min_qual) | (((q4[v] >> 8) & 0xff) >= (unsigned)min_qual) << 8 |
+                          (((q4[v] >> 16) & 0xff) >= (unsigned)min_qual) << 16 | ((q4[v] >> 24) >= (unsigned)min_qual) << 24;
+                if (!interior) {
+                    const int lo_k = min(max(v_lo - i, 0), 4), hi_k = min(max(v_hi - i, 0), 4);
+                    const uint32_t m_lo = lo_k >= 4 ? 0u : (0xffffffffu << (8 * lo_k));
+                    const uint32_t m_hi = hi_k >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * hi_k));
+                    ok &= m_lo & m_hi;
+                }
+                okm[v] = ok;
                 const int32_t rs[4] = {rv[v].x, rv[v].y, rv[v].z, rv[v].w};
-                int mmv[4];
-                bool okv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {                         // the four mm gathers are issued back to back
-                    const int q = (q4[v] >> (8 * j)) & 0xff;
-                    okv[j] = (i + j >= v_lo) && (i + j < v_hi) && (q >= min_qual);
-                    mmv[j] = okv[j] ? (int)__ldg(pair_mm + rs[j]) : 0;
+                for (int j = 0; j < 4; ++j) mmv[v][j] = ((ok >> (8 * j)) & 1u) ? (int)__ldg(pair_mm + rs[j]) : 0;
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int32_t ps[4] = {pv[v].x, pv[v].y, pv[v].z, pv[v].w};
+                uint32_t ok = okm[v];
+                if (b4[v] & 0xfcfcfcfcu) {                             // non-ACGT base(s): rare, exact per-event path
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (((b4[v] >> (8 * j)) & 0xfc) && ((ok >> (8 * j)) & 1)) {
+                            const unsigned pr = (unsigned)(ps[j] - rel0);
+                            if (pr < (unsigned)np && mmv[v][j] < M) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mmv[v][j]); }
+                            else bad |= pr < (unsigned)np ? 2u : 1u;
+                            ok &= ~(1u << (8 * j));
+                        }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int b = (b4[v] >> (8 * j)) & 0xff;
+                    const unsigned one = (ok >> (8 * j)) & 1u;
                     const unsigned pr = (unsigned)(ps[j] - rel0);
-                    const bool inb = pr < (unsigned)np, mm_ok = mmv[j] < M;
-                    bad |= (okv[j] && !inb) ? 1u : 0u;
-                    bad |= (okv[j] && !mm_ok) ? 2u : 0u;
-                    const bool count = okv[j] && inb && mm_ok;
-                    if (count && b >= 4) { if (nmask) atomicOr(nmask + p0 + pr, 1ull << mmv[j]); }   // rare
-                    const unsigned cell = min(pr, (unsigned)np) * (unsigned)M + (unsigned)min(mmv[j], M - 1);
-                    k1_red(s_cnt_u32 + (((cell << 2) + (unsigned)(b & 3)) << 2), (count && b < 4) ? 1u : 0u);
+                    const unsigned oob = pr >= (unsigned)np ? 1u : 0u, mmb = mmv[v][j] >= M ? 1u : 0u;
+                    bad |= (0u - one) & (oob | (mmb << 1));
+                    const unsigned cell = min(pr, (unsigned)np) * (unsigned)M + (unsigned)min(mmv[v][j], M - 1);
+                    const unsigned b = (b4[v] >> (8 * j)) & 3u;
+                    k1_red(s_cnt_u32 + ((cell << 4) | (b << 2)), one & (oob ^ 1u) & (mmb ^ 1u));
                 }
             }
         }

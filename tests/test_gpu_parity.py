@@ -339,3 +339,11 @@ def test_chunk_pipeline_equals_single_pass(eng, skip_mm):
     assert_snv_equal(a["snv"], b["snv"])
     assert_ld_equal(a["ld"], b["ld"], tol=0)
     assert (a["n_sites"], a["n_site_pairs"]) == (b["n_sites"], b["n_site_pairs"])
+
+
+@pytest.mark.parametrize("min_qual", [0, 1, 41, 129, 200])
+def test_min_base_quality_is_a_parameter(eng, null_lut, min_qual):
+    """K1's byte-SIMD quality test covers 1..128; 0 and > 128 take the scalar compare -- all must equal the oracle."""
+    for skip_mm in (True, False):
+        batch = synth.make_batch(9000, 70, 0.02, 31, skip_mm=skip_mm)
+        check_batch(eng, batch, null_lut, min_qual=min_qual)
