@@ -227,6 +227,9 @@ int64_t isb_launch_count(const isb_ctx *ctx);
 /* Measurement hooks (bench.py's roofline leg): when enabled, isb_profile_batch brackets K1 / K2 / K3 with CUDA
  * events on the context's stream.  isb_stage_times synchronises, returns the summed device milliseconds and call
  * counts per stage (index 0 = K1 pileup, 1 = K2 SNV, 2 = K3 linkage) since the last call, and resets them. */
+/* Self-test of K2's fast correctly-rounded quotient (one reciprocal + 3 FP64 ops instead of an IEEE division): number of
+ * pairs (c, s), s_lo <= s <= s_hi, 0 <= c <= s, whose result differs bitwise from the IEEE division; -1 on error. */
+int64_t isb_selftest_division(isb_ctx *ctx, int s_lo, int s_hi);
 int isb_enable_timing(isb_ctx *ctx, int on);
 int isb_stage_times(isb_ctx *ctx, double ms[3], int64_t calls[3]);
 

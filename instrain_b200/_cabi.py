@@ -37,7 +37,7 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
            "isb_scaffold_summary", "isb_launch_count",
-           "isb_enable_timing", "isb_stage_times",
+           "isb_enable_timing", "isb_stage_times", "isb_selftest_division",
            "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
            "isb_bam_peek_tid", "isb_pack_scaffold", "isb_events_count", "isb_events_pairs", "isb_events_reads_seen",
            "isb_events_reads_packed", "isb_events_copy", "isb_events_free",
@@ -110,6 +110,8 @@ def load():
     L.isb_linkage.restype = C.c_int
     L.isb_linkage.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i32, i32, C.c_int, C.c_int, vp, vp, vp, i32, vp,
                               C.c_int, vp, i64, C.POINTER(i64)]
+    L.isb_selftest_division.restype = i64
+    L.isb_selftest_division.argtypes = [vp, C.c_int, C.c_int]
     L.isb_enable_timing.restype = C.c_int
     L.isb_enable_timing.argtypes = [vp, C.c_int]
     L.isb_stage_times.restype = C.c_int

@@ -206,6 +206,15 @@ int isb_synchronize(isb_ctx *ctx)
 
 int64_t isb_launch_count(const isb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int64_t isb_selftest_division(isb_ctx *ctx, int s_lo, int s_hi)
+{
+    if (!ctx || s_lo < 1) return -1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    unsigned long long bad = 0;
+    if (isb_k2_selftest_division(ctx, s_lo, s_hi, &bad) != ISB_OK) return -1;
+    return (int64_t)bad;
+}
+
 int isb_enable_timing(isb_ctx *ctx, int on)
 {
     if (!ctx) return ISB_ERR_ARG;

@@ -107,6 +107,7 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
                   int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap);
 int isb_ensure(isb_ctx *ctx, int slot, size_t bytes);
+int isb_k2_selftest_division(isb_ctx *ctx, int s_lo, int s_hi, unsigned long long *h_mismatches);
 int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const unsigned long long *nmask,
                   int n_seg, const int32_t *seg_off, isb_summary_row *out);
 int isb_tile_offsets(isb_ctx *ctx, const int32_t *ref_pos, int64_t n, int32_t start, int32_t L, int tp, int n_tiles);
@@ -123,4 +124,33 @@ __device__ __forceinline__ int64_t isb_lower_bound(const int32_t *__restrict__ a
         if ((int64_t)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+ PTX; used by K1 and the staged K2) -----------------------------------
+__device__ __forceinline__ uint32_t isb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void isb_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(isb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void isb_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(isb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void isb_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(isb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(isb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void isb_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const uint32_t addr = isb_smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void isb_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(isb_smem_u32(bar)) : "memory");
 }

@@ -113,30 +113,6 @@ k1_pileup_tiles(const int32_t *__restrict__ ref_pos, const uint8_t *__restrict__
 //     means a run covers 1-2 positions, so the thread counts 4 events at a time with byte-SIMD logic + POPC into four
 //     registers and touches shared memory only when the position changes (~2 atomics per 20 events);
 //   * the finished tile is written out with 128-bit stores as before.
-__device__ __forceinline__ uint32_t k1_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void k1_mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k1_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void k1_mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k1_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void k1_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(k1_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k1_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void k1_mbar_wait(uint64_t *bar, unsigned parity)
-{
-    const uint32_t addr = k1_smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-
 // Per-thread state of the lane-serial M = 1 walk: current position and its four base counters.
 struct k1_run {
     int cur_p;
@@ -160,7 +136,7 @@ __device__ __forceinline__ void k1_flush(int32_t *s_cnt, int p, int rel0, int np
     if (doit) {
         const unsigned pr = (unsigned)(p - rel0);
         bad |= ((a0 | a1 | a2 | a3) && pr >= (unsigned)np && p != 0x7fffffff) ? 1u : 0u;
-        const uint32_t d = k1_smem_u32(s_cnt) + (min(pr, (unsigned)np) << 4);
+        const uint32_t d = isb_smem_u32(s_cnt) + (min(pr, (unsigned)np) << 4);
         k1_red(d + 0, a0);
         k1_red(d + 4, a1);
         k1_red(d + 8, a2);
@@ -261,7 +237,7 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
     const int tid = threadIdx.x;
     for (int i = tid; i < n_cnt4 + M; i += kT) reinterpret_cast<int4 *>(s_cnt)[i] = make_int4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int s = 0; s < kS; ++s) k1_mbar_init(s_bar + s, 1);
+        for (int s = 0; s < kS; ++s) isb_mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -280,12 +256,12 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
         c_hi = min(c_hi, n_bulk);
         const unsigned ne = c_hi > c_lo ? (unsigned)(c_hi - c_lo) : 0u;
         unsigned char *sp = s_stage + (size_t)st * STAGE_BYTES;
-        k1_mbar_expect_tx(s_bar + st, ne * (kM1 ? 6u : 10u));
+        isb_mbar_expect_tx(s_bar + st, ne * (kM1 ? 6u : 10u));
         if (ne) {
-            k1_bulk_g2s(sp, ref_pos + c_lo, ne * 4u, s_bar + st);
-            if (!kM1) k1_bulk_g2s(sp + CH * 4, read_id + c_lo, ne * 4u, s_bar + st);
-            k1_bulk_g2s(sp + CH * (kM1 ? 4 : 8), base + c_lo, ne, s_bar + st);
-            k1_bulk_g2s(sp + CH * (kM1 ? 5 : 9), qual + c_lo, ne, s_bar + st);
+            isb_bulk_g2s(sp, ref_pos + c_lo, ne * 4u, s_bar + st);
+            if (!kM1) isb_bulk_g2s(sp + CH * 4, read_id + c_lo, ne * 4u, s_bar + st);
+            isb_bulk_g2s(sp + CH * (kM1 ? 4 : 8), base + c_lo, ne, s_bar + st);
+            isb_bulk_g2s(sp + CH * (kM1 ? 5 : 9), qual + c_lo, ne, s_bar + st);
         }
     };
     if (tid == 0)
@@ -316,7 +292,7 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
             }
             __syncthreads();
         }
-        k1_mbar_wait(s_bar + st, (unsigned)((c / kS) & 1));
+        isb_mbar_wait(s_bar + st, (unsigned)((c / kS) & 1));
 
         // Run -> thread mapping.  Lanes of one warp take runs that are kT/32 (an ODD number of) runs apart: neighbouring
         // lanes then sit on different positions, so the flush atomics of one warp instruction do not collide on an
@@ -368,7 +344,7 @@ k1_pileup_tiles_tma(const int32_t *__restrict__ ref_pos, const uint8_t *__restri
                 b4[v] = *reinterpret_cast<const uint32_t *>(s_base + i0 + 4 * v);
                 q4[v] = *reinterpret_cast<const uint32_t *>(s_qual + i0 + 4 * v);
             }
-            const uint32_t s_cnt_u32 = k1_smem_u32(s_cnt);
+            const uint32_t s_cnt_u32 = isb_smem_u32(s_cnt);
             const bool interior = v_lo == 0 && v_hi == CH;
             // quality mask of each vector (byte-SIMD), clipped to the tile's slice on boundary chunks; then ALL mm gathers
             // of the run are issued before any of them is used

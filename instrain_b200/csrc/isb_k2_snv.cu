@@ -10,6 +10,7 @@
 // >= min_freq decisions and the float32 clonality are bit-identical to CPython's arithmetic.
 #include "isb_common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 #define K2_THREADS 256
 
@@ -31,39 +32,64 @@ __global__ void k2_build_thr2(const int32_t *__restrict__ lut, int n_lut, int lu
     thr2[T] = max(thr, lo);
 }
 
+// Correctly rounded c / s for the four base frequencies of one site from ONE correctly rounded reciprocal
+// (Markstein: with y = RN(1/s) and q = RN(c*y), q' = RN(q + (c - s*q)*y) is RN(c/s)).  Three FP64 operations per
+// quotient instead of a full IEEE division each.  Used for s <= K2_FAST_DIV_MAX, the range for which
+// isb_selftest_division (tests/test_gpu_parity.py) compares it bit for bit with __ddiv_rn for EVERY 0 <= c <= s.
+#define K2_FAST_DIV_MAX 65536
+__device__ __forceinline__ double k2_quot(double c, double s, double rcp)
+{
+    const double q = __dmul_rn(c, rcp);
+    const double e = __fma_rn(-q, s, c);
+    return __fma_rn(e, rcp, q);
+}
+
+__global__ void k2_selftest_division(int s_lo, int s_hi, unsigned long long *__restrict__ mismatches)
+{
+    const int s = s_lo + blockIdx.x;
+    if (s > s_hi) return;
+    const double ds = (double)s, rcp = __drcp_rn(ds);
+    unsigned long long bad = 0;
+    for (int c = threadIdx.x; c <= s; c += blockDim.x)
+        bad += __double_as_longlong(k2_quot((double)c, ds, rcp)) != __double_as_longlong(__ddiv_rn((double)c, ds));
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 struct k2_site_state {
     int n_rows;
     int cryptic;
     unsigned bases;
     int any_snp;
+    int C[4];                                                         // cumulative A,C,T,G counts up to the current level
 };
 
 __device__ __forceinline__ int k2_argmax4(const int *c)
 {
-    int b = 0;
+    int b = 0, v = c[0];                                  // np.argmax: first maximum (value tracked: no dynamic indexing)
 #pragma unroll
-    for (int i = 1; i < 4; ++i) if (c[i] > c[b]) b = i;   // np.argmax: first maximum
+    for (int i = 1; i < 4; ++i) if (c[i] > v) { v = c[i]; b = i; }
     return b;
 }
 
+// The reference's ascending-mm loop over levels [m0, m0 + mc) of ONE site; `st` carries anySNP / bases / cryptic / the
+// cumulative counts across calls.  crow[j], cov_row[j], clon_row[j] address level m0 + j (global rows, or the block's
+// shared-memory tiles in the staged kernel).
 // kWrite = false: compute covT / clonT / flags and count the rows of this site.
 // kWrite = true : emit the rows (cryptic already known) to rows[slot...].
 template <bool kWrite>
-__device__ __forceinline__ k2_site_state
-k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long long nm, int ref,
-             const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
-             int32_t *__restrict__ covT, float *__restrict__ clonT, isb_snv_row *__restrict__ rows, int64_t slot,
-             int64_t cap, int cryptic_final)
+__device__ __forceinline__ void
+k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, unsigned long long nm, int ref,
+               const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
+               int32_t *cov_row, float *clon_row, isb_snv_row *__restrict__ rows, int64_t slot, int64_t cap,
+               int cryptic_final)
 {
-    k2_site_state st = {0, 0, 0u, 0};
-    int C[4] = {0, 0, 0, 0};
-    for (int m = 0; m < M; ++m) {
-        const int4 E = __ldg(reinterpret_cast<const int4 *>(counts) + (size_t)p * M + m);
+    int *C = st.C;
+    for (int j = 0; j < mc; ++j) {
+        const int m = m0 + j;
+        const int4 E = crow[j];
         const int e_sum = E.x + E.y + E.z + E.w;
         const bool present = e_sum > 0 || ((nm >> m) & 1ull);       // mm is a key of MMcounts
-        if (!kWrite) {
-            covT[(size_t)p * M + m] = e_sum;                          // update_covT: exact-mm coverage
-        }
+        if (!kWrite) cov_row[j] = e_sum;                              // update_covT: exact-mm coverage
         float clon = CUDART_NAN_F;
         if (present) {
             C[0] += E.x; C[1] += E.y; C[2] += E.z; C[3] += E.w;       // mm_counts_to_counts(MMcounts, mm)
@@ -72,15 +98,21 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
         const bool counted = present && T >= min_cov;
         if (counted && !kWrite) {                                     // calculate_clonality, double, A,C,T,G order
             const double s = (double)T;
-            // 0/s == +0.0 exactly, so absent bases skip the (expensive) IEEE double division
-            const double f0 = C[0] ? __ddiv_rn((double)C[0], s) : 0.0, f1 = C[1] ? __ddiv_rn((double)C[1], s) : 0.0;
-            const double f2 = C[2] ? __ddiv_rn((double)C[2], s) : 0.0, f3 = C[3] ? __ddiv_rn((double)C[3], s) : 0.0;
+            double f0, f1, f2, f3;
+            if (T <= K2_FAST_DIV_MAX) {                               // one reciprocal, four 3-op quotients (bit-exact)
+                const double rcp = __drcp_rn(s);
+                f0 = k2_quot((double)C[0], s, rcp); f1 = k2_quot((double)C[1], s, rcp);
+                f2 = k2_quot((double)C[2], s, rcp); f3 = k2_quot((double)C[3], s, rcp);
+            } else {                                                  // 0/s == +0.0 exactly: absent bases skip the division
+                f0 = C[0] ? __ddiv_rn((double)C[0], s) : 0.0; f1 = C[1] ? __ddiv_rn((double)C[1], s) : 0.0;
+                f2 = C[2] ? __ddiv_rn((double)C[2], s) : 0.0; f3 = C[3] ? __ddiv_rn((double)C[3], s) : 0.0;
+            }
             double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
             prob = __dadd_rn(prob, __dmul_rn(f2, f2));
             prob = __dadd_rn(prob, __dmul_rn(f3, f3));
             clon = __double2float_rn(prob);
         }
-        if (!kWrite) clonT[(size_t)p * M + m] = clon;
+        if (!kWrite) clon_row[j] = clon;
         if (!counted) continue;                                       // call_snv_site -> (None, 0)
         int thr, i = 0;
         if (T < n_lut) {                                              // integer form of the two-part presence test
@@ -99,9 +131,8 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
             if (st.any_snp) st.cryptic = 1;
             continue;
         }
-        int tmp[4] = {C[0], C[1], C[2], C[3]};
-        tmp[con] = 0;
-        const int var = k2_argmax4(tmp);
+        const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
+        const int var = k2_argmax4(tmp);                              // selects, not tmp[con] = 0: keeps C[] in registers
         if (kWrite) {
             int cls;
             if (ref > 3) cls = ISB_CLS_AMBIGUOUS_REFERENCE;
@@ -110,7 +141,7 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
             else if (ref == con) cls = ISB_CLS_SNV;
             else if (ref == var) cls = ISB_CLS_CON_SNV;
             else {
-                const int cr = C[ref];                                // is_present(counts[ref], total, model, min_freq)
+                const int cr = ref == 0 ? C[0] : ref == 1 ? C[1] : ref == 2 ? C[2] : C[3];   // is_present(counts[ref], ...)
                 const bool pres = T < n_lut ? (cr >= thr) : (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq);
                 cls = pres ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
             }
@@ -129,30 +160,16 @@ k2_site_loop(int32_t p, int M, const int32_t *__restrict__ counts, unsigned long
         if (i >= 2) { st.any_snp = 1; st.bases |= (1u << con) | (1u << var); }
         else if (i == 1 && st.any_snp) st.cryptic = 1;
     }
-    return st;
 }
 
-__global__ void __launch_bounds__(K2_THREADS)
-k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigned long long *__restrict__ nmask,
-             const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
-             int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
-             uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
-             unsigned long long *__restrict__ n_rows)
+// Warp-aggregated row allocation (one global atomic per warp that has rows) + the second, row-writing pass of the sites
+// that have rows; that pass re-reads the site's counts from global memory (L2-resident, < 1 % of the sites).
+__device__ __forceinline__ void
+k2_emit_rows(const k2_site_state &st, int32_t p, int M, const int32_t *__restrict__ counts, unsigned long long nm, int ref,
+             const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
+             isb_snv_row *__restrict__ rows, int64_t cap, unsigned long long *__restrict__ n_rows)
 {
-    const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool active = p < L;
-    k2_site_state st = {0, 0, 0u, 0};
-    unsigned long long nm = 0;
-    int r = 4;
-    if (active) {
-        nm = nmask ? nmask[p] : 0ull;
-        r = ref[p];
-        st = k2_site_loop<false>(p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, covT, clonT,
-                                 nullptr, 0, 0, 0);
-        site_flags[p] = (uint8_t)(st.bases | (st.any_snp ? ISB_SITE_ANYSNP : 0));
-    }
-    // warp-aggregated row allocation: one global atomic per warp that has rows
     int incl = st.n_rows;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -164,9 +181,141 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
     unsigned long long base_slot = 0;
     if (lane == 0) base_slot = atomicAdd(n_rows, (unsigned long long)total);
     base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
-    if (st.n_rows > 0)
-        k2_site_loop<true>(p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, covT, clonT, rows,
-                           (int64_t)base_slot + incl - st.n_rows, cap, st.cryptic);
+    if (st.n_rows > 0) {
+        k2_site_state w = {0, 0, 0u, 0, {0, 0, 0, 0}};
+        k2_site_levels<true>(w, p, 0, M, reinterpret_cast<const int4 *>(counts) + (size_t)p * M, nm, ref, thr2, n_lut,
+                             lut_default, start, min_cov, min_freq, nullptr, nullptr, rows,
+                             (int64_t)base_slot + incl - st.n_rows, cap, st.cryptic);
+    }
+}
+
+// M = 1 (and the fallback): one thread per position straight from global memory -- with one level a warp's 32 rows are
+// one contiguous 512-byte block, already perfectly coalesced.
+__global__ void __launch_bounds__(K2_THREADS)
+k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigned long long *__restrict__ nmask,
+             const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
+             int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
+             uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
+             unsigned long long *__restrict__ n_rows)
+{
+    const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
+    const bool active = p < L;
+    k2_site_state st = {0, 0, 0u, 0, {0, 0, 0, 0}};
+    unsigned long long nm = 0;
+    int r = 4;
+    if (active) {
+        nm = nmask ? nmask[p] : 0ull;
+        r = ref[p];
+        k2_site_levels<false>(st, p, 0, M, reinterpret_cast<const int4 *>(counts) + (size_t)p * M, nm, r, thr2, n_lut,
+                              lut_default, start, min_cov, min_freq, covT + (size_t)p * M, clonT + (size_t)p * M, nullptr,
+                              0, 0, 0);
+        site_flags[p] = (uint8_t)(st.bases | (st.any_snp ? ISB_SITE_ANYSNP : 0));
+    }
+    k2_emit_rows(st, p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, rows, cap, n_rows);
+}
+
+// M > 1: a thread's M count quads are 16*M bytes apart from its neighbour's, so direct loads touch one 32-byte sector per
+// 16 useful bytes and the 4-byte covT / clonT stores one sector each.  The staged kernel moves the block's rows through
+// shared memory instead.  M <= K2S_MC (every realistic read filter: <= 15 mismatches per pair): the block's input rows
+// are ONE contiguous run, fetched with a single TMA 1-D bulk copy (cp.async.bulk + mbarrier complete_tx); the level loop
+// runs out of shared memory into two shared output tiles with the global layout, which leave as 128-bit coalesced stores.
+// M > K2S_MC: chunks of K2S_MC levels, per-row bulk copies into padded rows, the site state carried in registers.
+#define K2S_THREADS 128
+#define K2S_MC 16
+__global__ void __launch_bounds__(K2S_THREADS)
+k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const unsigned long long *__restrict__ nmask,
+                    const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
+                    int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
+                    uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
+                    unsigned long long *__restrict__ n_rows)
+{
+    extern __shared__ __align__(128) unsigned char k2_smem[];
+    const bool whole = M <= K2S_MC;                                   // one chunk: rows keep the global (unpadded) layout
+    const int MC = min(M, K2S_MC);
+    const int sin = whole ? M : (MC | 1);                             // input row stride in int4 units
+    const int sout = whole ? M : (MC | 1);                            // output row stride in words
+    int4 *s_in = reinterpret_cast<int4 *>(k2_smem);
+    int32_t *s_cov = reinterpret_cast<int32_t *>(s_in + (size_t)K2S_THREADS * sin);
+    float *s_clon = reinterpret_cast<float *>(s_cov + (size_t)K2S_THREADS * sout);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_clon + (size_t)K2S_THREADS * sout);   // 8-byte aligned: K2S_THREADS is even
+    const int t = threadIdx.x;
+    const int32_t p0 = blockIdx.x * K2S_THREADS;
+    const int32_t p = p0 + t;
+    const bool active = p < L;
+    const int npos = min(K2S_THREADS, L - p0);
+    if (t == 0) {
+        isb_mbar_init(bar, whole ? 1 : K2S_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    k2_site_state st = {0, 0, 0u, 0, {0, 0, 0, 0}};
+    unsigned long long nm = 0;
+    int r = 4;
+    if (whole) {
+        if (t == 0) {
+            const unsigned bytes = (unsigned)npos * (unsigned)M * 16u;
+            isb_mbar_expect_tx(bar, bytes);
+            isb_bulk_g2s(s_in, reinterpret_cast<const int4 *>(counts) + (size_t)p0 * M, bytes, bar);
+        }
+        if (active) {
+            nm = nmask ? nmask[p] : 0ull;
+            r = ref[p];
+        }
+        isb_mbar_wait(bar, 0);
+        if (active)
+            k2_site_levels<false>(st, p, 0, M, s_in + (size_t)t * M, nm, r, thr2, n_lut, lut_default, start, min_cov,
+                                  min_freq, s_cov + (size_t)t * M, s_clon + (size_t)t * M, nullptr, 0, 0, 0);
+        __syncthreads();
+        const int n_out = npos * M;                                   // words; the block's output run starts 16-byte aligned
+        const size_t g0 = (size_t)p0 * M;
+        const int n4 = n_out >> 2;
+        int4 *gc = reinterpret_cast<int4 *>(covT + g0);
+        int4 *gl = reinterpret_cast<int4 *>(clonT + g0);
+        const int4 *sc = reinterpret_cast<const int4 *>(s_cov), *sl = reinterpret_cast<const int4 *>(s_clon);
+        for (int e = t; e < n4; e += K2S_THREADS) { gc[e] = sc[e]; gl[e] = sl[e]; }
+        for (int e = (n4 << 2) + t; e < n_out; e += K2S_THREADS) { covT[g0 + e] = s_cov[e]; clonT[g0 + e] = s_clon[e]; }
+    } else {
+        if (active) {
+            nm = nmask ? nmask[p] : 0ull;
+            r = ref[p];
+        }
+        unsigned parity = 0;
+        for (int m0 = 0; m0 < M; m0 += MC) {
+            const int mc = min(MC, M - m0);
+            if (active) {                                             // own row -> own padded shared row
+                isb_mbar_expect_tx(bar, (unsigned)mc * 16u);
+                isb_bulk_g2s(s_in + (size_t)t * sin, reinterpret_cast<const int4 *>(counts) + (size_t)p * M + m0,
+                             (unsigned)mc * 16u, bar);
+            } else {
+                isb_mbar_arrive(bar);
+            }
+            isb_mbar_wait(bar, parity);
+            parity ^= 1u;
+            if (active)
+                k2_site_levels<false>(st, p, m0, mc, s_in + (size_t)t * sin, nm, r, thr2, n_lut, lut_default, start,
+                                      min_cov, min_freq, s_cov + (size_t)t * sout, s_clon + (size_t)t * sout, nullptr, 0,
+                                      0, 0);
+            __syncthreads();
+            // two rows per warp pass: 16 lanes per row (mc <= 16), no integer division
+            for (int q = (t >> 4); q < npos; q += K2S_THREADS / 16) {
+                const int j = t & 15;
+                if (j < mc) {
+                    const size_t g = (size_t)(p0 + q) * M + m0 + j;
+                    covT[g] = s_cov[q * sout + j];
+                    clonT[g] = s_clon[q * sout + j];
+                }
+            }
+            if (m0 + MC < M) __syncthreads();                         // tiles are reused by the next chunk
+        }
+    }
+    if (active) site_flags[p] = (uint8_t)(st.bases | (st.any_snp ? ISB_SITE_ANYSNP : 0));
+    k2_emit_rows(st, p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, rows, cap, n_rows);
+}
+
+static size_t k2s_smem_bytes(int M)
+{
+    const size_t sin = M <= K2S_MC ? (size_t)M : (size_t)(K2S_MC | 1), sout = sin;
+    return (size_t)K2S_THREADS * sin * 16 + 2 * (size_t)K2S_THREADS * sout * 4 + 16;
 }
 
 int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
@@ -182,9 +331,37 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
         ISB_LAUNCH_CHECK();
         ctx->thr2_min_freq = min_freq;
     }
-    k2_call_snvs<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
-        L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
-        site_flags, rows, cap, ctx->d_counters + 0);
+    static const int variant = getenv("ISB_K2_VARIANT") ? atoi(getenv("ISB_K2_VARIANT")) : -1;   // 0 = direct, 1 = staged
+    if (M > 1 && variant != 0) {
+        const size_t smem = k2s_smem_bytes(M);
+        static bool attr_set[64] = {false};                          // function attributes are per device
+        if (!attr_set[ctx->device & 63]) {
+            ISB_CUDA(cudaFuncSetAttribute(k2_call_snvs_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2s_smem_bytes(64)));
+            attr_set[ctx->device & 63] = true;
+        }
+        k2_call_snvs_staged<<<(L + K2S_THREADS - 1) / K2S_THREADS, K2S_THREADS, smem, st>>>(
+            L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
+            site_flags, rows, cap, ctx->d_counters + 0);
+    } else {
+        k2_call_snvs<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
+            L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
+            site_flags, rows, cap, ctx->d_counters + 0);
+    }
     ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
+// Self-test of the fast quotient: number of (c, s) pairs, s_lo <= s <= s_hi, 0 <= c <= s, whose k2_quot differs from __ddiv_rn.
+int isb_k2_selftest_division(isb_ctx *ctx, int s_lo, int s_hi, unsigned long long *h_mismatches)
+{
+    cudaStream_t st = ctx->stream;
+    ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 5, 0, sizeof(unsigned long long), st));
+    if (s_hi >= s_lo) {
+        k2_selftest_division<<<s_hi - s_lo + 1, 256, 0, st>>>(s_lo, s_hi, ctx->d_counters + 5);
+        ISB_LAUNCH_CHECK();
+    }
+    ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 5, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ISB_CUDA(cudaStreamSynchronize(st));
+    *h_mismatches = ctx->h_counters[5];
     return ISB_OK;
 }

@@ -347,3 +347,9 @@ def test_min_base_quality_is_a_parameter(eng, null_lut, min_qual):
     for skip_mm in (True, False):
         batch = synth.make_batch(9000, 70, 0.02, 31, skip_mm=skip_mm)
         check_batch(eng, batch, null_lut, min_qual=min_qual)
+
+
+def test_fast_quotient_is_exactly_ieee_division(eng):
+    """K2 computes the four base frequencies of a site from one reciprocal (Markstein correction).  Exhaustive check of
+    every 0 <= c <= s for all s in the range K2 uses it for (s <= 65536; 2.1e9 pairs), bit for bit against __ddiv_rn."""
+    assert eng.lib.isb_selftest_division(eng.ctx, 1, 65536) == 0
