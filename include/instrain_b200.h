@@ -199,6 +199,56 @@ typedef struct {
 
 int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb_params *prm, isb_result *out);
 
+/* ---- READ-MAJOR input: aligned segments ------------------------------------------------------------------------------ */
+/* The B200-first layout of the same information, as close to the BAM records as the path allows (what pysam hands
+ * the reference one pileup column at a time, profile_utilities.py:150-153, stored once per READ instead of once per
+ * column).  A segment is one CIGAR M/=/X block of a kept read: seg_len consecutive reference positions from seg_start,
+ * one 4-bit ONE-HOT code per aligned base:  A = 1, C = 2, T = 4, G = 8 when the base survives htslib's base-quality
+ * filter AFTER the mate-overlap tweak (i.e. it would be an event with qual >= min_qual), 0 when it does not (such a base
+ * is not an event at all) or when it is not A/C/T/G.  Passing non-ACGT bases -- which only make their pair's mm level a
+ * key of the position's MMcounts (the nmask bit) -- are listed separately (nev_pos / nev_pair; usually empty).
+ * 4 bits per aligned base + ~22 bytes per segment instead of 10 bytes per event: 16x less HBM traffic for the pileup
+ * and ~1.8x less PCIe traffic than the packed format.  The pileup kernel (K1r, isb_k1r_reads.cu) transposes on the fly:
+ * every thread owns 8 consecutive positions and counts the codes of the segments that cover them with bit-sliced
+ * (vertical, carry-save) counters -- no atomics.
+ *
+ * Layout rules (validated on the device; violations -> ISB_ERR_ORDER):
+ *   - segments sorted by seg_start (ascending, ties in any order), all inside [start, start + L), 1 <= seg_len <=
+ *     max_seg_len <= 256 (longer blocks are split by the packer);
+ *   - words: nibble j of a segment sits in bits 4*(j%8).. of word seg_word[i] + j/8; unused high nibbles of the last
+ *     data word are 0; the data words of consecutive segments are separated by EXACTLY one zero word, i.e.
+ *     seg_word[0] = 1, seg_word[i+1] = seg_word[i] + ceil(seg_len[i]/8) + 1, and the stream ends with one zero word,
+ *     padded with zero words to a multiple of 4 (n_words). */
+typedef struct {
+    int64_t n_segs;
+    const int32_t *seg_start;   /* [n_segs] batch coordinate of the first base */
+    const uint16_t *seg_len;    /* [n_segs] */
+    const int32_t *seg_pair;    /* [n_segs] read-pair id (index into pair_mm) */
+    const int64_t *seg_word;    /* [n_segs] index of the segment's first data word */
+    int64_t n_words;
+    const uint32_t *words;      /* [n_words] nibble stream */
+    int32_t max_seg_len;
+    int32_t pad;
+    int64_t n_nev;              /* passing non-ACGT read bases */
+    const int32_t *nev_pos;     /* [n_nev] batch coordinate */
+    const int32_t *nev_pair;    /* [n_nev] read-pair id */
+    int64_t n_pairs;
+    const uint8_t *pair_mm;     /* [n_pairs]; may be NULL when M == 1 */
+    int32_t start;
+    int32_t L;
+    const uint8_t *ref;         /* [L] (not needed by isb_pileup_reads) */
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+    int32_t pad2;
+} isb_reads_batch;
+
+/* stage K1r alone: counts[L][M][4] (+ nmask[L], may be NULL) from a read-major batch */
+int isb_pileup_reads(isb_ctx *ctx, const isb_reads_batch *in, int32_t *counts, uint64_t *nmask);
+/* K1r -> K2 -> K3 (site events materialised from the segments) on a read-major batch; same results as
+ * isb_profile_batch on the event columns of the same reads.  isb_params.min_qual is not used (the codes carry it). */
+int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params *prm, isb_result *out);
+
 /* ---- stage K4: merge-stage summary reductions (the row after the hot path) ----------------------------- */
 /* Numeric core of make_coverage_table (profile_utilities.py:425-506) with mm_counts_to_counts_shrunk (:508-532) and
  * get_basewise_clons (:534-546): per scaffold s (positions [scaffold_off[s], scaffold_off[s+1]) of covT / clonT) and mm

@@ -96,6 +96,7 @@ static int check_dev_err(isb_ctx *ctx)
     const unsigned e = *ctx->h_err;
     if (!e) return ISB_OK;
     if (e & ISB_DEV_ERR_ORDER) return isb_fail(ctx, ISB_ERR_ORDER, "events are not position-major (an event lies outside its position tile)");
+    if (e & ISB_DEV_ERR_SEG) return isb_fail(ctx, ISB_ERR_ORDER, "read-major batch violates its layout rules (segment order, range or word offsets)");
     if (e & ISB_DEV_ERR_MM) return isb_fail(ctx, ISB_ERR_ARG, "pair_mm value >= M");
     if (e & ISB_DEV_ERR_MULT) return isb_fail(ctx, ISB_ERR_UNSUPPORTED, "a read pair has more than 2 qualifying events on one site");
     return isb_fail(ctx, ISB_ERR_CUDA, "device-side error flag set");
@@ -369,7 +370,7 @@ int isb_scaffold_summary(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, co
 }
 
 // K1 -> K2 -> K3 on device-resident inputs; outputs staged / copied as requested by `out`.
-static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const uint8_t *d_base, const uint8_t *d_qual,
+static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, int64_t n, const int32_t *d_pos, const uint8_t *d_base, const uint8_t *d_qual,
                           const int32_t *d_rid, int64_t n_pairs, const uint8_t *d_mm, int32_t start, int32_t L, int M,
                           const uint8_t *d_ref, int32_t n_splits, const int32_t *d_splits, const isb_params *prm,
                           isb_result *out)
@@ -394,7 +395,7 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
     // identical (linkage never crosses a split; rows are appended through the same atomic counters).
     std::vector<int32_t> hs;
     std::vector<int> cut;                                    // chunk c = splits [cut[c], cut[c+1])
-    const bool want_pipe = (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
+    const bool want_pipe = !rd && (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
     if (want_pipe) {
         hs.resize((size_t)n_splits * 2);
         ISB_CUDA(cudaMemcpyAsync(hs.data(), d_splits, sizeof(int32_t) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -461,8 +462,10 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
         pipe_pairs = acc_pairs;
     } else {
         int ts = isb_time_begin(ctx, 0);
-        if ((rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
-                                (unsigned long long *)d_nmask))) return rc;
+        if (rd) rc = isb_k1r_launch(ctx, rd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask);
+        else rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
+                                (unsigned long long *)d_nmask);
+        if (rc) return rc;
         isb_time_end(ctx, ts);
         ts = isb_time_begin(ctx, 1);
         if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
@@ -470,9 +473,12 @@ static int profile_device(isb_ctx *ctx, int64_t n, const int32_t *d_pos, const u
         isb_time_end(ctx, ts);
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
         ts = do_ld ? isb_time_begin(ctx, 2) : -1;
-        if (do_ld && (rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
-                                         d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
-                                         prm->min_snp, d_ld, ld_cap))) return rc;
+        if (do_ld && rd) rc = isb_k3_launch_reads(ctx, rd, n_pairs, d_mm, start, L, M, d_counts, (const unsigned long long *)d_nmask,
+                                                  d_flags, n_splits, d_splits, prm->min_snp, d_ld, ld_cap);
+        else if (do_ld) rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
+                                           d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
+                                           prm->min_snp, d_ld, ld_cap);
+        if (rc) return rc;
         isb_time_end(ctx, ts);
     }
     if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
@@ -519,7 +525,7 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
     if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
     if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
     if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
-    return profile_device(ctx, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+    return profile_device(ctx, nullptr, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
                           d_splits, prm, out);
 }
 
@@ -557,8 +563,77 @@ int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb
     int qpass = prm->min_qual < 1 ? 1 : (prm->min_qual > 255 ? 255 : prm->min_qual);
     if ((rc = isb_k0_launch(ctx, n, d_off, d_idb, d_bqd, in->n_esc, d_esce, d_esci, in->start, L, qpass, c_pos, c_base,
                             c_qual, c_rid))) return rc;
-    return profile_device(ctx, n, c_pos, c_base, c_qual, c_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+    return profile_device(ctx, nullptr, n, c_pos, c_base, c_qual, c_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
                           d_splits, prm, out);
+}
+
+// host or device read-major batch -> device pointers (staged through the context's grow-only slots)
+static int stage_reads(isb_ctx *ctx, const isb_reads_batch *in, isb_reads_dev *rd, const uint8_t **d_mm)
+{
+    int rc;
+    if (in->n_segs < 0 || in->n_words < 0 || (in->n_words & 3))
+        return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: n_segs / n_words invalid (n_words must be a multiple of 4)");
+    if (in->n_segs > 0 && (!in->seg_start || !in->seg_len || !in->seg_pair || !in->seg_word || !in->words))
+        return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: null segment column");
+    memset(rd, 0, sizeof(*rd));
+    rd->n_segs = in->n_segs;
+    rd->n_words = in->n_words;
+    rd->max_seg_len = in->max_seg_len;
+    if ((rc = stage_in(ctx, SL_RD_START, in->seg_start, (size_t)in->n_segs, &rd->seg_start))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_LEN, in->seg_len, (size_t)in->n_segs, &rd->seg_len))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_PAIR, in->seg_pair, (size_t)in->n_segs, &rd->seg_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_WORD, in->seg_word, (size_t)in->n_segs, &rd->seg_word))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_WORDS, in->words, (size_t)in->n_words, &rd->words))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, d_mm))) return rc;
+    if (in->n_nev < 0 || (in->n_nev > 0 && (!in->nev_pos || !in->nev_pair)))
+        return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: null N-event column");
+    rd->n_nev = in->n_nev;
+    if ((rc = stage_in(ctx, SL_RD_NPOS, in->nev_pos, (size_t)in->n_nev, &rd->nev_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPAIR, in->nev_pair, (size_t)in->n_nev, &rd->nev_pair))) return rc;
+    return ISB_OK;
+}
+
+int isb_pileup_reads(isb_ctx *ctx, const isb_reads_batch *in, int32_t *counts, uint64_t *nmask)
+{
+    if (!ctx || !in) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!counts || (M > 1 && in->n_segs > 0 && !in->pair_mm)) return isb_fail(ctx, ISB_ERR_ARG, "isb_pileup_reads: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_reads_dev rd;
+    const uint8_t *d_mm;
+    if ((rc = stage_reads(ctx, in, &rd, &d_mm))) return rc;
+    int32_t *d_counts; uint64_t *d_nmask = nullptr;
+    if ((rc = stage_out(ctx, SL_COUNTS, counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if (nmask && (rc = stage_out(ctx, SL_NMASK, nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = isb_k1r_launch(ctx, &rd, d_mm, in->n_pairs, in->start, L, M, d_counts, (unsigned long long *)d_nmask))) return rc;
+    if ((rc = finish_out(ctx, counts, d_counts, (size_t)L * M * 4))) return rc;
+    if ((rc = finish_out(ctx, nmask, d_nmask, (size_t)L))) return rc;
+    if ((rc = fetch_status(ctx))) return rc;
+    return check_dev_err(ctx);
+}
+
+int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!in->ref || (M > 1 && !in->pair_mm) || (in->n_splits > 0 && !in->splits))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads: null input pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_reads_dev rd;
+    const uint8_t *d_mm, *d_ref; const int32_t *d_splits;
+    if ((rc = stage_reads(ctx, in, &rd, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    return profile_device(ctx, &rd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+                          in->n_splits, d_splits, prm, out);
 }
 
 }  // extern "C"

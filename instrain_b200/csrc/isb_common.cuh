@@ -15,6 +15,7 @@
 #define ISB_DEV_ERR_MM 0x2u           // pair_mm >= M
 #define ISB_DEV_ERR_MULT 0x4u         // a read pair has > 2 qualifying events on one site
 #define ISB_DEV_ERR_ROWBUF 0x8u       // linkage bit-row scratch too small (host grows it and re-runs K3)
+#define ISB_DEV_ERR_SEG 0x10u         // read-major batch violates its layout rules (order, range, word offsets)
 
 enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_REF_POS = 0, SL_BASE, SL_QUAL, SL_READ_ID, SL_PAIR_MM, SL_REF, SL_SPLITS,   // staged inputs
@@ -23,6 +24,8 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_PK_OFF, SL_PK_IDBASE, SL_PK_BQD, SL_PK_ESC_EVT, SL_PK_ESC_ID,                  // packed transfer format (K0 inputs)
     SL_K3_TILE_OFF, SL_PAIRS,
     SL_K4_CUM, SL_K4_CLON, SL_K4_STATE, SL_K4_HIST, SL_K4_OFF, SL_K4_OUT,
+    SL_RD_START, SL_RD_LEN, SL_RD_PAIR, SL_RD_WORD, SL_RD_WORDS, SL_RD_BOUNDS, SL_RD_NPOS, SL_RD_NPAIR,         // read-major batch (K1r inputs)
+    SL_RD_CAND, SL_RD_EVOFF, SL_RD_EVB, SL_RD_EVQ, SL_RD_EVID,                          // K3 site events from segments
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
     SL_COUNT
 };
@@ -106,6 +109,32 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
                   int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap);
+// read-major batch, device pointers (+ the per-tile segment bounds isb_k1r_launch computes)
+#define K1R_TILE 1024                 // positions per K1r block; also the granularity of the K3 candidate search
+struct isb_reads_dev {
+    int64_t n_segs;
+    const int32_t *seg_start;
+    const uint16_t *seg_len;
+    const int32_t *seg_pair;
+    const int64_t *seg_word;
+    int64_t n_words;
+    const uint32_t *words;
+    int32_t max_seg_len;
+    int64_t n_nev;                    // passing non-ACGT read bases (nmask only)
+    const int32_t *nev_pos;
+    const int32_t *nev_pair;
+    int n_tiles;
+    const int64_t *tile_lo;           // [n_tiles] first segment with seg_start > tile_first - max_seg_len
+    const int64_t *tile_hi;           // [n_tiles] first segment with seg_start >= tile_first + K1R_TILE
+    const int64_t *tile_wlo;          // [n_tiles] word range [wlo, whi) of those segments incl. both separators
+    const int64_t *tile_whi;
+};
+int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
+                   int M, int32_t *counts, unsigned long long *nmask);
+int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
+                        int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                        const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
+                        int64_t cap);
 int isb_ensure(isb_ctx *ctx, int slot, size_t bytes);
 int isb_k2_selftest_division(isb_ctx *ctx, int s_lo, int s_hi, unsigned long long *h_mismatches);
 int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const unsigned long long *nmask,

@@ -1,0 +1,399 @@
+// isb_k1r_reads.cu -- K1r: pileup counts straight from READ-MAJOR aligned segments, sm_100a.
+//
+// Same result as K1 (isb_k1_pileup.cu): counts[position][mm][A,C,T,G] (+ nmask) of samfile.pileup(...) column iteration
+// (inStrain/profile/profile_utilities.py:150-153) + get_base_counts_mm (:268-286) -- but the input is one 4-bit code per
+// aligned base, stored once per READ (include/instrain_b200.h, isb_reads_batch), not one 10-byte event per column entry.
+// The pileup is a transposition (reads x offsets -> positions), done here on the fly without atomics:
+//
+//   * a block owns a tile of K1R_TILE = 1024 positions, a thread 8 consecutive positions (one 32-bit word of nibbles);
+//   * the segments that can touch the tile (seg_start in (tile_first - max_seg_len, tile_end), a contiguous range of the
+//     start-sorted segment table: k1r_tile_bounds) are staged chunk by chunk in shared memory -- start / length / word
+//     offset by the threads, the nibble words of the chunk (contiguous in the stream) by ONE TMA 1-D bulk copy;
+//   * each thread binary-searches its own candidate range in the chunk and, per candidate, funnel-shifts the two
+//     words that hold its 8 positions into one register.  Because consecutive segments are separated by a zero word
+//     and codes of non-events are 0, no per-nibble bounds checks are needed;
+//   * counting is bit-sliced.  The codes are one-hot (A=1, C=2, T=4, G=8), so the 32 bits of that register are the 32
+//     (position, base) indicator bits of the candidate.  M = 1: they are added into eight VERTICAL counter planes
+//     (plane j = bit j of 32 independent counters) with a Harley-Seal carry-save tree, 8 candidates per block:
+//     7 CSAs + a 5-plane ripple = 24 logic ops per 8 candidates, instead of ~11 per candidate for per-base masks
+//     and horizontal adds.  The planes are turned into integers once per <= 248 candidates.
+//     M > 1 keeps horizontal 8-bit counters per (mm level, base) in shared memory, laid out [word][thread] so that
+//     every lane always hits its own bank, and flushes them to the thread's own cells of `counts` (plain stores).
+//
+// HBM traffic: 0.5 B per aligned base + ~22 B per segment in, 16*M B per position out (vs 6-10 B per event in for K1).
+// The kernel is bound by issue slots / shared-memory bandwidth, not by HBM (profiles/README.md).
+#include "isb_common.cuh"
+
+#define K1R_THREADS 128
+#define K1R_MAXLEN 256                 // hard cap of max_seg_len
+#define K1R_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
+#define K1R_WPS (K1R_MAXLEN / 8 + 1)   // worst-case words per segment incl. its separator
+
+struct k1r_args {
+    isb_reads_dev rd;
+    const uint8_t *pair_mm;
+    int64_t n_pairs;
+    int32_t start, L;
+    int M;
+    int seg_cap;                       // segments staged per chunk (shared-memory budget / bytes per segment)
+    int words_cap;                     // words staged per chunk: seg_cap * (max_seg_len / 8 + 2) + 8
+    int32_t *counts;
+    unsigned long long *nmask;
+    unsigned int *d_err;
+};
+
+// tile t covers relative positions [t*K1R_TILE, (t+1)*K1R_TILE): its candidate segment range and their word range
+__global__ void __launch_bounds__(256)
+k1r_tile_bounds(const int32_t *__restrict__ seg_start, const uint16_t *__restrict__ seg_len,
+                const int64_t *__restrict__ seg_word, int64_t n_segs, int32_t start, int n_tiles, int max_seg_len,
+                int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi, int64_t *__restrict__ tile_wlo,
+                int64_t *__restrict__ tile_whi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int64_t first = (int64_t)start + (int64_t)t * K1R_TILE;
+    const int64_t lo = isb_lower_bound(seg_start, 0, n_segs, first - max_seg_len + 1);
+    const int64_t hi = isb_lower_bound(seg_start, lo, n_segs, first + K1R_TILE);
+    tile_lo[t] = lo;
+    tile_hi[t] = hi;
+    tile_wlo[t] = hi > lo ? seg_word[lo] - 1 : 0;
+    tile_whi[t] = hi > lo ? seg_word[hi - 1] + ((seg_len[hi - 1] + 7) >> 3) + 1 : 0;
+}
+
+// carry-save adder on 32 independent bit lanes: h = majority(a, b, c), l = a ^ b ^ c (one LOP3 each)
+#define K1R_CSA(h, l, a, b, c)                       \
+    {                                                \
+        const uint32_t u_ = (a) ^ (b);               \
+        const uint32_t h_ = ((a) & (b)) | (u_ & (c)); \
+        l = u_ ^ (c);                                \
+        h = h_;                                      \
+    }
+
+// 8-bit -> 32-bit: byte j of `lo` counts position 2j, byte j of `hi` position 2j+1
+__device__ __forceinline__ void k1r_widen(int (&c)[8][4], int b, uint32_t lo, uint32_t hi)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        c[2 * j][b] += (int)((lo >> (8 * j)) & 0xffu);
+        c[2 * j + 1][b] += (int)((hi >> (8 * j)) & 0xffu);
+    }
+}
+
+// Vertical (bit-sliced) counters -> per-(position, base) integers.  Plane j holds bit j of 32 independent counters, bit
+// lane 4k + b = (position k, base b).  Per base, the eight lanes are pulled out as 0/1 bytes of two words (even / odd
+// positions) and summed with weight 2^j, then widened.
+__device__ __forceinline__ void k1r_planes_to_counts(int (&c)[8][4], uint32_t (&pl)[8])
+{
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            lo += ((pl[j] >> b) & 0x01010101u) << j;
+            hi += ((pl[j] >> (b + 4)) & 0x01010101u) << j;
+        }
+        k1r_widen(c, b, lo, hi);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pl[j] = 0u;
+}
+
+// Harley-Seal block: eight 1-bit inputs per lane into the planes with 7 carry-save adders + one 5-plane ripple
+__device__ __forceinline__ void k1r_add8(uint32_t (&pl)[8], const uint32_t (&x)[8])
+{
+    uint32_t t2a, t2b, t4a, t4b, t8;
+    K1R_CSA(t2a, pl[0], pl[0], x[0], x[1]);
+    K1R_CSA(t2b, pl[0], pl[0], x[2], x[3]);
+    K1R_CSA(t4a, pl[1], pl[1], t2a, t2b);
+    K1R_CSA(t2a, pl[0], pl[0], x[4], x[5]);
+    K1R_CSA(t2b, pl[0], pl[0], x[6], x[7]);
+    K1R_CSA(t4b, pl[1], pl[1], t2a, t2b);
+    K1R_CSA(t8, pl[2], pl[2], t4a, t4b);
+#pragma unroll
+    for (int j = 3; j < 8; ++j) {
+        const uint32_t cy = pl[j] & t8;
+        pl[j] ^= t8;
+        t8 = cy;
+    }
+}
+
+// M > 1: write (or add, once counts hold a partial sum) the thread's shared 8-bit counters to its cells of `counts`
+__device__ __forceinline__ void k1r_flush_levels(const k1r_args &a, uint32_t *s_acc, int t, int Mg, int m_base, int32_t P,
+                                                 bool add, bool clear)
+{
+    int4 *c4 = reinterpret_cast<int4 *>(a.counts);
+    for (int m = 0; m < Mg; ++m) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            w8[j] = s_acc[(size_t)(m * 8 + j) * K1R_THREADS + t];
+            if (clear) s_acc[(size_t)(m * 8 + j) * K1R_THREADS + t] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (P + k >= a.L) break;
+            const int sh = (k >> 1) * 8, h = k & 1;
+            int4 val;
+            val.x = (w8[0 + h] >> sh) & 0xff; val.y = (w8[2 + h] >> sh) & 0xff;
+            val.z = (w8[4 + h] >> sh) & 0xff; val.w = (w8[6 + h] >> sh) & 0xff;
+            int4 *dst = c4 + ((size_t)(P + k) * a.M + m_base + m);
+            if (add) { const int4 o = *dst; val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w; }
+            *dst = val;
+        }
+    }
+}
+
+template <bool kM1>
+__global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
+{
+    extern __shared__ __align__(128) unsigned char k1r_smem_raw[];
+    uint32_t *s_words = reinterpret_cast<uint32_t *>(k1r_smem_raw);
+    int2 *s_meta = reinterpret_cast<int2 *>(s_words + a.words_cap);     // x: nibble address of relative position 0, y: end
+    int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);  // relative start (sorted): the candidate search key
+    uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k1r_smem_raw + (((size_t)a.words_cap * 4 + (size_t)a.seg_cap * 13 + 7) & ~(size_t)7));
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bar) + 16);
+
+    const int t = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int32_t P = tile * K1R_TILE + t * 8;                  // first of the thread's 8 positions (relative)
+    const bool active = P < a.L;
+    const int maxlen = a.rd.max_seg_len;
+    const int64_t lo = a.rd.tile_lo[tile], hi = a.rd.tile_hi[tile];
+    const int m_base = kM1 ? 0 : (int)blockIdx.y * K1R_LEVELS;
+    const int Mg = kM1 ? 1 : min(K1R_LEVELS, a.M - m_base);
+
+    int c[8][4];                                                  // M = 1: the thread's 32 counters
+    uint32_t pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};            // M = 1: vertical counter planes (weights 1 .. 128)
+    int n8 = 0;                                                   // candidates since the last flush (counters hold <= 255)
+    bool spilled = false;                                         // M > 1: counts already hold a partial sum
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[k][b] = 0;
+    if (!kM1)
+        for (int w = 0; w < Mg * 8; ++w) s_acc[w * K1R_THREADS + t] = 0u;
+    if (t == 0) {
+        isb_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned parity = 0;
+    unsigned err = 0;
+
+    for (int64_t c0 = lo; c0 < hi; c0 += a.seg_cap) {
+        const int nc = (int)min((int64_t)a.seg_cap, hi - c0);
+        __syncthreads();                                          // previous chunk consumed (first pass: mbarrier init visible)
+        const int64_t last = c0 + nc - 1;
+        int64_t w_first, w_end;
+        if (c0 == lo && last == hi - 1) {                         // the usual case: the whole tile in one chunk
+            w_first = a.rd.tile_wlo[tile];
+            w_end = a.rd.tile_whi[tile];
+        } else {
+            w_first = __ldg(a.rd.seg_word + c0) - 1;              // the separator in front of the chunk's first segment
+            w_end = __ldg(a.rd.seg_word + last) + ((__ldg(a.rd.seg_len + last) + 7) >> 3) + 1;
+        }
+        const int64_t wb = w_first & ~(int64_t)3;                 // 16-byte aligned source
+        const int64_t wn = ((w_end - wb) + 3) & ~(int64_t)3;
+        if (w_first < 0 || wn <= 0 || wn > a.words_cap || wb + wn > a.rd.n_words) {   // layout rules violated (uniform)
+            err |= ISB_DEV_ERR_SEG;
+            continue;
+        }
+        if (t == 0) {
+            isb_mbar_expect_tx(bar, (unsigned)wn * 4u);
+            isb_bulk_g2s(s_words, a.rd.words + wb, (unsigned)wn * 4u, bar);
+        }
+        for (int i = t; i < nc; i += K1R_THREADS) {
+            const int64_t g = c0 + i;
+            const int32_t s_abs = __ldg(a.rd.seg_start + g);
+            const int32_t s = s_abs - a.start;
+            const int n = __ldg(a.rd.seg_len + g);
+            const int64_t w = __ldg(a.rd.seg_word + g);
+            const int64_t wl = w - wb;
+            if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + ((n + 7) >> 3) + 1 > wn ||
+                (g > 0 && __ldg(a.rd.seg_start + g - 1) > s_abs))
+                err |= ISB_DEV_ERR_SEG;
+            const int n_c = min(max(n, 0), maxlen);
+            const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
+            s_meta[i] = make_int2(wl_c * 8 - s, s + n_c);         // nibble address of position p = x + p; covered while p < y
+            s_start[i] = s;
+            if (!kM1) {
+                const int32_t pid = __ldg(a.rd.seg_pair + g);
+                int mm = 255;
+                if (pid >= 0 && (int64_t)pid < a.n_pairs) mm = __ldg(a.pair_mm + pid);
+                if (mm >= a.M) { err |= ISB_DEV_ERR_MM; mm = 255; }
+                s_mm[i] = (uint8_t)mm;
+            }
+        }
+        __syncthreads();
+        isb_mbar_wait(bar, parity);
+        parity ^= 1u;
+        if (!active) continue;
+
+        // candidates of this thread inside the chunk: seg_start in (P - maxlen, P + 8)
+        int cl, ch;
+        {
+            int l = 0, h = nc;
+            const int key = P - maxlen + 1;
+            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key) l = mid + 1; else h = mid; }
+            cl = l;
+            h = nc;
+            const int key2 = P + 8;
+            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key2) l = mid + 1; else h = mid; }
+            ch = l;
+        }
+        // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach)
+        auto fetch = [&](int i) -> uint32_t {
+            const int2 md = s_meta[i];
+            const int na = md.x + P;                               // nibble address of position P in the staged words
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(s_words) +
+                                                                   ((na >> 1) & ~3));
+            const uint32_t x = __funnelshift_r(w[0], w[1], na << 2);
+            return P < md.y ? x : 0u;                              // short segment: those words belong to a later one
+        };
+        if (kM1) {
+            int i = cl;
+            for (; i + 8 <= ch; i += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = fetch(i + u);
+                k1r_add8(pl, x);
+                n8 += 8;
+                if (n8 > 247) {                                    // the next block could overflow 255
+                    k1r_planes_to_counts(c, pl);
+                    n8 = 0;
+                }
+            }
+            if (i < ch) {
+                uint32_t x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (i + u < ch) ? fetch(min(i + u, ch - 1)) : 0u;
+                k1r_add8(pl, x);
+                n8 += 8;
+                if (n8 > 247) {
+                    k1r_planes_to_counts(c, pl);
+                    n8 = 0;
+                }
+            }
+        } else {
+            for (int i = cl; i < ch;) {
+                const int g_end = min(ch, i + 15);
+                n8 += g_end - i;
+                for (; i < g_end; ++i) {
+                    const uint32_t x = fetch(i);
+                    const int lv = (int)s_mm[i] - m_base;
+                    if ((unsigned)lv < (unsigned)Mg) {             // 8-bit counters per (level, base, even/odd position)
+                        uint32_t *acc = s_acc + (size_t)(lv * 8) * K1R_THREADS + t;
+                        acc[0 * K1R_THREADS] += x & 0x01010101u;
+                        acc[1 * K1R_THREADS] += (x >> 4) & 0x01010101u;
+                        acc[2 * K1R_THREADS] += (x >> 1) & 0x01010101u;
+                        acc[3 * K1R_THREADS] += (x >> 5) & 0x01010101u;
+                        acc[4 * K1R_THREADS] += (x >> 2) & 0x01010101u;
+                        acc[5 * K1R_THREADS] += (x >> 6) & 0x01010101u;
+                        acc[6 * K1R_THREADS] += (x >> 3) & 0x01010101u;
+                        acc[7 * K1R_THREADS] += (x >> 7) & 0x01010101u;
+                    }
+                }
+                if (n8 > 240) {                                    // flush before a byte can overflow
+                    k1r_flush_levels(a, s_acc, t, Mg, m_base, P, spilled, true);
+                    spilled = true;
+                    n8 = 0;
+                }
+            }
+        }
+    }
+    if (err) atomicOr(a.d_err, err);
+    if (!active) return;
+
+    if (kM1) {
+        k1r_planes_to_counts(c, pl);
+        int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (P + k >= a.L) break;
+            c4[k] = make_int4(c[k][0], c[k][1], c[k][2], c[k][3]);
+        }
+    } else {
+        k1r_flush_levels(a, s_acc, t, Mg, m_base, P, spilled, false);
+    }
+}
+
+// passing non-ACGT read bases ("N events"): the level becomes a key of the position's MMcounts (nmask bit), nothing else
+__global__ void __launch_bounds__(256)
+k1r_n_events(int64_t n_nev, const int32_t *__restrict__ nev_pos, const int32_t *__restrict__ nev_pair,
+             const uint8_t *__restrict__ pair_mm, int64_t n_pairs, int32_t start, int32_t L, int M,
+             unsigned long long *__restrict__ nmask, unsigned int *__restrict__ d_err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nev) return;
+    const int64_t p = (int64_t)nev_pos[i] - start;
+    const int32_t pid = nev_pair[i];
+    if (p < 0 || p >= L || pid < 0 || pid >= n_pairs) { atomicOr(d_err, ISB_DEV_ERR_SEG); return; }
+    const int mm = M > 1 ? pair_mm[pid] : 0;
+    if (mm >= M) { atomicOr(d_err, ISB_DEV_ERR_MM); return; }
+    atomicOr(nmask + p, 1ull << mm);
+}
+
+int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
+                   int M, int32_t *counts, unsigned long long *nmask)
+{
+    cudaStream_t st = ctx->stream;
+    if (L <= 0) return ISB_OK;
+    if (rd->max_seg_len < 1 || rd->max_seg_len > K1R_MAXLEN)
+        return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: max_seg_len must be in [1, 256]");
+    if (M > 1 && !pair_mm) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: pair_mm is required when M > 1");
+    if (((uintptr_t)rd->words & 15) != 0) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: words must be 16-byte aligned");
+    const int n_tiles = (L + K1R_TILE - 1) / K1R_TILE;
+    int rc;
+    if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 4 * (size_t)n_tiles))) return rc;
+    int64_t *tile_lo = (int64_t *)ctx->buf[SL_RD_BOUNDS].p, *tile_hi = tile_lo + n_tiles;
+    int64_t *tile_wlo = tile_hi + n_tiles, *tile_whi = tile_wlo + n_tiles;
+    k1r_tile_bounds<<<(n_tiles + 255) / 256, 256, 0, st>>>(rd->seg_start, rd->seg_len, rd->seg_word, rd->n_segs, start, n_tiles,
+                                                           rd->max_seg_len, tile_lo, tile_hi, tile_wlo, tile_whi);
+    ISB_LAUNCH_CHECK();
+    rd->n_tiles = n_tiles;
+    rd->tile_lo = tile_lo;
+    rd->tile_hi = tile_hi;
+    rd->tile_wlo = tile_wlo;
+    rd->tile_whi = tile_whi;
+
+    k1r_args a;
+    a.rd = *rd; a.pair_mm = pair_mm; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = M; a.counts = counts;
+    a.nmask = nmask; a.d_err = ctx->d_err;
+    // Shared-memory budget: the staging area should hold the whole candidate set of a tile (then every thread works in
+    // every chunk); two blocks per SM.  Bytes per staged segment: its words incl. separator + 8 (meta) + 1 (mm).
+    const int wps = rd->max_seg_len / 8 + 2;
+    const size_t per_seg = (size_t)wps * 4 + 13;
+    const int groups = M == 1 ? 1 : (M + K1R_LEVELS - 1) / K1R_LEVELS;
+    const int Mg = M == 1 ? 0 : (M < K1R_LEVELS ? M : K1R_LEVELS);
+    const size_t acc_bytes = (size_t)Mg * 8 * K1R_THREADS * 4;
+    const size_t budget = (size_t)110 * 1024;
+    const size_t stage_budget = acc_bytes + 24 * 1024 < budget ? budget - acc_bytes : 24 * 1024;
+    int seg_cap = (int)((stage_budget - 64) / per_seg);
+    const int64_t avg_need = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1R_TILE + rd->max_seg_len) * 1.25) + 32 : 32;
+    if (seg_cap > avg_need) seg_cap = (int)avg_need;              // no point staging more than a tile ever holds
+    if (seg_cap < 64) seg_cap = 64;
+    a.seg_cap = seg_cap;
+    a.words_cap = (seg_cap * wps + 8 + 3) & ~3;
+    const size_t smem = (((size_t)a.words_cap * 4 + (size_t)seg_cap * 13 + 7) & ~(size_t)7) + 16 + acc_bytes;
+    static bool attr_m1[64] = {false}, attr_mm[64] = {false};      // function attributes are per device
+    if (nmask) ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
+    if (M == 1) {
+        if (!attr_m1[ctx->device & 63])
+            ISB_CUDA(cudaFuncSetAttribute(k1r_pileup<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_m1[ctx->device & 63] = true;
+        k1r_pileup<true><<<n_tiles, K1R_THREADS, smem, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    } else {
+        if (!attr_mm[ctx->device & 63])
+            ISB_CUDA(cudaFuncSetAttribute(k1r_pileup<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_mm[ctx->device & 63] = true;
+        k1r_pileup<false><<<dim3(n_tiles, groups), K1R_THREADS, smem, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    }
+    if (nmask && rd->n_nev > 0) {
+        k1r_n_events<<<(unsigned)((rd->n_nev + 255) / 256), 256, 0, st>>>(rd->n_nev, rd->nev_pos, rd->nev_pair, pair_mm,
+                                                                          n_pairs, start, L, M, nmask, ctx->d_err);
+        ISB_LAUNCH_CHECK();
+    }
+    return ISB_OK;
+}

@@ -82,6 +82,19 @@ __device__ __forceinline__ bool k3_qualifies(const k3_args &a, int64_t e, unsign
     return a.qual[e] >= a.min_qual && b < 4 && ((bases >> b) & 1u);
 }
 
+// split = last split whose start <= abs_pos, if abs_pos <= its end (else -1)
+__device__ __forceinline__ int k3_site_split(const k3_args &a, int64_t abs_pos)
+{
+    int s_lo = 0, s_hi = a.n_splits;
+    while (s_lo < s_hi) {
+        const int mid = (s_lo + s_hi) >> 1;
+        if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
+    }
+    int split = s_lo - 1;
+    if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
+    return split;
+}
+
 // ---- per-site event range, split --------------------------------------------------------------------------------
 // One THREAD per site: the two lower bounds are scalar binary searches bounded by the site's position tile
 // (tile_off from a k1_tile_offsets launch: ~1e5 events => 17 steps).  The searches are pure latency (dependent
@@ -99,15 +112,71 @@ __global__ void __launch_bounds__(256) k3_site_ranges(k3_args a)
     const int64_t hi = isb_lower_bound(a.ref_pos, lo, t_hi, abs_pos + 1);
     a.site_ev[2 * k] = lo;
     a.site_ev[2 * k + 1] = hi;
-    // split = last split whose start <= abs_pos, if abs_pos <= its end
-    int s_lo = 0, s_hi = a.n_splits;
-    while (s_lo < s_hi) {
-        const int mid = (s_lo + s_hi) >> 1;
-        if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
+    a.meta[k].split = k3_site_split(a, abs_pos);
+}
+
+// ---- read-major front end: the events of the eligible sites, materialised from the aligned segments ---------------
+// K3 only ever looks at the events of linkage-eligible sites (~1 % of the positions), so with a read-major batch the
+// (base, pair id) lists of exactly those sites are gathered from the segments that cover them into compact scratch
+// columns, and the rest of K3 runs unchanged on those.  One thread per site finds its candidate segments
+// (seg_start in (p - max_seg_len, p]) inside the site's K1r tile range; a scan sizes the scratch; one warp per site
+// then tests the candidates and writes the passing ones.
+__global__ void __launch_bounds__(256) k3r_site_cand(k3_args a, isb_reads_dev rd, int64_t *__restrict__ cand_lo,
+                                                     int32_t *__restrict__ n_cand)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.S) return;
+    const int32_t p = a.site_pos[k];
+    const int64_t abs_pos = (int64_t)p + a.start;
+    const int t = p / K1R_TILE;
+    const int64_t t_lo = rd.tile_lo[t], t_hi = rd.tile_hi[t];
+    const int64_t lo = isb_lower_bound(rd.seg_start, t_lo, t_hi, abs_pos - rd.max_seg_len + 1);
+    const int64_t hi = isb_lower_bound(rd.seg_start, lo, t_hi, abs_pos + 1);
+    cand_lo[k] = lo;
+    n_cand[k] = (int32_t)(hi - lo);
+    a.meta[k].split = k3_site_split(a, abs_pos);
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3r_site_fill(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
+                                                            const int32_t *__restrict__ n_cand,
+                                                            const int64_t *__restrict__ ev_off, uint8_t *__restrict__ ev_base,
+                                                            uint8_t *__restrict__ ev_qual, int32_t *__restrict__ ev_id)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
+    for (int64_t k = warp0; k < a.S; k += n_warps) {
+        const int64_t abs_pos = (int64_t)a.site_pos[k] + a.start;
+        const int64_t clo = cand_lo[k], off = ev_off[k];
+        const int nc = n_cand[k];
+        int cnt = 0;
+        for (int i0 = 0; i0 < nc; i0 += 32) {
+            const int i = i0 + lane;
+            bool ok = false;
+            int b = 0, id = 0;
+            if (i < nc) {
+                const int64_t g = clo + i;
+                const int j = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
+                if (j >= 0 && j < (int)__ldg(rd.seg_len + g)) {
+                    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (j >> 3));
+                    const uint32_t code = (w >> ((j & 7) << 2)) & 15u;
+                    if (code) { ok = true; b = __ffs((int)code) - 1; id = __ldg(rd.seg_pair + g); }   // one-hot A,C,T,G
+                }
+            }
+            const unsigned mask = __ballot_sync(ISB_FULL, ok);
+            if (ok) {
+                const int64_t e = off + cnt + __popc(mask & ((1u << lane) - 1u));
+                ev_base[e] = (uint8_t)b;
+                ev_qual[e] = 255;
+                ev_id[e] = id;
+            }
+            cnt += __popc(mask);
+        }
+        if (lane == 0) {
+            a.site_ev[2 * k] = off;
+            a.site_ev[2 * k + 1] = off + cnt;
+        }
     }
-    int split = s_lo - 1;
-    if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
-    a.meta[k].split = split;
 }
 
 // ---- per-site pair-id window (warp per site, coalesced) -----------------------------------------------------------
@@ -446,10 +515,11 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a)
     }
 }
 
-int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
-                  const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
-                  int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
-                  int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap)
+static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_t *ref_pos, const uint8_t *base,
+                  const uint8_t *qual, const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
+                  int32_t L, int M, int min_qual, const int32_t *counts, const unsigned long long *nmask,
+                  const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
+                  int64_t cap)
 {
     cudaStream_t st = ctx->stream;
     int rc;
@@ -457,7 +527,7 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     if (ctx->keep_counters) ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
     else ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), st));
     ctx->h_counters[2] = ctx->h_counters[3] = 0;
-    if (L <= 0 || n <= 0) return ISB_OK;
+    if (L <= 0 || (!rd && n <= 0) || (rd && rd->n_segs <= 0)) return ISB_OK;
 
     // 1. ordered list of linkage-eligible sites
     const int nb = (int)(((int64_t)L + SCAN_BLOCK - 1) / SCAN_BLOCK);
@@ -497,25 +567,52 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     a.out = rows; a.cap = cap;
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
 
-    // 2. per-site event range + pair-id window (searches bounded by position-tile event offsets)
-    {
+    // 2. per-site event range + pair-id window
+    const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;
+    const int grid_sites = (int)(site_warps_blocks < (int64_t)ctx->sm_count * 32 ? site_warps_blocks : (int64_t)ctx->sm_count * 32);
+    const int nbs = (int)((S + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)(nb > nbs ? nb : nbs)))) return rc;
+    block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
+    if (!rd) {                                                  // position-major columns: searches bounded by tile offsets
         const int tp = 1024;
         const int n_tiles = (L + tp - 1) / tp;
         if ((rc = isb_tile_offsets(ctx, ref_pos, n, start, L, tp, n_tiles))) return rc;
         a.tile_off = (const int64_t *)ctx->buf[SL_K3_TILE_OFF].p;
         a.tile_tp = tp;
+        k3_site_ranges<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    } else {                                                    // read-major segments: gather the sites' events
+        if ((rc = isb_ensure(ctx, SL_RD_CAND, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)S))) return rc;
+        if ((rc = isb_ensure(ctx, SL_RD_EVOFF, sizeof(int64_t) * (size_t)S))) return rc;
+        int64_t *cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
+        int32_t *n_cand = (int32_t *)(cand_lo + S);
+        int64_t *ev_off = (int64_t *)ctx->buf[SL_RD_EVOFF].p;
+        k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
+        ISB_LAUNCH_CHECK();
+        WordsFn cf{n_cand};
+        scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(cf, S, block_sums);
+        ISB_LAUNCH_CHECK();
+        scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nbs, ctx->d_counters + 6);
+        ISB_LAUNCH_CHECK();
+        RowOffSink eos{ev_off};
+        scan_scatter<<<nbs, SCAN_THREADS, 0, st>>>(cf, S, block_sums, eos);
+        ISB_LAUNCH_CHECK();
+        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaStreamSynchronize(st));
+        const size_t n_ev_cap = (size_t)ctx->h_counters[6] + 16;
+        if ((rc = isb_ensure(ctx, SL_RD_EVB, n_ev_cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_RD_EVQ, n_ev_cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_RD_EVID, sizeof(int32_t) * n_ev_cap))) return rc;
+        uint8_t *ev_base = (uint8_t *)ctx->buf[SL_RD_EVB].p, *ev_qual = (uint8_t *)ctx->buf[SL_RD_EVQ].p;
+        int32_t *ev_id = (int32_t *)ctx->buf[SL_RD_EVID].p;
+        k3r_site_fill<<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cand_lo, n_cand, ev_off, ev_base, ev_qual, ev_id);
+        ISB_LAUNCH_CHECK();
+        a.base = ev_base; a.qual = ev_qual; a.read_id = ev_id; a.min_qual = 0;
     }
-    const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;
-    const int grid_sites = (int)(site_warps_blocks < (int64_t)ctx->sm_count * 32 ? site_warps_blocks : (int64_t)ctx->sm_count * 32);
-    k3_site_ranges<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
-    ISB_LAUNCH_CHECK();
     k3_site_windows<<<grid_sites, K3_THREADS, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
 
     // 3. bit-row storage offsets
-    const int nbs = (int)((S + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)(nb > nbs ? nb : nbs)))) return rc;
-    block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
     WordsFn wf{a.site_words};
     scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums);
     ISB_LAUNCH_CHECK();
@@ -571,4 +668,22 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
     k3_self_edges<<<grid_self, 128, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
+}
+
+int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
+                  const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
+                  int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
+                  int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap)
+{
+    return k3_run(ctx, nullptr, n, ref_pos, base, qual, read_id, n_pairs, pair_mm, start, L, M, min_qual, counts, nmask,
+                  site_flags, n_splits, splits, min_snp, rows, cap);
+}
+
+int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
+                        int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                        const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
+                        int64_t cap)
+{
+    return k3_run(ctx, rd, 0, nullptr, nullptr, nullptr, nullptr, n_pairs, pair_mm, start, L, M, 0, counts, nmask,
+                  site_flags, n_splits, splits, min_snp, rows, cap);
 }

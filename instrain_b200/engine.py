@@ -91,6 +91,25 @@ class Engine:
         return counts, nmask
 
     # ---- stage K2 ----------------------------------------------------------------------------------------------
+    def _reads_batch(self, rd, pair_mm, start, L, ref_codes, splits, M):
+        p = _cabi.ptr
+        n_pairs = len(pair_mm) if pair_mm is not None else 0
+        return _cabi.IsbReadsBatch(int(rd["n_segs"]), p(rd["seg_start"]), p(rd["seg_len"]), p(rd["seg_pair"]),
+                                   p(rd["seg_word"]), int(rd["n_words"]), p(rd["words"]), int(rd["max_seg_len"]), 0,
+                                   len(rd["nev_pos"]), p(rd["nev_pos"]), p(rd["nev_pair"]), n_pairs, p(pair_mm), start, L, p(ref_codes), 0 if splits is None else len(splits),
+                                   p(splits), M, 0)
+
+    def pileup_reads(self, rd, pair_mm, start, L, M, counts=None, nmask=None):
+        """K1r alone: counts[L, M, 4] (+ nmask[L]) from a read-major batch (instrain_b200.reads)."""
+        pair_mm = _pair_mm_u8(pair_mm)
+        if counts is None:
+            counts = np.empty((L, M, 4), dtype=np.int32)
+        if nmask is None:
+            nmask = np.empty(L, dtype=np.uint64)
+        batch = self._reads_batch(rd, pair_mm, start, L, None, None, M)
+        self._check(self.lib.isb_pileup_reads(self.ctx, C.byref(batch), _cabi.ptr(counts), _cabi.ptr(nmask)))
+        return counts, nmask
+
     def call_snvs(self, counts, nmask, ref_codes, start=0, min_cov=5, min_freq=0.05, cap=None):
         L, M = counts.shape[0], counts.shape[1]
         covT = np.empty((L, M), dtype=np.int32)
@@ -143,7 +162,7 @@ class Engine:
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
-                      snv_cap=None, ld_cap=None, packed=None, pipeline=False):
+                      snv_cap=None, ld_cap=None, packed=None, pipeline=False, reads=None):
         """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
 
         `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
@@ -156,7 +175,10 @@ class Engine:
             raise ValueError("mm levels M=%d exceeds ISB_MAX_MM=%d" % (M, _cabi.ISB_MAX_MM))
         splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
         p = _cabi.ptr
-        if packed is not None:                     # packed transfer format (instrain_b200.packed.encode_packed)
+        if reads is not None:                      # read-major aligned segments (instrain_b200.reads)
+            batch = self._reads_batch(reads, pair_mm, start, L, ref_codes, splits, M)
+            entry = self.lib.isb_profile_reads
+        elif packed is not None:                   # packed transfer format (instrain_b200.packed.encode_packed)
             if packed["min_qual"] != min_qual:
                 raise ValueError("packed batch was encoded with min_qual=%d" % packed["min_qual"])
             batch = _cabi.IsbPackedBatch(packed["n_events"], p(packed["pos_off"]), p(packed["id_base"]), p(packed["bqd"]),

@@ -1,0 +1,111 @@
+"""Read-major batch ("aligned segments") -- host-side encoders for isb_profile_reads / isb_pileup_reads.
+
+Layout and rules: include/instrain_b200.h (isb_reads_batch).  One 4-bit ONE-HOT code per aligned base, stored once per
+read: A=1, C=2, T=4, G=8 for a base that is an event (quality >= min_qual after htslib's mate-overlap tweak), 0 otherwise;
+passing non-ACGT bases go to the separate (nev_pos, nev_pair) list.
+
+`events_to_reads` rebuilds segments from position-major event columns (what the test fixtures and the oracle use):
+the events of a pair form runs of consecutive positions; a pair that enters the same column twice (both mates, htslib's
+overlap quirk) gets its second entries in a second layer of runs.  `build_reads` assembles the arrays from segments.
+"""
+import numpy as np
+
+MAX_SEG_LEN = 256
+
+
+NO_EVENT = 255
+
+
+def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_SEG_LEN):
+    """seg_*: per-segment arrays in ANY order; codes: one uint8 per aligned base of all segments -- 0..3 = A,C,T,G event,
+    4 = passing non-ACGT base, NO_EVENT (255) = not an event -- segment i occupying codes[code_off[i] : code_off[i] +
+    seg_len[i]] (default: back to back).  Splits segments longer than MAX_SEG_LEN, sorts by start (stable), lays out the
+    word stream and the N-event list."""
+    seg_start = np.asarray(seg_start, dtype=np.int64)
+    seg_len = np.asarray(seg_len, dtype=np.int64)
+    seg_pair = np.asarray(seg_pair, dtype=np.int64)
+    codes = np.asarray(codes, dtype=np.uint8)
+    if code_off is None:
+        code_off = np.concatenate([[0], np.cumsum(seg_len)[:-1]]) if len(seg_len) else np.zeros(0, np.int64)
+    code_off = np.asarray(code_off, dtype=np.int64)
+    if not 1 <= max_len <= MAX_SEG_LEN:
+        raise ValueError("max_len must be in [1, %d]" % MAX_SEG_LEN)
+    if len(seg_len) and seg_len.max() > max_len:                           # split long blocks
+        MAX_SEG_LEN_ = max_len
+        n_parts = (seg_len + MAX_SEG_LEN_ - 1) // MAX_SEG_LEN_
+        rep = np.repeat(np.arange(len(seg_len)), n_parts)
+        part = np.arange(len(rep)) - np.repeat(np.cumsum(n_parts) - n_parts, n_parts)
+        seg_start, seg_pair = seg_start[rep] + part * MAX_SEG_LEN_, seg_pair[rep]
+        code_off = code_off[rep] + part * MAX_SEG_LEN_
+        seg_len = np.minimum(seg_len[rep] - part * MAX_SEG_LEN_, MAX_SEG_LEN_)
+    order = np.argsort(seg_start, kind="stable")
+    seg_start, seg_len, seg_pair, code_off = seg_start[order], seg_len[order], seg_pair[order], code_off[order]
+    n = len(seg_start)
+    nw = (seg_len + 7) // 8
+    seg_word = np.ones(n, dtype=np.int64)
+    if n:
+        seg_word[1:] = 1 + np.cumsum(nw[:-1] + 1)
+    n_words = int(seg_word[-1] + nw[-1] + 1) if n else 1
+    n_words = (n_words + 3) // 4 * 4
+    # nibble j of segment i -> word seg_word[i] + j // 8, bits 4 * (j % 8)
+    tot = int(seg_len.sum())
+    seg_of = np.repeat(np.arange(n), seg_len)
+    j = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len)
+    c = codes[np.repeat(code_off, seg_len) + j]
+    onehot = np.where(c < 4, np.uint8(1) << np.minimum(c, 3), 0).astype(np.uint8)
+    is_n = c == 4
+    nev_pos = (np.repeat(seg_start, seg_len) + j)[is_n]
+    nev_pair = np.repeat(seg_pair, seg_len)[is_n]
+    nib = np.zeros(n_words * 8, dtype=np.uint8)
+    nib[(np.repeat(seg_word, seg_len) * 8 + j)] = onehot
+    nib = nib.reshape(-1, 8).astype(np.uint32)
+    words = np.zeros(n_words, dtype=np.uint32)
+    for k in range(8):
+        words |= nib[:, k] << np.uint32(4 * k)
+    return dict(n_segs=n, seg_start=seg_start.astype(np.int32), seg_len=seg_len.astype(np.uint16),
+                seg_pair=seg_pair.astype(np.int32), seg_word=seg_word, n_words=n_words, words=words,
+                max_seg_len=int(seg_len.max()) if n else 1, nev_pos=nev_pos.astype(np.int32),
+                nev_pair=nev_pair.astype(np.int32))
+
+
+def events_to_reads(ev, min_qual=30, max_len=MAX_SEG_LEN):
+    """Position-major (or any-order) event columns -> read-major batch arrays.  Events below min_qual keep their place in
+    their run as NO_EVENT."""
+    pos = np.asarray(ev["ref_pos"], dtype=np.int64)
+    rid = np.asarray(ev["read_id"], dtype=np.int64)
+    base = np.minimum(np.asarray(ev["base"]), 4).astype(np.uint8)
+    ok = np.asarray(ev["qual"]) >= min_qual
+    n = len(pos)
+    if n == 0:
+        return build_reads([], [], [], [])
+    order = np.lexsort((pos, rid))                                        # by pair, then position (stable)
+    pos, rid, base, ok = pos[order], rid[order], base[order], ok[order]
+    same = np.zeros(n, dtype=bool)
+    same[1:] = (rid[1:] == rid[:-1]) & (pos[1:] == pos[:-1])
+    # layer = index of the event among the events of its (pair, position)
+    grp_start = np.maximum.accumulate(np.where(~same, np.arange(n), 0))
+    layer = np.arange(n) - grp_start
+    order2 = np.lexsort((pos, layer, rid))
+    pos, rid, base, ok, layer = pos[order2], rid[order2], base[order2], ok[order2], layer[order2]
+    brk = np.ones(n, dtype=bool)
+    brk[1:] = (rid[1:] != rid[:-1]) | (layer[1:] != layer[:-1]) | (pos[1:] != pos[:-1] + 1)
+    starts = np.nonzero(brk)[0]
+    seg_len = np.diff(np.append(starts, n))
+    codes = np.where(ok, base, NO_EVENT).astype(np.uint8)
+    return build_reads(pos[starts], seg_len, rid[starts], codes, starts, max_len)
+
+
+def reads_to_events(rd, min_qual=30):
+    """Inverse view for tests: the passing events (position-major) a read-major batch encodes."""
+    seg_len = rd["seg_len"].astype(np.int64)
+    tot = int(seg_len.sum())
+    j = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len)
+    w = rd["words"][np.repeat(rd["seg_word"], seg_len) + j // 8]
+    code = (w >> (4 * (j % 8)).astype(np.uint32)) & 15
+    keep = code != 0
+    pos = np.concatenate([(np.repeat(rd["seg_start"].astype(np.int64), seg_len) + j)[keep], rd["nev_pos"].astype(np.int64)])
+    rid = np.concatenate([np.repeat(rd["seg_pair"], seg_len)[keep], rd["nev_pair"]])
+    base = np.concatenate([np.log2(code[keep]).astype(np.uint8), np.full(len(rd["nev_pos"]), 4, np.uint8)])
+    order = np.lexsort((rid, pos))
+    return dict(ref_pos=pos[order].astype(np.int32), base=base[order], qual=np.full(len(order), 255, np.uint8),
+                read_id=rid[order].astype(np.int32))

@@ -1,0 +1,153 @@
+"""GPU parity of the READ-MAJOR path (isb_pileup_reads / isb_profile_reads: K1r -> K2 -> K3 with site events gathered
+from the aligned segments) against the oracle on the event columns the segments encode, against the reference's golden
+tables, and against the position-major CUDA path."""
+import numpy as np
+import pytest
+
+from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from oracle import restate, synth
+from instrain_b200 import reads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(null_lut):
+    from instrain_b200.engine import Engine
+    e = Engine(0, null_lut[0], null_lut[1])
+    yield e
+    e.close()
+
+
+def check_reads(eng, batch, null_lut, tol=1e-9, rd=None, **kw):
+    exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"], **kw)
+    M = exp["counts"].shape[1]
+    if rd is None:
+        rd = reads.events_to_reads(batch, kw.get("min_qual", 30))
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, reads=rd,
+                            want=("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld"), **kw)
+    assert np.array_equal(got["counts"], exp["counts"])
+    assert np.array_equal(got["nmask"], exp["nmask"])
+    assert np.array_equal(got["covT"], exp["covT"])
+    ok = ~np.isnan(exp["clonT"])
+    assert np.array_equal(np.isnan(got["clonT"]), ~ok)
+    assert np.array_equal(got["clonT"][ok].view(np.uint32), exp["clonT"][ok].view(np.uint32))
+    assert np.array_equal(got["site_flags"], exp["site_flags"])
+    assert_snv_equal(got["snv"], exp["snv"])
+    assert_ld_equal(got["ld"], exp["ld"], tol=tol)
+    return got, exp
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_golden_tables_read_major(eng, which, null_lut):
+    """Segments rebuilt from the golden event columns reproduce the reference's raw_snp_table / raw_linkage_table."""
+    from test_oracle_golden import expected_rows
+    batch, exp = load_batch(which)
+    got, _ = check_reads(eng, batch, null_lut)
+    snv, ld = expected_rows(exp, batch["ref_codes"])
+    assert_snv_equal(got["snv"], snv)
+    assert_ld_equal(got["ld"], ld, tol=1e-6)
+
+
+@pytest.mark.parametrize("L,cov,dens,nsc,skip_mm,n_frac,seed", [
+    (30000, 50, 0.01, 2, False, 0.0, 20260102),
+    (30000, 50, 0.01, 1, True, 0.0, 20260102),
+    (12000, 100, 0.05, 1, False, 0.002, 20260105),   # non-ACGT read bases -> nmask
+    (12000, 100, 0.05, 1, True, 0.002, 20260105),    # same at M = 1
+    (700, 30, 0.02, 3, False, 0.0, 7),
+    (25000, 8, 0.01, 1, False, 0.0, 11),
+    (9000, 400, 0.01, 1, True, 0.0, 3),              # > 255 candidates per position: 8 -> 32 bit widening, several chunks
+    (9000, 400, 0.01, 1, False, 0.0, 3),             # same through the shared-memory counters (mid-run flush)
+])
+def test_synthetic_parity_read_major(eng, null_lut, L, cov, dens, nsc, skip_mm, n_frac, seed):
+    batch = synth.make_batch(L, cov, dens, seed, n_scaffolds=nsc, skip_mm=skip_mm, n_frac=n_frac)
+    check_reads(eng, batch, null_lut)
+
+
+def test_pileup_reads_stage(eng, null_lut):
+    batch, _ = load_batch("G1")
+    exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"], do_linkage=False)
+    L, M = exp["counts"].shape[:2]
+    rd = reads.events_to_reads(batch)
+    counts, nmask = eng.pileup_reads(rd, batch["pair_mm"], 0, L, M)
+    assert np.array_equal(counts, exp["counts"]) and np.array_equal(nmask, exp["nmask"])
+
+
+def test_many_mm_levels(eng, null_lut):
+    """M > 32: the shared-memory level groups of K1r (two passes over the candidates)."""
+    batch = synth.make_batch(6000, 60, 0.02, 5, skip_mm=False)
+    rng = np.random.default_rng(0)
+    batch["pair_mm"] = rng.integers(0, 50, len(batch["pair_mm"])).astype(batch["pair_mm"].dtype)
+    check_reads(eng, batch, null_lut)
+
+
+def test_short_and_split_segments(eng, null_lut):
+    """Segments of every length 1..40 plus blocks longer than 256 (split by the encoder), starts clustered."""
+    rng = np.random.default_rng(4)
+    L = 5000
+    starts, lens, pairs, codes = [], [], [], []
+    for i in range(3000):
+        n = int(rng.integers(1, 41)) if i % 7 else int(rng.integers(257, 700))
+        s = int(rng.integers(0, L - n))
+        starts.append(s); lens.append(n); pairs.append(i // 2)
+        c = rng.integers(0, 5, n).astype(np.uint8)
+        c[rng.random(n) < 0.2] = reads.NO_EVENT
+        codes.append(c)
+    rd = reads.build_reads(starts, lens, pairs, np.concatenate(codes))
+    assert rd["max_seg_len"] == 256
+    ev = reads.reads_to_events(rd)
+    n_pairs = 1500
+    ev["pair_mm"] = rng.integers(0, 6, n_pairs).astype(np.uint8)
+    ev["ref_codes"] = rng.integers(0, 4, L).astype(np.uint8)
+    ev["splits"] = np.array([[0, L - 1]], dtype=np.int32)
+    check_reads(eng, ev, null_lut, rd=rd)
+    ev["pair_mm"][:] = 0
+    check_reads(eng, ev, null_lut, rd=rd)
+
+
+def test_empty_and_sparse(eng, null_lut):
+    L = 3000
+    ref = np.zeros(L, np.uint8)
+    rd = reads.build_reads([], [], [], [])
+    got = eng.profile_batch(dict(pair_mm=np.zeros(0, np.uint8)), ref, np.array([[0, L - 1]], np.int32), M=1, reads=rd,
+                            want=("counts", "covT", "snv", "ld"))
+    assert got["counts"].sum() == 0 and got["n_snv"] == 0 and got["n_ld"] == 0
+    rd = reads.build_reads([2990], [10], [0], np.full(10, 2, np.uint8))     # one segment touching the last position
+    counts, nmask = eng.pileup_reads(rd, np.zeros(1, np.uint8), 0, L, 1)
+    assert counts[2990:, 0, 2].tolist() == [1] * 10 and counts.sum() == 10 and nmask.sum() == 0
+
+
+def test_layout_violations_rejected(eng):
+    from instrain_b200 import _cabi
+    batch, _ = load_batch("G1")
+    L, M = len(batch["ref_codes"]), int(batch["pair_mm"].max()) + 1
+    rd = reads.events_to_reads(batch)
+    bad = dict(rd); bad["seg_start"] = rd["seg_start"].copy(); bad["seg_start"][100:5000] = bad["seg_start"][100:5000][::-1]
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.pileup_reads(bad, batch["pair_mm"], 0, L, M)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+    bad = dict(rd); bad["seg_word"] = rd["seg_word"].copy(); bad["seg_word"][50:] += 40000
+    with pytest.raises(_cabi.IsbError):
+        eng.pileup_reads(bad, batch["pair_mm"], 0, L, M)
+    with pytest.raises(_cabi.IsbError) as ei:                                      # a segment beyond start + L
+        eng.pileup_reads(rd, batch["pair_mm"], 0, L - 50000, M)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+    with pytest.raises(_cabi.IsbError) as ei:                                      # mm value >= M
+        eng.pileup_reads(rd, batch["pair_mm"], 0, L, M - 1)
+    assert ei.value.code == _cabi.ISB_ERR_ARG
+
+
+def test_read_major_equals_position_major_larger(eng, null_lut):
+    """Both CUDA paths on a batch the oracle would take minutes for: identical tables."""
+    for skip_mm in (True, False):
+        batch = synth.make_batch(400000, 60, 0.01, 99, n_scaffolds=2, skip_mm=skip_mm)
+        rd = reads.events_to_reads(batch, max_len=150 if skip_mm else 256)
+        M = int(batch["pair_mm"].max()) + 1
+        want = ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld")
+        a = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want)
+        b = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want, reads=rd)
+        for k in ("counts", "nmask", "covT", "site_flags"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
+        assert_snv_equal(a["snv"], b["snv"])
+        assert_ld_equal(a["ld"], b["ld"], tol=0.0)

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--rep", type=int, default=10)
     ap.add_argument("--mm", action="store_true", help="keep per-pair mm (M ~ 12) instead of --skip_mm_profiling")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--seglen", type=int, default=150, help="max segment length of the read-major batch")
+    ap.add_argument("--reads", action="store_true", help="also time the read-major path (K1r, isb_profile_reads)")
     args = ap.parse_args()
 
     t0 = time.time()
@@ -106,6 +108,46 @@ def main():
     print(json.dumps(dict(n_snv=int(nrows.value))), flush=True)
     timed("k3_linkage", k3, 0)
     print(json.dumps(dict(n_ld=int(nrows.value))), flush=True)
+
+    if args.reads:
+        from instrain_b200 import reads as reads_mod
+        t1 = time.time()
+        rd1 = reads_mod.events_to_reads(b, max_len=args.seglen)
+        nw1 = rd1["n_words"]
+        seg_start = torch.cat([torch.from_numpy(rd1["seg_start"]).to(dev) + r * L1 for r in range(R)]).contiguous()
+        seg_len = torch.from_numpy(rd1["seg_len"].view(np.int16)).to(dev).repeat(R).contiguous()
+        seg_pair = torch.cat([torch.from_numpy(rd1["seg_pair"]).to(dev) + r * np1 for r in range(R)]).contiguous()
+        seg_word = torch.cat([torch.from_numpy(rd1["seg_word"]).to(dev) + r * nw1 for r in range(R)]).contiguous()
+        words = torch.from_numpy(rd1["words"].view(np.int32)).to(dev).repeat(R).contiguous()
+        print(json.dumps(dict(reads_setup_s=round(time.time() - t1, 1), n_segs=rd1["n_segs"] * R, n_words=nw1 * R,
+                              max_seg_len=rd1["max_seg_len"])), flush=True)
+        rb = _cabi.IsbReadsBatch(rd1["n_segs"] * R, p(seg_start), p(seg_len), p(seg_pair), p(seg_word), nw1 * R, p(words),
+                                 rd1["max_seg_len"], 0, 0, None, None, npairs, p(mm), 0, L, p(ref), splits.shape[0], p(splits), M, 0)
+        counts_r = torch.empty_like(counts)
+        nmask_r = torch.empty_like(nmask)
+
+        def k1r():
+            rc = lib.isb_pileup_reads(ctx, C.byref(rb), p(counts_r), p(nmask_r))
+            assert rc == 0, lib.isb_last_error(ctx)
+
+        k1(0)
+        timed("k1r_reads", k1r, nw1 * R * 4 + 22 * rd1["n_segs"] * R + 16 * M * L + 8 * L)
+        print(json.dumps(dict(k1r_equal=bool(torch.equal(counts, counts_r)), nmask_equal=bool(torch.equal(nmask, nmask_r)))),
+              flush=True)
+        prm_r = _cabi.IsbParams(5, 20, 30, 0, 0.05)
+        res_r = _cabi.IsbResult(p(counts_r), p(nmask_r), p(covT), p(clonT), p(flags), p(snv), snv.numel() // 32, p(ld),
+                                ld.numel() // 48, 0, 0, 0, 0)
+
+        def full_r():
+            rc = lib.isb_profile_reads(ctx, C.byref(rb), C.byref(prm_r), C.byref(res_r))
+            assert rc == 0, lib.isb_last_error(ctx)
+
+        eng.enable_timing(True)
+        timed("profile_reads", full_r, nw1 * R * 4 + 40 * M * L)
+        ms, calls = eng.stage_times()
+        print(json.dumps(dict(reads_stage_ms=[round(ms[k] / max(calls[k], 1), 4) for k in range(3)],
+                              n_snv=int(res_r.n_snv), n_ld=int(res_r.n_ld))), flush=True)
+        eng.enable_timing(False)
 
     batch = _cabi.IsbBatch(n, p(pos), p(base), p(qual), p(rid), npairs, p(mm), 0, L, p(ref), splits.shape[0], p(splits), M)
     prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
