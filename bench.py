@@ -6,10 +6,13 @@
 
 Workload (BASELINE.json configs[2] / north_star): synthetic metagenome, `--scaffolds` x `--L` bp at `--cov` x coverage,
 1 % SNV density, min_cov 5, min_freq 0.05, min_snp 20, window_length 10000, --skip_mm_profiling (M = 1) unless --mm.
-Defaults: 100 x 1 Mb x 100x = the full 100 Mb configuration (1e10 aligned bases = 100 GB of event columns in HBM);
-it is generated on the device (instrain_b200/synth.py) because it cannot be produced on, or shipped from, the host
-in bench time.  A "step" = one full pass of the hot path (isb_profile_batch: K1 pileup -> K2 SNV -> K3 linkage) over the
-whole resident data set.  Inputs are ~100 GB >> the 126 MB L2, so no L2 flush is needed between steps.
+Defaults: 100 x 1 Mb x 100x = the full 100 Mb configuration (1e10 aligned bases); it is generated on the device
+(instrain_b200/synth.py) because it cannot be produced on, or shipped from, the host in bench time.
+--layout reads (default): the data set is resident as READ-MAJOR aligned segments (4-bit code per aligned base, ~5.6 GB);
+a "step" = isb_profile_reads (K1r pileup from segments -> K2 SNV -> K3 linkage) over the whole resident data set.
+--layout events: the same fragments as position-major event columns (10 B per event, 100 GB), step = isb_profile_batch
+(K1 -> K2 -> K3).  Either way the inputs are far larger than the 126 MB L2, so no L2 flush is needed between steps.
+With --layout reads a short secondary run of the event layout on --also-events scaffolds is reported beside.
 
 Multi-GPU: scaffolds are independent, so every rank profiles its own 100-scaffold shard (weak scaling, no data-path
 collective) and the final SNV / linkage tables are gathered to rank 0 over NCCL inside the timed step.
@@ -47,6 +50,10 @@ def parse():
     ap.add_argument("--e2e-scaffolds", type=int, default=4, help="scaffolds in the bounded host-buffer (e2e) slice")
     ap.add_argument("--cpu-scaffolds", type=int, default=1, help="scaffolds in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="reads", choices=["reads", "events"],
+                    help="resident input layout: read-major aligned segments (default) or position-major event columns")
+    ap.add_argument("--also-events", type=int, default=10,
+                    help="with --layout reads: also time the position-major path on this many scaffolds (0 = skip)")
     return ap.parse_args()
 
 
@@ -142,7 +149,10 @@ def main():
     config = {"workload": workload, "scaffolds_per_gpu": args.scaffolds, "scaffold_len": args.L, "coverage": args.cov,
               "snv_density": args.dens, "min_cov": 5, "min_freq": 0.05, "min_snp": 20, "window_length": 10000,
               "sharding": "scaffolds per rank (weak), NCCL gather of SNV/linkage rows to rank 0" if world > 1 else "single GPU",
-              "l2": "inputs (%.0f GB) larger than L2; no flush needed" % (args.scaffolds * args.L * args.cov * 10 / 1e9)}
+              "layout": "read-major aligned segments (4-bit code per aligned base)" if args.layout == "reads"
+                        else "position-major event columns (10 B per event)",
+              "l2": "inputs (%.1f GB) larger than L2; no flush needed" % (
+                  args.scaffolds * args.L * args.cov * (0.56 if args.layout == "reads" else 10) / 1e9)}
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -172,11 +182,13 @@ def main():
 
     # ------------------------------------------------------------------------------------------------ B200 arm
     from instrain_b200.engine import Engine
+    use_reads = args.layout == "reads"
     t_gen = time.time()
-    d = synth.generate(local_rank, args.L, args.scaffolds, args.cov, args.dens, SEED + rank, skip_mm=not args.mm)
+    d = synth.generate(local_rank, args.L, args.scaffolds, args.cov, args.dens, SEED + rank, skip_mm=not args.mm,
+                       events=not use_reads, reads=use_reads)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
-    n, npairs, Ltot = d["ref_pos"].numel(), d["pair_mm"].numel(), args.L * args.scaffolds
+    n, npairs, Ltot = int(d["n_events"]), d["pair_mm"].numel(), args.L * args.scaffolds
     M = int(d["pair_mm"].max().item()) + 1 if npairs else 1
     eng = Engine(local_rank, lut, dflt)
     stream = torch.cuda.current_stream()
@@ -199,8 +211,20 @@ def main():
 
     snv = ld = None
     alloc_rows()
-    batch = _cabi.IsbBatch(n, p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), npairs, p(d["pair_mm"]), 0,
-                           Ltot, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M)
+
+    def reads_struct(rd, n_pairs, pair_mm, L_, ref, splits, M_):
+        return _cabi.IsbReadsBatch(int(rd["n_segs"]), p(rd["seg_start"]), p(rd["seg_len"]), p(rd["seg_pair"]),
+                                   p(rd["seg_word"]), int(rd["n_words"]), p(rd["words"]), int(rd["max_seg_len"]), 0,
+                                   len(rd["nev_pos"]), p(rd["nev_pos"]), p(rd["nev_pair"]), n_pairs, p(pair_mm), 0, L_,
+                                   p(ref), len(splits), p(splits), M_, 0)
+
+    if use_reads:
+        batch = reads_struct(d["reads"], npairs, d["pair_mm"], Ltot, d["ref_codes"], d["splits"], M)
+        entry = lib.isb_profile_reads
+    else:
+        batch = _cabi.IsbBatch(n, p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), npairs, p(d["pair_mm"]), 0,
+                               Ltot, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M)
+        entry = lib.isb_profile_batch
     prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
 
     def gather_tables():
@@ -218,11 +242,11 @@ def main():
 
     def step():
         nonlocal snv_cap, ld_cap
-        rc = lib.isb_profile_batch(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+        rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(res))
         if rc == _cabi.ISB_ERR_CAPACITY:
             snv_cap, ld_cap = max(snv_cap, int(res.n_snv) + 1024), max(ld_cap, int(res.n_ld) + 1024)
             alloc_rows()
-            rc = lib.isb_profile_batch(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+            rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(res))
         if rc != 0:
             raise RuntimeError(lib.isb_last_error(ctx).decode())
         gather_tables()
@@ -259,26 +283,78 @@ def main():
 
     # -------------------------------------------------------------------------------- roofline of the dominant kernel
     peak, peak_src = measured_peak()
-    k1_ms = stage_ms[0] / max(1, stage_calls[0])
-    ev_bytes = 10 if M > 1 else 6                     # at M = 1 K1 does not need (and does not read) read_id
-    alg_bytes = n * ev_bytes + 16 * M * Ltot + 8 * Ltot
-    alg_bytes_survey = n * 10 + 16 * M * Ltot         # 10*c + 16*M B/position
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        key = "M1" if M == 1 else "Mgt1"
-        traffic = tj[key]["dram_bytes_per_event"] * n
-    except Exception:
-        pass
-    roofline = {"kernel": "k1_pileup_tiles_tma<M=1>" if M == 1 else "k1_pileup_tiles<M>1>", "bound": "hbm",
-                "achieved": alg_bytes / k1_ms / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / k1_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
+    stage_per_step = {"k1_pileup": stage_ms[0] / args.steps, "k2_snv": stage_ms[1] / args.steps,
+                      "k3_linkage": stage_ms[2] / args.steps}
+
+    def traffic_of(key, units):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            e = tj[key]
+            return (e["dram_bytes_per_unit"] if "dram_bytes_per_unit" in e else e["dram_bytes_per_event"]) * units
+        except Exception:
+            return None
+
+    def events_roofline(k1_ms_, n_, M_, Ltot_):
+        ev_bytes = 10 if M_ > 1 else 6                # at M = 1 K1 does not need (and does not read) read_id
+        alg = n_ * ev_bytes + 16 * M_ * Ltot_ + 8 * Ltot_
+        return {"kernel": "k1_pileup_tiles_tma<M=1>" if M_ == 1 else "k1_pileup_tiles_tma<M>1>", "bound": "hbm",
+                "achieved": alg / k1_ms_ / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / k1_ms_ / 1e6 / peak,
+                "traffic": traffic_of("M1" if M_ == 1 else "Mgt1", n_), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg,
                 "bytes_def": "%d B/event (ref_pos i32 + base u8 + qual u8%s) + 16*M B/position counts + 8 B/position nmask"
-                             % (ev_bytes, " + read_id i32" if M > 1 else "; read_id not needed at M=1"),
-                "achieved_survey_def": alg_bytes_survey / k1_ms / 1e6, "launch_ms": k1_ms,
-                "stage_ms_per_step": {"k1_pileup": stage_ms[0] / args.steps, "k2_snv": stage_ms[1] / args.steps,
-                                      "k3_linkage": stage_ms[2] / args.steps}}
+                             % (ev_bytes, " + read_id i32" if M_ > 1 else "; read_id not needed at M=1"),
+                "achieved_survey_def": (n_ * 10 + 16 * M_ * Ltot_) / k1_ms_ / 1e6, "launch_ms": k1_ms_}
+
+    k1_ms = stage_ms[0] / max(1, stage_calls[0])
+    if use_reads:
+        rd = d["reads"]
+        # algorithmic bytes of K1r: the nibble stream + the segment table (start i32, len u16, word offset i64, + pair
+        # id i32 when M > 1) in, counts (+ nmask) out
+        alg_bytes = int(rd["n_words"]) * 4 + int(rd["n_segs"]) * (14 + (4 if M > 1 else 0)) + 16 * M * Ltot + 8 * Ltot
+        roofline = {"kernel": "k1r_pileup<M=1>" if M == 1 else "k1r_pileup<M>1>", "bound": "hbm",
+                    "achieved": alg_bytes / k1_ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg_bytes / k1_ms / 1e6 / peak,
+                    "traffic": traffic_of("K1r_M1" if M == 1 else "K1r_Mgt1", Ltot), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "bytes_def": "4 bits per aligned base (nibble stream incl. separators) + 14-18 B per segment in, 16*M B/position "
+                                 "counts + 8 B/position nmask out; the same pileup from event columns would read %d B/event"
+                                 % (10 if M > 1 else 6),
+                    "equivalent_event_column_rate": (n * (10 if M > 1 else 6) + 16 * M * Ltot + 8 * Ltot) / k1_ms / 1e6,
+                    "launch_ms": k1_ms,
+                    "note": "K1r is bound by issue slots / shared-memory bandwidth, not HBM: the read-major layout removed "
+                            "~90 % of the pileup's DRAM bytes (see position_major_path for the HBM-bound event-column kernel)"}
+    else:
+        roofline = events_roofline(k1_ms, n, M, Ltot)
+    roofline["stage_ms_per_step"] = stage_per_step
+
+    # position-major path on a subset, for comparison (the HBM-bound K1 kernel on 10 B/event columns)
+    pos_major = None
+    if use_reads and rank == 0 and args.also_events > 0:
+        n_sc = min(args.also_events, args.scaffolds)
+        de = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED + rank, skip_mm=not args.mm)
+        Le = n_sc * args.L
+        ne, npe = de["ref_pos"].numel(), de["pair_mm"].numel()
+        be = _cabi.IsbBatch(ne, p(de["ref_pos"]), p(de["base"]), p(de["qual"]), p(de["read_id"]), npe, p(de["pair_mm"]), 0,
+                            Le, p(de["ref_codes"]), de["splits"].shape[0], p(de["splits"]), M)
+        re_ = _cabi.IsbResult(p(counts), p(nmask), p(covT), p(clonT), p(flags), p(snv), snv_cap, p(ld), ld_cap, 0, 0, 0, 0)
+        for it in range(3 + 3):
+            if it == 3:
+                eng.enable_timing(True)
+                eng.stage_times()
+                torch.cuda.synchronize()
+                e0.record(stream)
+            if lib.isb_profile_batch(ctx, C.byref(be), C.byref(prm), C.byref(re_)) != 0:
+                raise RuntimeError(lib.isb_last_error(ctx).decode())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sm, sc = eng.stage_times()
+        eng.enable_timing(False)
+        ms_e = e0.elapsed_time(e1) / 3
+        pos_major = {"value": Le / (ms_e / 1e3), "unit": UNIT, "ms_per_step": ms_e, "scaffolds": n_sc,
+                     "roofline": events_roofline(sm[0] / max(1, sc[0]), ne, M, Le),
+                     "stage_ms_per_step": {"k1_pileup": sm[0] / 3, "k2_snv": sm[1] / 3, "k3_linkage": sm[2] / 3},
+                     "rows_equal": None}
+        del de, be
+        torch.cuda.empty_cache()
 
     # -------------------------------------------------------------------------------- e2e: host buffers through the C-ABI
     # Public call a user makes: pinned HOST buffers in (the host packer's packed transfer format, ~1 B/event),
@@ -288,7 +364,13 @@ def main():
     if rank == 0:
         from instrain_b200.packed import encode_packed
         n_sc = max(1, min(args.e2e_scaffolds, args.scaffolds))
-        hb = synth.to_host_batch(d, 0, n_sc)
+        # the first n_sc scaffolds of the data set, regenerated in both layouts (the generator is deterministic per seed)
+        ds = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED + rank, skip_mm=not args.mm, events=True,
+                            reads=True)
+        hb = synth.to_host_batch(ds, 0, n_sc)
+        hr = synth.reads_to_host(ds, 0, n_sc)["reads"]
+        del ds
+        torch.cuda.empty_cache()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         Ls = n_sc * args.L
         Ms = int(hb["pair_mm"].max()) + 1 if len(hb["pair_mm"]) else 1
@@ -308,6 +390,11 @@ def main():
                                       p(h["ref_codes"]), len(hb["splits"]), p(h["splits"]), Ms, 30)
         hres = _cabi.IsbResult(None, None, p(o["covT"]), p(o["clonT"]), p(o["flags"]), p(o["snv"]),
                                o["snv"].numel() // 32, p(o["ld"]), o["ld"].numel() // 48, 0, 0, 0, 0)
+        hrp = {k: pin(hr[k].view(np.int16) if k == "seg_len" else (hr[k].view(np.int32) if k == "words" else hr[k]))
+               for k in ("seg_start", "seg_len", "seg_pair", "seg_word", "words")}
+        hrp.update(n_segs=hr["n_segs"], n_words=hr["n_words"], max_seg_len=hr["max_seg_len"], nev_pos=hr["nev_pos"],
+                   nev_pair=hr["nev_pair"])
+        rbatch = reads_struct(hrp, len(hb["pair_mm"]), h["pair_mm"], Ls, h["ref_codes"], h["splits"], Ms)
 
         def time_call(fn, b):
             ts = []
@@ -323,7 +410,9 @@ def main():
             return float(np.median(ts))
 
         dt_col = time_call(lib.isb_profile_batch, hbatch)
-        dt = time_call(lib.isb_profile_batch_packed, pbatch)
+        dt_pk = time_call(lib.isb_profile_batch_packed, pbatch)
+        dt_rd = time_call(lib.isb_profile_reads, rbatch)
+        main_fn, main_b, dt = (lib.isb_profile_reads, rbatch, dt_rd) if use_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
 
         # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
         # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
@@ -338,7 +427,7 @@ def main():
 
             def worker(c, r):
                 for _ in range(n_it):
-                    if lib.isb_profile_batch_packed(c, C.byref(pbatch), C.byref(prm), C.byref(r)) != 0:
+                    if main_fn(c, C.byref(main_b), C.byref(prm), C.byref(r)) != 0:
                         errs.append(lib.isb_last_error(c).decode())
 
             for rep in range(2):                         # first repetition warms the second context's scratch buffers
@@ -356,22 +445,30 @@ def main():
             dt_pipe = None
             print("e2e pipelined leg skipped: %r" % (ex,), file=sys.stderr)
         common = len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
-        h2d = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
+        h2d_pk = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
+        h2d_rd = hr["n_words"] * 4 + hr["n_segs"] * (4 + 2 + 4 + 8) + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
         best = min(dt, dt_pipe) if dt_pipe else dt
-        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": best * 1e3, "api": "isb_profile_batch_packed (packed transfer format, K0 expands on the device)",
+        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rd if use_reads else h2d_pk),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": best * 1e3,
+               "api": ("isb_profile_reads (read-major aligned segments, 4 bits per aligned base)" if use_reads else
+                       "isb_profile_batch_packed (packed transfer format, K0 expands on the device)"),
                "single_context": {"value": Ls / dt, "ms_per_step": dt * 1e3},
                "two_contexts_pipelined": ({"value": Ls / dt_pipe, "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),
                "slice": "%d of the %d scaffolds per step, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, args.scaffolds),
-               "columnar_host_buffers": {"value": Ls / dt_col, "ms_per_step": dt_col * 1e3,
-                                         "h2d_bytes_per_step": int(len(hb["ref_pos"]) * 10 + common)}}
+               "other_host_formats": {
+                   "read_major_segments": {"value": Ls / dt_rd, "ms_per_step": dt_rd * 1e3, "h2d_bytes_per_step": int(h2d_rd)},
+                   "packed_events": {"value": Ls / dt_pk, "ms_per_step": dt_pk * 1e3, "h2d_bytes_per_step": int(h2d_pk)},
+                   "columnar_events": {"value": Ls / dt_col, "ms_per_step": dt_col * 1e3,
+                                       "h2d_bytes_per_step": int(len(hb["ref_pos"]) * 10 + common)}}}
 
     # -------------------------------------------------------------------------------- CPU baseline (oracle port) beside
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_sc = max(1, min(args.cpu_scaffolds, args.scaffolds))
-        hb = synth.to_host_batch(d, 0, n_sc)
+        ds = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED + rank, skip_mm=not args.mm)
+        hb = synth.to_host_batch(ds, 0, n_sc)
+        del ds
         a = time.time()
         cpu_oracle_pass(hb, lut, dflt, 1)
         dt = time.time() - a
@@ -385,6 +482,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 counts / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "position_major_path": pos_major,
             "rows": {"n_events_per_gpu": n, "n_pairs_per_gpu": npairs, "M": M, "n_snv": int(res.n_snv), "n_ld": int(res.n_ld),
                      "n_sites": int(res.n_sites), "n_site_pairs": int(res.n_site_pairs)},
             "setup_s": round(t_gen, 1)}))

@@ -1,4 +1,4 @@
-// isb_synth.cu -- libisb_synth.so: device-side synthetic metagenome -> position-major event columns.
+// isb_synth.cu -- libisb_synth.so: device-side synthetic metagenome -> position-major event columns and/or read-major segments.
 //
 // BENCH / TEST SUPPORT, not part of the hot path and not part of libinstrain_b200.so.  BASELINE.json's headline
 // workload (100 scaffolds x 1 Mb at 100x = 1e10 aligned bases = 100 GB of event columns) cannot be generated on the
@@ -212,6 +212,92 @@ __global__ void synth_events(isbs_params prm, int K, uint32_t dens24, int64_t Lt
     if (!kFill) cov[pg] = n;
 }
 
+// ---- read-major output: the same fragments as aligned segments (one per mate), sorted by start ------------------------
+// one thread per position: the segments STARTING there (mate 1 of the fragments starting at pg, then mate 2 of the
+// fragments whose second mate starts at pg).  kFill = false counts, kFill = true writes the segment table.
+#define SEG_WORDS ((READLEN + 7) / 8 + 1)          // data words + the zero separator
+template <bool kFill>
+__global__ void synth_seg_table(isbs_params prm, int K, uint32_t dens24, int64_t Ltot, const int32_t *__restrict__ slot_id,
+                                const uint16_t *__restrict__ slot_F, const int64_t *__restrict__ seg_off,
+                                int32_t *__restrict__ cnt, int32_t *__restrict__ seg_start, uint16_t *__restrict__ seg_len,
+                                int32_t *__restrict__ seg_pair, int64_t *__restrict__ seg_word, int64_t *__restrict__ seg_src,
+                                uint8_t *__restrict__ ref)
+{
+    const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pg >= Ltot) return;
+    const int64_t sc0 = (pg / prm.L) * prm.L;
+    int64_t w = kFill ? seg_off[pg] : 0;
+    int n = 0;
+    for (int k = 0; k < K; ++k) {                                      // mate 1
+        const int64_t s = pg * K + k;
+        const int32_t id = slot_id[s];
+        if (id < 0) continue;
+        if (kFill) {
+            seg_start[w] = (int32_t)pg; seg_len[w] = READLEN; seg_pair[w] = id; seg_word[w] = 1 + w * SEG_WORDS;
+            seg_src[w] = s * 2;
+            ++w;
+        }
+        ++n;
+    }
+    const int64_t x_lo = max(sc0, pg - (FRAG_MAX - READLEN));
+    for (int64_t xg = x_lo; xg <= pg - (FRAG_MIN - READLEN); ++xg) {    // mate 2 starts at xg + F - READLEN
+        for (int k = 0; k < K; ++k) {
+            const int64_t s = xg * K + k;
+            const int32_t id = slot_id[s];
+            if (id < 0 || (int64_t)slot_F[s] - READLEN != pg - xg) continue;
+            if (kFill) {
+                seg_start[w] = (int32_t)pg; seg_len[w] = READLEN; seg_pair[w] = id; seg_word[w] = 1 + w * SEG_WORDS;
+                seg_src[w] = s * 2 + 1;
+                ++w;
+            }
+            ++n;
+        }
+    }
+    if (!kFill) cnt[pg] = n;
+    else ref[pg] = pos_draw(prm.seed, pg, dens24).ref;
+}
+
+// one thread per segment: its READLEN one-hot codes (A=1,C=2,T=4,G=8; 0 = fails min_qual after the overlap tweak)
+__global__ void synth_seg_words(isbs_params prm, uint32_t dens24, int64_t n_segs, const int32_t *__restrict__ seg_start,
+                                const int64_t *__restrict__ seg_src, const uint16_t *__restrict__ slot_F, int min_qual,
+                                uint32_t *__restrict__ words)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_segs) return;
+    const int64_t s = seg_src[i] >> 1;
+    const int mate = (int)(seg_src[i] & 1);
+    const int F = slot_F[s];
+    const int64_t start = seg_start[i];
+    const int64_t xg = mate ? start - (F - READLEN) : start;
+    const uint64_t r1 = rng(prm.seed, TAG_FRAG, (uint64_t)s, 0);
+    const uint32_t hu = (r1 >> 32) & 0xffff;
+    const int hap = (hu >= 26214) + (hu >= 45875) + (hu >= 58982);
+    uint32_t *dst = words + 1 + i * SEG_WORDS;
+    for (int wj = 0; wj < SEG_WORDS; ++wj) {
+        uint32_t word = 0;
+        for (int nb = 0; nb < 8; ++nb) {
+            const int o = wj * 8 + nb;
+            if (o >= READLEN) break;
+            const int64_t pg = start + o;
+            const int d = (int)(pg - xg);
+            const pos_info pi = pos_draw(prm.seed, pg, dens24);
+            const int tb = hap_base(pi, hap);
+            int b1 = 0, q1 = 0, b2 = 0, q2 = 0;
+            const bool in1 = d < READLEN, in2 = d >= F - READLEN && d < F;
+            if (in1) ev_draw(prm.seed, s, 0, d, tb, b1, q1);
+            if (in2) ev_draw(prm.seed, s, 1, d - (F - READLEN), tb, b2, q2);
+            if (in1 && in2) {                      // htslib tweak_overlap_quality, a = mate 1
+                if (b1 == b2) { q1 = min(200, q1 + q2); q2 = 0; }
+                else if (q1 >= q2) { q1 = (int)(0.8 * q1); q2 = 0; }
+                else { q2 = (int)(0.8 * q2); q1 = 0; }
+            }
+            const int b = mate ? b2 : b1, q = mate ? q2 : q1;
+            if (q >= min_qual) word |= (1u << b) << (4 * nb);
+        }
+        dst[wj] = word;                            // the last word of the block is the zero separator
+    }
+}
+
 #define SYN_CUDA(call)                                                                                   \
     do {                                                                                                 \
         cudaError_t _e = (call);                                                                         \
@@ -277,6 +363,48 @@ int isbs_plan(int device, const isbs_params *prm, int64_t *n_events, int64_t *n_
     SYN_CUDA(cudaDeviceSynchronize());
     *n_events = g.n_events;
     *n_pairs = g.n_pairs;
+    return 0;
+}
+
+// Phase 2 (optional, before isbs_fill): the same data set as a read-major batch.  n_segs = 2 * n_pairs segments of READLEN
+// bases, n_words = isbs_reads_words(n_segs) words; all buffers caller-owned DEVICE memory.
+int64_t isbs_reads_words(int64_t n_segs) { return (1 + n_segs * SEG_WORDS + 3) / 4 * 4; }
+
+int isbs_fill_reads(int32_t *seg_start, uint16_t *seg_len, int32_t *seg_pair, int64_t *seg_word, uint32_t *words,
+                    uint8_t *pair_mm, uint8_t *ref, int min_qual)
+{
+    const uint32_t dens24 = (uint32_t)(g.prm.snv_density * 16777216.0);
+    const int64_t n_segs = 2 * g.n_pairs;
+    int64_t *seg_src = nullptr, *seg_off = nullptr;
+    int32_t *cnt = nullptr;
+    SYN_CUDA(cudaMalloc(&seg_src, sizeof(int64_t) * (size_t)(n_segs + 1)));
+    SYN_CUDA(cudaMalloc(&seg_off, sizeof(int64_t) * (size_t)g.Ltot));
+    SYN_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (size_t)g.Ltot));
+    synth_seg_table<false><<<(unsigned)((g.Ltot + 127) / 128), 128>>>(g.prm, g.K, dens24, g.Ltot, g.slot_id, g.slot_F, nullptr,
+                                                                      cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    SYN_CUDA(cudaGetLastError());
+    int64_t total = 0;
+    if (run_scan(CovFn{cnt}, OffSink{seg_off}, g.Ltot, g.scan_tmp, g.d_tot, &total)) return -1;
+    if (total != n_segs) { snprintf(g.err, sizeof(g.err), "segment count mismatch %lld vs %lld", (long long)total, (long long)n_segs); return -1; }
+    synth_seg_table<true><<<(unsigned)((g.Ltot + 127) / 128), 128>>>(g.prm, g.K, dens24, g.Ltot, g.slot_id, g.slot_F, seg_off,
+                                                                     nullptr, seg_start, seg_len, seg_pair, seg_word, seg_src, ref);
+    SYN_CUDA(cudaGetLastError());
+    SYN_CUDA(cudaMemset(words, 0, sizeof(uint32_t) * (size_t)isbs_reads_words(n_segs)));
+    if (n_segs > 0) {
+        synth_seg_words<<<(unsigned)((n_segs + 127) / 128), 128>>>(g.prm, dens24, n_segs, seg_start, seg_src, g.slot_F, min_qual, words);
+        SYN_CUDA(cudaGetLastError());
+    }
+    synth_pair_mm<<<(unsigned)((g.n_slots + 255) / 256), 256>>>(g.slot_id, g.slot_mm, g.n_slots, g.prm.skip_mm, pair_mm);
+    SYN_CUDA(cudaGetLastError());
+    SYN_CUDA(cudaDeviceSynchronize());
+    cudaFree(seg_src); cudaFree(seg_off); cudaFree(cnt);
+    return 0;
+}
+
+// Phase 3 without event columns: free the plan.
+int isbs_free(void)
+{
+    free_state();
     return 0;
 }
 

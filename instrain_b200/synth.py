@@ -31,6 +31,11 @@ def _load():
         _lib.isbs_plan.argtypes = [C.c_int, C.POINTER(_Params), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib.isbs_fill.restype = C.c_int
         _lib.isbs_fill.argtypes = [C.c_void_p] * 6
+        _lib.isbs_fill_reads.restype = C.c_int
+        _lib.isbs_fill_reads.argtypes = [C.c_void_p] * 7 + [C.c_int]
+        _lib.isbs_reads_words.restype = C.c_int64
+        _lib.isbs_reads_words.argtypes = [C.c_int64]
+        _lib.isbs_free.restype = C.c_int
     return _lib
 
 
@@ -54,8 +59,14 @@ def batch_splits(L, n_scaffolds, window_len=10000):
     return np.concatenate([one + s * L for s in range(n_scaffolds)]).astype(np.int32)
 
 
-def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, window_len=10000):
-    """Returns a dict of CUDA torch tensors (ref_pos, base, qual, read_id, pair_mm, ref_codes) + splits (CUDA int32)."""
+READLEN = 150
+
+
+def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, window_len=10000, events=True, reads=False,
+             min_qual=30):
+    """Returns a dict of CUDA torch tensors + splits (CUDA int32).  events=True: position-major event columns (ref_pos,
+    base, qual, read_id); reads=True: the SAME fragments as a read-major batch under key "reads" (seg_start, seg_len,
+    seg_pair, seg_word, words, ...; instrain_b200/reads.py layout).  Always: pair_mm, ref_codes."""
     import torch
     lib = _load()
     prm = _Params(L, n_scaffolds, coverage, float(snv_density), seed, 1 if skip_mm else 0, 0)
@@ -65,6 +76,27 @@ def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, 
     dev = torch.device("cuda", device)
     n, npairs, Ltot = n_ev.value, n_pairs.value, L * n_scaffolds
     pad = 16                                    # keep every column readable in whole 16-byte granules
+    rd = None
+    if reads:
+        n_segs = 2 * npairs
+        n_words = int(lib.isbs_reads_words(n_segs))
+        rd = dict(n_segs=n_segs, n_words=n_words, max_seg_len=READLEN,
+                  seg_start=torch.empty(max(n_segs, 1), dtype=torch.int32, device=dev)[:n_segs],
+                  seg_len=torch.empty(max(n_segs, 1), dtype=torch.int16, device=dev)[:n_segs],
+                  seg_pair=torch.empty(max(n_segs, 1), dtype=torch.int32, device=dev)[:n_segs],
+                  seg_word=torch.empty(max(n_segs, 1), dtype=torch.int64, device=dev)[:n_segs],
+                  words=torch.empty(n_words, dtype=torch.int32, device=dev),
+                  nev_pos=torch.empty(0, dtype=torch.int32, device=dev), nev_pair=torch.empty(0, dtype=torch.int32, device=dev))
+        pair_mm = torch.empty(max(npairs, 1), dtype=torch.uint8, device=dev)[:npairs]
+        ref_codes = torch.empty(Ltot, dtype=torch.uint8, device=dev)
+        if lib.isbs_fill_reads(rd["seg_start"].data_ptr(), rd["seg_len"].data_ptr(), rd["seg_pair"].data_ptr(),
+                               rd["seg_word"].data_ptr(), rd["words"].data_ptr(), pair_mm.data_ptr(),
+                               ref_codes.data_ptr(), min_qual) != 0:
+            raise RuntimeError("isbs_fill_reads: " + lib.isbs_last_error().decode())
+        if not events:
+            lib.isbs_free()
+            return dict(reads=rd, pair_mm=pair_mm, ref_codes=ref_codes, L=L, n_scaffolds=n_scaffolds, n_events=n,
+                        splits=torch.from_numpy(batch_splits(L, n_scaffolds, window_len)).to(dev))
     out = dict(
         ref_pos=torch.empty(n + pad, dtype=torch.int32, device=dev)[:n],
         base=torch.empty(n + pad, dtype=torch.uint8, device=dev)[:n],
@@ -77,8 +109,38 @@ def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, 
                      out["read_id"].data_ptr(), out["pair_mm"].data_ptr(), out["ref_codes"].data_ptr()) != 0:
         raise RuntimeError("isbs_fill: " + lib.isbs_last_error().decode())
     out["splits"] = torch.from_numpy(batch_splits(L, n_scaffolds, window_len)).to(dev)
-    out["L"], out["n_scaffolds"] = L, n_scaffolds
+    out["L"], out["n_scaffolds"], out["n_events"] = L, n_scaffolds, n
+    if rd is not None:
+        out["reads"] = rd
     return out
+
+
+def reads_to_host(d, lo_scaffold=0, n_scaffolds=1):
+    """Cut scaffolds [lo, lo+n) out of a generated read-major data set as a self-contained host (numpy) batch, coordinates,
+    pair ids and word offsets re-based to 0 (uniform READLEN segments: the word stream of a range is contiguous)."""
+    import torch
+    L, rd = d["L"], d["reads"]
+    p_lo, p_hi = lo_scaffold * L, (lo_scaffold + n_scaffolds) * L
+    bounds = torch.searchsorted(rd["seg_start"], torch.tensor([p_lo, p_hi], dtype=torch.int32, device=rd["seg_start"].device))
+    s_lo, s_hi = int(bounds[0]), int(bounds[1])
+    n = s_hi - s_lo
+    pair = rd["seg_pair"][s_lo:s_hi]
+    id_lo, id_hi = (int(pair.min()), int(pair.max()) + 1) if n else (0, 0)
+    w_lo = int(rd["seg_word"][s_lo]) - 1 if n else 0
+    spw = (READLEN + 7) // 8 + 1
+    n_words = (1 + n * spw + 3) // 4 * 4
+    words = np.zeros(n_words, dtype=np.uint32)
+    words[:1 + n * spw] = rd["words"][w_lo:w_lo + 1 + n * spw].cpu().numpy().view(np.uint32)
+    spl = d["splits"]
+    sel = (spl[:, 0] >= p_lo) & (spl[:, 0] < p_hi)
+    return dict(reads=dict(n_segs=n, n_words=n_words, max_seg_len=READLEN,
+                           seg_start=(rd["seg_start"][s_lo:s_hi] - p_lo).cpu().numpy(),
+                           seg_len=rd["seg_len"][s_lo:s_hi].cpu().numpy().view(np.uint16),
+                           seg_pair=(pair - id_lo).cpu().numpy(),
+                           seg_word=(rd["seg_word"][s_lo:s_hi] - w_lo).cpu().numpy(), words=words,
+                           nev_pos=np.zeros(0, np.int32), nev_pair=np.zeros(0, np.int32)),
+                pair_mm=d["pair_mm"][id_lo:id_hi].cpu().numpy(), ref_codes=d["ref_codes"][p_lo:p_hi].cpu().numpy(),
+                splits=(spl[sel] - p_lo).cpu().numpy())
 
 
 def to_host_batch(d, lo_scaffold=0, n_scaffolds=1):

@@ -151,3 +151,29 @@ def test_read_major_equals_position_major_larger(eng, null_lut):
         assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
         assert_snv_equal(a["snv"], b["snv"])
         assert_ld_equal(a["ld"], b["ld"], tol=0.0)
+
+
+def test_device_generator_reads_equal_events(eng, null_lut):
+    """The bench's device generator emits the SAME fragments as event columns and as aligned segments: both CUDA paths
+    give identical tables on the device-resident data, and a host slice of the segments matches the oracle."""
+    from instrain_b200 import synth as dsynth
+    for skip_mm in (True, False):
+        d = dsynth.generate(0, 50000, 3, 60, 0.01, 77, skip_mm=skip_mm, events=True, reads=True)
+        rd = d["reads"]
+        assert rd["n_segs"] == 2 * d["pair_mm"].numel() and int(rd["seg_len"].min()) == 150
+        M = int(d["pair_mm"].max().item()) + 1
+        ev = dict(ref_pos=d["ref_pos"], base=d["base"], qual=d["qual"], read_id=d["read_id"], pair_mm=d["pair_mm"].cpu().numpy())
+        ref, splits = d["ref_codes"].cpu().numpy(), d["splits"].cpu().numpy()
+        want = ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld")
+        a = eng.profile_batch(ev, ref, splits, M=M, want=want)
+        b = eng.profile_batch(ev, ref, splits, M=M, want=want, reads=rd)
+        for k in ("counts", "nmask", "covT", "site_flags"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
+        assert_snv_equal(a["snv"], b["snv"])
+        assert_ld_equal(a["ld"], b["ld"], tol=0.0)
+        assert a["n_snv"] > 100 and a["n_ld"] > 10
+        hb = dsynth.to_host_batch(d, 1, 2)
+        hr = dsynth.reads_to_host(d, 1, 2)
+        assert np.array_equal(hb["pair_mm"], hr["pair_mm"])
+        check_reads(eng, hb, null_lut, rd=hr["reads"])
