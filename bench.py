@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="reads", choices=["reads", "events"],
                     help="resident input layout: read-major aligned segments (default) or position-major event columns")
+    ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (20 or 21)")
     ap.add_argument("--also-events", type=int, default=10,
                     help="with --layout reads: also time the position-major path on this many scaffolds (0 = skip)")
     return ap.parse_args()
@@ -185,7 +186,7 @@ def main():
     use_reads = args.layout == "reads"
     t_gen = time.time()
     d = synth.generate(local_rank, args.L, args.scaffolds, args.cov, args.dens, SEED + rank, skip_mm=not args.mm,
-                       events=not use_reads, reads=use_reads)
+                       events=not use_reads, reads=use_reads, seg_words=args.seg_words)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
     n, npairs, Ltot = int(d["n_events"]), d["pair_mm"].numel(), args.L * args.scaffolds
@@ -366,7 +367,7 @@ def main():
         n_sc = max(1, min(args.e2e_scaffolds, args.scaffolds))
         # the first n_sc scaffolds of the data set, regenerated in both layouts (the generator is deterministic per seed)
         ds = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED + rank, skip_mm=not args.mm, events=True,
-                            reads=True)
+                            reads=True, seg_words=args.seg_words)
         hb = synth.to_host_batch(ds, 0, n_sc)
         hr = synth.reads_to_host(ds, 0, n_sc)["reads"]
         del ds

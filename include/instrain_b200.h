@@ -216,9 +216,10 @@ int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb
  *   - segments sorted by seg_start (ascending, ties in any order), all inside [start, start + L), 1 <= seg_len <=
  *     max_seg_len <= 256 (longer blocks are split by the packer);
  *   - words: nibble j of a segment sits in bits 4*(j%8).. of word seg_word[i] + j/8; unused high nibbles of the last
- *     data word are 0; the data words of consecutive segments are separated by EXACTLY one zero word, i.e.
- *     seg_word[0] = 1, seg_word[i+1] = seg_word[i] + ceil(seg_len[i]/8) + 1, and the stream ends with one zero word,
- *     padded with zero words to a multiple of 4 (n_words). */
+ *     data word are 0; the data words of consecutive segments (in table order) are separated by one or two zero words,
+ *     i.e. seg_word[0] >= 1, seg_word[i+1] = seg_word[i] + ceil(seg_len[i]/8) + 1 or + 2 (two when the packer wants an
+ *     odd block size: it spreads K1r's shared-memory banks), the stream ends with a zero word and is padded with zero
+ *     words to a multiple of 4 (n_words); `words` is 16-byte aligned. */
 typedef struct {
     int64_t n_segs;
     const int32_t *seg_start;   /* [n_segs] batch coordinate of the first base */

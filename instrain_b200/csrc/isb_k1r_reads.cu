@@ -23,11 +23,13 @@
 // HBM traffic: 0.5 B per aligned base + ~22 B per segment in, 16*M B per position out (vs 6-10 B per event in for K1).
 // The kernel is bound by issue slots / shared-memory bandwidth, not by HBM (profiles/README.md).
 #include "isb_common.cuh"
+#include <climits>
 
 #define K1R_THREADS 128
 #define K1R_MAXLEN 256                 // hard cap of max_seg_len
 #define K1R_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
 #define K1R_WPS (K1R_MAXLEN / 8 + 1)   // worst-case words per segment incl. its separator
+#define K1R_STAGE_IT 9                 // segment-table elements per thread per chunk: seg_cap <= 9 * 128
 
 struct k1r_args {
     isb_reads_dev rd;
@@ -202,26 +204,53 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
             isb_mbar_expect_tx(bar, (unsigned)wn * 4u);
             isb_bulk_g2s(s_words, a.rd.words + wb, (unsigned)wn * 4u, bar);
         }
-        for (int i = t; i < nc; i += K1R_THREADS) {
-            const int64_t g = c0 + i;
-            const int32_t s_abs = __ldg(a.rd.seg_start + g);
-            const int32_t s = s_abs - a.start;
-            const int n = __ldg(a.rd.seg_len + g);
-            const int64_t w = __ldg(a.rd.seg_word + g);
-            const int64_t wl = w - wb;
-            if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + ((n + 7) >> 3) + 1 > wn ||
-                (g > 0 && __ldg(a.rd.seg_start + g - 1) > s_abs))
-                err |= ISB_DEV_ERR_SEG;
-            const int n_c = min(max(n, 0), maxlen);
-            const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
-            s_meta[i] = make_int2(wl_c * 8 - s, s + n_c);         // nibble address of position p = x + p; covered while p < y
-            s_start[i] = s;
+        // Segment table of the chunk -> shared memory.  All global loads of the (up to K1R_STAGE_IT) elements a thread
+        // handles are issued before the first is used, so the block pays ONE memory latency here instead of one per
+        // element (ncu: the per-element version spent 36 % of its cycles on this loop's long-scoreboard stalls).
+        {
+            int32_t r_s[K1R_STAGE_IT], r_prev[K1R_STAGE_IT], r_pid[K1R_STAGE_IT];
+            int r_n[K1R_STAGE_IT];
+            int64_t r_w[K1R_STAGE_IT];
+#pragma unroll
+            for (int k = 0; k < K1R_STAGE_IT; ++k) {
+                const int i = t + k * K1R_THREADS;
+                const int64_t g = c0 + i;
+                r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1; r_pid[k] = 0;
+                if (i < nc) {
+                    r_s[k] = __ldg(a.rd.seg_start + g);
+                    r_n[k] = __ldg(a.rd.seg_len + g);
+                    r_w[k] = __ldg(a.rd.seg_word + g);
+                    if (g > 0) r_prev[k] = __ldg(a.rd.seg_start + g - 1);
+                    if (!kM1) r_pid[k] = __ldg(a.rd.seg_pair + g);
+                }
+            }
+            int r_mm[K1R_STAGE_IT];
             if (!kM1) {
-                const int32_t pid = __ldg(a.rd.seg_pair + g);
-                int mm = 255;
-                if (pid >= 0 && (int64_t)pid < a.n_pairs) mm = __ldg(a.pair_mm + pid);
-                if (mm >= a.M) { err |= ISB_DEV_ERR_MM; mm = 255; }
-                s_mm[i] = (uint8_t)mm;
+#pragma unroll
+                for (int k = 0; k < K1R_STAGE_IT; ++k) {
+                    r_mm[k] = 255;
+                    if (t + k * K1R_THREADS < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
+                        r_mm[k] = __ldg(a.pair_mm + r_pid[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K1R_STAGE_IT; ++k) {
+                const int i = t + k * K1R_THREADS;
+                if (i >= nc) break;
+                const int32_t s = r_s[k] - a.start;
+                const int n = r_n[k];
+                const int64_t wl = r_w[k] - wb;
+                if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + ((n + 7) >> 3) + 1 > wn ||
+                    r_prev[k] > r_s[k])
+                    err |= ISB_DEV_ERR_SEG;
+                const int n_c = min(max(n, 0), maxlen);
+                const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
+                s_meta[i] = make_int2(wl_c * 8 - s, s + n_c);     // nibble address of position p = x + p; covered while p < y
+                s_start[i] = s;
+                if (!kM1) {
+                    if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
+                    s_mm[i] = (uint8_t)r_mm[k];
+                }
             }
         }
         __syncthreads();
@@ -361,7 +390,7 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     a.nmask = nmask; a.d_err = ctx->d_err;
     // Shared-memory budget: the staging area should hold the whole candidate set of a tile (then every thread works in
     // every chunk); two blocks per SM.  Bytes per staged segment: its words incl. separator + 8 (meta) + 1 (mm).
-    const int wps = rd->max_seg_len / 8 + 2;
+    const int wps = rd->max_seg_len / 8 + 3;                      // data words + up to two separator words
     const size_t per_seg = (size_t)wps * 4 + 13;
     const int groups = M == 1 ? 1 : (M + K1R_LEVELS - 1) / K1R_LEVELS;
     const int Mg = M == 1 ? 0 : (M < K1R_LEVELS ? M : K1R_LEVELS);
@@ -372,6 +401,7 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     const int64_t avg_need = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1R_TILE + rd->max_seg_len) * 1.25) + 32 : 32;
     if (seg_cap > avg_need) seg_cap = (int)avg_need;              // no point staging more than a tile ever holds
     if (seg_cap < 64) seg_cap = 64;
+    if (seg_cap > K1R_STAGE_IT * K1R_THREADS) seg_cap = K1R_STAGE_IT * K1R_THREADS;
     a.seg_cap = seg_cap;
     a.words_cap = (seg_cap * wps + 8 + 3) & ~3;
     const size_t smem = (((size_t)a.words_cap * 4 + (size_t)seg_cap * 13 + 7) & ~(size_t)7) + 16 + acc_bytes;

@@ -215,13 +215,14 @@ __global__ void synth_events(isbs_params prm, int K, uint32_t dens24, int64_t Lt
 // ---- read-major output: the same fragments as aligned segments (one per mate), sorted by start ------------------------
 // one thread per position: the segments STARTING there (mate 1 of the fragments starting at pg, then mate 2 of the
 // fragments whose second mate starts at pg).  kFill = false counts, kFill = true writes the segment table.
-#define SEG_WORDS ((READLEN + 7) / 8 + 1)          // data words + the zero separator
+#define SEG_DATA_WORDS ((READLEN + 7) / 8)
+static int g_seg_words = SEG_DATA_WORDS + 1;       // data words + 1 (or 2) zero separator words
 template <bool kFill>
 __global__ void synth_seg_table(isbs_params prm, int K, uint32_t dens24, int64_t Ltot, const int32_t *__restrict__ slot_id,
                                 const uint16_t *__restrict__ slot_F, const int64_t *__restrict__ seg_off,
                                 int32_t *__restrict__ cnt, int32_t *__restrict__ seg_start, uint16_t *__restrict__ seg_len,
                                 int32_t *__restrict__ seg_pair, int64_t *__restrict__ seg_word, int64_t *__restrict__ seg_src,
-                                uint8_t *__restrict__ ref)
+                                uint8_t *__restrict__ ref, int SEG_WORDS)
 {
     const int64_t pg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pg >= Ltot) return;
@@ -260,7 +261,7 @@ __global__ void synth_seg_table(isbs_params prm, int K, uint32_t dens24, int64_t
 // one thread per segment: its READLEN one-hot codes (A=1,C=2,T=4,G=8; 0 = fails min_qual after the overlap tweak)
 __global__ void synth_seg_words(isbs_params prm, uint32_t dens24, int64_t n_segs, const int32_t *__restrict__ seg_start,
                                 const int64_t *__restrict__ seg_src, const uint16_t *__restrict__ slot_F, int min_qual,
-                                uint32_t *__restrict__ words)
+                                uint32_t *__restrict__ words, int SEG_WORDS)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_segs) return;
@@ -273,7 +274,7 @@ __global__ void synth_seg_words(isbs_params prm, uint32_t dens24, int64_t n_segs
     const uint32_t hu = (r1 >> 32) & 0xffff;
     const int hap = (hu >= 26214) + (hu >= 45875) + (hu >= 58982);
     uint32_t *dst = words + 1 + i * SEG_WORDS;
-    for (int wj = 0; wj < SEG_WORDS; ++wj) {
+    for (int wj = 0; wj < SEG_DATA_WORDS; ++wj) {
         uint32_t word = 0;
         for (int nb = 0; nb < 8; ++nb) {
             const int o = wj * 8 + nb;
@@ -294,7 +295,7 @@ __global__ void synth_seg_words(isbs_params prm, uint32_t dens24, int64_t n_segs
             const int b = mate ? b2 : b1, q = mate ? q2 : q1;
             if (q >= min_qual) word |= (1u << b) << (4 * nb);
         }
-        dst[wj] = word;                            // the last word of the block is the zero separator
+        dst[wj] = word;                            // the separator words stay zero (buffer is pre-zeroed)
     }
 }
 
@@ -368,7 +369,10 @@ int isbs_plan(int device, const isbs_params *prm, int64_t *n_events, int64_t *n_
 
 // Phase 2 (optional, before isbs_fill): the same data set as a read-major batch.  n_segs = 2 * n_pairs segments of READLEN
 // bases, n_words = isbs_reads_words(n_segs) words; all buffers caller-owned DEVICE memory.
-int64_t isbs_reads_words(int64_t n_segs) { return (1 + n_segs * SEG_WORDS + 3) / 4 * 4; }
+int64_t isbs_reads_words(int64_t n_segs) { return (1 + n_segs * g_seg_words + 3) / 4 * 4; }
+// words per segment block: READLEN/8 data words + 1 separator (default) or + 2 (an odd block size spreads the
+// shared-memory banks of K1r's per-lane word fetches)
+int isbs_set_seg_words(int w) { if (w < SEG_DATA_WORDS + 1 || w > SEG_DATA_WORDS + 2) return -1; g_seg_words = w; return 0; }
 
 int isbs_fill_reads(int32_t *seg_start, uint16_t *seg_len, int32_t *seg_pair, int64_t *seg_word, uint32_t *words,
                     uint8_t *pair_mm, uint8_t *ref, int min_qual)
@@ -381,17 +385,17 @@ int isbs_fill_reads(int32_t *seg_start, uint16_t *seg_len, int32_t *seg_pair, in
     SYN_CUDA(cudaMalloc(&seg_off, sizeof(int64_t) * (size_t)g.Ltot));
     SYN_CUDA(cudaMalloc(&cnt, sizeof(int32_t) * (size_t)g.Ltot));
     synth_seg_table<false><<<(unsigned)((g.Ltot + 127) / 128), 128>>>(g.prm, g.K, dens24, g.Ltot, g.slot_id, g.slot_F, nullptr,
-                                                                      cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                      cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, g_seg_words);
     SYN_CUDA(cudaGetLastError());
     int64_t total = 0;
     if (run_scan(CovFn{cnt}, OffSink{seg_off}, g.Ltot, g.scan_tmp, g.d_tot, &total)) return -1;
     if (total != n_segs) { snprintf(g.err, sizeof(g.err), "segment count mismatch %lld vs %lld", (long long)total, (long long)n_segs); return -1; }
     synth_seg_table<true><<<(unsigned)((g.Ltot + 127) / 128), 128>>>(g.prm, g.K, dens24, g.Ltot, g.slot_id, g.slot_F, seg_off,
-                                                                     nullptr, seg_start, seg_len, seg_pair, seg_word, seg_src, ref);
+                                                                     nullptr, seg_start, seg_len, seg_pair, seg_word, seg_src, ref, g_seg_words);
     SYN_CUDA(cudaGetLastError());
     SYN_CUDA(cudaMemset(words, 0, sizeof(uint32_t) * (size_t)isbs_reads_words(n_segs)));
     if (n_segs > 0) {
-        synth_seg_words<<<(unsigned)((n_segs + 127) / 128), 128>>>(g.prm, dens24, n_segs, seg_start, seg_src, g.slot_F, min_qual, words);
+        synth_seg_words<<<(unsigned)((n_segs + 127) / 128), 128>>>(g.prm, dens24, n_segs, seg_start, seg_src, g.slot_F, min_qual, words, g_seg_words);
         SYN_CUDA(cudaGetLastError());
     }
     synth_pair_mm<<<(unsigned)((g.n_slots + 255) / 256), 256>>>(g.slot_id, g.slot_mm, g.n_slots, g.prm.skip_mm, pair_mm);

@@ -16,7 +16,7 @@ MAX_SEG_LEN = 256
 NO_EVENT = 255
 
 
-def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_SEG_LEN):
+def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_SEG_LEN, odd_blocks=False):
     """seg_*: per-segment arrays in ANY order; codes: one uint8 per aligned base of all segments -- 0..3 = A,C,T,G event,
     4 = passing non-ACGT base, NO_EVENT (255) = not an event -- segment i occupying codes[code_off[i] : code_off[i] +
     seg_len[i]] (default: back to back).  Splits segments longer than MAX_SEG_LEN, sorts by start (stable), lays out the
@@ -42,10 +42,13 @@ def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_
     seg_start, seg_len, seg_pair, code_off = seg_start[order], seg_len[order], seg_pair[order], code_off[order]
     n = len(seg_start)
     nw = (seg_len + 7) // 8
+    blk = nw + 1                                                           # data words + separator(s)
+    if odd_blocks:
+        blk = blk + (1 - blk % 2)                                          # odd block sizes spread K1r's shared-memory banks
     seg_word = np.ones(n, dtype=np.int64)
     if n:
-        seg_word[1:] = 1 + np.cumsum(nw[:-1] + 1)
-    n_words = int(seg_word[-1] + nw[-1] + 1) if n else 1
+        seg_word[1:] = 1 + np.cumsum(blk[:-1])
+    n_words = int(seg_word[-1] + blk[-1]) if n else 1
     n_words = (n_words + 3) // 4 * 4
     # nibble j of segment i -> word seg_word[i] + j // 8, bits 4 * (j % 8)
     tot = int(seg_len.sum())
@@ -68,7 +71,7 @@ def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_
                 nev_pair=nev_pair.astype(np.int32))
 
 
-def events_to_reads(ev, min_qual=30, max_len=MAX_SEG_LEN):
+def events_to_reads(ev, min_qual=30, max_len=MAX_SEG_LEN, odd_blocks=False):
     """Position-major (or any-order) event columns -> read-major batch arrays.  Events below min_qual keep their place in
     their run as NO_EVENT."""
     pos = np.asarray(ev["ref_pos"], dtype=np.int64)
@@ -92,7 +95,7 @@ def events_to_reads(ev, min_qual=30, max_len=MAX_SEG_LEN):
     starts = np.nonzero(brk)[0]
     seg_len = np.diff(np.append(starts, n))
     codes = np.where(ok, base, NO_EVENT).astype(np.uint8)
-    return build_reads(pos[starts], seg_len, rid[starts], codes, starts, max_len)
+    return build_reads(pos[starts], seg_len, rid[starts], codes, starts, max_len, odd_blocks)
 
 
 def reads_to_events(rd, min_qual=30):

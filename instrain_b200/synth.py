@@ -36,6 +36,8 @@ def _load():
         _lib.isbs_reads_words.restype = C.c_int64
         _lib.isbs_reads_words.argtypes = [C.c_int64]
         _lib.isbs_free.restype = C.c_int
+        _lib.isbs_set_seg_words.restype = C.c_int
+        _lib.isbs_set_seg_words.argtypes = [C.c_int]
     return _lib
 
 
@@ -63,12 +65,15 @@ READLEN = 150
 
 
 def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, window_len=10000, events=True, reads=False,
-             min_qual=30):
+             min_qual=30, seg_words=None):
     """Returns a dict of CUDA torch tensors + splits (CUDA int32).  events=True: position-major event columns (ref_pos,
     base, qual, read_id); reads=True: the SAME fragments as a read-major batch under key "reads" (seg_start, seg_len,
     seg_pair, seg_word, words, ...; instrain_b200/reads.py layout).  Always: pair_mm, ref_codes."""
     import torch
     lib = _load()
+    spw = (READLEN + 7) // 8 + 1 if seg_words is None else int(seg_words)
+    if lib.isbs_set_seg_words(spw) != 0:
+        raise ValueError("seg_words must be %d or %d" % ((READLEN + 7) // 8 + 1, (READLEN + 7) // 8 + 2))
     prm = _Params(L, n_scaffolds, coverage, float(snv_density), seed, 1 if skip_mm else 0, 0)
     n_ev, n_pairs = C.c_int64(0), C.c_int64(0)
     if lib.isbs_plan(device, C.byref(prm), C.byref(n_ev), C.byref(n_pairs)) != 0:
@@ -80,7 +85,7 @@ def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, 
     if reads:
         n_segs = 2 * npairs
         n_words = int(lib.isbs_reads_words(n_segs))
-        rd = dict(n_segs=n_segs, n_words=n_words, max_seg_len=READLEN,
+        rd = dict(n_segs=n_segs, n_words=n_words, max_seg_len=READLEN, seg_words=spw,
                   seg_start=torch.empty(max(n_segs, 1), dtype=torch.int32, device=dev)[:n_segs],
                   seg_len=torch.empty(max(n_segs, 1), dtype=torch.int16, device=dev)[:n_segs],
                   seg_pair=torch.empty(max(n_segs, 1), dtype=torch.int32, device=dev)[:n_segs],
@@ -127,7 +132,7 @@ def reads_to_host(d, lo_scaffold=0, n_scaffolds=1):
     pair = rd["seg_pair"][s_lo:s_hi]
     id_lo, id_hi = (int(pair.min()), int(pair.max()) + 1) if n else (0, 0)
     w_lo = int(rd["seg_word"][s_lo]) - 1 if n else 0
-    spw = (READLEN + 7) // 8 + 1
+    spw = rd["seg_words"]
     n_words = (1 + n * spw + 3) // 4 * 4
     words = np.zeros(n_words, dtype=np.uint32)
     words[:1 + n * spw] = rd["words"][w_lo:w_lo + 1 + n * spw].cpu().numpy().view(np.uint32)

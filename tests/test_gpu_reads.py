@@ -141,7 +141,7 @@ def test_read_major_equals_position_major_larger(eng, null_lut):
     """Both CUDA paths on a batch the oracle would take minutes for: identical tables."""
     for skip_mm in (True, False):
         batch = synth.make_batch(400000, 60, 0.01, 99, n_scaffolds=2, skip_mm=skip_mm)
-        rd = reads.events_to_reads(batch, max_len=150 if skip_mm else 256)
+        rd = reads.events_to_reads(batch, max_len=150 if skip_mm else 256, odd_blocks=skip_mm)
         M = int(batch["pair_mm"].max()) + 1
         want = ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld")
         a = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want)
@@ -158,7 +158,8 @@ def test_device_generator_reads_equal_events(eng, null_lut):
     give identical tables on the device-resident data, and a host slice of the segments matches the oracle."""
     from instrain_b200 import synth as dsynth
     for skip_mm in (True, False):
-        d = dsynth.generate(0, 50000, 3, 60, 0.01, 77, skip_mm=skip_mm, events=True, reads=True)
+        d = dsynth.generate(0, 50000, 3, 60, 0.01, 77, skip_mm=skip_mm, events=True, reads=True,
+                            seg_words=21 if skip_mm else None)
         rd = d["reads"]
         assert rd["n_segs"] == 2 * d["pair_mm"].numel() and int(rd["seg_len"].min()) == 150
         M = int(d["pair_mm"].max().item()) + 1
