@@ -17,8 +17,10 @@
 #include "isb_common.cuh"
 #include "isb_scan.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 #define K3_THREADS 256
+#define K3_ROW_SCRATCH 64            // words of per-warp shared scratch for assembling a site's bit rows
 
 struct k3_args {
     // events
@@ -137,44 +139,115 @@ __global__ void __launch_bounds__(256) k3r_site_cand(k3_args a, isb_reads_dev rd
     a.meta[k].split = k3_site_split(a, abs_pos);
 }
 
-__global__ void __launch_bounds__(K3_THREADS) k3r_site_fill(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
-                                                            const int32_t *__restrict__ n_cand,
-                                                            const int64_t *__restrict__ ev_off, uint8_t *__restrict__ ev_base,
-                                                            uint8_t *__restrict__ ev_qual, int32_t *__restrict__ ev_id)
+// One candidate of a site: is position abs_pos covered by segment g with a passing A/C/T/G base?
+__device__ __forceinline__ bool k3r_candidate(const isb_reads_dev &rd, int64_t g, int64_t abs_pos, int &b, int &id)
 {
+    const int j = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
+    if (j < 0 || j >= (int)__ldg(rd.seg_len + g)) return false;
+    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (j >> 3));
+    const uint32_t code = (w >> ((j & 7) << 2)) & 15u;
+    if (!code) return false;
+    b = __ffs((int)code) - 1;                                       // one-hot A,C,T,G
+    id = __ldg(rd.seg_pair + g);
+    return true;
+}
+
+__device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m, int na, unsigned bases, int b, int id,
+                                           unsigned int *d_err)
+{
+    const int w = (id >> 5) - m.wlo;
+    const uint32_t bit = 1u << (id & 31);
+    const int r = __popc(bases & ((1u << b) - 1u));
+    const bool dbl = atomicOr(any + w, bit) & bit;                    // second entry of this pair on this site
+    uint32_t *ge1 = any + (size_t)(1 + r) * m.nw;
+    if (atomicOr(ge1 + w, bit) & bit) {
+        uint32_t *ge2 = any + (size_t)(1 + na + r) * m.nw;
+        if (atomicOr(ge2 + w, bit) & bit) atomicOr(d_err, ISB_DEV_ERR_MULT);
+    }
+    return dbl;
+}
+
+// Fused read-major front end (warp per site): gather the site's qualifying (pair id, base) entries from its candidate
+// segments into a per-warp shared-memory list, derive the pair-id window, allocate the bit rows with one atomicAdd on
+// the word counter, assemble them (shared-memory scratch for the common small windows) and store them.  The events
+// never touch global memory; sites with more qualifying entries than the list holds gather a second time.
+#define K3R_EV_CAP 320
+__global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
+                                                            const int32_t *__restrict__ n_cand, int64_t *__restrict__ row_off,
+                                                            unsigned long long *__restrict__ row_words_total, int64_t row_cap)
+{
+    __shared__ uint32_t s_rows[K3_THREADS / 32][K3_ROW_SCRATCH];
+    __shared__ int32_t s_id[K3_THREADS / 32][K3R_EV_CAP];
+    __shared__ uint8_t s_b[K3_THREADS / 32][K3R_EV_CAP];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     for (int64_t k = warp0; k < a.S; k += n_warps) {
-        const int64_t abs_pos = (int64_t)a.site_pos[k] + a.start;
-        const int64_t clo = cand_lo[k], off = ev_off[k];
+        const int32_t p = a.site_pos[k];
+        const int64_t abs_pos = (int64_t)p + a.start;
+        const unsigned bases = a.site_flags[p] & 0xF;
+        const int na = __popc(bases);
+        const int64_t clo = cand_lo[k];
         const int nc = n_cand[k];
-        int cnt = 0;
+        int cnt = 0, idmin = INT_MAX, idmax = -1;
         for (int i0 = 0; i0 < nc; i0 += 32) {
-            const int i = i0 + lane;
-            bool ok = false;
             int b = 0, id = 0;
-            if (i < nc) {
-                const int64_t g = clo + i;
-                const int j = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
-                if (j >= 0 && j < (int)__ldg(rd.seg_len + g)) {
-                    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (j >> 3));
-                    const uint32_t code = (w >> ((j & 7) << 2)) & 15u;
-                    if (code) { ok = true; b = __ffs((int)code) - 1; id = __ldg(rd.seg_pair + g); }   // one-hot A,C,T,G
-                }
-            }
+            bool ok = (i0 + lane < nc) && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id);
+            ok = ok && ((bases >> b) & 1u);
             const unsigned mask = __ballot_sync(ISB_FULL, ok);
             if (ok) {
-                const int64_t e = off + cnt + __popc(mask & ((1u << lane) - 1u));
-                ev_base[e] = (uint8_t)b;
-                ev_qual[e] = 255;
-                ev_id[e] = id;
+                const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+                if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
+                idmin = min(idmin, id);
+                idmax = max(idmax, id);
             }
             cnt += __popc(mask);
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            idmin = min(idmin, __shfl_xor_sync(ISB_FULL, idmin, d));
+            idmax = max(idmax, __shfl_xor_sync(ISB_FULL, idmax, d));
+        }
+        isb_site_meta m = a.meta[k];                                   // .split was set by k3r_site_cand
+        m.ev_lo_rel = 0;
+        m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
+        m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
+        const int n_words = (1 + 2 * na) * m.nw;
+        unsigned long long off = 0;
+        if (lane == 0 && n_words > 0) off = atomicAdd(row_words_total, (unsigned long long)n_words);
+        off = __shfl_sync(ISB_FULL, off, 0);
+        const bool fits = (int64_t)(off + n_words) <= row_cap;
+        if (!fits) {                                                   // host grows the row storage and re-runs
+            if (lane == 0) atomicOr(a.d_err, ISB_DEV_ERR_ROWBUF);
+            m.nw = 0;
+        }
         if (lane == 0) {
-            a.site_ev[2 * k] = off;
-            a.site_ev[2 * k + 1] = off + cnt;
+            a.meta[k] = m;
+            row_off[k] = (int64_t)off;
+            a.has2[k] = 0;
+        }
+        if (m.nw == 0) continue;
+        const bool in_smem = n_words <= K3_ROW_SCRATCH;
+        uint32_t *g_any = a.rows + off;
+        uint32_t *any = in_smem ? s_rows[wib] : g_any;
+        for (int i = lane; i < n_words; i += 32) any[i] = 0u;
+        __syncwarp();
+        bool dbl = false;
+        if (cnt <= K3R_EV_CAP) {
+            for (int e = lane; e < cnt; e += 32) dbl |= k3_row_set(any, m, na, bases, s_b[wib][e], s_id[wib][e], a.d_err);
+        } else {
+            for (int i0 = 0; i0 < nc; i0 += 32) {
+                int b = 0, id = 0;
+                if (i0 + lane < nc && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id) && ((bases >> b) & 1u))
+                    dbl |= k3_row_set(any, m, na, bases, b, id, a.d_err);
+            }
+        }
+        if (__any_sync(ISB_FULL, dbl) && lane == 0) a.has2[k] = 1;
+        __syncwarp();
+        if (in_smem) {
+            for (int i = lane; i < n_words; i += 32) g_any[i] = any[i];
+            __syncwarp();
         }
     }
 }
@@ -217,7 +290,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_site_windows(k3_args a)
 // Warp per site.  Rows of a site that fit in the warp's 64-word shared-memory scratch (the common case: 1 + 2*|bases|
 // rows x <= 12 words) are assembled there with shared-memory atomics and stored once, coalesced; larger windows fall
 // back to global atomics on the (pre-zeroed) row storage.
-#define K3_ROW_SCRATCH 64
 __global__ void __launch_bounds__(K3_THREADS) k3_build_rows(k3_args a)
 {
     __shared__ uint32_t s_rows[K3_THREADS / 32][K3_ROW_SCRATCH];
@@ -478,14 +550,26 @@ __global__ void __launch_bounds__(256) k3_pair_stats(k3_args a, int64_t n_pairs_
 // Self edges: a pair with two entries (first, second in column order) on ONE site gives the combo
 // "b_first:b_second" on the edge (p, p) (itertools.combinations over the pair's entry list).  Rare: one thread per
 // flagged site, exact and slow.
-__global__ void __launch_bounds__(128) k3_self_edges(k3_args a)
+template <bool kReads>
+__global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
+                                                     const int32_t *__restrict__ n_cand)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.S; k += stride) {
         if (!a.has2[k] || a.meta[k].split < 0) continue;
         const int32_t p = a.site_pos[k];
+        const int64_t abs_pos = (int64_t)p + a.start;
         const unsigned bases = a.site_flags[p] & 0xF;
-        const int64_t lo = a.site_ev[2 * k], hi = a.site_ev[2 * k + 1];
+        // entries of the site in column order: event range (position-major) or candidate segments (read-major)
+        const int64_t lo = kReads ? cand_lo[k] : a.site_ev[2 * k];
+        const int64_t hi = kReads ? lo + n_cand[k] : a.site_ev[2 * k + 1];
+        auto entry = [&](int64_t e, int &b, int &rid) -> bool {
+            if (kReads) return k3r_candidate(rd, e, abs_pos, b, rid) && ((bases >> b) & 1u);
+            if (!k3_qualifies(a, e, bases)) return false;
+            b = a.base[e];
+            rid = a.read_id[e];
+            return true;
+        };
         int K[16];
         for (int i = 0; i < 16; ++i) K[i] = 0;
         int C[4] = {0, 0, 0, 0};
@@ -494,14 +578,16 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a)
             C[0] += E.x; C[1] += E.y; C[2] += E.z; C[3] += E.w;
             bool added = false;
             for (int64_t e2 = lo; e2 < hi; ++e2) {
-                if (!k3_qualifies(a, e2, bases)) continue;
-                const int rid = a.read_id[e2];
+                int b2, rid;
+                if (!entry(e2, b2, rid)) continue;
                 if ((a.M > 1 ? a.pair_mm[rid] : 0) != m) continue;
-                for (int64_t e1 = lo; e1 < e2; ++e1)
-                    if (a.read_id[e1] == rid && k3_qualifies(a, e1, bases)) {
-                        K[a.base[e1] * 4 + a.base[e2]] += 1;
+                for (int64_t e1 = lo; e1 < e2; ++e1) {
+                    int b1, rid1;
+                    if (entry(e1, b1, rid1) && rid1 == rid) {
+                        K[b1 * 4 + b2] += 1;
                         added = true;
                     }
+                }
             }
             if (!added) continue;
             if (!k3_level_present(a, p, m, E)) continue;
@@ -567,80 +653,66 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
     a.out = rows; a.cap = cap;
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
 
-    // 2. per-site event range + pair-id window
+    // 2.-5. bit rows of the sites, then linked pairs
     const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;
     const int grid_sites = (int)(site_warps_blocks < (int64_t)ctx->sm_count * 32 ? site_warps_blocks : (int64_t)ctx->sm_count * 32);
     const int nbs = (int)((S + SCAN_BLOCK - 1) / SCAN_BLOCK);
     if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)(nb > nbs ? nb : nbs)))) return rc;
     block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
-    if (!rd) {                                                  // position-major columns: searches bounded by tile offsets
-        const int tp = 1024;
-        const int n_tiles = (L + tp - 1) / tp;
-        if ((rc = isb_tile_offsets(ctx, ref_pos, n, start, L, tp, n_tiles))) return rc;
-        a.tile_off = (const int64_t *)ctx->buf[SL_K3_TILE_OFF].p;
-        a.tile_tp = tp;
-        k3_site_ranges<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
-        ISB_LAUNCH_CHECK();
-    } else {                                                    // read-major segments: gather the sites' events
-        if ((rc = isb_ensure(ctx, SL_RD_CAND, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)S))) return rc;
-        if ((rc = isb_ensure(ctx, SL_RD_EVOFF, sizeof(int64_t) * (size_t)S))) return rc;
-        int64_t *cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
-        int32_t *n_cand = (int32_t *)(cand_lo + S);
-        int64_t *ev_off = (int64_t *)ctx->buf[SL_RD_EVOFF].p;
-        k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
-        ISB_LAUNCH_CHECK();
-        WordsFn cf{n_cand};
-        scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(cf, S, block_sums);
-        ISB_LAUNCH_CHECK();
-        scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nbs, ctx->d_counters + 6);
-        ISB_LAUNCH_CHECK();
-        RowOffSink eos{ev_off};
-        scan_scatter<<<nbs, SCAN_THREADS, 0, st>>>(cf, S, block_sums, eos);
-        ISB_LAUNCH_CHECK();
-        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 6, ctx->d_counters + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        ISB_CUDA(cudaStreamSynchronize(st));
-        const size_t n_ev_cap = (size_t)ctx->h_counters[6] + 16;
-        if ((rc = isb_ensure(ctx, SL_RD_EVB, n_ev_cap))) return rc;
-        if ((rc = isb_ensure(ctx, SL_RD_EVQ, n_ev_cap))) return rc;
-        if ((rc = isb_ensure(ctx, SL_RD_EVID, sizeof(int32_t) * n_ev_cap))) return rc;
-        uint8_t *ev_base = (uint8_t *)ctx->buf[SL_RD_EVB].p, *ev_qual = (uint8_t *)ctx->buf[SL_RD_EVQ].p;
-        int32_t *ev_id = (int32_t *)ctx->buf[SL_RD_EVID].p;
-        k3r_site_fill<<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cand_lo, n_cand, ev_off, ev_base, ev_qual, ev_id);
-        ISB_LAUNCH_CHECK();
-        a.base = ev_base; a.qual = ev_qual; a.read_id = ev_id; a.min_qual = 0;
-    }
-    k3_site_windows<<<grid_sites, K3_THREADS, 0, st>>>(a);
-    ISB_LAUNCH_CHECK();
-
-    // 3. bit-row storage offsets
-    WordsFn wf{a.site_words};
-    scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums);
-    ISB_LAUNCH_CHECK();
-    scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nbs, ctx->d_counters + 4);
-    ISB_LAUNCH_CHECK();
-    RowOffSink ros{(int64_t *)ctx->buf[SL_ROW_OFF].p};
-    scan_scatter<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums, ros);
-    ISB_LAUNCH_CHECK();
-    ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    ISB_CUDA(cudaStreamSynchronize(st));
-    const size_t total_words = (size_t)ctx->h_counters[4];
-    if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (total_words + 4)))) return rc;
-    a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
-    ISB_CUDA(cudaMemsetAsync(a.rows, 0, sizeof(uint32_t) * (total_words + 4), st));
-
-    // 4. mm <= m masks
-    if (M > 1) {
+    if (M > 1) {                                                // mm <= m masks
         a.nwp = (n_pairs + 31) / 32;
         if ((rc = isb_ensure(ctx, SL_MM_MASK, sizeof(uint32_t) * (size_t)a.nwp * M))) return rc;
         k3_mm_masks<<<(int)((a.nwp + 255) / 256), 256, 0, st>>>(pair_mm, n_pairs, M, a.nwp, (uint32_t *)ctx->buf[SL_MM_MASK].p);
         ISB_LAUNCH_CHECK();
         a.mle = (const uint32_t *)ctx->buf[SL_MM_MASK].p;
     }
-
-    // 5. rows, pairs, self edges
-    k3_build_rows<<<grid_sites, K3_THREADS, 0, st>>>(a);
-    ISB_LAUNCH_CHECK();
-    for (int attempt = 0; attempt < 2; ++attempt) {                    // linked-pair list, then one thread per pair
+    int64_t *cand_lo = nullptr;
+    int32_t *n_cand = nullptr;
+    if (!rd) {                                                  // position-major columns
+        const int tp = 1024;                                    // searches bounded by position-tile event offsets
+        const int n_tiles = (L + tp - 1) / tp;
+        if ((rc = isb_tile_offsets(ctx, ref_pos, n, start, L, tp, n_tiles))) return rc;
+        a.tile_off = (const int64_t *)ctx->buf[SL_K3_TILE_OFF].p;
+        a.tile_tp = tp;
+        k3_site_ranges<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+        ISB_LAUNCH_CHECK();
+        k3_site_windows<<<grid_sites, K3_THREADS, 0, st>>>(a);
+        ISB_LAUNCH_CHECK();
+        WordsFn wf{a.site_words};                               // bit-row storage offsets
+        scan_reduce<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums);
+        ISB_LAUNCH_CHECK();
+        scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nbs, ctx->d_counters + 4);
+        ISB_LAUNCH_CHECK();
+        RowOffSink ros{(int64_t *)ctx->buf[SL_ROW_OFF].p};
+        scan_scatter<<<nbs, SCAN_THREADS, 0, st>>>(wf, S, block_sums, ros);
+        ISB_LAUNCH_CHECK();
+        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 4, ctx->d_counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaStreamSynchronize(st));
+        const size_t total_words = (size_t)ctx->h_counters[4];
+        if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (total_words + 4)))) return rc;
+        a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
+        ISB_CUDA(cudaMemsetAsync(a.rows, 0, sizeof(uint32_t) * (total_words + 4), st));
+        k3_build_rows<<<grid_sites, K3_THREADS, 0, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    } else {                                                    // read-major segments: candidate ranges of the sites
+        if ((rc = isb_ensure(ctx, SL_RD_CAND, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)S))) return rc;
+        cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
+        n_cand = (int32_t *)(cand_lo + S);
+        k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
+        ISB_LAUNCH_CHECK();
+        // initial guess of the row storage (words per site); the fused kernel reports the exact need if it is too small
+        static const int rows_init = getenv("ISB_K3_ROWS_INIT") ? atoi(getenv("ISB_K3_ROWS_INIT")) : 48;
+        if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)S * (size_t)(rows_init > 0 ? rows_init : 1) + 64)))) return rc;
+    }
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (rd) {                                               // fused gather + window + rows (no host sync needed)
+            const int64_t row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
+            a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
+            ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
+            k3r_site_rows<<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
+                                                           ctx->d_counters + 4, row_cap);
+            ISB_LAUNCH_CHECK();
+        }
         int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
         if (cap_pairs < 8 * S) {
             if ((rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(8 * S)))) return rc;
@@ -652,8 +724,16 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(unsigned long long), st));
         k3_enum_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
         ISB_LAUNCH_CHECK();
-        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         ISB_CUDA(cudaStreamSynchronize(st));
+        if (rd && (*ctx->h_err & ISB_DEV_ERR_ROWBUF)) {         // row storage too small: grow to the counted size, redo
+            if (*ctx->h_err & ~ISB_DEV_ERR_ROWBUF) return ISB_OK;   // another error is pending: let the caller report it
+            ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), st));
+            const size_t need = (size_t)ctx->h_counters[4];
+            if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (need + need / 8 + 1024)))) return rc;
+            continue;
+        }
         const int64_t n_listed = (int64_t)ctx->h_counters[3];
         if (n_listed <= cap_pairs) {
             if (n_listed > 0) {
@@ -663,9 +743,11 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
             break;
         }
         if ((rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(n_listed + n_listed / 8)))) return rc;
+        if (attempt == 3) return isb_fail(ctx, ISB_ERR_CUDA, "linkage: scratch sizing did not converge");
     }
     const int grid_self = (int)((S + 127) / 128 < (int64_t)ctx->sm_count * 8 ? (S + 127) / 128 : (int64_t)ctx->sm_count * 8);
-    k3_self_edges<<<grid_self, 128, 0, st>>>(a);
+    if (rd) k3_self_edges<true><<<grid_self, 128, 0, st>>>(a, *rd, cand_lo, n_cand);
+    else k3_self_edges<false><<<grid_self, 128, 0, st>>>(a, isb_reads_dev{}, nullptr, nullptr);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

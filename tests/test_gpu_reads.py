@@ -178,3 +178,26 @@ def test_device_generator_reads_equal_events(eng, null_lut):
         hr = dsynth.reads_to_host(d, 1, 2)
         assert np.array_equal(hb["pair_mm"], hr["pair_mm"])
         check_reads(eng, hb, null_lut, rd=hr["reads"])
+
+
+def test_row_storage_regrow(null_lut):
+    """The fused K3 front end sizes its bit-row storage by a guess and regrows it from the counted need: force the
+    smallest guess (separate process: the guess is read once per process)."""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from conftest import load_batch, load_lut, assert_ld_equal\n"
+            "from oracle import restate\n"
+            "from instrain_b200 import reads\n"
+            "from instrain_b200.engine import Engine\n"
+            "lut = load_lut(); b, _ = load_batch('G1')\n"
+            "exp = restate.profile_events(b, b['ref_codes'], lut[0], lut[1], b['splits'])\n"
+            "e = Engine(0, lut[0], lut[1])\n"
+            "for _ in range(2):\n"
+            "    got = e.profile_batch(b, b['ref_codes'], b['splits'], M=exp['counts'].shape[1], reads=reads.events_to_reads(b), want=('ld',))\n"
+            "    assert_ld_equal(got['ld'], exp['ld'], tol=1e-9)\n"
+            "print('regrow ok', len(got['ld']))\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                      os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ISB_K3_ROWS_INIT="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
