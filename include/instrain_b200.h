@@ -309,6 +309,25 @@ int64_t isb_events_reads_packed(void *events);
 void isb_events_copy(void *events, int32_t *ref_pos, uint8_t *base, uint8_t *qual, int32_t *read_id, uint8_t *pair_mm);
 void isb_events_free(void *events);
 
+/* Same reads as a READ-MAJOR batch (isb_reads_batch): one segment per CIGAR M/=/X block (clipped to the scaffold, split at
+ * 256 bases), sorted by start, one-hot codes for the bases with quality >= min_qual after the overlap tweak, passing
+ * non-ACGT bases in the N-event list.  isb_reads_stream_words() words hold the scaffold's stream ([data words + one zero
+ * word] per segment); a batch stream is one leading zero word + the scaffolds' streams + zero padding to a multiple of
+ * 4 words, and isb_reads_copy() rebases seg_word to word_base = the index where this scaffold's stream is placed. */
+void *isb_pack_scaffold_reads(void *bam, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                              const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual);
+int64_t isb_reads_segs(void *reads);
+int64_t isb_reads_stream_words(void *reads);
+int64_t isb_reads_pairs(void *reads);
+int64_t isb_reads_n_events(void *reads);
+int64_t isb_reads_nev(void *reads);
+int isb_reads_max_len(void *reads);
+int64_t isb_reads_reads_seen(void *reads);
+int64_t isb_reads_reads_packed(void *reads);
+void isb_reads_copy(void *reads, int32_t *seg_start, uint16_t *seg_len, int32_t *seg_pair, int64_t *seg_word,
+                    uint32_t *words, int32_t *nev_pos, int32_t *nev_pair, uint8_t *pair_mm, int64_t word_base);
+void isb_reads_free(void *reads);
+
 /* ---- host read filter (C++, no GPU): BAM -> sR2M --------------------------------------------------------------------- */
 /* Default configuration of the reference's read filter: get_paired_reads (filter_reads.py:885-956),
  * paired_read_filter with pairing_filter='paired_only' (:471-532), filter_scaff2pair2info / evaluate_pair (:201-300,

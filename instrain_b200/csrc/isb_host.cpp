@@ -266,29 +266,30 @@ int isb_bam_peek_tid(void *h)
     return tid < 0 ? -1 : tid;
 }
 
-// Consume every record of scaffold `tid` (the file is coordinate-sorted, so they are contiguous) and pack the reads
-// whose name is in the given list.  names: n_names NUL-free strings concatenated in names_blob, name_off[n_names+1];
-// name_mm[i] = R2M value (0 in set mode).  Coordinates are shifted by pos_offset, pair ids start at pair_id_offset
-// and follow BAM order of first appearance.  Returns an opaque result (isb_events_*), or NULL on error.
-void *isb_pack_scaffold(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
-                        const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset)
+struct Loaded {
+    std::vector<BamRec> recs;
+    std::vector<uint32_t> cigs;
+    std::vector<uint8_t> seq, qual;
+    int64_t n_reads_seen = 0;
+};
+
+// Consume every record of scaffold `tid` (the file is coordinate-sorted, so they are contiguous), keep the reads whose
+// name is in the list and apply the mate-overlap quality tweak in file order (bam_plp overlap_push, ignore_overlaps=True).
+static void load_scaffold(Bam *b, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off, Loaded &ld)
 {
-    Bam *b = (Bam *)h;
     std::unordered_map<std::string, int32_t> name2idx;
     name2idx.reserve((size_t)n_names * 2 + 16);
     for (int64_t i = 0; i < n_names; ++i)
         name2idx.emplace(std::string(names_blob + name_off[i], (size_t)(name_off[i + 1] - name_off[i])), (int32_t)i);
-
-    std::vector<BamRec> recs;
-    std::vector<uint32_t> cigs;
-    std::vector<uint8_t> seq, qual;
-    Events *ev = new Events();
+    std::vector<BamRec> &recs = ld.recs;
+    std::vector<uint32_t> &cigs = ld.cigs;
+    std::vector<uint8_t> &seq = ld.seq, &qual = ld.qual;
     for (;;) {
-        const int t = isb_bam_peek_tid(h);
+        const int t = isb_bam_peek_tid(b);
         if (t != tid) break;
         const uint8_t *p = b->pending.data();
         b->has_pending = false;
-        ev->n_reads_seen++;
+        ld.n_reads_seen++;
         int32_t core[8];
         memcpy(core, p, 32);
         BamRec r;
@@ -316,24 +317,38 @@ void *isb_pack_scaffold(void *h, int tid, int64_t n_names, const char *names_blo
         memcpy(qual.data() + r.seq_off, q, r.l_seq);
         recs.push_back(r);
     }
-    // mate-overlap handling in file order (bam_plp overlap_push with ignore_overlaps=True)
-    {
-        std::unordered_map<int32_t, int32_t> pending;                // name idx -> first mate record
-        for (size_t i = 0; i < recs.size(); ++i) {
-            const BamRec &r = recs[i];
-            if ((r.flag & 0x8) || !(r.flag & 0x2)) continue;
-            const int64_t end = r.pos + ref_len_of(cigs.data() + r.cig_off, r.n_cigar);
-            const int64_t aisize = r.isize < 0 ? -(int64_t)r.isize : r.isize;
-            if ((r.mtid >= 0 && r.tid != r.mtid) || (aisize >= 2 * (int64_t)r.l_seq && r.mpos >= end)) continue;
-            auto it = pending.find(r.name_idx);
-            if (it == pending.end()) {
-                if (r.mpos >= r.pos) pending.emplace(r.name_idx, (int32_t)i);
-            } else {
-                tweak_overlap(recs[it->second], r, cigs.data(), seq.data(), qual.data());
-                pending.erase(it);
-            }
+    std::unordered_map<int32_t, int32_t> pending;                    // name idx -> first mate record
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const BamRec &r = recs[i];
+        if ((r.flag & 0x8) || !(r.flag & 0x2)) continue;
+        const int64_t end = r.pos + ref_len_of(cigs.data() + r.cig_off, r.n_cigar);
+        const int64_t aisize = r.isize < 0 ? -(int64_t)r.isize : r.isize;
+        if ((r.mtid >= 0 && r.tid != r.mtid) || (aisize >= 2 * (int64_t)r.l_seq && r.mpos >= end)) continue;
+        auto it = pending.find(r.name_idx);
+        if (it == pending.end()) {
+            if (r.mpos >= r.pos) pending.emplace(r.name_idx, (int32_t)i);
+        } else {
+            tweak_overlap(recs[it->second], r, cigs.data(), seq.data(), qual.data());
+            pending.erase(it);
         }
     }
+}
+
+// Pack the reads of scaffold `tid` whose name is in the given list as position-major event columns.
+// names: n_names NUL-free strings concatenated in names_blob, name_off[n_names+1];
+// name_mm[i] = R2M value (0 in set mode).  Coordinates are shifted by pos_offset, pair ids start at pair_id_offset
+// and follow BAM order of first appearance.  Returns an opaque result (isb_events_*), or NULL on error.
+void *isb_pack_scaffold(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                        const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset)
+{
+    Bam *b = (Bam *)h;
+    Loaded ld;
+    load_scaffold(b, tid, n_names, names_blob, name_off, ld);
+    std::vector<BamRec> &recs = ld.recs;
+    std::vector<uint32_t> &cigs = ld.cigs;
+    std::vector<uint8_t> &seq = ld.seq, &qual = ld.qual;
+    Events *ev = new Events();
+    ev->n_reads_seen = ld.n_reads_seen;
     // expand M/=/X bases in file order, then stable counting sort by position
     const int64_t L = tid >= 0 && tid < (int)b->ref_lens.size() ? b->ref_lens[tid] : 0;
     std::vector<int32_t> pair_of_name((size_t)n_names, -1);
@@ -398,6 +413,111 @@ void isb_events_copy(void *e, int32_t *ref_pos, uint8_t *base, uint8_t *qual, in
     if (pair_mm) memcpy(pair_mm, ev->pair_mm.data(), ev->pair_mm.size());
 }
 void isb_events_free(void *e) { delete (Events *)e; }
+
+// ---- read-major packer: the same reads as aligned segments (include/instrain_b200.h, isb_reads_batch) -------------------
+// One segment per CIGAR M/=/X block (clipped to the scaffold, split at 256 bases), sorted by start; one-hot 4-bit codes
+// (A=1,C=2,T=4,G=8) for the bases whose quality after the overlap tweak is >= min_qual, 0 otherwise; passing non-ACGT
+// bases go to the N-event list.  The word stream of the scaffold is [data words + one zero word] per segment; the caller
+// concatenates scaffolds behind one leading zero word (isb_reads_copy's word_base).
+struct ReadsOut {
+    std::vector<int32_t> seg_start, seg_pair, nev_pos, nev_pair;
+    std::vector<uint16_t> seg_len;
+    std::vector<int64_t> seg_word;                                   // relative to the scaffold's stream
+    std::vector<uint32_t> words;
+    std::vector<uint8_t> pair_mm;
+    int64_t n_reads_seen = 0, n_reads_packed = 0, n_events = 0;
+    int max_len = 1;
+};
+
+void *isb_pack_scaffold_reads(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                              const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual)
+{
+    Bam *b = (Bam *)h;
+    Loaded ld;
+    load_scaffold(b, tid, n_names, names_blob, name_off, ld);
+    ReadsOut *out = new ReadsOut();
+    out->n_reads_seen = ld.n_reads_seen;
+    const int64_t L = tid >= 0 && tid < (int)b->ref_lens.size() ? b->ref_lens[tid] : 0;
+    std::vector<int32_t> pair_of_name((size_t)n_names, -1);
+    int32_t next_pair = 0;
+    struct Seg { int32_t start; uint16_t len; int32_t pair; int64_t src; };   // src: offset into the record's seq/qual
+    std::vector<Seg> segs;
+    for (const BamRec &r : ld.recs) {
+        if (pair_of_name[r.name_idx] < 0) {
+            pair_of_name[r.name_idx] = next_pair++;
+            out->pair_mm.push_back(name_mm ? name_mm[r.name_idx] : 0);
+        }
+        const int32_t pid = pair_of_name[r.name_idx] + pair_id_offset;
+        int64_t pos = r.pos, qp = 0;
+        for (int c = 0; c < r.n_cigar; ++c) {
+            const int op = ld.cigs[r.cig_off + c] & 0xf;
+            const int64_t len = ld.cigs[r.cig_off + c] >> 4;
+            if (is_match(op)) {
+                int64_t lo = pos < 0 ? 0 : pos, hi = pos + len > L ? L : pos + len;     // clip to the scaffold
+                for (int64_t s0 = lo; s0 < hi; s0 += 256) {
+                    const int64_t n = hi - s0 < 256 ? hi - s0 : 256;
+                    segs.push_back(Seg{(int32_t)s0, (uint16_t)n, pid, (int64_t)r.seq_off + qp + (s0 - pos)});
+                }
+                pos += len; qp += len;
+            } else if (op == OP_I || op == OP_S) qp += len;
+            else if (op == OP_D || op == OP_N) pos += len;
+        }
+        out->n_reads_packed++;
+    }
+    std::vector<int32_t> order(segs.size());
+    for (size_t i = 0; i < segs.size(); ++i) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return segs[x].start < segs[y].start; });
+    const size_t n = segs.size();
+    out->seg_start.resize(n); out->seg_len.resize(n); out->seg_pair.resize(n); out->seg_word.resize(n);
+    int64_t w = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const Seg &sg = segs[order[i]];
+        out->seg_start[i] = sg.start + pos_offset;
+        out->seg_len[i] = sg.len;
+        out->seg_pair[i] = sg.pair;
+        out->seg_word[i] = w;
+        w += ((int64_t)sg.len + 7) / 8 + 1;
+        if (sg.len > out->max_len) out->max_len = sg.len;
+    }
+    out->words.assign((size_t)w, 0u);
+    for (size_t i = 0; i < n; ++i) {
+        const Seg &sg = segs[order[i]];
+        uint32_t *dst = out->words.data() + out->seg_word[i];
+        for (int j = 0; j < sg.len; ++j) {
+            if ((int)ld.qual[sg.src + j] < min_qual) continue;
+            const int code = NT16_TO_CODE[ld.seq[sg.src + j]];
+            out->n_events++;
+            if (code < 4) dst[j >> 3] |= (1u << code) << ((j & 7) << 2);
+            else { out->nev_pos.push_back(sg.start + j + pos_offset); out->nev_pair.push_back(sg.pair); }
+        }
+    }
+    return out;
+}
+
+int64_t isb_reads_segs(void *r) { return (int64_t)((ReadsOut *)r)->seg_start.size(); }
+int64_t isb_reads_stream_words(void *r) { return (int64_t)((ReadsOut *)r)->words.size(); }
+int64_t isb_reads_pairs(void *r) { return (int64_t)((ReadsOut *)r)->pair_mm.size(); }
+int64_t isb_reads_n_events(void *r) { return ((ReadsOut *)r)->n_events; }
+int64_t isb_reads_nev(void *r) { return (int64_t)((ReadsOut *)r)->nev_pos.size(); }
+int isb_reads_max_len(void *r) { return ((ReadsOut *)r)->max_len; }
+int64_t isb_reads_reads_seen(void *r) { return ((ReadsOut *)r)->n_reads_seen; }
+int64_t isb_reads_reads_packed(void *r) { return ((ReadsOut *)r)->n_reads_packed; }
+// copy out; seg_word values are rebased to word_base (the index in the batch stream where this scaffold's stream starts)
+void isb_reads_copy(void *r, int32_t *seg_start, uint16_t *seg_len, int32_t *seg_pair, int64_t *seg_word, uint32_t *words,
+                    int32_t *nev_pos, int32_t *nev_pair, uint8_t *pair_mm, int64_t word_base)
+{
+    ReadsOut *o = (ReadsOut *)r;
+    const size_t n = o->seg_start.size();
+    if (seg_start) memcpy(seg_start, o->seg_start.data(), n * 4);
+    if (seg_len) memcpy(seg_len, o->seg_len.data(), n * 2);
+    if (seg_pair) memcpy(seg_pair, o->seg_pair.data(), n * 4);
+    if (seg_word) for (size_t i = 0; i < n; ++i) seg_word[i] = o->seg_word[i] + word_base;
+    if (words) memcpy(words, o->words.data(), o->words.size() * 4);
+    if (nev_pos) memcpy(nev_pos, o->nev_pos.data(), o->nev_pos.size() * 4);
+    if (nev_pair) memcpy(nev_pair, o->nev_pair.data(), o->nev_pair.size() * 4);
+    if (pair_mm) memcpy(pair_mm, o->pair_mm.data(), o->pair_mm.size());
+}
+void isb_reads_free(void *r) { delete (ReadsOut *)r; }
 
 }  // extern "C"
 

@@ -1,4 +1,4 @@
-"""Host packer: BAM -> position-major event columns (ctypes face of instrain_b200/csrc/isb_host.cpp).
+"""Host packer: BAM -> read-major aligned segments or position-major event columns (ctypes face of csrc/isb_host.cpp).
 
 Replaces the reference's pysam.AlignmentFile + samfile.pileup(...) (inStrain/profile/profile_utilities.py:56,150-153)
 for the hot path: decodes the BAM once, applies htslib's mate-overlap quality tweak, expands CIGARs and emits the
@@ -35,6 +35,16 @@ def _lib():
             getattr(L, f).argtypes = [vp]
         L.isb_events_copy.argtypes = [vp] * 6
         L.isb_events_free.argtypes = [vp]
+        L.isb_pack_scaffold_reads.restype = vp
+        L.isb_pack_scaffold_reads.argtypes = [vp, C.c_int, i64, C.c_char_p, vp, vp, i32, i32, C.c_int]
+        for f in ("isb_reads_segs", "isb_reads_stream_words", "isb_reads_pairs", "isb_reads_n_events", "isb_reads_nev",
+                  "isb_reads_reads_seen", "isb_reads_reads_packed"):
+            getattr(L, f).restype = i64
+            getattr(L, f).argtypes = [vp]
+        L.isb_reads_max_len.restype = C.c_int
+        L.isb_reads_max_len.argtypes = [vp]
+        L.isb_reads_copy.argtypes = [vp] * 9 + [i64]
+        L.isb_reads_free.argtypes = [vp]
         L._packer_ready = True
     return L
 
@@ -65,6 +75,46 @@ class BamPacker:
     def peek_tid(self):
         """tid of the next record: >= 0; -1 unmapped tail; -2 end of file."""
         return int(self.lib.isb_bam_peek_tid(self.h))
+
+    @staticmethod
+    def _names(r2m):
+        names = list(r2m.keys()) if isinstance(r2m, dict) else list(r2m)
+        enc = [s.encode() for s in names]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        if enc:
+            off[1:] = np.cumsum([len(b) for b in enc])
+        if isinstance(r2m, dict):
+            mm = np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names))
+            if len(mm) and (mm.min() < 0 or mm.max() >= _cabi.ISB_MAX_MM):
+                raise ValueError("R2M mismatch count outside [0, %d)" % _cabi.ISB_MAX_MM)
+            mm = mm.astype(np.uint8)
+        else:
+            mm = np.zeros(len(names), dtype=np.uint8)
+        return len(names), b"".join(enc), off, mm
+
+    def pack_scaffold_reads(self, tid, r2m, pos_offset=0, pair_id_offset=0, min_qual=30):
+        """Consume the records of scaffold `tid` as READ-MAJOR aligned segments (instrain_b200/reads.py layout, the
+        scaffold's own word stream: `stream` = [data words + one zero word] per segment, seg_word relative to it)."""
+        n_names, blob, off, mm = self._names(r2m)
+        r = self.lib.isb_pack_scaffold_reads(self.h, tid, n_names, blob, off.ctypes.data, mm.ctypes.data, pos_offset,
+                                             pair_id_offset, min_qual)
+        if not r:
+            raise IOError("isb_pack_scaffold_reads failed: " + self.lib.isb_bam_error(self.h).decode())
+        try:
+            n, nw = int(self.lib.isb_reads_segs(r)), int(self.lib.isb_reads_stream_words(r))
+            npairs, nev = int(self.lib.isb_reads_pairs(r)), int(self.lib.isb_reads_nev(r))
+            out = dict(seg_start=np.empty(n, np.int32), seg_len=np.empty(n, np.uint16), seg_pair=np.empty(n, np.int32),
+                       seg_word=np.empty(n, np.int64), stream=np.empty(nw, np.uint32), nev_pos=np.empty(nev, np.int32),
+                       nev_pair=np.empty(nev, np.int32), pair_mm=np.empty(npairs, np.uint8))
+            self.lib.isb_reads_copy(r, *[out[k].ctypes.data for k in ("seg_start", "seg_len", "seg_pair", "seg_word", "stream",
+                                                                      "nev_pos", "nev_pair", "pair_mm")], 0)
+            out["max_seg_len"] = int(self.lib.isb_reads_max_len(r))
+            out["n_events"] = int(self.lib.isb_reads_n_events(r))
+            out["reads_seen"] = int(self.lib.isb_reads_reads_seen(r))
+            out["reads_packed"] = int(self.lib.isb_reads_reads_packed(r))
+        finally:
+            self.lib.isb_reads_free(r)
+        return out
 
     def pack_scaffold(self, tid, r2m, pos_offset=0, pair_id_offset=0):
         """Consume the records of scaffold `tid`; r2m is the reference's sR2M[scaffold]: dict name -> mm, or a set."""

@@ -6,9 +6,9 @@ Same arguments and keyword names as the reference (`kwargs` = vars(args) + s2s +
 Where the reference farms (scaffold, split) commands to worker processes (profile_controller.py:243-271) and each worker
 runs profile_split's per-column Python loop (profile_utilities.py:115-266), this shim
   1. streams the BAM once through the C++ host packer (instrain_b200/packer.py),
-  2. concatenates scaffolds into batches (one int32 coordinate space per batch) and encodes each batch in the packed
-     host->device transfer format (instrain_b200/packed.py),
-  3. runs K0 (expand) -> K1 -> K2 -> K3 for the whole batch through the C-ABI (isb_profile_batch_packed),
+  2. concatenates scaffolds into batches (one int32 coordinate space per batch) of READ-MAJOR aligned segments
+     (4-bit code per aligned base; instrain_b200/reads.py),
+  3. runs K1r -> K2 -> K3 for the whole batch through the C-ABI (isb_profile_reads),
   4. turns the row arrays into the reference's per-scaffold tables (instrain_b200/tables.py).
 There is no CPU fallback: without the CUDA library / a GPU this raises.
 """
@@ -20,7 +20,7 @@ import pandas as pd
 
 from . import summary, tables
 from .engine import Engine
-from .packed import encode_packed
+from . import reads as reads_mod
 from .packer import BamPacker
 from .synth import iterate_splits
 
@@ -101,14 +101,13 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
     def _flush(batch):
         cat = np.concatenate
-        ev = dict(ref_pos=cat(batch["ref_pos"]), base=cat(batch["base"]), qual=cat(batch["qual"]),
-                  read_id=cat(batch["read_id"]), pair_mm=cat(batch["pair_mm"]))
         ref_codes = cat(batch["ref"])
         offs = np.array(batch["off"], dtype=np.int64)
-        # host -> device in the packed transfer format (~1 B/event); kernel K0 expands it to the event columns in HBM
-        pk = encode_packed(ev, 0, len(ref_codes), 30)
-        out = engine.profile_batch(ev, ref_codes, np.array(batch["splits"], np.int32), min_cov=min_cov, min_freq=min_freq,
-                                   min_snp=min_snp, want=("covT", "clonT", "nmask", "snv", "ld"), packed=pk)
+        # host -> device as read-major aligned segments (4 bits per aligned base); K1r transposes on the device
+        rd = reads_mod.concat_streams(batch["parts"])
+        out = engine.profile_batch(dict(pair_mm=cat(batch["pair_mm"])), ref_codes, np.array(batch["splits"], np.int32),
+                                   min_cov=min_cov, min_freq=min_freq, min_snp=min_snp,
+                                   want=("covT", "clonT", "nmask", "snv", "ld"), reads=rd)
         # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
         bounds = np.append(offs, len(ref_codes)).astype(np.int32)
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
@@ -124,8 +123,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             res.scaffolds[name] = sp
             res.scaffold_list.append(name)
 
-    new_batch = lambda: dict(names=[], off=[], ref=[], splits=[], ref_pos=[], base=[], qual=[], read_id=[], pair_mm=[],
-                             n_events=0, L=0, n_pairs=0)
+    new_batch = lambda: dict(names=[], off=[], ref=[], splits=[], parts=[], pair_mm=[], n_events=0, L=0, n_pairs=0)
     batch = new_batch()
     with BamPacker(bam) as bp:
         while True:
@@ -134,12 +132,12 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
                 break
             name = bp.ref_names[tid]
             if name not in sR2M or name not in s2s:
-                bp.pack_scaffold(tid, {})                                  # consume and drop
+                bp.pack_scaffold_reads(tid, {})                            # consume and drop
                 continue
             if name == "FailureScaffoldHeaderTesting" and kwargs.get("debug", False):
                 # the reference's fault-injection hook (profile_utilities.py:137-139, test_profile_17): the scaffold fails,
                 # the failure is logged, the run survives
-                bp.pack_scaffold(tid, {})
+                bp.pack_scaffold_reads(tid, {})
                 logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(name, time.strftime("%m-%d %H:%M"), 1))
                 res.failures.append(name)
                 continue
@@ -147,14 +145,14 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
                 flush(batch)
                 batch = new_batch()
-            ev = bp.pack_scaffold(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
+            ev = bp.pack_scaffold_reads(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
             batch["names"].append(name)
             batch["off"].append(batch["L"])
             batch["ref"].append(encode_reference(s2s[name]))
             batch["splits"].extend((s + batch["L"], e + batch["L"]) for s, e in _fdb_splits(Fdb, name, L, window_length))
-            for k in ("ref_pos", "base", "qual", "read_id", "pair_mm"):
-                batch[k].append(ev[k])
-            batch["n_events"] += len(ev["ref_pos"])
+            batch["parts"].append(ev)
+            batch["pair_mm"].append(ev["pair_mm"])
+            batch["n_events"] += ev["n_events"]
             batch["L"] += L
             batch["n_pairs"] += len(ev["pair_mm"])
     flush(batch)

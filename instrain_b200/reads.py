@@ -112,3 +112,22 @@ def reads_to_events(rd, min_qual=30):
     order = np.lexsort((rid, pos))
     return dict(ref_pos=pos[order].astype(np.int32), base=base[order], qual=np.full(len(order), 255, np.uint8),
                 read_id=rid[order].astype(np.int32))
+
+
+def concat_streams(parts):
+    """Scaffold-wise packer outputs (BamPacker.pack_scaffold_reads; coordinates / pair ids already offset) -> one batch:
+    one leading zero word + the scaffolds' streams + zero padding to a multiple of 4 words."""
+    n_words = 1 + sum(len(p["stream"]) for p in parts)
+    n_words = (n_words + 3) // 4 * 4
+    words = np.zeros(n_words, dtype=np.uint32)
+    seg_word, base = [], 1
+    for p in parts:
+        words[base:base + len(p["stream"])] = p["stream"]
+        seg_word.append(p["seg_word"] + base)
+        base += len(p["stream"])
+    cat = lambda k, dt: (np.concatenate([p[k] for p in parts]) if parts else np.zeros(0, dt)).astype(dt, copy=False)
+    return dict(n_segs=sum(len(p["seg_start"]) for p in parts), seg_start=cat("seg_start", np.int32),
+                seg_len=cat("seg_len", np.uint16), seg_pair=cat("seg_pair", np.int32),
+                seg_word=np.concatenate(seg_word) if seg_word else np.zeros(0, np.int64), n_words=n_words, words=words,
+                max_seg_len=max([p["max_seg_len"] for p in parts] + [1]), nev_pos=cat("nev_pos", np.int32),
+                nev_pair=cat("nev_pair", np.int32))

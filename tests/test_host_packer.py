@@ -129,3 +129,52 @@ def test_read_filter_reproduces_reference_rdic():
     for s in mi.index:
         if s in tal:
             assert all(int(mi.loc[s, c]) == tal[s][c] for c in tal[s]), s
+
+
+def _canon(ev, keep=None):
+    """(position, pair, base) triples of the events, sorted."""
+    sel = slice(None) if keep is None else keep
+    pos, rid, base = ev["ref_pos"][sel], ev["read_id"][sel], np.minimum(ev["base"][sel], 4)
+    o = np.lexsort((base, rid, pos))
+    return pos[o], rid[o], base[o]
+
+
+@pytest.mark.parametrize("bam,r2m_json", [("c1_G1_subset.bam", "c1_G1_subset_r2m.json"), ("small_scaffold.bam", None)])
+def test_read_major_packer_matches_event_packer(bam, r2m_json):
+    """isb_pack_scaffold_reads (aligned segments, one-hot codes) encodes exactly the events of isb_pack_scaffold that
+    pass min_qual -- same positions, pair ids (BAM order of first appearance), bases -- and obeys the layout rules."""
+    from instrain_b200 import build, reads
+    build.build()
+    from instrain_b200.packer import BamPacker
+    path = os.path.join(GOLDEN, bam)
+    if r2m_json:
+        rdic = json.load(open(os.path.join(GOLDEN, r2m_json)))
+    else:
+        meta = json.load(open(os.path.join(GOLDEN, "small_scaffold.json")))
+        rdic = {meta["scaffold"]: meta["r2m"]}
+    n_tot = 0
+    with BamPacker(path) as pa, BamPacker(path) as pb:
+        while True:
+            tid = pa.peek_tid()
+            if tid < 0:
+                break
+            name = pa.ref_names[tid]
+            r2m = rdic.get(name, {})
+            ev = pa.pack_scaffold(tid, r2m, pos_offset=700, pair_id_offset=11)
+            pb.peek_tid()
+            part = pb.pack_scaffold_reads(tid, r2m, pos_offset=700, pair_id_offset=11, min_qual=30)
+            rd = reads.concat_streams([part])
+            assert np.array_equal(part["pair_mm"], ev["pair_mm"])
+            assert part["reads_seen"] == ev["reads_seen"] and part["reads_packed"] == ev["reads_packed"]
+            ok = ev["qual"] >= 30
+            assert part["n_events"] == int(ok.sum())
+            back = reads.reads_to_events(rd)
+            for x, y in zip(_canon(back), _canon(ev, ok)):
+                assert np.array_equal(x, y), name
+            if rd["n_segs"]:
+                nw = (rd["seg_len"].astype(np.int64) + 7) // 8
+                assert rd["seg_word"][0] == 1 and np.all(np.diff(rd["seg_word"]) == nw[:-1] + 1)
+                assert np.all(np.diff(rd["seg_start"]) >= 0) and rd["seg_len"].min() >= 1 and rd["max_seg_len"] <= 256
+                assert rd["n_words"] % 4 == 0 and rd["seg_word"][-1] + nw[-1] < rd["n_words"]
+            n_tot += part["n_events"]
+    assert n_tot > 1000
