@@ -281,6 +281,18 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
         };
         if (kM1) {
             int i = cl;
+            for (; i + 16 <= ch; i += 16) {                        // two Harley-Seal blocks per trip: 16 fetches in flight
+                uint32_t x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { x[u] = fetch(i + u); y[u] = fetch(i + 8 + u); }
+                k1r_add8(pl, x);
+                k1r_add8(pl, y);
+                n8 += 16;
+                if (n8 > 239) {                                    // the next trip could overflow 255
+                    k1r_planes_to_counts(c, pl);
+                    n8 = 0;
+                }
+            }
             for (; i + 8 <= ch; i += 8) {
                 uint32_t x[8];
 #pragma unroll
