@@ -115,6 +115,7 @@ def test_argument_errors(eng):
     (12000, 100, 0.05, 1, False, 0.002, 20260105),  # LD-stress shaped + non-ACGT read bases (nmask)
     (700, 30, 0.02, 3, False, 0.0, 7),              # tiny scaffolds (test_profile_18), one split each
     (25000, 8, 0.01, 1, False, 0.0, 11),            # low coverage around min_cov
+    (12000, 500, 0.05, 1, True, 0.0, 20260105),     # BASELINE configs[4] shaped (LD stress): 500x, 5 % SNVs, wide bit rows
 ])
 def test_synthetic_parity(eng, null_lut, L, cov, dens, nsc, skip_mm, n_frac, seed):
     batch = synth.make_batch(L, cov, dens, seed, n_scaffolds=nsc, skip_mm=skip_mm, n_frac=n_frac)

@@ -58,6 +58,7 @@ def test_golden_tables_read_major(eng, which, null_lut):
     (25000, 8, 0.01, 1, False, 0.0, 11),
     (9000, 400, 0.01, 1, True, 0.0, 3),              # > 255 candidates per position: 8 -> 32 bit widening, several chunks
     (9000, 400, 0.01, 1, False, 0.0, 3),             # same through the shared-memory counters (mid-run flush)
+    (12000, 500, 0.05, 1, True, 0.0, 20260105),      # BASELINE configs[4] shaped (LD stress): 500x, 5 % SNVs, wide bit rows
 ])
 def test_synthetic_parity_read_major(eng, null_lut, L, cov, dens, nsc, skip_mm, n_frac, seed):
     batch = synth.make_batch(L, cov, dens, seed, n_scaffolds=nsc, skip_mm=skip_mm, n_frac=n_frac)
