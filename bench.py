@@ -396,6 +396,13 @@ def main():
         hrp.update(n_segs=hr["n_segs"], n_words=hr["n_words"], max_seg_len=hr["max_seg_len"], nev_pos=hr["nev_pos"],
                    nev_pair=hr["nev_pair"])
         rbatch = reads_struct(hrp, len(hb["pair_mm"]), h["pair_mm"], Ls, h["ref_codes"], h["splits"], Ms)
+        from instrain_b200.reads import compact_reads
+        hc = compact_reads(hr)                          # compact transfer format: 3 bits per aligned base, no word offsets
+        hcp = {"base2": pin(hc["base2"].view(np.int16)), "pass": pin(hc["pass"])}
+        cbatch = _cabi.IsbReadsCompact(int(hr["n_segs"]), p(hrp["seg_start"]), p(hrp["seg_len"]), p(hrp["seg_pair"]),
+                                       int(hc["n_units"]), p(hcp["base2"]), p(hcp["pass"]), int(hr["max_seg_len"]), 0,
+                                       len(hr["nev_pos"]), p(hr["nev_pos"]), p(hr["nev_pair"]), len(hb["pair_mm"]),
+                                       p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]), p(h["splits"]), Ms, 0)
 
         def time_call(fn, b):
             ts = []
@@ -413,7 +420,8 @@ def main():
         dt_col = time_call(lib.isb_profile_batch, hbatch)
         dt_pk = time_call(lib.isb_profile_batch_packed, pbatch)
         dt_rd = time_call(lib.isb_profile_reads, rbatch)
-        main_fn, main_b, dt = (lib.isb_profile_reads, rbatch, dt_rd) if use_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
+        dt_rc = time_call(lib.isb_profile_reads_compact, cbatch)
+        main_fn, main_b, dt = (lib.isb_profile_reads_compact, cbatch, dt_rc) if use_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
 
         # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
         # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
@@ -448,16 +456,19 @@ def main():
         common = len(hb["pair_mm"]) + Ls + hb["splits"].nbytes
         h2d_pk = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
         h2d_rd = hr["n_words"] * 4 + hr["n_segs"] * (4 + 2 + 4 + 8) + common
+        h2d_rc = hc["n_units"] * 3 + hr["n_segs"] * (4 + 2 + 4) + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
         best = min(dt, dt_pipe) if dt_pipe else dt
-        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rd if use_reads else h2d_pk),
+        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rc if use_reads else h2d_pk),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": best * 1e3,
-               "api": ("isb_profile_reads (read-major aligned segments, 4 bits per aligned base)" if use_reads else
+               "api": ("isb_profile_reads_compact (read-major aligned segments in the compact transfer format: 3 bits per "
+                       "aligned base, K0r expands on the device)" if use_reads else
                        "isb_profile_batch_packed (packed transfer format, K0 expands on the device)"),
                "single_context": {"value": Ls / dt, "ms_per_step": dt * 1e3},
                "two_contexts_pipelined": ({"value": Ls / dt_pipe, "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),
                "slice": "%d of the %d scaffolds per step, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, args.scaffolds),
                "other_host_formats": {
+                   "read_major_compact": {"value": Ls / dt_rc, "ms_per_step": dt_rc * 1e3, "h2d_bytes_per_step": int(h2d_rc)},
                    "read_major_segments": {"value": Ls / dt_rd, "ms_per_step": dt_rd * 1e3, "h2d_bytes_per_step": int(h2d_rd)},
                    "packed_events": {"value": Ls / dt_pk, "ms_per_step": dt_pk * 1e3, "h2d_bytes_per_step": int(h2d_pk)},
                    "columnar_events": {"value": Ls / dt_col, "ms_per_step": dt_col * 1e3,

@@ -250,6 +250,41 @@ int isb_pileup_reads(isb_ctx *ctx, const isb_reads_batch *in, int32_t *counts, u
  * isb_profile_batch on the event columns of the same reads.  isb_params.min_qual is not used (the codes carry it). */
 int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params *prm, isb_result *out);
 
+/* ---- READ-MAJOR input, compact TRANSFER format ------------------------------------------------------------------------ */
+/* The same aligned segments in 3 bits per aligned base and without word offsets, for batches that cross PCIe (host
+ * buffers): ~32 % fewer bytes than isb_reads_batch.  Segments are cut into units of 8 bases (the last unit of a segment
+ * zero-padded); unit k of segment i is element unit_off[i] + k of both unit arrays, unit_off = exclusive prefix sum of
+ * ceil(seg_len / 8) in table order (implicit: not transferred).  Base j of a unit: 2-bit code (A,C,T,G = 0..3; inStrain's
+ * order, profile_utilities.py:34-35) in bits 2j..2j+1 of base2, event bit j of pass (1 = the base survives htslib's
+ * base-quality filter after the mate-overlap tweak and is A/C/T/G).  Passing non-ACGT bases go to nev_pos / nev_pair as
+ * in isb_reads_batch.  K0r (isb_k0r_expand.cu) rebuilds seg_word and the canonical nibble stream in device memory, then
+ * K1r -> K2 -> K3 run as in isb_profile_reads: results are identical.  Same ordering / range rules for the segments. */
+typedef struct {
+    int64_t n_segs;
+    const int32_t *seg_start;   /* [n_segs] ascending */
+    const uint16_t *seg_len;    /* [n_segs] 1 .. max_seg_len */
+    const int32_t *seg_pair;    /* [n_segs] */
+    int64_t n_units;            /* sum of ceil(seg_len / 8) */
+    const uint16_t *base2;      /* [n_units] */
+    const uint8_t *pass;        /* [n_units] */
+    int32_t max_seg_len;
+    int32_t pad;
+    int64_t n_nev;
+    const int32_t *nev_pos;
+    const int32_t *nev_pair;
+    int64_t n_pairs;
+    const uint8_t *pair_mm;     /* [n_pairs]; may be NULL when M == 1 */
+    int32_t start;
+    int32_t L;
+    const uint8_t *ref;         /* [L] */
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+    int32_t pad2;
+} isb_reads_compact;
+
+int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const isb_params *prm, isb_result *out);
+
 /* ---- stage K4: merge-stage summary reductions (the row after the hot path) ----------------------------- */
 /* Numeric core of make_coverage_table (profile_utilities.py:425-506) with mm_counts_to_counts_shrunk (:508-532) and
  * get_basewise_clons (:534-546): per scaffold s (positions [scaffold_off[s], scaffold_off[s+1]) of covT / clonT) and mm

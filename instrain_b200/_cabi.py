@@ -36,7 +36,7 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
-           "isb_pileup_reads", "isb_profile_reads",
+           "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact",
            "isb_scaffold_summary", "isb_launch_count",
            "isb_enable_timing", "isb_stage_times", "isb_selftest_division",
            "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
@@ -66,6 +66,15 @@ class IsbPackedBatch(C.Structure):
 class IsbReadsBatch(C.Structure):
     _fields_ = [("n_segs", C.c_int64), ("seg_start", C.c_void_p), ("seg_len", C.c_void_p), ("seg_pair", C.c_void_p),
                 ("seg_word", C.c_void_p), ("n_words", C.c_int64), ("words", C.c_void_p), ("max_seg_len", C.c_int32),
+                ("pad", C.c_int32), ("n_nev", C.c_int64), ("nev_pos", C.c_void_p), ("nev_pair", C.c_void_p),
+                ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
+                ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
+                ("M", C.c_int32), ("pad2", C.c_int32)]
+
+
+class IsbReadsCompact(C.Structure):
+    _fields_ = [("n_segs", C.c_int64), ("seg_start", C.c_void_p), ("seg_len", C.c_void_p), ("seg_pair", C.c_void_p),
+                ("n_units", C.c_int64), ("base2", C.c_void_p), ("pass_", C.c_void_p), ("max_seg_len", C.c_int32),
                 ("pad", C.c_int32), ("n_nev", C.c_int64), ("nev_pos", C.c_void_p), ("nev_pair", C.c_void_p),
                 ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
                 ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
@@ -139,6 +148,8 @@ def load():
     L.isb_pileup_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), vp, vp]
     L.isb_profile_reads.restype = C.c_int
     L.isb_profile_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    L.isb_profile_reads_compact.restype = C.c_int
+    L.isb_profile_reads_compact.argtypes = [vp, C.POINTER(IsbReadsCompact), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     _lib = L
     return L
 

@@ -636,4 +636,48 @@ int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params 
                           in->n_splits, d_splits, prm, out);
 }
 
+// Compact transfer format: copy the 3-bit columns, expand them on the device (K0r) into context-owned HBM, then the same
+// K1r -> K2 -> K3 as isb_profile_reads.
+int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!in->ref || (M > 1 && !in->pair_mm) || (in->n_splits > 0 && !in->splits))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_compact: null input pointer");
+    if (in->n_segs < 0 || in->n_units < 0 || (in->n_segs > 0 && (!in->seg_start || !in->seg_len || !in->seg_pair)) ||
+        (in->n_units > 0 && (!in->base2 || !in->pass)) || in->n_nev < 0 || (in->n_nev > 0 && (!in->nev_pos || !in->nev_pair)))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_compact: null or negative-sized segment column");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_reads_dev rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.n_segs = in->n_segs;
+    rd.max_seg_len = in->max_seg_len;
+    rd.n_nev = in->n_nev;
+    rd.n_words = (1 + in->n_units + in->n_segs + 3) & ~(int64_t)3;
+    const uint16_t *d_b2; const uint8_t *d_ps, *d_mm, *d_ref; const int32_t *d_splits;
+    if ((rc = stage_in(ctx, SL_RD_START, in->seg_start, (size_t)in->n_segs, &rd.seg_start))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_LEN, in->seg_len, (size_t)in->n_segs, &rd.seg_len))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_PAIR, in->seg_pair, (size_t)in->n_segs, &rd.seg_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_RC_BASE2, in->base2, (size_t)in->n_units, &d_b2))) return rc;
+    if ((rc = stage_in(ctx, SL_RC_PASS, in->pass, (size_t)in->n_units, &d_ps))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPOS, in->nev_pos, (size_t)in->n_nev, &rd.nev_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPAIR, in->nev_pair, (size_t)in->n_nev, &rd.nev_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    if ((rc = isb_ensure(ctx, SL_RD_WORD, sizeof(int64_t) * ((size_t)in->n_segs + 2)))) return rc;
+    if ((rc = isb_ensure(ctx, SL_RD_WORDS, sizeof(uint32_t) * ((size_t)rd.n_words + 4)))) return rc;
+    int64_t *d_seg_word = (int64_t *)ctx->buf[SL_RD_WORD].p;
+    uint32_t *d_words = (uint32_t *)ctx->buf[SL_RD_WORDS].p;
+    if ((rc = isb_k0r_launch(ctx, in->n_segs, rd.seg_len, in->n_units, d_b2, d_ps, d_seg_word, rd.n_words, d_words))) return rc;
+    rd.seg_word = d_seg_word;
+    rd.words = d_words;
+    return profile_device(ctx, &rd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+                          in->n_splits, d_splits, prm, out);
+}
+
 }  // extern "C"

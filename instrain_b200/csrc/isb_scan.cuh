@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce(F f, int64_t n, int6
 }
 
 // single CTA: in-place exclusive scan of block_sums[0..nb), grand total -> *total
-__global__ void __launch_bounds__(1024) scan_blocksums(int64_t *__restrict__ block_sums, int nb,
+static __global__ void __launch_bounds__(1024) scan_blocksums(int64_t *__restrict__ block_sums, int nb,
                                                        unsigned long long *__restrict__ total)
 {
     __shared__ int64_t s_warp[32];

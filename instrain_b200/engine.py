@@ -175,7 +175,14 @@ class Engine:
             raise ValueError("mm levels M=%d exceeds ISB_MAX_MM=%d" % (M, _cabi.ISB_MAX_MM))
         splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
         p = _cabi.ptr
-        if reads is not None:                      # read-major aligned segments (instrain_b200.reads)
+        if reads is not None and "base2" in reads:  # compact transfer format (instrain_b200.reads.compact_reads)
+            batch = _cabi.IsbReadsCompact(int(reads["n_segs"]), p(reads["seg_start"]), p(reads["seg_len"]),
+                                          p(reads["seg_pair"]), int(reads["n_units"]), p(reads["base2"]), p(reads["pass"]),
+                                          int(reads["max_seg_len"]), 0, len(reads["nev_pos"]), p(reads["nev_pos"]),
+                                          p(reads["nev_pair"]), len(pair_mm), p(pair_mm), start, L, p(ref_codes),
+                                          len(splits), p(splits), M, 0)
+            entry = self.lib.isb_profile_reads_compact
+        elif reads is not None:                    # read-major aligned segments (instrain_b200.reads)
             batch = self._reads_batch(reads, pair_mm, start, L, ref_codes, splits, M)
             entry = self.lib.isb_profile_reads
         elif packed is not None:                   # packed transfer format (instrain_b200.packed.encode_packed)

@@ -114,6 +114,26 @@ def reads_to_events(rd, min_qual=30):
                 read_id=rid[order].astype(np.int32))
 
 
+def compact_reads(rd):
+    """Read-major batch -> compact TRANSFER format (include/instrain_b200.h, isb_reads_compact): per unit of 8 bases one
+    uint16 of 2-bit base codes and one uint8 of event bits; no word offsets (the device rebuilds the canonical stream)."""
+    seg_len = rd["seg_len"].astype(np.int64)
+    nw = (seg_len + 7) // 8
+    n_units = int(nw.sum())
+    k = np.arange(n_units, dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
+    w = rd["words"][np.repeat(np.asarray(rd["seg_word"], dtype=np.int64), nw) + k].astype(np.uint32)
+    base2 = np.zeros(n_units, dtype=np.uint16)
+    ps = np.zeros(n_units, dtype=np.uint8)
+    for t in range(8):
+        nib = (w >> np.uint32(4 * t)) & np.uint32(15)
+        code = np.select([nib == 2, nib == 4, nib == 8], [1, 2, 3], 0).astype(np.uint16)
+        base2 |= code << np.uint16(2 * t)
+        ps |= (nib != 0).astype(np.uint8) << np.uint8(t)
+    out = {k_: rd[k_] for k_ in ("n_segs", "seg_start", "seg_len", "seg_pair", "max_seg_len", "nev_pos", "nev_pair")}
+    out.update(n_units=n_units, base2=base2, **{"pass": ps})
+    return out
+
+
 def concat_streams(parts):
     """Scaffold-wise packer outputs (BamPacker.pack_scaffold_reads; coordinates / pair ids already offset) -> one batch:
     one leading zero word + the scaffolds' streams + zero padding to a multiple of 4 words."""

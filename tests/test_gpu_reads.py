@@ -181,6 +181,35 @@ def test_device_generator_reads_equal_events(eng, null_lut):
         check_reads(eng, hb, null_lut, rd=hr["reads"])
 
 
+@pytest.mark.parametrize("which", ["G1", "synth_mm", "synth_m1", "synth_n"])
+def test_compact_transfer_format(eng, which, null_lut):
+    """isb_profile_reads_compact (3 bits per aligned base, no word offsets; K0r rebuilds the stream on the device) gives
+    the oracle's tables, from segments with odd block sizes, short pieces and non-ACGT bases alike."""
+    if which == "G1":
+        batch, _ = load_batch("G1")
+        rd = reads.events_to_reads(batch)
+    elif which == "synth_mm":
+        batch = synth.make_batch(30000, 50, 0.01, 20260102, n_scaffolds=2, skip_mm=False)
+        rd = reads.events_to_reads(batch, max_len=37, odd_blocks=True)          # many short pieces, two separators
+    elif which == "synth_m1":
+        batch = synth.make_batch(20000, 300, 0.02, 5, skip_mm=True)
+        rd = reads.events_to_reads(batch, max_len=150)
+    else:
+        batch = synth.make_batch(12000, 100, 0.05, 20260105, skip_mm=False, n_frac=0.002)
+        rd = reads.events_to_reads(batch)
+    check_reads(eng, batch, null_lut, rd=reads.compact_reads(rd))
+
+
+def test_compact_format_rejects_inconsistent_units(eng, null_lut):
+    from instrain_b200 import _cabi
+    batch = synth.make_batch(5000, 30, 0.01, 1, skip_mm=True)
+    rd = reads.compact_reads(reads.events_to_reads(batch))
+    rd["n_units"] -= 3                                                            # table needs more units than given
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=rd)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+
+
 def test_row_storage_regrow(null_lut):
     """The fused K3 front end sizes its bit-row storage by a guess and regrows it from the counted need: force the
     smallest guess (separate process: the guess is read once per process)."""

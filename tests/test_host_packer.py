@@ -178,3 +178,25 @@ def test_read_major_packer_matches_event_packer(bam, r2m_json):
                 assert rd["n_words"] % 4 == 0 and rd["seg_word"][-1] + nw[-1] < rd["n_words"]
             n_tot += part["n_events"]
     assert n_tot > 1000
+
+
+def test_compact_reads_round_trip():
+    """reads.compact_reads: decoding the 3-bit units gives back exactly the nibbles of the read-major stream."""
+    from oracle import synth
+    from instrain_b200 import reads
+    batch = synth.make_batch(4000, 40, 0.02, 3, skip_mm=False, n_frac=0.003)
+    for kw in (dict(), dict(max_len=37, odd_blocks=True)):
+        rd = reads.events_to_reads(batch, **kw)
+        c = reads.compact_reads(rd)
+        nw = (rd["seg_len"].astype(np.int64) + 7) // 8
+        assert c["n_units"] == nw.sum() == len(c["base2"]) == len(c["pass"])
+        k = np.arange(c["n_units"]) - np.repeat(np.cumsum(nw) - nw, nw)
+        w = rd["words"][np.repeat(rd["seg_word"], nw) + k]
+        dec = np.zeros(c["n_units"], dtype=np.uint32)
+        for t in range(8):
+            code = (c["base2"].astype(np.uint32) >> (2 * t)) & 3
+            ok = (c["pass"].astype(np.uint32) >> t) & 1
+            dec |= (ok << code) << np.uint32(4 * t)
+        assert np.array_equal(dec, w)
+        # 3 bytes per 8 bases + 10 bytes per segment, against 4 bytes per 8 bases + separators + 18 bytes per segment
+        assert 3 * c["n_units"] + 10 * c["n_segs"] < 0.75 * (4 * rd["n_words"] + 18 * rd["n_segs"])
