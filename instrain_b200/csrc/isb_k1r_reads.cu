@@ -150,15 +150,18 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
 {
     extern __shared__ __align__(128) unsigned char k1r_smem_raw[];
     uint32_t *s_words = reinterpret_cast<uint32_t *>(k1r_smem_raw);
-    int2 *s_meta = reinterpret_cast<int2 *>(s_words + a.words_cap);     // x: nibble address of relative position 0, y: end
+    // one packed word per segment (a 32-bit load has half the bank conflicts of a 64-bit one when every lane follows its
+    // own segment): bits 11.. = nibble address of tile position 0 + 1024, bits 0..10 = tile-relative end + 256
+    uint32_t *s_meta = s_words + a.words_cap;
     int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);  // relative start (sorted): the candidate search key
     uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(k1r_smem_raw + (((size_t)a.words_cap * 4 + (size_t)a.seg_cap * 13 + 7) & ~(size_t)7));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k1r_smem_raw + (((size_t)a.words_cap * 4 + (size_t)a.seg_cap * 9 + 7) & ~(size_t)7));
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bar) + 16);
 
     const int t = threadIdx.x;
     const int tile = blockIdx.x;
-    const int32_t P = tile * K1R_TILE + t * 8;                  // first of the thread's 8 positions (relative)
+    const int32_t T0 = tile * K1R_TILE;
+    const int32_t P = T0 + t * 8;                               // first of the thread's 8 positions (relative)
     const bool active = P < a.L;
     const int maxlen = a.rd.max_seg_len;
     const int64_t lo = a.rd.tile_lo[tile], hi = a.rd.tile_hi[tile];
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
                     err |= ISB_DEV_ERR_SEG;
                 const int n_c = min(max(n, 0), maxlen);
                 const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
-                s_meta[i] = make_int2(wl_c * 8 - s, s + n_c);     // nibble address of position p = x + p; covered while p < y
+                const int s_rel = min(max(s - T0, -255), K1R_TILE - 1);   // candidates start in (T0 - 256, T0 + 1024)
+                s_meta[i] = ((uint32_t)(wl_c * 8 - s_rel + 1024) << 11) | (uint32_t)(s_rel + n_c + 256);
                 s_start[i] = s;
                 if (!kM1) {
                     if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
@@ -271,13 +275,14 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
             ch = l;
         }
         // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach)
+        const int P_na = t * 8 - 1024, P_end = t * 8 + 256;
         auto fetch = [&](int i) -> uint32_t {
-            const int2 md = s_meta[i];
-            const int na = md.x + P;                               // nibble address of position P in the staged words
+            const uint32_t md = s_meta[i];
+            const int na = (int)(md >> 11) + P_na;                 // nibble address of position P in the staged words
             const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(s_words) +
                                                                    ((na >> 1) & ~3));
             const uint32_t x = __funnelshift_r(w[0], w[1], na << 2);
-            return P < md.y ? x : 0u;                              // short segment: those words belong to a later one
+            return P_end < (int)(md & 0x7ffu) ? x : 0u;            // short segment: those words belong to a later one
         };
         if (kM1) {
             int i = cl;
@@ -358,274 +363,6 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// K1r v2 (M = 1): scatter to position-aligned rows, then count -- every shared-memory access conflict-free.
-//
-// v1 above gathers: every thread follows its own candidate segments, so the meta and word loads of a warp land on random
-// banks (ncu: 63.3 M shared wavefronts for 19.8 M ideal, the LSU data pipe at 80 % of its peak, issue slots 30 % used).
-// v2 turns the tile's part of the stream into a position-aligned matrix first:
-//
-//   col[row][c]   c = one of the tile's 128 columns (8 positions, one 32-bit word of nibbles), row = i mod K for the
-//                 i-th candidate segment of the tile
-//
-//   scatter   one THREAD per word of the stream (coalesced global loads straight from L2, which a bulk prefetch warmed):
-//             the thread at word q of segment i (found from a separator bit mask + a per-group prefix: one LDS.64, LOP,
-//             POPC, IADD) funnel-shifts (w[q], w[q+1]) by the segment's start mod 8 into the aligned word of column
-//             start/8 + j + 1 and stores it to col[i mod K][that column].  The lanes of a warp write consecutive columns
-//             of at most a few rows; zero words are not written (the matrix is cleared first), so separators, short
-//             segments and the zero padding cost nothing.
-//   count     thread c walks its candidate rows (cl_c .. ch_c, the segments that start in the 8 (D + 1) positions up to
-//             the column's end, D = ceil((max_seg_len - 1) / 8)) down column c: lane = bank, no conflicts, no meta, no
-//             shifts; the words go into the same vertical carry-save counters as in v1.  256 threads: two threads share
-//             a column (first / second half of its rows) and add their counts through shared memory at the end.
-//
-// Two segments never collide in a cell while every column has at most K candidates: both would be candidates of that
-// column, hence less than K apart.  K is sized from the batch density (1.25 x the mean + 24); a tile where some column
-// has more (checked with one __syncthreads_or) is processed in passes of K consecutive segments, which always fit.
-#define K1V_THREADS 256
-#define K1V_COLS (K1R_TILE / 8)
-#define K1V_STAGE_IT 6                 // segment-table elements per thread per chunk: seg_cap <= 6 * 256
-
-struct k1v_args {
-    isb_reads_dev rd;
-    int32_t start, L;
-    int K;                             // rows of the aligned matrix (multiple of 8)
-    int seg_cap;                       // segments staged per chunk
-    int grp_cap;                       // 32-word groups of the stream per chunk
-    int32_t *counts;
-    unsigned int *d_err;
-};
-
-__global__ void __launch_bounds__(K1V_THREADS, 2) k1r_pileup_v2(k1v_args a)
-{
-    extern __shared__ __align__(128) unsigned char k1v_smem_raw[];
-    uint32_t *col = reinterpret_cast<uint32_t *>(k1v_smem_raw);                       // [K][128]
-    int2 *s_meta = reinterpret_cast<int2 *>(col + (size_t)a.K * K1V_COLS);            // x: column - word index, y: row << 8 | shift
-    int2 *s_grp = s_meta + a.seg_cap;                                                 // x: separator bits, y: owner of lane 0 (- 1 if it is a separator)
-    int32_t *s_start = reinterpret_cast<int32_t *>(s_grp + a.grp_cap);                // tile-relative start (sorted): search key
-    int32_t *s_woff = s_start + a.seg_cap;                                            // first data word, relative to the chunk's word base
-    __shared__ int s_qend;                                                            // word after the chunk's last data word
-
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int tile = blockIdx.x;
-    const int c = t & (K1V_COLS - 1), half = t >> 7;
-    const int32_t T0 = tile * K1R_TILE;                                               // tile origin, relative to a.start
-    const int32_t P = T0 + c * 8;
-    const int maxlen = a.rd.max_seg_len;
-    const int D = (maxlen + 6) >> 3;
-    const int64_t lo = a.rd.tile_lo[tile], hi = a.rd.tile_hi[tile];
-    const int K = a.K;
-
-    int cnt[8][4];
-    uint32_t pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    int n8 = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) cnt[k][b] = 0;
-    unsigned err = 0;
-
-    if (t == 0 && hi > lo) {                                    // warm L2 with the tile's part of the stream
-        const int64_t w0 = a.rd.tile_wlo[tile] & ~(int64_t)3;
-        int64_t bytes = ((a.rd.tile_whi[tile] - w0 + 3) & ~(int64_t)3) * 4;
-        if (w0 >= 0 && w0 * 4 + bytes <= a.rd.n_words * 4) {
-            const char *src = reinterpret_cast<const char *>(a.rd.words + w0);
-            while (bytes > 0) {
-                const unsigned piece = (unsigned)(bytes < 32768 ? bytes : 32768);
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(piece) : "memory");
-                src += piece;
-                bytes -= piece;
-            }
-        }
-    }
-
-    for (int64_t c0 = lo; c0 < hi; c0 += a.seg_cap) {
-        const int nc = (int)min((int64_t)a.seg_cap, hi - c0);
-        const int64_t last = c0 + nc - 1;
-        int64_t w_first, w_end;
-        if (c0 == lo && last == hi - 1) {
-            w_first = a.rd.tile_wlo[tile];
-            w_end = a.rd.tile_whi[tile];
-        } else {
-            w_first = __ldg(a.rd.seg_word + c0) - 1;
-            w_end = __ldg(a.rd.seg_word + last) + ((__ldg(a.rd.seg_len + last) + 7) >> 3) + 1;
-        }
-        const int64_t wb = w_first & ~(int64_t)3;
-        const int64_t wn = w_end - wb;                          // words of the chunk incl. the separator after its last segment
-        __syncthreads();                                        // previous chunk consumed
-        if (w_first < 0 || wn <= 0 || wn > (int64_t)a.grp_cap * 32 || wb + wn > a.rd.n_words) {   // uniform
-            err |= ISB_DEV_ERR_SEG;
-            continue;
-        }
-        const int n_grp = (int)((wn + 31) >> 5);
-        for (int g = t; g < n_grp; g += K1V_THREADS) s_grp[g] = make_int2(0, 0);
-        __syncthreads();
-        // ---- segment table of the chunk (all global loads of a thread issued before the first use)
-        {
-            int32_t r_s[K1V_STAGE_IT], r_prev[K1V_STAGE_IT];
-            int r_n[K1V_STAGE_IT];
-            int64_t r_w[K1V_STAGE_IT];
-#pragma unroll
-            for (int k = 0; k < K1V_STAGE_IT; ++k) {
-                const int i = t + k * K1V_THREADS;
-                const int64_t g = c0 + i;
-                r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1;
-                if (i < nc) {
-                    r_s[k] = __ldg(a.rd.seg_start + g);
-                    r_n[k] = __ldg(a.rd.seg_len + g);
-                    r_w[k] = __ldg(a.rd.seg_word + g);
-                    if (g > 0) r_prev[k] = __ldg(a.rd.seg_start + g - 1);
-                }
-            }
-            int row = t % K;
-            const int row_step = K1V_THREADS % K;
-#pragma unroll
-            for (int k = 0; k < K1V_STAGE_IT; ++k) {
-                const int i = t + k * K1V_THREADS;
-                if (i >= nc) break;
-                const int32_t s = r_s[k] - a.start;
-                const int n = r_n[k];
-                const int64_t wl = r_w[k] - wb;
-                if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + ((n + 7) >> 3) + 1 > wn ||
-                    r_prev[k] > r_s[k])
-                    err |= ISB_DEV_ERR_SEG;
-                const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
-                const int32_t s_rel = s - T0;
-                s_start[i] = s_rel;
-                s_woff[i] = wl_c;
-                s_meta[i] = make_int2((s_rel >> 3) + 1 - wl_c, (row << 8) | (32 - 4 * (s_rel & 7)));
-                atomicOr(reinterpret_cast<unsigned int *>(&s_grp[(wl_c - 1) >> 5].x), 1u << ((wl_c - 1) & 31));
-                if (i == nc - 1) s_qend = (int)min((int64_t)wl_c + ((min(max(n, 1), maxlen) + 7) >> 3), wn - 1);
-                row += row_step;
-                if (row >= K) row -= K;
-            }
-        }
-        __syncthreads();
-        // ---- owner prefix of every 32-word group: y + popc(separator bits at or below the lane) = segment of the word
-        for (int i = t; i < nc; i += K1V_THREADS) {
-            const int g = (s_woff[i] - 1) >> 5;
-            const int gp = i ? (s_woff[i - 1] - 1) >> 5 : -1;
-            for (int gg = gp + 1; gg <= g; ++gg) s_grp[gg].y = i - 1;
-            if (i == nc - 1)
-                for (int gg = g + 1; gg < n_grp; ++gg) s_grp[gg].y = i;
-        }
-        // ---- candidate rows of the thread's column: segments starting in [8 (c - D), 8 c + 8) relative to the tile
-        int cl, ch;
-        {
-            int l = 0, h = nc;
-            const int key = (c - D) * 8;
-            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key) l = mid + 1; else h = mid; }
-            cl = l;
-            h = nc;
-            const int key2 = c * 8 + 8;
-            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key2) l = mid + 1; else h = mid; }
-            ch = l;
-        }
-        const int step = __syncthreads_or(ch - cl > K) ? K : nc;  // (barrier: the group prefixes are complete)
-
-        for (int sub = 0; sub < nc; sub += step) {
-            const int sub_end = min(nc, sub + step);
-            {                                                   // clear the matrix
-                uint4 *c4 = reinterpret_cast<uint4 *>(col);
-                const int n4 = K * (K1V_COLS / 4);
-                for (int e = t; e < n4; e += K1V_THREADS) c4[e] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            __syncthreads();
-            // ---- scatter: one thread per stream word
-            {
-                const int q_begin = s_woff[sub] - 1;
-                const int q_end = sub_end < nc ? s_woff[sub_end] - 1 : s_qend;
-                const uint32_t *wsrc = a.rd.words + wb;
-                const int q_max = (int)wn - 1;
-                const uint32_t le = (2u << lane) - 1u;
-                constexpr int U = 4;
-                for (int g0 = (q_begin >> 5) + warp; g0 * 32 < q_end; g0 += U * (K1V_THREADS / 32)) {
-                    uint32_t w[U], nx[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int q = (g0 + u * (K1V_THREADS / 32)) * 32 + lane;
-                        w[u] = __ldg(wsrc + min(q, q_max));
-                        nx[u] = 0u;
-                        if (lane == 31) nx[u] = __ldg(wsrc + min(q + 1, q_max));
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int g = g0 + u * (K1V_THREADS / 32);
-                        const int q = g * 32 + lane;
-                        const uint32_t up = __shfl_down_sync(ISB_FULL, w[u], 1);
-                        if (lane != 31) nx[u] = up;
-                        if (g * 32 >= q_end) continue;          // warp-uniform
-                        const int2 gr = s_grp[g];
-                        const int owner = gr.y + __popc((uint32_t)gr.x & le);
-                        const int2 m = s_meta[max(owner, 0)];
-                        const int cc = q + m.x;
-                        const uint32_t x = __funnelshift_rc(w[u], nx[u], (uint32_t)m.y & 63u);
-                        if (q >= q_begin && q < q_end && (unsigned)cc < (unsigned)K1V_COLS && x != 0u)
-                            col[((m.y >> 1) & ~(K1V_COLS - 1)) + cc] = x;
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- count: the thread's half of its column's candidate rows
-            {
-                const int ra = max(cl, sub), rb = min(ch, sub_end);
-                const int len = max(rb - ra, 0);
-                const int h0 = (len + 1) >> 1;
-                int first = half ? ra + h0 : ra;
-                int remaining = half ? len - h0 : h0;
-                int r = first % K;
-                while (remaining > 0) {
-                    const int span = min(remaining, K - r);
-                    const uint32_t *src = col + (size_t)r * K1V_COLS + c;
-                    int i = 0;
-                    for (; i + 16 <= span; i += 16) {
-                        uint32_t x[8], y[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { x[u] = src[(i + u) * K1V_COLS]; y[u] = src[(i + 8 + u) * K1V_COLS]; }
-                        k1r_add8(pl, x);
-                        k1r_add8(pl, y);
-                        n8 += 16;
-                        if (n8 > 239) { k1r_planes_to_counts(cnt, pl); n8 = 0; }
-                    }
-                    for (; i < span; i += 8) {
-                        uint32_t x[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) x[u] = (i + u < span) ? src[(i + u) * K1V_COLS] : 0u;
-                        k1r_add8(pl, x);
-                        n8 += 8;
-                        if (n8 > 247) { k1r_planes_to_counts(cnt, pl); n8 = 0; }
-                    }
-                    remaining -= span;
-                    r = 0;
-                }
-            }
-            if (sub + step < nc) __syncthreads();               // the matrix is cleared again
-        }
-    }
-    if (err) atomicOr(a.d_err, err);
-
-    // ---- the two halves of a column add up through shared memory; 128-bit stores of the thread's 8 positions
-    k1r_planes_to_counts(cnt, pl);
-    __syncthreads();
-    int32_t *s_red = reinterpret_cast<int32_t *>(col);          // [32][128]
-    if (half) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) s_red[(k * 4 + b) * K1V_COLS + c] = cnt[k][b];
-    }
-    __syncthreads();
-    if (!half && P < a.L) {
-        int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (P + k >= a.L) break;
-            c4[k] = make_int4(cnt[k][0] + s_red[(k * 4 + 0) * K1V_COLS + c], cnt[k][1] + s_red[(k * 4 + 1) * K1V_COLS + c],
-                              cnt[k][2] + s_red[(k * 4 + 2) * K1V_COLS + c], cnt[k][3] + s_red[(k * 4 + 3) * K1V_COLS + c]);
-        }
-    }
-}
-
 // passing non-ACGT read bases ("N events"): the level becomes a key of the position's MMcounts (nmask bit), nothing else
 __global__ void __launch_bounds__(256)
 k1r_n_events(int64_t n_nev, const int32_t *__restrict__ nev_pos, const int32_t *__restrict__ nev_pair,
@@ -669,9 +406,9 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     a.rd = *rd; a.pair_mm = pair_mm; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = M; a.counts = counts;
     a.nmask = nmask; a.d_err = ctx->d_err;
     // Shared-memory budget: the staging area should hold the whole candidate set of a tile (then every thread works in
-    // every chunk); two blocks per SM.  Bytes per staged segment: its words incl. separator + 8 (meta) + 1 (mm).
+    // every chunk); two blocks per SM.  Bytes per staged segment: its words incl. separator + 4 (meta) + 4 (start) + 1 (mm).
     const int wps = rd->max_seg_len / 8 + 3;                      // data words + up to two separator words
-    const size_t per_seg = (size_t)wps * 4 + 13;
+    const size_t per_seg = (size_t)wps * 4 + 9;
     const int groups = M == 1 ? 1 : (M + K1R_LEVELS - 1) / K1R_LEVELS;
     const int Mg = M == 1 ? 0 : (M < K1R_LEVELS ? M : K1R_LEVELS);
     const size_t acc_bytes = (size_t)Mg * 8 * K1R_THREADS * 4;
@@ -684,36 +421,10 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     if (seg_cap > K1R_STAGE_IT * K1R_THREADS) seg_cap = K1R_STAGE_IT * K1R_THREADS;
     a.seg_cap = seg_cap;
     a.words_cap = (seg_cap * wps + 8 + 3) & ~3;
-    const size_t smem = (((size_t)a.words_cap * 4 + (size_t)seg_cap * 13 + 7) & ~(size_t)7) + 16 + acc_bytes;
+    const size_t smem = (((size_t)a.words_cap * 4 + (size_t)seg_cap * 9 + 7) & ~(size_t)7) + 16 + acc_bytes;
     static bool attr_m1[64] = {false}, attr_mm[64] = {false};      // function attributes are per device
     if (nmask) ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
-    static const int variant = getenv("ISB_K1R_VARIANT") ? atoi(getenv("ISB_K1R_VARIANT")) : 2;   // 1 = gather (v1), 2 = scatter + count
-    if (M == 1 && variant != 1) {
-        k1v_args v;
-        v.rd = *rd; v.start = start; v.L = L; v.counts = counts; v.d_err = ctx->d_err;
-        const int Dc = (rd->max_seg_len + 6) >> 3;
-        const double dens = rd->n_segs > 0 ? (double)rd->n_segs / L : 0.0;
-        int K = ((int)(dens * 8 * (Dc + 1) * 1.25) + 24 + 7) & ~7;
-        int cap = (int)(dens * (K1R_TILE + 8 * (Dc + 1)) * 1.25) + 32;
-        if (cap < 64) cap = 64;
-        if (cap > K1V_STAGE_IT * K1V_THREADS) cap = K1V_STAGE_IT * K1V_THREADS;
-        static const int k_env = getenv("ISB_K1R_ROWS") ? atoi(getenv("ISB_K1R_ROWS")) : 0;      // tests: force the pass mode
-        if (k_env > 0) K = (k_env + 7) & ~7;
-        const int grp_cap = (cap * (rd->max_seg_len / 8 + 3) + 8 + 31) / 32 + 1;
-        const size_t fixed = (size_t)cap * 16 + (size_t)grp_cap * 8 + 64;
-        const size_t budget = (size_t)112 * 1024;                 // two blocks per SM
-        const int k_max = (int)(((budget > fixed + 32 * 512 ? budget - fixed : 32 * 512) / 512)) & ~7;
-        if (K > k_max) K = k_max;
-        if (K < 32) K = 32;                                       // the reduction at the end needs 32 rows
-        v.K = K; v.seg_cap = cap; v.grp_cap = grp_cap;
-        const size_t smem_v = (size_t)K * 512 + fixed;
-        static bool attr_v2[64] = {false};
-        if (!attr_v2[ctx->device & 63])
-            ISB_CUDA(cudaFuncSetAttribute(k1r_pileup_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_v2[ctx->device & 63] = true;
-        k1r_pileup_v2<<<n_tiles, K1V_THREADS, smem_v, st>>>(v);
-        ISB_LAUNCH_CHECK();
-    } else if (M == 1) {
+    if (M == 1) {
         if (!attr_m1[ctx->device & 63])
             ISB_CUDA(cudaFuncSetAttribute(k1r_pileup<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_m1[ctx->device & 63] = true;

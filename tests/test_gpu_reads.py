@@ -231,28 +231,3 @@ def test_row_storage_regrow(null_lut):
     env = dict(os.environ, ISB_K3_ROWS_INIT="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
-
-
-@pytest.mark.parametrize("env", [dict(ISB_K1R_ROWS="32"), dict(ISB_K1R_VARIANT="1")])
-def test_k1r_variants_and_pass_mode(env):
-    """K1r at M = 1: (a) the scatter + count kernel with a 32-row matrix, which forces its pass mode (K consecutive
-    segments per pass) on every tile; (b) the gather kernel (variant 1).  Both must give the oracle's counts.  Separate
-    process: the variant / row count are read once per process."""
-    import subprocess, sys, os
-    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-            "import numpy as np\n"
-            "from conftest import load_lut\n"
-            "from oracle import restate, synth\n"
-            "from instrain_b200 import reads\n"
-            "from instrain_b200.engine import Engine\n"
-            "lut = load_lut(); e = Engine(0, lut[0], lut[1])\n"
-            "for (L, cov, ml, nf) in ((30000, 50, 150, 0.0), (9000, 400, 256, 0.002), (3000, 20, 37, 0.0)):\n"
-            "    b = synth.make_batch(L, cov, 0.02, 11, skip_mm=True, n_frac=nf)\n"
-            "    exp = restate.profile_events(b, b['ref_codes'], lut[0], lut[1], b['splits'])\n"
-            "    rd = reads.events_to_reads(b, max_len=ml)\n"
-            "    counts, nmask = e.pileup_reads(rd, b['pair_mm'], 0, L, 1)\n"
-            "    assert np.array_equal(counts, exp['counts']) and np.array_equal(nmask, exp['nmask'])\n"
-            "print('k1r ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                    os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "k1r ok" in r.stdout, r.stdout + r.stderr
