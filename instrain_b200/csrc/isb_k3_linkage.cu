@@ -191,18 +191,43 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
         const int64_t clo = cand_lo[k];
         const int nc = n_cand[k];
         int cnt = 0, idmin = INT_MAX, idmax = -1;
-        for (int i0 = 0; i0 < nc; i0 += 32) {
-            int b = 0, id = 0;
-            bool ok = (i0 + lane < nc) && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id);
-            ok = ok && ((bases >> b) & 1u);
-            const unsigned mask = __ballot_sync(ISB_FULL, ok);
-            if (ok) {
-                const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-                if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
-                idmin = min(idmin, id);
-                idmax = max(idmax, id);
+        // Candidates in batches of 4 x 32.  Each batch costs TWO memory latencies: all table loads (start, length, word
+        // offset, pair id) of the lane's four candidates are issued together, then the four stream words.  (One
+        // candidate at a time, table entry -> word address -> word, was a chain of ~4 dependent loads per 32
+        // candidates: ncu showed the kernel waiting on exactly that, 1.5 of K3's 2.7 ms.)
+        for (int i0 = 0; i0 < nc; i0 += 128) {
+            int j4[4], id4[4];
+            int64_t wd4[4];
+            bool cov[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int idx = i0 + r * 32 + lane;
+                const int64_t g = clo + min(idx, nc - 1);
+                j4[r] = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
+                const int len = (int)__ldg(rd.seg_len + g);
+                wd4[r] = __ldg(rd.seg_word + g);
+                id4[r] = __ldg(rd.seg_pair + g);
+                cov[r] = idx < nc && j4[r] >= 0 && j4[r] < len;
             }
-            cnt += __popc(mask);
+            uint32_t w4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w4[r] = cov[r] ? __ldg(rd.words + wd4[r] + (j4[r] >> 3)) : 0u;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (i0 + r * 32 >= nc) break;                          // warp-uniform
+                const uint32_t code = (w4[r] >> ((j4[r] & 7) << 2)) & 15u;
+                const int b = __ffs((int)code) - 1;                    // one-hot A,C,T,G (-1: not an event)
+                const int id = id4[r];
+                const bool ok = code != 0u && ((bases >> (b & 3)) & 1u);
+                const unsigned mask = __ballot_sync(ISB_FULL, ok);
+                if (ok) {
+                    const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+                    if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
+                    idmin = min(idmin, id);
+                    idmax = max(idmax, id);
+                }
+                cnt += __popc(mask);
+            }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
