@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="reads", choices=["reads", "events"],
                     help="resident input layout: read-major aligned segments (default) or position-major event columns")
-    ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (20 or 21)")
+    ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (21 or 22)")
     ap.add_argument("--also-events", type=int, default=10,
                     help="with --layout reads: also time the position-major path on this many scaffolds (0 = skip)")
     return ap.parse_args()

@@ -215,11 +215,15 @@ int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb
  * Layout rules (validated on the device; violations -> ISB_ERR_ORDER):
  *   - segments sorted by seg_start (ascending, ties in any order), all inside [start, start + L), 1 <= seg_len <=
  *     max_seg_len <= 256 (longer blocks are split by the packer);
- *   - words: nibble j of a segment sits in bits 4*(j%8).. of word seg_word[i] + j/8; unused high nibbles of the last
- *     data word are 0; the data words of consecutive segments (in table order) are separated by one or two zero words,
- *     i.e. seg_word[0] >= 1, seg_word[i+1] = seg_word[i] + ceil(seg_len[i]/8) + 1 or + 2 (two when the packer wants an
- *     odd block size: it spreads K1r's shared-memory banks), the stream ends with a zero word and is padded with zero
- *     words to a multiple of 4 (n_words); `words` is 16-byte aligned. */
+ *   - words: the stream is POSITION-ALIGNED.  Word k of segment i covers the batch coordinates [8 * (seg_start[i] / 8
+ *     + k), + 8): the base at coordinate p sits in nibble (p - seg_start[i]) + seg_start[i] % 8 of the segment's words,
+ *     i.e. bits 4 * (n % 8).. of word seg_word[i] + n / 8; the nibbles before the first and after the last base are 0.  A
+ *     segment has ceil((seg_start % 8 + seg_len) / 8) data words.  (A pileup thread that owns 8 consecutive
+ *     coordinates therefore needs exactly one word of every read that covers them, unshifted.)  `start` must be a
+ *     multiple of 8;
+ *   - the data words of consecutive segments (in table order) are separated by one or two zero words, i.e.
+ *     seg_word[0] >= 1, seg_word[i+1] = seg_word[i] + (data words of i) + 1 or + 2, the stream ends with a zero word and
+ *     is padded with zero words to a multiple of 4 (n_words); `words` is 16-byte aligned. */
 typedef struct {
     int64_t n_segs;
     const int32_t *seg_start;   /* [n_segs] batch coordinate of the first base */
@@ -253,8 +257,9 @@ int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params 
 /* ---- READ-MAJOR input, compact TRANSFER format ------------------------------------------------------------------------ */
 /* The same aligned segments in 3 bits per aligned base and without word offsets, for batches that cross PCIe (host
  * buffers): ~32 % fewer bytes than isb_reads_batch.  Segments are cut into units of 8 bases (the last unit of a segment
- * zero-padded); unit k of segment i is element unit_off[i] + k of both unit arrays, unit_off = exclusive prefix sum of
- * ceil(seg_len / 8) in table order (implicit: not transferred).  Base j of a unit: 2-bit code (A,C,T,G = 0..3; inStrain's
+ * zero-padded); units are position-aligned like the words of isb_reads_batch (unit k of segment i covers the batch
+ * coordinates [8 * (seg_start[i] / 8 + k), + 8)); unit k of segment i is element unit_off[i] + k of both unit arrays,
+ * unit_off = exclusive prefix sum of ceil((seg_start % 8 + seg_len) / 8) in table order (implicit: not transferred).  Base j of a unit: 2-bit code (A,C,T,G = 0..3; inStrain's
  * order, profile_utilities.py:34-35) in bits 2j..2j+1 of base2, event bit j of pass (1 = the base survives htslib's
  * base-quality filter after the mate-overlap tweak and is A/C/T/G).  Passing non-ACGT bases go to nev_pos / nev_pair as
  * in isb_reads_batch.  K0r (isb_k0r_expand.cu) rebuilds seg_word and the canonical nibble stream in device memory, then
@@ -264,7 +269,7 @@ typedef struct {
     const int32_t *seg_start;   /* [n_segs] ascending */
     const uint16_t *seg_len;    /* [n_segs] 1 .. max_seg_len */
     const int32_t *seg_pair;    /* [n_segs] */
-    int64_t n_units;            /* sum of ceil(seg_len / 8) */
+    int64_t n_units;            /* sum of ceil((seg_start % 8 + seg_len) / 8) */
     const uint16_t *base2;      /* [n_units] */
     const uint8_t *pass;        /* [n_units] */
     int32_t max_seg_len;

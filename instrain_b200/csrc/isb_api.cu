@@ -673,7 +673,7 @@ int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const i
     if ((rc = isb_ensure(ctx, SL_RD_WORDS, sizeof(uint32_t) * ((size_t)rd.n_words + 4)))) return rc;
     int64_t *d_seg_word = (int64_t *)ctx->buf[SL_RD_WORD].p;
     uint32_t *d_words = (uint32_t *)ctx->buf[SL_RD_WORDS].p;
-    if ((rc = isb_k0r_launch(ctx, in->n_segs, rd.seg_len, in->n_units, d_b2, d_ps, d_seg_word, rd.n_words, d_words))) return rc;
+    if ((rc = isb_k0r_launch(ctx, in->n_segs, rd.seg_start, rd.seg_len, in->n_units, d_b2, d_ps, d_seg_word, rd.n_words, d_words))) return rc;
     rd.seg_word = d_seg_word;
     rd.words = d_words;
     return profile_device(ctx, &rd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,

@@ -141,7 +141,7 @@ int isb_k2_selftest_division(isb_ctx *ctx, int s_lo, int s_hi, unsigned long lon
 int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const unsigned long long *nmask,
                   int n_seg, const int32_t *seg_off, isb_summary_row *out);
 int isb_tile_offsets(isb_ctx *ctx, const int32_t *ref_pos, int64_t n, int32_t start, int32_t L, int tp, int n_tiles);
-int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const uint16_t *seg_len, int64_t n_units, const uint16_t *base2,
+int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, int64_t n_units, const uint16_t *base2,
                    const uint8_t *pass, int64_t *seg_word, int64_t n_words, uint32_t *words);
 int isb_k0_launch(isb_ctx *ctx, int64_t n, const int64_t *pos_off, const int32_t *id_base, const uint8_t *bqd,
                   int64_t n_esc, const int64_t *esc_evt, const int32_t *esc_id, int32_t start, int32_t L, int qpass,

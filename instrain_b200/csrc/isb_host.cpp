@@ -417,7 +417,8 @@ void isb_events_free(void *e) { delete (Events *)e; }
 // ---- read-major packer: the same reads as aligned segments (include/instrain_b200.h, isb_reads_batch) -------------------
 // One segment per CIGAR M/=/X block (clipped to the scaffold, split at 256 bases), sorted by start; one-hot 4-bit codes
 // (A=1,C=2,T=4,G=8) for the bases whose quality after the overlap tweak is >= min_qual, 0 otherwise; passing non-ACGT
-// bases go to the N-event list.  The word stream of the scaffold is [data words + one zero word] per segment; the caller
+// bases go to the N-event list.  The word stream of the scaffold is [data words + one zero word] per segment, the data
+// words position-aligned in batch coordinates (word 0 of a segment covers [start & ~7, (start & ~7) + 8)); the caller
 // concatenates scaffolds behind one leading zero word (isb_reads_copy's word_base).
 struct ReadsOut {
     std::vector<int32_t> seg_start, seg_pair, nev_pos, nev_pair;
@@ -476,18 +477,19 @@ void *isb_pack_scaffold_reads(void *h, int tid, int64_t n_names, const char *nam
         out->seg_len[i] = sg.len;
         out->seg_pair[i] = sg.pair;
         out->seg_word[i] = w;
-        w += ((int64_t)sg.len + 7) / 8 + 1;
+        w += ((int64_t)((sg.start + pos_offset) & 7) + sg.len + 7) / 8 + 1;      // position-aligned words + one zero word
         if (sg.len > out->max_len) out->max_len = sg.len;
     }
     out->words.assign((size_t)w, 0u);
     for (size_t i = 0; i < n; ++i) {
         const Seg &sg = segs[order[i]];
         uint32_t *dst = out->words.data() + out->seg_word[i];
+        const int sh = (sg.start + pos_offset) & 7;                     // nibble of the first base in word 0
         for (int j = 0; j < sg.len; ++j) {
             if ((int)ld.qual[sg.src + j] < min_qual) continue;
             const int code = NT16_TO_CODE[ld.seq[sg.src + j]];
             out->n_events++;
-            if (code < 4) dst[j >> 3] |= (1u << code) << ((j & 7) << 2);
+            if (code < 4) dst[(j + sh) >> 3] |= (1u << code) << (((j + sh) & 7) << 2);
             else { out->nev_pos.push_back(sg.start + j + pos_offset); out->nev_pair.push_back(sg.pair); }
         }
     }

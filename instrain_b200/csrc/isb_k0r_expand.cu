@@ -2,16 +2,17 @@
 //
 // Only on the host-buffer (end-to-end) path.  The nibble stream costs 4 bits per aligned base + 8 bytes of word offset
 // per segment over PCIe; the compact form carries the same information in 3 bits per aligned base (2-bit base code +
-// 1 event bit, in units of 8 bases: one uint16 + one uint8) and no word offsets: the stream layout is canonical (one
+// 1 event bit, in position-aligned units of 8 bases: one uint16 + one uint8) and no word offsets: the stream layout is canonical (one
 // leading zero word, [data words + one zero word] per segment in table order, zero padding to a multiple of 4 words),
-// so seg_word is an exclusive scan of ceil(seg_len / 8) done here.  The expanded stream is written to context-owned HBM
+// so seg_word is an exclusive scan of the segments' word counts ceil((start % 8 + seg_len) / 8) done here.  The expanded stream is written to context-owned HBM
 // (0.5 B per base at HBM speed, against 0.375 B per base saved on a link that is ~100x slower).
 #include "isb_common.cuh"
 #include "isb_scan.cuh"
 
-struct UnitsFn {   // data words (= 8-base units) of segment i
+struct UnitsFn {   // data words (= position-aligned 8-base units) of segment i
+    const int32_t *seg_start;
     const uint16_t *seg_len;
-    __device__ int operator()(int64_t i) const { return ((int)seg_len[i] + 7) >> 3; }
+    __device__ int operator()(int64_t i) const { return ((seg_start[i] & 7) + (int)seg_len[i] + 7) >> 3; }
 };
 struct SegWordSink {   // seg_word[i] = leading zero word + units before + one separator per earlier segment
     int64_t *seg_word;
@@ -20,7 +21,8 @@ struct SegWordSink {   // seg_word[i] = leading zero word + units before + one s
 
 // one warp per segment, lanes over its units: coalesced 2-byte / 1-byte loads, coalesced word stores
 __global__ void __launch_bounds__(256)
-k0r_expand_units(int64_t n_segs, const uint16_t *__restrict__ seg_len, const int64_t *__restrict__ seg_word,
+k0r_expand_units(int64_t n_segs, const int32_t *__restrict__ seg_start, const uint16_t *__restrict__ seg_len,
+                 const int64_t *__restrict__ seg_word,
                  int64_t n_units, const uint16_t *__restrict__ base2, const uint8_t *__restrict__ pass, int64_t n_words,
                  uint32_t *__restrict__ words, unsigned int *__restrict__ d_err)
 {
@@ -28,7 +30,7 @@ k0r_expand_units(int64_t n_segs, const uint16_t *__restrict__ seg_len, const int
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp0; i < n_segs; i += n_warps) {
-        const int nw = ((int)seg_len[i] + 7) >> 3;
+        const int nw = ((seg_start[i] & 7) + (int)seg_len[i] + 7) >> 3;
         const int64_t w0 = seg_word[i];
         const int64_t u0 = w0 - 1 - i;
         if (u0 < 0 || u0 + nw > n_units || w0 + nw + 1 > n_words) {       // table and unit arrays disagree (uniform)
@@ -46,7 +48,7 @@ k0r_expand_units(int64_t n_segs, const uint16_t *__restrict__ seg_len, const int
 }
 
 // seg_word[] and the nibble stream (n_words = round4(1 + n_units + n_segs)) from the compact columns; all on ctx->stream
-int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const uint16_t *seg_len, int64_t n_units, const uint16_t *base2,
+int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, int64_t n_units, const uint16_t *base2,
                    const uint8_t *pass, int64_t *seg_word, int64_t n_words, uint32_t *words)
 {
     cudaStream_t st = ctx->stream;
@@ -56,7 +58,7 @@ int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const uint16_t *seg_len, int64_
     const int nb = (int)((n_segs + SCAN_BLOCK - 1) / SCAN_BLOCK);
     if ((rc = isb_ensure(ctx, SL_SCAN_TMP, sizeof(int64_t) * (size_t)nb))) return rc;
     int64_t *block_sums = (int64_t *)ctx->buf[SL_SCAN_TMP].p;
-    UnitsFn uf{seg_len};
+    UnitsFn uf{seg_start, seg_len};
     scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(uf, n_segs, block_sums);
     ISB_LAUNCH_CHECK();
     scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nb, ctx->d_counters + 6);
@@ -66,7 +68,7 @@ int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const uint16_t *seg_len, int64_
     ISB_LAUNCH_CHECK();
     const int64_t blocks = (n_segs * 32 + 255) / 256;
     const int grid = (int)(blocks < (int64_t)ctx->sm_count * 16 ? blocks : (int64_t)ctx->sm_count * 16);
-    k0r_expand_units<<<grid, 256, 0, st>>>(n_segs, seg_len, seg_word, n_units, base2, pass, n_words, words, ctx->d_err);
+    k0r_expand_units<<<grid, 256, 0, st>>>(n_segs, seg_start, seg_len, seg_word, n_units, base2, pass, n_words, words, ctx->d_err);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }

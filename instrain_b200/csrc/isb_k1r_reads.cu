@@ -9,9 +9,10 @@
 //   * the segments that can touch the tile (seg_start in (tile_first - max_seg_len, tile_end), a contiguous range of the
 //     start-sorted segment table: k1r_tile_bounds) are staged chunk by chunk in shared memory -- start / length / word
 //     offset by the threads, the nibble words of the chunk (contiguous in the stream) by ONE TMA 1-D bulk copy;
-//   * each thread binary-searches its own candidate range in the chunk and, per candidate, funnel-shifts the two
-//     words that hold its 8 positions into one register.  Because consecutive segments are separated by a zero word
-//     and codes of non-events are 0, no per-nibble bounds checks are needed;
+//   * each thread binary-searches its own candidate range in the chunk and, per candidate, loads the ONE word of the
+//     segment that holds its 8 positions (the stream is position-aligned: word k of a segment covers the batch
+//     coordinates [8 (start / 8 + k), + 8)).  Codes of non-events and the nibbles outside the segment are 0, so no
+//     per-nibble bounds checks are needed;
 //   * counting is bit-sliced.  The codes are one-hot (A=1, C=2, T=4, G=8), so the 32 bits of that register are the 32
 //     (position, base) indicator bits of the candidate.  M = 1: they are added into eight VERTICAL counter planes
 //     (plane j = bit j of 32 independent counters) with a Harley-Seal carry-save tree, 8 candidates per block:
@@ -59,7 +60,7 @@ k1r_tile_bounds(const int32_t *__restrict__ seg_start, const uint16_t *__restric
     tile_lo[t] = lo;
     tile_hi[t] = hi;
     tile_wlo[t] = hi > lo ? seg_word[lo] - 1 : 0;
-    tile_whi[t] = hi > lo ? seg_word[hi - 1] + ((seg_len[hi - 1] + 7) >> 3) + 1 : 0;
+    tile_whi[t] = hi > lo ? seg_word[hi - 1] + (((seg_start[hi - 1] & 7) + seg_len[hi - 1] + 7) >> 3) + 1 : 0;
 }
 
 // carry-save adder on 32 independent bit lanes: h = majority(a, b, c), l = a ^ b ^ c (one LOP3 each)
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
     extern __shared__ __align__(128) unsigned char k1r_smem_raw[];
     uint32_t *s_words = reinterpret_cast<uint32_t *>(k1r_smem_raw);
     // one packed word per segment (a 32-bit load has half the bank conflicts of a 64-bit one when every lane follows its
-    // own segment): bits 11.. = nibble address of tile position 0 + 1024, bits 0..10 = tile-relative end + 256
+    // own segment): bits 11.. = staged index of the word that covers tile column 0, + 160; bits 0..10 = tile-relative end + 256
     uint32_t *s_meta = s_words + a.words_cap;
     int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);  // relative start (sorted): the candidate search key
     uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
             w_end = a.rd.tile_whi[tile];
         } else {
             w_first = __ldg(a.rd.seg_word + c0) - 1;              // the separator in front of the chunk's first segment
-            w_end = __ldg(a.rd.seg_word + last) + ((__ldg(a.rd.seg_len + last) + 7) >> 3) + 1;
+            w_end = __ldg(a.rd.seg_word + last) + (((__ldg(a.rd.seg_start + last) & 7) + __ldg(a.rd.seg_len + last) + 7) >> 3) + 1;
         }
         const int64_t wb = w_first & ~(int64_t)3;                 // 16-byte aligned source
         const int64_t wn = ((w_end - wb) + 3) & ~(int64_t)3;
@@ -243,13 +244,13 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
                 const int32_t s = r_s[k] - a.start;
                 const int n = r_n[k];
                 const int64_t wl = r_w[k] - wb;
-                if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + ((n + 7) >> 3) + 1 > wn ||
+                if (n < 1 || n > maxlen || s < 0 || (int64_t)s + n > (int64_t)a.L || wl < 1 || wl + (((s & 7) + n + 7) >> 3) + 1 > wn ||
                     r_prev[k] > r_s[k])
                     err |= ISB_DEV_ERR_SEG;
                 const int n_c = min(max(n, 0), maxlen);
                 const int wl_c = (int)min(max(wl, (int64_t)1), wn - 1);
                 const int s_rel = min(max(s - T0, -255), K1R_TILE - 1);   // candidates start in (T0 - 256, T0 + 1024)
-                s_meta[i] = ((uint32_t)(wl_c * 8 - s_rel + 1024) << 11) | (uint32_t)(s_rel + n_c + 256);
+                s_meta[i] = ((uint32_t)(wl_c - (s_rel >> 3) + 160) << 11) | (uint32_t)(s_rel + n_c + 256);
                 s_start[i] = s;
                 if (!kM1) {
                     if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
@@ -274,14 +275,12 @@ __global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
             while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key2) l = mid + 1; else h = mid; }
             ch = l;
         }
-        // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach)
-        const int P_na = t * 8 - 1024, P_end = t * 8 + 256;
+        // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach).  The stream
+        // is position-aligned: the thread's column is ONE word of the segment, no shift.
+        const int t_off = t - 160, P_end = t * 8 + 256;
         auto fetch = [&](int i) -> uint32_t {
             const uint32_t md = s_meta[i];
-            const int na = (int)(md >> 11) + P_na;                 // nibble address of position P in the staged words
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(s_words) +
-                                                                   ((na >> 1) & ~3));
-            const uint32_t x = __funnelshift_r(w[0], w[1], na << 2);
+            const uint32_t x = s_words[(int)(md >> 11) + t_off];
             return P_end < (int)(md & 0x7ffu) ? x : 0u;            // short segment: those words belong to a later one
         };
         if (kM1) {
@@ -388,6 +387,7 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
         return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: max_seg_len must be in [1, 256]");
     if (M > 1 && !pair_mm) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: pair_mm is required when M > 1");
     if (((uintptr_t)rd->words & 15) != 0) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: words must be 16-byte aligned");
+    if (start & 7) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: start must be a multiple of 8 (the stream is position-aligned)");
     const int n_tiles = (L + K1R_TILE - 1) / K1R_TILE;
     int rc;
     if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 4 * (size_t)n_tiles))) return rc;
@@ -407,7 +407,7 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     a.nmask = nmask; a.d_err = ctx->d_err;
     // Shared-memory budget: the staging area should hold the whole candidate set of a tile (then every thread works in
     // every chunk); two blocks per SM.  Bytes per staged segment: its words incl. separator + 4 (meta) + 4 (start) + 1 (mm).
-    const int wps = rd->max_seg_len / 8 + 3;                      // data words + up to two separator words
+    const int wps = (rd->max_seg_len + 14) / 8 + 2;               // position-aligned data words + up to two separator words
     const size_t per_seg = (size_t)wps * 4 + 9;
     const int groups = M == 1 ? 1 : (M + K1R_LEVELS - 1) / K1R_LEVELS;
     const int Mg = M == 1 ? 0 : (M < K1R_LEVELS ? M : K1R_LEVELS);

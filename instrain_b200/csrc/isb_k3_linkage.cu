@@ -142,10 +142,12 @@ __global__ void __launch_bounds__(256) k3r_site_cand(k3_args a, isb_reads_dev rd
 // One candidate of a site: is position abs_pos covered by segment g with a passing A/C/T/G base?
 __device__ __forceinline__ bool k3r_candidate(const isb_reads_dev &rd, int64_t g, int64_t abs_pos, int &b, int &id)
 {
-    const int j = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
+    const int32_t s = __ldg(rd.seg_start + g);
+    const int j = (int)(abs_pos - (int64_t)s);
     if (j < 0 || j >= (int)__ldg(rd.seg_len + g)) return false;
-    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (j >> 3));
-    const uint32_t code = (w >> ((j & 7) << 2)) & 15u;
+    const int jn = j + (s & 7);                                       // position-aligned stream: nibble index in the segment's words
+    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (jn >> 3));
+    const uint32_t code = (w >> ((jn & 7) << 2)) & 15u;
     if (!code) return false;
     b = __ffs((int)code) - 1;                                       // one-hot A,C,T,G
     id = __ldg(rd.seg_pair + g);
@@ -203,11 +205,13 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
             for (int r = 0; r < 4; ++r) {
                 const int idx = i0 + r * 32 + lane;
                 const int64_t g = clo + min(idx, nc - 1);
-                j4[r] = (int)(abs_pos - (int64_t)__ldg(rd.seg_start + g));
+                const int32_t s = __ldg(rd.seg_start + g);
+                const int j = (int)(abs_pos - (int64_t)s);
                 const int len = (int)__ldg(rd.seg_len + g);
                 wd4[r] = __ldg(rd.seg_word + g);
                 id4[r] = __ldg(rd.seg_pair + g);
-                cov[r] = idx < nc && j4[r] >= 0 && j4[r] < len;
+                cov[r] = idx < nc && j >= 0 && j < len;
+                j4[r] = j + (s & 7);                                   // nibble index in the segment's (position-aligned) words
             }
             uint32_t w4[4];
 #pragma unroll

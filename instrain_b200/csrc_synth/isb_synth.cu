@@ -215,8 +215,8 @@ __global__ void synth_events(isbs_params prm, int K, uint32_t dens24, int64_t Lt
 // ---- read-major output: the same fragments as aligned segments (one per mate), sorted by start ------------------------
 // one thread per position: the segments STARTING there (mate 1 of the fragments starting at pg, then mate 2 of the
 // fragments whose second mate starts at pg).  kFill = false counts, kFill = true writes the segment table.
-#define SEG_DATA_WORDS ((READLEN + 7) / 8)
-static int g_seg_words = SEG_DATA_WORDS + 1;       // data words + 1 (or 2) zero separator words
+#define SEG_DATA_WORDS ((READLEN + 14) / 8)        // position-aligned words of a READLEN segment at the worst offset
+static int g_seg_words = SEG_DATA_WORDS + 1;       // block size: data words (one may stay empty) + 1 (or 2) zero separator words
 template <bool kFill>
 __global__ void synth_seg_table(isbs_params prm, int K, uint32_t dens24, int64_t Ltot, const int32_t *__restrict__ slot_id,
                                 const uint16_t *__restrict__ slot_F, const int64_t *__restrict__ seg_off,
@@ -274,10 +274,12 @@ __global__ void synth_seg_words(isbs_params prm, uint32_t dens24, int64_t n_segs
     const uint32_t hu = (r1 >> 32) & 0xffff;
     const int hap = (hu >= 26214) + (hu >= 45875) + (hu >= 58982);
     uint32_t *dst = words + 1 + i * SEG_WORDS;
+    const int sh = (int)(start & 7);               // position-aligned stream: base o sits at nibble o + sh
     for (int wj = 0; wj < SEG_DATA_WORDS; ++wj) {
         uint32_t word = 0;
         for (int nb = 0; nb < 8; ++nb) {
-            const int o = wj * 8 + nb;
+            const int o = wj * 8 + nb - sh;
+            if (o < 0) continue;
             if (o >= READLEN) break;
             const int64_t pg = start + o;
             const int d = (int)(pg - xg);

@@ -2,7 +2,9 @@
 
 Layout and rules: include/instrain_b200.h (isb_reads_batch).  One 4-bit ONE-HOT code per aligned base, stored once per
 read: A=1, C=2, T=4, G=8 for a base that is an event (quality >= min_qual after htslib's mate-overlap tweak), 0 otherwise;
-passing non-ACGT bases go to the separate (nev_pos, nev_pair) list.
+passing non-ACGT bases go to the separate (nev_pos, nev_pair) list.  The stream is POSITION-ALIGNED: the words of a
+segment cover the 8-position columns of the batch coordinate system (word 0 = coordinates [start & ~7, (start & ~7) + 8)),
+so the nibble of coordinate p is nibble (p - start) + (start & 7) of the segment's words.
 
 `events_to_reads` rebuilds segments from position-major event columns (what the test fixtures and the oracle use):
 the events of a pair form runs of consecutive positions; a pair that enters the same column twice (both mates, htslib's
@@ -41,7 +43,8 @@ def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_
     order = np.argsort(seg_start, kind="stable")
     seg_start, seg_len, seg_pair, code_off = seg_start[order], seg_len[order], seg_pair[order], code_off[order]
     n = len(seg_start)
-    nw = (seg_len + 7) // 8
+    sh = seg_start & 7                                                     # position-aligned words: leading zero nibbles
+    nw = (sh + seg_len + 7) // 8
     blk = nw + 1                                                           # data words + separator(s)
     if odd_blocks:
         blk = blk + (1 - blk % 2)                                          # odd block sizes spread K1r's shared-memory banks
@@ -50,7 +53,7 @@ def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_
         seg_word[1:] = 1 + np.cumsum(blk[:-1])
     n_words = int(seg_word[-1] + blk[-1]) if n else 1
     n_words = (n_words + 3) // 4 * 4
-    # nibble j of segment i -> word seg_word[i] + j // 8, bits 4 * (j % 8)
+    # base j of segment i -> nibble j + sh[i]: word seg_word[i] + (j + sh) // 8, bits 4 * ((j + sh) % 8)
     tot = int(seg_len.sum())
     seg_of = np.repeat(np.arange(n), seg_len)
     j = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len)
@@ -60,7 +63,7 @@ def build_reads(seg_start, seg_len, seg_pair, codes, code_off=None, max_len=MAX_
     nev_pos = (np.repeat(seg_start, seg_len) + j)[is_n]
     nev_pair = np.repeat(seg_pair, seg_len)[is_n]
     nib = np.zeros(n_words * 8, dtype=np.uint8)
-    nib[(np.repeat(seg_word, seg_len) * 8 + j)] = onehot
+    nib[(np.repeat(seg_word * 8 + sh, seg_len) + j)] = onehot
     nib = nib.reshape(-1, 8).astype(np.uint32)
     words = np.zeros(n_words, dtype=np.uint32)
     for k in range(8):
@@ -103,8 +106,9 @@ def reads_to_events(rd, min_qual=30):
     seg_len = rd["seg_len"].astype(np.int64)
     tot = int(seg_len.sum())
     j = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(seg_len) - seg_len, seg_len)
-    w = rd["words"][np.repeat(rd["seg_word"], seg_len) + j // 8]
-    code = (w >> (4 * (j % 8)).astype(np.uint32)) & 15
+    jn = j + np.repeat(rd["seg_start"].astype(np.int64) & 7, seg_len)      # nibble index inside the segment's words
+    w = rd["words"][np.repeat(rd["seg_word"], seg_len) + jn // 8]
+    code = (w >> (4 * (jn % 8)).astype(np.uint32)) & 15
     keep = code != 0
     pos = np.concatenate([(np.repeat(rd["seg_start"].astype(np.int64), seg_len) + j)[keep], rd["nev_pos"].astype(np.int64)])
     rid = np.concatenate([np.repeat(rd["seg_pair"], seg_len)[keep], rd["nev_pair"]])
@@ -118,7 +122,7 @@ def compact_reads(rd):
     """Read-major batch -> compact TRANSFER format (include/instrain_b200.h, isb_reads_compact): per unit of 8 bases one
     uint16 of 2-bit base codes and one uint8 of event bits; no word offsets (the device rebuilds the canonical stream)."""
     seg_len = rd["seg_len"].astype(np.int64)
-    nw = (seg_len + 7) // 8
+    nw = ((rd["seg_start"].astype(np.int64) & 7) + seg_len + 7) // 8       # units = the segment's (position-aligned) words
     n_units = int(nw.sum())
     k = np.arange(n_units, dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
     w = rd["words"][np.repeat(np.asarray(rd["seg_word"], dtype=np.int64), nw) + k].astype(np.uint32)

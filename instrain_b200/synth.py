@@ -71,9 +71,11 @@ def generate(device, L, n_scaffolds, coverage, snv_density, seed, skip_mm=True, 
     seg_pair, seg_word, words, ...; instrain_b200/reads.py layout).  Always: pair_mm, ref_codes."""
     import torch
     lib = _load()
-    spw = (READLEN + 7) // 8 + 1 if seg_words is None else int(seg_words)
+    spw = (READLEN + 14) // 8 + 1 if seg_words is None else int(seg_words)      # position-aligned data words + separator
     if lib.isbs_set_seg_words(spw) != 0:
-        raise ValueError("seg_words must be %d or %d" % ((READLEN + 7) // 8 + 1, (READLEN + 7) // 8 + 2))
+        raise ValueError("seg_words must be %d or %d" % ((READLEN + 14) // 8 + 1, (READLEN + 14) // 8 + 2))
+    if reads and L % 8:
+        raise ValueError("scaffold length must be a multiple of 8 (the read-major stream is position-aligned)")
     prm = _Params(L, n_scaffolds, coverage, float(snv_density), seed, 1 if skip_mm else 0, 0)
     n_ev, n_pairs = C.c_int64(0), C.c_int64(0)
     if lib.isbs_plan(device, C.byref(prm), C.byref(n_ev), C.byref(n_pairs)) != 0:

@@ -160,7 +160,7 @@ def test_device_generator_reads_equal_events(eng, null_lut):
     from instrain_b200 import synth as dsynth
     for skip_mm in (True, False):
         d = dsynth.generate(0, 50000, 3, 60, 0.01, 77, skip_mm=skip_mm, events=True, reads=True,
-                            seg_words=21 if skip_mm else None)
+                            seg_words=22 if skip_mm else None)
         rd = d["reads"]
         assert rd["n_segs"] == 2 * d["pair_mm"].numel() and int(rd["seg_len"].min()) == 150
         M = int(d["pair_mm"].max().item()) + 1

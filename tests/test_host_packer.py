@@ -172,7 +172,7 @@ def test_read_major_packer_matches_event_packer(bam, r2m_json):
             for x, y in zip(_canon(back), _canon(ev, ok)):
                 assert np.array_equal(x, y), name
             if rd["n_segs"]:
-                nw = (rd["seg_len"].astype(np.int64) + 7) // 8
+                nw = ((rd["seg_start"].astype(np.int64) & 7) + rd["seg_len"].astype(np.int64) + 7) // 8   # position-aligned words
                 assert rd["seg_word"][0] == 1 and np.all(np.diff(rd["seg_word"]) == nw[:-1] + 1)
                 assert np.all(np.diff(rd["seg_start"]) >= 0) and rd["seg_len"].min() >= 1 and rd["max_seg_len"] <= 256
                 assert rd["n_words"] % 4 == 0 and rd["seg_word"][-1] + nw[-1] < rd["n_words"]
@@ -188,7 +188,7 @@ def test_compact_reads_round_trip():
     for kw in (dict(), dict(max_len=37, odd_blocks=True)):
         rd = reads.events_to_reads(batch, **kw)
         c = reads.compact_reads(rd)
-        nw = (rd["seg_len"].astype(np.int64) + 7) // 8
+        nw = ((rd["seg_start"].astype(np.int64) & 7) + rd["seg_len"].astype(np.int64) + 7) // 8
         assert c["n_units"] == nw.sum() == len(c["base2"]) == len(c["pass"])
         k = np.arange(c["n_units"]) - np.repeat(np.cumsum(nw) - nw, nw)
         w = rd["words"][np.repeat(rd["seg_word"], nw) + k]
