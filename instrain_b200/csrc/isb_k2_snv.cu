@@ -214,6 +214,105 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
     k2_emit_rows(st, p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, rows, cap, n_rows);
 }
 
+// M = 1 specialisation (--skip_mm_profiling, the throughput configuration).  With a single level the reference's loop
+// body runs once per site: no cumulative state, `cryptic` can never be set (it needs an earlier level with a SNP), and
+// a site has at most ONE row -- so rows are allocated with a ballot (one atomic per warp that has rows) and written in
+// the same pass.  ncu on the generic kernel at M = 1: 254 warp instructions per 32 sites, 80 % of them integer / control
+// overhead of the level loop, the state struct and the second (row-writing) pass that 27 % of the warps entered.
+__global__ void __launch_bounds__(K2_THREADS)
+k2_call_snvs_m1(int32_t L, const int32_t *__restrict__ counts, const unsigned long long *__restrict__ nmask,
+                const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
+                int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
+                uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
+                unsigned long long *__restrict__ n_rows)
+{
+    const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
+    const bool active = p < L;
+    bool is_row = false;
+    int C[4] = {0, 0, 0, 0}, T = 0, i = 0, con = 0, thr = 0, r = 4;
+    if (active) {
+        const int4 E = __ldg(reinterpret_cast<const int4 *>(counts) + p);
+        r = ref[p];
+        T = E.x + E.y + E.z + E.w;
+        const bool present = T > 0 || (nmask && (nmask[p] & 1ull));   // level 0 is a key of MMcounts
+        const bool counted = present && T >= min_cov;
+        C[0] = E.x; C[1] = E.y; C[2] = E.z; C[3] = E.w;
+        float clon = CUDART_NAN_F;
+        if (counted) {                                                // calculate_clonality, double, A,C,T,G order
+            const int mx = max(max(C[0], C[1]), max(C[2], C[3]));
+            if (mx == T && T > 0) {
+                clon = 1.0f;                                          // one base only: (T/T)^2 + 0 + 0 + 0 is exactly 1
+            } else {
+                const double s = (double)T;
+                double f0, f1, f2, f3;
+                if (T <= K2_FAST_DIV_MAX) {
+                    const double rcp = __drcp_rn(s);
+                    f0 = k2_quot((double)C[0], s, rcp); f1 = k2_quot((double)C[1], s, rcp);
+                    f2 = k2_quot((double)C[2], s, rcp); f3 = k2_quot((double)C[3], s, rcp);
+                } else {
+                    f0 = C[0] ? __ddiv_rn((double)C[0], s) : 0.0; f1 = C[1] ? __ddiv_rn((double)C[1], s) : 0.0;
+                    f2 = C[2] ? __ddiv_rn((double)C[2], s) : 0.0; f3 = C[3] ? __ddiv_rn((double)C[3], s) : 0.0;
+                }
+                double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
+                prob = __dadd_rn(prob, __dmul_rn(f2, f2));
+                prob = __dadd_rn(prob, __dmul_rn(f3, f3));
+                clon = __double2float_rn(prob);
+            }
+        }
+        covT[p] = T;
+        clonT[p] = clon;
+        unsigned flags = 0u;
+        if (counted) {
+            if (T < n_lut) {
+                thr = __ldg(thr2 + T);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) i += (C[b] >= thr);
+            } else {
+                thr = lut_default;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (C[b] >= thr && __ddiv_rn((double)C[b], (double)T) >= min_freq) ++i;
+            }
+            con = k2_argmax4(C);
+            is_row = (i > 1) || (i == 1 && con != r) || (i == 0);
+            if (is_row && i >= 2) {
+                const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
+                flags = ISB_SITE_ANYSNP | (1u << con) | (1u << k2_argmax4(tmp));
+            }
+        }
+        site_flags[p] = (uint8_t)flags;
+    }
+    const unsigned mask = __ballot_sync(ISB_FULL, is_row);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base_slot = 0;
+    if (lane == 0) base_slot = atomicAdd(n_rows, (unsigned long long)__popc(mask));
+    base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
+    if (!is_row) return;
+    const int64_t slot = (int64_t)base_slot + __popc(mask & ((1u << lane) - 1u));
+    if (slot >= cap) return;
+    const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
+    const int var = k2_argmax4(tmp);
+    int cls;
+    if (r > 3) cls = ISB_CLS_AMBIGUOUS_REFERENCE;
+    else if (i == 0) cls = ISB_CLS_DIVERGENT_SITE;
+    else if (i == 1) cls = ISB_CLS_SNS;
+    else if (r == con) cls = ISB_CLS_SNV;
+    else if (r == var) cls = ISB_CLS_CON_SNV;
+    else {
+        const int cr = r == 0 ? C[0] : r == 1 ? C[1] : r == 2 ? C[2] : C[3];                   // is_present(counts[ref], ...)
+        const bool pres = T < n_lut ? (cr >= thr) : (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq);
+        cls = pres ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
+    }
+    int4 lo, hi;
+    lo.x = p + start; lo.y = C[0]; lo.z = C[1]; lo.w = C[2];
+    hi.x = C[3]; hi.y = 0;
+    hi.z = (r & 0xff) | (con << 8) | (var << 16) | (i << 24);
+    hi.w = cls;
+    int4 *dst = reinterpret_cast<int4 *>(rows + slot);
+    dst[0] = lo; dst[1] = hi;
+}
+
 // M > 1: a thread's M count quads are 16*M bytes apart from its neighbour's, so direct loads touch one 32-byte sector per
 // 16 useful bytes and the 4-byte covT / clonT stores one sector each.  The staged kernel moves the block's rows through
 // shared memory instead.  M <= K2S_MC (every realistic read filter: <= 15 mismatches per pair): the block's input rows
@@ -331,7 +430,7 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
         ISB_LAUNCH_CHECK();
         ctx->thr2_min_freq = min_freq;
     }
-    static const int variant = getenv("ISB_K2_VARIANT") ? atoi(getenv("ISB_K2_VARIANT")) : -1;   // 0 = direct, 1 = staged
+    static const int variant = getenv("ISB_K2_VARIANT") ? atoi(getenv("ISB_K2_VARIANT")) : -1;   // 0 = generic direct kernel, otherwise M = 1: specialised, M > 1: staged
     if (M > 1 && variant != 0) {
         const size_t smem = k2s_smem_bytes(M);
         static bool attr_set[64] = {false};                          // function attributes are per device
@@ -341,6 +440,10 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
         }
         k2_call_snvs_staged<<<(L + K2S_THREADS - 1) / K2S_THREADS, K2S_THREADS, smem, st>>>(
             L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
+            site_flags, rows, cap, ctx->d_counters + 0);
+    } else if (M == 1 && variant != 0) {
+        k2_call_snvs_m1<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
+            L, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
             site_flags, rows, cap, ctx->d_counters + 0);
     } else {
         k2_call_snvs<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
