@@ -176,7 +176,7 @@ __device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m
 #define K3R_EV_CAP 320
 __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
                                                             const int32_t *__restrict__ n_cand, int64_t *__restrict__ row_off,
-                                                            unsigned long long *__restrict__ row_words_total, int64_t row_cap, int batch_loads)
+                                                            unsigned long long *__restrict__ row_words_total, int64_t row_cap)
 {
     __shared__ uint32_t s_rows[K3_THREADS / 32][K3_ROW_SCRATCH];
     __shared__ int32_t s_id[K3_THREADS / 32][K3R_EV_CAP];
@@ -193,60 +193,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
         const int64_t clo = cand_lo[k];
         const int nc = n_cand[k];
         int cnt = 0, idmin = INT_MAX, idmax = -1;
-        if (!batch_loads) {
-            for (int i0 = 0; i0 < nc; i0 += 32) {
-                int b = 0, id = 0;
-                bool ok = (i0 + lane < nc) && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id);
-                ok = ok && ((bases >> b) & 1u);
-                const unsigned mask = __ballot_sync(ISB_FULL, ok);
-                if (ok) {
-                    const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-                    if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
-                    idmin = min(idmin, id);
-                    idmax = max(idmax, id);
-                }
-                cnt += __popc(mask);
+        for (int i0 = 0; i0 < nc; i0 += 32) {
+            int b = 0, id = 0;
+            bool ok = (i0 + lane < nc) && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id);
+            ok = ok && ((bases >> b) & 1u);
+            const unsigned mask = __ballot_sync(ISB_FULL, ok);
+            if (ok) {
+                const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+                if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
+                idmin = min(idmin, id);
+                idmax = max(idmax, id);
             }
-        } else
-        // Candidates in batches of 4 x 32.  Each batch costs TWO memory latencies: all table loads (start, length, word
-        // offset, pair id) of the lane's four candidates are issued together, then the four stream words.  (One
-        // candidate at a time, table entry -> word address -> word, was a chain of ~4 dependent loads per 32
-        // candidates: ncu showed the kernel waiting on exactly that, 1.5 of K3's 2.7 ms.)
-        for (int i0 = 0; i0 < nc; i0 += 128) {
-            int j4[4], id4[4];
-            int64_t wd4[4];
-            bool cov[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int idx = i0 + r * 32 + lane;
-                const int64_t g = clo + min(idx, nc - 1);
-                const int32_t s = __ldg(rd.seg_start + g);
-                const int j = (int)(abs_pos - (int64_t)s);
-                const int len = (int)__ldg(rd.seg_len + g);
-                wd4[r] = __ldg(rd.seg_word + g);
-                id4[r] = __ldg(rd.seg_pair + g);
-                cov[r] = idx < nc && j >= 0 && j < len;
-                j4[r] = j + (s & 7);                                   // nibble index in the segment's (position-aligned) words
-            }
-            uint32_t w4[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) w4[r] = cov[r] ? __ldg(rd.words + wd4[r] + (j4[r] >> 3)) : 0u;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (i0 + r * 32 >= nc) break;                          // warp-uniform
-                const uint32_t code = (w4[r] >> ((j4[r] & 7) << 2)) & 15u;
-                const int b = __ffs((int)code) - 1;                    // one-hot A,C,T,G (-1: not an event)
-                const int id = id4[r];
-                const bool ok = code != 0u && ((bases >> (b & 3)) & 1u);
-                const unsigned mask = __ballot_sync(ISB_FULL, ok);
-                if (ok) {
-                    const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-                    if (slot < K3R_EV_CAP) { s_id[wib][slot] = id; s_b[wib][slot] = (uint8_t)b; }
-                    idmin = min(idmin, id);
-                    idmax = max(idmax, id);
-                }
-                cnt += __popc(mask);
-            }
+            cnt += __popc(mask);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -712,7 +670,6 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
     }
     int64_t *cand_lo = nullptr;
     int32_t *n_cand = nullptr;
-    int k3r_batch = 0;
     if (!rd) {                                                  // position-major columns
         const int tp = 1024;                                    // searches bounded by position-tile event offsets
         const int n_tiles = (L + tp - 1) / tp;
@@ -746,8 +703,6 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
         ISB_LAUNCH_CHECK();
         // initial guess of the row storage (words per site); the fused kernel reports the exact need if it is too small
-        static const int k3r_batch_env = getenv("ISB_K3R_BATCH") ? atoi(getenv("ISB_K3R_BATCH")) : 0;
-        k3r_batch = k3r_batch_env;
         static const int rows_init = getenv("ISB_K3_ROWS_INIT") ? atoi(getenv("ISB_K3_ROWS_INIT")) : 48;
         if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)S * (size_t)(rows_init > 0 ? rows_init : 1) + 64)))) return rc;
     }
@@ -757,7 +712,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
             a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
             ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
             k3r_site_rows<<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
-                                                           ctx->d_counters + 4, row_cap, k3r_batch);
+                                                           ctx->d_counters + 4, row_cap);
             ISB_LAUNCH_CHECK();
         }
         int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
