@@ -27,7 +27,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_RD_START, SL_RD_LEN, SL_RD_PAIR, SL_RD_WORD, SL_RD_WORDS, SL_RD_BOUNDS, SL_RD_NPOS, SL_RD_NPAIR,         // read-major batch (K1r inputs)
     SL_RC_BASE2, SL_RC_PASS,                                                       // compact transfer format (K0r inputs)
     SL_RD_CAND, SL_RD_EVOFF, SL_RD_EVB, SL_RD_EVQ, SL_RD_EVID,                          // K3 site events from segments
-    SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2, SL_SUFMIN,
+    SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
     SL_COUNT
 };
 

@@ -146,15 +146,9 @@ __device__ __forceinline__ void k1r_flush_levels(const k1r_args &a, uint32_t *s_
     }
 }
 
-// M = 1: 256 threads per tile -- two threads share a column (8 positions), each takes half of the column's candidate
-// segments, and the halves add up through shared memory at the end.  The staged tile (~99 KB) allows two blocks per SM
-// either way; with 128 threads that was 2 warps per scheduler (ncu: 12 % warps active, LSU pipe 60 %, issue 34 % -- bound
-// by latency, not by a pipe), with 256 it is 4.  M > 1 keeps one thread per column (its shared-memory counters are per thread).
 template <bool kM1>
-__global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pileup(k1r_args a)
+__global__ void __launch_bounds__(K1R_THREADS) k1r_pileup(k1r_args a)
 {
-    constexpr int NT = kM1 ? 2 * K1R_THREADS : K1R_THREADS;        // threads per block
-    constexpr int STAGE_IT = kM1 ? (K1R_STAGE_IT + 1) / 2 : K1R_STAGE_IT;
     extern __shared__ __align__(128) unsigned char k1r_smem_raw[];
     uint32_t *s_words = reinterpret_cast<uint32_t *>(k1r_smem_raw);
     // one packed word per segment (a 32-bit load has half the bank conflicts of a 64-bit one when every lane follows its
@@ -165,9 +159,7 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
     uint64_t *bar = reinterpret_cast<uint64_t *>(k1r_smem_raw + (((size_t)a.words_cap * 4 + (size_t)a.seg_cap * 9 + 7) & ~(size_t)7));
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bar) + 16);
 
-    const int tid = threadIdx.x;
-    const int t = tid & (K1R_THREADS - 1);                      // the thread's column of the tile
-    const int half = tid / K1R_THREADS;                         // M = 1: which half of the column's candidates
+    const int t = threadIdx.x;
     const int tile = blockIdx.x;
     const int32_t T0 = tile * K1R_TILE;
     const int32_t P = T0 + t * 8;                               // first of the thread's 8 positions (relative)
@@ -187,7 +179,7 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
         for (int b = 0; b < 4; ++b) c[k][b] = 0;
     if (!kM1)
         for (int w = 0; w < Mg * 8; ++w) s_acc[w * K1R_THREADS + t] = 0u;
-    if (tid == 0) {
+    if (t == 0) {
         isb_mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -212,7 +204,7 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
             err |= ISB_DEV_ERR_SEG;
             continue;
         }
-        if (tid == 0) {
+        if (t == 0) {
             isb_mbar_expect_tx(bar, (unsigned)wn * 4u);
             isb_bulk_g2s(s_words, a.rd.words + wb, (unsigned)wn * 4u, bar);
         }
@@ -220,12 +212,12 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
         // handles are issued before the first is used, so the block pays ONE memory latency here instead of one per
         // element (ncu: the per-element version spent 36 % of its cycles on this loop's long-scoreboard stalls).
         {
-            int32_t r_s[STAGE_IT], r_prev[STAGE_IT], r_pid[STAGE_IT];
-            int r_n[STAGE_IT];
-            int64_t r_w[STAGE_IT];
+            int32_t r_s[K1R_STAGE_IT], r_prev[K1R_STAGE_IT], r_pid[K1R_STAGE_IT];
+            int r_n[K1R_STAGE_IT];
+            int64_t r_w[K1R_STAGE_IT];
 #pragma unroll
-            for (int k = 0; k < STAGE_IT; ++k) {
-                const int i = tid + k * NT;
+            for (int k = 0; k < K1R_STAGE_IT; ++k) {
+                const int i = t + k * K1R_THREADS;
                 const int64_t g = c0 + i;
                 r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1; r_pid[k] = 0;
                 if (i < nc) {
@@ -236,18 +228,18 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
                     if (!kM1) r_pid[k] = __ldg(a.rd.seg_pair + g);
                 }
             }
-            int r_mm[STAGE_IT];
+            int r_mm[K1R_STAGE_IT];
             if (!kM1) {
 #pragma unroll
-                for (int k = 0; k < STAGE_IT; ++k) {
+                for (int k = 0; k < K1R_STAGE_IT; ++k) {
                     r_mm[k] = 255;
-                    if (tid + k * NT < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
+                    if (t + k * K1R_THREADS < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
                         r_mm[k] = __ldg(a.pair_mm + r_pid[k]);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < STAGE_IT; ++k) {
-                const int i = tid + k * NT;
+            for (int k = 0; k < K1R_STAGE_IT; ++k) {
+                const int i = t + k * K1R_THREADS;
                 if (i >= nc) break;
                 const int32_t s = r_s[k] - a.start;
                 const int n = r_n[k];
@@ -292,8 +284,6 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
             return P_end < (int)(md & 0x7ffu) ? x : 0u;            // short segment: those words belong to a later one
         };
         if (kM1) {
-            const int mid = cl + ((ch - cl + 1) >> 1);             // first half of the candidates / second half
-            if (half) cl = mid; else ch = mid;
             int i = cl;
             for (; i + 16 <= ch; i += 16) {                        // two Harley-Seal blocks per trip: 16 fetches in flight
                 uint32_t x[8], y[8];
@@ -357,28 +347,17 @@ __global__ void __launch_bounds__(kM1 ? 2 * K1R_THREADS : K1R_THREADS, 2) k1r_pi
         }
     }
     if (err) atomicOr(a.d_err, err);
+    if (!active) return;
 
-    if (kM1) {                                                    // the halves of a column add up through shared memory
+    if (kM1) {
         k1r_planes_to_counts(c, pl);
-        __syncthreads();                                          // every thread is done with the staged words
-        int32_t *s_red = reinterpret_cast<int32_t *>(s_words);    // [32][K1R_THREADS]: lane = bank
-        if (half) {
+        int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) s_red[(k * 4 + b) * K1R_THREADS + t] = c[k][b];
+        for (int k = 0; k < 8; ++k) {
+            if (P + k >= a.L) break;
+            c4[k] = make_int4(c[k][0], c[k][1], c[k][2], c[k][3]);
         }
-        __syncthreads();
-        if (!half && active) {
-            int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (P + k >= a.L) break;
-                c4[k] = make_int4(c[k][0] + s_red[(k * 4 + 0) * K1R_THREADS + t], c[k][1] + s_red[(k * 4 + 1) * K1R_THREADS + t],
-                                  c[k][2] + s_red[(k * 4 + 2) * K1R_THREADS + t], c[k][3] + s_red[(k * 4 + 3) * K1R_THREADS + t]);
-            }
-        }
-    } else if (active) {
+    } else {
         k1r_flush_levels(a, s_acc, t, Mg, m_base, P, spilled, false);
     }
 }
@@ -442,7 +421,6 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
     if (seg_cap > K1R_STAGE_IT * K1R_THREADS) seg_cap = K1R_STAGE_IT * K1R_THREADS;
     a.seg_cap = seg_cap;
     a.words_cap = (seg_cap * wps + 8 + 3) & ~3;
-    if (M == 1 && a.words_cap < 32 * K1R_THREADS) a.words_cap = 32 * K1R_THREADS;   // the staging area doubles as the [32][128] reduction buffer
     const size_t smem = (((size_t)a.words_cap * 4 + (size_t)seg_cap * 9 + 7) & ~(size_t)7) + 16 + acc_bytes;
     static bool attr_m1[64] = {false}, attr_mm[64] = {false};      // function attributes are per device
     if (nmask) ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
@@ -450,7 +428,7 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
         if (!attr_m1[ctx->device & 63])
             ISB_CUDA(cudaFuncSetAttribute(k1r_pileup<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_m1[ctx->device & 63] = true;
-        k1r_pileup<true><<<n_tiles, 2 * K1R_THREADS, smem, st>>>(a);
+        k1r_pileup<true><<<n_tiles, K1R_THREADS, smem, st>>>(a);
         ISB_LAUNCH_CHECK();
     } else {
         if (!attr_mm[ctx->device & 63])

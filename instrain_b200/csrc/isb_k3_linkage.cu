@@ -460,82 +460,11 @@ __device__ __forceinline__ bool k3_level_present(const k3_args &a, int32_t p, in
     return a.nmask && ((a.nmask[p] >> m) & 1ull);
 }
 
-// Suffix minimum of the sites' first pair-id word: sufmin[k] = min over j >= k (inside k's block of K3_SUF_BLOCK sites) of
-// wlo_j, btop[b] = min over all sites of the blocks after b.  Two sites can only be linked when their pair-id windows
-// overlap, and min(sufmin[j], btop[block of j]) never decreases with j, so the partner scan of a site stops at the first
-// j whose bound is past the site's own window -- typically a handful of sites instead of the rest of its split.
-#define K3_SUF_THREADS 256
-#define K3_SUF_ITEMS 8
-#define K3_SUF_BLOCK (K3_SUF_THREADS * K3_SUF_ITEMS)
-__global__ void __launch_bounds__(K3_SUF_THREADS) k3_sufmin_blocks(k3_args a, int32_t *__restrict__ sufmin, int32_t *__restrict__ bmin)
-{
-    __shared__ int s_warp[K3_SUF_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * K3_SUF_BLOCK + (int64_t)threadIdx.x * K3_SUF_ITEMS;
-    int v[K3_SUF_ITEMS];
-    int run = INT_MAX;
-#pragma unroll
-    for (int k = K3_SUF_ITEMS - 1; k >= 0; --k) {                      // the thread's own items, right to left
-        int w = INT_MAX;
-        if (base + k < a.S) { const isb_site_meta m = a.meta[base + k]; if (m.nw > 0) w = m.wlo; }
-        run = min(run, w);
-        v[k] = run;
-    }
-    int incl = run;                                                     // suffix min over the threads of the warp
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int u = __shfl_down_sync(ISB_FULL, incl, d);
-        if (lane + d < 32) incl = min(incl, u);
-    }
-    if (lane == 0) s_warp[warp] = incl;
-    __syncthreads();
-    int after = INT_MAX;                                                // min over the later warps of the block
-    for (int w = warp + 1; w < K3_SUF_THREADS / 32; ++w) after = min(after, s_warp[w]);
-    int next = __shfl_down_sync(ISB_FULL, incl, 1);                     // suffix min of the later threads of the warp
-    if (lane == 31) next = INT_MAX;
-    const int tail = min(next, after);
-#pragma unroll
-    for (int k = 0; k < K3_SUF_ITEMS; ++k)
-        if (base + k < a.S) sufmin[base + k] = min(v[k], tail);
-    if (threadIdx.x == 0) bmin[blockIdx.x] = min(incl, after);
-}
-
-// single block: btop[b] = min(bmin[b+1 ..]) in place
-__global__ void __launch_bounds__(1024) k3_sufmin_tops(int32_t *__restrict__ bmin, int nb)
-{
-    __shared__ int s_carry;
-    __shared__ int s_warp[32];
-    if (threadIdx.x == 0) s_carry = INT_MAX;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int hi = nb; hi > 0; hi -= 1024) {                             // chunks of 1024 blocks, right to left
-        const int i = hi - 1024 + (int)threadIdx.x;
-        const int v = i >= 0 ? bmin[i] : INT_MAX;
-        int incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int u = __shfl_down_sync(ISB_FULL, incl, d);
-            if (lane + d < 32) incl = min(incl, u);
-        }
-        if (lane == 0) s_warp[warp] = incl;
-        __syncthreads();
-        int after = s_carry;
-        for (int w = warp + 1; w < 32; ++w) after = min(after, s_warp[w]);
-        int next = __shfl_down_sync(ISB_FULL, incl, 1);
-        if (lane == 31) next = INT_MAX;
-        __syncthreads();
-        if (i >= 0) bmin[i] = min(next, after);                         // exclusive: the blocks after i
-        if (threadIdx.x == 0) s_carry = min(incl, after);
-        __syncthreads();
-    }
-}
-
 // Linked site pairs are first ENUMERATED (warp per site, lanes over the partner sites of the same split: window overlap
 // + one AND over the `any` rows), then evaluated one THREAD per pair.  The evaluation is a chain of dependent global
 // loads (rows, counts, masks); with one pair per lane of a site-warp only ~3.7 linked pairs per site kept the machine
 // busy (300 us for 3.7e5 pairs), one thread per pair puts every pair in flight at once.
-__global__ void __launch_bounds__(K3_THREADS) k3_enum_pairs(k3_args a, const int32_t *__restrict__ sufmin,
-                                                            const int32_t *__restrict__ btop)
+__global__ void __launch_bounds__(K3_THREADS) k3_enum_pairs(k3_args a)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
@@ -544,10 +473,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_enum_pairs(k3_args a, const int
         const isb_site_meta mi = a.meta[k];
         if (mi.split < 0 || mi.nw == 0) continue;
         const uint32_t *any_i = a.rows + a.row_off[k] - mi.wlo;
-        const int w_end = mi.wlo + mi.nw;
         for (int64_t jb = k + 1;; jb += 32) {
-            // every later site's window starts at or after this bound (warp-uniform, never decreases with jb)
-            if (jb >= a.S || min(__ldg(sufmin + jb), __ldg(btop + jb / K3_SUF_BLOCK)) >= w_end) break;
             const int64_t j = jb + lane;
             isb_site_meta mj;
             mj.ev_lo_rel = 0; mj.nw = 0; mj.wlo = 0; mj.split = -2;
@@ -798,14 +724,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         a.pair_i = (int32_t *)ctx->buf[SL_PAIRS].p;
         a.pair_j = a.pair_i + cap_pairs;
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(unsigned long long), st));
-        const int nb_suf = (int)((S + K3_SUF_BLOCK - 1) / K3_SUF_BLOCK);
-        if ((rc = isb_ensure(ctx, SL_SUFMIN, sizeof(int32_t) * ((size_t)S + (size_t)nb_suf)))) return rc;
-        int32_t *sufmin = (int32_t *)ctx->buf[SL_SUFMIN].p, *btop = sufmin + S;
-        k3_sufmin_blocks<<<nb_suf, K3_SUF_THREADS, 0, st>>>(a, sufmin, btop);
-        ISB_LAUNCH_CHECK();
-        k3_sufmin_tops<<<1, 1024, 0, st>>>(btop, nb_suf);
-        ISB_LAUNCH_CHECK();
-        k3_enum_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a, sufmin, btop);
+        k3_enum_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
         ISB_LAUNCH_CHECK();
         ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         ISB_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
