@@ -51,9 +51,10 @@ class ProfileResult:
     def __init__(self):
         self.scaffold_list = []
         self.scaffolds = {}
-        self.raw_snp_table = self.raw_linkage_table = self.cumulative_scaffold_table = None
+        self.raw_snp_table = self.raw_linkage_table = self.cumulative_scaffold_table = self.cumulative_snv_table = None
         self.timing = {}
         self.failures = []
+        self.store = None                     # SNVprofileStore at ISP_loc once profile_bam has written it
 
     def get(self, name):
         return getattr(self, name)
@@ -118,8 +119,9 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         for name, off in zip(batch["names"], offs):
             sp = ScaffoldProfile(name, len(s2s[name]))
             sl = slice(int(off), int(off) + len(s2s[name]))
-            sp.covT = tables.basewise(out["covT"][sl], "coverage")
-            sp.clonT = tables.basewise(out["clonT"][sl], "clonality")
+            levels = tables.present_levels(out["covT"][sl], out["nmask"][sl])
+            sp.covT = tables.basewise(out["covT"][sl], "coverage", levels)
+            sp.clonT = tables.basewise(out["clonT"][sl], "clonality", levels)
             res.scaffolds[name] = sp
             res.scaffold_list.append(name)
 
@@ -158,6 +160,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     flush(batch)
     res.raw_snp_table = pd.concat(snp_tabs, ignore_index=True) if snp_tabs else pd.DataFrame(columns=tables.SNV_COLUMNS)
     res.raw_linkage_table = pd.concat(ld_tabs, ignore_index=True) if ld_tabs else pd.DataFrame(columns=tables.LD_COLUMNS)
+    res.cumulative_snv_table = tables.cumulative_snv_table(res.raw_snp_table)
     res.cumulative_scaffold_table = (pd.concat(sum_tabs, ignore_index=True) if sum_tabs
                                      else pd.DataFrame(columns=summary.COLUMNS))
     for name, sp in res.scaffolds.items():
@@ -171,8 +174,10 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
 
 def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
-    """Drop-in for inStrain.profile.profile_bam (profile/__init__.py:7-18).  Returns an inStrain SNVprofile stored at
-    ISP_loc when the reference package (with its h5py dependency) is importable, else the ProfileResult itself."""
+    """Drop-in for inStrain.profile.profile_bam (profile/__init__.py:7-18).  Writes the SNVprofile directory at ISP_loc
+    (instrain_b200/store.py: attributes.tsv, csv.gz tables, covT / clonT .hd5) and returns the ProfileResult, whose
+    `.store` is the on-disk object (same store / get interface as inStrain.SNVprofile.SNVprofile); `.get(name)` serves
+    the in-memory tables."""
     s2s = kwargs.pop("s2s", None)
     if s2s is None:
         raise ValueError("profile_bam needs kwargs['s2s'] (scaffold -> sequence), as ProfileController.run_profile passes it")
@@ -187,18 +192,9 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
-    try:
-        import inStrain.SNVprofile
-    except Exception:
-        return res
-    Sprofile = inStrain.SNVprofile.SNVprofile(ISP_loc)
-    Sprofile.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
-    Sprofile.store("bam_loc", bam, "value", "Location of .bam file")
-    Sprofile.store("scaffold_list", res.scaffold_list, "list", "1d list of scaffolds, in same order as counts_table")
-    Sprofile.store("raw_linkage_table", res.raw_linkage_table, "pandas", "Contains raw linkage information")
-    Sprofile.store("raw_snp_table", res.raw_snp_table, "pandas", "Contains raw SNP information on a mm level")
-    Sprofile.store("cumulative_scaffold_table", res.cumulative_scaffold_table, "pandas",
-                   "Cumulative coverage on mm level. Formerly scaffoldTable.csv")
-    Sprofile.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
-    Sprofile.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
-    return Sprofile
+    # the SNVprofile directory at ISP_loc (gen_snv_profile, profile_utilities.py:670-706), written natively:
+    # inStrain.SNVprofile.SNVprofile(ISP_loc) of the reference opens it unchanged
+    if ISP_loc is not None and kwargs.get("store", True):
+        from .store import store_profile
+        res.store = store_profile(ISP_loc, bam, res)
+    return res

@@ -1,0 +1,167 @@
+"""On-disk SNVprofile layout written natively (the step after the hot path).
+
+The reference's `inStrain.SNVprofile.SNVprofile` (SNVprofile.py:24-113,555-640,789-862) is a directory
+    <ISP_loc>/{output,raw_data,log,figures}/   +   raw_data/attributes.tsv  (name, value, type, description)
+whose attributes are files next to the table, one storage type per attribute: value (inline), dictionary (.json),
+list (.txt), numpy (.npz), pandas (.csv.gz), pickle (.pickle) and `special` (covT / clonT -> .hd5, one gzip dataset
+per "<scaffold>::<mm>").  The reference class needs h5py at import time; this module writes and reads the same layout
+with instrain_b200.hd5, so `profile_bam` leaves an IS directory behind that `inStrain.SNVprofile.SNVprofile(ISP_loc)`
+(compare, GeneProfile, polymorpher, plotting) opens unchanged.  Same method names and argument meaning: store / get.
+"""
+import json
+import logging
+import os
+import pickle
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from . import hd5
+
+MIRRORED_VERSION = "1.9.1"          # inStrain/_version.py of the reference this layout follows
+FIRST_LEVELS = ["output", "raw_data", "log", "figures"]
+_README = ("The data in this folder can be easily accessed using the inStrain python API.\nFor information on how this is "
+           "done, see the inStrain documentaion at https://instrain.readthedocs.io/en/latest/\n")
+_EXT = {"dictionary": ".json", "list": ".txt", "numpy": ".npz", "pandas": ".csv.gz", "pickle": ".pickle", "special": ".hd5"}
+_HD5_NAMES = ("covT", "clonT", "clonTR", "snpsCounted")
+
+
+def _json_default(o):
+    if isinstance(o, np.integer):
+        return int(o)
+    if isinstance(o, np.floating):
+        return float(o)
+    if isinstance(o, (set, np.ndarray)):
+        return list(o)
+    raise TypeError(type(o))
+
+
+class SNVprofileStore:
+    def __init__(self, location):
+        self.location = os.path.abspath(location)
+        for lvl in FIRST_LEVELS:
+            os.makedirs(os.path.join(self.location, lvl), exist_ok=True)
+        if not os.path.exists(self._attributes_loc()):
+            self._write_attributes(pd.DataFrame({"value": [], "type": [], "description": []}))
+            self.store("location", self.location, "value", "Location of SNVprofile object")
+            self.store("version", MIRRORED_VERSION, "value", "Version of inStrain")
+            with open(self._fileloc("_README.txt"), "w") as o:
+                o.write(_README)
+        elif self.get("location") != self.location:
+            self.store("location", self.location, "value", "Location of SNVprofile object")
+
+    # ---- the reference's public pair -------------------------------------------------------------------------------
+    def store(self, name, value, type, description):                      # noqa: A002 - the reference's argument name
+        if type == "value":
+            stored = value
+        else:
+            if type not in _EXT:
+                logging.error("I dont know how to save a {0} type, so Im just going to pickle it".format(type))
+                type = "pickle"
+            if type == "special" and name not in _HD5_NAMES:
+                logging.error("I dont know how to store {0}! Ill just pickle it".format(name))
+                stored = self._fileloc(name) + ".pickle"
+                self._save("pickle", value, stored)
+            else:
+                stored = self._fileloc(name) + _EXT[type]
+                self._save(type, value, stored)
+        Adb = self._read_attributes()
+        if name in Adb.index:
+            for thing, new in (("type", type), ("description", description)):
+                if Adb.loc[name, thing] != new:
+                    logging.error("WILL NOT OVERWRITE {0}; {1} arent the same ({2} vs {3}))".format(
+                        name, thing, Adb.loc[name, thing], new))
+                    return
+            Adb.at[name, "value"] = stored
+        else:
+            Adb = pd.concat([Adb, pd.DataFrame({"value": stored, "type": type, "description": description}, index=[name])])
+        self._write_attributes(Adb)
+
+    def get(self, name, **kwargs):
+        Adb = self._read_attributes()
+        if name not in Adb.index:
+            return None
+        typ = Adb.loc[name, "type"]
+        if typ == "value":
+            return Adb.loc[name, "value"]
+        filename = os.path.join(self.location, "raw_data", os.path.basename(str(Adb.loc[name, "value"])))
+        if typ == "dictionary":
+            with open(filename) as fp:
+                return json.load(fp)
+        if typ == "list":
+            with open(filename) as f:
+                return [line.strip() for line in f]
+        if typ == "numpy":
+            return np.load(filename, allow_pickle=True)["arr_0"]
+        if typ == "pandas":
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return pd.read_csv(filename, index_col=0)
+        if typ == "special" and filename.endswith(".hd5"):
+            return hd5.load_special(filename, scaffolds=kwargs.get("scaffolds", ()))
+        if typ in ("pickle", "special"):
+            with open(filename, "rb") as f:
+                return pickle.load(f)
+        logging.error("I dont know how to load a {0} type!".format(typ))
+        return None
+
+    def get_location(self, name):
+        if name in FIRST_LEVELS:
+            return os.path.join(self.location, name)
+        raise KeyError(name)
+
+    def __str__(self):
+        return str(self._read_attributes())
+
+    # ---- storage back ends --------------------------------------------------------------------------------------------
+    def _save(self, typ, value, loc):
+        if typ == "dictionary":
+            assert isinstance(value, dict)
+            with open(loc, "w") as fp:
+                json.dump(value, fp, default=_json_default)
+        elif typ == "list":
+            assert isinstance(value, list)
+            with open(loc, "w") as f:
+                for s in value:
+                    f.write(str(s) + "\n")
+        elif typ == "numpy":
+            np.savez_compressed(loc, value)
+        elif typ == "pandas":
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                value.to_csv(loc)
+        elif typ == "special":
+            hd5.store_special(loc, value)
+        else:
+            with open(loc, "wb") as f:
+                pickle.dump(value, f, pickle.HIGHEST_PROTOCOL)
+
+    def _fileloc(self, name):
+        return os.path.join(self.location, "raw_data/{0}".format(name))
+
+    def _attributes_loc(self):
+        return os.path.join(self.location, "raw_data/attributes.tsv")
+
+    def _read_attributes(self):
+        return pd.read_csv(self._attributes_loc(), sep="\t", index_col="name")
+
+    def _write_attributes(self, Adb):
+        Adb.to_csv(self._attributes_loc(), sep="\t", index_label="name")
+
+
+def store_profile(ISP_loc, bam, res):
+    """What gen_snv_profile stores for a profile run (profile_utilities.py:670-706), from a ProfileResult."""
+    S = SNVprofileStore(ISP_loc)
+    S.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
+    S.store("bam_loc", bam, "value", "Location of .bam file")
+    S.store("scaffold_list", list(res.scaffold_list), "list", "1d list of scaffolds that were profiled")
+    S.store("raw_linkage_table", res.raw_linkage_table, "pandas", "Raw table of linkage information")
+    S.store("raw_snp_table", res.cumulative_snv_table, "pandas", "Contains raw SNP information on a mm level")
+    S.store("cumulative_scaffold_table", res.cumulative_scaffold_table, "pandas",
+            "Cumulative coverage on mm level. Formerly scaffoldTable.csv")
+    S.store("cumulative_snv_table", res.cumulative_snv_table, "pandas", "Cumulative SNP on mm level. Formerly snpLocations.pickle")
+    S.store("scaffold_2_mm_2_read_2_snvs", {}, "pickle", "crazy nonsense needed for linkage")
+    S.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
+    S.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
+    return S

@@ -43,6 +43,24 @@ def snv_table(rows, scaffold_names, scaffold_off, seqs):
         "cryptic": rows["cryptic"].astype(bool), "position_coverage": cnt.sum(1)}, columns=SNV_COLUMNS)
 
 
+def cumulative_snv_table(raw):
+    """raw_snp_table -> cumulative_snv_table: _parse_Sdb (profile_utilities.py:600-616) adds var_freq / con_freq / ref_freq
+    = count of that base / position_coverage (ref_freq NaN when the reference base is not A/C/T/G).  The reference applies
+    it in place, so its stored raw_snp_table carries the same three columns."""
+    out = raw.copy()
+    if len(out) == 0:
+        return out
+    cnt = out[["A", "C", "T", "G"]].values.astype(np.float64)
+    cov = out["position_coverage"].values.astype(np.float64)
+    lut = {b: i for i, b in enumerate("ACTG")}
+    rows = np.arange(len(out))
+    for col, src in (("var_freq", "var_base"), ("con_freq", "con_base"), ("ref_freq", "ref_base")):
+        idx = np.array([lut.get(b, -1) for b in out[src]], dtype=np.int64)
+        val = cnt[rows, np.maximum(idx, 0)] / cov
+        out[col] = np.where(idx >= 0, val, np.nan)
+    return out
+
+
 def linkage_table(rows, scaffold_names, scaffold_off):
     rows = rows[np.lexsort((rows["mm"], rows["pos_b"], rows["pos_a"]))]
     names = np.asarray(scaffold_names, dtype=object)
@@ -58,13 +76,25 @@ def linkage_table(rows, scaffold_names, scaffold_off):
         "mm": rows["mm"].astype(np.int64), "scaffold": names[sidx]}, columns=LD_COLUMNS)
 
 
-def basewise(dense, kind):
+def present_levels(covT, nmask):
+    """mm levels that are keys of a scaffold's covT / clonT dicts in the reference: every level that is a key of some
+    column's MMcounts (update_covT profile_utilities.py:288-295 and update_snp_table snv_utilities.py:87-96 create
+    covT[mm] / clonT[mm] on first sight of mm) -- a level with coverage somewhere, or one made present only by a
+    non-ACGT read base (the defaultdict side effect, profile_utilities.py:280-281 -> nmask)."""
+    M = covT.shape[1]
+    bits = int(np.bitwise_or.reduce(nmask)) if len(nmask) else 0
+    return [mm for mm in range(M) if (bits >> mm) & 1 or (covT[:, mm] > 0).any()]
+
+
+def basewise(dense, kind, levels=None):
     """Dense [L, M] array of one scaffold -> {mm: pd.Series} like shrink_basewise: coverage keeps values > 0 (int32),
-    clonality drops NaN (float32).  A level appears iff it has at least one retained position."""
+    clonality drops NaN (float32).  `levels` = the dict keys (present_levels); a present level with no retained position
+    is an EMPTY Series, as in the reference's stored covT / clonT (e.g. clonT of a level that never reaches min_cov).
+    Without `levels`, a level appears iff it has at least one retained position."""
     out = {}
-    for mm in range(dense.shape[1]):
+    for mm in (range(dense.shape[1]) if levels is None else levels):
         col = dense[:, mm]
         keep = np.nonzero(col > 0)[0] if kind == "coverage" else np.nonzero(~np.isnan(col) & (col > 0))[0]
-        if len(keep):
+        if len(keep) or levels is not None:
             out[mm] = pd.Series(col[keep].astype("int32" if kind == "coverage" else "float32"), index=keep)
     return out

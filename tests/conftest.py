@@ -55,3 +55,37 @@ def assert_ld_equal(a, b, tol=1e-6):
     for f in ("r2", "d_prime"):
         assert np.array_equal(np.isnan(a[f]), np.isnan(b[f])), f
         assert np.allclose(a[f], b[f], rtol=0, atol=tol, equal_nan=True), f
+
+
+def basewise_digest(values, index):
+    """sha1 over the 2 x N array the reference stores for one (scaffold, mm) dataset of covT / clonT
+    (`np.array([series.values, series.index])`, SNVprofile.py:717-733): int64 for coverage, float64 for clonality."""
+    import hashlib
+    values = np.asarray(values)
+    dt = "<f8" if values.dtype.kind == "f" else "<i8"
+    return np.frombuffer(hashlib.sha1(values.astype(dt).tobytes() + np.asarray(index).astype(dt).tobytes()).digest(), np.uint8)
+
+
+def assert_basewise_matches_digest(which, names, offs, lens, covT, clonT, nmask):
+    """Dense covT / clonT / nmask of the C1 batch -> per-scaffold {mm: Series} (instrain_b200.tables) -> compared with the
+    digests of the reference's OWN stored covT.hd5 / clonT.hd5 (tests/golden/c1_<set>_hd5_digest.npz): same dataset
+    names (levels, empty ones included), same lengths, same values and positions bit for bit."""
+    from instrain_b200 import tables
+    z = np.load(os.path.join(GOLDEN, "c1_%s_hd5_digest.npz" % which))
+    gold = {k: (int(n1), bytes(d1), int(n2), bytes(d2)) for k, n1, d1, n2, d2 in
+            zip(z["names"], z["cov_n"], z["cov_sha"], z["clon_n"], z["clon_sha"])}
+    seen = set()
+    for name, off, L in zip(names, offs, lens):
+        sl = slice(int(off), int(off) + int(L))
+        lv = tables.present_levels(covT[sl], nmask[sl])
+        cov = tables.basewise(covT[sl], "coverage", lv)
+        clon = tables.basewise(clonT[sl], "clonality", lv)
+        for mm in lv:
+            key = "%s::%d" % (name, mm)
+            assert key in gold, "level not in the reference's store: " + key
+            seen.add(key)
+            n1, d1, n2, d2 = gold[key]
+            assert len(cov[mm]) == n1 and bytes(basewise_digest(cov[mm].values, cov[mm].index.values)) == d1, "covT " + key
+            assert len(clon[mm]) == n2 and bytes(basewise_digest(clon[mm].values, clon[mm].index.values)) == d2, "clonT " + key
+    assert seen == set(gold), sorted(set(gold) - seen)[:5]
+    return len(seen)

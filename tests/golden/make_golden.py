@@ -145,10 +145,35 @@ def make_small_scaffold():
     print("small scaffold:", name, len(seqs[name]), "bp,", len(r2m), "pairs,", len(snp), "snv rows,", len(ld), "ld rows")
 
 
+def make_hd5_digests(which):
+    """c1_<set>_hd5_digest.npz: per dataset of the reference's stored covT.hd5 / clonT.hd5 (read with the repo's own HDF5
+    reader, instrain_b200/hd5.py -- h5py is not installable here) its length and a sha1 of the 2 x N array.  Pins the
+    basewise coverage / clonality of the hot path at every position and the set of mm levels per scaffold."""
+    from instrain_b200 import hd5
+    sys.path.insert(0, os.path.dirname(HERE))
+    from conftest import basewise_digest
+    raw = load_set(which)[4]
+    cov = hd5.read_hd5(os.path.join(raw, "covT.hd5"))
+    clon = hd5.read_hd5(os.path.join(raw, "clonT.hd5"))
+    assert set(cov) == set(clon)
+    names = sorted(cov)
+    np.savez_compressed(
+        os.path.join(HERE, "c1_%s_hd5_digest.npz" % which), names=np.array(names),
+        cov_n=np.array([cov[k].shape[1] for k in names], np.int32),
+        cov_sha=np.stack([basewise_digest(cov[k][0], cov[k][1]) for k in names]),
+        clon_n=np.array([clon[k].shape[1] for k in names], np.int32),
+        clon_sha=np.stack([basewise_digest(clon[k][0], clon[k][1]) for k in names]))
+    print(which, "hd5 digests:", len(names), "datasets,", sum(clon[k].shape[1] == 0 for k in names), "empty clonT levels")
+
+
 TD_DIR = os.path.join(ref_harness.REFERENCE_ROOT, "test", "test_data")
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["hd5"]:                   # only the covT / clonT digests (fast)
+        for which in ("G1", "G2"):
+            make_hd5_digests(which)
+        sys.exit(0)
     make_small_scaffold()
     make_subset_bam("G1")
     model = ref_harness.null_model(1e-6)
@@ -158,5 +183,6 @@ if __name__ == "__main__":
         batch, exp = make_batch(which)
         np.savez_compressed(os.path.join(HERE, "c1_%s_batch.npz" % which), **batch)
         np.savez_compressed(os.path.join(HERE, "c1_%s_expected.npz" % which), **exp)
+        make_hd5_digests(which)
         print(which, "events", len(batch["ref_pos"]), "pairs", len(batch["pair_mm"]), "L", len(batch["ref_codes"]),
               "snv rows", len(exp["snv_pos"]), "ld rows", len(exp["ld_pos_a"]))

@@ -7,7 +7,7 @@ Bar (BASELINE.json north_star): per-position counts and SNV calls bit-exact; r2 
 import numpy as np
 import pytest
 
-from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from conftest import assert_basewise_matches_digest, assert_ld_equal, assert_snv_equal, load_batch
 from oracle import restate, synth
 
 pytestmark = pytest.mark.gpu
@@ -57,6 +57,10 @@ def test_golden_tables_through_cabi(eng, which, null_lut):
     # test_profile_13 (reference test/tests/test_profile.py:726-750)
     cov_cum = np.cumsum(got["covT"], axis=1)
     assert np.array_equal(cov_cum[got["snv"]["pos"], got["snv"]["mm"]], got["snv"]["cnt"].sum(1))
+    # the reference's stored covT.hd5 / clonT.hd5 (digests): every position, every mm level, empty levels included
+    n = assert_basewise_matches_digest(which, batch["scaffold_names"], batch["scaffold_off"], batch["scaffold_len"],
+                                       got["covT"], got["clonT"], got["nmask"])
+    assert n == {"G1": 1267, "G2": 1429}[which]
 
 
 # ---- stage entry points ----------------------------------------------------------------------------------------------

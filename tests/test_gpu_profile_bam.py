@@ -32,11 +32,12 @@ def golden_tables(names):
     return snv[snv["scaffold"].isin(names)], ld[ld["scaffold"].isin(names)]
 
 
-def test_profile_bam_matches_reference_goldens():
+def test_profile_bam_matches_reference_goldens(tmp_path):
     from instrain_b200.profile import profile_bam
     rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
     seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
-    res = profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, rdic, "unused.IS", s2s=seqs,
+    isp = str(tmp_path / "subset.IS")
+    res = profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, rdic, isp, s2s=seqs,
                       min_cov=5, min_freq=0.05, min_snp=20, window_length=10000)
     assert sorted(res.scaffold_list) == sorted(rdic)
     g_snv, g_ld = golden_tables(set(rdic))
@@ -66,15 +67,37 @@ def test_profile_bam_matches_reference_goldens():
             tot = sum(int(sp.covT[m].get(pos, 0)) for m in sp.covT if m <= mm)
             assert tot == cov
         break
+    # the SNVprofile directory profile_bam left at ISP_loc: tables and covT / clonT read back equal the in-memory result,
+    # and the covT / clonT datasets equal the reference's stored ones for these scaffolds (digests of its .hd5 files)
+    from conftest import basewise_digest
+    from instrain_b200.store import SNVprofileStore
+    S = SNVprofileStore(isp)
+    assert S.get("object_type") == "profile" and S.get("scaffold_list") == res.scaffold_list
+    back = S.get("raw_snp_table")
+    assert len(back) == len(res.raw_snp_table) and list(back.columns[-3:]) == ["var_freq", "con_freq", "ref_freq"]
+    assert len(S.get("raw_linkage_table")) == len(res.raw_linkage_table)
+    assert len(S.get("cumulative_scaffold_table")) == len(res.cumulative_scaffold_table)
+    z = np.load(os.path.join(GOLDEN, "c1_G1_hd5_digest.npz"))
+    gold = {str(k): (bytes(a), bytes(b)) for k, a, b in zip(z["names"], z["cov_sha"], z["clon_sha"])}
+    covT, clonT = S.get("covT"), S.get("clonT")
+    n = 0
+    for s in rdic:
+        want = {int(k.rsplit("::", 1)[1]) for k in gold if k.rsplit("::", 1)[0] == s}
+        assert set(covT[s]) == set(clonT[s]) == want, s
+        for mm in want:
+            assert bytes(basewise_digest(covT[s][mm].values, covT[s][mm].index.values)) == gold["%s::%d" % (s, mm)][0]
+            assert bytes(basewise_digest(clonT[s][mm].values, clonT[s][mm].index.values)) == gold["%s::%d" % (s, mm)][1]
+            n += 1
+    assert n > 50
 
 
-def test_profile_bam_tiny_scaffold_vs_reference_functions():
+def test_profile_bam_tiny_scaffold_vs_reference_functions(tmp_path):
     """The reference's test_profile_18 input (one 126 bp scaffold).  Expected tables were produced by the reference's OWN
     process_bam_sites / calculate_ld (oracle/ref_harness.py) on the emulated pileup -- tests/golden/make_golden.py."""
     from instrain_b200.profile import profile_bam
     fx = json.load(open(os.path.join(GOLDEN, "small_scaffold.json")))
     name = fx["scaffold"]
-    res = profile_bam(os.path.join(GOLDEN, "small_scaffold.bam"), None, {name: fx["r2m"]}, "unused.IS",
+    res = profile_bam(os.path.join(GOLDEN, "small_scaffold.bam"), None, {name: fx["r2m"]}, str(tmp_path / "tiny.IS"),
                       s2s={name: fx["seq"]}, min_cov=5, min_freq=0.05, min_snp=20)
     assert res.scaffold_list == [name] and not res.failures
     exp = pd.DataFrame(fx["snp"]).sort_values(["position", "mm"]).reset_index(drop=True)

@@ -1,0 +1,117 @@
+"""the covT / clonT HDF5 stores (instrain_b200/hd5.py) -- CPU tests.
+
+  * the oracle's basewise coverage / clonality equal the reference's OWN stored covT.hd5 / clonT.hd5 (committed digests,
+    tests/golden/c1_<set>_hd5_digest.npz, made by tests/golden/make_golden.py with the repo's HDF5 reader);
+  * the reader parses the reference's stored files (libhdf5 output) when /root/reference is there;
+  * writer -> reader round trips: dtypes, empty datasets, edge chunks, group B-trees of 1 .. 3 levels, and the
+    SNVprofile-style store_special / load_special pair (SNVprofile.py:717-786).
+"""
+import os
+import struct
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, assert_basewise_matches_digest, basewise_digest, load_batch, load_lut
+from instrain_b200 import hd5
+from oracle import restate
+
+REF_RAW = "/root/reference/test/test_data/N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010%s.forRC.IS/raw_data"
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_oracle_basewise_equals_reference_store(which):
+    lut, dflt = load_lut()
+    b, _ = load_batch(which)
+    exp = restate.profile_events(b, b["ref_codes"], lut, dflt, b["splits"], do_linkage=False)
+    n = assert_basewise_matches_digest(which, b["scaffold_names"], b["scaffold_off"], b["scaffold_len"],
+                                       exp["covT"], exp["clonT"], exp["nmask"])
+    assert n == {"G1": 1267, "G2": 1429}[which]
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+@pytest.mark.parametrize("name", ["covT", "clonT"])
+def test_reader_on_reference_files(which, name):
+    path = os.path.join(REF_RAW % which, name + ".hd5")
+    if not os.path.exists(path):
+        pytest.skip("reference test data not present on this machine")
+    ds = hd5.read_hd5(path)
+    z = np.load(os.path.join(GOLDEN, "c1_%s_hd5_digest.npz" % which))
+    assert sorted(ds) == list(z["names"])
+    pre = "cov" if name == "covT" else "clon"
+    for k, n, sha in zip(z["names"], z[pre + "_n"], z[pre + "_sha"]):
+        a = ds[str(k)]
+        assert a.shape == (2, n) and a.dtype == (np.int64 if name == "covT" else np.float64)
+        assert bytes(basewise_digest(a[0], a[1])) == bytes(sha), k
+
+
+def _random_sets(rng, n_sets, max_n):
+    out = {}
+    for i in range(n_sets):
+        n = int(rng.integers(0, max_n)) if i % 7 else 0
+        idx = np.sort(rng.choice(max(4 * n, 1), n, replace=False))
+        if i % 2:
+            out["scaffold_%d::%d" % (i // 3, i % 3)] = np.array([rng.integers(1, 500, n), idx])
+        else:
+            out["scaffold_%d::%d" % (i // 3, i % 3)] = np.array([rng.random(n).astype(np.float32), idx])
+    return out
+
+
+@pytest.mark.parametrize("n_sets,max_n", [(1, 50), (9, 3000), (300, 400), (9000, 6)])
+def test_write_read_round_trip(tmp_path, n_sets, max_n):
+    rng = np.random.default_rng(n_sets)
+    ds = _random_sets(rng, n_sets, max_n)
+    path = str(tmp_path / "t.hd5")
+    size = hd5.write_hd5(path, ds)
+    assert size == os.path.getsize(path)
+    back = hd5.read_hd5(path)
+    assert set(back) == set(ds)
+    for k, a in ds.items():
+        assert back[k].shape == a.shape, k
+        assert back[k].dtype == (np.float64 if a.dtype.kind == "f" else np.int64)
+        assert np.array_equal(back[k], a), k
+    # the file is self-consistent the way libhdf5 checks it on open: signature, end-of-file address, root symbol table
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and struct.unpack_from("<Q", raw, 40)[0] == len(raw)
+    btree, heap = struct.unpack_from("<QQ", raw, 80)
+    assert raw[btree:btree + 4] == b"TREE" and raw[heap:heap + 4] == b"HEAP"
+
+
+def test_large_dataset_chunks(tmp_path):
+    """A 1 Mb scaffold's worth of positions: 64 chunks of 1 x 31250, the last ones partial."""
+    n = 1_000_003
+    a = np.array([np.arange(n) % 97 + 1, np.arange(n)])
+    path = str(tmp_path / "big.hd5")
+    hd5.write_hd5(path, {"s::0": a})
+    assert np.array_equal(hd5.read_hd5(path)["s::0"], a)
+
+
+def test_store_special_round_trip(tmp_path):
+    """scaffold -> mm -> Series, as SNVprofile.store(..., 'special') receives it."""
+    rng = np.random.default_rng(5)
+    obj = {}
+    for s in ("scaffA", "scaffB|with odd:chars", "c"):
+        obj[s] = {}
+        for mm in (0, 2, 11):
+            n = int(rng.integers(0, 200))
+            idx = np.sort(rng.choice(1000, n, replace=False))
+            obj[s][mm] = pd.Series(rng.integers(1, 90, n).astype("int32"), index=idx)
+    path = str(tmp_path / "covT.hd5")
+    hd5.store_special(path, obj)
+    back = hd5.load_special(path)
+    assert set(back) == set(obj)
+    for s in obj:
+        assert set(back[s]) == set(obj[s])
+        for mm in obj[s]:
+            assert np.array_equal(back[s][mm].values, obj[s][mm].values)
+            assert np.array_equal(back[s][mm].index.values, obj[s][mm].index.values)
+    only = hd5.load_special(path, scaffolds=["c"])
+    assert list(only) == ["c"]
+
+
+def test_reader_rejects_foreign_files(tmp_path):
+    p = tmp_path / "x.hd5"
+    p.write_bytes(b"not an hdf5 file at all" * 10)
+    with pytest.raises(ValueError):
+        hd5.read_hd5(str(p))
