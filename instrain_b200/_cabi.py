@@ -107,10 +107,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("ISB_LIB_PATH", LIB_PATH)     # A/B builds of the same sources (tools/gpu_ab.sh)
+    if not os.path.exists(path):
         raise ImportError("libinstrain_b200.so is not built (%s). Run `python -m instrain_b200.build` (needs nvcc); "
-                          "instrain_b200 has no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                          "instrain_b200 has no CPU fallback." % path)
+    L = C.CDLL(path)
     vp, i32, i64, u32, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double
     L.isb_create.restype = vp
     L.isb_create.argtypes = [C.c_int, vp, C.c_int, C.c_int]

@@ -111,7 +111,9 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
                   int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap);
 // read-major batch, device pointers (+ the per-tile segment bounds isb_k1r_launch computes)
+#ifndef K1R_TILE
 #define K1R_TILE 1024                 // positions per K1r block; also the granularity of the K3 candidate search
+#endif
 struct isb_reads_dev {
     int64_t n_segs;
     const int32_t *seg_start;

@@ -26,7 +26,7 @@
 #include "isb_common.cuh"
 #include <climits>
 
-#define K1R_THREADS 128
+#define K1R_THREADS (K1R_TILE / 8)     // one thread per 8 positions (one word of nibbles)
 #define K1R_MAXLEN 256                 // hard cap of max_seg_len
 #define K1R_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
 #define K1R_WPS (K1R_MAXLEN / 8 + 1)   // worst-case words per segment incl. its separator
