@@ -8,8 +8,10 @@ Workload (BASELINE.json configs[2] / north_star): synthetic metagenome, `--scaff
 1 % SNV density, min_cov 5, min_freq 0.05, min_snp 20, window_length 10000, --skip_mm_profiling (M = 1) unless --mm.
 Defaults: 100 x 1 Mb x 100x = the full 100 Mb configuration (1e10 aligned bases); it is generated on the device
 (instrain_b200/synth.py) because it cannot be produced on, or shipped from, the host in bench time.
---layout reads (default): the data set is resident as READ-MAJOR aligned segments (4-bit code per aligned base, ~5.6 GB);
-a "step" = isb_profile_reads (K1r pileup from segments -> K2 SNV -> K3 linkage) over the whole resident data set.
+--layout cols (default): the data set is resident as COLUMN WORDS (include/instrain_b200.h, isb_cols_batch: the one-hot
+nibble words of the reads regrouped per 8-position column, 4 bits per aligned base + a 4-byte pair id per word, ~11 GB);
+a "step" = isb_profile_cols (K1c streaming pileup with the SNV call fused into its epilogue -> K3 linkage).
+--layout reads: READ-MAJOR aligned segments (~5.6 GB); step = isb_profile_reads (K1r transposing pileup -> K2 -> K3).
 --layout events: the same fragments as position-major event columns (10 B per event, 100 GB), step = isb_profile_batch
 (K1 -> K2 -> K3).  Either way the inputs are far larger than the 126 MB L2, so no L2 flush is needed between steps.
 With --layout reads a short secondary run of the event layout on --also-events scaffolds is reported beside.
@@ -50,8 +52,10 @@ def parse():
     ap.add_argument("--e2e-scaffolds", type=int, default=4, help="scaffolds in the bounded host-buffer (e2e) slice")
     ap.add_argument("--cpu-scaffolds", type=int, default=1, help="scaffolds in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--layout", default="reads", choices=["reads", "events"],
-                    help="resident input layout: read-major aligned segments (default) or position-major event columns")
+    ap.add_argument("--layout", default="cols", choices=["cols", "reads", "events"],
+                    help="resident input layout: column words (default), read-major aligned segments or position-major event columns")
+    ap.add_argument("--keep-counts", action="store_true",
+                    help="ask for the full counts / nmask arrays (column words at M = 1: disables the fused pileup + SNV kernel)")
     ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (21 or 22)")
     ap.add_argument("--also-events", type=int, default=10,
                     help="with --layout reads: also time the position-major path on this many scaffolds (0 = skip)")
@@ -150,10 +154,11 @@ def main():
     config = {"workload": workload, "scaffolds_per_gpu": args.scaffolds, "scaffold_len": args.L, "coverage": args.cov,
               "snv_density": args.dens, "min_cov": 5, "min_freq": 0.05, "min_snp": 20, "window_length": 10000,
               "sharding": "scaffolds per rank (weak), NCCL gather of SNV/linkage rows to rank 0" if world > 1 else "single GPU",
-              "layout": "read-major aligned segments (4-bit code per aligned base)" if args.layout == "reads"
-                        else "position-major event columns (10 B per event)",
+              "layout": {"cols": "column words (4-bit one-hot code per aligned base, regrouped per 8-position column; pair id per word for linkage)",
+                         "reads": "read-major aligned segments (4-bit code per aligned base)",
+                         "events": "position-major event columns (10 B per event)"}[args.layout],
               "l2": "inputs (%.1f GB) larger than L2; no flush needed" % (
-                  args.scaffolds * args.L * args.cov * (0.56 if args.layout == "reads" else 10) / 1e9)}
+                  args.scaffolds * args.L * args.cov * {"cols": 1.07, "reads": 0.56, "events": 10}[args.layout] / 1e9)}
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -183,15 +188,25 @@ def main():
 
     # ------------------------------------------------------------------------------------------------ B200 arm
     from instrain_b200.engine import Engine
+    use_cols = args.layout == "cols"
     use_reads = args.layout == "reads"
     t_gen = time.time()
     d = synth.generate(local_rank, args.L, args.scaffolds, args.cov, args.dens, SEED + rank, skip_mm=not args.mm,
-                       events=not use_reads, reads=use_reads, seg_words=args.seg_words)
+                       events=args.layout == "events", reads=use_reads or use_cols, seg_words=args.seg_words)
     torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
     n, npairs, Ltot = int(d["n_events"]), d["pair_mm"].numel(), args.L * args.scaffolds
     M = int(d["pair_mm"].max().item()) + 1 if npairs else 1
     eng = Engine(local_rank, lut, dflt)
+    cd = None
+    if use_cols:                                     # lay the generated reads out as column words, drop the read-major copy
+        cd = synth.reads_to_cols_device(eng, d)
+        cd["n_real_words"] = int((cd["ids"] >= 0).sum().item())
+        cd["n_segs"] = int(d["reads"]["n_segs"])
+        del d["reads"]
+        eng.close()
+        eng = Engine(local_rank, lut, dflt)          # releases the conversion's staging buffers
+        torch.cuda.empty_cache()
+    t_gen = time.time() - t_gen
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     lib, ctx, p = eng.lib, eng.ctx, _cabi.ptr
@@ -208,7 +223,9 @@ def main():
         nonlocal snv, ld, res
         snv = torch.empty(snv_cap * 32, dtype=torch.uint8, device=dev)
         ld = torch.empty(ld_cap * 48, dtype=torch.uint8, device=dev)
-        res = _cabi.IsbResult(p(counts), p(nmask), p(covT), p(clonT), p(flags), p(snv), snv_cap, p(ld), ld_cap, 0, 0, 0, 0)
+        lean = use_cols and not args.keep_counts         # counts / nmask not requested: K1c runs the SNV call in its epilogue at M = 1
+        res = _cabi.IsbResult(None if lean else p(counts), None if lean else p(nmask), p(covT), p(clonT), p(flags), p(snv), snv_cap,
+                              p(ld), ld_cap, 0, 0, 0, 0)
 
     snv = ld = None
     alloc_rows()
@@ -219,7 +236,11 @@ def main():
                                    len(rd["nev_pos"]), p(rd["nev_pos"]), p(rd["nev_pair"]), n_pairs, p(pair_mm), 0, L_,
                                    p(ref), len(splits), p(splits), M_, 0)
 
-    if use_reads:
+    if use_cols:
+        batch = _cabi.IsbColsBatch(cd["n_groups"], p(cd["grp_off"]), cd["n_chunks"], p(cd["words"]), p(cd["ids"]), 0, None, None,
+                                   npairs, p(d["pair_mm"]), 0, Ltot, p(d["ref_codes"]), len(d["splits"]), p(d["splits"]), M, 0)
+        entry = lib.isb_profile_cols
+    elif use_reads:
         batch = reads_struct(d["reads"], npairs, d["pair_mm"], Ltot, d["ref_codes"], d["splits"], M)
         entry = lib.isb_profile_reads
     else:
@@ -307,7 +328,29 @@ def main():
                 "achieved_survey_def": (n_ * 10 + 16 * M_ * Ltot_) / k1_ms_ / 1e6, "launch_ms": k1_ms_}
 
     k1_ms = stage_ms[0] / max(1, stage_calls[0])
-    if use_reads:
+    if use_cols:
+        fused = M == 1 and not args.keep_counts
+        # algorithmic bytes of K1c: the real (non-padding) nibble words (+ their pair ids when M > 1) + the group offsets in;
+        # fused M = 1: ref in, covT + clonT + site_flags out (+ 32 B per SNV row, 16 B of counts per linkage site);
+        # otherwise counts + nmask out
+        in_bytes = cd["n_real_words"] * (4 if M == 1 else 8) + (cd["n_groups"] + 1) * 8
+        out_bytes = (Ltot * (1 + 4 + 4 + 1) + int(res.n_snv) * 32 + int(res.n_sites) * 16) if fused else (16 * M * Ltot + 8 * Ltot)
+        alg_bytes = in_bytes + out_bytes
+        key = "K1c_fused_M1" if fused else ("K1c_M1" if M == 1 else "K1c_Mgt1")
+        roofline = {"kernel": "k1c_pileup_m1<fused SNV call>" if fused else ("k1c_pileup_m1" if M == 1 else "k1c_pileup_mm"),
+                    "bound": "hbm", "achieved": alg_bytes / k1_ms / 1e6, "peak": peak, "unit": "GB/s",
+                    "frac": alg_bytes / k1_ms / 1e6 / peak, "traffic": traffic_of(key, Ltot), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "bytes_def": ("4 bits per aligned base (one 32-bit word per read and 8-position column, padding words not counted)%s"
+                                  " + 8 B per 64 positions of offsets in; %s out") % (
+                                      " + 4 B pair id per word" if M > 1 else "",
+                                      "ref 1 B in, covT 4 + clonT 4 + site_flags 1 B per position, 32 B per SNV row, 16 B counts per linkage site"
+                                      if fused else "16*M B/position counts + 8 B/position nmask"),
+                    "padding_words_frac": cd["n_chunks"] * 32 / max(1, cd["n_real_words"]) - 1,
+                    "launch_ms": k1_ms,
+                    "note": ("the stage is ONE kernel: pileup counts + the per-site SNV call (K2) in its epilogue" if fused else
+                             "pileup counts only; K2 runs as its own kernel")}
+    elif use_reads:
         rd = d["reads"]
         # algorithmic bytes of K1r: the nibble stream + the segment table (start i32, len u16, word offset i64, + pair
         # id i32 when M > 1) in, counts (+ nmask) out
@@ -329,7 +372,7 @@ def main():
 
     # position-major path on a subset, for comparison (the HBM-bound K1 kernel on 10 B/event columns)
     pos_major = None
-    if use_reads and rank == 0 and args.also_events > 0:
+    if (use_reads or use_cols) and rank == 0 and args.also_events > 0:
         n_sc = min(args.also_events, args.scaffolds)
         de = synth.generate(local_rank, args.L, n_sc, args.cov, args.dens, SEED + rank, skip_mm=not args.mm)
         Le = n_sc * args.L
@@ -421,7 +464,8 @@ def main():
         dt_pk = time_call(lib.isb_profile_batch_packed, pbatch)
         dt_rd = time_call(lib.isb_profile_reads, rbatch)
         dt_rc = time_call(lib.isb_profile_reads_compact, cbatch)
-        main_fn, main_b, dt = (lib.isb_profile_reads_compact, cbatch, dt_rc) if use_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
+        via_reads = use_reads or use_cols             # host buffers cross PCIe in the compact read-major format either way
+        main_fn, main_b, dt = (lib.isb_profile_reads_compact, cbatch, dt_rc) if via_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
 
         # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
         # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
@@ -459,10 +503,10 @@ def main():
         h2d_rc = hc["n_units"] * 3 + hr["n_segs"] * (4 + 2 + 4) + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
         best = min(dt, dt_pipe) if dt_pipe else dt
-        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rc if use_reads else h2d_pk),
+        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rc if via_reads else h2d_pk),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": best * 1e3,
                "api": ("isb_profile_reads_compact (read-major aligned segments in the compact transfer format: 3 bits per "
-                       "aligned base, K0r expands on the device)" if use_reads else
+                       "aligned base, K0r expands on the device)" if via_reads else
                        "isb_profile_batch_packed (packed transfer format, K0 expands on the device)"),
                "single_context": {"value": Ls / dt, "ms_per_step": dt * 1e3},
                "two_contexts_pipelined": ({"value": Ls / dt_pipe, "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),

@@ -290,6 +290,67 @@ typedef struct {
 
 int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const isb_params *prm, isb_result *out);
 
+/* ---- COLUMN-WORD input: the pileup-major form of the aligned segments ------------------------------------------------- */
+/* The same one-hot nibble words as isb_reads_batch (one 32-bit word = the codes of 8 consecutive, 8-aligned batch
+ * coordinates of ONE read), stored where the pileup needs them instead of where the read is: per COLUMN WORD (8
+ * positions) the words of all reads covering it.  This is the transposition pysam's pileup engine performs column by
+ * column in the reference (profile_utilities.py:150-153, :275), done once by the packer at word granularity -- the
+ * north-star "columnar, position-major" layout with 4 bits per aligned base instead of 10 bytes.
+ *   - position p (relative to `start`, a multiple of 8) lies in column word c = p / 8, GROUP g = c / 8 (64 positions),
+ *     lane c % 8;
+ *   - group g owns chunks [grp_off[g], grp_off[g+1]); a chunk is 8 lanes x 4 words (128 bytes, one cache line).  Slot i
+ *     of column (g, lane) is word ((grp_off[g] + i / 4) * 8 + lane) * 4 + i % 4 of `words`, its read-pair id the same
+ *     element of `ids`.  Every column of a group is padded to the group's depth 4 * (grp_off[g+1] - grp_off[g]) with
+ *     word 0 / id -1 (8 neighbouring columns see almost the same reads: ~6 % padding at 100x, against ~12 % for groups
+ *     of 32);
+ *   - the words of a column keep the table order of their segments (BAM order);
+ *   - passing non-ACGT read bases go to nev_pos / nev_pair as in isb_reads_batch.
+ * K1c (isb_k1c_cols.cu) streams it: a warp takes 4 consecutive groups, lane = column word, every load instruction reads
+ * four whole 128-byte lines, bit-sliced counting, no shared memory, atomics or searches -- an HBM-bound kernel on 0.5 B
+ * per aligned base.  The linkage stage reads the entries of an SNV site as one nibble of each word of its column
+ * (addresses follow from the position). */
+#define ISB_COLS_LANES 8
+#define ISB_COLS_GROUP (8 * ISB_COLS_LANES)   /* positions per group */
+#define ISB_COLS_CHUNK (4 * ISB_COLS_LANES)   /* words per chunk */
+typedef struct {
+    int64_t n_groups;           /* ceil(L / ISB_COLS_GROUP) */
+    const int64_t *grp_off;     /* [n_groups + 1] chunk offsets, grp_off[0] = 0 */
+    int64_t n_chunks;           /* = grp_off[n_groups] */
+    const uint32_t *words;      /* [n_chunks * ISB_COLS_CHUNK], 16-byte aligned */
+    const int32_t *ids;         /* [n_chunks * ISB_COLS_CHUNK], 16-byte aligned; may be NULL for isb_pileup_cols at M == 1 */
+    int64_t n_nev;
+    const int32_t *nev_pos;
+    const int32_t *nev_pair;
+    int64_t n_pairs;
+    const uint8_t *pair_mm;     /* [n_pairs]; may be NULL when M == 1 */
+    int32_t start;
+    int32_t L;
+    const uint8_t *ref;         /* [L] (not needed by isb_pileup_cols) */
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+    int32_t pad;
+} isb_cols_batch;
+
+/* Layout conversion on the device: read-major batch -> column words.  grp_off[n_groups + 1] is always written and
+ * *n_chunks set; words / ids (room for cap_chunks chunks) are filled when given (NULL: sizing call).  ISB_ERR_CAPACITY
+ * when cap_chunks < *n_chunks.  Host or device pointers. */
+int isb_cols_from_reads(isb_ctx *ctx, const isb_reads_batch *in, int64_t *grp_off, int64_t *n_chunks, uint32_t *words,
+                        int32_t *ids, int64_t cap_chunks);
+/* The same conversion on the host (C++, no GPU; what the host packer runs after isb_pack_scaffold_reads).  Returns the
+ * number of chunks, or -1 when the segments violate the layout rules of isb_reads_batch; words / ids may be NULL
+ * (sizing call) and are not written when cap_chunks is too small. */
+int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, const int32_t *seg_pair,
+                                 const int64_t *seg_word, const uint32_t *words_in, int64_t n_words_in, int32_t start,
+                                 int32_t L, int64_t *grp_off, uint32_t *words, int32_t *ids, int64_t cap_chunks);
+/* stage K1c alone: counts[L][M][4] (+ nmask[L], may be NULL) from a column-word batch */
+int isb_pileup_cols(isb_ctx *ctx, const isb_cols_batch *in, int32_t *counts, uint64_t *nmask);
+/* K1c -> K2 -> K3 on a column-word batch; same results as isb_profile_reads / isb_profile_batch on the same reads.
+ * When M == 1 and the caller asks for neither counts nor nmask (isb_result.counts == isb_result.nmask == NULL), the SNV
+ * call runs in the epilogue of the pileup kernel (one pass: the counts of a position never leave the registers,
+ * except at linkage sites). */
+int isb_profile_cols(isb_ctx *ctx, const isb_cols_batch *in, const isb_params *prm, isb_result *out);
+
 /* ---- stage K4: merge-stage summary reductions (the row after the hot path) ----------------------------- */
 /* Numeric core of make_coverage_table (profile_utilities.py:425-506) with mm_counts_to_counts_shrunk (:508-532) and
  * get_basewise_clons (:534-546): per scaffold s (positions [scaffold_off[s], scaffold_off[s+1]) of covT / clonT) and mm

@@ -37,6 +37,7 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
            "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact",
+           "isb_cols_from_reads", "isb_cols_from_reads_host", "isb_pileup_cols", "isb_profile_cols",
            "isb_scaffold_summary", "isb_launch_count",
            "isb_enable_timing", "isb_stage_times", "isb_selftest_division",
            "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
@@ -79,6 +80,14 @@ class IsbReadsCompact(C.Structure):
                 ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
                 ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
                 ("M", C.c_int32), ("pad2", C.c_int32)]
+
+
+class IsbColsBatch(C.Structure):
+    _fields_ = [("n_groups", C.c_int64), ("grp_off", C.c_void_p), ("n_chunks", C.c_int64), ("words", C.c_void_p),
+                ("ids", C.c_void_p), ("n_nev", C.c_int64), ("nev_pos", C.c_void_p), ("nev_pair", C.c_void_p),
+                ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32), ("L", C.c_int32),
+                ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p), ("M", C.c_int32),
+                ("pad", C.c_int32)]
 
 
 class IsbParams(C.Structure):
@@ -151,6 +160,14 @@ def load():
     L.isb_profile_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     L.isb_profile_reads_compact.restype = C.c_int
     L.isb_profile_reads_compact.argtypes = [vp, C.POINTER(IsbReadsCompact), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    L.isb_cols_from_reads.restype = C.c_int
+    L.isb_cols_from_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), vp, C.POINTER(i64), vp, vp, i64]
+    L.isb_cols_from_reads_host.restype = i64
+    L.isb_cols_from_reads_host.argtypes = [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, i64]
+    L.isb_pileup_cols.restype = C.c_int
+    L.isb_pileup_cols.argtypes = [vp, C.POINTER(IsbColsBatch), vp, vp]
+    L.isb_profile_cols.restype = C.c_int
+    L.isb_profile_cols.argtypes = [vp, C.POINTER(IsbColsBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     _lib = L
     return L
 

@@ -44,5 +44,14 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A/B build of the same sources with extra -D defines -> lib/libisb_<name>.so (select it with ISB_LIB_PATH)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, "libisb_%s.so" % name)
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + sources() + ["-o", out, "-lz"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

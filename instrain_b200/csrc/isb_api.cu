@@ -370,7 +370,7 @@ int isb_scaffold_summary(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, co
 }
 
 // K1 -> K2 -> K3 on device-resident inputs; outputs staged / copied as requested by `out`.
-static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, int64_t n, const int32_t *d_pos, const uint8_t *d_base, const uint8_t *d_qual,
+static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int64_t n, const int32_t *d_pos, const uint8_t *d_base, const uint8_t *d_qual,
                           const int32_t *d_rid, int64_t n_pairs, const uint8_t *d_mm, int32_t start, int32_t L, int M,
                           const uint8_t *d_ref, int32_t n_splits, const int32_t *d_splits, const isb_params *prm,
                           isb_result *out)
@@ -395,7 +395,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, int64_t n, const int3
     // identical (linkage never crosses a split; rows are appended through the same atomic counters).
     std::vector<int32_t> hs;
     std::vector<int> cut;                                    // chunk c = splits [cut[c], cut[c+1])
-    const bool want_pipe = !rd && (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
+    const bool want_pipe = !rd && !cd && (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
     if (want_pipe) {
         hs.resize((size_t)n_splits * 2);
         ISB_CUDA(cudaMemcpyAsync(hs.data(), d_splits, sizeof(int32_t) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -461,19 +461,31 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, int64_t n, const int3
         pipe_sites = acc_sites;
         pipe_pairs = acc_pairs;
     } else {
+        // Column words at M = 1 when the caller wants neither counts nor nmask: the SNV call runs in K1c's epilogue (one
+        // pass; counts are written at flagged sites only, nmask exists only if the batch has N events).
+        static const int fuse_env = getenv("ISB_K1C_FUSE") ? atoi(getenv("ISB_K1C_FUSE")) : 1;
+        const bool fused = cd && M == 1 && !out->counts && !out->nmask && fuse_env != 0;
+        if (fused && cd->n_nev == 0) d_nmask = nullptr;
         int ts = isb_time_begin(ctx, 0);
-        if (rd) rc = isb_k1r_launch(ctx, rd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask);
+        if (cd) {
+            isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, fuse_env == 2 ? 1 : 0};
+            rc = isb_k1c_launch(ctx, cd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask, fused ? &fz : nullptr);
+        } else if (rd) rc = isb_k1r_launch(ctx, rd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask);
         else rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
                                 (unsigned long long *)d_nmask);
         if (rc) return rc;
         isb_time_end(ctx, ts);
-        ts = isb_time_begin(ctx, 1);
-        if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
-                                prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
-        isb_time_end(ctx, ts);
+        if (!fused) {
+            ts = isb_time_begin(ctx, 1);
+            if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
+                                    prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
+            isb_time_end(ctx, ts);
+        }
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
         ts = do_ld ? isb_time_begin(ctx, 2) : -1;
-        if (do_ld && rd) rc = isb_k3_launch_reads(ctx, rd, n_pairs, d_mm, start, L, M, d_counts, (const unsigned long long *)d_nmask,
+        if (do_ld && cd) rc = isb_k3_launch_cols(ctx, cd, n_pairs, d_mm, start, L, M, d_counts, (const unsigned long long *)d_nmask,
+                                                 d_flags, n_splits, d_splits, prm->min_snp, d_ld, ld_cap);
+        else if (do_ld && rd) rc = isb_k3_launch_reads(ctx, rd, n_pairs, d_mm, start, L, M, d_counts, (const unsigned long long *)d_nmask,
                                                   d_flags, n_splits, d_splits, prm->min_snp, d_ld, ld_cap);
         else if (do_ld) rc = isb_k3_launch(ctx, n, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, prm->min_qual,
                                            d_counts, (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits,
@@ -525,7 +537,7 @@ int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, 
     if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
     if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
     if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
-    return profile_device(ctx, nullptr, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+    return profile_device(ctx, nullptr, nullptr, n, d_pos, d_base, d_qual, d_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
                           d_splits, prm, out);
 }
 
@@ -563,7 +575,7 @@ int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb
     int qpass = prm->min_qual < 1 ? 1 : (prm->min_qual > 255 ? 255 : prm->min_qual);
     if ((rc = isb_k0_launch(ctx, n, d_off, d_idb, d_bqd, in->n_esc, d_esce, d_esci, in->start, L, qpass, c_pos, c_base,
                             c_qual, c_rid))) return rc;
-    return profile_device(ctx, nullptr, n, c_pos, c_base, c_qual, c_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
+    return profile_device(ctx, nullptr, nullptr, n, c_pos, c_base, c_qual, c_rid, in->n_pairs, d_mm, in->start, L, M, d_ref, in->n_splits,
                           d_splits, prm, out);
 }
 
@@ -632,7 +644,7 @@ int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params 
     if ((rc = stage_reads(ctx, in, &rd, &d_mm))) return rc;
     if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
     if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
-    return profile_device(ctx, &rd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+    return profile_device(ctx, &rd, nullptr, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
                           in->n_splits, d_splits, prm, out);
 }
 
@@ -676,7 +688,107 @@ int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const i
     if ((rc = isb_k0r_launch(ctx, in->n_segs, rd.seg_start, rd.seg_len, in->n_units, d_b2, d_ps, d_seg_word, rd.n_words, d_words))) return rc;
     rd.seg_word = d_seg_word;
     rd.words = d_words;
-    return profile_device(ctx, &rd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+    return profile_device(ctx, &rd, nullptr, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+                          in->n_splits, d_splits, prm, out);
+}
+
+// host or device column-word batch -> device pointers
+static int stage_cols(isb_ctx *ctx, const isb_cols_batch *in, isb_cols_dev *cd, const uint8_t **d_mm)
+{
+    int rc;
+    const int64_t n_groups = ((int64_t)in->L + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP;
+    if (in->n_groups != n_groups || in->n_chunks < 0 || !in->grp_off || (in->n_chunks > 0 && !in->words))
+        return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: n_groups must be ceil(L / 64); grp_off / words must not be null");
+    if (in->n_nev < 0 || (in->n_nev > 0 && (!in->nev_pos || !in->nev_pair)))
+        return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: null N-event column");
+    memset(cd, 0, sizeof(*cd));
+    cd->n_groups = n_groups;
+    cd->n_chunks = in->n_chunks;
+    cd->n_nev = in->n_nev;
+    if ((rc = stage_in(ctx, SL_CD_OFF, in->grp_off, (size_t)n_groups + 1, &cd->grp_off))) return rc;
+    if ((rc = stage_in(ctx, SL_CD_WORDS, in->words, (size_t)in->n_chunks * ISB_COLS_CHUNK, &cd->words))) return rc;
+    if ((rc = stage_in(ctx, SL_CD_IDS, in->ids, (size_t)in->n_chunks * ISB_COLS_CHUNK, &cd->ids))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPOS, in->nev_pos, (size_t)in->n_nev, &cd->nev_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPAIR, in->nev_pair, (size_t)in->n_nev, &cd->nev_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, d_mm))) return rc;
+    return ISB_OK;
+}
+
+int isb_cols_from_reads(isb_ctx *ctx, const isb_reads_batch *in, int64_t *grp_off, int64_t *n_chunks, uint32_t *words,
+                        int32_t *ids, int64_t cap_chunks)
+{
+    if (!ctx || !in || !grp_off || !n_chunks) return ISB_ERR_ARG;
+    int rc = check_common(ctx, in->L, 1);
+    if (rc) return rc;
+    if (words && (!ids || cap_chunks < 0)) return isb_fail(ctx, ISB_ERR_ARG, "isb_cols_from_reads: ids / cap_chunks invalid");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_reads_dev rd;
+    const uint8_t *d_mm;
+    isb_reads_batch tmp = *in;
+    tmp.pair_mm = nullptr;                                        // not needed here
+    tmp.n_pairs = 0;
+    if ((rc = stage_reads(ctx, &tmp, &rd, &d_mm))) return rc;
+    const size_t n_groups = (size_t)(((int64_t)in->L + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP);
+    int64_t *d_off; uint32_t *d_words = nullptr; int32_t *d_ids = nullptr;
+    if ((rc = stage_out(ctx, SL_CD_OFF, grp_off, n_groups + 1, &d_off))) return rc;
+    if (words) {
+        if ((rc = stage_out(ctx, SL_CD_WORDS, words, (size_t)cap_chunks * ISB_COLS_CHUNK, &d_words))) return rc;
+        if ((rc = stage_out(ctx, SL_CD_IDS, ids, (size_t)cap_chunks * ISB_COLS_CHUNK, &d_ids))) return rc;
+    }
+    rc = isb_cols_convert(ctx, &rd, in->start, in->L, d_off, d_words, d_ids, cap_chunks, n_chunks);
+    if (rc && rc != ISB_ERR_CAPACITY) return rc;
+    const int rc_cap = rc;
+    if ((rc = finish_out(ctx, grp_off, d_off, n_groups + 1))) return rc;
+    if (words && rc_cap == ISB_OK) {
+        if ((rc = finish_out(ctx, words, d_words, (size_t)*n_chunks * ISB_COLS_CHUNK))) return rc;
+        if ((rc = finish_out(ctx, ids, d_ids, (size_t)*n_chunks * ISB_COLS_CHUNK))) return rc;
+    }
+    if ((rc = fetch_status(ctx))) return rc;
+    if ((rc = check_dev_err(ctx))) return rc;
+    return rc_cap;
+}
+
+int isb_pileup_cols(isb_ctx *ctx, const isb_cols_batch *in, int32_t *counts, uint64_t *nmask)
+{
+    if (!ctx || !in) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!counts || (M > 1 && in->n_chunks > 0 && (!in->pair_mm || !in->ids))) return isb_fail(ctx, ISB_ERR_ARG, "isb_pileup_cols: null pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_cols_dev cd;
+    const uint8_t *d_mm;
+    if ((rc = stage_cols(ctx, in, &cd, &d_mm))) return rc;
+    int32_t *d_counts; uint64_t *d_nmask = nullptr;
+    if ((rc = stage_out(ctx, SL_COUNTS, counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if (nmask && (rc = stage_out(ctx, SL_NMASK, nmask, (size_t)L, &d_nmask))) return rc;
+    if ((rc = isb_k1c_launch(ctx, &cd, d_mm, in->n_pairs, in->start, L, M, d_counts, (unsigned long long *)d_nmask, nullptr))) return rc;
+    if ((rc = finish_out(ctx, counts, d_counts, (size_t)L * M * 4))) return rc;
+    if ((rc = finish_out(ctx, nmask, d_nmask, (size_t)L))) return rc;
+    if ((rc = fetch_status(ctx))) return rc;
+    return check_dev_err(ctx);
+}
+
+int isb_profile_cols(isb_ctx *ctx, const isb_cols_batch *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!in->ref || (M > 1 && !in->pair_mm) || (in->n_splits > 0 && !in->splits) || (in->n_chunks > 0 && !in->ids))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_cols: null input pointer");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_cols_dev cd;
+    const uint8_t *d_mm, *d_ref; const int32_t *d_splits;
+    if ((rc = stage_cols(ctx, in, &cd, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    return profile_device(ctx, nullptr, &cd, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
                           in->n_splits, d_splits, prm, out);
 }
 

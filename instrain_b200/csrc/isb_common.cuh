@@ -27,6 +27,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_RD_START, SL_RD_LEN, SL_RD_PAIR, SL_RD_WORD, SL_RD_WORDS, SL_RD_BOUNDS, SL_RD_NPOS, SL_RD_NPAIR,         // read-major batch (K1r inputs)
     SL_RC_BASE2, SL_RC_PASS,                                                       // compact transfer format (K0r inputs)
     SL_RD_CAND, SL_RD_EVOFF, SL_RD_EVB, SL_RD_EVQ, SL_RD_EVID,                          // K3 site events from segments
+    SL_CD_OFF, SL_CD_WORDS, SL_CD_IDS, SL_CD_CNT,                                  // column-word batch (K1c inputs) + conversion scratch
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
     SL_COUNT
 };
@@ -138,6 +139,40 @@ int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, 
                         int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                         const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
                         int64_t cap);
+// column-word batch (include/instrain_b200.h, isb_cols_batch), device pointers
+struct isb_cols_dev {
+    int64_t n_groups;                 // groups of ISB_COLS_GROUP = 64 positions (ISB_COLS_LANES = 8 column words)
+    const int64_t *grp_off;           // [n_groups + 1] chunk offsets
+    int64_t n_chunks;
+    const uint32_t *words;            // [n_chunks][ISB_COLS_LANES][4]
+    const int32_t *ids;               // same indexing: read-pair id of each word, -1 = padding
+    int64_t n_nev;
+    const int32_t *nev_pos;
+    const int32_t *nev_pair;
+};
+// fused SNV call (M = 1) in the epilogue of K1c: everything isb_k2_launch would take
+struct isb_k2_fuse {
+    const uint8_t *ref;
+    int min_cov;
+    double min_freq;
+    int32_t *covT;
+    float *clonT;
+    uint8_t *site_flags;
+    isb_snv_row *rows;
+    int64_t cap;
+    int full_counts;                  // 1: write counts of every position; 0: only of flagged sites (what K3 reads)
+};
+int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
+                   int M, int32_t *counts, unsigned long long *nmask, const isb_k2_fuse *fuse);
+int isb_cols_convert(isb_ctx *ctx, const isb_reads_dev *rd, int32_t start, int32_t L, int64_t *grp_off, uint32_t *words,
+                     int32_t *ids, int64_t cap_chunks, int64_t *n_chunks);
+int isb_k3_launch_cols(isb_ctx *ctx, const isb_cols_dev *cd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
+                       int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                       const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
+                       int64_t cap);
+int isb_k1r_n_events_launch(isb_ctx *ctx, int64_t n_nev, const int32_t *nev_pos, const int32_t *nev_pair, const uint8_t *pair_mm,
+                            int64_t n_pairs, int32_t start, int32_t L, int M, unsigned long long *nmask);
+int isb_k2_prepare(isb_ctx *ctx, double min_freq);
 int isb_ensure(isb_ctx *ctx, int slot, size_t bytes);
 int isb_k2_selftest_division(isb_ctx *ctx, int s_lo, int s_hi, unsigned long long *h_mismatches);
 int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const float *clonT, const unsigned long long *nmask,

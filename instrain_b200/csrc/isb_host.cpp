@@ -716,3 +716,51 @@ void isb_filter_copy(void *h, int tid, char *names_blob, int64_t *name_off, int3
 void isb_filter_free(void *h) { delete (Filter *)h; }
 
 }  // extern "C"
+
+// ---- read-major segments -> column words (host side of isb_cols_from_reads; include/instrain_b200.h, isb_cols_batch) ----
+// The packer's transposition at word granularity: every data word of a segment goes to the list of the column word it
+// covers, lists keep table (= BAM) order, the 8 lists of a group are padded to the group's depth and interleaved in
+// 16-byte units.  Two passes over the segment table (count, fill).
+extern "C" int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len,
+                                            const int32_t *seg_pair, const int64_t *seg_word, const uint32_t *words_in,
+                                            int64_t n_words_in, int32_t start, int32_t L, int64_t *grp_off, uint32_t *words,
+                                            int32_t *ids, int64_t cap_chunks)
+{
+    if ((start & 7) || L < 0 || !grp_off || n_segs < 0) return -1;
+    const int LN = ISB_COLS_LANES;
+    const int64_t n_groups = ((int64_t)L + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP;
+    std::vector<int32_t> cnt((size_t)n_groups * LN, 0);
+    for (int64_t i = 0; i < n_segs; ++i) {
+        const int64_t s = seg_start[i], n = seg_len[i];
+        const int64_t nw = ((s & 7) + n + 7) >> 3;
+        if (n < 1 || n > 256 || s < start || s + n > (int64_t)start + L || seg_word[i] < 0 || seg_word[i] + nw > n_words_in ||
+            (i > 0 && seg_start[i - 1] > s))
+            return -1;
+        const int64_t c_lo = (s - start) >> 3;
+        for (int64_t k = 0; k < nw; ++k) cnt[(size_t)(c_lo + k)]++;
+    }
+    grp_off[0] = 0;
+    for (int64_t g = 0; g < n_groups; ++g) {
+        int mx = 0;
+        for (int l = 0; l < LN; ++l) mx = std::max(mx, (int)cnt[(size_t)g * LN + l]);
+        grp_off[g + 1] = grp_off[g] + (mx + 3) / 4;
+    }
+    const int64_t n_chunks = grp_off[n_groups];
+    if (!words || !ids || n_chunks > cap_chunks) return n_chunks;
+    std::fill(words, words + n_chunks * ISB_COLS_CHUNK, 0u);
+    std::fill(ids, ids + n_chunks * ISB_COLS_CHUNK, -1);
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int64_t i = 0; i < n_segs; ++i) {
+        const int64_t s = seg_start[i], n = seg_len[i];
+        const int64_t nw = ((s & 7) + n + 7) >> 3;
+        const int64_t c_lo = (s - start) >> 3;
+        for (int64_t k = 0; k < nw; ++k) {
+            const int64_t c = c_lo + k;
+            const int slot = cnt[(size_t)c]++;
+            const int64_t idx = ((grp_off[c / LN] + (slot >> 2)) * LN + (c % LN)) * 4 + (slot & 3);
+            words[idx] = words_in[seg_word[i] + k];
+            ids[idx] = seg_pair[i];
+        }
+    }
+    return n_chunks;
+}

@@ -24,6 +24,7 @@
 // HBM traffic: 0.5 B per aligned base + ~22 B per segment in, 16*M B per position out (vs 6-10 B per event in for K1).
 // The kernel is bound by issue slots / shared-memory bandwidth, not by HBM (profiles/README.md).
 #include "isb_common.cuh"
+#include "isb_bitslice.cuh"
 #include <climits>
 
 #define K1R_THREADS (K1R_TILE / 8)     // one thread per 8 positions (one word of nibbles)
@@ -61,63 +62,6 @@ k1r_tile_bounds(const int32_t *__restrict__ seg_start, const uint16_t *__restric
     tile_hi[t] = hi;
     tile_wlo[t] = hi > lo ? seg_word[lo] - 1 : 0;
     tile_whi[t] = hi > lo ? seg_word[hi - 1] + (((seg_start[hi - 1] & 7) + seg_len[hi - 1] + 7) >> 3) + 1 : 0;
-}
-
-// carry-save adder on 32 independent bit lanes: h = majority(a, b, c), l = a ^ b ^ c (one LOP3 each)
-#define K1R_CSA(h, l, a, b, c)                       \
-    {                                                \
-        const uint32_t u_ = (a) ^ (b);               \
-        const uint32_t h_ = ((a) & (b)) | (u_ & (c)); \
-        l = u_ ^ (c);                                \
-        h = h_;                                      \
-    }
-
-// 8-bit -> 32-bit: byte j of `lo` counts position 2j, byte j of `hi` position 2j+1
-__device__ __forceinline__ void k1r_widen(int (&c)[8][4], int b, uint32_t lo, uint32_t hi)
-{
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        c[2 * j][b] += (int)((lo >> (8 * j)) & 0xffu);
-        c[2 * j + 1][b] += (int)((hi >> (8 * j)) & 0xffu);
-    }
-}
-
-// Vertical (bit-sliced) counters -> per-(position, base) integers.  Plane j holds bit j of 32 independent counters, bit
-// lane 4k + b = (position k, base b).  Per base, the eight lanes are pulled out as 0/1 bytes of two words (even / odd
-// positions) and summed with weight 2^j, then widened.
-__device__ __forceinline__ void k1r_planes_to_counts(int (&c)[8][4], uint32_t (&pl)[8])
-{
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        uint32_t lo = 0u, hi = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            lo += ((pl[j] >> b) & 0x01010101u) << j;
-            hi += ((pl[j] >> (b + 4)) & 0x01010101u) << j;
-        }
-        k1r_widen(c, b, lo, hi);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pl[j] = 0u;
-}
-
-// Harley-Seal block: eight 1-bit inputs per lane into the planes with 7 carry-save adders + one 5-plane ripple
-__device__ __forceinline__ void k1r_add8(uint32_t (&pl)[8], const uint32_t (&x)[8])
-{
-    uint32_t t2a, t2b, t4a, t4b, t8;
-    K1R_CSA(t2a, pl[0], pl[0], x[0], x[1]);
-    K1R_CSA(t2b, pl[0], pl[0], x[2], x[3]);
-    K1R_CSA(t4a, pl[1], pl[1], t2a, t2b);
-    K1R_CSA(t2a, pl[0], pl[0], x[4], x[5]);
-    K1R_CSA(t2b, pl[0], pl[0], x[6], x[7]);
-    K1R_CSA(t4b, pl[1], pl[1], t2a, t2b);
-    K1R_CSA(t8, pl[2], pl[2], t4a, t4b);
-#pragma unroll
-    for (int j = 3; j < 8; ++j) {
-        const uint32_t cy = pl[j] & t8;
-        pl[j] ^= t8;
-        t8 = cy;
-    }
 }
 
 // M > 1: write (or add, once counts hold a partial sum) the thread's shared 8-bit counters to its cells of `counts`
@@ -378,6 +322,16 @@ k1r_n_events(int64_t n_nev, const int32_t *__restrict__ nev_pos, const int32_t *
     atomicOr(nmask + p, 1ull << mm);
 }
 
+int isb_k1r_n_events_launch(isb_ctx *ctx, int64_t n_nev, const int32_t *nev_pos, const int32_t *nev_pair, const uint8_t *pair_mm,
+                            int64_t n_pairs, int32_t start, int32_t L, int M, unsigned long long *nmask)
+{
+    if (n_nev <= 0 || !nmask) return ISB_OK;
+    k1r_n_events<<<(unsigned)((n_nev + 255) / 256), 256, 0, ctx->stream>>>(n_nev, nev_pos, nev_pair, pair_mm, n_pairs, start, L, M,
+                                                                           nmask, ctx->d_err);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
+}
+
 int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
                    int M, int32_t *counts, unsigned long long *nmask)
 {
@@ -437,10 +391,6 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
         k1r_pileup<false><<<dim3(n_tiles, groups), K1R_THREADS, smem, st>>>(a);
         ISB_LAUNCH_CHECK();
     }
-    if (nmask && rd->n_nev > 0) {
-        k1r_n_events<<<(unsigned)((rd->n_nev + 255) / 256), 256, 0, st>>>(rd->n_nev, rd->nev_pos, rd->nev_pair, pair_mm,
-                                                                          n_pairs, start, L, M, nmask, ctx->d_err);
-        ISB_LAUNCH_CHECK();
-    }
+    if (nmask && rd->n_nev > 0) return isb_k1r_n_events_launch(ctx, rd->n_nev, rd->nev_pos, rd->nev_pair, pair_mm, n_pairs, start, L, M, nmask);
     return ISB_OK;
 }

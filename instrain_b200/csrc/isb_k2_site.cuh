@@ -1,0 +1,118 @@
+// isb_k2_site.cuh -- the per-site arithmetic of the SNV caller shared by K2 (isb_k2_snv.cu) and the fused pileup + SNV
+// kernel of the column-word path (isb_k1c_cols.cu): exact quotients, np.argmax, and the single-level (M = 1) site call.
+// Reference: call_snv_site / update_snp_table / calc_snp_class / calculate_clonality (inStrain/profile/snv_utilities.py:40-231),
+// is_present (inStrain/readComparer.py:307-316).
+#pragma once
+#include "isb_common.cuh"
+#include <math_constants.h>
+
+// Correctly rounded c / s for the four base frequencies of one site from ONE correctly rounded reciprocal
+// (Markstein: with y = RN(1/s) and q = RN(c*y), q' = RN(q + (c - s*q)*y) is RN(c/s)).  Three FP64 operations per
+// quotient instead of a full IEEE division each.  Used for s <= K2_FAST_DIV_MAX, the range for which
+// isb_selftest_division (tests/test_gpu_parity.py) compares it bit for bit with __ddiv_rn for EVERY 0 <= c <= s.
+#define K2_FAST_DIV_MAX 65536
+__device__ __forceinline__ double k2_quot(double c, double s, double rcp)
+{
+    const double q = __dmul_rn(c, rcp);
+    const double e = __fma_rn(-q, s, c);
+    return __fma_rn(e, rcp, q);
+}
+
+__device__ __forceinline__ int k2_argmax4(const int *c)
+{
+    int b = 0, v = c[0];                                  // np.argmax: first maximum (value tracked: no dynamic indexing)
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (c[i] > v) { v = c[i]; b = i; }
+    return b;
+}
+
+// One site at M = 1 (--skip_mm_profiling): the reference's loop body runs once, `cryptic` can never be set and the site
+// has at most one row.  C = A,C,T,G counts, r = reference base code, nm0 = "level 0 is a key of MMcounts although no
+// A/C/T/G base was counted" (a passing non-ACGT read base, profile_utilities.py:280-281).
+struct k2_m1_site {
+    int T;            // coverage (covT)
+    float clon;       // clonality (NaN = unset)
+    unsigned flags;   // site_flags byte
+    bool is_row;      // the site emits a raw_snp_table row
+    int i, con, thr;  // allele count ("morphia"), consensus base, threshold used (for the row / class)
+};
+
+__device__ __forceinline__ k2_m1_site k2_site_m1(const int (&C)[4], int r, bool nm0, const int32_t *__restrict__ thr2,
+                                                 int n_lut, int lut_default, int min_cov, double min_freq)
+{
+    k2_m1_site s;
+    s.T = C[0] + C[1] + C[2] + C[3];
+    s.clon = CUDART_NAN_F;
+    s.flags = 0u;
+    s.is_row = false;
+    s.i = 0; s.con = 0; s.thr = 0;
+    const int T = s.T;
+    const bool present = T > 0 || nm0;
+    const bool counted = present && T >= min_cov;
+    if (!counted) return s;                                           // call_snv_site -> (None, 0)
+    const int mx = max(max(C[0], C[1]), max(C[2], C[3]));
+    if (mx == T && T > 0) {
+        s.clon = 1.0f;                                                // one base only: (T/T)^2 + 0 + 0 + 0 is exactly 1
+    } else {                                                          // calculate_clonality, double, A,C,T,G order
+        const double sd = (double)T;
+        double f0, f1, f2, f3;
+        if (T <= K2_FAST_DIV_MAX) {
+            const double rcp = __drcp_rn(sd);
+            f0 = k2_quot((double)C[0], sd, rcp); f1 = k2_quot((double)C[1], sd, rcp);
+            f2 = k2_quot((double)C[2], sd, rcp); f3 = k2_quot((double)C[3], sd, rcp);
+        } else {
+            f0 = C[0] ? __ddiv_rn((double)C[0], sd) : 0.0; f1 = C[1] ? __ddiv_rn((double)C[1], sd) : 0.0;
+            f2 = C[2] ? __ddiv_rn((double)C[2], sd) : 0.0; f3 = C[3] ? __ddiv_rn((double)C[3], sd) : 0.0;
+        }
+        double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
+        prob = __dadd_rn(prob, __dmul_rn(f2, f2));
+        prob = __dadd_rn(prob, __dmul_rn(f3, f3));
+        s.clon = __double2float_rn(prob);
+    }
+    int i = 0;
+    if (T < n_lut) {                                                  // integer form of the two-part presence test
+        s.thr = __ldg(thr2 + T);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) i += (C[b] >= s.thr);
+    } else {
+        s.thr = lut_default;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (C[b] >= s.thr && __ddiv_rn((double)C[b], (double)T) >= min_freq) ++i;
+    }
+    s.i = i;
+    s.con = k2_argmax4(C);
+    s.is_row = (i > 1) || (i == 1 && s.con != r) || (i == 0);
+    if (s.is_row && i >= 2) {
+        const int tmp[4] = {s.con == 0 ? 0 : C[0], s.con == 1 ? 0 : C[1], s.con == 2 ? 0 : C[2], s.con == 3 ? 0 : C[3]};
+        s.flags = ISB_SITE_ANYSNP | (1u << s.con) | (1u << k2_argmax4(tmp));
+    }
+    return s;
+}
+
+// the raw_snp_table row of a site for which k2_site_m1 said is_row (pos = batch coordinate)
+__device__ __forceinline__ void k2_write_row_m1(isb_snv_row *__restrict__ dst_row, int32_t pos, const int (&C)[4], int r,
+                                                const k2_m1_site &s, int n_lut, double min_freq)
+{
+    const int con = s.con, i = s.i, T = s.T, thr = s.thr;
+    const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
+    const int var = k2_argmax4(tmp);
+    int cls;
+    if (r > 3) cls = ISB_CLS_AMBIGUOUS_REFERENCE;
+    else if (i == 0) cls = ISB_CLS_DIVERGENT_SITE;
+    else if (i == 1) cls = ISB_CLS_SNS;
+    else if (r == con) cls = ISB_CLS_SNV;
+    else if (r == var) cls = ISB_CLS_CON_SNV;
+    else {
+        const int cr = r == 0 ? C[0] : r == 1 ? C[1] : r == 2 ? C[2] : C[3];                   // is_present(counts[ref], ...)
+        const bool pres = T < n_lut ? (cr >= thr) : (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq);
+        cls = pres ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
+    }
+    int4 lo, hi;
+    lo.x = pos; lo.y = C[0]; lo.z = C[1]; lo.w = C[2];
+    hi.x = C[3]; hi.y = 0;
+    hi.z = (r & 0xff) | (con << 8) | (var << 16) | (i << 24);
+    hi.w = cls;
+    int4 *dst = reinterpret_cast<int4 *>(dst_row);
+    dst[0] = lo; dst[1] = hi;
+}

@@ -9,6 +9,7 @@
 // All floating-point tests are IEEE double with explicit round-to-nearest intrinsics (no FMA contraction) so the
 // >= min_freq decisions and the float32 clonality are bit-identical to CPython's arithmetic.
 #include "isb_common.cuh"
+#include "isb_k2_site.cuh"
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -32,18 +33,6 @@ __global__ void k2_build_thr2(const int32_t *__restrict__ lut, int n_lut, int lu
     thr2[T] = max(thr, lo);
 }
 
-// Correctly rounded c / s for the four base frequencies of one site from ONE correctly rounded reciprocal
-// (Markstein: with y = RN(1/s) and q = RN(c*y), q' = RN(q + (c - s*q)*y) is RN(c/s)).  Three FP64 operations per
-// quotient instead of a full IEEE division each.  Used for s <= K2_FAST_DIV_MAX, the range for which
-// isb_selftest_division (tests/test_gpu_parity.py) compares it bit for bit with __ddiv_rn for EVERY 0 <= c <= s.
-#define K2_FAST_DIV_MAX 65536
-__device__ __forceinline__ double k2_quot(double c, double s, double rcp)
-{
-    const double q = __dmul_rn(c, rcp);
-    const double e = __fma_rn(-q, s, c);
-    return __fma_rn(e, rcp, q);
-}
-
 __global__ void k2_selftest_division(int s_lo, int s_hi, unsigned long long *__restrict__ mismatches)
 {
     const int s = s_lo + blockIdx.x;
@@ -62,14 +51,6 @@ struct k2_site_state {
     int any_snp;
     int C[4];                                                         // cumulative A,C,T,G counts up to the current level
 };
-
-__device__ __forceinline__ int k2_argmax4(const int *c)
-{
-    int b = 0, v = c[0];                                  // np.argmax: first maximum (value tracked: no dynamic indexing)
-#pragma unroll
-    for (int i = 1; i < 4; ++i) if (c[i] > v) { v = c[i]; b = i; }
-    return b;
-}
 
 // The reference's ascending-mm loop over levels [m0, m0 + mc) of ONE site; `st` carries anySNP / bases / cryptic / the
 // cumulative counts across calls.  crow[j], cov_row[j], clon_row[j] address level m0 + j (global rows, or the block's
@@ -228,89 +209,29 @@ k2_call_snvs_m1(int32_t L, const int32_t *__restrict__ counts, const unsigned lo
 {
     const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
     const bool active = p < L;
-    bool is_row = false;
-    int C[4] = {0, 0, 0, 0}, T = 0, i = 0, con = 0, thr = 0, r = 4;
+    k2_m1_site s;
+    s.is_row = false;
+    int C[4] = {0, 0, 0, 0}, r = 4;
     if (active) {
         const int4 E = __ldg(reinterpret_cast<const int4 *>(counts) + p);
         r = ref[p];
-        T = E.x + E.y + E.z + E.w;
-        const bool present = T > 0 || (nmask && (nmask[p] & 1ull));   // level 0 is a key of MMcounts
-        const bool counted = present && T >= min_cov;
         C[0] = E.x; C[1] = E.y; C[2] = E.z; C[3] = E.w;
-        float clon = CUDART_NAN_F;
-        if (counted) {                                                // calculate_clonality, double, A,C,T,G order
-            const int mx = max(max(C[0], C[1]), max(C[2], C[3]));
-            if (mx == T && T > 0) {
-                clon = 1.0f;                                          // one base only: (T/T)^2 + 0 + 0 + 0 is exactly 1
-            } else {
-                const double s = (double)T;
-                double f0, f1, f2, f3;
-                if (T <= K2_FAST_DIV_MAX) {
-                    const double rcp = __drcp_rn(s);
-                    f0 = k2_quot((double)C[0], s, rcp); f1 = k2_quot((double)C[1], s, rcp);
-                    f2 = k2_quot((double)C[2], s, rcp); f3 = k2_quot((double)C[3], s, rcp);
-                } else {
-                    f0 = C[0] ? __ddiv_rn((double)C[0], s) : 0.0; f1 = C[1] ? __ddiv_rn((double)C[1], s) : 0.0;
-                    f2 = C[2] ? __ddiv_rn((double)C[2], s) : 0.0; f3 = C[3] ? __ddiv_rn((double)C[3], s) : 0.0;
-                }
-                double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
-                prob = __dadd_rn(prob, __dmul_rn(f2, f2));
-                prob = __dadd_rn(prob, __dmul_rn(f3, f3));
-                clon = __double2float_rn(prob);
-            }
-        }
-        covT[p] = T;
-        clonT[p] = clon;
-        unsigned flags = 0u;
-        if (counted) {
-            if (T < n_lut) {
-                thr = __ldg(thr2 + T);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) i += (C[b] >= thr);
-            } else {
-                thr = lut_default;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (C[b] >= thr && __ddiv_rn((double)C[b], (double)T) >= min_freq) ++i;
-            }
-            con = k2_argmax4(C);
-            is_row = (i > 1) || (i == 1 && con != r) || (i == 0);
-            if (is_row && i >= 2) {
-                const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
-                flags = ISB_SITE_ANYSNP | (1u << con) | (1u << k2_argmax4(tmp));
-            }
-        }
-        site_flags[p] = (uint8_t)flags;
+        const bool nm0 = (E.x + E.y + E.z + E.w) == 0 && nmask && (nmask[p] & 1ull);   // level 0 is a key of MMcounts
+        s = k2_site_m1(C, r, nm0, thr2, n_lut, lut_default, min_cov, min_freq);
+        covT[p] = s.T;
+        clonT[p] = s.clon;
+        site_flags[p] = (uint8_t)s.flags;
     }
-    const unsigned mask = __ballot_sync(ISB_FULL, is_row);
+    const unsigned mask = __ballot_sync(ISB_FULL, s.is_row);
     if (!mask) return;
     const int lane = threadIdx.x & 31;
     unsigned long long base_slot = 0;
     if (lane == 0) base_slot = atomicAdd(n_rows, (unsigned long long)__popc(mask));
     base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
-    if (!is_row) return;
+    if (!s.is_row) return;
     const int64_t slot = (int64_t)base_slot + __popc(mask & ((1u << lane) - 1u));
     if (slot >= cap) return;
-    const int tmp[4] = {con == 0 ? 0 : C[0], con == 1 ? 0 : C[1], con == 2 ? 0 : C[2], con == 3 ? 0 : C[3]};
-    const int var = k2_argmax4(tmp);
-    int cls;
-    if (r > 3) cls = ISB_CLS_AMBIGUOUS_REFERENCE;
-    else if (i == 0) cls = ISB_CLS_DIVERGENT_SITE;
-    else if (i == 1) cls = ISB_CLS_SNS;
-    else if (r == con) cls = ISB_CLS_SNV;
-    else if (r == var) cls = ISB_CLS_CON_SNV;
-    else {
-        const int cr = r == 0 ? C[0] : r == 1 ? C[1] : r == 2 ? C[2] : C[3];                   // is_present(counts[ref], ...)
-        const bool pres = T < n_lut ? (cr >= thr) : (cr >= thr && __ddiv_rn((double)cr, (double)T) >= min_freq);
-        cls = pres ? ISB_CLS_CON_SNV : ISB_CLS_POP_SNV;
-    }
-    int4 lo, hi;
-    lo.x = p + start; lo.y = C[0]; lo.z = C[1]; lo.w = C[2];
-    hi.x = C[3]; hi.y = 0;
-    hi.z = (r & 0xff) | (con << 8) | (var << 16) | (i << 24);
-    hi.w = cls;
-    int4 *dst = reinterpret_cast<int4 *>(rows + slot);
-    dst[0] = lo; dst[1] = hi;
+    k2_write_row_m1(rows + slot, p + start, C, r, s, n_lut, min_freq);
 }
 
 // M > 1: a thread's M count quads are 16*M bytes apart from its neighbour's, so direct loads touch one 32-byte sector per
@@ -417,19 +338,29 @@ static size_t k2s_smem_bytes(int M)
     return (size_t)K2S_THREADS * sin * 16 + 2 * (size_t)K2S_THREADS * sout * 4 + 16;
 }
 
-int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
-                  const uint8_t *ref, int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT,
-                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap)
+// Row counter reset + the merged integer threshold table of (context, min_freq); also called by the fused pileup + SNV
+// kernel of the column-word path (isb_k1c_cols.cu), which runs k2_site_m1 in its epilogue.
+int isb_k2_prepare(isb_ctx *ctx, double min_freq)
 {
     cudaStream_t st = ctx->stream;
     if (!ctx->keep_counters) ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 0, 0, sizeof(unsigned long long), st));
-    if (L <= 0) return ISB_OK;
     if (!ctx->d_thr2 || ctx->thr2_min_freq != min_freq) {             // (re)build the merged integer threshold table
         if (!ctx->d_thr2) ISB_CUDA(cudaMalloc(&ctx->d_thr2, sizeof(int32_t) * (size_t)ctx->n_lut));
         k2_build_thr2<<<(ctx->n_lut + 255) / 256, 256, 0, st>>>(ctx->d_lut, ctx->n_lut, ctx->lut_default, min_freq, ctx->d_thr2);
         ISB_LAUNCH_CHECK();
         ctx->thr2_min_freq = min_freq;
     }
+    return ISB_OK;
+}
+
+int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                  const uint8_t *ref, int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT,
+                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap)
+{
+    cudaStream_t st = ctx->stream;
+    int rc = isb_k2_prepare(ctx, min_freq);
+    if (rc) return rc;
+    if (L <= 0) return ISB_OK;
     static const int variant = getenv("ISB_K2_VARIANT") ? atoi(getenv("ISB_K2_VARIANT")) : -1;   // 0 = generic direct kernel, otherwise M = 1: specialised, M > 1: staged
     if (M > 1 && variant != 0) {
         const size_t smem = k2s_smem_bytes(M);

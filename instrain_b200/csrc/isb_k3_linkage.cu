@@ -154,6 +154,47 @@ __device__ __forceinline__ bool k3r_candidate(const isb_reads_dev &rd, int64_t g
     return true;
 }
 
+// ---- column-word front end (isb_cols_batch): the entries of a site are ONE nibble of every word of its column list ----
+// Site p lives in column word c = p / 8, lane c % 8 of group c / 8; slot i of its list is word
+// ((grp_off[g] + i / 4) * 8 + lane) * 4 + i % 4 of `words` / `ids` (table order of the segments = column order).  No
+// candidate search and no dependent address chain: every load address follows from p alone.
+struct k3c_column {
+    int64_t base;   // index of slot 0
+    int depth;      // slots (incl. padding)
+    int sh;         // bit offset of the site's nibble
+};
+
+__device__ __forceinline__ k3c_column k3c_site_column(const isb_cols_dev &cd, int32_t p)
+{
+    k3c_column col;
+    const int64_t c = p >> 3, g = c / ISB_COLS_LANES;
+    const int64_t c0 = __ldg(cd.grp_off + g), c1 = __ldg(cd.grp_off + g + 1);
+    const bool ok = c0 >= 0 && c1 >= c0 && c1 <= cd.n_chunks && c1 - c0 <= (1 << 24);   // K1c has flagged a violation
+    col.base = (c0 * ISB_COLS_LANES + (c % ISB_COLS_LANES)) * 4;
+    col.depth = ok ? (int)(c1 - c0) * 4 : 0;
+    col.sh = (p & 7) << 2;
+    return col;
+}
+
+__device__ __forceinline__ bool k3c_candidate(const isb_cols_dev &cd, const k3c_column &col, int i, int64_t n_pairs, int &b,
+                                              int &id)
+{
+    const int64_t idx = col.base + (int64_t)(i >> 2) * ISB_COLS_CHUNK + (i & 3);
+    const uint32_t code = (__ldg(cd.words + idx) >> col.sh) & 15u;
+    if (!code) return false;
+    id = __ldg(cd.ids + idx);
+    if (id < 0 || (int64_t)id >= n_pairs) return false;               // padding / invalid (K1c reports ids >= n_pairs at M > 1)
+    b = __ffs((int)code) - 1;                                         // one-hot A,C,T,G
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k3c_site_split(k3_args a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.S) return;
+    a.meta[k].split = k3_site_split(a, (int64_t)a.site_pos[k] + a.start);
+}
+
 __device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m, int na, unsigned bases, int b, int id,
                                            unsigned int *d_err)
 {
@@ -174,7 +215,9 @@ __device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m
 // the word counter, assemble them (shared-memory scratch for the common small windows) and store them.  The events
 // never touch global memory; sites with more qualifying entries than the list holds gather a second time.
 #define K3R_EV_CAP 320
-__global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
+template <bool kCols>
+__global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads_dev rd, isb_cols_dev cd,
+                                                            const int64_t *__restrict__ cand_lo,
                                                             const int32_t *__restrict__ n_cand, int64_t *__restrict__ row_off,
                                                             unsigned long long *__restrict__ row_words_total, int64_t row_cap)
 {
@@ -190,12 +233,17 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
         const int64_t abs_pos = (int64_t)p + a.start;
         const unsigned bases = a.site_flags[p] & 0xF;
         const int na = __popc(bases);
-        const int64_t clo = cand_lo[k];
-        const int nc = n_cand[k];
+        k3c_column col = {0, 0, 0};
+        if (kCols) col = k3c_site_column(cd, p);
+        const int64_t clo = kCols ? 0 : cand_lo[k];
+        const int nc = kCols ? col.depth : n_cand[k];
+        auto candidate = [&](int i, int &b, int &id) -> bool {
+            return kCols ? k3c_candidate(cd, col, i, a.n_pairs, b, id) : k3r_candidate(rd, clo + i, abs_pos, b, id);
+        };
         int cnt = 0, idmin = INT_MAX, idmax = -1;
         for (int i0 = 0; i0 < nc; i0 += 32) {
             int b = 0, id = 0;
-            bool ok = (i0 + lane < nc) && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id);
+            bool ok = (i0 + lane < nc) && candidate(i0 + lane, b, id);
             ok = ok && ((bases >> b) & 1u);
             const unsigned mask = __ballot_sync(ISB_FULL, ok);
             if (ok) {
@@ -241,7 +289,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
         } else {
             for (int i0 = 0; i0 < nc; i0 += 32) {
                 int b = 0, id = 0;
-                if (i0 + lane < nc && k3r_candidate(rd, clo + i0 + lane, abs_pos, b, id) && ((bases >> b) & 1u))
+                if (i0 + lane < nc && candidate(i0 + lane, b, id) && ((bases >> b) & 1u))
                     dbl |= k3_row_set(any, m, na, bases, b, id, a.d_err);
             }
         }
@@ -587,9 +635,9 @@ __global__ void __launch_bounds__(256) k3_pair_stats(k3_args a, int64_t n_pairs_
 // Self edges: a pair with two entries (first, second in column order) on ONE site gives the combo
 // "b_first:b_second" on the edge (p, p) (itertools.combinations over the pair's entry list).  Rare: one thread per
 // flagged site, exact and slow.
-template <bool kReads>
-__global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd, const int64_t *__restrict__ cand_lo,
-                                                     const int32_t *__restrict__ n_cand)
+template <int kMode>   // 0 = position-major events, 1 = read-major segments, 2 = column words
+__global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd, isb_cols_dev cd,
+                                                     const int64_t *__restrict__ cand_lo, const int32_t *__restrict__ n_cand)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.S; k += stride) {
@@ -597,11 +645,15 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
         const int32_t p = a.site_pos[k];
         const int64_t abs_pos = (int64_t)p + a.start;
         const unsigned bases = a.site_flags[p] & 0xF;
-        // entries of the site in column order: event range (position-major) or candidate segments (read-major)
-        const int64_t lo = kReads ? cand_lo[k] : a.site_ev[2 * k];
-        const int64_t hi = kReads ? lo + n_cand[k] : a.site_ev[2 * k + 1];
+        // entries of the site in column order: event range (position-major), candidate segments (read-major) or the
+        // slots of the site's column list (column words)
+        k3c_column col = {0, 0, 0};
+        if (kMode == 2) col = k3c_site_column(cd, p);
+        const int64_t lo = kMode == 2 ? 0 : (kMode == 1 ? cand_lo[k] : a.site_ev[2 * k]);
+        const int64_t hi = kMode == 2 ? col.depth : (kMode == 1 ? lo + n_cand[k] : a.site_ev[2 * k + 1]);
         auto entry = [&](int64_t e, int &b, int &rid) -> bool {
-            if (kReads) return k3r_candidate(rd, e, abs_pos, b, rid) && ((bases >> b) & 1u);
+            if (kMode == 2) return k3c_candidate(cd, col, (int)e, a.n_pairs, b, rid) && ((bases >> b) & 1u);
+            if (kMode == 1) return k3r_candidate(rd, e, abs_pos, b, rid) && ((bases >> b) & 1u);
             if (!k3_qualifies(a, e, bases)) return false;
             b = a.base[e];
             rid = a.read_id[e];
@@ -638,7 +690,7 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
     }
 }
 
-static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_t *ref_pos, const uint8_t *base,
+static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd, int64_t n, const int32_t *ref_pos, const uint8_t *base,
                   const uint8_t *qual, const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
                   int32_t L, int M, int min_qual, const int32_t *counts, const unsigned long long *nmask,
                   const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
@@ -650,7 +702,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
     if (ctx->keep_counters) ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, 3 * sizeof(unsigned long long), st));
     else ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), st));
     ctx->h_counters[2] = ctx->h_counters[3] = 0;
-    if (L <= 0 || (!rd && n <= 0) || (rd && rd->n_segs <= 0)) return ISB_OK;
+    if (L <= 0 || (!rd && !cd && n <= 0) || (rd && rd->n_segs <= 0) || (cd && cd->n_chunks <= 0)) return ISB_OK;
 
     // 1. ordered list of linkage-eligible sites
     const int nb = (int)(((int64_t)L + SCAN_BLOCK - 1) / SCAN_BLOCK);
@@ -705,7 +757,9 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
     }
     int64_t *cand_lo = nullptr;
     int32_t *n_cand = nullptr;
-    if (!rd) {                                                  // position-major columns
+    const isb_reads_dev rd_none = {};
+    const isb_cols_dev cd_none = {};
+    if (!rd && !cd) {                                           // position-major columns
         const int tp = 1024;                                    // searches bounded by position-tile event offsets
         const int n_tiles = (L + tp - 1) / tp;
         if ((rc = isb_tile_offsets(ctx, ref_pos, n, start, L, tp, n_tiles))) return rc;
@@ -731,23 +785,29 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         ISB_CUDA(cudaMemsetAsync(a.rows, 0, sizeof(uint32_t) * (total_words + 4), st));
         k3_build_rows<<<grid_sites, K3_THREADS, 0, st>>>(a);
         ISB_LAUNCH_CHECK();
-    } else {                                                    // read-major segments: candidate ranges of the sites
-        if ((rc = isb_ensure(ctx, SL_RD_CAND, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)S))) return rc;
-        cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
-        n_cand = (int32_t *)(cand_lo + S);
-        k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
+    } else {
+        if (rd) {                                               // read-major segments: candidate ranges of the sites
+            if ((rc = isb_ensure(ctx, SL_RD_CAND, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)S))) return rc;
+            cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
+            n_cand = (int32_t *)(cand_lo + S);
+            k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
+        } else {                                                // column words: only the split of each site is needed
+            k3c_site_split<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+        }
         ISB_LAUNCH_CHECK();
         // initial guess of the row storage (words per site); the fused kernel reports the exact need if it is too small
         static const int rows_init = getenv("ISB_K3_ROWS_INIT") ? atoi(getenv("ISB_K3_ROWS_INIT")) : 48;
         if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)S * (size_t)(rows_init > 0 ? rows_init : 1) + 64)))) return rc;
     }
     for (int attempt = 0; attempt < 4; ++attempt) {
-        if (rd) {                                               // fused gather + window + rows (no host sync needed)
+        if (rd || cd) {                                         // fused gather + window + rows (no host sync needed)
             const int64_t row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
             a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
             ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
-            k3r_site_rows<<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
-                                                           ctx->d_counters + 4, row_cap);
+            if (rd) k3r_site_rows<false><<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cd_none, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
+                                                                          ctx->d_counters + 4, row_cap);
+            else k3r_site_rows<true><<<grid_sites, K3_THREADS, 0, st>>>(a, rd_none, *cd, nullptr, nullptr, (int64_t *)ctx->buf[SL_ROW_OFF].p,
+                                                                      ctx->d_counters + 4, row_cap);
             ISB_LAUNCH_CHECK();
         }
         int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
@@ -766,7 +826,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         ISB_CUDA(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         ISB_CUDA(cudaStreamSynchronize(st));
-        if (rd && (*ctx->h_err & ISB_DEV_ERR_ROWBUF)) {         // row storage too small: grow to the counted size, redo
+        if ((rd || cd) && (*ctx->h_err & ISB_DEV_ERR_ROWBUF)) { // row storage too small: grow to the counted size, redo
             if (*ctx->h_err & ~ISB_DEV_ERR_ROWBUF) return ISB_OK;   // another error is pending: let the caller report it
             ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), st));
             const size_t need = (size_t)ctx->h_counters[4];
@@ -785,8 +845,9 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n, const int32_
         if (attempt == 3) return isb_fail(ctx, ISB_ERR_CUDA, "linkage: scratch sizing did not converge");
     }
     const int grid_self = (int)((S + 127) / 128 < (int64_t)ctx->sm_count * 8 ? (S + 127) / 128 : (int64_t)ctx->sm_count * 8);
-    if (rd) k3_self_edges<true><<<grid_self, 128, 0, st>>>(a, *rd, cand_lo, n_cand);
-    else k3_self_edges<false><<<grid_self, 128, 0, st>>>(a, isb_reads_dev{}, nullptr, nullptr);
+    if (rd) k3_self_edges<1><<<grid_self, 128, 0, st>>>(a, *rd, cd_none, cand_lo, n_cand);
+    else if (cd) k3_self_edges<2><<<grid_self, 128, 0, st>>>(a, rd_none, *cd, nullptr, nullptr);
+    else k3_self_edges<0><<<grid_self, 128, 0, st>>>(a, rd_none, cd_none, nullptr, nullptr);
     ISB_LAUNCH_CHECK();
     return ISB_OK;
 }
@@ -796,7 +857,7 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
                   int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows, int64_t cap)
 {
-    return k3_run(ctx, nullptr, n, ref_pos, base, qual, read_id, n_pairs, pair_mm, start, L, M, min_qual, counts, nmask,
+    return k3_run(ctx, nullptr, nullptr, n, ref_pos, base, qual, read_id, n_pairs, pair_mm, start, L, M, min_qual, counts, nmask,
                   site_flags, n_splits, splits, min_snp, rows, cap);
 }
 
@@ -805,6 +866,16 @@ int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, 
                         const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
                         int64_t cap)
 {
-    return k3_run(ctx, rd, 0, nullptr, nullptr, nullptr, nullptr, n_pairs, pair_mm, start, L, M, 0, counts, nmask,
+    return k3_run(ctx, rd, nullptr, 0, nullptr, nullptr, nullptr, nullptr, n_pairs, pair_mm, start, L, M, 0, counts, nmask,
+                  site_flags, n_splits, splits, min_snp, rows, cap);
+}
+
+int isb_k3_launch_cols(isb_ctx *ctx, const isb_cols_dev *cd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
+                       int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
+                       const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
+                       int64_t cap)
+{
+    if (cd->n_chunks > 0 && !cd->ids) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: ids is required for linkage");
+    return k3_run(ctx, nullptr, cd, 0, nullptr, nullptr, nullptr, nullptr, n_pairs, pair_mm, start, L, M, 0, counts, nmask,
                   site_flags, n_splits, splits, min_snp, rows, cap);
 }

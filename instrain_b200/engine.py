@@ -110,6 +110,40 @@ class Engine:
         self._check(self.lib.isb_pileup_reads(self.ctx, C.byref(batch), _cabi.ptr(counts), _cabi.ptr(nmask)))
         return counts, nmask
 
+    # ---- column words (instrain_b200.cols) ---------------------------------------------------------------------------
+    def _cols_batch(self, cd, pair_mm, start, L, ref_codes, splits, M):
+        p = _cabi.ptr
+        n_pairs = len(pair_mm) if pair_mm is not None else 0
+        return _cabi.IsbColsBatch(int(cd["n_groups"]), p(cd["grp_off"]), int(cd["n_chunks"]), p(cd["words"]), p(cd["ids"]),
+                                  len(cd["nev_pos"]), p(cd["nev_pos"]), p(cd["nev_pair"]), n_pairs, p(pair_mm), start, L,
+                                  p(ref_codes), 0 if splits is None else len(splits), p(splits), M, 0)
+
+    def pileup_cols(self, cd, pair_mm, start, L, M, counts=None, nmask=None):
+        """K1c alone: counts[L, M, 4] (+ nmask[L]) from a column-word batch (instrain_b200.cols)."""
+        pair_mm = _pair_mm_u8(pair_mm)
+        if counts is None:
+            counts = np.empty((L, M, 4), dtype=np.int32)
+        if nmask is None:
+            nmask = np.empty(L, dtype=np.uint64)
+        batch = self._cols_batch(cd, pair_mm, start, L, None, None, M)
+        self._check(self.lib.isb_pileup_cols(self.ctx, C.byref(batch), _cabi.ptr(counts), _cabi.ptr(nmask)))
+        return counts, nmask
+
+    def cols_from_reads(self, rd, L, start=0):
+        """Device-side layout conversion (isb_cols_from_reads): read-major batch -> column-word batch (numpy arrays)."""
+        batch = self._reads_batch(rd, None, start, L, None, None, 1)
+        from .cols import GROUP, CHUNK
+        n_groups = (L + GROUP - 1) // GROUP
+        grp_off = np.zeros(n_groups + 1, dtype=np.int64)
+        n = C.c_int64(0)
+        p = _cabi.ptr
+        self._check(self.lib.isb_cols_from_reads(self.ctx, C.byref(batch), p(grp_off), C.byref(n), None, None, 0))
+        words = np.empty(n.value * CHUNK, dtype=np.uint32)
+        ids = np.empty(n.value * CHUNK, dtype=np.int32)
+        self._check(self.lib.isb_cols_from_reads(self.ctx, C.byref(batch), p(grp_off), C.byref(n), p(words), p(ids), n.value))
+        return dict(n_groups=n_groups, grp_off=grp_off, n_chunks=int(n.value), words=words, ids=ids,
+                    nev_pos=rd["nev_pos"], nev_pair=rd["nev_pair"])
+
     def call_snvs(self, counts, nmask, ref_codes, start=0, min_cov=5, min_freq=0.05, cap=None):
         L, M = counts.shape[0], counts.shape[1]
         covT = np.empty((L, M), dtype=np.int32)
@@ -162,7 +196,7 @@ class Engine:
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
-                      snv_cap=None, ld_cap=None, packed=None, pipeline=False, reads=None):
+                      snv_cap=None, ld_cap=None, packed=None, pipeline=False, reads=None, cols=None):
         """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
 
         `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
@@ -175,7 +209,10 @@ class Engine:
             raise ValueError("mm levels M=%d exceeds ISB_MAX_MM=%d" % (M, _cabi.ISB_MAX_MM))
         splits = np.ascontiguousarray(splits, dtype=np.int32).reshape(-1, 2)
         p = _cabi.ptr
-        if reads is not None and "base2" in reads:  # compact transfer format (instrain_b200.reads.compact_reads)
+        if cols is not None:                        # column words (instrain_b200.cols)
+            batch = self._cols_batch(cols, pair_mm, start, L, ref_codes, splits, M)
+            entry = self.lib.isb_profile_cols
+        elif reads is not None and "base2" in reads:  # compact transfer format (instrain_b200.reads.compact_reads)
             batch = _cabi.IsbReadsCompact(int(reads["n_segs"]), p(reads["seg_start"]), p(reads["seg_len"]),
                                           p(reads["seg_pair"]), int(reads["n_units"]), p(reads["base2"]), p(reads["pass"]),
                                           int(reads["max_seg_len"]), 0, len(reads["nev_pos"]), p(reads["nev_pos"]),

@@ -167,3 +167,32 @@ def to_host_batch(d, lo_scaffold=0, n_scaffolds=1):
         qual=d["qual"][e_lo:e_hi].cpu().numpy(), read_id=(rid - id_lo).cpu().numpy(),
         pair_mm=d["pair_mm"][id_lo:id_hi].cpu().numpy(), ref_codes=d["ref_codes"][p_lo:p_hi].cpu().numpy(),
         splits=(spl[sel] - p_lo).cpu().numpy())
+
+
+def reads_to_cols_device(eng, d):
+    """Lay the generated read-major data set out as COLUMN WORDS in HBM (include/instrain_b200.h, isb_cols_batch) with
+    the library's device-side conversion (isb_cols_from_reads, device pointers in and out; two calls: sizing, fill)."""
+    import torch
+    from . import _cabi
+    from .cols import CHUNK, GROUP
+    rd = d["reads"]
+    Ltot = d["L"] * d["n_scaffolds"]
+    dev = rd["words"].device
+    p = _cabi.ptr
+    batch = _cabi.IsbReadsBatch(int(rd["n_segs"]), p(rd["seg_start"]), p(rd["seg_len"]), p(rd["seg_pair"]), p(rd["seg_word"]),
+                                int(rd["n_words"]), p(rd["words"]), int(rd["max_seg_len"]), 0, 0, None, None, 0, None, 0,
+                                Ltot, None, 0, None, 1, 0)
+    n_groups = (Ltot + GROUP - 1) // GROUP
+    grp_off = torch.empty(n_groups + 1, dtype=torch.int64, device=dev)
+    n = C.c_int64(0)
+    rc = eng.lib.isb_cols_from_reads(eng.ctx, C.byref(batch), p(grp_off), C.byref(n), None, None, 0)
+    if rc != 0:
+        raise RuntimeError("isb_cols_from_reads: " + eng.lib.isb_last_error(eng.ctx).decode())
+    words = torch.empty(max(n.value, 1) * CHUNK, dtype=torch.int32, device=dev)[:n.value * CHUNK]
+    ids = torch.empty(max(n.value, 1) * CHUNK, dtype=torch.int32, device=dev)[:n.value * CHUNK]
+    rc = eng.lib.isb_cols_from_reads(eng.ctx, C.byref(batch), p(grp_off), C.byref(n), p(words), p(ids), n.value)
+    if rc != 0:
+        raise RuntimeError("isb_cols_from_reads: " + eng.lib.isb_last_error(eng.ctx).decode())
+    torch.cuda.synchronize()
+    return dict(n_groups=n_groups, grp_off=grp_off, n_chunks=int(n.value), words=words, ids=ids,
+                nev_pos=rd["nev_pos"], nev_pair=rd["nev_pair"])

@@ -26,7 +26,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
       --log-file $out/${tag}_launches.csv python bench.py $SMALL > $out/${tag}_launches.log 2>&1
   echo "ncu launches exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on \
-      -k regex:'k1r_pileup|k2_call|k2_stage|k3r_site_rows|k3r_site_cand|k3_enum_pairs|k3_pair_stats' -s 12 -c 14 \
+      -k regex:'k1c_pileup|k1r_pileup|k2_call|k3r_site_rows|k3_enum_pairs|k3_pair_stats' -s 8 -c 8 \
       -f -o $out/${tag}_full python bench.py $SMALL > $out/${tag}_full.log 2>&1
   echo "ncu full exit $?"
 fi
