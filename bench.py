@@ -346,7 +346,7 @@ def main():
                                       " + 4 B pair id per word" if M > 1 else "",
                                       "ref 1 B in, covT 4 + clonT 4 + site_flags 1 B per position, 32 B per SNV row, 16 B counts per linkage site"
                                       if fused else "16*M B/position counts + 8 B/position nmask"),
-                    "padding_words_frac": cd["n_chunks"] * 32 / max(1, cd["n_real_words"]) - 1,
+                    "padding_words_frac": cd["n_chunks"] * 64 / max(1, cd["n_real_words"]) - 1,
                     "launch_ms": k1_ms,
                     "note": ("the stage is ONE kernel: pileup counts + the per-site SNV call (K2) in its epilogue" if fused else
                              "pileup counts only; K2 runs as its own kernel")}

@@ -298,26 +298,27 @@ int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const i
  * north-star "columnar, position-major" layout with 4 bits per aligned base instead of 10 bytes.
  *   - position p (relative to `start`, a multiple of 8) lies in column word c = p / 8, GROUP g = c / 8 (64 positions),
  *     lane c % 8;
- *   - group g owns chunks [grp_off[g], grp_off[g+1]); a chunk is 8 lanes x 4 words (128 bytes, one cache line).  Slot i
- *     of column (g, lane) is word ((grp_off[g] + i / 4) * 8 + lane) * 4 + i % 4 of `words`, its read-pair id the same
- *     element of `ids`.  Every column of a group is padded to the group's depth 4 * (grp_off[g+1] - grp_off[g]) with
- *     word 0 / id -1 (8 neighbouring columns see almost the same reads: ~6 % padding at 100x, against ~12 % for groups
- *     of 32);
+ *   - group g owns chunks [grp_off[g], grp_off[g+1]); a chunk is 8 lanes x 8 words (256 bytes): 8 consecutive slots of
+ *     each of the group's 8 columns, a column's 8 slots contiguous (one 32-byte sector).  Slot i of column (g, lane) is
+ *     word ((grp_off[g] + i / 8) * 8 + lane) * 8 + i % 8 of `words`, its read-pair id the same element of `ids`.  Every
+ *     column of a group is padded to the group's depth 8 * (grp_off[g+1] - grp_off[g]) with word 0 / id -1 (8
+ *     neighbouring columns see almost the same reads: ~8 % padding at 100x);
  *   - the words of a column keep the table order of their segments (BAM order);
  *   - passing non-ACGT read bases go to nev_pos / nev_pair as in isb_reads_batch.
- * K1c (isb_k1c_cols.cu) streams it: a warp takes 4 consecutive groups, lane = column word, every load instruction reads
- * four whole 128-byte lines, bit-sliced counting, no shared memory, atomics or searches -- an HBM-bound kernel on 0.5 B
- * per aligned base.  The linkage stage reads the entries of an SNV site as one nibble of each word of its column
- * (addresses follow from the position). */
-#define ISB_COLS_LANES 8
-#define ISB_COLS_GROUP (8 * ISB_COLS_LANES)   /* positions per group */
-#define ISB_COLS_CHUNK (4 * ISB_COLS_LANES)   /* words per chunk */
+ * K1c (isb_k1c_cols.cu) streams it: a warp takes 4 consecutive groups, lane = column word, one 256-bit load per lane and
+ * chunk (a warp instruction reads 1 KB: four whole 256-byte chunks), bit-sliced counting, no shared memory, atomics or
+ * searches -- an HBM-bound kernel on 0.5 B per aligned base.  The linkage stage reads the entries of an SNV site as one
+ * nibble of each word of its column: whole 32-byte sectors at addresses that follow from the position alone. */
+#define ISB_COLS_LANES 8                                  /* column words per group */
+#define ISB_COLS_UNIT 8                                   /* consecutive slots of one column per chunk (32 bytes) */
+#define ISB_COLS_GROUP (8 * ISB_COLS_LANES)               /* positions per group */
+#define ISB_COLS_CHUNK (ISB_COLS_UNIT * ISB_COLS_LANES)   /* words per chunk */
 typedef struct {
     int64_t n_groups;           /* ceil(L / ISB_COLS_GROUP) */
     const int64_t *grp_off;     /* [n_groups + 1] chunk offsets, grp_off[0] = 0 */
     int64_t n_chunks;           /* = grp_off[n_groups] */
-    const uint32_t *words;      /* [n_chunks * ISB_COLS_CHUNK], 16-byte aligned */
-    const int32_t *ids;         /* [n_chunks * ISB_COLS_CHUNK], 16-byte aligned; may be NULL for isb_pileup_cols at M == 1 */
+    const uint32_t *words;      /* [n_chunks * ISB_COLS_CHUNK], 32-byte aligned */
+    const int32_t *ids;         /* [n_chunks * ISB_COLS_CHUNK], 32-byte aligned; may be NULL for isb_pileup_cols at M == 1 */
     int64_t n_nev;
     const int32_t *nev_pos;
     const int32_t *nev_pair;

@@ -3,7 +3,7 @@ isb_pileup_cols.
 
 Layout and rules: include/instrain_b200.h (isb_cols_batch).  The one-hot nibble words of a read-major batch
 (instrain_b200/reads.py), regrouped per COLUMN WORD (8 positions): group g = 64 positions = 8 column words, chunk =
-8 lanes x 4 words; slot i of column (g, lane) is word ((grp_off[g] + i // 4) * 8 + lane) * 4 + i % 4, its read-pair
+8 lanes x 8 words; slot i of column (g, lane) is word ((grp_off[g] + i // 8) * 8 + lane) * 8 + i % 8, its read-pair
 id the same element of `ids` (-1 = padding).  Words of a column keep the table order of their segments.
 
 `reads_to_cols` calls the C++ host packer routine (isb_cols_from_reads_host, no GPU); `reads_to_cols_numpy` is an
@@ -11,9 +11,10 @@ independent vectorised restatement used by the tests to pin it.
 """
 import numpy as np
 
-LANES = 8            # column words per group (ISB_COLS_LANES)
-GROUP = 8 * LANES    # positions per group
-CHUNK = 4 * LANES    # words per chunk
+LANES = 8               # column words per group (ISB_COLS_LANES)
+UNIT = 8                # consecutive slots of one column per chunk (ISB_COLS_UNIT)
+GROUP = 8 * LANES       # positions per group
+CHUNK = UNIT * LANES    # words per chunk
 
 
 def _seg_columns(rd, start):
@@ -34,7 +35,7 @@ def reads_to_cols_numpy(rd, L, start=0):
     n_groups = (L + GROUP - 1) // GROUP
     seg, col, src = _seg_columns(rd, start)
     cnt = np.bincount(col, minlength=n_groups * LANES).astype(np.int64) if len(col) else np.zeros(n_groups * LANES, np.int64)
-    depth_chunks = (cnt.reshape(n_groups, LANES).max(axis=1) + 3) // 4 if n_groups else np.zeros(0, np.int64)
+    depth_chunks = (cnt.reshape(n_groups, LANES).max(axis=1) + UNIT - 1) // UNIT if n_groups else np.zeros(0, np.int64)
     grp_off = np.zeros(n_groups + 1, dtype=np.int64)
     grp_off[1:] = np.cumsum(depth_chunks)
     n_chunks = int(grp_off[-1])
@@ -45,7 +46,7 @@ def reads_to_cols_numpy(rd, L, start=0):
         col_s, seg_s, src_s = col[order], seg[order], src[order]
         first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
         slot = np.arange(len(col_s), dtype=np.int64) - first[col_s]
-        idx = ((grp_off[col_s // LANES] + (slot >> 2)) * LANES + (col_s % LANES)) * 4 + (slot & 3)
+        idx = ((grp_off[col_s // LANES] + slot // UNIT) * LANES + (col_s % LANES)) * UNIT + slot % UNIT
         words[idx] = rd["words"][src_s]
         ids[idx] = rd["seg_pair"][seg_s]
     return dict(n_groups=n_groups, grp_off=grp_off, n_chunks=n_chunks, words=words, ids=ids,
@@ -79,8 +80,8 @@ def reads_to_cols(rd, L, start=0):
 def cols_to_events(cd, L, start=0):
     """Inverse view for tests: the passing events (position-major, column order) a column-word batch encodes."""
     pos, rid, base = [], [], []
-    w = cd["words"].reshape(-1, LANES, 4)
-    i = cd["ids"].reshape(-1, LANES, 4)
+    w = cd["words"].reshape(-1, LANES, UNIT)
+    i = cd["ids"].reshape(-1, LANES, UNIT)
     for g in range(cd["n_groups"]):
         c0, c1 = int(cd["grp_off"][g]), int(cd["grp_off"][g + 1])
         if c1 == c0:

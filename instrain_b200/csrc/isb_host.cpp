@@ -720,7 +720,7 @@ void isb_filter_free(void *h) { delete (Filter *)h; }
 // ---- read-major segments -> column words (host side of isb_cols_from_reads; include/instrain_b200.h, isb_cols_batch) ----
 // The packer's transposition at word granularity: every data word of a segment goes to the list of the column word it
 // covers, lists keep table (= BAM) order, the 8 lists of a group are padded to the group's depth and interleaved in
-// 16-byte units.  Two passes over the segment table (count, fill).
+// 32-byte units.  Two passes over the segment table (count, fill).
 extern "C" int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len,
                                             const int32_t *seg_pair, const int64_t *seg_word, const uint32_t *words_in,
                                             int64_t n_words_in, int32_t start, int32_t L, int64_t *grp_off, uint32_t *words,
@@ -743,7 +743,7 @@ extern "C" int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_s
     for (int64_t g = 0; g < n_groups; ++g) {
         int mx = 0;
         for (int l = 0; l < LN; ++l) mx = std::max(mx, (int)cnt[(size_t)g * LN + l]);
-        grp_off[g + 1] = grp_off[g] + (mx + 3) / 4;
+        grp_off[g + 1] = grp_off[g] + (mx + ISB_COLS_UNIT - 1) / ISB_COLS_UNIT;
     }
     const int64_t n_chunks = grp_off[n_groups];
     if (!words || !ids || n_chunks > cap_chunks) return n_chunks;
@@ -757,7 +757,7 @@ extern "C" int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_s
         for (int64_t k = 0; k < nw; ++k) {
             const int64_t c = c_lo + k;
             const int slot = cnt[(size_t)c]++;
-            const int64_t idx = ((grp_off[c / LN] + (slot >> 2)) * LN + (c % LN)) * 4 + (slot & 3);
+            const int64_t idx = ((grp_off[c / LN] + slot / ISB_COLS_UNIT) * LN + (c % LN)) * ISB_COLS_UNIT + slot % ISB_COLS_UNIT;
             words[idx] = words_in[seg_word[i] + k];
             ids[idx] = seg_pair[i];
         }

@@ -5,15 +5,16 @@
 // nibble word per (read, 8 aligned positions) as the read-major stream, but stored where the pileup needs it
 // (include/instrain_b200.h, isb_cols_batch): for every column word (8 consecutive positions) the words of the reads
 // that cover it, and the column lists of 8 neighbouring column words (one GROUP = 64 positions) interleaved in
-// 16-byte units, so that a row of a group is one 128-byte line.  The transposition "reads -> columns" that pysam's pileup engine performs per column
+// 32-byte units (8 slots of one column), so that a chunk row of a group is 256 contiguous bytes.  The transposition "reads -> columns" that pysam's pileup engine performs per column
 // is done once by the packer (isb_cols_from_reads*), so the kernel is a pure stream:
 //
-//   * a warp takes 4 consecutive groups (256 positions), lane = column word; per trip every lane issues 128-bit loads,
-//     8 lanes per 128-byte line (four whole lines per warp instruction), no shared memory, no atomics, no searches;
+//   * a warp takes 4 consecutive groups (256 positions), lane = column word; every lane issues ONE 256-bit load per
+//     chunk row (LDG.E.256: a warp instruction reads 1 KB), no shared memory, no atomics, no searches;
 //   * counting is bit-sliced as in K1r (isb_bitslice.cuh): 24 logic ops per 8 words;
-//   * M = 1 can run the SNV call of K2 (k2_site_m1, isb_k2_site.cuh) in its epilogue, on the 8 positions a lane holds
-//     in registers: covT / clonT / site_flags / SNV rows leave the kernel directly, counts are written only where the
-//     linkage stage reads them (flagged sites) unless the caller asks for the full array;
+//   * M = 1 can run the SNV call of K2 (k2_site_m1, isb_k2_site.cuh) in its epilogue: the warp's counts are transposed
+//     through shared memory to "lane = position", covT / clonT / site_flags / SNV rows leave the kernel directly with
+//     coalesced stores, counts are written only where the linkage stage reads them (flagged sites) unless the caller
+//     asks for the full array;
 //   * M > 1 gathers pair_mm[id] per word and keeps 8-bit counters per (level, base) in shared memory, [word][thread].
 //
 // HBM traffic: 0.5 B per aligned base (+ chunk padding, + 4 B id per word at M > 1) in, 16*M B per position out
@@ -28,11 +29,13 @@
 #define K1C_THREADS (32 * K1C_WARPS)
 #define K1C_LEVELS 32                      // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
 #ifndef K1C_ROWS
-#define K1C_ROWS 4                         // chunk rows (16-byte loads per lane) per trip of the M = 1 main loop; even
+#define K1C_ROWS 2                         // chunk rows (one 256-bit load per lane each) per trip of the M = 1 main loop
 #endif
 #ifndef K1C_MINB
 #define K1C_MINB 1                         // __launch_bounds__ min blocks per SM of the M = 1 kernels
 #endif
+#define K1C_TILE (256 + 32)                // count quads of a warp's 256 positions + one pad quad per 8 positions
+static_assert(ISB_COLS_UNIT == 8 && 32 % ISB_COLS_LANES == 0, "K1c loads one 8-word unit per lane and chunk");
 
 struct k1c_args {
     isb_cols_dev cd;
@@ -43,7 +46,6 @@ struct k1c_args {
     int M;
     int32_t *counts;
     int write_counts;                      // fused kernel: 1 = every position, 0 = only flagged sites (what K3 reads)
-    int vec_ok;                            // ref / covT / clonT / site_flags allow 8 / 16-byte vector accesses
     const unsigned long long *nmask;       // fused kernel: read where a position has no A/C/T/G count (may be NULL)
     isb_k2_fuse k2;
     const int32_t *thr2;
@@ -51,6 +53,14 @@ struct k1c_args {
     unsigned long long *n_rows;
     unsigned int *d_err;
 };
+
+// one 32-byte unit (8 words of one column) with a single 256-bit load; streamed data: no L1 allocation
+__device__ __forceinline__ void k1c_ld256(const void *p, uint32_t (&x)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
 
 // chunk range of the lane's group (lanes of one group read the same two offsets: broadcast); 0 chunks beyond the batch
 __device__ __forceinline__ void k1c_group_range(const k1c_args &a, int64_t g, int64_t &c0, int &nch)
@@ -75,8 +85,8 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MINB) k1c_pileup_m1(k1c_args 
     int64_t c0;
     int nch;                                                                     // per group: lanes of a warp may differ
     k1c_group_range(a, wg * (32 / ISB_COLS_LANES) + lane / ISB_COLS_LANES, c0, nch);
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.cd.words) + c0 * ISB_COLS_LANES + (lane % ISB_COLS_LANES);
-    constexpr int RS = ISB_COLS_LANES;                                           // uint4 units per chunk row
+    // the lane's unit of chunk row r: words + ((c0 + r) * LANES + lane % LANES) * 8
+    const uint32_t *src = a.cd.words + (c0 * ISB_COLS_LANES + (lane % ISB_COLS_LANES)) * ISB_COLS_UNIT;
 
     int c[8][4];
     uint32_t pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};            // vertical counter planes (weights 1 .. 128)
@@ -87,26 +97,21 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MINB) k1c_pileup_m1(k1c_args 
         for (int b = 0; b < 4; ++b) c[k][b] = 0;
 
     int ch = 0;
-    for (; ch + K1C_ROWS <= nch; ch += K1C_ROWS) {                // K1C_ROWS chunk rows = 4 * K1C_ROWS words per lane in flight
-        uint4 v[K1C_ROWS];
+    for (; ch + K1C_ROWS <= nch; ch += K1C_ROWS) {                // K1C_ROWS x 32 bytes per lane in flight
+        uint32_t x[K1C_ROWS][8];
 #pragma unroll
-        for (int r = 0; r < K1C_ROWS; ++r) v[r] = __ldg(src + (size_t)(ch + r) * RS);
+        for (int r = 0; r < K1C_ROWS; ++r) k1c_ld256(src + (size_t)(ch + r) * ISB_COLS_CHUNK, x[r]);
 #pragma unroll
-        for (int r = 0; r < K1C_ROWS; r += 2) {
-            const uint32_t x[8] = {v[r].x, v[r].y, v[r].z, v[r].w, v[r + 1].x, v[r + 1].y, v[r + 1].z, v[r + 1].w};
-            k1r_add8(pl, x);
-        }
-        n8 += 4 * K1C_ROWS;
-        if (n8 > 255 - 4 * K1C_ROWS) {                            // the next trip could overflow 255
+        for (int r = 0; r < K1C_ROWS; ++r) k1r_add8(pl, x[r]);
+        n8 += 8 * K1C_ROWS;
+        if (n8 > 255 - 8 * K1C_ROWS) {                            // the next trip could overflow 255
             k1r_planes_to_counts(c, pl);
             n8 = 0;
         }
     }
-    for (; ch < nch; ch += 2) {
-        const uint4 v0 = __ldg(src + (size_t)ch * RS);
-        uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
-        if (ch + 1 < nch) v1 = __ldg(src + (size_t)(ch + 1) * RS);
-        const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    for (; ch < nch; ++ch) {
+        uint32_t x[8];
+        k1c_ld256(src + (size_t)ch * ISB_COLS_CHUNK, x);
         k1r_add8(pl, x);
         n8 += 8;
         if (n8 > 247) {
@@ -116,78 +121,75 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MINB) k1c_pileup_m1(k1c_args 
     }
     k1r_planes_to_counts(c, pl);
 
-    // first of the lane's 8 positions (relative).  Lanes of the last warp may lie beyond L: they stay (the fused
-    // epilogue uses full-warp ballots) and every access below is guarded.
-    const int32_t P = (int32_t)min(wg * 256 + lane * 8, (int64_t)a.L);
-    int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
-    if (!kFuse || a.write_counts) {
+    if (!kFuse) {                                                 // counts of the lane's 8 positions (128 contiguous bytes)
+        const int64_t P = wg * 256 + lane * 8;
+        int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (P + k >= a.L) break;
             c4[k] = make_int4(c[k][0], c[k][1], c[k][2], c[k][3]);
         }
+        return;
     }
-    if (!kFuse) return;
 
-    // ---- fused SNV call of the lane's 8 positions (K2 at M = 1) ------------------------------------------------
-    const bool full = P + 8 <= a.L;
-    uint32_t rlo = 0x04040404u, rhi = 0x04040404u;
-    if (full && a.vec_ok) {
-        const uint2 rr = __ldg(reinterpret_cast<const uint2 *>(a.k2.ref + P));
-        rlo = rr.x; rhi = rr.y;
-    } else {
-        rlo = rhi = 0u;
+    // ---- fused SNV call (K2 at M = 1) ------------------------------------------------------------------------------
+    // The warp's 256 count quads are transposed through a warp-private shared-memory tile (one pad quad per 8
+    // positions: conflict-free both ways), then 8 rounds of "lane = position" run the site arithmetic of K2 with fully
+    // coalesced covT / clonT / site_flags stores.  Rows are allocated ONCE per warp (prefix sum of the lanes' row bits,
+    // one atomic) and written by re-evaluating the ~1 % of sites that have one.
+    __shared__ int4 s_tile[kFuse ? K1C_WARPS * K1C_TILE : 1];
+    int4 *tile = s_tile + (threadIdx.x >> 5) * K1C_TILE;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t r = (P + k < a.L) ? (uint32_t)a.k2.ref[P + k] : 4u;
-            if (k < 4) rlo |= r << (8 * k); else rhi |= r << (8 * (k - 4));
-        }
+    for (int k = 0; k < 8; ++k) tile[lane * 9 + k] = make_int4(c[k][0], c[k][1], c[k][2], c[k][3]);
+    __syncwarp();
+    const int64_t W0 = wg * 256;
+    int4 *counts4 = reinterpret_cast<int4 *>(a.counts);
+    unsigned rowmask = 0u;                                        // bit r: position W0 + 32 r + lane emits a raw_snp_table row
+    auto site = [&](int64_t p, const int4 &E, int (&C)[4], int &r) -> k2_m1_site {
+        C[0] = E.x; C[1] = E.y; C[2] = E.z; C[3] = E.w;
+        r = a.k2.ref[p];
+        const int T = E.x + E.y + E.z + E.w;
+        const int thr_T = (T >= a.k2.min_cov && T < a.n_lut) ? __ldg(a.thr2 + T) : a.lut_default;
+        const bool nm0 = T == 0 && a.nmask && (a.nmask[p] & 1ull);
+        return k2_site_m1(C, r, nm0, thr_T, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
+    };
+#pragma unroll 2
+    for (int rd = 0; rd < 8; ++rd) {
+        const int q = rd * 32 + lane;
+        const int64_t p = W0 + q;
+        if (p >= a.L) continue;
+        const int4 E = tile[q + (q >> 3)];
+        int C[4], r;
+        const k2_m1_site s = site(p, E, C, r);
+        a.k2.covT[p] = s.T;
+        a.k2.clonT[p] = s.clon;
+        a.k2.site_flags[p] = (uint8_t)s.flags;
+        if (a.write_counts || s.flags) counts4[p] = E;            // K3 reads counts at flagged sites only
+        rowmask |= (s.is_row ? 1u : 0u) << rd;
     }
-    int cov[8];
-    float cl[8];
-    uint32_t fl[2] = {0u, 0u};
+    const int my_rows = __popc(rowmask);
+    int incl = my_rows;                                           // warp prefix sum of the row counts
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int32_t p = P + k;
-        const int r = (int)(((k < 4 ? rlo : rhi) >> (8 * (k & 3))) & 0xffu);
-        k2_m1_site s;
-        s.T = 0; s.clon = CUDART_NAN_F; s.flags = 0u; s.is_row = false; s.i = 0; s.con = 0; s.thr = 0;
-        if (p < a.L) {
-            const bool nm0 = (c[k][0] + c[k][1] + c[k][2] + c[k][3]) == 0 && a.nmask && (a.nmask[p] & 1ull);
-            s = k2_site_m1(c[k], r, nm0, a.thr2, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
-            if (!a.write_counts && s.flags) c4[k] = make_int4(c[k][0], c[k][1], c[k][2], c[k][3]);
-        }
-        cov[k] = s.T;
-        cl[k] = s.clon;
-        fl[k >> 2] |= s.flags << (8 * (k & 3));
-        const unsigned mask = __ballot_sync(ISB_FULL, s.is_row);
-        if (mask) {                                               // one atomic per warp and position slot that has rows
-            const int leader = __ffs(mask) - 1;
-            unsigned long long base_slot = 0;
-            if (lane == leader) base_slot = atomicAdd(a.n_rows, (unsigned long long)__popc(mask));
-            base_slot = __shfl_sync(ISB_FULL, base_slot, leader);
-            if (s.is_row) {
-                const int64_t slot = (int64_t)base_slot + __popc(mask & ((1u << lane) - 1u));
-                if (slot < a.k2.cap) k2_write_row_m1(a.k2.rows + slot, p + a.start, c[k], r, s, a.n_lut, a.k2.min_freq);
-            }
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(ISB_FULL, incl, d);
+        if (lane >= d) incl += v;
     }
-    if (full && a.vec_ok) {
-        int4 *cv = reinterpret_cast<int4 *>(a.k2.covT + P);
-        cv[0] = make_int4(cov[0], cov[1], cov[2], cov[3]);
-        cv[1] = make_int4(cov[4], cov[5], cov[6], cov[7]);
-        float4 *cf = reinterpret_cast<float4 *>(a.k2.clonT + P);
-        cf[0] = make_float4(cl[0], cl[1], cl[2], cl[3]);
-        cf[1] = make_float4(cl[4], cl[5], cl[6], cl[7]);
-        *reinterpret_cast<uint2 *>(a.k2.site_flags + P) = make_uint2(fl[0], fl[1]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (P + k >= a.L) break;
-            a.k2.covT[P + k] = cov[k];
-            a.k2.clonT[P + k] = cl[k];
-            a.k2.site_flags[P + k] = (uint8_t)((fl[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        }
+    const int total = __shfl_sync(ISB_FULL, incl, 31);
+    if (total == 0) return;
+    unsigned long long base_slot = 0;
+    if (lane == 31) base_slot = atomicAdd(a.n_rows, (unsigned long long)total);
+    base_slot = __shfl_sync(ISB_FULL, base_slot, 31);
+    int64_t slot = (int64_t)base_slot + incl - my_rows;
+    while (rowmask) {
+        const int rd = __ffs((int)rowmask) - 1;
+        rowmask &= rowmask - 1u;
+        const int q = rd * 32 + lane;
+        const int64_t p = W0 + q;
+        const int4 E = tile[q + (q >> 3)];
+        int C[4], r;
+        const k2_m1_site s = site(p, E, C, r);
+        if (slot < a.k2.cap) k2_write_row_m1(a.k2.rows + slot, (int32_t)p + a.start, C, r, s, a.n_lut, a.k2.min_freq);
+        ++slot;
     }
 }
 
@@ -229,24 +231,19 @@ __global__ void __launch_bounds__(K1C_THREADS) k1c_pileup_mm(k1c_args a)
     int nch;
     k1c_group_range(a, wg * (32 / ISB_COLS_LANES) + lane / ISB_COLS_LANES, c0, nch);
     const int64_t P64 = wg * 256 + lane * 8;
-    constexpr int RS = ISB_COLS_LANES;
-    const uint4 *src = reinterpret_cast<const uint4 *>(a.cd.words) + c0 * RS + (lane % RS);
-    const int4 *sid = reinterpret_cast<const int4 *>(a.cd.ids) + c0 * RS + (lane % RS);
+    const size_t unit0 = (size_t)(c0 * ISB_COLS_LANES + (lane % ISB_COLS_LANES)) * ISB_COLS_UNIT;
+    const uint32_t *src = a.cd.words + unit0;
+    const int32_t *sid = a.cd.ids + unit0;
     int n8 = 0;
     bool spilled = false;
     unsigned err = 0;
-    for (int ch = 0; ch < nch; ch += 2) {                         // two chunk rows per trip: ids, then all mm gathers, then counts
-        const bool two = ch + 1 < nch;
-        const uint4 w0 = __ldg(src + (size_t)ch * RS);
-        const int4 i0 = __ldg(sid + (size_t)ch * RS);
-        uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
-        int4 i1 = make_int4(-1, -1, -1, -1);
-        if (two) {
-            w1 = __ldg(src + (size_t)(ch + 1) * RS);
-            i1 = __ldg(sid + (size_t)(ch + 1) * RS);
-        }
-        const uint32_t x[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    for (int ch = 0; ch < nch; ++ch) {                            // one chunk row per trip: words + ids, all mm gathers, then counts
+        uint32_t x[8], idu[8];
+        k1c_ld256(src + (size_t)ch * ISB_COLS_CHUNK, x);
+        k1c_ld256(sid + (size_t)ch * ISB_COLS_CHUNK, idu);
+        int id[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) id[u] = (int)idu[u];
         int mm[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -293,8 +290,8 @@ int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm,
     if (cd->n_groups != n_groups) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: n_groups must be ceil(L / 64)");
     if (cd->n_chunks < 0 || !cd->grp_off || (cd->n_chunks > 0 && !cd->words))
         return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: null grp_off / words");
-    if (((uintptr_t)cd->words & 15) != 0 || ((uintptr_t)cd->ids & 15) != 0 || ((uintptr_t)counts & 15) != 0)
-        return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: words, ids and counts must be 16-byte aligned");
+    if (((uintptr_t)cd->words & 31) != 0 || ((uintptr_t)cd->ids & 31) != 0 || ((uintptr_t)counts & 15) != 0)
+        return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: words and ids must be 32-byte aligned, counts 16-byte aligned");
     if (start & 7) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: start must be a multiple of 8");
     if (M > 1 && (!pair_mm || !cd->ids)) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: pair_mm and ids are required when M > 1");
     if (fuse && M != 1) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: the fused SNV call needs M == 1");
@@ -315,8 +312,6 @@ int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm,
         a.n_rows = ctx->d_counters + 0;
         a.nmask = nmask;
         a.write_counts = fuse->full_counts ? 1 : 0;
-        a.vec_ok = (((uintptr_t)fuse->ref & 7) == 0 && ((uintptr_t)fuse->covT & 15) == 0 && ((uintptr_t)fuse->clonT & 15) == 0 &&
-                    ((uintptr_t)fuse->site_flags & 7) == 0) ? 1 : 0;
         k1c_pileup_m1<true><<<blocks, K1C_THREADS, 0, st>>>(a);
         ISB_LAUNCH_CHECK();
     } else if (M == 1) {
@@ -369,8 +364,8 @@ k0c_columns(isb_reads_dev rd, int32_t start, int32_t L, int64_t n_cols, int32_t 
     int depth = 0;
     if (kFill && real) {
         const int64_t g = c / ISB_COLS_LANES;
-        base = (grp_off[g] * ISB_COLS_LANES + sl) * 4;
-        depth = (int)(grp_off[g + 1] - grp_off[g]) * 4;
+        base = (grp_off[g] * ISB_COLS_LANES + sl) * ISB_COLS_UNIT;
+        depth = (int)(grp_off[g + 1] - grp_off[g]) * ISB_COLS_UNIT;
     }
     int slot = 0;
     if (real && c * 8 < L) {
@@ -380,7 +375,7 @@ k0c_columns(isb_reads_dev rd, int32_t start, int32_t L, int64_t n_cols, int32_t 
             if (s >= W8 + 8) break;
             if (s + (int64_t)__ldg(rd.seg_len + i) - 1 < W8) continue;    // ends before the column
             if (kFill && slot < depth) {
-                const int64_t idx = base + (int64_t)(slot >> 2) * ISB_COLS_CHUNK + (slot & 3);
+                const int64_t idx = base + (int64_t)(slot / ISB_COLS_UNIT) * ISB_COLS_CHUNK + (slot % ISB_COLS_UNIT);
                 words[idx] = __ldg(rd.words + __ldg(rd.seg_word + i) + ((W8 >> 3) - (s >> 3)));
                 ids[idx] = __ldg(rd.seg_pair + i);
             }
@@ -389,7 +384,7 @@ k0c_columns(isb_reads_dev rd, int32_t start, int32_t L, int64_t n_cols, int32_t 
     }
     if (kFill) {
         for (; slot < depth; ++slot) {                                      // padding up to the group's depth
-            const int64_t idx = base + (int64_t)(slot >> 2) * ISB_COLS_CHUNK + (slot & 3);
+            const int64_t idx = base + (int64_t)(slot / ISB_COLS_UNIT) * ISB_COLS_CHUNK + (slot % ISB_COLS_UNIT);
             words[idx] = 0u;
             ids[idx] = -1;
         }
@@ -397,7 +392,7 @@ k0c_columns(isb_reads_dev rd, int32_t start, int32_t L, int64_t n_cols, int32_t 
         int mx = slot;
 #pragma unroll
         for (int d = ISB_COLS_LANES / 2; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(ISB_FULL, mx, d));   // max over the group's lanes
-        if (real && sl == 0) grp_chunks[c / ISB_COLS_LANES] = (mx + 3) >> 2;
+        if (real && sl == 0) grp_chunks[c / ISB_COLS_LANES] = (mx + ISB_COLS_UNIT - 1) / ISB_COLS_UNIT;
     }
 }
 

@@ -37,7 +37,8 @@ struct k2_m1_site {
     int i, con, thr;  // allele count ("morphia"), consensus base, threshold used (for the row / class)
 };
 
-__device__ __forceinline__ k2_m1_site k2_site_m1(const int (&C)[4], int r, bool nm0, const int32_t *__restrict__ thr2,
+// thr_T = thr2[T] (the merged integer threshold of coverage T = sum of C) when T < n_lut; unused otherwise.
+__device__ __forceinline__ k2_m1_site k2_site_m1(const int (&C)[4], int r, bool nm0, int thr_T,
                                                  int n_lut, int lut_default, int min_cov, double min_freq)
 {
     k2_m1_site s;
@@ -71,7 +72,7 @@ __device__ __forceinline__ k2_m1_site k2_site_m1(const int (&C)[4], int r, bool 
     }
     int i = 0;
     if (T < n_lut) {                                                  // integer form of the two-part presence test
-        s.thr = __ldg(thr2 + T);
+        s.thr = thr_T;
 #pragma unroll
         for (int b = 0; b < 4; ++b) i += (C[b] >= s.thr);
     } else {

@@ -217,7 +217,9 @@ k2_call_snvs_m1(int32_t L, const int32_t *__restrict__ counts, const unsigned lo
         r = ref[p];
         C[0] = E.x; C[1] = E.y; C[2] = E.z; C[3] = E.w;
         const bool nm0 = (E.x + E.y + E.z + E.w) == 0 && nmask && (nmask[p] & 1ull);   // level 0 is a key of MMcounts
-        s = k2_site_m1(C, r, nm0, thr2, n_lut, lut_default, min_cov, min_freq);
+        const int T = E.x + E.y + E.z + E.w;
+        const int thr_T = (T >= min_cov && T < n_lut) ? __ldg(thr2 + T) : lut_default;
+        s = k2_site_m1(C, r, nm0, thr_T, n_lut, lut_default, min_cov, min_freq);
         covT[p] = s.T;
         clonT[p] = s.clon;
         site_flags[p] = (uint8_t)s.flags;

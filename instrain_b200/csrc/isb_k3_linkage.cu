@@ -156,7 +156,7 @@ __device__ __forceinline__ bool k3r_candidate(const isb_reads_dev &rd, int64_t g
 
 // ---- column-word front end (isb_cols_batch): the entries of a site are ONE nibble of every word of its column list ----
 // Site p lives in column word c = p / 8, lane c % 8 of group c / 8; slot i of its list is word
-// ((grp_off[g] + i / 4) * 8 + lane) * 4 + i % 4 of `words` / `ids` (table order of the segments = column order).  No
+// ((grp_off[g] + i / 8) * 8 + lane) * 8 + i % 8 of `words` / `ids` (table order of the segments = column order).  No
 // candidate search and no dependent address chain: every load address follows from p alone.
 struct k3c_column {
     int64_t base;   // index of slot 0
@@ -170,22 +170,34 @@ __device__ __forceinline__ k3c_column k3c_site_column(const isb_cols_dev &cd, in
     const int64_t c = p >> 3, g = c / ISB_COLS_LANES;
     const int64_t c0 = __ldg(cd.grp_off + g), c1 = __ldg(cd.grp_off + g + 1);
     const bool ok = c0 >= 0 && c1 >= c0 && c1 <= cd.n_chunks && c1 - c0 <= (1 << 24);   // K1c has flagged a violation
-    col.base = (c0 * ISB_COLS_LANES + (c % ISB_COLS_LANES)) * 4;
-    col.depth = ok ? (int)(c1 - c0) * 4 : 0;
+    col.base = (c0 * ISB_COLS_LANES + (c % ISB_COLS_LANES)) * ISB_COLS_UNIT;
+    col.depth = ok ? (int)(c1 - c0) * ISB_COLS_UNIT : 0;
     col.sh = (p & 7) << 2;
     return col;
+}
+
+__device__ __forceinline__ int64_t k3c_slot_index(const k3c_column &col, int i)
+{
+    return col.base + (int64_t)(i / ISB_COLS_UNIT) * ISB_COLS_CHUNK + (i % ISB_COLS_UNIT);
+}
+
+// entry of slot i from an already loaded (word, id) pair
+__device__ __forceinline__ bool k3c_decode(const k3c_column &col, uint32_t w, int id_in, int64_t n_pairs, int &b, int &id)
+{
+    const uint32_t code = (w >> col.sh) & 15u;
+    if (!code || id_in < 0 || (int64_t)id_in >= n_pairs) return false;   // no event / padding / invalid id
+    id = id_in;
+    b = __ffs((int)code) - 1;                                         // one-hot A,C,T,G
+    return true;
 }
 
 __device__ __forceinline__ bool k3c_candidate(const isb_cols_dev &cd, const k3c_column &col, int i, int64_t n_pairs, int &b,
                                               int &id)
 {
-    const int64_t idx = col.base + (int64_t)(i >> 2) * ISB_COLS_CHUNK + (i & 3);
-    const uint32_t code = (__ldg(cd.words + idx) >> col.sh) & 15u;
-    if (!code) return false;
-    id = __ldg(cd.ids + idx);
-    if (id < 0 || (int64_t)id >= n_pairs) return false;               // padding / invalid (K1c reports ids >= n_pairs at M > 1)
-    b = __ffs((int)code) - 1;                                         // one-hot A,C,T,G
-    return true;
+    const int64_t idx = k3c_slot_index(col, i);
+    const uint32_t w = __ldg(cd.words + idx);
+    if (!((w >> col.sh) & 15u)) return false;
+    return k3c_decode(col, w, __ldg(cd.ids + idx), n_pairs, b, id);
 }
 
 __global__ void __launch_bounds__(256) k3c_site_split(k3_args a)
@@ -241,10 +253,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
             return kCols ? k3c_candidate(cd, col, i, a.n_pairs, b, id) : k3r_candidate(rd, clo + i, abs_pos, b, id);
         };
         int cnt = 0, idmin = INT_MAX, idmax = -1;
-        for (int i0 = 0; i0 < nc; i0 += 32) {
-            int b = 0, id = 0;
-            bool ok = (i0 + lane < nc) && candidate(i0 + lane, b, id);
-            ok = ok && ((bases >> b) & 1u);
+        auto append = [&](bool ok, int b, int id) {
             const unsigned mask = __ballot_sync(ISB_FULL, ok);
             if (ok) {
                 const int slot = cnt + __popc(mask & ((1u << lane) - 1u));
@@ -253,6 +262,39 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
                 idmax = max(idmax, id);
             }
             cnt += __popc(mask);
+        };
+        if (kCols) {
+            // every address follows from the position: the words and ids of 4 x 32 slots are requested before the first is
+            // used (one memory latency per 128 slots instead of two dependent ones per 32)
+            for (int i0 = 0; i0 < nc; i0 += 128) {
+                uint32_t w[4];
+                int idv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    w[u] = 0u;
+                    idv[u] = -1;
+                    if (i < nc) {
+                        const int64_t idx = k3c_slot_index(col, i);
+                        w[u] = __ldg(cd.words + idx);
+                        idv[u] = __ldg(cd.ids + idx);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + u * 32 >= nc) break;                      // warp-uniform
+                    int b = 0, id = 0;
+                    const bool ok = k3c_decode(col, w[u], idv[u], a.n_pairs, b, id) && ((bases >> b) & 1u);
+                    append(ok, b, id);
+                }
+            }
+        } else {
+            for (int i0 = 0; i0 < nc; i0 += 32) {
+                int b = 0, id = 0;
+                bool ok = (i0 + lane < nc) && candidate(i0 + lane, b, id);
+                ok = ok && ((bases >> b) & 1u);
+                append(ok, b, id);
+            }
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {

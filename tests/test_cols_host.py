@@ -40,7 +40,7 @@ def test_host_conversion_golden_and_column_order():
     # column order: ids of a column, read in slot order, are the pair ids of its covering segments in table order
     s = rd["seg_start"].astype(np.int64)
     e = s + rd["seg_len"].astype(np.int64) - 1
-    w = a["ids"].reshape(-1, cols.LANES, 4)
+    w = a["ids"].reshape(-1, cols.LANES, cols.UNIT)
     rng = np.random.default_rng(0)
     for c in rng.integers(0, (L + 7) // 8, 200):
         g, lane = c // cols.LANES, c % cols.LANES
