@@ -45,10 +45,10 @@ def build(force=False, verbose=False):
 
 
 def build_variant(name, defines):
-    """A/B build of the same sources with extra -D defines -> lib/libisb_<name>.so (select it with ISB_LIB_PATH)."""
+    """A/B build of the same sources with extra -D defines -> lib/libisbv_<name>.so (select it with ISB_LIB_PATH)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    out = os.path.join(LIB_DIR, "libisb_%s.so" % name)
+    out = os.path.join(LIB_DIR, "libisbv_%s.so" % name)   # "isbv": never matches libisb_synth.so in a cleanup glob
     subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + sources() + ["-o", out, "-lz"])
     return out
 

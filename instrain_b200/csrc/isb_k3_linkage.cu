@@ -200,11 +200,33 @@ __device__ __forceinline__ bool k3c_candidate(const isb_cols_dev &cd, const k3c_
     return k3c_decode(col, w, __ldg(cd.ids + idx), n_pairs, b, id);
 }
 
-__global__ void __launch_bounds__(256) k3c_site_split(k3_args a)
+// Everything the warp-per-site kernel needs to know about a site before it can request the site's words, computed by
+// one THREAD per site (site_pos -> flags / group offsets / split are dependent loads: here every site's chain is in
+// flight at once, the warp kernel then starts with ONE 32-byte load).
+struct __align__(16) k3c_site_rec {
+    int64_t base;        // index of slot 0 of the site's column list
+    int32_t depth;       // slots (incl. padding)
+    int32_t p;           // relative position
+    int32_t split;       // split index, -1 if the position is in no split
+    uint32_t bases_sh;   // bits 0-3: the site's allele set, bits 8-15: bit offset of its nibble
+    int32_t pad[2];
+};
+
+__global__ void __launch_bounds__(256) k3c_site_prep(k3_args a, isb_cols_dev cd, k3c_site_rec *__restrict__ recs)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.S) return;
-    a.meta[k].split = k3_site_split(a, (int64_t)a.site_pos[k] + a.start);
+    const int32_t p = a.site_pos[k];
+    const k3c_column col = k3c_site_column(cd, p);
+    k3c_site_rec r;
+    r.base = col.base;
+    r.depth = col.depth;
+    r.p = p;
+    r.split = k3_site_split(a, (int64_t)p + a.start);
+    r.bases_sh = (uint32_t)(a.site_flags[p] & 0xF) | ((uint32_t)col.sh << 8);
+    r.pad[0] = r.pad[1] = 0;
+    recs[k] = r;
+    a.meta[k].split = r.split;
 }
 
 __device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m, int na, unsigned bases, int b, int id,
@@ -223,12 +245,14 @@ __device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m
 }
 
 // Fused read-major front end (warp per site): gather the site's qualifying (pair id, base) entries from its candidate
-// segments into a per-warp shared-memory list, derive the pair-id window, allocate the bit rows with one atomicAdd on
-// the word counter, assemble them (shared-memory scratch for the common small windows) and store them.  The events
-// never touch global memory; sites with more qualifying entries than the list holds gather a second time.
+// segments (or, column words: from its column list) into a per-warp shared-memory list, derive the pair-id window,
+// assemble the bit rows (shared-memory scratch for the common small windows) and store them in the site's fixed row
+// slot.  The events never touch global memory; sites with more qualifying entries than the list holds gather a second
+// time.
 #define K3R_EV_CAP 320
 template <bool kCols>
 __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads_dev rd, isb_cols_dev cd,
+                                                            const k3c_site_rec *__restrict__ recs,
                                                             const int64_t *__restrict__ cand_lo,
                                                             const int32_t *__restrict__ n_cand, int64_t *__restrict__ row_off,
                                                             unsigned long long *__restrict__ row_words_total, int64_t row_cap)
@@ -241,12 +265,25 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
     const int64_t warp0 = ((int64_t)blockIdx.x * K3_THREADS + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * K3_THREADS) >> 5;
     for (int64_t k = warp0; k < a.S; k += n_warps) {
-        const int32_t p = a.site_pos[k];
-        const int64_t abs_pos = (int64_t)p + a.start;
-        const unsigned bases = a.site_flags[p] & 0xF;
-        const int na = __popc(bases);
         k3c_column col = {0, 0, 0};
-        if (kCols) col = k3c_site_column(cd, p);
+        int32_t p, split;
+        unsigned bases;
+        if (kCols) {                                                   // one 32-byte record (k3c_site_prep)
+            const int4 r0 = __ldg(reinterpret_cast<const int4 *>(recs + k));
+            const int4 r1 = __ldg(reinterpret_cast<const int4 *>(recs + k) + 1);
+            col.base = ((int64_t)(uint32_t)r0.x) | ((int64_t)r0.y << 32);
+            col.depth = r0.z;
+            p = r0.w;
+            split = r1.x;
+            bases = (unsigned)r1.y & 0xFu;
+            col.sh = ((unsigned)r1.y >> 8) & 0xFFu;
+        } else {
+            p = a.site_pos[k];
+            split = a.meta[k].split;                                   // set by k3r_site_cand
+            bases = a.site_flags[p] & 0xF;
+        }
+        const int64_t abs_pos = (int64_t)p + a.start;
+        const int na = __popc(bases);
         const int64_t clo = kCols ? 0 : cand_lo[k];
         const int nc = kCols ? col.depth : n_cand[k];
         auto candidate = [&](int i, int &b, int &id) -> bool {
@@ -301,14 +338,20 @@ __global__ void __launch_bounds__(K3_THREADS) k3r_site_rows(k3_args a, isb_reads
             idmin = min(idmin, __shfl_xor_sync(ISB_FULL, idmin, d));
             idmax = max(idmax, __shfl_xor_sync(ISB_FULL, idmax, d));
         }
-        isb_site_meta m = a.meta[k];                                   // .split was set by k3r_site_cand
+        isb_site_meta m;
+        m.split = split;
         m.ev_lo_rel = 0;
         m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
         m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
         const int n_words = (1 + 2 * na) * m.nw;
-        unsigned long long off = 0;
-        if (lane == 0 && n_words > 0) off = atomicAdd(row_words_total, (unsigned long long)n_words);
-        off = __shfl_sync(ISB_FULL, off, 0);
+        // Row storage: site k owns the fixed slot [k * K3_ROW_SCRATCH, + K3_ROW_SCRATCH) -- no allocation, nothing to
+        // wait for; only rows wider than a slot (deep coverage, many alleles) are allocated with an atomic behind the
+        // S fixed slots.
+        unsigned long long off = (unsigned long long)k * K3_ROW_SCRATCH;
+        if (n_words > K3_ROW_SCRATCH) {
+            if (lane == 0) off = (unsigned long long)a.S * K3_ROW_SCRATCH + atomicAdd(row_words_total, (unsigned long long)n_words);
+            off = __shfl_sync(ISB_FULL, off, 0);
+        }
         const bool fits = (int64_t)(off + n_words) <= row_cap;
         if (!fits) {                                                   // host grows the row storage and re-runs
             if (lane == 0) atomicOr(a.d_err, ISB_DEV_ERR_ROWBUF);
@@ -593,20 +636,24 @@ __global__ void __launch_bounds__(K3_THREADS) k3_enum_pairs(k3_args a)
     }
 }
 
-// Thread-per-site enumeration (the default; ISB_K3_ENUM=0 selects the warp-per-site kernel above): every site's partner
-// scan is in flight at once.  The warp-per-site kernel keeps ONE site per warp in flight and is bound by the latency of
+// Few-threads-per-site enumeration (the default; ISB_K3_ENUM=0 selects the warp-per-site kernel above): every site's
+// partner scan is in flight at once, split over K3_ENUM_LANES threads.  The warp-per-site kernel keeps ONE site per warp in flight and is bound by the latency of
 // its dependent loads (meta -> row offset -> `any` words): 71 us per 1e5 sites against ~45 us here (B200, K3 stage
 // 0.62 -> 0.57 ms per 2e7 positions).  Slots are allocated with one atomic per group of lanes that found a link in the
 // same trip.
+#ifndef K3_ENUM_LANES
+#define K3_ENUM_LANES 4              // threads per site: lane s of a site takes its partners k + 1 + s, k + 1 + s + LANES, ...
+#endif
 __global__ void __launch_bounds__(256) k3_enum_pairs_t(k3_args a)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = t / K3_ENUM_LANES;
     if (k >= a.S) return;
     const isb_site_meta mi = a.meta[k];
     if (mi.split < 0 || mi.nw == 0) return;
     const uint32_t *any_i = a.rows + a.row_off[k] - mi.wlo;
     const int i_hi = mi.wlo + mi.nw;
-    for (int64_t j = k + 1; j < a.S; ++j) {
+    for (int64_t j = k + 1 + (t % K3_ENUM_LANES); j < a.S; j += K3_ENUM_LANES) {
         const isb_site_meta mj = a.meta[j];
         if (mj.split != mi.split) break;
         const int lo = max(mi.wlo, mj.wlo), hi = min(i_hi, mj.wlo + mj.nw);
@@ -628,7 +675,10 @@ __global__ void __launch_bounds__(256) k3_enum_pairs_t(k3_args a)
     }
 }
 
-__global__ void __launch_bounds__(256) k3_pair_stats(k3_args a, int64_t n_pairs_listed)
+#ifndef K3_STATS_MINB
+#define K3_STATS_MINB 4              // 64 registers: 4 blocks of 256 threads per SM (measured: K3 stage 0.394 -> 0.367 ms per 2e7 positions)
+#endif
+__global__ void __launch_bounds__(256, K3_STATS_MINB) k3_pair_stats(k3_args a, int64_t n_pairs_listed)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs_listed) return;
@@ -799,6 +849,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
     }
     int64_t *cand_lo = nullptr;
     int32_t *n_cand = nullptr;
+    k3c_site_rec *recs = nullptr;
     const isb_reads_dev rd_none = {};
     const isb_cols_dev cd_none = {};
     if (!rd && !cd) {                                           // position-major columns
@@ -833,22 +884,26 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
             cand_lo = (int64_t *)ctx->buf[SL_RD_CAND].p;
             n_cand = (int32_t *)(cand_lo + S);
             k3r_site_cand<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *rd, cand_lo, n_cand);
-        } else {                                                // column words: only the split of each site is needed
-            k3c_site_split<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+        } else {                                                // column words: one record per site
+            if ((rc = isb_ensure(ctx, SL_RD_CAND, sizeof(k3c_site_rec) * (size_t)S))) return rc;
+            recs = (k3c_site_rec *)ctx->buf[SL_RD_CAND].p;
+            k3c_site_prep<<<(int)((S + 255) / 256), 256, 0, st>>>(a, *cd, recs);
         }
         ISB_LAUNCH_CHECK();
         // initial guess of the row storage (words per site); the fused kernel reports the exact need if it is too small
-        static const int rows_init = getenv("ISB_K3_ROWS_INIT") ? atoi(getenv("ISB_K3_ROWS_INIT")) : 48;
-        if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)S * (size_t)(rows_init > 0 ? rows_init : 1) + 64)))) return rc;
+        // row storage: S fixed slots + an initial guess of the overflow region (words per site; the fused kernel reports
+        // the exact need if it is too small)
+        static const int rows_init = getenv("ISB_K3_ROWS_INIT") ? atoi(getenv("ISB_K3_ROWS_INIT")) : 8;
+        if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)S * (size_t)(K3_ROW_SCRATCH + (rows_init > 0 ? rows_init : 1)) + 64)))) return rc;
     }
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (rd || cd) {                                         // fused gather + window + rows (no host sync needed)
             const int64_t row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
             a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
             ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
-            if (rd) k3r_site_rows<false><<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cd_none, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
+            if (rd) k3r_site_rows<false><<<grid_sites, K3_THREADS, 0, st>>>(a, *rd, cd_none, nullptr, cand_lo, n_cand, (int64_t *)ctx->buf[SL_ROW_OFF].p,
                                                                           ctx->d_counters + 4, row_cap);
-            else k3r_site_rows<true><<<grid_sites, K3_THREADS, 0, st>>>(a, rd_none, *cd, nullptr, nullptr, (int64_t *)ctx->buf[SL_ROW_OFF].p,
+            else k3r_site_rows<true><<<grid_sites, K3_THREADS, 0, st>>>(a, rd_none, *cd, recs, nullptr, nullptr, (int64_t *)ctx->buf[SL_ROW_OFF].p,
                                                                       ctx->d_counters + 4, row_cap);
             ISB_LAUNCH_CHECK();
         }
@@ -862,7 +917,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
         a.pair_j = a.pair_i + cap_pairs;
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, sizeof(unsigned long long), st));
         static const int enum_variant = getenv("ISB_K3_ENUM") ? atoi(getenv("ISB_K3_ENUM")) : 1;
-        if (enum_variant == 1) k3_enum_pairs_t<<<(int)((S + 255) / 256), 256, 0, st>>>(a);
+        if (enum_variant == 1) k3_enum_pairs_t<<<(int)((S * K3_ENUM_LANES + 255) / 256), 256, 0, st>>>(a);
         else k3_enum_pairs<<<grid_sites, K3_THREADS, 0, st>>>(a);
         ISB_LAUNCH_CHECK();
         ISB_CUDA(cudaMemcpyAsync(ctx->h_counters + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -871,7 +926,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
         if ((rd || cd) && (*ctx->h_err & ISB_DEV_ERR_ROWBUF)) { // row storage too small: grow to the counted size, redo
             if (*ctx->h_err & ~ISB_DEV_ERR_ROWBUF) return ISB_OK;   // another error is pending: let the caller report it
             ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), st));
-            const size_t need = (size_t)ctx->h_counters[4];
+            const size_t need = (size_t)S * K3_ROW_SCRATCH + (size_t)ctx->h_counters[4];   // fixed slots + counted overflow
             if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (need + need / 8 + 1024)))) return rc;
             continue;
         }

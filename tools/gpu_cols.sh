@@ -1,13 +1,12 @@
 #!/bin/bash
-# Column-word path: its GPU parity tests, then A/B bench runs (20 scaffolds) of build variants / switches.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_cols.sh r1t'
+# Full GPU parity suite, then A/B bench runs (20 scaffolds) of build variants / switches.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_cols.sh r1u'
 tag=${1:-cols}
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-timeout 700 python -m pytest tests/test_gpu_cols.py -x -q > $out/${tag}_pytest.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> $out/${tag}_pytest.log
 tail -5 $out/${tag}_pytest.log
-bash tools/gpu_ab.sh $tag "ISB_K1C_FUSE=0 -- " "ISB_LIB_PATH=instrain_b200/lib/libisb_rows4.so -- " \
-    "ISB_LIB_PATH=instrain_b200/lib/libisb_rows1.so -- " "ISB_LIB_PATH=instrain_b200/lib/libisb_mb8.so -- " \
-    "ISB_LIB_PATH=instrain_b200/lib/libisb_mb8.so ISB_K1C_FUSE=0 -- "
+bash tools/gpu_ab.sh $tag "ISB_LIB_PATH=instrain_b200/lib/libisbv_enum1.so -- " "ISB_LIB_PATH=instrain_b200/lib/libisbv_enum8.so -- " \
+    "ISB_LIB_PATH=instrain_b200/lib/libisbv_stats4.so -- " " -- --layout reads"
