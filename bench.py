@@ -447,6 +447,15 @@ def main():
                                        len(hr["nev_pos"]), p(hr["nev_pos"]), p(hr["nev_pair"]), len(hb["pair_mm"]),
                                        p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]), p(h["splits"]), Ms, 0)
 
+        from instrain_b200.reads import delta_reads
+        hd = delta_reads(hr, hb["ref_codes"])           # reference-delta transfer format: event bits + mismatch entries
+        hdp = {"pass": pin(hd["pass"]), "mis_word": pin(hd["mis_word"].view(np.int32)), "mis_code": pin(hd["mis_code"])}
+        dbatch = _cabi.IsbReadsDelta(int(hr["n_segs"]), p(hrp["seg_start"]), p(hrp["seg_len"]), p(hrp["seg_pair"]),
+                                     int(hd["n_units"]), p(hdp["pass"]), len(hd["mis_word"]), p(hdp["mis_word"]), p(hdp["mis_code"]),
+                                     int(hr["max_seg_len"]), 0, len(hr["nev_pos"]), p(hr["nev_pos"]), p(hr["nev_pair"]),
+                                     len(hb["pair_mm"]), p(h["pair_mm"]), 0, Ls, p(h["ref_codes"]), len(hb["splits"]),
+                                     p(h["splits"]), Ms, 0)
+
         def time_call(fn, b):
             ts = []
             for it in range(2 + 3):
@@ -464,8 +473,9 @@ def main():
         dt_pk = time_call(lib.isb_profile_batch_packed, pbatch)
         dt_rd = time_call(lib.isb_profile_reads, rbatch)
         dt_rc = time_call(lib.isb_profile_reads_compact, cbatch)
-        via_reads = use_reads or use_cols             # host buffers cross PCIe in the compact read-major format either way
-        main_fn, main_b, dt = (lib.isb_profile_reads_compact, cbatch, dt_rc) if via_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
+        dt_rdl = time_call(lib.isb_profile_reads_delta, dbatch)
+        via_reads = use_reads or use_cols             # host buffers cross PCIe in a read-major transfer format either way
+        main_fn, main_b, dt = (lib.isb_profile_reads_delta, dbatch, dt_rdl) if via_reads else (lib.isb_profile_batch_packed, pbatch, dt_pk)
 
         # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
         # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
@@ -501,17 +511,19 @@ def main():
         h2d_pk = pk["n_events"] + (Ls + 1) * 8 + Ls * 4 + len(pk["esc_evt"]) * 12 + common
         h2d_rd = hr["n_words"] * 4 + hr["n_segs"] * (4 + 2 + 4 + 8) + common
         h2d_rc = hc["n_units"] * 3 + hr["n_segs"] * (4 + 2 + 4) + common
+        h2d_rdl = hd["n_units"] + len(hd["mis_word"]) * 5 + hr["n_segs"] * (4 + 2 + 4) + common
         d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
         best = min(dt, dt_pipe) if dt_pipe else dt
-        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rc if via_reads else h2d_pk),
+        e2e = {"value": Ls / best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_rdl if via_reads else h2d_pk),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": best * 1e3,
-               "api": ("isb_profile_reads_compact (read-major aligned segments in the compact transfer format: 3 bits per "
-                       "aligned base, K0r expands on the device)" if via_reads else
+               "api": ("isb_profile_reads_delta (read-major aligned segments in the reference-delta transfer format: event bits "
+                       "+ one entry per base that differs from the reference, K0d rebuilds the stream on the device)" if via_reads else
                        "isb_profile_batch_packed (packed transfer format, K0 expands on the device)"),
                "single_context": {"value": Ls / dt, "ms_per_step": dt * 1e3},
                "two_contexts_pipelined": ({"value": Ls / dt_pipe, "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),
                "slice": "%d of the %d scaffolds per step, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, args.scaffolds),
                "other_host_formats": {
+                   "read_major_delta": {"value": Ls / dt_rdl, "ms_per_step": dt_rdl * 1e3, "h2d_bytes_per_step": int(h2d_rdl)},
                    "read_major_compact": {"value": Ls / dt_rc, "ms_per_step": dt_rc * 1e3, "h2d_bytes_per_step": int(h2d_rc)},
                    "read_major_segments": {"value": Ls / dt_rd, "ms_per_step": dt_rd * 1e3, "h2d_bytes_per_step": int(h2d_rd)},
                    "packed_events": {"value": Ls / dt_pk, "ms_per_step": dt_pk * 1e3, "h2d_bytes_per_step": int(h2d_pk)},

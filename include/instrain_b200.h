@@ -290,6 +290,45 @@ typedef struct {
 
 int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const isb_params *prm, isb_result *out);
 
+/* ---- READ-MAJOR input, reference-delta TRANSFER format ------------------------------------------------------------------ */
+/* The smallest form of the same aligned segments for batches that cross PCIe: reads are almost everywhere identical to
+ * the reference, which the call receives anyway.  Per unit of 8 bases (units exactly as in isb_reads_compact) only the
+ * event bits `pass` travel (1 byte); every passing A/C/T/G base that DIFFERS from the reference base at its position
+ * (or whose reference base is not A/C/T/G) is listed once: mis_word = index of its word in the canonical nibble stream
+ * (1 + unit index + segment index: one leading zero word, one separator per segment), mis_code = bits 4-6 the nibble
+ * position in the word, bits 0-3 the XOR of the one-hot codes of the reference base (0 if not A/C/T/G) and of the read
+ * base.  ~1.1 bits per aligned base + 5 bytes per mismatch instead of 3 bits per base: about half the bytes of
+ * isb_reads_compact at 1 % divergence.  K0d (isb_k0r_expand.cu) rebuilds the nibble stream on the device (reference
+ * codes masked by the event bits, then the listed nibbles flipped), then K1r -> K2 -> K3 run as in isb_profile_reads:
+ * results are identical. */
+typedef struct {
+    int64_t n_segs;
+    const int32_t *seg_start;   /* [n_segs] ascending */
+    const uint16_t *seg_len;    /* [n_segs] 1 .. max_seg_len */
+    const int32_t *seg_pair;    /* [n_segs] */
+    int64_t n_units;            /* sum of ceil((seg_start % 8 + seg_len) / 8) */
+    const uint8_t *pass;        /* [n_units] */
+    int64_t n_mis;
+    const uint32_t *mis_word;   /* [n_mis] */
+    const uint8_t *mis_code;    /* [n_mis] */
+    int32_t max_seg_len;
+    int32_t pad;
+    int64_t n_nev;
+    const int32_t *nev_pos;
+    const int32_t *nev_pair;
+    int64_t n_pairs;
+    const uint8_t *pair_mm;     /* [n_pairs]; may be NULL when M == 1 */
+    int32_t start;
+    int32_t L;
+    const uint8_t *ref;         /* [L] */
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t M;
+    int32_t pad2;
+} isb_reads_delta;
+
+int isb_profile_reads_delta(isb_ctx *ctx, const isb_reads_delta *in, const isb_params *prm, isb_result *out);
+
 /* ---- COLUMN-WORD input: the pileup-major form of the aligned segments ------------------------------------------------- */
 /* The same one-hot nibble words as isb_reads_batch (one 32-bit word = the codes of 8 consecutive, 8-aligned batch
  * coordinates of ONE read), stored where the pileup needs them instead of where the read is: per COLUMN WORD (8

@@ -36,7 +36,7 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
-           "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact",
+           "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact", "isb_profile_reads_delta",
            "isb_cols_from_reads", "isb_cols_from_reads_host", "isb_pileup_cols", "isb_profile_cols",
            "isb_scaffold_summary", "isb_launch_count",
            "isb_enable_timing", "isb_stage_times", "isb_selftest_division",
@@ -80,6 +80,15 @@ class IsbReadsCompact(C.Structure):
                 ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p), ("start", C.c_int32),
                 ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32), ("splits", C.c_void_p),
                 ("M", C.c_int32), ("pad2", C.c_int32)]
+
+
+class IsbReadsDelta(C.Structure):
+    _fields_ = [("n_segs", C.c_int64), ("seg_start", C.c_void_p), ("seg_len", C.c_void_p), ("seg_pair", C.c_void_p),
+                ("n_units", C.c_int64), ("pass_", C.c_void_p), ("n_mis", C.c_int64), ("mis_word", C.c_void_p),
+                ("mis_code", C.c_void_p), ("max_seg_len", C.c_int32), ("pad", C.c_int32), ("n_nev", C.c_int64),
+                ("nev_pos", C.c_void_p), ("nev_pair", C.c_void_p), ("n_pairs", C.c_int64), ("pair_mm", C.c_void_p),
+                ("start", C.c_int32), ("L", C.c_int32), ("ref", C.c_void_p), ("n_splits", C.c_int32),
+                ("splits", C.c_void_p), ("M", C.c_int32), ("pad2", C.c_int32)]
 
 
 class IsbColsBatch(C.Structure):
@@ -160,6 +169,8 @@ def load():
     L.isb_profile_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     L.isb_profile_reads_compact.restype = C.c_int
     L.isb_profile_reads_compact.argtypes = [vp, C.POINTER(IsbReadsCompact), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    L.isb_profile_reads_delta.restype = C.c_int
+    L.isb_profile_reads_delta.argtypes = [vp, C.POINTER(IsbReadsDelta), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     L.isb_cols_from_reads.restype = C.c_int
     L.isb_cols_from_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), vp, C.POINTER(i64), vp, vp, i64]
     L.isb_cols_from_reads_host.restype = i64

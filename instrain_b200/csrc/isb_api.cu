@@ -692,6 +692,55 @@ int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const i
                           in->n_splits, d_splits, prm, out);
 }
 
+// Reference-delta transfer format: copy the event bits and the mismatch list, rebuild the stream on the device (K0d), then
+// the same K1r -> K2 -> K3 as isb_profile_reads.
+int isb_profile_reads_delta(isb_ctx *ctx, const isb_reads_delta *in, const isb_params *prm, isb_result *out)
+{
+    if (!ctx || !in || !prm || !out) return ISB_ERR_ARG;
+    const int32_t L = in->L;
+    const int M = in->M;
+    int rc = check_common(ctx, L, M);
+    if (rc) return rc;
+    if (!in->ref || (M > 1 && !in->pair_mm) || (in->n_splits > 0 && !in->splits))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_delta: null input pointer");
+    if (in->n_segs < 0 || in->n_units < 0 || in->n_mis < 0 || (in->n_segs > 0 && (!in->seg_start || !in->seg_len || !in->seg_pair)) ||
+        (in->n_units > 0 && !in->pass) || (in->n_mis > 0 && (!in->mis_word || !in->mis_code)) || in->n_nev < 0 ||
+        (in->n_nev > 0 && (!in->nev_pos || !in->nev_pair)))
+        return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_delta: null or negative-sized column");
+    if (in->start & 7) return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_delta: start must be a multiple of 8");
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream));
+    isb_reads_dev rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.n_segs = in->n_segs;
+    rd.max_seg_len = in->max_seg_len;
+    rd.n_nev = in->n_nev;
+    rd.n_words = (1 + in->n_units + in->n_segs + 3) & ~(int64_t)3;
+    if (rd.n_words > 0xffffffffll) return isb_fail(ctx, ISB_ERR_ARG, "isb_profile_reads_delta: batch too large for 32-bit word indices");
+    const uint8_t *d_ps, *d_mc, *d_mm, *d_ref; const uint32_t *d_mw; const int32_t *d_splits;
+    if ((rc = stage_in(ctx, SL_RD_START, in->seg_start, (size_t)in->n_segs, &rd.seg_start))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_LEN, in->seg_len, (size_t)in->n_segs, &rd.seg_len))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_PAIR, in->seg_pair, (size_t)in->n_segs, &rd.seg_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_RC_PASS, in->pass, (size_t)in->n_units, &d_ps))) return rc;
+    if ((rc = stage_in(ctx, SL_RC_MISW, in->mis_word, (size_t)in->n_mis, &d_mw))) return rc;
+    if ((rc = stage_in(ctx, SL_RC_MISC, in->mis_code, (size_t)in->n_mis, &d_mc))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPOS, in->nev_pos, (size_t)in->n_nev, &rd.nev_pos))) return rc;
+    if ((rc = stage_in(ctx, SL_RD_NPAIR, in->nev_pair, (size_t)in->n_nev, &rd.nev_pair))) return rc;
+    if ((rc = stage_in(ctx, SL_PAIR_MM, in->pair_mm, (size_t)in->n_pairs, &d_mm))) return rc;
+    if ((rc = stage_in(ctx, SL_REF, in->ref, (size_t)L, &d_ref))) return rc;
+    if ((rc = stage_in(ctx, SL_SPLITS, in->splits, (size_t)in->n_splits * 2, &d_splits))) return rc;
+    if ((rc = isb_ensure(ctx, SL_RD_WORD, sizeof(int64_t) * ((size_t)in->n_segs + 2)))) return rc;
+    if ((rc = isb_ensure(ctx, SL_RD_WORDS, sizeof(uint32_t) * ((size_t)rd.n_words + 4)))) return rc;
+    int64_t *d_seg_word = (int64_t *)ctx->buf[SL_RD_WORD].p;
+    uint32_t *d_words = (uint32_t *)ctx->buf[SL_RD_WORDS].p;
+    if ((rc = isb_k0d_launch(ctx, in->n_segs, rd.seg_start, rd.seg_len, in->n_units, d_ps, d_ref, in->start, L, in->n_mis, d_mw, d_mc,
+                             d_seg_word, rd.n_words, d_words))) return rc;
+    rd.seg_word = d_seg_word;
+    rd.words = d_words;
+    return profile_device(ctx, &rd, nullptr, 0, nullptr, nullptr, nullptr, nullptr, in->n_pairs, d_mm, in->start, L, M, d_ref,
+                          in->n_splits, d_splits, prm, out);
+}
+
 // host or device column-word batch -> device pointers
 static int stage_cols(isb_ctx *ctx, const isb_cols_batch *in, isb_cols_dev *cd, const uint8_t **d_mm)
 {

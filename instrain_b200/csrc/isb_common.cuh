@@ -25,7 +25,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_K3_TILE_OFF, SL_PAIRS,
     SL_K4_CUM, SL_K4_CLON, SL_K4_STATE, SL_K4_HIST, SL_K4_OFF, SL_K4_OUT,
     SL_RD_START, SL_RD_LEN, SL_RD_PAIR, SL_RD_WORD, SL_RD_WORDS, SL_RD_BOUNDS, SL_RD_NPOS, SL_RD_NPAIR,         // read-major batch (K1r inputs)
-    SL_RC_BASE2, SL_RC_PASS,                                                       // compact transfer format (K0r inputs)
+    SL_RC_BASE2, SL_RC_PASS, SL_RC_MISW, SL_RC_MISC,                               // compact / delta transfer formats (K0r / K0d inputs)
     SL_RD_CAND, SL_RD_EVOFF, SL_RD_EVB, SL_RD_EVQ, SL_RD_EVID,                          // K3 site events from segments
     SL_CD_OFF, SL_CD_WORDS, SL_CD_IDS, SL_CD_CNT,                                  // column-word batch (K1c inputs) + conversion scratch
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
@@ -180,6 +180,9 @@ int isb_k4_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *covT, const flo
 int isb_tile_offsets(isb_ctx *ctx, const int32_t *ref_pos, int64_t n, int32_t start, int32_t L, int tp, int n_tiles);
 int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, int64_t n_units, const uint16_t *base2,
                    const uint8_t *pass, int64_t *seg_word, int64_t n_words, uint32_t *words);
+int isb_k0d_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, int64_t n_units,
+                   const uint8_t *pass, const uint8_t *ref, int32_t start, int32_t L, int64_t n_mis, const uint32_t *mis_word,
+                   const uint8_t *mis_code, int64_t *seg_word, int64_t n_words, uint32_t *words);
 int isb_k0_launch(isb_ctx *ctx, int64_t n, const int64_t *pos_off, const int32_t *id_base, const uint8_t *bqd,
                   int64_t n_esc, const int64_t *esc_evt, const int32_t *esc_id, int32_t start, int32_t L, int qpass,
                   int32_t *ref_pos, uint8_t *base, uint8_t *qual, int32_t *read_id);

@@ -212,6 +212,13 @@ class Engine:
         if cols is not None:                        # column words (instrain_b200.cols)
             batch = self._cols_batch(cols, pair_mm, start, L, ref_codes, splits, M)
             entry = self.lib.isb_profile_cols
+        elif reads is not None and "mis_word" in reads:   # reference-delta transfer format (instrain_b200.reads.delta_reads)
+            batch = _cabi.IsbReadsDelta(int(reads["n_segs"]), p(reads["seg_start"]), p(reads["seg_len"]), p(reads["seg_pair"]),
+                                        int(reads["n_units"]), p(reads["pass"]), len(reads["mis_word"]), p(reads["mis_word"]),
+                                        p(reads["mis_code"]), int(reads["max_seg_len"]), 0, len(reads["nev_pos"]),
+                                        p(reads["nev_pos"]), p(reads["nev_pair"]), len(pair_mm), p(pair_mm), start, L,
+                                        p(ref_codes), len(splits), p(splits), M, 0)
+            entry = self.lib.isb_profile_reads_delta
         elif reads is not None and "base2" in reads:  # compact transfer format (instrain_b200.reads.compact_reads)
             batch = _cabi.IsbReadsCompact(int(reads["n_segs"]), p(reads["seg_start"]), p(reads["seg_len"]),
                                           p(reads["seg_pair"]), int(reads["n_units"]), p(reads["base2"]), p(reads["pass"]),

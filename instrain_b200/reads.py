@@ -138,6 +138,77 @@ def compact_reads(rd):
     return out
 
 
+def _units(rd):
+    """(unit count per segment, flat unit -> segment index, flat unit -> index inside its segment, source word index)."""
+    seg_len = rd["seg_len"].astype(np.int64)
+    nw = ((rd["seg_start"].astype(np.int64) & 7) + seg_len + 7) // 8
+    n_units = int(nw.sum())
+    seg = np.repeat(np.arange(len(nw)), nw)
+    k = np.arange(n_units, dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
+    src = np.repeat(np.asarray(rd["seg_word"], dtype=np.int64), nw) + k
+    return nw, seg, k, src
+
+
+def delta_reads(rd, ref_codes, start=0):
+    """Read-major batch -> reference-delta TRANSFER format (include/instrain_b200.h, isb_reads_delta): per unit of 8 bases
+    the event bits only; per passing base that differs from the reference one (mis_word, mis_code) entry.  ref_codes[i] is
+    the reference code (0..3 = A,C,T,G, 4 = other) of batch coordinate start + i."""
+    ref_codes = np.asarray(ref_codes, dtype=np.uint8)
+    nw, seg, k, src = _units(rd)
+    n_units = len(seg)
+    w = rd["words"][src].astype(np.uint32)
+    ps = np.zeros(n_units, dtype=np.uint8)
+    pos0 = (np.repeat(rd["seg_start"].astype(np.int64) & ~np.int64(7), nw) + 8 * k) - start    # ref index of nibble 0
+    canon_word = 1 + np.arange(n_units, dtype=np.int64) + seg                                  # canonical stream index
+    mis_word, mis_code = [], []
+    L = len(ref_codes)
+    for t in range(8):
+        nib = (w >> np.uint32(4 * t)) & np.uint32(15)
+        has = nib != 0
+        ps |= has.astype(np.uint8) << np.uint8(t)
+        r = np.full(n_units, 4, dtype=np.uint8)
+        inside = (pos0 + t >= 0) & (pos0 + t < L)
+        r[inside] = ref_codes[(pos0 + t)[inside]]
+        ref_hot = np.where(r < 4, np.uint32(1) << np.minimum(r, 3).astype(np.uint32), 0).astype(np.uint32)
+        diff = has & (nib != ref_hot)
+        mis_word.append(canon_word[diff])
+        mis_code.append(((nib[diff] ^ ref_hot[diff]) | np.uint32(t << 4)).astype(np.uint8))
+    out = {k_: rd[k_] for k_ in ("n_segs", "seg_start", "seg_len", "seg_pair", "max_seg_len", "nev_pos", "nev_pair")}
+    mw = np.concatenate(mis_word) if mis_word else np.zeros(0, np.int64)
+    if len(mw) and mw.max() > 0xffffffff:
+        raise ValueError("batch too large for 32-bit word indices")
+    out.update(n_units=n_units, mis_word=mw.astype(np.uint32), mis_code=np.concatenate(mis_code) if mis_code else np.zeros(0, np.uint8),
+               **{"pass": ps})
+    return out
+
+
+def delta_to_words(dl, ref_codes, start=0):
+    """What K0d computes (numpy restatement, for the CPU round-trip test): the canonical nibble stream of a delta batch
+    -> (seg_word, n_words, words)."""
+    ref_codes = np.asarray(ref_codes, dtype=np.uint8)
+    s = dl["seg_start"].astype(np.int64)
+    nw = ((s & 7) + dl["seg_len"].astype(np.int64) + 7) // 8
+    n = len(s)
+    seg_word = 1 + (np.cumsum(nw) - nw) + np.arange(n)
+    n_words = (1 + int(nw.sum()) + n + 3) // 4 * 4
+    words = np.zeros(n_words, dtype=np.uint32)
+    seg = np.repeat(np.arange(n), nw)
+    k = np.arange(int(nw.sum()), dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
+    pos0 = (np.repeat(s & ~np.int64(7), nw) + 8 * k) - start
+    L = len(ref_codes)
+    w = np.zeros(len(seg), dtype=np.uint32)
+    for t in range(8):
+        r = np.full(len(seg), 4, dtype=np.uint8)
+        inside = (pos0 + t >= 0) & (pos0 + t < L)
+        r[inside] = ref_codes[(pos0 + t)[inside]]
+        hot = np.where(r < 4, np.uint32(1) << np.minimum(r, 3).astype(np.uint32), 0).astype(np.uint32)
+        w |= np.where((dl["pass"] >> np.uint8(t)) & 1, hot, 0).astype(np.uint32) << np.uint32(4 * t)
+    words[np.repeat(seg_word, nw) + k] = w
+    np.bitwise_xor.at(words, dl["mis_word"].astype(np.int64),
+                      (dl["mis_code"].astype(np.uint32) & 15) << (4 * (dl["mis_code"].astype(np.uint32) >> 4)))
+    return seg_word, n_words, words
+
+
 def concat_streams(parts):
     """Scaffold-wise packer outputs (BamPacker.pack_scaffold_reads; coordinates / pair ids already offset) -> one batch:
     one leading zero word + the scaffolds' streams + zero padding to a multiple of 4 words."""

@@ -200,6 +200,42 @@ def test_compact_transfer_format(eng, which, null_lut):
     check_reads(eng, batch, null_lut, rd=reads.compact_reads(rd))
 
 
+@pytest.mark.parametrize("which", ["G1", "synth_mm", "synth_m1", "synth_n"])
+def test_delta_transfer_format(eng, which, null_lut):
+    """isb_profile_reads_delta (event bits + one entry per base that differs from the reference; K0d rebuilds the stream
+    on the device from the reference) gives the oracle's tables: real reads with indels, odd block sizes and short
+    pieces, deep coverage, non-ACGT read bases and an N in the reference."""
+    if which == "G1":
+        batch, _ = load_batch("G1")
+        rd = reads.events_to_reads(batch)
+    elif which == "synth_mm":
+        batch = synth.make_batch(30000, 50, 0.01, 20260102, n_scaffolds=2, skip_mm=False)
+        rd = reads.events_to_reads(batch, max_len=37, odd_blocks=True)
+    elif which == "synth_m1":
+        batch = synth.make_batch(20000, 300, 0.02, 5, skip_mm=True)
+        rd = reads.events_to_reads(batch, max_len=150)
+    else:
+        batch = synth.make_batch(12001, 100, 0.05, 20260105, skip_mm=False, n_frac=0.002)   # L not a multiple of 8
+        rd = reads.events_to_reads(batch)
+        batch["ref_codes"] = batch["ref_codes"].copy()
+        batch["ref_codes"][100:140] = 4                                          # reference N run: every base is a mismatch
+    check_reads(eng, batch, null_lut, rd=reads.delta_reads(rd, batch["ref_codes"]))
+
+
+def test_delta_format_rejects_bad_entries(eng, null_lut):
+    from instrain_b200 import _cabi
+    batch = synth.make_batch(5000, 30, 0.01, 1, skip_mm=True)
+    dl = reads.delta_reads(reads.events_to_reads(batch), batch["ref_codes"])
+    bad = dict(dl); bad["mis_word"] = dl["mis_word"].copy(); bad["mis_word"][0] = 0xfffffff0     # beyond the stream
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=bad)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+    bad = dict(dl); bad["n_units"] = dl["n_units"] - 3
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=bad)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+
+
 def test_compact_format_rejects_inconsistent_units(eng, null_lut):
     from instrain_b200 import _cabi
     batch = synth.make_batch(5000, 30, 0.01, 1, skip_mm=True)
