@@ -17,7 +17,8 @@ a "step" = isb_profile_cols (K1c streaming pileup with the SNV call fused into i
 With --layout reads a short secondary run of the event layout on --also-events scaffolds is reported beside.
 
 Multi-GPU: scaffolds are independent, so every rank profiles its own 100-scaffold shard (weak scaling, no data-path
-collective) and the final SNV / linkage tables are gathered to rank 0 over NCCL inside the timed step.
+collective) and the final SNV / linkage tables are gathered to rank 0 over NCCL inside the timed region; the gather of
+step i runs on a side stream underneath the kernels of step i + 1 (two alternating sets of row buffers).
 """
 import argparse
 import ctypes as C
@@ -218,14 +219,25 @@ def main():
     flags = torch.empty(Ltot, dtype=torch.uint8, device=dev)
     snv_cap, ld_cap = max(1 << 16, Ltot // 16), max(1 << 18, Ltot // 2)
     res = None
+    # world > 1: two sets of row buffers, alternated, so that the NCCL gather of step i (side stream) overlaps the kernels
+    # of step i + 1; a set is reused only after its gather has completed (event).
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    sets, gather_done = [], [None, None]
 
     def alloc_rows():
         nonlocal snv, ld, res
-        snv = torch.empty(snv_cap * 32, dtype=torch.uint8, device=dev)
-        ld = torch.empty(ld_cap * 48, dtype=torch.uint8, device=dev)
+        if side is not None:
+            side.synchronize()                           # no gather may still read the buffers being replaced
+        sets.clear()
         lean = use_cols and not args.keep_counts         # counts / nmask not requested: K1c runs the SNV call in its epilogue at M = 1
-        res = _cabi.IsbResult(None if lean else p(counts), None if lean else p(nmask), p(covT), p(clonT), p(flags), p(snv), snv_cap,
-                              p(ld), ld_cap, 0, 0, 0, 0)
+        for _ in range(2 if world > 1 else 1):
+            s_ = torch.empty(snv_cap * 32, dtype=torch.uint8, device=dev)
+            l_ = torch.empty(ld_cap * 48, dtype=torch.uint8, device=dev)
+            r_ = _cabi.IsbResult(None if lean else p(counts), None if lean else p(nmask), p(covT), p(clonT), p(flags), p(s_), snv_cap,
+                                 p(l_), ld_cap, 0, 0, 0, 0)
+            sets.append((s_, l_, r_))
+        snv, ld, res = sets[0]
+        gather_done[0] = gather_done[1] = None
 
     snv = ld = None
     alloc_rows()
@@ -249,29 +261,45 @@ def main():
         entry = lib.isb_profile_batch
     prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
 
-    def gather_tables():
-        """NCCL gather of the final SNV / linkage rows to rank 0 (the only collective of the job)."""
+    def gather_tables(cur):
+        """NCCL gather of the final SNV / linkage rows of set `cur` to rank 0 (the only collective of the job), enqueued on
+        the side stream: it runs underneath the next step's kernels."""
         if world == 1:
             return
-        mine = torch.tensor([res.n_snv, res.n_ld], dtype=torch.int64, device=dev)
-        allc = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        mx = torch.stack(allc).max(0).values.tolist()
-        for buf, rowb, m in ((snv, 32, mx[0]), (ld, 48, mx[1])):
-            view = buf[:m * rowb]
-            dst = [torch.empty_like(view) for _ in range(world)] if rank == 0 else None
-            dist.gather(view, dst, dst=0)
+        s_, l_, r_ = sets[cur]
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            mine = torch.tensor([r_.n_snv, r_.n_ld], dtype=torch.int64, device=dev)
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            mx = torch.stack(allc).max(0).values.tolist()
+            for buf, rowb, m in ((s_, 32, mx[0]), (l_, 48, mx[1])):
+                view = buf[:m * rowb]
+                dst = [torch.empty_like(view) for _ in range(world)] if rank == 0 else None
+                dist.gather(view, dst, dst=0)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            gather_done[cur] = ev
+
+    step_no = 0
 
     def step():
-        nonlocal snv_cap, ld_cap
-        rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+        nonlocal snv_cap, ld_cap, step_no, res
+        cur = step_no % len(sets)
+        if gather_done[cur] is not None:
+            stream.wait_event(gather_done[cur])          # this set's rows were gathered two steps ago: wait for that only
+        r_ = sets[cur][2]
+        rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(r_))
         if rc == _cabi.ISB_ERR_CAPACITY:
-            snv_cap, ld_cap = max(snv_cap, int(res.n_snv) + 1024), max(ld_cap, int(res.n_ld) + 1024)
+            snv_cap, ld_cap = max(snv_cap, int(r_.n_snv) + 1024), max(ld_cap, int(r_.n_ld) + 1024)
             alloc_rows()
-            rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(res))
+            cur, r_ = 0, sets[0][2]
+            rc = entry(ctx, C.byref(batch), C.byref(prm), C.byref(r_))
         if rc != 0:
             raise RuntimeError(lib.isb_last_error(ctx).decode())
-        gather_tables()
+        res = r_
+        gather_tables(cur)
+        step_no += 1
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -287,6 +315,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    if side is not None:
+        stream.wait_stream(side)                         # the last gathers belong to the timed region
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:

@@ -80,47 +80,49 @@ int isb_k0r_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const
 // ~1.1 bits + change per aligned base instead of 3.  K0d rebuilds the same nibble stream as K0r: every unit gets the
 // one-hot codes of its 8 reference bases masked by the event bits, then the entries flip the differing nibbles.
 
-// one warp per segment, lanes over its units (as k0r_expand_units); ref is indexed by batch coordinate - start
+// One THREAD per segment walks the segment's units (<= 33): the three table loads of every segment are in flight at
+// once and the unit loads of a thread are independent of each other (unrolled: issued in batches).  The first version
+// (one warp per segment, lanes over units, grid-stride) ran 35 dependent table -> unit -> store chains per warp with
+// 20 of 32 lanes busy: 173 us per 1e8 aligned bases, more than the whole K1r -> K2 -> K3 that follows it.
+// ref is indexed by batch coordinate - start.
 __global__ void __launch_bounds__(256)
 k0d_expand_units(int64_t n_segs, const int32_t *__restrict__ seg_start, const uint16_t *__restrict__ seg_len,
                  const int64_t *__restrict__ seg_word, int64_t n_units, const uint8_t *__restrict__ pass,
                  const uint8_t *__restrict__ ref, int32_t start, int32_t L, int64_t n_words, uint32_t *__restrict__ words,
                  unsigned int *__restrict__ d_err)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_segs) return;
     const bool ref_aligned = (reinterpret_cast<uintptr_t>(ref) & 7) == 0;
-    for (int64_t i = warp0; i < n_segs; i += n_warps) {
-        const int32_t s = seg_start[i];
-        const int nw = ((s & 7) + (int)seg_len[i] + 7) >> 3;
-        const int64_t w0 = seg_word[i];
-        const int64_t u0 = w0 - 1 - i;
-        const int64_t r0 = (int64_t)(s & ~7) - start;                      // reference index of the first unit's first base
-        if (u0 < 0 || u0 + nw > n_units || w0 + nw + 1 > n_words || r0 < 0 || r0 + 8 * (int64_t)(nw - 1) >= L) {
-            if (lane == 0) atomicOr(d_err, ISB_DEV_ERR_SEG);                // table, unit arrays or range disagree (uniform)
-            continue;
-        }
-        for (int k = lane; k < nw; k += 32) {
-            const uint32_t ps = pass[u0 + k];
-            const int64_t r = r0 + 8 * (int64_t)k;
-            uint32_t w = 0u;
-            if (ref_aligned && r + 8 <= L) {                                // the unit's 8 reference bases in one load
-                const uint2 rr = __ldg(reinterpret_cast<const uint2 *>(ref + r));
+    const int32_t s = seg_start[i];
+    const int nw = ((s & 7) + (int)seg_len[i] + 7) >> 3;
+    const int64_t w0 = seg_word[i];
+    const int64_t u0 = w0 - 1 - i;
+    const int64_t r0 = (int64_t)(s & ~7) - start;                          // reference index of the first unit's first base
+    if (u0 < 0 || u0 + nw > n_units || w0 + nw + 1 > n_words || r0 < 0 || r0 + 8 * (int64_t)(nw - 1) >= L) {
+        atomicOr(d_err, ISB_DEV_ERR_SEG);                                   // table, unit arrays or range disagree
+        return;
+    }
+#pragma unroll 4
+    for (int k = 0; k < nw; ++k) {
+        const uint32_t ps = __ldg(pass + u0 + k);
+        const int64_t r = r0 + 8 * (int64_t)k;
+        uint32_t w = 0u;
+        if (ref_aligned && r + 8 <= L) {                                    // the unit's 8 reference bases in one load
+            const uint2 rr = __ldg(reinterpret_cast<const uint2 *>(ref + r));
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const uint32_t c = ((t < 4 ? rr.x : rr.y) >> (8 * (t & 3))) & 0xffu;
-                    if (((ps >> t) & 1u) && c < 4u) w |= (1u << c) << (4 * t);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const uint32_t c = (r + t < L) ? (uint32_t)__ldg(ref + r + t) : 4u;
-                    if (((ps >> t) & 1u) && c < 4u) w |= (1u << c) << (4 * t);
-                }
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t c = ((t < 4 ? rr.x : rr.y) >> (8 * (t & 3))) & 0xffu;
+                if (((ps >> t) & 1u) && c < 4u) w |= (1u << c) << (4 * t);
             }
-            words[w0 + k] = w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t c = (r + t < L) ? (uint32_t)__ldg(ref + r + t) : 4u;
+                if (((ps >> t) & 1u) && c < 4u) w |= (1u << c) << (4 * t);
+            }
         }
+        words[w0 + k] = w;
     }
 }
 
@@ -154,9 +156,8 @@ int isb_k0d_launch(isb_ctx *ctx, int64_t n_segs, const int32_t *seg_start, const
     SegWordSink sink{seg_word};
     scan_scatter<<<nb, SCAN_THREADS, 0, st>>>(uf, n_segs, block_sums, sink);
     ISB_LAUNCH_CHECK();
-    const int64_t blocks = (n_segs * 32 + 255) / 256;
-    const int grid = (int)(blocks < (int64_t)ctx->sm_count * 16 ? blocks : (int64_t)ctx->sm_count * 16);
-    k0d_expand_units<<<grid, 256, 0, st>>>(n_segs, seg_start, seg_len, seg_word, n_units, pass, ref, start, L, n_words, words, ctx->d_err);
+    k0d_expand_units<<<(unsigned)((n_segs + 255) / 256), 256, 0, st>>>(n_segs, seg_start, seg_len, seg_word, n_units, pass, ref, start, L,
+                                                                       n_words, words, ctx->d_err);
     ISB_LAUNCH_CHECK();
     if (n_mis > 0) {
         k0d_apply_mismatches<<<(unsigned)((n_mis + 255) / 256), 256, 0, st>>>(n_mis, mis_word, mis_code, n_words, words, ctx->d_err);
