@@ -328,6 +328,14 @@ typedef struct {
 } isb_reads_delta;
 
 int isb_profile_reads_delta(isb_ctx *ctx, const isb_reads_delta *in, const isb_params *prm, isb_result *out);
+/* The encoder on the host (C++, no GPU; what the host packer runs after isb_pack_scaffold_reads): pass[n_units] and the
+ * mismatch entries of a read-major batch against ref[L] (reference codes of the batch coordinates start .. start + L).
+ * Returns the number of entries -- only the first cap_mis are stored (call again with larger buffers when it is larger;
+ * mis_word / mis_code may be NULL for a counting call) -- or -1 when the segments violate the layout rules of
+ * isb_reads_batch or n_units is not the sum of their unit counts. */
+int64_t isb_reads_delta_host(int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len, const int64_t *seg_word,
+                             const uint32_t *words_in, int64_t n_words_in, int32_t start, int32_t L, const uint8_t *ref,
+                             uint8_t *pass, int64_t n_units, uint32_t *mis_word, uint8_t *mis_code, int64_t cap_mis);
 
 /* ---- COLUMN-WORD input: the pileup-major form of the aligned segments ------------------------------------------------- */
 /* The same one-hot nibble words as isb_reads_batch (one 32-bit word = the codes of 8 consecutive, 8-aligned batch

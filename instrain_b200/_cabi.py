@@ -36,7 +36,7 @@ CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
 EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
-           "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact", "isb_profile_reads_delta",
+           "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact", "isb_profile_reads_delta", "isb_reads_delta_host",
            "isb_cols_from_reads", "isb_cols_from_reads_host", "isb_pileup_cols", "isb_profile_cols",
            "isb_scaffold_summary", "isb_launch_count",
            "isb_enable_timing", "isb_stage_times", "isb_selftest_division",
@@ -171,6 +171,8 @@ def load():
     L.isb_profile_reads_compact.argtypes = [vp, C.POINTER(IsbReadsCompact), C.POINTER(IsbParams), C.POINTER(IsbResult)]
     L.isb_profile_reads_delta.restype = C.c_int
     L.isb_profile_reads_delta.argtypes = [vp, C.POINTER(IsbReadsDelta), C.POINTER(IsbParams), C.POINTER(IsbResult)]
+    L.isb_reads_delta_host.restype = i64
+    L.isb_reads_delta_host.argtypes = [i64, vp, vp, vp, vp, i64, i32, i32, vp, vp, i64, vp, vp, i64]
     L.isb_cols_from_reads.restype = C.c_int
     L.isb_cols_from_reads.argtypes = [vp, C.POINTER(IsbReadsBatch), vp, C.POINTER(i64), vp, vp, i64]
     L.isb_cols_from_reads_host.restype = i64

@@ -764,3 +764,48 @@ extern "C" int64_t isb_cols_from_reads_host(int64_t n_segs, const int32_t *seg_s
     }
     return n_chunks;
 }
+
+// ---- read-major segments -> reference-delta transfer format (host side of isb_profile_reads_delta) -------------------
+// Per 8-base unit the event bits; per passing base whose one-hot code differs from the reference's (reference not
+// A/C/T/G: code 0) one (word index in the canonical stream, nibble position | XOR of the codes) entry.  Entries are
+// produced in stream order.  Returns the number of entries (only the first cap_mis are stored: call again with larger
+// buffers when it exceeds cap_mis), or -1 when the segments violate the layout rules / n_units does not match.
+extern "C" int64_t isb_reads_delta_host(int64_t n_segs, const int32_t *seg_start, const uint16_t *seg_len,
+                                        const int64_t *seg_word, const uint32_t *words_in, int64_t n_words_in, int32_t start,
+                                        int32_t L, const uint8_t *ref, uint8_t *pass, int64_t n_units, uint32_t *mis_word,
+                                        uint8_t *mis_code, int64_t cap_mis)
+{
+    if ((start & 7) || L < 0 || n_segs < 0 || !ref || (n_units > 0 && !pass)) return -1;
+    int64_t u = 0, n_mis = 0;
+    for (int64_t i = 0; i < n_segs; ++i) {
+        const int64_t s = seg_start[i], n = seg_len[i];
+        const int64_t nw = ((s & 7) + n + 7) >> 3;
+        if (n < 1 || n > 256 || s < start || s + n > (int64_t)start + L || seg_word[i] < 0 || seg_word[i] + nw > n_words_in ||
+            (i > 0 && seg_start[i - 1] > s) || u + nw > n_units)
+            return -1;
+        const int64_t r0 = (s & ~(int64_t)7) - start;                  // reference index of nibble 0 of the first unit
+        for (int64_t k = 0; k < nw; ++k, ++u) {
+            const uint32_t w = words_in[seg_word[i] + k];
+            uint32_t ps = 0;
+            for (int t = 0; t < 8; ++t) {
+                const uint32_t nib = (w >> (4 * t)) & 15u;
+                if (!nib) continue;
+                ps |= 1u << t;
+                const int64_t r = r0 + 8 * k + t;
+                const uint32_t rc = (r >= 0 && r < L) ? ref[r] : 4u;
+                const uint32_t hot = rc < 4u ? (1u << rc) : 0u;
+                if (nib != hot) {
+                    const int64_t cw = 1 + u + i;                      // canonical stream: leading zero word + one separator per segment
+                    if (cw > 0xffffffffll) return -1;
+                    if (n_mis < cap_mis && mis_word && mis_code) {
+                        mis_word[n_mis] = (uint32_t)cw;
+                        mis_code[n_mis] = (uint8_t)((nib ^ hot) | ((uint32_t)t << 4));
+                    }
+                    ++n_mis;
+                }
+            }
+            pass[u] = (uint8_t)ps;
+        }
+    }
+    return u == n_units ? n_mis : -1;
+}

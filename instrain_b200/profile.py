@@ -13,6 +13,7 @@ runs profile_split's per-column Python loop (profile_utilities.py:115-266), this
 There is no CPU fallback: without the CUDA library / a GPU this raises.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -79,6 +80,9 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     min_snp = int(kwargs.get("min_snp", 20))
     window_length = int(kwargs.get("window_length", 10000))
     fdr = float(kwargs.get("fdr", 1e-6)) or 1e-6                      # 0 -> 1e-6 (controller.py:207-208)
+    transfer = kwargs.get("b200_transfer") or os.environ.get("ISB_TRANSFER", "segments")
+    if transfer not in ("segments", "delta", "cols"):
+        raise ValueError("b200_transfer must be 'segments', 'delta' or 'cols'")
     own = engine is None
     if own:
         engine = Engine(device, model_file=kwargs.get("model_file"), fdr=fdr)
@@ -104,11 +108,22 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         cat = np.concatenate
         ref_codes = cat(batch["ref"])
         offs = np.array(batch["off"], dtype=np.int64)
-        # host -> device as read-major aligned segments (4 bits per aligned base); K1r transposes on the device
+        # host -> device as read-major aligned segments (4 bits per aligned base); K1r transposes on the device.
+        # Opt-in (kwargs["b200_transfer"] / ISB_TRANSFER): "delta" sends the reference-delta transfer format (about a
+        # quarter of the bytes; K0d rebuilds the stream), "cols" lays the batch out as column words on the host (the
+        # packer's transposition) and runs the streaming K1c.  Results are identical.
         rd = reads_mod.concat_streams(batch["parts"])
+        fmt = {}
+        if transfer == "delta":
+            fmt["reads"] = reads_mod.delta_reads_host(rd, ref_codes)
+        elif transfer == "cols":
+            from .cols import reads_to_cols
+            fmt["cols"] = reads_to_cols(rd, len(ref_codes))
+        else:
+            fmt["reads"] = rd
         out = engine.profile_batch(dict(pair_mm=cat(batch["pair_mm"])), ref_codes, np.array(batch["splits"], np.int32),
                                    min_cov=min_cov, min_freq=min_freq, min_snp=min_snp,
-                                   want=("covT", "clonT", "nmask", "snv", "ld"), reads=rd)
+                                   want=("covT", "clonT", "nmask", "snv", "ld"), **fmt)
         # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
         bounds = np.append(offs, len(ref_codes)).astype(np.int32)
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)

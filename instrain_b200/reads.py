@@ -182,6 +182,34 @@ def delta_reads(rd, ref_codes, start=0):
     return out
 
 
+def delta_reads_host(rd, ref_codes, start=0):
+    """delta_reads through the C++ host routine (isb_reads_delta_host): what the host pipeline uses.  Same result as
+    delta_reads up to the order of the mismatch entries (stream order here)."""
+    from . import _cabi
+    lib = _cabi.load()
+    p = _cabi.ptr
+    ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+    seg_start = np.ascontiguousarray(rd["seg_start"], dtype=np.int32)
+    seg_len = np.ascontiguousarray(rd["seg_len"], dtype=np.uint16)
+    seg_word = np.ascontiguousarray(rd["seg_word"], dtype=np.int64)
+    win = np.ascontiguousarray(rd["words"], dtype=np.uint32)
+    n_units = int((((seg_start.astype(np.int64) & 7) + seg_len.astype(np.int64) + 7) // 8).sum())
+    ps = np.zeros(n_units, dtype=np.uint8)
+    cap = max(1024, n_units // 8)
+    while True:
+        mw, mc = np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.uint8)
+        n = lib.isb_reads_delta_host(int(rd["n_segs"]), p(seg_start), p(seg_len), p(seg_word), p(win), len(win), start,
+                                     len(ref_codes), p(ref_codes), p(ps), n_units, p(mw), p(mc), cap)
+        if n < 0:
+            raise ValueError("read-major batch violates its layout rules")
+        if n <= cap:
+            break
+        cap = int(n)
+    out = {k_: rd[k_] for k_ in ("n_segs", "seg_start", "seg_len", "seg_pair", "max_seg_len", "nev_pos", "nev_pair")}
+    out.update(n_units=n_units, mis_word=mw[:n].copy(), mis_code=mc[:n].copy(), **{"pass": ps})
+    return out
+
+
 def delta_to_words(dl, ref_codes, start=0):
     """What K0d computes (numpy restatement, for the CPU round-trip test): the canonical nibble stream of a delta batch
     -> (seg_word, n_words, words)."""

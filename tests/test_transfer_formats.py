@@ -43,3 +43,32 @@ def test_delta_round_trip(which):
     sw2, n_words2, words2 = canonical_stream(rd)
     assert n_words == n_words2 and np.array_equal(sw, sw2) and np.array_equal(words, words2)
     assert len(dl["mis_word"]) < 0.2 * int(rd["seg_len"].sum())       # a delta: far fewer entries than bases
+
+
+@pytest.mark.parametrize("which", ["G2", "short_odd", "ragged"])
+def test_delta_host_encoder_equals_numpy(which):
+    """isb_reads_delta_host (C++, what the host pipeline runs) and the numpy encoder agree: same event bits, same set of
+    mismatch entries; its output decodes to the canonical stream."""
+    if which == "G2":
+        b, _ = load_batch("G2")
+        rd = reads.events_to_reads(b)
+    elif which == "short_odd":
+        b = synth.make_batch(20000, 40, 0.02, 9, n_scaffolds=2, skip_mm=False, n_frac=0.001)
+        rd = reads.events_to_reads(b, max_len=37, odd_blocks=True)
+        b["ref_codes"] = b["ref_codes"].copy()
+        b["ref_codes"][1000:1040] = 4
+    else:
+        b = synth.make_batch(1001, 20, 0.02, 3, skip_mm=True)
+        rd = reads.events_to_reads(b)
+    a = reads.delta_reads(rd, b["ref_codes"])
+    h = reads.delta_reads_host(rd, b["ref_codes"])
+    assert h["n_units"] == a["n_units"] and np.array_equal(h["pass"], a["pass"])
+    key = lambda d: np.sort(d["mis_word"].astype(np.int64) * 256 + d["mis_code"])
+    assert np.array_equal(key(h), key(a))
+    sw, n_words, words = reads.delta_to_words(h, b["ref_codes"])
+    sw2, n_words2, words2 = canonical_stream(rd)
+    assert n_words == n_words2 and np.array_equal(words, words2)
+    bad = dict(rd)
+    bad["seg_start"] = rd["seg_start"][::-1].copy()
+    with pytest.raises(ValueError):
+        reads.delta_reads_host(bad, b["ref_codes"])
