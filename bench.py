@@ -359,7 +359,7 @@ def main():
 
     k1_ms = stage_ms[0] / max(1, stage_calls[0])
     if use_cols:
-        fused = M == 1 and not args.keep_counts
+        fused = M == 1 and not args.keep_counts and os.environ.get("ISB_K1C_FUSE", "1") != "0"   # the library's own A/B switch
         # algorithmic bytes of K1c: the real (non-padding) nibble words (+ their pair ids when M > 1) + the group offsets in;
         # fused M = 1: ref in, covT + clonT + site_flags out (+ 32 B per SNV row, 16 B of counts per linkage site);
         # otherwise counts + nmask out

@@ -19,7 +19,7 @@
 //   * M > 1 gathers pair_mm[id] per word and keeps 8-bit counters per (level, base) in shared memory, [word][thread].
 //
 // HBM traffic: 0.5 B per aligned base (+ chunk padding, + 4 B id per word at M > 1) in, 16*M B per position out
-// (fused M = 1: 9 B per position out).  Measured on B200: the unfused M = 1 kernel runs at 0.85 of the HBM copy peak;
+// (fused M = 1: 9 B per position out).  Measured on B200: the unfused M = 1 kernel runs at 0.81 of the HBM copy peak;
 // the fused one at 0.64 (its SNV epilogue is issue-bound) but replaces two kernels and a 32 B/position round trip.
 #include "isb_common.cuh"
 #include "isb_bitslice.cuh"
