@@ -446,6 +446,9 @@ const char *isb_bam_ref_name(void *bam, int tid);
 int64_t isb_bam_ref_len(void *bam, int tid);
 const char *isb_bam_error(void *bam);
 int isb_bam_peek_tid(void *bam);                           /* next record's tid; -1 unmapped tail; -2 end of file */
+/* Reposition at a BGZF virtual offset taken from the BAM's .bai index (first alignment of a scaffold): several readers of
+ * one BAM, one per host thread, can then pack different scaffolds concurrently.  0 on success. */
+int isb_bam_seek(void *bam, uint64_t voffset);
 /* Consume all records of scaffold `tid`; pack the reads whose name is in the list (names_blob + name_off[n_names+1];
  * name_mm[i] = R2M value, 0 in set mode).  Positions are shifted by pos_offset, pair ids start at pair_id_offset and
  * follow BAM order of first appearance.  Returns an events handle (NULL on error). */

@@ -245,6 +245,25 @@ void isb_bam_close(void *h)
     delete b;
 }
 
+// Reposition the reader at a BGZF virtual offset (compressed block offset << 16 | offset inside the inflated block), as
+// stored in a .bai index: lets several readers (one per host thread) each stream their own scaffolds of one BAM.
+int isb_bam_seek(void *h, uint64_t voffset)
+{
+    Bam *b = (Bam *)h;
+    if (!b || fseeko(b->fp, (off_t)(voffset >> 16), SEEK_SET) != 0) return -1;
+    b->buf.clear();
+    b->off = 0;
+    b->eof = false;
+    b->has_pending = false;
+    b->pending.clear();
+    const size_t u = (size_t)(voffset & 0xffff);
+    if (u) {
+        if (!ensure(b, u)) return -1;
+        b->off = u;
+    }
+    return 0;
+}
+
 int isb_bam_n_refs(void *h) { return (int)((Bam *)h)->ref_names.size(); }
 const char *isb_bam_ref_name(void *h, int tid) { return ((Bam *)h)->ref_names[tid].c_str(); }
 int64_t isb_bam_ref_len(void *h, int tid) { return ((Bam *)h)->ref_lens[tid]; }

@@ -28,6 +28,8 @@ def _lib():
         L.isb_bam_error.argtypes = [vp]
         L.isb_bam_peek_tid.restype = C.c_int
         L.isb_bam_peek_tid.argtypes = [vp]
+        L.isb_bam_seek.restype = C.c_int
+        L.isb_bam_seek.argtypes = [vp, C.c_uint64]
         L.isb_pack_scaffold.restype = vp
         L.isb_pack_scaffold.argtypes = [vp, C.c_int, i64, C.c_char_p, vp, vp, i32, i32]
         for f in ("isb_events_count", "isb_events_pairs", "isb_events_reads_seen", "isb_events_reads_packed"):
@@ -71,6 +73,11 @@ class BamPacker:
 
     def __exit__(self, *a):
         self.close()
+
+    def seek(self, voffset):
+        """Reposition at a BGZF virtual offset (read_bai): the next record read is the one stored there."""
+        if self.lib.isb_bam_seek(self.h, int(voffset)) != 0:
+            raise IOError("isb_bam_seek failed")
 
     def peek_tid(self):
         """tid of the next record: >= 0; -1 unmapped tail; -2 end of file."""
@@ -146,3 +153,81 @@ class BamPacker:
         finally:
             self.lib.isb_events_free(e)
         return out
+
+
+def read_bai(path):
+    """First-alignment virtual offset of every reference of a .bai index (SAM spec 5.2): the smallest chunk begin over the
+    reference's bins (the metadata pseudo-bin 37450 excluded); None for references without alignments."""
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"BAI\1":
+        raise IOError("not a BAI index: %s" % path)
+    n_ref, = struct.unpack_from("<i", data, 4)
+    o, out = 8, []
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", data, o)
+        o += 4
+        first = None
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", data, o)
+            o += 8
+            if b != 37450 and n_chunk > 0:
+                begs = np.frombuffer(data, dtype="<u8", count=2 * n_chunk, offset=o)[0::2]
+                m = int(begs.min())
+                first = m if first is None else min(first, m)
+            o += 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", data, o)
+        o += 4 + 8 * n_intv
+        out.append(first)
+    return out
+
+
+def find_bai(bam):
+    for cand in (bam + ".bai", bam[:-4] + ".bai" if bam.endswith(".bam") else None):
+        if cand and __import__("os").path.exists(cand):
+            return cand
+    return None
+
+
+def pack_scaffolds_parallel(bam, jobs, threads, min_qual=30, window=None):
+    """Pack several scaffolds of one indexed BAM concurrently: `jobs` = [(tid, r2m, pos_offset), ...]; yields the
+    pack_scaffold_reads results in job order.  Every host thread owns a BamPacker and seeks to its scaffold through the
+    .bai index; the C++ packer releases the GIL (ctypes), so plain threads scale.  Pair ids of every result start at 0
+    (pair_id_offset is applied by the consumer: it depends on the scaffolds before it)."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    bai = find_bai(bam)
+    if bai is None:
+        raise IOError("no .bai index next to %s (needed for packer_threads > 1)" % bam)
+    first = read_bai(bai)
+    tls = threading.local()
+    opened, lock = [], threading.Lock()
+
+    def work(job):
+        tid, r2m, pos_offset = job
+        if first[tid] is None:
+            return None
+        bp = getattr(tls, "bp", None)
+        if bp is None:
+            bp = tls.bp = BamPacker(bam)
+            with lock:
+                opened.append(bp)
+        bp.seek(first[tid])
+        if bp.peek_tid() != tid:
+            raise IOError("index does not lead to scaffold %d" % tid)
+        return bp.pack_scaffold_reads(tid, r2m, pos_offset=pos_offset, pair_id_offset=0, min_qual=min_qual)
+
+    window = window or 2 * threads
+    try:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            pending = []
+            for job in jobs:
+                pending.append(ex.submit(work, job))
+                if len(pending) >= window:
+                    yield pending.pop(0).result()
+            for fut in pending:
+                yield fut.result()
+    finally:
+        for bp in opened:
+            bp.close()

@@ -1,6 +1,6 @@
 """Per-stage device timings on synthetic data (development tool; run on the GPU box through gpurun).
 
-    python tools/microbench.py [--L 200000] [--cov 100] [--rep 10] [--mm]
+    python tests/microbench.py [--L 200000] [--cov 100] [--rep 10] [--mm]
 Events are generated on the host with oracle/synth.py (test infrastructure used as a data generator only),
 replicated `rep` times on the device with shifted coordinates, and each stage is timed with CUDA events on the
 context's stream.  Prints one JSON line per measurement.
