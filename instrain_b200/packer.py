@@ -183,6 +183,52 @@ def read_bai(path):
     return out
 
 
+def scan_scaffold_offsets(bam):
+    """The same list as read_bai, computed by walking the BAM itself (pure Python: every BGZF block is inflated once) --
+    for BAMs that come without an index.  inStrain requires indexed BAMs, so this is a fallback for small inputs."""
+    import struct
+    import zlib
+    with open(bam, "rb") as f:
+        raw = f.read()
+    blocks, o = [], 0                                      # (compressed offset, inflated bytes)
+    while o + 18 <= len(raw):
+        xlen = raw[o + 10] | (raw[o + 11] << 8)
+        extra, bsize, i = raw[o + 12:o + 12 + xlen], None, 0
+        while i + 4 <= xlen:
+            slen = extra[i + 2] | (extra[i + 3] << 8)
+            if extra[i:i + 2] == b"BC" and slen == 2:
+                bsize = extra[i + 4] | (extra[i + 5] << 8)
+            i += 4 + slen
+        if bsize is None:
+            raise IOError("BGZF block without BC field")
+        blocks.append((o, zlib.decompress(raw[o + 12 + xlen:o + bsize + 1 - 8], -15)))
+        o += bsize + 1
+    data = b"".join(b for _, b in blocks)
+    starts = np.cumsum([0] + [len(b) for _, b in blocks])  # inflated offset of every block
+
+    def voffset(u):
+        k = int(np.searchsorted(starts, u, side="right")) - 1
+        while k + 1 < len(blocks) and len(blocks[k][1]) == 0:
+            k += 1
+        return (blocks[k][0] << 16) | (u - int(starts[k]))
+
+    l_text, = struct.unpack_from("<i", data, 4)
+    u = 8 + l_text
+    n_ref, = struct.unpack_from("<i", data, u)
+    u += 4
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", data, u)
+        u += 8 + l_name
+    first = [None] * n_ref
+    while u + 4 <= len(data):
+        block_size, = struct.unpack_from("<i", data, u)
+        tid, = struct.unpack_from("<i", data, u + 4)
+        if 0 <= tid < n_ref and first[tid] is None:
+            first[tid] = voffset(u)
+        u += 4 + block_size
+    return first
+
+
 def find_bai(bam):
     for cand in (bam + ".bai", bam[:-4] + ".bai" if bam.endswith(".bam") else None):
         if cand and __import__("os").path.exists(cand):
@@ -198,9 +244,7 @@ def pack_scaffolds_parallel(bam, jobs, threads, min_qual=30, window=None):
     import threading
     from concurrent.futures import ThreadPoolExecutor
     bai = find_bai(bam)
-    if bai is None:
-        raise IOError("no .bai index next to %s (needed for packer_threads > 1)" % bam)
-    first = read_bai(bai)
+    first = read_bai(bai) if bai is not None else scan_scaffold_offsets(bam)
     tls = threading.local()
     opened, lock = [], threading.Lock()
 

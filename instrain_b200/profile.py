@@ -69,11 +69,104 @@ def _fdb_splits(Fdb, scaffold, length, window_length):
     return iterate_splits(length, window_length)
 
 
+def _new_batch():
+    return dict(names=[], off=[], ref=[], splits=[], parts=[], pair_mm=[], n_events=0, L=0, n_pairs=0)
+
+
+def _add_to_batch(batch, name, seq, ev, splits):
+    """Append one packed scaffold (positions already offset by batch["L"]; pair ids by batch["n_pairs"])."""
+    L = len(seq)
+    batch["names"].append(name)
+    batch["off"].append(batch["L"])
+    batch["ref"].append(encode_reference(seq))
+    batch["splits"].extend((s + batch["L"], e + batch["L"]) for s, e in splits)
+    batch["parts"].append(ev)
+    batch["pair_mm"].append(ev["pair_mm"])
+    batch["n_events"] += ev["n_events"]
+    batch["L"] += L
+    batch["n_pairs"] += len(ev["pair_mm"])
+
+
+def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events=400_000_000, packer_threads=1, debug=False):
+    """Stream the BAM through the host packer and yield ("batch", batch dict) for every batch of scaffolds (one int32
+    coordinate space each) and ("failure", scaffold) for the reference's fault-injection scaffold
+    (profile_utilities.py:137-139, test_profile_17).
+
+    packer_threads == 1: one sequential pass over the BAM (batches are closed by the number of events actually packed).
+    packer_threads > 1 : scaffolds are packed concurrently by that many host threads, each seeking through the .bai
+    index (instrain_b200.packer.pack_scaffolds_parallel); batches are planned up front from the scaffold lengths and the
+    R2M sizes (300 aligned bases assumed per read pair).  Both give the same batches whenever everything fits one."""
+    if packer_threads <= 1:
+        batch = _new_batch()
+        with BamPacker(bam) as bp:
+            while True:
+                tid = bp.peek_tid()
+                if tid < 0:
+                    break
+                name = bp.ref_names[tid]
+                if name not in sR2M or name not in s2s:
+                    bp.pack_scaffold_reads(tid, {})                            # consume and drop
+                    continue
+                if name == "FailureScaffoldHeaderTesting" and debug:
+                    bp.pack_scaffold_reads(tid, {})
+                    yield "failure", name
+                    continue
+                L = len(s2s[name])
+                if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
+                    yield "batch", batch
+                    batch = _new_batch()
+                ev = bp.pack_scaffold_reads(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
+                _add_to_batch(batch, name, s2s[name], ev, _fdb_splits(Fdb, name, L, window_length))
+        if batch["names"]:
+            yield "batch", batch
+        return
+
+    from .packer import find_bai, pack_scaffolds_parallel, read_bai, scan_scaffold_offsets
+    with BamPacker(bam) as bp:
+        ref_names = bp.ref_names
+    bai = find_bai(bam)
+    first = read_bai(bai) if bai is not None else scan_scaffold_offsets(bam)
+    # plan: scaffolds in file (= tid) order, batch index and position offset of each
+    plan, b_idx, b_L, b_est = [], 0, 0, 0
+    for tid, name in enumerate(ref_names):
+        if first[tid] is None or name not in sR2M or name not in s2s:
+            continue
+        if name == "FailureScaffoldHeaderTesting" and debug:
+            plan.append((tid, name, None, None))
+            continue
+        L = len(s2s[name])
+        if b_est and (b_L + L >= 2 ** 31 - 1 or b_est > max_batch_events):
+            b_idx, b_L, b_est = b_idx + 1, 0, 0
+        plan.append((tid, name, b_idx, b_L))
+        b_L += L
+        b_est += 300 * len(sR2M[name])
+    jobs = [(tid, sR2M[name], off) for tid, name, bi, off in plan if bi is not None]
+    packed = pack_scaffolds_parallel(bam, jobs, packer_threads)
+    batch, cur = _new_batch(), 0
+    for tid, name, bi, off in plan:
+        if bi is None:
+            yield "failure", name
+            continue
+        ev = next(packed)
+        if bi != cur:
+            if batch["names"]:
+                yield "batch", batch
+            batch, cur = _new_batch(), bi
+        assert off == batch["L"]
+        if batch["n_pairs"]:                                                   # pair ids were numbered from 0 per scaffold
+            ev["seg_pair"] = ev["seg_pair"] + np.int32(batch["n_pairs"])
+            ev["nev_pair"] = ev["nev_pair"] + np.int32(batch["n_pairs"])
+        _add_to_batch(batch, name, s2s[name], ev, _fdb_splits(Fdb, name, len(s2s[name]), window_length))
+    if batch["names"]:
+        yield "batch", batch
+
+
 def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch_events=400_000_000, **kwargs):
     """Profile every scaffold of `sR2M` found in the BAM.  Returns (ProfileResult, engine).
 
     kwargs (reference names and defaults, argumentParser.py:107-173): min_cov 5, min_freq 0.05, min_snp 20,
     window_length 10000, skip_mm_profiling False (then sR2M values are sets), model_file/fdr for the null model.
+    Own keywords: packer_threads (host threads packing scaffolds concurrently; default 1), b200_transfer.
     """
     min_cov = int(kwargs.get("min_cov", 5))
     min_freq = float(kwargs.get("min_freq", 0.05))
@@ -140,39 +233,14 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             res.scaffolds[name] = sp
             res.scaffold_list.append(name)
 
-    new_batch = lambda: dict(names=[], off=[], ref=[], splits=[], parts=[], pair_mm=[], n_events=0, L=0, n_pairs=0)
-    batch = new_batch()
-    with BamPacker(bam) as bp:
-        while True:
-            tid = bp.peek_tid()
-            if tid < 0:
-                break
-            name = bp.ref_names[tid]
-            if name not in sR2M or name not in s2s:
-                bp.pack_scaffold_reads(tid, {})                            # consume and drop
-                continue
-            if name == "FailureScaffoldHeaderTesting" and kwargs.get("debug", False):
-                # the reference's fault-injection hook (profile_utilities.py:137-139, test_profile_17): the scaffold fails,
-                # the failure is logged, the run survives
-                bp.pack_scaffold_reads(tid, {})
-                logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(name, time.strftime("%m-%d %H:%M"), 1))
-                res.failures.append(name)
-                continue
-            L = len(s2s[name])
-            if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
-                flush(batch)
-                batch = new_batch()
-            ev = bp.pack_scaffold_reads(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
-            batch["names"].append(name)
-            batch["off"].append(batch["L"])
-            batch["ref"].append(encode_reference(s2s[name]))
-            batch["splits"].extend((s + batch["L"], e + batch["L"]) for s, e in _fdb_splits(Fdb, name, L, window_length))
-            batch["parts"].append(ev)
-            batch["pair_mm"].append(ev["pair_mm"])
-            batch["n_events"] += ev["n_events"]
-            batch["L"] += L
-            batch["n_pairs"] += len(ev["pair_mm"])
-    flush(batch)
+    for kind, payload in iter_batches(bam, sR2M, s2s, Fdb=Fdb, window_length=window_length,
+                                      max_batch_events=max_batch_events, packer_threads=int(kwargs.get("packer_threads", 1) or 1),
+                                      debug=kwargs.get("debug", False)):
+        if kind == "failure":
+            logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(payload, time.strftime("%m-%d %H:%M"), 1))
+            res.failures.append(payload)
+        else:
+            flush(payload)
     res.raw_snp_table = pd.concat(snp_tabs, ignore_index=True) if snp_tabs else pd.DataFrame(columns=tables.SNV_COLUMNS)
     res.raw_linkage_table = pd.concat(ld_tabs, ignore_index=True) if ld_tabs else pd.DataFrame(columns=tables.LD_COLUMNS)
     res.cumulative_snv_table = tables.cumulative_snv_table(res.raw_snp_table)

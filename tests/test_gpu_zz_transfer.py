@@ -1,6 +1,6 @@
 """profile_bam with the opt-in host -> device formats (kwargs["b200_transfer"]): the reference-delta transfer format
 (C++ host encoder -> K0d -> K1r) and column words laid out on the host (C++ host conversion -> K1c) give exactly the
-tables of the default read-major path on a real BAM.  (Named to sort last: these paths were added after the last GPU
+tables of the default read-major path on a real BAM; so does packing the scaffolds on several host threads.  (Named to sort last: these paths were added after the last GPU
 session of round 1; their pieces are covered by test_gpu_reads.py / test_gpu_cols.py / the CPU suite.)"""
 import json
 import os
@@ -13,15 +13,15 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("transfer", ["delta", "cols"])
-def test_profile_bam_transfer_formats(transfer):
+@pytest.mark.parametrize("transfer,threads", [("delta", 1), ("cols", 1), ("segments", 3)])
+def test_profile_bam_transfer_formats(transfer, threads):
     from instrain_b200.profile import profile_bam
     rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
     seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
     bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
     kw = dict(s2s=seqs, min_cov=5, min_freq=0.05, min_snp=20, window_length=10000, store=False)
     a = profile_bam(bam, None, rdic, None, **kw)
-    b = profile_bam(bam, None, rdic, None, b200_transfer=transfer, **kw)
+    b = profile_bam(bam, None, rdic, None, b200_transfer=transfer, packer_threads=threads, **kw)
     assert a.scaffold_list == b.scaffold_list and len(a.raw_snp_table) > 1000 and len(a.raw_linkage_table) > 1000
     for name, key in (("raw_snp_table", ["scaffold", "position", "mm"]),
                       ("raw_linkage_table", ["scaffold", "position_A", "position_B", "mm"]),

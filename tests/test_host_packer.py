@@ -200,3 +200,85 @@ def test_compact_reads_round_trip():
         assert np.array_equal(dec, w)
         # 3 bytes per 8 bases + 10 bytes per segment, against 4 bytes per 8 bases + separators + 18 bytes per segment
         assert 3 * c["n_units"] + 10 * c["n_segs"] < 0.75 * (4 * rd["n_words"] + 18 * rd["n_segs"])
+
+
+REF_BAM = "/root/reference/test/test_data/N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.sorted.bam"
+
+
+def _sequential(bam, rdic):
+    from instrain_b200.packer import BamPacker
+    out = {}
+    with BamPacker(bam) as bp:
+        names = bp.ref_names
+        while True:
+            tid = bp.peek_tid()
+            if tid < 0:
+                break
+            out[tid] = bp.pack_scaffold_reads(tid, rdic.get(names[tid], {}))
+    return names, out
+
+
+def _assert_same_pack(a, b):
+    for k in ("seg_start", "seg_len", "seg_pair", "seg_word", "stream", "nev_pos", "nev_pair", "pair_mm"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["reads_seen"] == b["reads_seen"] and a["n_events"] == b["n_events"] and a["max_seg_len"] == b["max_seg_len"]
+
+
+def test_parallel_packing_equals_sequential_unindexed():
+    """Several packer threads, each seeking to its scaffolds (offsets scanned from the BAM itself: the fixture has no
+    .bai), produce exactly the sequential packer's segments, in job order."""
+    from instrain_b200 import packer
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    names, seq = _sequential(bam, rdic)
+    assert packer.find_bai(bam) is None
+    first = packer.scan_scaffold_offsets(bam)
+    assert [t for t, f in enumerate(first) if f is not None] == sorted(seq)
+    jobs = [(tid, rdic.get(names[tid], {}), 0) for tid in sorted(seq, reverse=True)]      # any order, not only file order
+    for threads in (1, 3):
+        got = list(packer.pack_scaffolds_parallel(bam, jobs, threads))
+        assert len(got) == len(jobs)
+        for (tid, _, _), g in zip(jobs, got):
+            _assert_same_pack(g, seq[tid])
+    shifted = list(packer.pack_scaffolds_parallel(bam, [(jobs[0][0], jobs[0][1], 4096)], 2))[0]   # pos_offset is honoured
+    assert np.array_equal(shifted["seg_start"], seq[jobs[0][0]]["seg_start"] + 4096)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BAM + ".bai"), reason="reference test data not present")
+def test_bai_offsets_and_parallel_packing_on_reference_bam():
+    """read_bai (the reference's own samtools index) == offsets scanned from the BAM; 178 scaffolds packed by 4 threads ==
+    sequential."""
+    from instrain_b200 import packer
+    rdic = json.load(open(REF_BAM.replace(".sorted.bam", ".forRC.IS") + "/raw_data/Rdic.json"))
+    first = packer.read_bai(REF_BAM + ".bai")
+    assert first == packer.scan_scaffold_offsets(REF_BAM)
+    names, seq = _sequential(REF_BAM, rdic)
+    jobs = [(tid, rdic.get(names[tid], {}), 0) for tid in range(len(names)) if first[tid] is not None]
+    got = list(packer.pack_scaffolds_parallel(REF_BAM, jobs, 4))
+    for (tid, _, _), g in zip(jobs, got):
+        _assert_same_pack(g, seq[tid])
+
+
+@pytest.mark.parametrize("max_batch_events", [400_000_000, 1])
+def test_iter_batches_parallel_equals_sequential(max_batch_events):
+    """profile_bam's batch stream: packing the scaffolds on several host threads (index seeks, pair ids shifted afterwards)
+    yields the same batches -- segments, word streams, pair ids, reference codes, splits -- as the sequential pass, with
+    everything in one batch and with one batch per scaffold."""
+    from instrain_b200 import reads as reads_mod
+    from instrain_b200.profile import iter_batches
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    a = list(iter_batches(bam, rdic, seqs, max_batch_events=max_batch_events, packer_threads=1))
+    b = list(iter_batches(bam, rdic, seqs, max_batch_events=max_batch_events, packer_threads=3))
+    assert len(a) == len(b) == (1 if max_batch_events > 1 else len(rdic))
+    for (ka, x), (kb, y) in zip(a, b):
+        assert ka == kb == "batch" and x["names"] == y["names"] and x["off"] == y["off"] and x["splits"] == y["splits"]
+        assert (x["L"], x["n_pairs"], x["n_events"]) == (y["L"], y["n_pairs"], y["n_events"])
+        assert np.array_equal(np.concatenate(x["ref"]), np.concatenate(y["ref"]))
+        assert np.array_equal(np.concatenate(x["pair_mm"]), np.concatenate(y["pair_mm"]))
+        rx, ry = reads_mod.concat_streams(x["parts"]), reads_mod.concat_streams(y["parts"])
+        for k in ("seg_start", "seg_len", "seg_pair", "seg_word", "words", "nev_pos", "nev_pair"):
+            assert np.array_equal(rx[k], ry[k]), k
+        assert rx["n_segs"] == ry["n_segs"] and rx["n_words"] == ry["n_words"] and rx["max_seg_len"] == ry["max_seg_len"]
+        assert rx["seg_pair"].max() < x["n_pairs"]
