@@ -247,31 +247,42 @@ def pack_scaffolds_parallel(bam, jobs, threads, min_qual=30, window=None):
     first = read_bai(bai) if bai is not None else scan_scaffold_offsets(bam)
     tls = threading.local()
     opened, lock = [], threading.Lock()
+    jobs = list(jobs)
+    # runs of consecutive jobs: one seek per run, then the reader simply continues into the next scaffold when it is the
+    # one wanted (small scaffolds share BGZF blocks: seeking to each would inflate every block several times)
+    run_len = max(1, len(jobs) // (threads * 8))
+    runs = [jobs[i:i + run_len] for i in range(0, len(jobs), run_len)]
 
-    def work(job):
-        tid, r2m, pos_offset = job
-        if first[tid] is None:
-            return None
+    def work(run):
         bp = getattr(tls, "bp", None)
         if bp is None:
             bp = tls.bp = BamPacker(bam)
             with lock:
                 opened.append(bp)
-        bp.seek(first[tid])
-        if bp.peek_tid() != tid:
-            raise IOError("index does not lead to scaffold %d" % tid)
-        return bp.pack_scaffold_reads(tid, r2m, pos_offset=pos_offset, pair_id_offset=0, min_qual=min_qual)
+        out, at = [], None                                   # at = tid the reader is positioned on, when known
+        for tid, r2m, pos_offset in run:
+            if first[tid] is None:
+                out.append(None)
+                continue
+            if at != tid:
+                bp.seek(first[tid])
+                if bp.peek_tid() != tid:
+                    raise IOError("index does not lead to scaffold %d" % tid)
+            out.append(bp.pack_scaffold_reads(tid, r2m, pos_offset=pos_offset, pair_id_offset=0, min_qual=min_qual))
+            nxt = bp.peek_tid()
+            at = nxt if nxt >= 0 else None
+        return out
 
     window = window or 2 * threads
     try:
         with ThreadPoolExecutor(max_workers=threads) as ex:
             pending = []
-            for job in jobs:
-                pending.append(ex.submit(work, job))
+            for run in runs:
+                pending.append(ex.submit(work, run))
                 if len(pending) >= window:
-                    yield pending.pop(0).result()
+                    yield from pending.pop(0).result()
             for fut in pending:
-                yield fut.result()
+                yield from fut.result()
     finally:
         for bp in opened:
             bp.close()
