@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="cols", choices=["cols", "reads", "events"],
                     help="resident input layout: column words (default), read-major aligned segments or position-major event columns")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="ISB_PIPELINE: cut the batch into chunks and run K3 of chunk c underneath the pileup of the later chunks")
     ap.add_argument("--keep-counts", action="store_true",
                     help="ask for the full counts / nmask arrays (column words at M = 1: disables the fused pileup + SNV kernel)")
     ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (21 or 22)")
@@ -259,7 +261,7 @@ def main():
         batch = _cabi.IsbBatch(n, p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), npairs, p(d["pair_mm"]), 0,
                                Ltot, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M)
         entry = lib.isb_profile_batch
-    prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
+    prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_PIPELINE if args.pipeline else 0, 0.05)
 
     def gather_tables(cur):
         """NCCL gather of the final SNV / linkage rows of set `cur` to rank 0 (the only collective of the job), enqueued on

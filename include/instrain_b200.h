@@ -150,8 +150,10 @@ typedef struct {
 #define ISB_SKIP_LINKAGE 0x2   /* K1+K2 only (BASELINE config 2) */
 #define ISB_NO_SYNC 0x4        /* all-device buffers only: enqueue and return; row counts valid after isb_synchronize */
 #define ISB_PIPELINE 0x8       /* opt-in: overlap K2/K3 of one position chunk with K1 of the next on a second stream (batches
-                                * >= 2^22 positions).  Measured on B200: +2 % at M = 1, -10 % at M = 15 (K1 is ~70 % issue-bound, so the
-                                * co-running latency-bound kernels slow it down almost as much as they hide) -- off by default. */
+                                * >= 2^22 positions).  Event columns, measured on B200: +2 % at M = 1, -10 % at M = 15 (K1 is ~70 %
+                                * issue-bound, so the co-running latency-bound kernels slow it down almost as much as they hide).
+                                * Column words (isb_profile_cols): implemented after the last GPU session of round 1, not yet
+                                * measured -- off by default. */
 
 typedef struct {
     /* outputs (host or device); any may be NULL to skip the copy-out (the kernels still run) */

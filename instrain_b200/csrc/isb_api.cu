@@ -395,7 +395,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     // identical (linkage never crosses a split; rows are appended through the same atomic counters).
     std::vector<int32_t> hs;
     std::vector<int> cut;                                    // chunk c = splits [cut[c], cut[c+1])
-    const bool want_pipe = !rd && !cd && (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16;
+    const bool want_pipe = !rd && (prm->flags & ISB_PIPELINE) && L >= (1 << 22) && n_splits >= 16 && (!cd || do_ld);
     if (want_pipe) {
         hs.resize((size_t)n_splits * 2);
         ISB_CUDA(cudaMemcpyAsync(hs.data(), d_splits, sizeof(int32_t) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -414,7 +414,83 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
             cut.push_back(n_splits);
         }
     }
-    if (cut.size() >= 3) {
+    static const int fuse_env = getenv("ISB_K1C_FUSE") ? atoi(getenv("ISB_K1C_FUSE")) : 1;
+    if (cut.size() >= 3 && cd) {
+        // Column words: the K1c launches (fused with the SNV call at M = 1) of all chunks go back to back on the main
+        // stream; chunk c's linkage (+ K2 when not fused) runs on the second stream underneath K1c of the later chunks.
+        // K1c is cut at 64-position (group) boundaries rounded UP from the split boundaries, so chunk c's splits are
+        // complete once K1c(c) is; K3 addresses the batch's column lists through col_shift.
+        const int n_chunks = (int)cut.size() - 1;
+        cudaStream_t main_st = ctx->stream, aux = ctx->aux_stream;
+        const bool fused = M == 1 && !out->counts && !out->nmask && fuse_env != 0;
+        if (fused && cd->n_nev == 0) d_nmask = nullptr;
+        std::vector<int64_t> a((size_t)n_chunks + 1);
+        a[0] = start;
+        for (int c = 1; c < n_chunks; ++c) {
+            int64_t x = (int64_t)start + ((((int64_t)hs[2 * cut[c]] - start) + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP) * ISB_COLS_GROUP;
+            if (x > (int64_t)start + L) x = (int64_t)start + L;
+            a[c] = x < a[c - 1] ? a[c - 1] : x;
+        }
+        a[n_chunks] = (int64_t)start + L;
+        std::vector<cudaEvent_t> ev((size_t)n_chunks + 1);
+        for (auto &e : ev) ISB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), main_st));
+        if (d_nmask) {                                       // N-event bits once for the whole batch
+            ISB_CUDA(cudaMemsetAsync(d_nmask, 0, sizeof(uint64_t) * (size_t)L, main_st));
+            if ((rc = isb_k1r_n_events_launch(ctx, cd->n_nev, cd->nev_pos, cd->nev_pair, d_mm, n_pairs, start, L, M,
+                                              (unsigned long long *)d_nmask))) return rc;
+        }
+        ctx->keep_counters = 1;
+        int ts = isb_time_begin(ctx, 0);
+        rc = ISB_OK;
+        for (int c = 0; c < n_chunks && rc == ISB_OK; ++c) {
+            const int64_t len = a[c + 1] - a[c];
+            if (len > 0) {
+                const size_t off = (size_t)(a[c] - start);
+                isb_cols_dev cdk = *cd;
+                cdk.grp_off = cd->grp_off + off / ISB_COLS_GROUP;
+                cdk.n_groups = (len + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP;
+                isb_k2_fuse fz = {d_ref + off, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off, d_snv,
+                                  snv_cap, fuse_env == 2 ? 1 : 0};
+                rc = isb_k1c_launch(ctx, &cdk, d_mm, n_pairs, (int32_t)a[c], (int32_t)len, M, d_counts + off * M * 4,
+                                    d_nmask ? (unsigned long long *)d_nmask + off : nullptr, fused ? &fz : nullptr, false);
+            }
+            if (rc == ISB_OK) cudaEventRecord(ev[c], main_st);
+        }
+        isb_time_end(ctx, ts);
+        if (rc) { ctx->keep_counters = 0; for (auto &e : ev) cudaEventDestroy(e); return rc; }
+        ctx->stream = aux;
+        int64_t acc_sites = 0, acc_pairs = 0;
+        for (int c = 0; c < n_chunks && rc == ISB_OK; ++c) {
+            const int32_t c_lo = hs[2 * cut[c]], c_len = hs[2 * (cut[c + 1] - 1) + 1] - c_lo + 1;
+            const size_t off = (size_t)(c_lo - start);
+            cudaStreamWaitEvent(aux, ev[c], 0);
+            if (!fused) {
+                int t2 = isb_time_begin(ctx, 1);
+                rc = isb_k2_launch(ctx, c_len, M, d_counts + off * M * 4, d_nmask ? (const unsigned long long *)d_nmask + off : nullptr,
+                                   d_ref + off, c_lo, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off,
+                                   d_snv, snv_cap);
+                isb_time_end(ctx, t2);
+            }
+            if (rc == ISB_OK) {
+                int t3 = isb_time_begin(ctx, 2);
+                rc = isb_k3_launch_cols(ctx, cd, n_pairs, d_mm, c_lo, c_len, M, d_counts + off * M * 4,
+                                        d_nmask ? (const unsigned long long *)d_nmask + off : nullptr, d_flags + off,
+                                        cut[c + 1] - cut[c], d_splits + 2 * cut[c], prm->min_snp, d_ld, ld_cap, (int32_t)(c_lo - start));
+                isb_time_end(ctx, t3);
+                acc_sites += (int64_t)ctx->h_counters[2];
+                acc_pairs += (int64_t)ctx->h_counters[3];
+            }
+        }
+        cudaEventRecord(ev[n_chunks], aux);
+        ctx->stream = main_st;
+        ctx->keep_counters = 0;
+        cudaStreamWaitEvent(main_st, ev[n_chunks], 0);
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (rc) return rc;
+        pipe_sites = acc_sites;
+        pipe_pairs = acc_pairs;
+    } else if (cut.size() >= 3) {
         const int n_chunks = (int)cut.size() - 1;
         cudaStream_t main_st = ctx->stream, aux = ctx->aux_stream;
         std::vector<cudaEvent_t> ev(n_chunks + 1);
@@ -463,7 +539,6 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     } else {
         // Column words at M = 1 when the caller wants neither counts nor nmask: the SNV call runs in K1c's epilogue (one
         // pass; counts are written at flagged sites only, nmask exists only if the batch has N events).
-        static const int fuse_env = getenv("ISB_K1C_FUSE") ? atoi(getenv("ISB_K1C_FUSE")) : 1;
         const bool fused = cd && M == 1 && !out->counts && !out->nmask && fuse_env != 0;
         if (fused && cd->n_nev == 0) d_nmask = nullptr;
         int ts = isb_time_begin(ctx, 0);

@@ -162,14 +162,15 @@ struct isb_k2_fuse {
     int64_t cap;
     int full_counts;                  // 1: write counts of every position; 0: only of flagged sites (what K3 reads)
 };
+// init_nmask = false: nmask (when given) already holds the N-event bits of the range (chunked calls set it once per batch)
 int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
-                   int M, int32_t *counts, unsigned long long *nmask, const isb_k2_fuse *fuse);
+                   int M, int32_t *counts, unsigned long long *nmask, const isb_k2_fuse *fuse, bool init_nmask = true);
 int isb_cols_convert(isb_ctx *ctx, const isb_reads_dev *rd, int32_t start, int32_t L, int64_t *grp_off, uint32_t *words,
                      int32_t *ids, int64_t cap_chunks, int64_t *n_chunks);
 int isb_k3_launch_cols(isb_ctx *ctx, const isb_cols_dev *cd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
                        int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                        const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
-                       int64_t cap);
+                       int64_t cap, int32_t col_shift = 0);
 int isb_k1r_n_events_launch(isb_ctx *ctx, int64_t n_nev, const int32_t *nev_pos, const int32_t *nev_pair, const uint8_t *pair_mm,
                             int64_t n_pairs, int32_t start, int32_t L, int M, unsigned long long *nmask);
 int isb_k2_prepare(isb_ctx *ctx, double min_freq);

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(K1C_THREADS) k1c_pileup_mm(k1c_args a)
 }
 
 int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
-                   int M, int32_t *counts, unsigned long long *nmask, const isb_k2_fuse *fuse)
+                   int M, int32_t *counts, unsigned long long *nmask, const isb_k2_fuse *fuse, bool init_nmask)
 {
     cudaStream_t st = ctx->stream;
     if (L <= 0) return ISB_OK;
@@ -298,7 +298,7 @@ int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm,
     if (M > 1 && (!pair_mm || !cd->ids)) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: pair_mm and ids are required when M > 1");
     if (fuse && M != 1) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: the fused SNV call needs M == 1");
     int rc;
-    if (nmask) {
+    if (nmask && init_nmask) {
         ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
         if ((rc = isb_k1r_n_events_launch(ctx, cd->n_nev, cd->nev_pos, cd->nev_pair, pair_mm, n_pairs, start, L, M, nmask))) return rc;
     }

@@ -32,6 +32,7 @@ struct k3_args {
     int64_t n_pairs;
     const uint8_t *pair_mm;
     int32_t start, L;
+    int32_t col_shift;             // column words: position of `start` relative to the batch the column lists index (chunked calls)
     int M, min_qual, min_snp;
     const int32_t *counts;
     const unsigned long long *nmask;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) k3c_site_prep(k3_args a, isb_cols_dev cd,
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.S) return;
     const int32_t p = a.site_pos[k];
-    const k3c_column col = k3c_site_column(cd, p);
+    const k3c_column col = k3c_site_column(cd, p + a.col_shift);
     k3c_site_rec r;
     r.base = col.base;
     r.depth = col.depth;
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
         // entries of the site in column order: event range (position-major), candidate segments (read-major) or the
         // slots of the site's column list (column words)
         k3c_column col = {0, 0, 0};
-        if (kMode == 2) col = k3c_site_column(cd, p);
+        if (kMode == 2) col = k3c_site_column(cd, p + a.col_shift);
         const int64_t lo = kMode == 2 ? 0 : (kMode == 1 ? cand_lo[k] : a.site_ev[2 * k]);
         const int64_t hi = kMode == 2 ? col.depth : (kMode == 1 ? lo + n_cand[k] : a.site_ev[2 * k + 1]);
         auto entry = [&](int64_t e, int &b, int &rid) -> bool {
@@ -786,7 +787,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
                   const uint8_t *qual, const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
                   int32_t L, int M, int min_qual, const int32_t *counts, const unsigned long long *nmask,
                   const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
-                  int64_t cap)
+                  int64_t cap, int32_t col_shift = 0)
 {
     cudaStream_t st = ctx->stream;
     int rc;
@@ -824,7 +825,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
     a.n = n; a.ref_pos = ref_pos; a.base = base; a.qual = qual; a.read_id = read_id;
     a.n_pairs = n_pairs; a.pair_mm = pair_mm; a.start = start; a.L = L; a.M = M; a.min_qual = min_qual;
     a.min_snp = min_snp; a.counts = counts; a.nmask = nmask; a.site_flags = site_flags;
-    a.n_splits = n_splits; a.splits = splits;
+    a.n_splits = n_splits; a.splits = splits; a.col_shift = col_shift;
     a.S = S; a.site_pos = site_pos;
     a.site_ev = (int64_t *)ctx->buf[SL_SITE_META].p;
     a.meta = (isb_site_meta *)((int64_t *)ctx->buf[SL_SITE_META].p + 2 * S);
@@ -970,9 +971,9 @@ int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, 
 int isb_k3_launch_cols(isb_ctx *ctx, const isb_cols_dev *cd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
                        int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                        const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,
-                       int64_t cap)
+                       int64_t cap, int32_t col_shift)
 {
     if (cd->n_chunks > 0 && !cd->ids) return isb_fail(ctx, ISB_ERR_ARG, "column-word batch: ids is required for linkage");
     return k3_run(ctx, nullptr, cd, 0, nullptr, nullptr, nullptr, nullptr, n_pairs, pair_mm, start, L, M, 0, counts, nmask,
-                  site_flags, n_splits, splits, min_snp, rows, cap);
+                  site_flags, n_splits, splits, min_snp, rows, cap, col_shift);
 }

@@ -38,3 +38,33 @@ def test_profile_bam_transfer_formats(transfer, threads):
         for m in a.scaffolds[s].covT:
             assert a.scaffolds[s].covT[m].equals(b.scaffolds[s].covT[m])
             assert a.scaffolds[s].clonT[m].equals(b.scaffolds[s].clonT[m])
+
+
+@pytest.mark.parametrize("skip_mm,lean", [(True, True), (True, False), (False, False)])
+def test_cols_chunk_pipeline_equals_single_pass(skip_mm, lean):
+    """ISB_PIPELINE on the column-word path (opt-in): K1c of all chunks back to back on the main stream, K3 (+ K2 when not
+    fused) of chunk c on a second stream underneath; the tables must equal the single-pass ones exactly."""
+    from conftest import assert_ld_equal, assert_snv_equal, load_lut
+    from instrain_b200 import synth as dsynth
+    from instrain_b200.engine import Engine
+    lut = load_lut()
+    eng = Engine(0, lut[0], lut[1])
+    try:
+        d = dsynth.generate(0, 300000, 15, 12, 0.01, 99, skip_mm=skip_mm, events=False, reads=True)   # 4.5e6 positions
+        cd = dsynth.reads_to_cols_device(eng, d)
+        ev = dict(pair_mm=d["pair_mm"].cpu().numpy())
+        ref, spl = d["ref_codes"].cpu().numpy(), d["splits"].cpu().numpy()
+        M = int(ev["pair_mm"].max()) + 1 if len(ev["pair_mm"]) else 1
+        want = ("covT", "clonT", "site_flags", "snv", "ld") if lean else ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld")
+        a = eng.profile_batch(ev, ref, spl, M=M, want=want, min_cov=3, min_snp=3, cols=cd)
+        b = eng.profile_batch(ev, ref, spl, M=M, want=want, min_cov=3, min_snp=3, cols=cd, pipeline=True)
+        assert len(a["snv"]) > 1000 and len(a["ld"]) > 100
+        for k in ("counts", "nmask", "covT", "site_flags"):
+            if k in want:
+                assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
+        assert_snv_equal(a["snv"], b["snv"])
+        assert_ld_equal(a["ld"], b["ld"], tol=0)
+        assert (a["n_sites"], a["n_site_pairs"]) == (b["n_sites"], b["n_site_pairs"])
+    finally:
+        eng.close()
