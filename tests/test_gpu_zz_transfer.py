@@ -10,7 +10,7 @@ import pytest
 
 from conftest import GOLDEN
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]     # these paths have not run on a GPU yet: never hang the suite
 
 
 @pytest.mark.parametrize("transfer,threads", [("delta", 1), ("cols", 1), ("segments", 3)])
