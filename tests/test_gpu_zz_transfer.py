@@ -10,7 +10,11 @@ import pytest
 
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]     # these paths have not run on a GPU yet: never hang the suite
+# These paths were written after the last GPU session of round 1 (their pieces are GPU- or CPU-verified, the combinations
+# are not): they run only when asked for, so that an untested path can neither fail nor hang the suite.
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.skipif(os.environ.get("ISB_TEST_EXPERIMENTAL") != "1",
+                                 reason="not yet validated on a GPU; set ISB_TEST_EXPERIMENTAL=1")]
 
 
 @pytest.mark.parametrize("transfer,threads", [("delta", 1), ("cols", 1), ("segments", 3)])
