@@ -90,3 +90,44 @@ def test_read_filter_restatement_reproduces_rdic(which, n_pairs):
     mi = pd.read_csv(isd + "mapping_info.csv.gz")
     mi = mi[mi.scaffold != "all_scaffolds"].set_index("scaffold")
     assert all(int(mi.loc[s, c]) == tal[s][c] for s in mi.index if s in tal for c in tal[s])
+
+
+def _param_case(name):
+    """The reference's own outputs for non-default settings (tests/golden/make_param_goldens.py) + the oracle's inputs."""
+    import hashlib
+    z = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_G1_%s.npz" % name)))
+    batch, _ = load_batch("G1")
+    if bool(z["set_mode"]):
+        batch["pair_mm"] = np.zeros_like(batch["pair_mm"])
+    off = dict(zip(batch["scaffold_names"], batch["scaffold_off"].astype(np.int64)))
+    ln = dict(zip(batch["scaffold_names"], batch["scaffold_len"].astype(np.int64)))
+    keep = np.zeros(len(batch["ref_codes"]), dtype=bool)
+    for s in z["scaffolds"]:
+        keep[off[s]:off[s] + ln[s]] = True
+    sha = lambda a: np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    return z, batch, off, ln, keep, sha
+
+
+def check_against_param_golden(out, z, batch, off, ln, keep, sha):
+    """`out` = profile of the WHOLE G1 batch (oracle or CUDA path) with the fixture's settings: its rows inside the chosen
+    scaffolds and their dense covT / clonT must equal what the reference's own functions returned."""
+    snv, ld = expected_rows(z, batch["ref_codes"])
+    assert_snv_equal(out["snv"][keep[out["snv"]["pos"]]], snv)
+    assert_ld_equal(out["ld"][keep[out["ld"]["pos_a"]]], ld, tol=1e-9)
+    for s, M, c_sha, l_sha in zip(z["scaffolds"], z["M"], z["cov_sha"], z["clon_sha"]):
+        sl = slice(int(off[s]), int(off[s] + ln[s]))
+        cov, clon = out["covT"][sl, :M], out["clonT"][sl, :M]
+        assert not out["covT"][sl, M:].any() and np.isnan(out["clonT"][sl, M:]).all(), s
+        assert np.array_equal(sha(cov.astype(np.int32)), c_sha), "covT " + s
+        assert np.array_equal(sha(clon.astype(np.float32)), l_sha), "clonT " + s
+
+
+@pytest.mark.parametrize("name", ["params_P1", "params_P2", "params_P3"])
+def test_oracle_reproduces_reference_with_other_settings(name):
+    """Pins the oracle's PARAMETER handling on the reference: min_cov / min_freq / min_snp / fdr away from the defaults
+    and set-mode R2M (--skip_mm_profiling), against outputs of the reference's own functions run on the same reads."""
+    z, batch, off, ln, keep, sha = _param_case(name)
+    out = restate.profile_events(batch, batch["ref_codes"], z["lut"], int(z["lut_default"]), batch["splits"],
+                                 min_cov=int(z["min_cov"]), min_freq=float(z["min_freq"]), min_snp=int(z["min_snp"]))
+    assert len(z["snv_pos"]) > 1000 and len(z["ld_pos_a"]) > 1000
+    check_against_param_golden(out, z, batch, off, ln, keep, sha)
