@@ -97,5 +97,54 @@ def main():
         print(pname, "scaffolds", len(names), "snv rows", len(snp), "ld rows", len(ld))
 
 
+def rows_to_arrays(snp, ld):
+    return dict(
+        snv_pos=np.array([r["position"] for r in snp], np.int32), snv_mm=np.array([r["mm"] for r in snp], np.int32),
+        snv_cnt=np.array([[r["A"], r["C"], r["T"], r["G"]] for r in snp], np.int32).reshape(-1, 4),
+        snv_con=np.array([B[r["con_base"]] for r in snp], np.uint8), snv_var=np.array([B[r["var_base"]] for r in snp], np.uint8),
+        snv_allele_count=np.array([r["allele_count"] for r in snp], np.uint8),
+        snv_cls=np.array([CLS[r["class"]] for r in snp], np.uint8), snv_cryptic=np.array([r["cryptic"] for r in snp], np.uint8),
+        ld_pos_a=np.array([r["position_A"] for r in ld], np.int32), ld_pos_b=np.array([r["position_B"] for r in ld], np.int32),
+        ld_mm=np.array([r["mm"] for r in ld], np.int32),
+        ld_counts=np.array([[r["countAB"], r["countAb"], r["countaB"], r["countab"]] for r in ld], np.int32).reshape(-1, 4),
+        ld_alleles=np.array([[B[r[c]] for c in ("allele_A", "allele_a", "allele_B", "allele_b")] for r in ld], np.uint8).reshape(-1, 4),
+        ld_r2=np.array([r["r2"] for r in ld], np.float64), ld_d_prime=np.array([r["d_prime"] for r in ld], np.float64))
+
+
+def make_ns_case():
+    """The reference's edge-case input `N5_271_010G1_scaffold_963_Ns` (a reference with an N, ~185x coverage, 26395 reads of
+    which 970 pairs pass the default read filter; the reference's tests only check that it runs): INPUT batch (events of
+    the pairs the pinned read filter keeps) + what the reference's functions return for it with default settings."""
+    from oracle import read_filter
+    td = os.path.join(ref_harness.REFERENCE_ROOT, "test", "test_data")
+    refs, reads = bamio.read_bam(os.path.join(td, "N5_271_010G1_scaffold_963_Ns.fasta.sorted.bam"))
+    seqs = bamio.read_fasta(os.path.join(td, "N5_271_010G1_scaffold_963_Ns.fasta"))
+    name = refs[0][0]
+    rs = [r for r in reads if r.tid == 0]
+    kept, _, _ = read_filter.filter_pairs({name: read_filter.pair2info(rs)})
+    r2m = kept[name]
+    ev = pileup_emul.scaffold_events(rs, r2m)
+    seq = seqs[name]
+    model = ref_harness.null_model(1e-6)
+    out = ref_harness.run_split(ev, seq, 0, len(seq) - 1, r2m, model, scaffold=name)
+    M = max(r2m.values()) + 1
+    cov = np.zeros((len(seq), M), dtype=np.int32)
+    clon = np.full((len(seq), M), np.nan, dtype=np.float32)
+    for mm, arr in out["covT"].items():
+        cov[:, mm] = arr
+    for mm, arr in out["clonT"].items():
+        clon[:, mm] = arr
+    sev = restate.sort_events(ev)
+    exp = rows_to_arrays(out["snp"], out["ld"])
+    exp.update(ref_codes=restate.encode_ref(seq), ref_pos=sev["ref_pos"].astype(np.int32), base=sev["base"], qual=sev["qual"],
+               read_id=sev["read_id"].astype(np.int32), pair_mm=sev["pair_mm"].astype(np.int32),
+               splits=np.array([[0, len(seq) - 1]], np.int32), covT=cov, clonT=clon)
+    np.savez_compressed(os.path.join(HERE, "c963_Ns.npz"), **exp)
+    print("c963_Ns: events", len(sev["ref_pos"]), "pairs", len(sev["pair_mm"]), "N in reference", int((exp["ref_codes"] > 3).sum()),
+          "snv rows", len(out["snp"]), "ld rows", len(out["ld"]))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] != ["ns"]:
+        main()
+    make_ns_case()

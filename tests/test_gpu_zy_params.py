@@ -5,7 +5,7 @@ clonT of 30 scaffolds.  (The same fixtures pin the oracle in tests/test_oracle_g
 import numpy as np
 import pytest
 
-from test_oracle_golden import _param_case, check_against_param_golden
+from test_oracle_golden import _param_case, check_against_param_golden, check_ns_case, load_ns_case
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
@@ -25,5 +25,22 @@ def test_cuda_reproduces_reference_with_other_settings(name):
         for layout in (dict(cols=cd), dict(reads=rd), {}):
             out = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], **kw, **layout)
             check_against_param_golden(out, z, batch, off, ln, keep, sha)
+    finally:
+        eng.close()
+
+
+def test_cuda_reproduces_reference_on_n_reference_case(null_lut):
+    """scaffold_963_Ns (an N in the reference, ~185x coverage): the three layouts against the reference's own outputs."""
+    from instrain_b200 import cols, reads
+    from instrain_b200.engine import Engine
+    z, batch = load_ns_case()
+    M = int(batch["pair_mm"].max()) + 1
+    rd = reads.events_to_reads(batch)
+    cd = cols.reads_to_cols(rd, len(batch["ref_codes"]))
+    eng = Engine(0, null_lut[0], null_lut[1])
+    try:
+        for layout in (dict(cols=cd), dict(reads=rd), {}):
+            out = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=("covT", "clonT", "snv", "ld"), **layout)
+            check_ns_case(out, z, batch)
     finally:
         eng.close()

@@ -282,3 +282,27 @@ def test_iter_batches_parallel_equals_sequential(max_batch_events):
             assert np.array_equal(rx[k], ry[k]), k
         assert rx["n_segs"] == ry["n_segs"] and rx["n_words"] == ry["n_words"] and rx["max_seg_len"] == ry["max_seg_len"]
         assert rx["seg_pair"].max() < x["n_pairs"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test/test_data"), reason="reference tree not present")
+@pytest.mark.parametrize("bam", ["N5_271_010G1_scaffold_963_Ns.fasta.sorted.bam", "SmallScaffold.fa.sorted.bam",
+                                 "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G2.sorted.bam"])
+def test_packer_and_filter_on_reference_edge_case_bams(bam):
+    """The reference's edge-case inputs (N reference at ~185x with 26 k reads, a tiny scaffold, the second sample): the C++
+    read filter gives the restatement's sR2M, and the C++ packer the emulation's events, record for record.  For the Ns
+    BAM the packed events are exactly the committed fixture the oracle / CUDA tests profile (tests/golden/c963_Ns.npz)."""
+    from instrain_b200.read_filter import filter_reads
+    path = os.path.join("/root/reference/test/test_data", bam)
+    names, (exp, _, _) = _oracle_filter(path)
+    got, _, _ = filter_reads(path, names)
+    assert {s: d for s, d in got.items() if d} == {s: d for s, d in exp.items() if d}
+    n = compare_bam(path, exp)
+    assert n > 1000
+    if "963_Ns" in bam:
+        z = np.load(os.path.join(GOLDEN, "c963_Ns.npz"))
+        from instrain_b200.packer import BamPacker
+        with BamPacker(path) as bp:
+            ev = bp.pack_scaffold(bp.peek_tid(), exp[names[0]])
+        for k in ("ref_pos", "base", "qual", "read_id"):
+            assert np.array_equal(ev[k], z[k]), k
+        assert np.array_equal(ev["pair_mm"], z["pair_mm"].astype(np.uint8))

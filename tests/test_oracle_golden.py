@@ -131,3 +131,31 @@ def test_oracle_reproduces_reference_with_other_settings(name):
                                  min_cov=int(z["min_cov"]), min_freq=float(z["min_freq"]), min_snp=int(z["min_snp"]))
     assert len(z["snv_pos"]) > 1000 and len(z["ld_pos_a"]) > 1000
     check_against_param_golden(out, z, batch, off, ln, keep, sha)
+
+
+def load_ns_case():
+    z = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c963_Ns.npz")))
+    batch = {k: z[k] for k in ("ref_codes", "ref_pos", "base", "qual", "read_id", "pair_mm", "splits")}
+    return z, batch
+
+
+def check_ns_case(out, z, batch):
+    snv, ld = expected_rows(z, batch["ref_codes"])
+    assert_snv_equal(out["snv"], snv)
+    assert_ld_equal(out["ld"], ld, tol=1e-9)
+    assert np.array_equal(out["covT"], z["covT"])
+    ok = ~np.isnan(z["clonT"])
+    assert np.array_equal(np.isnan(out["clonT"]), ~ok)
+    assert np.array_equal(out["clonT"][ok].view(np.uint32), z["clonT"][ok].view(np.uint32))
+
+
+def test_oracle_reproduces_reference_on_n_reference_case():
+    """The reference's edge-case BAM with an N in the reference sequence (scaffold_963_Ns, ~185x): rows (incl. the
+    AmbiguousReference class at the N), covT and clonT at every position, against the reference's own functions
+    (tests/golden/make_param_goldens.py ns)."""
+    from conftest import load_lut
+    z, batch = load_ns_case()
+    lut, dflt = load_lut()
+    out = restate.profile_events(batch, batch["ref_codes"], lut, dflt, batch["splits"])
+    assert len(out["snv"]) == 686 and (out["snv"]["cls"] == 0).sum() >= 1          # class 0 = AmbiguousReference
+    check_ns_case(out, z, batch)
