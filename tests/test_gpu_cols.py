@@ -207,9 +207,7 @@ def test_cols_equal_read_major_larger(eng, null_lut):
 def test_device_generator_cols(eng, null_lut):
     """bench.py's resident data set: the generator's read-major batch converted on the device (isb_cols_from_reads with
     device pointers) gives the same tables as the read-major path on the same data."""
-    import ctypes as C
-    import torch
-    from instrain_b200 import _cabi, synth as dsynth
+    from instrain_b200 import synth as dsynth
     for skip_mm in (True, False):
         d = dsynth.generate(0, 50000, 3, 60, 0.01, 77, skip_mm=skip_mm, events=False, reads=True)
         cd = dsynth.reads_to_cols_device(eng, d)

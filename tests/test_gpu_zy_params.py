@@ -2,7 +2,6 @@
 tests/golden/make_param_goldens.py from the reference's functions): min_cov / min_freq / min_snp / fdr away from the
 defaults, and set-mode R2M (--skip_mm_profiling), in all three input layouts.  SNV rows, linkage rows and the dense covT /
 clonT of 30 scaffolds.  (The same fixtures pin the oracle in tests/test_oracle_golden.py.)"""
-import numpy as np
 import pytest
 
 from test_oracle_golden import _param_case, check_against_param_golden, check_ns_case, load_ns_case
