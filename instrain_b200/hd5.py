@@ -228,7 +228,10 @@ class _Writer:
         self.buf += b
         return a
 
-    def add_dataset(self, name, arr, level=4):
+    @staticmethod
+    def prepare(arr, level=4):
+        """The CPU-heavy, state-free half of add_dataset: dtype widening, chunking and deflate of one dataset (zlib
+        releases the GIL: write_hd5 runs this on a thread pool).  Returns (rows, n, C, datatype message, chunks)."""
         arr = np.ascontiguousarray(arr)
         if arr.ndim != 2:
             raise ValueError("2-D arrays only")
@@ -244,14 +247,18 @@ class _Writer:
         C = max(1, -(-n // per_row)) if n else 1024    # empty dataset: no chunk index (libhdf5 does the same)
         if rows * (-(-n // C) if n else 0) > 2 * CHUNK_K:
             raise ValueError("too many rows for a single-node chunk index")
-        keys = []
+        chunks = []
         for r in range(rows):
             for c0 in range(0, n, C):
                 blk = np.zeros(C, dtype=arr.dtype)
                 seg = arr[r, c0:c0 + C]
                 blk[:len(seg)] = seg
-                z = zlib.compress(blk.tobytes(), level)
-                keys.append(((r, c0, 0), len(z), self._append(z)))
+                chunks.append(((r, c0, 0), zlib.compress(blk.tobytes(), level)))
+        return rows, n, C, dt, chunks
+
+    def add_dataset(self, name, arr, level=4, prepared=None):
+        rows, n, C, dt, chunks = prepared if prepared is not None else self.prepare(arr, level)
+        keys = [(offs, len(z), self._append(z)) for offs, z in chunks]
         btree = UNDEF
         if keys:
             node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(keys), UNDEF, UNDEF))
@@ -331,22 +338,42 @@ class _Writer:
         return bytes(self.buf)
 
 
-def write_hd5(path, datasets, level=4):
+def write_hd5(path, datasets, level=4, threads=None):
     """datasets: {name -> 2-D array}; integer arrays are stored as int64, float arrays as float64 (what
-    `np.array([values, index])` gives the reference)."""
+    `np.array([values, index])` gives the reference).  The deflate of the datasets runs on `threads` host threads
+    (default: the cores of the process, at most 16); the file is byte-identical for every thread count."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    if threads is None:
+        try:
+            threads = min(16, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            threads = min(16, os.cpu_count() or 1)
     w = _Writer()
-    for name, arr in datasets.items():
-        w.add_dataset(name, arr, level)
+    items = list(datasets.items())
+    if threads <= 1 or len(items) < 2:
+        for name, arr in items:
+            w.add_dataset(name, arr, level)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            window, pending = 4 * threads, []                  # bounded look-ahead: compressed chunks wait in memory
+            for name, arr in items:
+                pending.append((name, ex.submit(_Writer.prepare, arr, level)))
+                if len(pending) >= window:
+                    nm, fut = pending.pop(0)
+                    w.add_dataset(nm, None, level, prepared=fut.result())
+            for nm, fut in pending:
+                w.add_dataset(nm, None, level, prepared=fut.result())
     data = w.finish()
     with open(path, "wb") as f:
         f.write(data)
     return len(data)
 
 
-def store_special(path, obj):
+def store_special(path, obj, threads=None):
     """Mirror of SNVprofile._store_special for covT / clonT (SNVprofile.py:717-733): obj = scaffold -> mm -> Series."""
     ds = {}
     for scaff, clon in obj.items():
         for mm, arr in clon.items():
             ds["{0}::{1}".format(scaff, mm)] = np.array([np.asarray(arr.values), np.asarray(arr.index)])
-    return write_hd5(path, ds)
+    return write_hd5(path, ds, threads=threads)

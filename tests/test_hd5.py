@@ -115,3 +115,16 @@ def test_reader_rejects_foreign_files(tmp_path):
     p.write_bytes(b"not an hdf5 file at all" * 10)
     with pytest.raises(ValueError):
         hd5.read_hd5(str(p))
+
+
+def test_threaded_writer_is_byte_identical(tmp_path):
+    """write_hd5 deflates the datasets on a thread pool; the file must not depend on the thread count."""
+    rng = np.random.default_rng(3)
+    ds = {"s%d::%d" % (i, m): np.array([rng.integers(0, 200, n), np.arange(n)]) for i in range(12) for m in range(3)
+          for n in [int(rng.integers(0, 5000))]}
+    ds["f::0"] = np.array([rng.random(700), np.arange(700)], dtype=np.float64)
+    sizes = [hd5.write_hd5(str(tmp_path / ("t%d.hd5" % t)), ds, threads=t) for t in (1, 3, 8)]
+    blobs = [open(str(tmp_path / ("t%d.hd5" % t)), "rb").read() for t in (1, 3, 8)]
+    assert sizes[0] == len(blobs[0]) and blobs[0] == blobs[1] == blobs[2]
+    back = hd5.read_hd5(str(tmp_path / "t8.hd5"))
+    assert set(back) == set(ds) and all(np.array_equal(back[k], ds[k].astype(back[k].dtype)) for k in ds)
