@@ -306,3 +306,40 @@ def test_packer_and_filter_on_reference_edge_case_bams(bam):
         for k in ("ref_pos", "base", "qual", "read_id"):
             assert np.array_equal(ev[k], z[k]), k
         assert np.array_equal(ev["pair_mm"], z["pair_mm"].astype(np.uint8))
+
+
+def test_profile_scaffolds_host_loop_without_gpu():
+    """The host loop of profile_bam (batch stream -> transfer format -> engine call -> failure handling) driven by a stub
+    engine that records what it is handed and then fails like a crashed batch: the reference's behaviour is to log the
+    scaffolds of the batch as failures and carry on (profile_utilities.py:92-112)."""
+    from instrain_b200 import reads as reads_mod
+    from instrain_b200.profile import profile_scaffolds
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+
+    class StubEngine:
+        def __init__(self):
+            self.calls = []
+
+        def profile_batch(self, ev, ref_codes, splits, **kw):
+            self.calls.append((len(ev["pair_mm"]), len(ref_codes), len(splits), sorted(k for k in ("reads", "cols") if k in kw),
+                               {k: v for k, v in kw.items() if k in ("reads", "cols")}))
+            raise RuntimeError("no GPU in this test")
+
+    seen = {}
+    for transfer, threads in (("segments", 1), ("delta", 1), ("cols", 2)):
+        eng = StubEngine()
+        res = profile_scaffolds(bam, rdic, seqs, engine=eng, b200_transfer=transfer, packer_threads=threads)
+        assert sorted(res.failures) == sorted(rdic) and res.scaffold_list == [] and len(res.raw_snp_table) == 0
+        (n_pairs, L, n_splits, keys, fmt), = eng.calls
+        assert L == sum(len(seqs[s]) for s in rdic) and n_pairs == sum(len(v) for v in rdic.values())
+        seen[transfer] = fmt
+    rd = seen["segments"]["reads"]
+    assert "mis_word" in seen["delta"]["reads"] and np.array_equal(seen["delta"]["reads"]["seg_start"], rd["seg_start"])
+    ref = np.concatenate([__import__("instrain_b200.profile", fromlist=["encode_reference"]).encode_reference(seqs[s])
+                          for s in seqs if s in rdic])
+    _, _, words = reads_mod.delta_to_words(seen["delta"]["reads"], ref)
+    assert int(words.sum()) > 0
+    assert seen["cols"]["cols"]["n_chunks"] > 0 and int((seen["cols"]["cols"]["ids"] >= 0).sum()) == int(
+        (((rd["seg_start"].astype(np.int64) & 7) + rd["seg_len"].astype(np.int64) + 7) // 8).sum())
