@@ -1,0 +1,76 @@
+"""CPU mirrors of reference tests that have an INDEPENDENT known answer for the hot path's outputs (they need the
+reference's test data, so they run in the build container only).
+
+test_profile_3 (test/tests/test_profile.py:347-378): `inStrain profile ... -l 0.98`, then
+  * _internal_verify_Sdb     (test_utils.py:265-298): per scaffold, breadth_minCov / coverage / coverage_median never
+                             decrease with mm; conANI_reference != 0 wherever there are consensus-divergent sites;
+  * coverage and breadth at the highest mm against the output of an independent tool (calculate_breadth, stored as
+    `...bam.CB`), one-sided within 0.1 / 0.01 (the profile only sees the reads that pass the filter);
+  * _internal_verify_OdbSdb  (test_utils.py:300-317): divergent_site_count == number of SNV-table positions, at the
+                             lowest and at the highest mm.
+Here the path is: C++ read filter (min_read_ani 0.98) -> C++ packer -> oracle (C restatement) -> summary restatement;
+the CUDA path equals the oracle on the same events (tests/test_gpu_*.py)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_lut
+from oracle import bamio, restate, summary
+
+TD = "/root/reference/test/test_data/"
+BAM = TD + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.sorted.bam"
+pytestmark = pytest.mark.skipif(not os.path.exists(BAM), reason="reference test data not present")
+
+
+def test_profile_3_mirror():
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.read_filter import filter_reads
+    seqs = bamio.read_fasta(TD + "N5_271_010G1_scaffold_min1000.fa")
+    with BamPacker(BAM) as bp:
+        names = bp.ref_names
+    r2m, _, _ = filter_reads(BAM, names, min_read_ani=0.98)
+    r2m_095, _, _ = filter_reads(BAM, names)
+    assert 0 < sum(len(v) for v in r2m.values()) < sum(len(v) for v in r2m_095.values())     # -l 0.98 drops pairs
+    lut, dflt = load_lut()
+    odb, sdb = [], []
+    with BamPacker(BAM) as bp:
+        while True:
+            tid = bp.peek_tid()
+            if tid < 0:
+                break
+            name = bp.ref_names[tid]
+            ev = bp.pack_scaffold(tid, r2m.get(name, {}))
+            if not r2m.get(name):
+                continue
+            L = len(seqs[name])
+            out = restate.profile_events(ev, restate.encode_ref(seqs[name]), lut, dflt, np.array([[0, L - 1]], np.int32),
+                                         do_linkage=False)
+            for r in summary.scaffold_summary(out["covT"], out["clonT"], out["nmask"], out["snv"], 0):
+                odb.append(dict(r, scaffold=name))
+            for row in out["snv"]:
+                sdb.append(dict(scaffold=name, position=int(row["pos"]), mm=int(row["mm"])))
+    Odb, Sdb = pd.DataFrame(odb), pd.DataFrame(sdb)
+    assert Odb["scaffold"].nunique() > 150 and len(Sdb) > 300
+    # _internal_verify_Sdb
+    for scaff, d in Odb.groupby("scaffold"):
+        d = d.sort_values("mm")
+        for thing in ("breadth_minCov", "coverage", "coverage_median"):
+            assert d[thing].tolist() == sorted(d[thing].tolist()), (scaff, thing)
+    assert (Odb["conANI_reference"][Odb["consensus_divergent_sites"] > 0] != 0).all()
+    # against calculate_breadth
+    Cdb = pd.read_csv(TD + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.bam.CB")
+    s2c, s2b = Cdb.set_index("scaffold")["coverage"].to_dict(), Cdb.set_index("scaffold")["breadth"].to_dict()
+    for scaff, db in Odb.groupby("scaffold"):
+        top = db.sort_values("mm", ascending=False).iloc[0]
+        assert top["coverage"] - s2c[scaff] < 0.1, (scaff, top["coverage"], s2c[scaff])
+        assert top["breadth"] - s2b[scaff] < 0.01, (scaff, top["breadth"], s2b[scaff])
+    # _internal_verify_OdbSdb
+    low_mm = Sdb["mm"].min()
+    for scaff, db in Sdb[Sdb["mm"] == low_mm].groupby("scaffold"):
+        snps = Odb["divergent_site_count"][(Odb["scaffold"] == scaff) & (Odb["mm"] == low_mm)].fillna(0).tolist()[0]
+        assert snps == len(db), (scaff, snps, len(db))
+    top = Odb.sort_values("mm").drop_duplicates(subset="scaffold", keep="last")
+    for scaff, db in Sdb.sort_values("mm").drop_duplicates(subset=["scaffold", "position"], keep="last").groupby("scaffold"):
+        assert top["divergent_site_count"][top["scaffold"] == scaff].fillna(0).tolist()[0] == len(db), scaff
