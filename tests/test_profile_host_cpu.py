@@ -1,0 +1,135 @@
+"""profile_bam's HOST side end to end without a GPU: BAM -> C++ packer -> batch stream -> transfer format -> [engine] ->
+reference-shaped tables -> SNVprofile directory, with the two engine calls answered by the oracle (a test stub: the CUDA
+engine gives the same answers, tests/test_gpu_*.py).  Everything around the kernels -- batching, offsets, formats,
+tables, the merge-stage summary table, the on-disk store -- is checked against the reference's stored goldens."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN, load_batch, load_lut
+from instrain_b200 import _cabi, cols as cols_mod, reads as reads_mod
+from oracle import restate
+from oracle import summary as osum
+
+
+class OracleEngine:
+    """Same two methods as instrain_b200.engine.Engine, computed by the oracle (test infrastructure)."""
+
+    def __init__(self):
+        self.lut, self.dflt = load_lut()
+        self.formats = []
+
+    def profile_batch(self, ev, ref_codes, splits, min_cov=5, min_freq=0.05, min_snp=20, want=(), reads=None, cols=None, **kw):
+        L = len(ref_codes)
+        if cols is not None:
+            self.formats.append("cols")
+            events = cols_mod.cols_to_events(cols, L)
+        elif "mis_word" in reads:
+            self.formats.append("delta")
+            seg_word, n_words, words = reads_mod.delta_to_words(reads, ref_codes)
+            events = reads_mod.reads_to_events(dict(reads, seg_word=seg_word, n_words=n_words, words=words))
+        else:
+            self.formats.append("segments")
+            events = reads_mod.reads_to_events(reads)
+        events["pair_mm"] = np.asarray(ev["pair_mm"])
+        out = restate.profile_events(events, ref_codes, self.lut, self.dflt, splits, min_cov=min_cov, min_freq=min_freq,
+                                     min_snp=min_snp)
+        out["M"] = out["counts"].shape[1]
+        for k in ("n_snv", "n_ld"):
+            out[k] = len(out[k[2:]])
+        return out
+
+    def scaffold_summary(self, covT, clonT, nmask, bounds):
+        """What K4 returns (include/instrain_b200.h, isb_summary_row), with numpy."""
+        L, M = covT.shape
+        n_sc = len(bounds) - 1
+        rows = np.zeros(n_sc * M, dtype=_cabi.SUMMARY_DT)
+        for s in range(n_sc):
+            sl = slice(int(bounds[s]), int(bounds[s + 1]))
+            cum = np.zeros(sl.stop - sl.start, dtype=np.int64)
+            last = np.full(sl.stop - sl.start, np.nan, dtype=np.float32)
+            for m in range(M):
+                cum = cum + covT[sl, m]
+                c = clonT[sl, m]
+                last = np.where(np.isnan(c), last, c)
+                r = rows[s * M + m]
+                n = len(cum)
+                vals = last[~np.isnan(last)]
+                r["length"], r["nonzero"], r["sum_cov"] = n, np.count_nonzero(cum), cum.sum()
+                r["sum_cov2"] = int((cum.astype(object) ** 2).sum())
+                r["counted"], r["sum_clon"] = len(vals), float(vals.astype(np.float64).sum())
+                sc = np.sort(cum)
+                r["cov_med_lo"], r["cov_med_hi"] = sc[(n - 1) // 2], sc[n // 2]
+                if len(vals):
+                    sv = np.sort(vals)
+                    r["clon_med_lo"], r["clon_med_hi"] = sv[(len(sv) - 1) // 2], sv[len(sv) // 2]
+                else:
+                    r["clon_med_lo"] = r["clon_med_hi"] = np.nan
+                r["present"] = int((covT[sl, m] > 0).any() or (((nmask[sl] >> np.uint64(m)) & np.uint64(1)) != 0).any())
+        return rows
+
+
+def golden_tables(names):
+    from instrain_b200._cabi import CLASS_NAMES
+    batch, exp = load_batch("G1")
+    sn = list(batch["scaffold_names"])
+    off = batch["scaffold_off"].astype(np.int64)
+    sidx = np.searchsorted(off, exp["snv_pos"], side="right") - 1
+    snv = pd.DataFrame({"scaffold": np.array(sn, dtype=object)[sidx], "position": exp["snv_pos"] - off[sidx],
+                        "mm": exp["snv_mm"], "A": exp["snv_cnt"][:, 0], "C": exp["snv_cnt"][:, 1],
+                        "T": exp["snv_cnt"][:, 2], "G": exp["snv_cnt"][:, 3],
+                        "con_base": np.array(list("ACTG"))[exp["snv_con"]], "var_base": np.array(list("ACTG"))[exp["snv_var"]],
+                        "allele_count": exp["snv_allele_count"], "class": np.array(CLASS_NAMES, dtype=object)[exp["snv_cls"]],
+                        "cryptic": exp["snv_cryptic"].astype(bool)})
+    lidx = np.searchsorted(off, exp["ld_pos_a"], side="right") - 1
+    ld = pd.DataFrame({"scaffold": np.array(sn, dtype=object)[lidx], "position_A": exp["ld_pos_a"] - off[lidx],
+                       "position_B": exp["ld_pos_b"] - off[lidx], "mm": exp["ld_mm"], "countAB": exp["ld_counts"][:, 0],
+                       "countAb": exp["ld_counts"][:, 1], "countaB": exp["ld_counts"][:, 2], "countab": exp["ld_counts"][:, 3],
+                       "r2": exp["ld_r2"], "d_prime": exp["ld_d_prime"]})
+    summ = pd.DataFrame(exp["sum_values"], columns=list(exp["sum_columns"]))
+    summ.insert(0, "scaffold", np.array(sn, dtype=object)[exp["sum_scaffold"]])
+    return snv[snv["scaffold"].isin(names)], ld[ld["scaffold"].isin(names)], summ[summ["scaffold"].isin(names)]
+
+
+@pytest.mark.parametrize("transfer,threads", [("segments", 1), ("delta", 2), ("cols", 3)])
+def test_profile_bam_host_side_against_goldens(tmp_path, transfer, threads):
+    from instrain_b200.profile import profile_scaffolds
+    from instrain_b200.store import SNVprofileStore, store_profile
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    eng = OracleEngine()
+    res = profile_scaffolds(bam, rdic, seqs, engine=eng, b200_transfer=transfer, packer_threads=threads)
+    assert eng.formats == [transfer] and not res.failures and sorted(res.scaffold_list) == sorted(rdic)
+    g_snv, g_ld, g_sum = golden_tables(set(rdic))
+    key = ["scaffold", "position", "mm"]
+    a, b = res.raw_snp_table.sort_values(key).reset_index(drop=True), g_snv.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) > 1000
+    for c in ["scaffold", "position", "mm", "A", "C", "T", "G", "con_base", "var_base", "allele_count", "class", "cryptic"]:
+        assert (a[c].values == b[c].values).all(), c
+    key = ["scaffold", "position_A", "position_B", "mm"]
+    a, b = res.raw_linkage_table.sort_values(key).reset_index(drop=True), g_ld.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) > 1000
+    for c in key + ["countAB", "countAb", "countaB", "countab"]:
+        assert (a[c].values == b[c].values).all(), c
+    for c in ("r2", "d_prime"):
+        assert np.allclose(a[c].values, b[c].values, rtol=0, atol=1e-9, equal_nan=True), c
+    key = ["scaffold", "mm"]
+    a = res.cumulative_scaffold_table.sort_values(key).reset_index(drop=True)
+    b = g_sum.sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) > 30 and (a["scaffold"].values == b["scaffold"].values).all()
+    for c in osum.COLUMNS:
+        assert np.allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=0, atol=1e-9, equal_nan=True), c
+    # the SNVprofile directory
+    S = store_profile(str(tmp_path / "p.IS"), bam, res)
+    S2 = SNVprofileStore(str(tmp_path / "p.IS"))
+    assert S2.get("scaffold_list") == res.scaffold_list and len(S2.get("raw_snp_table")) == len(res.raw_snp_table)
+    covT = S2.get("covT")
+    for s, sp in res.scaffolds.items():
+        assert set(covT[s]) == set(sp.covT)
+        for mm in sp.covT:
+            assert np.array_equal(covT[s][mm].values, sp.covT[mm].values) and np.array_equal(covT[s][mm].index.values, sp.covT[mm].index.values)
+    assert S is not None
