@@ -218,9 +218,32 @@ def _msg(mtype, payload, flags=0):
     return struct.pack("<HHB3x", mtype, len(payload), flags) + payload
 
 
+class _FileBuf:
+    """The part of a bytearray the writer uses (len, +=, patching the first bytes), backed by a file: the covT / clonT
+    stores of a 100 Mb profile are gigabytes of deflated chunks, which need not sit in memory before they are written."""
+
+    def __init__(self, fh, n_zero):
+        self.fh, self.n = fh, 0
+        self += b"\0" * n_zero
+
+    def __len__(self):
+        return self.n
+
+    def __iadd__(self, b):
+        self.fh.write(b)
+        self.n += len(b)
+        return self
+
+    def patch_head(self, b):
+        self.fh.seek(0)
+        self.fh.write(b)
+        self.fh.seek(0, 2)
+
+
 class _Writer:
-    def __init__(self):
-        self.buf = bytearray(96 + 40)           # superblock + root object header, patched at the end
+    def __init__(self, fh=None):
+        # superblock + root object header come first and are patched at the end
+        self.buf = _FileBuf(fh, 96 + 40) if fh is not None else bytearray(96 + 40)
         self.entries = []                       # (name bytes, object header address)
 
     def _append(self, b):
@@ -333,6 +356,9 @@ class _Writer:
         assert len(sb) == 96
         root = struct.pack("<BBHII4x", 1, 0, 1, 1, 24) + _msg(0x11, struct.pack("<QQ", btree, heap_addr))
         assert len(root) == 40
+        if isinstance(self.buf, _FileBuf):
+            self.buf.patch_head(sb + root)
+            return len(self.buf)
         self.buf[0:96] = sb
         self.buf[96:136] = root
         return bytes(self.buf)
@@ -349,25 +375,23 @@ def write_hd5(path, datasets, level=4, threads=None):
             threads = min(16, len(os.sched_getaffinity(0)))
         except AttributeError:
             threads = min(16, os.cpu_count() or 1)
-    w = _Writer()
     items = list(datasets.items())
-    if threads <= 1 or len(items) < 2:
-        for name, arr in items:
-            w.add_dataset(name, arr, level)
-    else:
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            window, pending = 4 * threads, []                  # bounded look-ahead: compressed chunks wait in memory
+    with open(path, "wb") as f:                                   # chunks go to the file as they are produced
+        w = _Writer(f)
+        if threads <= 1 or len(items) < 2:
             for name, arr in items:
-                pending.append((name, ex.submit(_Writer.prepare, arr, level)))
-                if len(pending) >= window:
-                    nm, fut = pending.pop(0)
+                w.add_dataset(name, arr, level)
+        else:
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                window, pending = 4 * threads, []                  # bounded look-ahead: compressed chunks wait in memory
+                for name, arr in items:
+                    pending.append((name, ex.submit(_Writer.prepare, arr, level)))
+                    if len(pending) >= window:
+                        nm, fut = pending.pop(0)
+                        w.add_dataset(nm, None, level, prepared=fut.result())
+                for nm, fut in pending:
                     w.add_dataset(nm, None, level, prepared=fut.result())
-            for nm, fut in pending:
-                w.add_dataset(nm, None, level, prepared=fut.result())
-    data = w.finish()
-    with open(path, "wb") as f:
-        f.write(data)
-    return len(data)
+        return w.finish()
 
 
 def store_special(path, obj, threads=None):
