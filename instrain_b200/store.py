@@ -114,6 +114,52 @@ class SNVprofileStore:
     def __str__(self):
         return str(self._read_attributes())
 
+    # ---- user-facing output tables (SNVprofile.generate, SNVprofile.py:192-442) ---------------------------------------------
+    def get_output_base(self):
+        return os.path.join(self.location, "output", os.path.basename(self.location) + "_")
+
+    def _nonredundant(self, name, subset, drop_cryptic=False):
+        """One row per `subset` key: the row of the highest mm (get_nonredundant_*_table, SNVprofile.py:483-522)."""
+        db = self.get(name)
+        if db is not None and drop_cryptic and "cryptic" in db:
+            db = db[db["cryptic"] == False]                              # noqa: E712 - v1.6: cryptic SNVs are not reported
+        if db is None or len(db) == 0:
+            return pd.DataFrame()
+        if "mm" not in db.columns:                                        # a table without levels is already nonredundant
+            return db
+        return db.sort_values("mm", kind="stable").drop_duplicates(subset=subset, keep="last").sort_index().drop(columns=["mm"])
+
+    _OUTPUTS = {
+        "SNVs": ("cumulative_snv_table", ["scaffold", "position"],
+                 ["scaffold", "position", "position_coverage", "allele_count", "ref_base", "con_base", "var_base", "ref_freq",
+                  "con_freq", "var_freq", "A", "C", "T", "G", "gene", "mutation", "mutation_type", "cryptic"]),
+        "scaffold_info": ("cumulative_scaffold_table", ["scaffold"],
+                          ["scaffold", "length", "coverage", "breadth", "nucl_diversity", "coverage_median", "coverage_std",
+                           "coverage_SEM", "breadth_minCov", "breadth_expected", "nucl_diversity_median",
+                           "nucl_diversity_rarefied", "nucl_diversity_rarefied_median", "breadth_rarefied", "conANI_reference",
+                           "popANI_reference", "SNS_count", "SNV_count", "divergent_site_count"]),
+        "linkage": ("raw_linkage_table", ["scaffold", "position_A", "position_B"],
+                    ["scaffold", "position_A", "position_B", "distance", "r2", "d_prime", "r2_normalized", "d_prime_normalized",
+                     "allele_A", "allele_a", "allele_B", "allele_b", "countab", "countAb", "countaB", "countAB", "total"]),
+    }
+
+    def generate(self, name, store=True, return_table=False, **kwargs):
+        """The user-facing tables the hot path feeds -- SNVs, scaffold_info, linkage -- as the reference's
+        SNVprofile.generate writes them into output/ (one row per site / scaffold / site pair at its highest mm, the
+        reference's column order, .tsv, .tsv.gz beyond 1e6 rows).  gene_info / genome_info / mapping_info come from other
+        modules of inStrain and are not produced here."""
+        if name not in self._OUTPUTS:
+            raise KeyError("generate(%r): only %s come out of the profile hot path" % (name, sorted(self._OUTPUTS)))
+        source, subset, order = self._OUTPUTS[name]
+        db = self._nonredundant(source, subset, drop_cryptic=(name == "SNVs"))
+        if len(db) > 0:                                                   # reorder_columns (SNVprofile.py:1151-1165);
+            cols = set(db.columns)                                        # columns outside the order keep the table's order
+            db = db[[c for c in order if c in cols] + [c for c in db.columns if c not in order]]
+        if store:
+            ft = ".tsv.gz" if (len(db) > 1e6 or kwargs.get("force_compress", False)) else ".tsv"
+            db.to_csv(self.get_output_base() + name + ft, index=False, sep="\t")
+        return db if return_table else None
+
     # ---- storage back ends --------------------------------------------------------------------------------------------
     def _save(self, typ, value, loc):
         if typ == "dictionary":
@@ -164,4 +210,6 @@ def store_profile(ISP_loc, bam, res):
     S.store("scaffold_2_mm_2_read_2_snvs", {}, "pickle", "crazy nonsense needed for linkage")
     S.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
     S.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
+    for name in ("SNVs", "scaffold_info", "linkage"):                     # ProfileController.write_output (controller.py:352-360)
+        S.generate(name)
     return S

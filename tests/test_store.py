@@ -116,3 +116,40 @@ def test_tables_equal_reference_stored_csv(g1_result):
             assert np.allclose(mine[c].values, gold[c].values, rtol=0, atol=1e-9, equal_nan=True), c
         else:
             assert (mine[c].values == gold[c].values).all(), c
+
+
+REF_IS = "/root/reference/test/test_data/N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.forRC.IS"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_IS), reason="reference test data not present")
+@pytest.mark.parametrize("name,key", [("SNVs", ["scaffold", "position"]), ("scaffold_info", ["scaffold"]),
+                                      ("linkage", ["scaffold", "position_A", "position_B"])])
+def test_generate_reproduces_reference_output_tables(tmp_path, name, key):
+    """SNVprofileStore.generate (the user-facing output/*.tsv of the hot path's tables; SNVprofile.generate,
+    SNVprofile.py:192-442) applied to the reference's OWN stored raw tables reproduces the reference's stored output file:
+    same rows, same values, the reference's column order (columns the profile hot path does not own -- gene annotations
+    -- excepted)."""
+    import shutil
+    from instrain_b200.store import SNVprofileStore
+    loc = tmp_path / os.path.basename(REF_IS)
+    os.makedirs(loc / "raw_data")
+    for f in ("attributes.tsv", "cumulative_snv_table.csv.gz", "cumulative_scaffold_table.csv.gz", "raw_linkage_table.csv.gz"):
+        shutil.copy(os.path.join(REF_IS, "raw_data", f), loc / "raw_data" / f)
+    S = SNVprofileStore(str(loc))
+    got = S.generate(name, return_table=True)
+    out = str(loc / "output" / (os.path.basename(REF_IS) + "_" + name + ".tsv"))
+    assert os.path.exists(out)
+    ref = pd.read_csv(os.path.join(REF_IS, "output", os.path.basename(REF_IS) + "_" + name + ".tsv"), sep="\t")
+    back = pd.read_csv(out, sep="\t")
+    assert len(back) == len(got) == len(ref) > 100
+    gene_cols = {"gene", "mutation", "mutation_type"}                  # merged in from SNP_mutation_types (gene module)
+    common = [c for c in ref.columns if c in back.columns and c not in gene_cols]
+    assert set(ref.columns) - set(back.columns) <= gene_cols
+    assert [c for c in back.columns if c in common][:len(key)] == key  # the reference's leading column order
+    a = back.sort_values(key).reset_index(drop=True)
+    b = ref.sort_values(key).reset_index(drop=True)
+    for c in common:
+        if a[c].dtype.kind == "f" or b[c].dtype.kind == "f":
+            assert np.allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=0, atol=1e-12, equal_nan=True), c
+        else:
+            assert (a[c].values == b[c].values).all(), c
