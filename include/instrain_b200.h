@@ -494,6 +494,10 @@ int64_t isb_filter_apply(void *filter, double min_read_ani, int min_mapq, double
 int isb_filter_n_refs(void *filter);
 double isb_filter_max_insert(void *filter);
 void isb_filter_tally(void *filter, int tid, int64_t tally[6]);
+/* The other per-scaffold columns of mapping_info: stats[10] = unfiltered_reads, unfiltered_pairs, unfiltered_singletons,
+ * mean_mistmaches, mean_insert_distance, mean_mapq_score, mean_pair_length, mean_PID, median_insert (over the pairs that
+ * pass the pairing filter; NaN when there are none), and that number of pairs. */
+void isb_filter_stats(void *filter, int tid, double stats[10]);
 int64_t isb_filter_n_pairs(void *filter, int tid);
 int64_t isb_filter_names_bytes(void *filter, int tid);
 void isb_filter_copy(void *filter, int tid, char *names_blob, int64_t *name_off, int32_t *mm);

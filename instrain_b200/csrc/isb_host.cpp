@@ -706,6 +706,37 @@ int64_t isb_filter_apply(void *h, double min_read_ani, int min_mapq, double max_
     return kept;
 }
 
+// Per-scaffold columns of the reference's mapping_info table that are not threshold tallies (paired_read_filter tallies,
+// filter_reads.py:484-502, and the means / median of filter_scaff2pair2info, :253-266, taken over the pairs that pass the
+// pairing filter): out[10] = unfiltered_reads, unfiltered_pairs, unfiltered_singletons, mean_mistmaches,
+// mean_insert_distance, mean_mapq_score, mean_pair_length, mean_PID, median_insert, number of pairs averaged over.
+void isb_filter_stats(void *h, int tid, double out[10])
+{
+    const ScaffoldPairs &sp = ((Filter *)h)->sc[tid];
+    double reads = 0, pairs = 0, singles = 0, s_nm = 0, s_ins = 0, s_mapq = 0, s_len = 0, s_pid = 0;
+    std::vector<int64_t> ins;
+    for (const PairInfo &pi : sp.info) {
+        reads += pi.reads;
+        if (pi.reads == 1) singles += 1;
+        if (pi.reads != 2) continue;
+        pairs += 1;
+        s_nm += (double)pi.nm; s_ins += (double)pi.insert; s_mapq += (double)pi.mapq; s_len += (double)pi.length;
+        s_pid += 1.0 - (double)pi.nm / (double)pi.length;
+        ins.push_back(pi.insert);
+    }
+    double median = 0.0 / 0.0;
+    if (!ins.empty()) {
+        const size_t n = ins.size(), k = n / 2;
+        std::nth_element(ins.begin(), ins.begin() + k, ins.end());
+        median = (double)ins[k];
+        if (n % 2 == 0) median = ((double)*std::max_element(ins.begin(), ins.begin() + k) + (double)ins[k]) / 2.0;
+    }
+    const double nan = 0.0 / 0.0;
+    out[0] = reads; out[1] = pairs; out[2] = singles;
+    out[3] = pairs ? s_nm / pairs : nan; out[4] = pairs ? s_ins / pairs : nan; out[5] = pairs ? s_mapq / pairs : nan;
+    out[6] = pairs ? s_len / pairs : nan; out[7] = pairs ? s_pid / pairs : nan; out[8] = median; out[9] = pairs;
+}
+
 int isb_filter_n_refs(void *h) { return (int)((Filter *)h)->sc.size(); }
 double isb_filter_max_insert(void *h) { return ((Filter *)h)->max_insert; }
 void isb_filter_tally(void *h, int tid, int64_t out[6]) { memcpy(out, ((Filter *)h)->sc[tid].tally, sizeof(int64_t) * 6); }

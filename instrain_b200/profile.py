@@ -262,6 +262,7 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     `.store` is the on-disk object (same store / get interface as inStrain.SNVprofile.SNVprofile); `.get(name)` serves
     the in-memory tables."""
     s2s = kwargs.pop("s2s", None)
+    report = None
     if s2s is None:
         raise ValueError("profile_bam needs kwargs['s2s'] (scaffold -> sequence), as ProfileController.run_profile passes it")
     if sR2M is None:
@@ -270,8 +271,10 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
         from .read_filter import filter_reads
         with _BP(bam) as bp:
             names = bp.ref_names
-        sR2M, _, _ = filter_reads(bam, names, **{k: kwargs[k] for k in ("min_read_ani", "min_mapq", "max_insert_relative",
-                                                                       "min_insert") if k in kwargs})
+        fkw = {k: kwargs[k] for k in ("min_read_ani", "min_mapq", "max_insert_relative", "min_insert") if k in kwargs}
+        sR2M, _, _ = filter_reads(bam, names, **fkw)
+        from .read_filter import mapping_info as _mapping_info
+        report = _mapping_info(bam, names, **fkw)
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
@@ -279,5 +282,7 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     # inStrain.SNVprofile.SNVprofile(ISP_loc) of the reference opens it unchanged
     if ISP_loc is not None and kwargs.get("store", True):
         from .store import store_profile
-        res.store = store_profile(ISP_loc, bam, res)
+        fdef = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)    # this shim's filter defaults
+        res.store = store_profile(ISP_loc, bam, res, mapping_info=report,
+                                  **{k: kwargs.get(k, v) for k, v in fdef.items()})
     return res

@@ -148,8 +148,23 @@ class SNVprofileStore:
         SNVprofile.generate writes them into output/ (one row per site / scaffold / site pair at its highest mm, the
         reference's column order, .tsv, .tsv.gz beyond 1e6 rows).  gene_info / genome_info / mapping_info come from other
         modules of inStrain and are not produced here."""
+        if name == "mapping_info":                                       # the read filter's report, with its settings as a header
+            db = self.get("mapping_info")                                # line (write_mapping_info, filter_reads.py:699-720)
+            if db is None:
+                return None
+            order = ["scaffold", "pass_pairing_filter", "filtered_pairs"]
+            db = db[order + [c for c in db.columns if c not in order]]
+            if store:
+                values = {"min_read_ani": kwargs.get("min_read_ani", 0.97), "max_insert_relative": kwargs.get("max_insert_relative", 3),
+                          "min_insert": kwargs.get("min_insert", 50), "min_mapq": kwargs.get("min_mapq", 2),
+                          "pairing_filter": kwargs.get("pairing_filter", "paired_only")}
+                ft = ".tsv.gz" if kwargs.get("force_compress", False) else ".tsv"
+                with open(self.get_output_base() + name + ft, "w") as f:
+                    f.write("# {0}\n".format(" ".join("{0}:{1}".format(k, v) for k, v in values.items())))
+                    db.to_csv(f, index=False, sep="\t")
+            return db if return_table else None
         if name not in self._OUTPUTS:
-            raise KeyError("generate(%r): only %s come out of the profile hot path" % (name, sorted(self._OUTPUTS)))
+            raise KeyError("generate(%r): only %s come out of the profile hot path" % (name, sorted(self._OUTPUTS) + ["mapping_info"]))
         source, subset, order = self._OUTPUTS[name]
         db = self._nonredundant(source, subset, drop_cryptic=(name == "SNVs"))
         if len(db) > 0:                                                   # reorder_columns (SNVprofile.py:1151-1165);
@@ -196,9 +211,13 @@ class SNVprofileStore:
         Adb.to_csv(self._attributes_loc(), sep="\t", index_label="name")
 
 
-def store_profile(ISP_loc, bam, res):
-    """What gen_snv_profile stores for a profile run (profile_utilities.py:670-706), from a ProfileResult."""
+def store_profile(ISP_loc, bam, res, mapping_info=None, **kwargs):
+    """What gen_snv_profile stores for a profile run (profile_utilities.py:670-706), from a ProfileResult; plus the read
+    filter's report when profile_bam ran the filter itself (ProfileController.load_paired_reads stores it,
+    controller.py:301-304).  kwargs: the filter settings for the header of output/*_mapping_info.tsv."""
     S = SNVprofileStore(ISP_loc)
+    if mapping_info is not None:
+        S.store("mapping_info", mapping_info, "pandas", "Report on reads")
     S.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
     S.store("bam_loc", bam, "value", "Location of .bam file")
     S.store("scaffold_list", list(res.scaffold_list), "list", "1d list of scaffolds that were profiled")
@@ -212,4 +231,6 @@ def store_profile(ISP_loc, bam, res):
     S.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
     for name in ("SNVs", "scaffold_info", "linkage"):                     # ProfileController.write_output (controller.py:352-360)
         S.generate(name)
+    if mapping_info is not None:
+        S.generate("mapping_info", **kwargs)
     return S

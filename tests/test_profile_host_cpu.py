@@ -133,3 +133,37 @@ def test_profile_bam_host_side_against_goldens(tmp_path, transfer, threads):
         for mm in sp.covT:
             assert np.array_equal(covT[s][mm].values, sp.covT[mm].values) and np.array_equal(covT[s][mm].index.values, sp.covT[mm].index.values)
     assert S is not None
+
+
+def test_profile_bam_runs_its_own_read_filter_and_reports_it(tmp_path, monkeypatch):
+    """profile_bam(sR2M=None): the C++ read filter supplies sR2M, its report becomes the stored `mapping_info` attribute and
+    output/*_mapping_info.tsv (settings as a `#` header line, the reference's leading columns), next to the SNVs /
+    scaffold_info / linkage tables."""
+    import instrain_b200.profile as P
+    from instrain_b200.store import SNVprofileStore
+
+    class E(OracleEngine):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(P, "Engine", E)
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    isp = str(tmp_path / "own_filter.IS")
+    res = P.profile_bam(bam, None, None, isp, s2s=seqs, min_read_ani=0.95)
+    assert not res.failures and len(res.raw_snp_table) > 1000
+    S = SNVprofileStore(isp)
+    mi = S.get("mapping_info")
+    assert mi["scaffold"].tolist()[0] == "all_scaffolds" and set(mi["scaffold"][1:]) >= set(res.scaffold_list)
+    assert int(mi["filtered_pairs"][0]) == int(mi["filtered_pairs"][1:].sum()) > 1000
+    out = os.path.join(isp, "output")
+    base = "own_filter.IS_"
+    assert {base + n + ".tsv" for n in ("SNVs", "scaffold_info", "linkage", "mapping_info")} <= set(os.listdir(out))
+    lines = open(os.path.join(out, base + "mapping_info.tsv")).read().splitlines()
+    assert lines[0] == "# min_read_ani:0.95 max_insert_relative:3 min_insert:50 min_mapq:-1 pairing_filter:paired_only"
+    assert lines[1].split("\t")[:3] == ["scaffold", "pass_pairing_filter", "filtered_pairs"]
+    snvs = pd.read_csv(os.path.join(out, base + "SNVs.tsv"), sep="\t")
+    assert not snvs.duplicated(["scaffold", "position"]).any() and list(snvs.columns[:4]) == ["scaffold", "position", "position_coverage", "allele_count"]

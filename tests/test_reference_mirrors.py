@@ -74,3 +74,22 @@ def test_profile_3_mirror():
     top = Odb.sort_values("mm").drop_duplicates(subset="scaffold", keep="last")
     for scaff, db in Sdb.sort_values("mm").drop_duplicates(subset=["scaffold", "position"], keep="last").groupby("scaffold"):
         assert top["divergent_site_count"][top["scaffold"] == scaff].fillna(0).tolist()[0] == len(db), scaff
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_mapping_info_reproduces_reference_table(which):
+    """instrain_b200.read_filter.mapping_info (C++ filter) against the reference's stored mapping_info of both samples:
+    all 19 columns of all 179 rows (per-scaffold tallies, means, median insert, and the weighted all_scaffolds row)."""
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.read_filter import MAPPING_INFO_COLUMNS, mapping_info
+    bam = TD + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010%s.sorted.bam" % which
+    ref = pd.read_csv(TD + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010%s.forRC.IS/raw_data/mapping_info.csv.gz" % which,
+                      index_col=0)
+    with BamPacker(bam) as bp:
+        names = bp.ref_names
+    got = mapping_info(bam, names)
+    assert list(got.columns) == list(ref.columns) == MAPPING_INFO_COLUMNS and len(got) == len(ref) == 179
+    assert got["scaffold"][0] == ref["scaffold"][0] == "all_scaffolds" and set(got["scaffold"]) == set(ref["scaffold"])
+    a, b = got.set_index("scaffold").loc[ref["scaffold"]], ref.set_index("scaffold")
+    for c in MAPPING_INFO_COLUMNS[1:]:
+        assert np.allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=0, atol=1e-9, equal_nan=True), c
