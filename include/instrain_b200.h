@@ -491,6 +491,13 @@ void isb_reads_free(void *reads);
  * pass_max_insert, pass_min_insert, pass_min_mapq, filtered_pairs (the mapping_info columns). */
 void *isb_filter_open(const char *bam_path);
 int64_t isb_filter_apply(void *filter, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert);
+/* All pairing filters of the reference + priority reads (paired_read_filter, filter_reads.py:471-532): pairing_mode 0 =
+ * paired_only (isb_filter_apply), 1 = non_discordant, 2 = all_reads (mates on two scaffolds are merged: summed NM, insert
+ * -2); the n_priority names pass the pairing filter regardless.  tally2[3] = unfiltered_priority_reads,
+ * filtered_singletons, filtered_priority_reads.  Returns the number of kept names, -1 for an unknown mode. */
+int64_t isb_filter_apply2(void *filter, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert,
+                          int pairing_mode, int64_t n_priority, const char *names_blob, const int64_t *name_off);
+void isb_filter_tally2(void *filter, int tid, int64_t tally2[3]);
 int isb_filter_n_refs(void *filter);
 double isb_filter_max_insert(void *filter);
 void isb_filter_tally(void *filter, int tid, int64_t tally[6]);

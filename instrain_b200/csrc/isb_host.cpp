@@ -558,6 +558,10 @@ struct PairInfo {
     int32_t reads = 0;
     int32_t first = 0, last = 0;       // aligned span of the first read
     uint8_t keep = 0;
+    // what the pairing filter hands to the thresholds (isb_filter_apply2): selected, and the possibly merged info
+    uint8_t sel = 0;
+    int64_t e_nm = 0, e_insert = -1, e_mapq = 0, e_length = 0;
+    int32_t e_reads = 0;
 };
 
 struct ScaffoldPairs {
@@ -565,6 +569,7 @@ struct ScaffoldPairs {
     std::vector<PairInfo> info;
     std::unordered_map<std::string, int32_t> index;
     int64_t tally[6] = {0, 0, 0, 0, 0, 0};           // pass_pairing_filter, pass_min_read_ani, pass_max_insert, pass_min_insert, pass_min_mapq, filtered_pairs
+    int64_t tally2[3] = {0, 0, 0};                   // unfiltered_priority_reads, filtered_singletons, filtered_priority_reads
 };
 
 struct Filter {
@@ -668,6 +673,92 @@ void *isb_filter_open(const char *bam_path)
     return f;
 }
 
+// Pairing filter + thresholds, all modes of the reference (paired_read_filter, filter_reads.py:471-532, then
+// filter_scaff2pair2info, :201-300).  pairing_mode: 0 = paired_only, 1 = non_discordant, 2 = all_reads; priority reads
+// (n_priority names in names_blob / name_off) pass the pairing filter regardless.  Scaffolds in header order, names in
+// file order -- the reference's dict orders.  Returns the number of kept names, -1 for an unknown mode.
+int64_t isb_filter_apply2(void *h, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert,
+                          int pairing_mode, int64_t n_priority, const char *names_blob, const int64_t *name_off)
+{
+    Filter *f = (Filter *)h;
+    if (pairing_mode < 0 || pairing_mode > 2) return -1;
+    std::unordered_map<std::string, int> priority;
+    for (int64_t i = 0; i < n_priority; ++i)
+        priority.emplace(std::string(names_blob + name_off[i], (size_t)(name_off[i + 1] - name_off[i])), 1);
+    std::unordered_map<std::string, std::pair<int32_t, int32_t>> where;          // name -> (scaffold, index) of its first copy
+    for (size_t s = 0; s < f->sc.size(); ++s) {
+        ScaffoldPairs &sp = f->sc[s];
+        sp.tally2[0] = sp.tally2[1] = sp.tally2[2] = 0;
+        for (size_t k = 0; k < sp.info.size(); ++k) {
+            PairInfo &pi = sp.info[k];
+            pi.sel = 0; pi.keep = 0;
+            pi.e_nm = pi.nm; pi.e_insert = pi.insert; pi.e_mapq = pi.mapq; pi.e_length = pi.length; pi.e_reads = pi.reads;
+            const bool prio = !priority.empty() && priority.count(sp.names[k]);
+            sp.tally2[0] += prio;
+            if (pairing_mode == 0) {
+                pi.sel = pi.reads == 2 || prio;
+            } else if (pairing_mode == 1) {
+                auto it = where.find(sp.names[k]);
+                if (it == where.end() || prio) {
+                    pi.sel = 1;
+                    where[sp.names[k]] = {(int32_t)s, (int32_t)k};
+                } else {                                                         // discordant: drop the earlier copy too
+                    f->sc[it->second.first].info[it->second.second].sel = 0;
+                }
+            } else {
+                auto it = where.find(sp.names[k]);
+                if (it != where.end()) {                                         // _merge_info with the first copy
+                    PairInfo &o = f->sc[it->second.first].info[it->second.second];
+                    const int64_t nm = pi.e_nm + o.e_nm, mq = pi.e_mapq + o.e_mapq, ln = pi.e_length + o.e_length;
+                    const int32_t rd = pi.e_reads + o.e_reads;
+                    pi.e_nm = o.e_nm = nm; pi.e_insert = o.e_insert = -2; pi.e_mapq = o.e_mapq = mq;
+                    pi.e_length = o.e_length = ln; pi.e_reads = o.e_reads = rd;
+                    pi.sel = 1;
+                } else {
+                    where[sp.names[k]] = {(int32_t)s, (int32_t)k};
+                    pi.sel = 1;
+                }
+            }
+        }
+    }
+    std::vector<int64_t> ins;
+    for (auto &sp : f->sc)
+        for (auto &pi : sp.info)
+            if (pi.sel && pi.e_reads == 2) ins.push_back(pi.e_insert);
+    double median = 0.0;
+    if (!ins.empty()) {                                               // np.median
+        const size_t n = ins.size(), k = n / 2;
+        std::nth_element(ins.begin(), ins.begin() + k, ins.end());
+        median = (double)ins[k];
+        if (n % 2 == 0) median = ((double)*std::max_element(ins.begin(), ins.begin() + k) + (double)ins[k]) / 2.0;
+    }
+    f->max_insert = median * max_insert_relative;
+    int64_t kept = 0;
+    for (auto &sp : f->sc) {
+        for (int i = 0; i < 6; ++i) sp.tally[i] = 0;
+        for (size_t k = 0; k < sp.info.size(); ++k) {
+            PairInfo &pi = sp.info[k];
+            if (!pi.sel) continue;
+            sp.tally[0]++;
+            const bool f_ani = (1.0 - (double)pi.e_nm / (double)pi.e_length) > min_read_ani;
+            const bool f_mapq = pi.e_mapq > min_mapq;
+            bool f_min = true, f_max = true;
+            if (pi.e_reads == 2 && pi.e_insert != -1) { f_min = pi.e_insert > min_insert; f_max = (double)pi.e_insert < f->max_insert; }
+            sp.tally[1] += f_ani; sp.tally[2] += f_max; sp.tally[3] += f_min; sp.tally[4] += f_mapq;
+            if (f_ani && f_mapq && f_min && f_max) {
+                pi.keep = 1;
+                sp.tally[5]++;
+                ++kept;
+                sp.tally2[1] += pi.e_reads == 1;
+                sp.tally2[2] += !priority.empty() && priority.count(sp.names[k]);
+            }
+        }
+    }
+    return kept;
+}
+
+void isb_filter_tally2(void *h, int tid, int64_t out[3]) { memcpy(out, ((Filter *)h)->sc[tid].tally2, sizeof(int64_t) * 3); }
+
 // Apply the thresholds (reference defaults: 0.95, -1, 3, 50).  Returns the number of kept pairs.
 int64_t isb_filter_apply(void *h, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert)
 {
@@ -700,7 +791,7 @@ int64_t isb_filter_apply(void *h, double min_read_ani, int min_mapq, double max_
             bool f_min = true, f_max = true;
             if (pi.insert != -1) { f_min = pi.insert > min_insert; f_max = (double)pi.insert < f->max_insert; }
             sp.tally[1] += f_ani; sp.tally[2] += f_max; sp.tally[3] += f_min; sp.tally[4] += f_mapq;
-            if (f_ani && f_mapq && f_min && f_max) { pi.keep = 1; sp.tally[5]++; ++kept; }
+            if (f_ani && f_mapq && f_min && f_max) { pi.keep = 1; pi.e_nm = pi.nm; sp.tally[5]++; ++kept; }
         }
     }
     return kept;
@@ -758,7 +849,7 @@ void isb_filter_copy(void *h, int tid, char *names_blob, int64_t *name_off, int3
         name_off[k] = off;
         memcpy(names_blob + off, sp.names[i].data(), sp.names[i].size());
         off += (int64_t)sp.names[i].size();
-        mm[k] = (int32_t)sp.info[i].nm;
+        mm[k] = (int32_t)sp.info[i].e_nm;                         // summed NM (of both scaffolds' reads under all_reads)
         ++k;
     }
     name_off[k] = off;

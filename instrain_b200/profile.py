@@ -271,10 +271,16 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
         from .read_filter import filter_reads
         with _BP(bam) as bp:
             names = bp.ref_names
-        fkw = {k: kwargs[k] for k in ("min_read_ani", "min_mapq", "max_insert_relative", "min_insert") if k in kwargs}
-        sR2M, _, _ = filter_reads(bam, names, **fkw)
-        from .read_filter import mapping_info as _mapping_info
-        report = _mapping_info(bam, names, **fkw)
+        fkw = {k: kwargs[k] for k in ("min_read_ani", "min_mapq", "max_insert_relative", "min_insert", "pairing_filter")
+               if k in kwargs}
+        pr = kwargs.get("priority_reads")
+        if pr is not None and not isinstance(pr, (set, list, tuple)):      # the CLI hands a file name (argumentParser.py:95-97)
+            from .read_filter import load_priority_reads
+            pr = load_priority_reads(pr)
+        sR2M, _, _ = filter_reads(bam, names, priority_reads=pr or (), **fkw)
+        if fkw.get("pairing_filter", "paired_only") == "paired_only" and not pr:
+            from .read_filter import mapping_info as _mapping_info
+            report = _mapping_info(bam, names, **fkw)
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)

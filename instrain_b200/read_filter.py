@@ -1,7 +1,8 @@
-"""BAM -> sR2M with the reference's default read filter (ctypes face of the C++ filter in csrc/isb_host.cpp).
+"""BAM -> sR2M with the reference's read filter (ctypes face of the C++ filter in csrc/isb_host.cpp).
 
-Mirrors inStrain.filter_reads.load_paired_reads (inStrain/filter_reads.py:157-199) for pairing_filter='paired_only'
-without priority reads: returns (scaffold -> {read-pair name -> summed NM}, per-scaffold tallies, max_insert).
+Mirrors inStrain.filter_reads.load_paired_reads (inStrain/filter_reads.py:157-199): every pairing filter ('paired_only',
+'non_discordant', 'all_reads') and priority reads; returns (scaffold -> {read-pair name -> summed NM}, per-scaffold
+tallies, max_insert).
 """
 import ctypes as C
 
@@ -21,6 +22,9 @@ def _lib():
         L.isb_filter_open.argtypes = [C.c_char_p]
         L.isb_filter_apply.restype = i64
         L.isb_filter_apply.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int]
+        L.isb_filter_apply2.restype = i64
+        L.isb_filter_apply2.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, i64, C.c_char_p, vp]
+        L.isb_filter_tally2.argtypes = [vp, C.c_int, vp]
         L.isb_filter_n_refs.restype = C.c_int
         L.isb_filter_n_refs.argtypes = [vp]
         L.isb_filter_max_insert.restype = C.c_double
@@ -37,21 +41,48 @@ def _lib():
     return L
 
 
-def filter_reads(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50, **_):
+PAIRING_MODES = {"paired_only": 0, "non_discordant": 1, "all_reads": 2}
+
+
+def _apply(lib, h, min_read_ani, min_mapq, max_insert_relative, min_insert, pairing_filter, priority_reads):
+    if pairing_filter not in PAIRING_MODES:
+        raise ValueError("Do not know paired read filter %r" % (pairing_filter,))
+    if pairing_filter == "paired_only" and not priority_reads:
+        lib.isb_filter_apply(h, float(min_read_ani), int(min_mapq), float(max_insert_relative), int(min_insert))
+        return
+    enc = [s.encode() for s in priority_reads]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        off[1:] = np.cumsum([len(b) for b in enc])
+    if lib.isb_filter_apply2(h, float(min_read_ani), int(min_mapq), float(max_insert_relative), int(min_insert),
+                             PAIRING_MODES[pairing_filter], len(enc), b"".join(enc), off.ctypes.data) < 0:
+        raise ValueError("isb_filter_apply2 failed")
+
+
+def filter_reads(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50,
+                 pairing_filter="paired_only", priority_reads=(), **_):
     """ref_names: the BAM's reference names in header order (BamPacker(bam).ref_names).  Returns (sR2M, tallies, max_insert);
-    scaffolds without kept pairs are absent from sR2M (as parse_filter_reads drops them, controller.py:260-322)."""
+    scaffolds without kept pairs are absent from sR2M (as parse_filter_reads drops them, controller.py:260-322).
+    pairing_filter: 'paired_only' (default), 'non_discordant' or 'all_reads'; priority_reads: names that pass the pairing
+    filter regardless (filter_reads.py:471-532)."""
     lib = _lib()
     h = lib.isb_filter_open(bam.encode())
     if not h:
         raise IOError("cannot read BAM %s" % bam)
     try:
-        lib.isb_filter_apply(h, float(min_read_ani), int(min_mapq), float(max_insert_relative), int(min_insert))
+        priority_reads = list(priority_reads)
+        _apply(lib, h, min_read_ani, min_mapq, max_insert_relative, min_insert, pairing_filter, priority_reads)
         sr2m, tallies = {}, {}
         for tid in range(lib.isb_filter_n_refs(h)):
             t = np.zeros(6, dtype=np.int64)
             lib.isb_filter_tally(h, tid, t.ctypes.data)
             if t[0]:
                 tallies[ref_names[tid]] = dict(zip(TALLY_COLUMNS, (int(x) for x in t)))
+                if pairing_filter != "paired_only" or priority_reads:
+                    t2 = np.zeros(3, dtype=np.int64)
+                    lib.isb_filter_tally2(h, tid, t2.ctypes.data)
+                    tallies[ref_names[tid]].update(unfiltered_priority_reads=int(t2[0]), filtered_singletons=int(t2[1]),
+                                                   filtered_priority_reads=int(t2[2]))
             n = int(lib.isb_filter_n_pairs(h, tid))
             if n == 0:
                 continue
@@ -66,13 +97,26 @@ def filter_reads(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_rela
         lib.isb_filter_free(h)
 
 
+def load_priority_reads(file_loc):
+    """Names of the reads that pass the pairing filter regardless (--priority_reads; load_priority_reads,
+    filter_reads.py:428-469): a FASTQ (names from the @ lines) or a plain list of names, optionally gzipped."""
+    import gzip
+    opener = gzip.open if str(file_loc).endswith(".gz") else open
+    with opener(file_loc, "rt") as f:
+        lines = f.readlines()
+    if lines and lines[0].startswith("@"):
+        return {ln[1:].strip() for ln in lines if ln.startswith("@")}
+    return {ln.strip() for ln in lines}
+
+
 MAPPING_INFO_COLUMNS = ["scaffold", "unfiltered_reads", "unfiltered_pairs", "unfiltered_singletons", "unfiltered_priority_reads",
                         "pass_pairing_filter", "pass_min_read_ani", "pass_max_insert", "pass_min_insert", "pass_min_mapq",
                         "filtered_pairs", "filtered_singletons", "filtered_priority_reads", "mean_mistmaches",
                         "mean_insert_distance", "mean_mapq_score", "mean_pair_length", "mean_PID", "median_insert"]
 
 
-def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50, **_):
+def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50,
+                 pairing_filter="paired_only", priority_reads=(), **_):
     """The reference's `mapping_info` table (the read report of filter_scaff2pair2info, filter_reads.py:230-298, with the
     pairing tallies of paired_read_filter, :484-502) for the default pairing filter: one row per scaffold with reads,
     preceded by the `all_scaffolds` row (sums; means weighted by pass_pairing_filter)."""
@@ -82,7 +126,11 @@ def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_rela
     if not h:
         raise IOError("cannot read BAM %s" % bam)
     try:
-        lib.isb_filter_apply(h, float(min_read_ani), int(min_mapq), float(max_insert_relative), int(min_insert))
+        priority_reads = list(priority_reads)
+        if pairing_filter != "paired_only" or priority_reads:
+            raise NotImplementedError("mapping_info: the means are taken over the paired_only selection; other pairing filters "
+                                      "are served by filter_reads (sR2M + tallies)")
+        _apply(lib, h, min_read_ani, min_mapq, max_insert_relative, min_insert, pairing_filter, priority_reads)
         rows = []
         for tid in range(lib.isb_filter_n_refs(h)):
             t = np.zeros(6, dtype=np.int64)

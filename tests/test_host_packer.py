@@ -98,7 +98,7 @@ def test_read_filter_matches_restatement_on_fixture_bam():
     assert got == {s: d for s, d in exp.items() if d}
     for s, t in exp_tal.items():
         if t["pass_pairing_filter"]:
-            assert tal[s] == t, s
+            assert tal[s] == {k: t[k] for k in tal[s]}, s      # the six threshold tallies of the default mode
     # non-default thresholds
     from oracle import read_filter as orf
     refs, reads = bamio.read_bam(path)
@@ -343,3 +343,15 @@ def test_profile_scaffolds_host_loop_without_gpu():
     assert int(words.sum()) > 0
     assert seen["cols"]["cols"]["n_chunks"] > 0 and int((seen["cols"]["cols"]["ids"] >= 0).sum()) == int(
         (((rd["seg_start"].astype(np.int64) & 7) + rd["seg_len"].astype(np.int64) + 7) // 8).sum())
+
+
+def test_priority_read_files(tmp_path):
+    from instrain_b200.read_filter import load_priority_reads
+    (tmp_path / "a.fastq").write_text("@r1 extra\nACGT\n+\nIIII\n@r2\nAC\n+\nII\n")
+    (tmp_path / "b.txt").write_text("r3\nr4\n")
+    import gzip
+    with gzip.open(str(tmp_path / "c.txt.gz"), "wt") as f:
+        f.write("r5\n")
+    assert load_priority_reads(str(tmp_path / "a.fastq")) == {"r1 extra", "r2"}
+    assert load_priority_reads(str(tmp_path / "b.txt")) == {"r3", "r4"}
+    assert load_priority_reads(str(tmp_path / "c.txt.gz")) == {"r5"}

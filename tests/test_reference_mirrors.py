@@ -93,3 +93,48 @@ def test_mapping_info_reproduces_reference_table(which):
     a, b = got.set_index("scaffold").loc[ref["scaffold"]], ref.set_index("scaffold")
     for c in MAPPING_INFO_COLUMNS[1:]:
         assert np.allclose(a[c].values.astype(float), b[c].values.astype(float), rtol=0, atol=1e-9, equal_nan=True), c
+
+
+def _ref_filter(s2p2i, pairing_filter, priority, **thr):
+    """The reference's OWN paired_read_filter + filter_scaff2pair2info (imported from /root/reference) on pair infos."""
+    from oracle import ref_harness
+    ref_harness.load_reference()
+    import inStrain.filter_reads as fr
+    as_ref = {s: {p: np.array(list(i) + [0, 0], dtype="int64") for p, i in d.items()} for s, d in s2p2i.items()}
+    tallys = {}
+    filt = fr.paired_read_filter(as_ref, priority_reads_set=set(priority), tallys=tallys, pairing_filter=pairing_filter)
+    r2m, Rdb = fr.filter_scaff2pair2info(filt, tallys, priority_reads_set=set(priority), pairing_filter=pairing_filter, **thr)
+    return {s: {p: int(v) for p, v in d.items()} for s, d in r2m.items()}, Rdb
+
+
+@pytest.mark.parametrize("pairing_filter,use_priority", [("paired_only", True), ("non_discordant", False),
+                                                         ("non_discordant", True), ("all_reads", False)])
+def test_read_filter_modes_against_reference_functions(pairing_filter, use_priority):
+    """The non-default pairing filters and priority reads: restatement (oracle/read_filter.py) and the C++ filter against
+    the reference's own paired_read_filter / filter_scaff2pair2info run on the same pair infos -- sR2M and every tally."""
+    from oracle import read_filter as orf
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.read_filter import filter_reads
+    refs, reads = bamio.read_bam(BAM)
+    by = {}
+    for r in reads:
+        if r.tid >= 0:
+            by.setdefault(refs[r.tid][0], []).append(r)
+    s2i = {s: orf.pair2info(rs) for s, rs in by.items()}
+    singles = [p for d in s2i.values() for p, i in d.items() if i[4] == 1]
+    priority = singles[::7] if use_priority else []
+    thr = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)
+    exp, Rdb = _ref_filter(s2i, pairing_filter, priority, **thr)
+    got, tal, _ = orf.filter_pairs(s2i, pairing_filter=pairing_filter, priority_reads=priority, **thr)
+    assert got == exp and sum(len(v) for v in exp.values()) > 7000
+    R = Rdb[Rdb["scaffold"] != "all_scaffolds"].set_index("scaffold")
+    for s, t in tal.items():
+        for c, v in t.items():
+            assert int(R.loc[s, c]) == int(v), (s, c)
+    with BamPacker(BAM) as bp:
+        names = bp.ref_names
+    cpp, cpp_tal, _ = filter_reads(BAM, names, pairing_filter=pairing_filter, priority_reads=priority, **thr)
+    assert cpp == {s: d for s, d in exp.items() if d}
+    for s, t in cpp_tal.items():
+        for c, v in t.items():
+            assert int(R.loc[s, c]) == int(v), (s, c)
