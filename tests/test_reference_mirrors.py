@@ -138,3 +138,60 @@ def test_read_filter_modes_against_reference_functions(pairing_filter, use_prior
     for s, t in cpp_tal.items():
         for c, v in t.items():
             assert int(R.loc[s, c]) == int(v), (s, c)
+
+
+def test_hot_path_with_singletons_in_r2m_against_reference_functions():
+    """pairing_filter='all_reads' puts singletons and pairs split over two scaffolds into R2M.  The hot path on such an
+    R2M: the oracle (and with it the CUDA path) against the reference's own process_bam_sites / calculate_ld fed with the
+    same emulated columns, on the 8 best-covered scaffolds -- SNV rows, linkage rows, covT."""
+    from conftest import assert_ld_equal, assert_snv_equal
+    from oracle import pileup_emul, read_filter as orf, ref_harness
+    from test_oracle_golden import expected_rows
+    refs, reads = bamio.read_bam(BAM)
+    seqs = bamio.read_fasta(TD + "N5_271_010G1_scaffold_min1000.fa")
+    by = {}
+    for r in reads:
+        if r.tid >= 0:
+            by.setdefault(refs[r.tid][0], []).append(r)
+    r2m_all, _, _ = orf.filter_pairs({s: orf.pair2info(rs) for s, rs in by.items()}, pairing_filter="all_reads")
+    r2m_po, _, _ = orf.filter_pairs({s: orf.pair2info(rs) for s, rs in by.items()})
+    lut, dflt = load_lut()
+    model = ref_harness.null_model(1e-6)
+    from instrain_b200.packer import BamPacker, read_bai
+    first = read_bai(BAM + ".bai")
+    B = {b: i for i, b in enumerate("ACTG")}
+    CLS = {n: i for i, n in enumerate(restate.CLASS_NAMES)}
+    n_single = 0
+    for name in sorted(r2m_all, key=lambda s: -len(r2m_all[s]))[:8]:
+        r2m = r2m_all[name]
+        n_single += len(set(r2m) - set(r2m_po.get(name, {})))
+        ev = pileup_emul.scaffold_events(by[name], r2m)
+        seq = seqs[name]
+        out = ref_harness.run_split(ev, seq, 0, len(seq) - 1, r2m, model, scaffold=name)
+        z = dict(
+            snv_pos=np.array([r["position"] for r in out["snp"]], np.int32), snv_mm=np.array([r["mm"] for r in out["snp"]], np.int32),
+            snv_cnt=np.array([[r["A"], r["C"], r["T"], r["G"]] for r in out["snp"]], np.int32).reshape(-1, 4),
+            snv_con=np.array([B[r["con_base"]] for r in out["snp"]], np.uint8), snv_var=np.array([B[r["var_base"]] for r in out["snp"]], np.uint8),
+            snv_allele_count=np.array([r["allele_count"] for r in out["snp"]], np.uint8),
+            snv_cls=np.array([CLS[r["class"]] for r in out["snp"]], np.uint8), snv_cryptic=np.array([r["cryptic"] for r in out["snp"]], np.uint8),
+            ld_pos_a=np.array([r["position_A"] for r in out["ld"]], np.int32), ld_pos_b=np.array([r["position_B"] for r in out["ld"]], np.int32),
+            ld_mm=np.array([r["mm"] for r in out["ld"]], np.int32),
+            ld_counts=np.array([[r["countAB"], r["countAb"], r["countaB"], r["countab"]] for r in out["ld"]], np.int32).reshape(-1, 4),
+            ld_alleles=np.array([[B[r[c]] for c in ("allele_A", "allele_a", "allele_B", "allele_b")] for r in out["ld"]], np.uint8).reshape(-1, 4),
+            ld_r2=np.array([r["r2"] for r in out["ld"]], np.float64), ld_d_prime=np.array([r["d_prime"] for r in out["ld"]], np.float64))
+        sev = restate.sort_events(ev)
+        ref_codes = restate.encode_ref(seq)
+        got = restate.profile_events(sev, ref_codes, lut, dflt, np.array([[0, len(seq) - 1]], np.int32))
+        snv, ld = expected_rows(z, ref_codes)
+        assert_snv_equal(got["snv"], snv)
+        assert_ld_equal(got["ld"], ld, tol=1e-9)
+        for mm, arr in out["covT"].items():
+            assert np.array_equal(got["covT"][:, mm], arr), (name, mm)
+        with BamPacker(BAM) as bp:                               # the C++ packer on the same R2M: the emulation's events
+            tid = bp.ref_names.index(name)
+            bp.seek(first[tid])
+            pk = bp.pack_scaffold(tid, r2m)
+        for k in ("ref_pos", "base", "qual", "read_id"):
+            assert np.array_equal(pk[k], sev[k]), (name, k)
+        assert np.array_equal(pk["pair_mm"], sev["pair_mm"].astype(np.uint8))
+    assert n_single > 100                                        # the case is exercised: names beyond the paired_only set
