@@ -26,6 +26,13 @@ def extract_SNVS_from_bam(bam_loc, R2M, positions, scaffold, engine=None, device
                 raise ValueError("scaffold %s is not in the .bam file %s" % (scaffold, bam_loc))
             want = bp.ref_names.index(scaffold)
             ev = None
+            from .packer import find_bai, read_bai
+            bai = find_bai(bam_loc)
+            if bai is not None:                                  # indexed BAM: go straight to the scaffold's first record
+                first = read_bai(bai)[want]
+                if first is None:
+                    return {p: np.zeros(4, dtype=int) for p in set(positions)}
+                bp.seek(first)
             while True:
                 tid = bp.peek_tid()
                 if tid < 0 or tid > want:
@@ -33,7 +40,7 @@ def extract_SNVS_from_bam(bam_loc, R2M, positions, scaffold, engine=None, device
                 if tid == want:
                     ev = bp.pack_scaffold(tid, set(R2M.keys()) if isinstance(R2M, dict) else R2M)
                     break
-                bp.pack_scaffold(tid, {})                        # sequential reader: skip earlier scaffolds
+                bp.pack_scaffold(tid, {})                        # no index: the sequential reader skips earlier scaffolds
             L = bp.ref_lens[want]
         if ev is None or len(ev["ref_pos"]) == 0:
             return {p: np.zeros(4, dtype=int) for p in set(positions)}

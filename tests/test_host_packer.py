@@ -355,3 +355,30 @@ def test_priority_read_files(tmp_path):
     assert load_priority_reads(str(tmp_path / "a.fastq")) == {"r1 extra", "r2"}
     assert load_priority_reads(str(tmp_path / "b.txt")) == {"r3", "r4"}
     assert load_priority_reads(str(tmp_path / "c.txt.gz")) == {"r5"}
+
+
+def test_iter_batches_honours_fdb_splits():
+    """The split table the reference hands over (Fdb, inStrain/profile/fasta.py:30-73) is used as given; without it the same
+    geometry is derived from window_length."""
+    import pandas as pd
+    from instrain_b200.profile import iter_batches
+    from instrain_b200.synth import iterate_splits
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    rows = []
+    for s in rdic:
+        L = len(seqs[s])
+        cuts = [0, L // 3, 2 * L // 3, L]
+        for i in range(3):
+            rows.append(dict(scaffold=s, split_number=i, start=cuts[i], end=cuts[i + 1] - 1))
+    Fdb = pd.DataFrame(rows).sample(frac=1.0, random_state=0)                     # any row order
+    (_, with_fdb), = iter_batches(bam, rdic, seqs, Fdb=Fdb)
+    (_, plain), = iter_batches(bam, rdic, seqs, window_length=500)
+    exp_fdb, exp_plain = [], []
+    for name, off in zip(with_fdb["names"], with_fdb["off"]):
+        L = len(seqs[name])
+        cuts = [0, L // 3, 2 * L // 3, L]
+        exp_fdb += [(cuts[i] + off, cuts[i + 1] - 1 + off) for i in range(3)]
+        exp_plain += [(s + off, e + off) for s, e in iterate_splits(L, 500)]
+    assert with_fdb["splits"] == exp_fdb and plain["splits"] == exp_plain and len(exp_plain) > len(exp_fdb)
