@@ -195,3 +195,49 @@ def test_hot_path_with_singletons_in_r2m_against_reference_functions():
             assert np.array_equal(pk[k], sev[k]), (name, k)
         assert np.array_equal(pk["pair_mm"], sev["pair_mm"].astype(np.uint8))
     assert n_single > 100                                        # the case is exercised: names beyond the paired_only set
+
+
+@pytest.mark.parametrize("seed,cov,dens,n_frac,skip_mm", [(1, 25, 0.03, 0.0, False), (2, 60, 0.05, 0.004, False),
+                                                           (3, 12, 0.02, 0.0, True), (4, 90, 0.08, 0.002, False),
+                                                           (5, 40, 0.04, 0.01, True)])
+def test_oracle_equals_reference_functions_on_random_inputs(seed, cov, dens, n_frac, skip_mm):
+    """Beyond the bundled BAMs: random synthetic read sets (haplotype mixtures, sequencing errors, low-quality bases,
+    non-ACGT read bases, several mm levels or set mode) through the reference's own process_bam_sites / calculate_ld and
+    through the oracle -- SNV rows, linkage rows, covT, clonT."""
+    from conftest import assert_ld_equal, assert_snv_equal
+    from oracle import ref_harness, synth
+    from test_oracle_golden import expected_rows
+    L = 900
+    batch = synth.make_batch(L, cov, dens, 4000 + seed, skip_mm=skip_mm, n_frac=n_frac)
+    n_pairs = len(batch["pair_mm"])
+    names = ["r%d" % i for i in range(n_pairs)]
+    ev = dict(batch, names=names)
+    seq = "".join("ACTGN"[c] for c in batch["ref_codes"])
+    r2m = set(names) if skip_mm else {n: int(m) for n, m in zip(names, batch["pair_mm"])}
+    model = ref_harness.null_model(1e-6)
+    lut, dflt = load_lut()
+    (s0, e0), = [tuple(x) for x in batch["splits"]] if len(batch["splits"]) == 1 else [(0, L - 1)]
+    out = ref_harness.run_split(ev, seq, int(s0), int(e0), r2m, model, min_cov=5, min_freq=0.05, min_snp=10)
+    got = restate.profile_events(batch, batch["ref_codes"], lut, dflt, batch["splits"], min_snp=10)
+    B = {b: i for i, b in enumerate("ACTG")}
+    CLS = {n: i for i, n in enumerate(restate.CLASS_NAMES)}
+    z = dict(
+        snv_pos=np.array([r["position"] for r in out["snp"]], np.int32), snv_mm=np.array([r["mm"] for r in out["snp"]], np.int32),
+        snv_cnt=np.array([[r["A"], r["C"], r["T"], r["G"]] for r in out["snp"]], np.int32).reshape(-1, 4),
+        snv_con=np.array([B[r["con_base"]] for r in out["snp"]], np.uint8), snv_var=np.array([B[r["var_base"]] for r in out["snp"]], np.uint8),
+        snv_allele_count=np.array([r["allele_count"] for r in out["snp"]], np.uint8),
+        snv_cls=np.array([CLS[r["class"]] for r in out["snp"]], np.uint8), snv_cryptic=np.array([r["cryptic"] for r in out["snp"]], np.uint8),
+        ld_pos_a=np.array([r["position_A"] for r in out["ld"]], np.int32), ld_pos_b=np.array([r["position_B"] for r in out["ld"]], np.int32),
+        ld_mm=np.array([r["mm"] for r in out["ld"]], np.int32),
+        ld_counts=np.array([[r["countAB"], r["countAb"], r["countaB"], r["countab"]] for r in out["ld"]], np.int32).reshape(-1, 4),
+        ld_alleles=np.array([[B[r[c]] for c in ("allele_A", "allele_a", "allele_B", "allele_b")] for r in out["ld"]], np.uint8).reshape(-1, 4),
+        ld_r2=np.array([r["r2"] for r in out["ld"]], np.float64), ld_d_prime=np.array([r["d_prime"] for r in out["ld"]], np.float64))
+    snv, ld = expected_rows(z, batch["ref_codes"])
+    assert len(snv) > 5
+    assert_snv_equal(got["snv"], snv)
+    assert_ld_equal(got["ld"], ld, tol=1e-9)
+    for mm, arr in out["covT"].items():
+        assert np.array_equal(got["covT"][:, mm], arr), mm
+    for mm, arr in out["clonT"].items():
+        mine = got["clonT"][:, mm]
+        assert np.array_equal(np.isnan(mine), np.isnan(arr)) and np.array_equal(mine[~np.isnan(arr)], arr[~np.isnan(arr)].astype(np.float32)), mm
