@@ -231,7 +231,7 @@ def main():
         if side is not None:
             side.synchronize()                           # no gather may still read the buffers being replaced
         sets.clear()
-        lean = use_cols and not args.keep_counts         # counts / nmask not requested: K1c runs the SNV call in its epilogue at M = 1
+        lean = (use_cols or use_reads) and not args.keep_counts   # counts / nmask not requested: the SNV call runs in the pileup kernel's epilogue at M = 1
         for _ in range(2 if world > 1 else 1):
             s_ = torch.empty(snv_cap * 32, dtype=torch.uint8, device=dev)
             l_ = torch.empty(ld_cap * 48, dtype=torch.uint8, device=dev)

@@ -378,9 +378,14 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     int rc;
     const bool do_ld = !(prm->flags & ISB_SKIP_LINKAGE);
     int64_t pipe_sites = -1, pipe_pairs = -1;
-    int32_t *d_counts, *d_covT; uint64_t *d_nmask; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_snv; isb_ld_row *d_ld;
-    if ((rc = stage_out(ctx, SL_COUNTS, out->counts, (size_t)L * M * 4, &d_counts))) return rc;
-    if ((rc = stage_out(ctx, SL_NMASK, out->nmask, (size_t)L, &d_nmask))) return rc;
+    int32_t *d_counts = nullptr, *d_covT; uint64_t *d_nmask = nullptr; float *d_clonT; uint8_t *d_flags; isb_snv_row *d_snv; isb_ld_row *d_ld;
+    // Read-major segments at M = 1 when the caller does not ask for the raw counts (the reference stores none either,
+    // profile_utilities.py:195-216): ONE kernel does pileup + SNV call + the bit rows of the linkage sites (K1f), the
+    // linkage back end follows without a host round trip.  No dense counts array exists on this path.
+    static const int k1f_env = getenv("ISB_K1F") ? atoi(getenv("ISB_K1F")) : 1;
+    const bool fused_reads = rd && M == 1 && !out->counts && k1f_env != 0;
+    if (!fused_reads && (rc = stage_out(ctx, SL_COUNTS, out->counts, (size_t)L * M * 4, &d_counts))) return rc;
+    if ((!fused_reads || out->nmask || rd->n_nev > 0) && (rc = stage_out(ctx, SL_NMASK, out->nmask, (size_t)L, &d_nmask))) return rc;
     if ((rc = stage_out(ctx, SL_COVT, out->covT, (size_t)L * M, &d_covT))) return rc;
     if ((rc = stage_out(ctx, SL_CLONT, out->clonT, (size_t)L * M, &d_clonT))) return rc;
     if ((rc = stage_out(ctx, SL_FLAGS, out->site_flags, (size_t)L, &d_flags))) return rc;
@@ -415,7 +420,19 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
         }
     }
     static const int fuse_env = getenv("ISB_K1C_FUSE") ? atoi(getenv("ISB_K1C_FUSE")) : 1;
-    if (cut.size() >= 3 && cd) {
+    if (fused_reads) {
+        isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, 0};
+        isb_k1f_linkage lk = {n_splits, d_splits, prm->min_snp, d_ld, ld_cap};
+        for (int attempt = 0;; ++attempt) {
+            if ((rc = isb_k1f_profile_launch(ctx, rd, n_pairs, start, L, (unsigned long long *)d_nmask, &fz, do_ld ? &lk : nullptr))) return rc;
+            if (prm->flags & ISB_NO_SYNC) break;                 // the caller checks capacities itself (isb_synchronize)
+            if ((rc = fetch_status(ctx))) return rc;
+            bool again = false;
+            if ((rc = isb_k1f_grow(ctx, &again))) return rc;
+            if (!again) break;
+            if (attempt == 4) return isb_fail(ctx, ISB_ERR_CUDA, "fused read-major path: scratch sizing did not converge");
+        }
+    } else if (cut.size() >= 3 && cd) {
         // Column words: the K1c launches (fused with the SNV call at M = 1) of all chunks go back to back on the main
         // stream; chunk c's linkage (+ K2 when not fused) runs on the second stream underneath K1c of the later chunks.
         // K1c is cut at 64-position (group) boundaries rounded UP from the split boundaries, so chunk c's splits are
@@ -568,8 +585,8 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
         if (rc) return rc;
         isb_time_end(ctx, ts);
     }
-    if ((rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
-    if ((rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
+    if (d_counts && (rc = finish_out(ctx, out->counts, d_counts, (size_t)L * M * 4))) return rc;
+    if (d_nmask && (rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
     if ((rc = finish_out(ctx, out->covT, d_covT, (size_t)L * M))) return rc;
     if ((rc = finish_out(ctx, out->clonT, d_clonT, (size_t)L * M))) return rc;
     if ((rc = finish_out(ctx, out->site_flags, d_flags, (size_t)L))) return rc;

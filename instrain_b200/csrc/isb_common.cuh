@@ -16,6 +16,9 @@
 #define ISB_DEV_ERR_MULT 0x4u         // a read pair has > 2 qualifying events on one site
 #define ISB_DEV_ERR_ROWBUF 0x8u       // linkage bit-row scratch too small (host grows it and re-runs K3)
 #define ISB_DEV_ERR_SEG 0x10u         // read-major batch violates its layout rules (order, range, word offsets)
+#define ISB_DEV_ERR_SITECAP 0x20u     // fused read-major path: more linkage sites than site slots (host grows them and re-runs)
+
+#define ISB_K3_ROW_SLOT 64            // words of the fixed bit-row slot every linkage site owns (wider rows go to an overflow region)
 
 enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_REF_POS = 0, SL_BASE, SL_QUAL, SL_READ_ID, SL_PAIR_MM, SL_REF, SL_SPLITS,   // staged inputs
@@ -29,6 +32,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_RD_CAND, SL_RD_EVOFF, SL_RD_EVB, SL_RD_EVQ, SL_RD_EVID,                          // K3 site events from segments
     SL_CD_OFF, SL_CD_WORDS, SL_CD_IDS, SL_CD_CNT,                                  // column-word batch (K1c inputs) + conversion scratch
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
+    SL_TILE_SITES, SL_SITE_COUNTS,                                                 // fused read-major path: per-tile site slots, counts per site
     SL_COUNT
 };
 
@@ -54,6 +58,7 @@ struct isb_ctx {
     unsigned long long *h_counters;   // pinned mirror
     unsigned int *h_err;
     int64_t launches;
+    int64_t sites_cap;                // fused read-major path: linkage-site slots allocated so far (grow-only)
     isb_devbuf buf[SL_COUNT];
     char err[512];
     // optional per-stage device timing (isb_enable_timing): CUDA events recorded on ctx->stream around K1 / K2 / K3
@@ -115,6 +120,8 @@ int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
 #ifndef K1R_TILE
 #define K1R_TILE 1024                 // positions per K1r block; also the granularity of the K3 candidate search
 #endif
+struct isb_k2_fuse;
+typedef struct isb_k2_fuse isb_k2_fuse_fwd;
 struct isb_reads_dev {
     int64_t n_segs;
     const int32_t *seg_start;
@@ -135,6 +142,38 @@ struct isb_reads_dev {
 };
 int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
                    int M, int32_t *counts, unsigned long long *nmask);
+// Fused read-major path (M = 1): K1f (pileup + SNV call + bit rows of the linkage sites, isb_k1f_fused.cu) and the
+// linkage back end on its per-tile site slots (isb_k3_linkage.cu).  Everything is enqueued on ctx->stream without a
+// host round trip; the caller reads the counters / error word afterwards and re-runs after isb_k1f_grow when a scratch
+// capacity was exceeded.
+struct isb_k1f_linkage {
+    int32_t n_splits;
+    const int32_t *splits;
+    int min_snp;
+    isb_ld_row *rows;
+    int64_t cap;
+};
+int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int32_t start, int32_t L,
+                           unsigned long long *nmask, const isb_k2_fuse_fwd *fuse, const isb_k1f_linkage *ld);
+int isb_k1f_grow(isb_ctx *ctx, bool *again);
+int isb_k1f_pileup_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
+                          int M, int32_t *counts, unsigned long long *nmask);
+// linkage back end over per-tile site slots (tile = K1R_TILE positions): linked site pairs -> LD rows, device-side counts
+struct isb_k3_tiles {
+    int n_tiles;
+    const int32_t *tile_first;        // [n_tiles] first site slot of the tile
+    const int32_t *tile_cnt;          // [n_tiles] sites of the tile (slots are contiguous and position-ordered inside a tile)
+    int64_t sites_cap;
+    const int32_t *site_pos;          // [sites_cap] relative position
+    isb_site_meta *meta;
+    const int64_t *row_off;
+    uint8_t *has2;
+    const int4 *site_counts;          // [sites_cap] A,C,T,G counts of the site (M = 1)
+    uint32_t *rows;
+};
+int isb_k3_backend_tiles(isb_ctx *ctx, const isb_reads_dev *rd, const isb_k3_tiles *ts, int64_t n_pairs, int32_t start, int32_t L,
+                         const unsigned long long *nmask, const uint8_t *site_flags, int32_t n_splits, const int32_t *splits,
+                         int min_snp, isb_ld_row *rows, int64_t cap);
 int isb_k3_launch_reads(isb_ctx *ctx, const isb_reads_dev *rd, int64_t n_pairs, const uint8_t *pair_mm, int32_t start,
                         int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                         const uint8_t *site_flags, int32_t n_splits, const int32_t *splits, int min_snp, isb_ld_row *rows,

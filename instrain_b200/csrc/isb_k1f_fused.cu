@@ -1,0 +1,789 @@
+// isb_k1f_fused.cu -- K1f: the per-position part of the path straight from BAM-ORDER aligned segments, sm_100a.
+//
+//   k1f_pileup<M1, fused>   pileup counts (+ at M = 1, fused: the per-site SNV call and the bit rows of the linkage sites)
+//
+// Replaces, for a whole batch of scaffolds at once: samfile.pileup(...) column iteration
+// (inStrain/profile/profile_utilities.py:150-153) + get_base_counts_mm (:268-286); fused: update_covT (:288-295),
+// update_snp_table / call_snv_site / calc_snp_class / calculate_clonality (inStrain/profile/snv_utilities.py:40-231) and
+// update_linked_reads (inStrain/profile/linkage.py:254-283).
+//
+// Input = isb_reads_batch (include/instrain_b200.h): one 4-bit one-hot code per aligned base, stored once per READ, in
+// BAM order.  The pileup is a transposition (reads x offsets -> positions); it is done on the fly, in registers:
+//
+//   * a block owns a tile of 1024 positions, a thread one column word (8 positions); the segment TABLE of the tile
+//     (seg_start in (tile_first - max_seg_len, tile_end): a contiguous range of the start-sorted table) is staged in
+//     shared memory as one packed word per segment; the nibble WORDS are never staged: word k of a segment is needed by
+//     exactly one thread of the grid, so it goes from HBM to that thread's register with one coalesced load;
+//   * CIRCULAR SCHEDULE.  Thread t needs the segments [cl_t, ch_t) (~coverage many).  A warp steps through them
+//     together: with Pm = max_t (ch_t - cl_t) rounded up to 8 and base = min_t cl_t, lane t visits at step s the one
+//     index j in [cl_t, cl_t + Pm) with j = base + s (mod Pm) -- a rotation of its own range.  Lanes whose ranges
+//     overlap therefore visit the SAME segment at the same step: the shared-memory read of its table word is a
+//     broadcast and their word loads are consecutive addresses (the lanes of a warp fall into <= 3 such bands).  The
+//     free-running per-thread loops of the first K1r put every lane on its own segment at every step (3.1x bank
+//     conflicts, 32 sectors per load).  A lock-step loop over the union of the ranges would be conflict-free too, but
+//     runs 2.6x as many steps;
+//   * counting is bit-sliced (isb_bitslice.cuh): 24 logic ops per 8 words;
+//   * fused epilogue (M = 1): the warp's 256 count quads are transposed through shared memory to "lane = position";
+//     sites with one base only (or below min_cov) are finished with integer compares and coalesced stores, the ~12 %
+//     that need the double-precision clonality / the allele tests are compacted into dense batches of 32 first;
+//   * linkage front end: the tile's anySNP sites get contiguous site slots (one atomic per tile); one warp per site
+//     gathers the site's (pair id, base) entries from the staged segment table + the words (L1 / L2 hits: the block
+//     has just streamed them) and assembles the bit rows  any | ge1[b] | ge2[b]  with ballots and REDUX.OR (no atomics).
+//
+// HBM traffic, fused: 0.5 B per aligned base + 14 B per segment + 1 B per position in, 9 B per position + 32 B per SNV
+// row + ~300 B per linkage site out; the counts of a position never leave the SM.
+#include "isb_common.cuh"
+#include "isb_bitslice.cuh"
+#include "isb_k2_site.cuh"
+#include "isb_k3_dev.cuh"
+#include <climits>
+#include <cstdlib>
+
+#define K1F_TILE K1R_TILE
+#define K1F_THREADS (K1F_TILE / 8)     // one thread per column word
+#define K1F_WARPS (K1F_THREADS / 32)
+#define K1F_MAXLEN 256                 // hard cap of max_seg_len
+#define K1F_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
+#define K1F_STAGE_IT 9                 // segment-table elements per thread per chunk: seg_cap <= 9 * 128
+#define K1F_TILE4 (256 + 32)           // count quads of a warp's 256 positions + one pad quad per 8 positions
+#ifndef K1F_MINB
+#define K1F_MINB 5                     // __launch_bounds__ min blocks per SM of the fused kernel (<= 102 registers)
+#endif
+static_assert(K1F_WARPS == 4, "the site bookkeeping of the fused epilogue assumes 4 warps per tile");
+
+struct k1f_args {
+    isb_reads_dev rd;
+    const uint8_t *pair_mm;
+    int64_t n_pairs;
+    int32_t start, L;
+    int M;
+    int seg_cap;                       // segments staged per chunk
+    int32_t *counts;
+    unsigned int *d_err;
+    // fused SNV call (M = 1)
+    const unsigned long long *nmask;   // read only when min_cov <= 0 (a level without counts cannot be "counted" otherwise)
+    isb_k2_fuse k2;
+    const int32_t *thr2;
+    int n_lut, lut_default;
+    unsigned long long *n_rows;
+    // linkage front end
+    int do_ld;
+    int32_t n_splits;
+    const int32_t *splits;
+    int32_t *tile_first, *tile_cnt;
+    int64_t sites_cap;
+    int32_t *site_pos;
+    isb_site_meta *meta;
+    int64_t *row_off;
+    uint8_t *has2;
+    int4 *site_counts;
+    uint32_t *rows;
+    int64_t row_cap;
+    unsigned long long *n_sites, *row_words_total;
+};
+
+// tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range
+__global__ void __launch_bounds__(256)
+k1f_tile_bounds(const int32_t *__restrict__ seg_start, int64_t n_segs, int32_t start, int n_tiles, int max_seg_len,
+                int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int64_t first = (int64_t)start + (int64_t)t * K1F_TILE;
+    const int64_t lo = isb_lower_bound(seg_start, 0, n_segs, first - max_seg_len + 1);
+    tile_lo[t] = lo;
+    tile_hi[t] = isb_lower_bound(seg_start, lo, n_segs, first + K1F_TILE);
+}
+
+__device__ __forceinline__ int k1f_warp_max(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(ISB_FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ int k1f_warp_min(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(ISB_FULL, v, d));
+    return v;
+}
+
+// M > 1: write (or add, once counts hold a partial sum) the thread's shared 8-bit counters to its cells of `counts`
+__device__ __forceinline__ void k1f_flush_levels(const k1f_args &a, uint32_t *s_acc, int t, int Mg, int m_base, int32_t P,
+                                                 bool add, bool clear)
+{
+    int4 *c4 = reinterpret_cast<int4 *>(a.counts);
+    for (int m = 0; m < Mg; ++m) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            w8[j] = s_acc[(size_t)(m * 8 + j) * K1F_THREADS + t];
+            if (clear) s_acc[(size_t)(m * 8 + j) * K1F_THREADS + t] = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (P + k >= a.L) break;
+            const int sh = (k >> 1) * 8, h = k & 1;
+            int4 val;
+            val.x = (w8[0 + h] >> sh) & 0xff; val.y = (w8[2 + h] >> sh) & 0xff;
+            val.z = (w8[4 + h] >> sh) & 0xff; val.w = (w8[6 + h] >> sh) & 0xff;
+            int4 *dst = c4 + ((size_t)(P + k) * a.M + m_base + m);
+            if (add) { const int4 o = *dst; val.x += o.x; val.y += o.y; val.z += o.z; val.w += o.w; }
+            *dst = val;
+        }
+    }
+}
+
+// M = 1: add the thread's vertical counter planes into its 8 count quads of the warp's shared-memory tile and clear them.
+// The 32-bit counts live in shared memory, not in registers: they are touched once per <= 248 steps, and 32 registers
+// less per thread is one more resident block per SM.
+__device__ __forceinline__ void k1f_flush_planes(int4 *tile_lane, uint32_t (&pl)[8])
+{
+    int c[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[k][b] = 0;
+    k1r_planes_to_counts(c, pl);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int4 v = tile_lane[k];
+        v.x += c[k][0]; v.y += c[k][1]; v.z += c[k][2]; v.w += c[k][3];
+        tile_lane[k] = v;
+    }
+}
+
+template <bool kM1, bool kFuse>
+__global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1f_args a)
+{
+    static_assert(kM1 || !kFuse, "the fused epilogue is the M = 1 SNV call");
+    extern __shared__ __align__(16) unsigned char k1f_smem[];
+    // one packed word per staged segment: bits 11.. = index (relative to the chunk's word base wb) of the word that covers
+    // tile column 0, + 160; bits 0..10 = tile-relative end + 256
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(k1f_smem);
+    int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);   // start relative to a.start (sorted): the search key
+    uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);     // M > 1 only
+    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kM1 ? 8 : 9)) + 15) & ~(size_t)15);
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_x);                  // M > 1: [Mg * 8][K1F_THREADS]
+    // fused epilogue scratch
+    int4 *s_tile = reinterpret_cast<int4 *>(s_x);                         // [K1F_WARPS][K1F_TILE4]
+    uint32_t *s_rows = reinterpret_cast<uint32_t *>(s_tile + K1F_WARPS * K1F_TILE4);   // [K1F_WARPS][ISB_K3_ROW_SLOT]
+    int32_t *s_cl = reinterpret_cast<int32_t *>(s_rows + K1F_WARPS * ISB_K3_ROW_SLOT); // [K1F_THREADS] candidate range per column
+    int32_t *s_ch = s_cl + K1F_THREADS;
+    int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: sites per warp, offsets, slot base
+    uint16_t *s_site = reinterpret_cast<uint16_t *>(s_misc + 16);         // [K1F_WARPS][256]: position in the warp | bases << 8
+    uint8_t *s_q = reinterpret_cast<uint8_t *>(s_site + K1F_WARPS * 256); // [K1F_WARPS][256]: positions for the general path
+
+    const int t = threadIdx.x;
+    const int lane = t & 31, wib = t >> 5;
+    const int tile = blockIdx.x;
+    const int32_t T0 = tile * K1F_TILE;
+    const int32_t P = T0 + t * 8;                               // first of the thread's 8 positions (relative)
+    const bool active = P < a.L;
+    const int maxlen = a.rd.max_seg_len;
+    const int64_t lo = a.rd.tile_lo[tile], hi = a.rd.tile_hi[tile];
+    const int m_base = kM1 ? 0 : (int)blockIdx.y * K1F_LEVELS;
+    const int Mg = kM1 ? 1 : min(K1F_LEVELS, a.M - m_base);
+    const bool single = hi - lo <= (int64_t)a.seg_cap;            // the whole tile in one chunk (the usual case)
+
+    uint32_t pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};            // M = 1: vertical counter planes (weights 1 .. 128)
+    int n8 = 0;                                                   // steps since the last flush (counters hold <= 255)
+    bool spilled = false;                                         // M > 1: counts already hold a partial sum
+    int4 *tile4 = s_tile + wib * K1F_TILE4;                       // M = 1: the warp's count quads (pad quad per 8 positions)
+    int4 *tile_lane = tile4 + lane * 9;                           //        this thread's 8
+    if (kM1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tile_lane[k] = make_int4(0, 0, 0, 0);
+    } else {
+        for (int w = 0; w < Mg * 8; ++w) s_acc[w * K1F_THREADS + t] = 0u;
+    }
+    unsigned err = 0;
+    int64_t wb = 0;                                               // word base of the (last) chunk
+    const int P_end = t * 8 + 256;
+
+    for (int64_t c0 = lo; c0 < hi; c0 += a.seg_cap) {
+        const int nc = (int)min((int64_t)a.seg_cap, hi - c0);
+        __syncthreads();                                          // previous chunk consumed
+        wb = __ldg(a.rd.seg_word + c0) - 1;                       // the separator in front of the chunk's first segment
+        if (wb < 0 || wb >= a.rd.n_words) {                       // layout rules violated (block-uniform)
+            err |= ISB_DEV_ERR_SEG;
+            continue;
+        }
+        // Segment table of the chunk -> shared memory.  All global loads of the (up to K1F_STAGE_IT) elements a thread
+        // handles are issued before the first is used: the block pays ONE memory latency here.
+        {
+            int32_t r_s[K1F_STAGE_IT], r_prev[K1F_STAGE_IT], r_pid[K1F_STAGE_IT];
+            int r_n[K1F_STAGE_IT];
+            int64_t r_w[K1F_STAGE_IT];
+#pragma unroll
+            for (int k = 0; k < K1F_STAGE_IT; ++k) {
+                const int i = t + k * K1F_THREADS;
+                const int64_t g = c0 + i;
+                r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1; r_pid[k] = 0;
+                if (i < nc) {
+                    r_s[k] = __ldg(a.rd.seg_start + g);
+                    r_n[k] = __ldg(a.rd.seg_len + g);
+                    r_w[k] = __ldg(a.rd.seg_word + g);
+                    if (g > 0) r_prev[k] = __ldg(a.rd.seg_start + g - 1);
+                    if (!kM1) r_pid[k] = __ldg(a.rd.seg_pair + g);
+                }
+            }
+            int r_mm[K1F_STAGE_IT];
+            if (!kM1) {
+#pragma unroll
+                for (int k = 0; k < K1F_STAGE_IT; ++k) {
+                    r_mm[k] = 255;
+                    if (t + k * K1F_THREADS < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
+                        r_mm[k] = __ldg(a.pair_mm + r_pid[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K1F_STAGE_IT; ++k) {
+                const int i = t + k * K1F_THREADS;
+                if (i >= nc) break;
+                const int64_t s64 = (int64_t)r_s[k] - a.start;
+                const int n = r_n[k];
+                const int64_t wl = r_w[k] - wb;
+                const int nw = (int)(((s64 & 7) + n + 7) >> 3);
+                bool bad = n < 1 || n > maxlen || s64 < 0 || s64 + n > (int64_t)a.L || wl < 1 || wl > (1 << 20) ||
+                           r_w[k] + nw + 1 > a.rd.n_words || r_prev[k] > r_s[k];
+                if (bad) err |= ISB_DEV_ERR_SEG;
+                const int32_t s = bad ? T0 : (int32_t)s64;
+                const int n_c = bad ? 0 : n;                      // a segment that breaks the rules covers nothing
+                const int wl_c = bad ? 1 : (int)wl;
+                const int s_rel = min(max(s - T0, -255), K1F_TILE - 1);   // candidates start in (T0 - 256, T0 + 1024)
+                s_meta[i] = ((uint32_t)(wl_c - (s_rel >> 3) + 160) << 11) | (uint32_t)(s_rel + n_c + 256);
+                s_start[i] = s;
+                if (!kM1) {
+                    if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
+                    s_mm[i] = (uint8_t)r_mm[k];
+                }
+            }
+        }
+        __syncthreads();
+
+        // candidates of this thread inside the chunk: seg_start in (P - maxlen, P + 8)
+        int cl = 0, ch = 0;
+        if (active) {
+            int l = 0, h = nc;
+            const int key = P - maxlen + 1;
+            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key) l = mid + 1; else h = mid; }
+            cl = l;
+            h = nc;
+            const int key2 = P + 8;
+            while (l < h) { const int mid = (l + h) >> 1; if (s_start[mid] < key2) l = mid + 1; else h = mid; }
+            ch = l;
+        }
+        if (kFuse) { s_cl[t] = cl; s_ch[t] = ch; }
+        // circular schedule of the warp (see the header)
+        const int len = ch - cl;
+        const int Pm = (k1f_warp_max(len) + 7) & ~7;
+        if (Pm == 0) continue;                                    // warp-uniform; no block barrier inside the loop body below
+        const int base = k1f_warp_min(len > 0 ? cl : INT_MAX);
+        int j = cl;
+        if (len > 0) {
+            const int r = (cl - base) % Pm;
+            j = cl + (r ? Pm - r : 0);
+        }
+        const int wrap = cl + Pm;
+        // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach).  The stream
+        // is position-aligned: the thread's column is ONE word of the segment, no shift.
+        const uint32_t *wsrc = a.rd.words + wb + (t - 160);
+        auto meta_at = [&](int &jj) -> uint32_t {
+            const uint32_t md = jj < ch ? s_meta[jj] : 0u;        // 0: end field 0, never covers
+            jj = (jj + 1 == wrap) ? cl : jj + 1;
+            return md;
+        };
+        auto word_of = [&](uint32_t md) -> uint32_t {
+            return P_end < (int)(md & 0x7ffu) ? __ldg(wsrc + (md >> 11)) : 0u;
+        };
+        if (kM1) {
+            int s = 0;
+            for (; s + 16 <= Pm; s += 16) {                       // two Harley-Seal blocks per trip: 16 loads in flight
+                uint32_t x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = meta_at(j);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y[u] = meta_at(j);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) y[u] = word_of(y[u]);
+                k1r_add8(pl, x);
+                k1r_add8(pl, y);
+                n8 += 16;
+                if (n8 > 239) {                                    // the next trip could overflow 255
+                    k1f_flush_planes(tile_lane, pl);
+                    n8 = 0;
+                }
+            }
+            if (s < Pm) {                                          // Pm is a multiple of 8
+                uint32_t x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = meta_at(j);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
+                k1r_add8(pl, x);
+                n8 += 8;
+                if (n8 > 239) {
+                    k1f_flush_planes(tile_lane, pl);
+                    n8 = 0;
+                }
+            }
+        } else {
+            for (int s = 0; s < Pm; s += 8) {
+                uint32_t x[8];
+                int lv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    lv[u] = j < ch ? (int)s_mm[j] - m_base : -1;
+                    x[u] = meta_at(j);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if ((unsigned)lv[u] < (unsigned)Mg) {          // 8-bit counters per (level, base, even/odd position)
+                        uint32_t *acc = s_acc + (size_t)(lv[u] * 8) * K1F_THREADS + t;
+                        acc[0 * K1F_THREADS] += x[u] & 0x01010101u;
+                        acc[1 * K1F_THREADS] += (x[u] >> 4) & 0x01010101u;
+                        acc[2 * K1F_THREADS] += (x[u] >> 1) & 0x01010101u;
+                        acc[3 * K1F_THREADS] += (x[u] >> 5) & 0x01010101u;
+                        acc[4 * K1F_THREADS] += (x[u] >> 2) & 0x01010101u;
+                        acc[5 * K1F_THREADS] += (x[u] >> 6) & 0x01010101u;
+                        acc[6 * K1F_THREADS] += (x[u] >> 3) & 0x01010101u;
+                        acc[7 * K1F_THREADS] += (x[u] >> 7) & 0x01010101u;
+                    }
+                }
+                n8 += 8;
+                if (n8 > 240) {                                    // flush before a byte can overflow (warp-uniform)
+                    if (active) k1f_flush_levels(a, s_acc, t, Mg, m_base, P, spilled, true);
+                    spilled = true;
+                    n8 = 0;
+                }
+            }
+        }
+    }
+    if (err) atomicOr(a.d_err, err);
+
+    if (!kFuse) {
+        if (!active) return;
+        if (kM1) {
+            k1f_flush_planes(tile_lane, pl);
+            int4 *c4 = reinterpret_cast<int4 *>(a.counts) + P;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (P + k >= a.L) break;
+                c4[k] = tile_lane[k];
+            }
+        } else {
+            k1f_flush_levels(a, s_acc, t, Mg, m_base, P, spilled, false);
+        }
+        return;
+    }
+
+    // ---- fused SNV call (K2 at M = 1) ------------------------------------------------------------------------------
+    k1f_flush_planes(tile_lane, pl);
+    __syncwarp();
+    const int32_t W0 = T0 + wib * 256;
+    int4 *counts4 = reinterpret_cast<int4 *>(a.counts);
+    const bool full_counts = a.counts != nullptr && a.k2.full_counts;
+    uint8_t *q_list = s_q + wib * 256;
+    uint16_t *site_list = s_site + wib * 256;
+    int nq = 0;                                                   // positions waiting for the general path (warp-uniform)
+    const bool all_general = a.k2.min_cov < 1;                    // then "below min_cov" is not a simple case
+#pragma unroll 2
+    for (int rd = 0; rd < 8; ++rd) {
+        const int q = rd * 32 + lane;
+        const int32_t p = W0 + q;
+        const bool in = p < a.L;
+        const int4 E = tile4[q + (q >> 3)];
+        const int T = E.x + E.y + E.z + E.w;
+        const int mx = max(max(E.x, E.y), max(E.z, E.w));
+        bool simple = false;
+        float clon = CUDART_NAN_F;
+        if (in && !all_general) {
+            if (T < a.k2.min_cov) {
+                simple = true;                                    // call_snv_site -> (None, 0): coverage only
+            } else if (mx == T && T < a.n_lut) {                  // one base only: clonality exactly 1; a row unless it is the
+                const int con = E.x == T ? 0 : (E.y == T ? 1 : (E.z == T ? 2 : 3));   // reference base and passes the threshold
+                if (T >= __ldg(a.thr2 + T) && con == (int)a.k2.ref[p]) { simple = true; clon = 1.0f; }
+            }
+        }
+        if (in) {
+            a.k2.covT[p] = T;
+            if (simple) {
+                a.k2.clonT[p] = clon;
+                a.k2.site_flags[p] = 0;
+                if (full_counts) counts4[p] = E;
+            }
+        }
+        const bool need = in && !simple;
+        const unsigned nm = __ballot_sync(ISB_FULL, need);
+        if (need) q_list[nq + __popc(nm & ((1u << lane) - 1u))] = (uint8_t)q;
+        nq += __popc(nm);
+    }
+    __syncwarp();
+    int ns = 0;                                                   // anySNP sites of the warp (warp-uniform)
+    for (int b0 = 0; b0 < nq; b0 += 32) {                         // general path, dense: lane = one waiting position
+        const bool on = b0 + lane < nq;
+        const int q = on ? (int)q_list[b0 + lane] : 0;
+        const int32_t p = W0 + q;
+        const int4 E = tile4[q + (q >> 3)];
+        int C[4] = {E.x, E.y, E.z, E.w};
+        int r = 0;
+        k2_m1_site s;
+        s.T = 0; s.clon = CUDART_NAN_F; s.flags = 0u; s.is_row = false; s.i = 0; s.con = 0; s.thr = 0;
+        if (on) {
+            r = a.k2.ref[p];
+            const int T = E.x + E.y + E.z + E.w;
+            const int thr_T = (T >= a.k2.min_cov && T < a.n_lut) ? __ldg(a.thr2 + T) : a.lut_default;
+            const bool nm0 = T == 0 && a.nmask && (a.nmask[p] & 1ull);
+            s = k2_site_m1(C, r, nm0, thr_T, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
+            a.k2.clonT[p] = s.clon;
+            a.k2.site_flags[p] = (uint8_t)s.flags;
+            if (full_counts) counts4[p] = E;
+        }
+        const bool row = on && s.is_row;
+        const unsigned rm = __ballot_sync(ISB_FULL, row);
+        if (rm) {                                                 // one row allocation per batch of 32
+            unsigned long long base_slot = 0;
+            if (lane == 0) base_slot = atomicAdd(a.n_rows, (unsigned long long)__popc(rm));
+            base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
+            const int64_t slot = (int64_t)base_slot + __popc(rm & ((1u << lane) - 1u));
+            if (row && slot < a.k2.cap) k2_write_row_m1(a.k2.rows + slot, p + a.start, C, r, s, a.n_lut, a.k2.min_freq);
+        }
+        const bool st = on && (s.flags & ISB_SITE_ANYSNP);
+        const unsigned sm = __ballot_sync(ISB_FULL, st);
+        if (st) site_list[ns + __popc(sm & ((1u << lane) - 1u))] = (uint16_t)(q | ((s.flags & 0xFu) << 8));
+        ns += __popc(sm);
+    }
+    if (!a.do_ld) return;
+
+    // ---- linkage front end: site slots of the tile, then one warp per site ---------------------------------------------
+    if (lane == 0) s_misc[wib] = ns;
+    __syncthreads();
+    if (t == 0) {
+        int tot = 0;
+        for (int w = 0; w < K1F_WARPS; ++w) { s_misc[4 + w] = tot; tot += s_misc[w]; }
+        unsigned long long b0 = 0;
+        if (tot) b0 = atomicAdd(a.n_sites, (unsigned long long)tot);
+        s_misc[8] = tot;
+        s_misc[9] = (int32_t)(b0 < (unsigned long long)INT_MAX ? b0 : (unsigned long long)INT_MAX);
+        a.tile_first[tile] = s_misc[9];
+        a.tile_cnt[tile] = tot;
+    }
+    __syncthreads();
+    const int tot = s_misc[8];
+    const int64_t sbase = s_misc[9];
+    const uint32_t *wsrc0 = a.rd.words + wb - 160;                // single-chunk tiles: word index = wsrc0[(meta >> 11) + column]
+    for (int si = wib; si < tot; si += K1F_WARPS) {
+        int ow = 0;
+#pragma unroll
+        for (int w = 1; w < K1F_WARPS; ++w) if (si >= s_misc[4 + w]) ow = w;
+        const unsigned ent = s_site[ow * 256 + si - s_misc[4 + ow]];
+        const int q = ent & 0xff;
+        const unsigned bases = ent >> 8;
+        const int pt = ow * 256 + q;                               // tile-relative position
+        const int32_t p = T0 + pt;
+        const int64_t abs_pos = (int64_t)p + a.start;
+        const int64_t slot = sbase + si;
+        if (slot >= a.sites_cap) {                                 // host grows the site slots and re-runs
+            if (lane == 0) atomicOr(a.d_err, ISB_DEV_ERR_SITECAP);
+            continue;
+        }
+        const int na = __popc(bases);
+        const int tcol = pt >> 3, sh = (pt & 7) << 2;
+        // candidate segments of the site: staged table (single-chunk tile) or the global table
+        int cl_ = 0, ch_ = 0;
+        int64_t glo = 0;
+        if (single) {
+            cl_ = s_cl[tcol];
+            ch_ = s_ch[tcol];
+        } else {
+            glo = isb_lower_bound(a.rd.seg_start, lo, hi, abs_pos - maxlen + 1);
+            ch_ = (int)(isb_lower_bound(a.rd.seg_start, glo, hi, abs_pos + 1) - glo);
+        }
+        auto cand = [&](int i, int &b, int &id) -> bool {
+            bool ok;
+            if (single) {
+                const uint32_t md = s_meta[i];
+                if (!(pt + 256 < (int)(md & 0x7ffu)) || s_start[i] > p) return false;
+                const uint32_t code = (__ldg(wsrc0 + (md >> 11) + tcol) >> sh) & 15u;
+                if (!code) return false;
+                b = __ffs((int)code) - 1;
+                id = __ldg(a.rd.seg_pair + lo + i);
+                ok = true;
+            } else {
+                ok = k3r_candidate(a.rd, glo + i, abs_pos, b, id);
+            }
+            if (ok && (id < 0 || (int64_t)id >= a.n_pairs)) { atomicOr(a.d_err, ISB_DEV_ERR_SEG); ok = false; }
+            return ok && ((bases >> b) & 1u);
+        };
+        int idmin = INT_MAX, idmax = -1;
+        for (int i0 = cl_; i0 < ch_; i0 += 32) {
+            int b = 0, id = 0;
+            if (i0 + lane < ch_ && cand(i0 + lane, b, id)) { idmin = min(idmin, id); idmax = max(idmax, id); }
+        }
+        idmin = k1f_warp_min(idmin);
+        idmax = k1f_warp_max(idmax);
+        isb_site_meta m;
+        m.split = isb_site_split(a.splits, a.n_splits, abs_pos);
+        m.ev_lo_rel = 0;
+        m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
+        m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
+        const int n_words = (1 + 2 * na) * m.nw;
+        // Row storage: slot k owns the fixed region [k * ROW_SLOT, + ROW_SLOT); only rows wider than that (deep coverage)
+        // are allocated with an atomic behind the sites_cap fixed regions.
+        unsigned long long off = (unsigned long long)slot * ISB_K3_ROW_SLOT;
+        if (n_words > ISB_K3_ROW_SLOT) {
+            if (lane == 0) off = (unsigned long long)a.sites_cap * ISB_K3_ROW_SLOT + atomicAdd(a.row_words_total, (unsigned long long)n_words);
+            off = __shfl_sync(ISB_FULL, off, 0);
+        }
+        if ((int64_t)(off + n_words) > a.row_cap) {               // host grows the row storage and re-runs
+            if (lane == 0) atomicOr(a.d_err, ISB_DEV_ERR_ROWBUF);
+            m.nw = 0;
+        }
+        if (lane == 0) {
+            a.meta[slot] = m;
+            a.row_off[slot] = (int64_t)off;
+            a.site_pos[slot] = p;
+            a.site_counts[slot] = s_tile[ow * K1F_TILE4 + q + (q >> 3)];
+        }
+        bool dup = false;
+        if (m.nw > 0) {
+            const bool in_smem = n_words <= ISB_K3_ROW_SLOT;
+            uint32_t *g_any = a.rows + off;
+            uint32_t *any = in_smem ? s_rows + wib * ISB_K3_ROW_SLOT : g_any;
+            for (int i = lane; i < n_words; i += 32) any[i] = 0u;
+            __syncwarp();
+            // bits of 32 candidates at a time, word by word: ballot the lanes whose pair id falls into the word, OR their
+            // bits with REDUX, one lane updates the (warp-private) row word.  A pair seen twice on the site (htslib's
+            // overlap quirk) shows up as fewer bits than lanes, or as a bit that is already set: exact slow path below.
+            for (int i0 = cl_; i0 < ch_; i0 += 32) {
+                int b = 0, id = 0;
+                const bool ok = i0 + lane < ch_ && cand(i0 + lane, b, id);
+                const int w = ok ? (id >> 5) - m.wlo : -1;
+                const uint32_t bit = 1u << (id & 31);
+                const int r = __popc(bases & ((1u << b) - 1u));
+                unsigned live = __ballot_sync(ISB_FULL, ok);
+                while (live) {
+                    const int src = __ffs((int)live) - 1;
+                    const int wv = __shfl_sync(ISB_FULL, w, src);
+                    const bool mine = ok && w == wv;
+                    const unsigned m_any = __ballot_sync(ISB_FULL, mine);
+                    live &= ~m_any;
+                    uint32_t bits_any = 0u;
+                    if (mine) bits_any = __reduce_or_sync(m_any, bit);
+                    bits_any = __shfl_sync(ISB_FULL, bits_any, src);
+                    const uint32_t old = any[wv];
+                    if (__popc(m_any) != __popc(bits_any) || (old & bits_any)) dup = true;
+                    __syncwarp();
+                    if (lane == 0) any[wv] = old | bits_any;
+                    for (int rr = 0; rr < na; ++rr) {
+                        const bool mr = mine && r == rr;
+                        const unsigned m_r = __ballot_sync(ISB_FULL, mr);
+                        if (!m_r) continue;
+                        uint32_t bits = 0u;
+                        if (mr) bits = __reduce_or_sync(m_r, bit);
+                        bits = __shfl_sync(ISB_FULL, bits, __ffs((int)m_r) - 1);
+                        if (lane == 0) any[(size_t)(1 + rr) * m.nw + wv] |= bits;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (dup) {                                             // exact path with the multiplicity planes
+                for (int i = lane; i < n_words; i += 32) any[i] = 0u;
+                __syncwarp();
+                for (int i0 = cl_; i0 < ch_; i0 += 32) {
+                    int b = 0, id = 0;
+                    if (i0 + lane < ch_ && cand(i0 + lane, b, id)) k3_row_set(any, m, na, bases, b, id, a.d_err);
+                }
+                __syncwarp();
+            }
+            if (in_smem) {
+                for (int i = lane; i < n_words; i += 32) g_any[i] = any[i];
+                __syncwarp();
+            }
+        }
+        if (lane == 0) a.has2[slot] = dup ? 1 : 0;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+
+static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
+{
+    size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
+    if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
+    else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
+    if (fuse)
+        b += 4 * K1F_WARPS * ISB_K3_ROW_SLOT + 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256;
+    return b;
+}
+
+// tile bounds + staging capacity of a batch
+static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L, int *seg_cap)
+{
+    cudaStream_t st = ctx->stream;
+    if (rd->max_seg_len < 1 || rd->max_seg_len > K1F_MAXLEN)
+        return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: max_seg_len must be in [1, 256]");
+    if (((uintptr_t)rd->words & 15) != 0) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: words must be 16-byte aligned");
+    if (start & 7) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: start must be a multiple of 8 (the stream is position-aligned)");
+    const int n_tiles = (L + K1F_TILE - 1) / K1F_TILE;
+    int rc;
+    if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 4 * (size_t)n_tiles))) return rc;
+    int64_t *tile_lo = (int64_t *)ctx->buf[SL_RD_BOUNDS].p, *tile_hi = tile_lo + n_tiles;
+    k1f_tile_bounds<<<(n_tiles + 255) / 256, 256, 0, st>>>(rd->seg_start, rd->n_segs, start, n_tiles, rd->max_seg_len, tile_lo, tile_hi);
+    ISB_LAUNCH_CHECK();
+    rd->n_tiles = n_tiles;
+    rd->tile_lo = tile_lo;
+    rd->tile_hi = tile_hi;
+    rd->tile_wlo = rd->tile_whi = nullptr;
+    // staging capacity: what a tile holds on average + 15 % + 48 (the Poisson spread of ~800 segments is 3.5 %), capped
+    int64_t cap = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1F_TILE + rd->max_seg_len) * 1.15) + 48 : 64;
+    if (cap < 64) cap = 64;
+    if (cap > K1F_STAGE_IT * K1F_THREADS) cap = K1F_STAGE_IT * K1F_THREADS;
+    *seg_cap = (int)((cap + 3) & ~(int64_t)3);
+    return ISB_OK;
+}
+
+int isb_k1f_pileup_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,
+                          int M, int32_t *counts, unsigned long long *nmask)
+{
+    cudaStream_t st = ctx->stream;
+    if (L <= 0) return ISB_OK;
+    if (M > 1 && !pair_mm) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: pair_mm is required when M > 1");
+    int rc, seg_cap = 0;
+    if ((rc = k1f_prepare(ctx, rd, start, L, &seg_cap))) return rc;
+    k1f_args a;
+    memset(&a, 0, sizeof(a));
+    a.rd = *rd; a.pair_mm = pair_mm; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = M; a.counts = counts;
+    a.d_err = ctx->d_err; a.seg_cap = seg_cap;
+    const int groups = M == 1 ? 1 : (M + K1F_LEVELS - 1) / K1F_LEVELS;
+    const int Mg = M == 1 ? 0 : (M < K1F_LEVELS ? M : K1F_LEVELS);
+    const size_t smem = k1f_smem_bytes(seg_cap, M == 1, false, Mg);
+    static bool attr_m1[64] = {false}, attr_mm[64] = {false};      // function attributes are per device
+    if (nmask) ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
+    if (M == 1) {
+        if (!attr_m1[ctx->device & 63])
+            ISB_CUDA(cudaFuncSetAttribute(k1f_pileup<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_m1[ctx->device & 63] = true;
+        k1f_pileup<true, false><<<rd->n_tiles, K1F_THREADS, smem, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    } else {
+        if (!attr_mm[ctx->device & 63])
+            ISB_CUDA(cudaFuncSetAttribute(k1f_pileup<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_mm[ctx->device & 63] = true;
+        k1f_pileup<false, false><<<dim3(rd->n_tiles, groups), K1F_THREADS, smem, st>>>(a);
+        ISB_LAUNCH_CHECK();
+    }
+    if (nmask && rd->n_nev > 0) return isb_k1r_n_events_launch(ctx, rd->n_nev, rd->nev_pos, rd->nev_pair, pair_mm, n_pairs, start, L, M, nmask);
+    return ISB_OK;
+}
+
+// Fused path: K1f<fused> (+ the linkage back end when `ld` is given).  Counters: [0] SNV rows, [1] LD rows, [2] sites,
+// [3] linked site pairs, [4] overflow row words; nothing is read back here.
+int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int32_t start, int32_t L,
+                           unsigned long long *nmask, const isb_k2_fuse *fuse, const isb_k1f_linkage *ld)
+{
+    cudaStream_t st = ctx->stream;
+    int rc, seg_cap = 0;
+    ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), st));
+    if (L <= 0) return ISB_OK;
+    if ((rc = k1f_prepare(ctx, rd, start, L, &seg_cap))) return rc;
+    if ((rc = isb_k2_prepare(ctx, fuse->min_freq))) return rc;
+    if (nmask) {                                                  // N events only make level 0 a key of MMcounts
+        ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
+        if ((rc = isb_k1r_n_events_launch(ctx, rd->n_nev, rd->nev_pos, rd->nev_pair, nullptr, n_pairs, start, L, 1, nmask))) return rc;
+    }
+    k1f_args a;
+    memset(&a, 0, sizeof(a));
+    a.rd = *rd; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = 1; a.d_err = ctx->d_err; a.seg_cap = seg_cap;
+    a.nmask = nmask;
+    a.k2 = *fuse;
+    a.thr2 = ctx->d_thr2; a.n_lut = ctx->n_lut; a.lut_default = ctx->lut_default;
+    a.n_rows = ctx->d_counters + 0;
+    isb_k3_tiles ts;
+    memset(&ts, 0, sizeof(ts));
+    if (ld) {
+        const int n_tiles = rd->n_tiles;
+        // site slots: 1 % SNV sites with headroom, grown on demand (isb_k1f_grow); ISB_K1F_SITES_INIT forces a small
+        // first guess (tests of the re-run path)
+        static const int64_t sites_init = getenv("ISB_K1F_SITES_INIT") ? atoll(getenv("ISB_K1F_SITES_INIT")) : 0;
+        const int64_t want = sites_init > 0 ? sites_init : (int64_t)L / 72 + 4096;
+        if (ctx->sites_cap < want) ctx->sites_cap = want;
+        const int64_t cap = ctx->sites_cap;
+        if ((rc = isb_ensure(ctx, SL_TILE_SITES, sizeof(int32_t) * 2 * (size_t)n_tiles))) return rc;
+        if ((rc = isb_ensure(ctx, SL_SITE_POS, sizeof(int32_t) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_SITE_META, sizeof(isb_site_meta) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_ROW_OFF, sizeof(int64_t) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_HAS2, (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_SITE_COUNTS, sizeof(int4) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)cap * (ISB_K3_ROW_SLOT + 8) + 64)))) return rc;
+        a.do_ld = 1;
+        a.n_splits = ld->n_splits; a.splits = ld->splits;
+        a.tile_first = (int32_t *)ctx->buf[SL_TILE_SITES].p;
+        a.tile_cnt = a.tile_first + n_tiles;
+        a.sites_cap = cap;
+        a.site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
+        a.meta = (isb_site_meta *)ctx->buf[SL_SITE_META].p;
+        a.row_off = (int64_t *)ctx->buf[SL_ROW_OFF].p;
+        a.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;
+        a.site_counts = (int4 *)ctx->buf[SL_SITE_COUNTS].p;
+        a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
+        a.row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
+        a.n_sites = ctx->d_counters + 2;
+        a.row_words_total = ctx->d_counters + 4;
+        ts.n_tiles = n_tiles; ts.tile_first = a.tile_first; ts.tile_cnt = a.tile_cnt; ts.sites_cap = cap;
+        ts.site_pos = a.site_pos; ts.meta = a.meta; ts.row_off = a.row_off; ts.has2 = a.has2; ts.site_counts = a.site_counts;
+        ts.rows = a.rows;
+    }
+    const size_t smem = k1f_smem_bytes(seg_cap, true, true, 0);
+    static bool attr[64] = {false};
+    if (!attr[ctx->device & 63])
+        ISB_CUDA(cudaFuncSetAttribute(k1f_pileup<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr[ctx->device & 63] = true;
+    int ts0 = isb_time_begin(ctx, 0);
+    k1f_pileup<true, true><<<rd->n_tiles, K1F_THREADS, smem, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    isb_time_end(ctx, ts0);
+    if (ld) {
+        int ts2 = isb_time_begin(ctx, 2);
+        rc = isb_k3_backend_tiles(ctx, rd, &ts, n_pairs, start, L, nmask, fuse->site_flags, ld->n_splits, ld->splits, ld->min_snp,
+                                  ld->rows, ld->cap);
+        isb_time_end(ctx, ts2);
+        if (rc) return rc;
+    }
+    return ISB_OK;
+}
+
+// After the counters / error word of a fused run are on the host: grow what was too small.  *again = true -> re-run.
+int isb_k1f_grow(isb_ctx *ctx, bool *again)
+{
+    *again = false;
+    const unsigned e = *ctx->h_err;
+    if (e & ~(ISB_DEV_ERR_SITECAP | ISB_DEV_ERR_ROWBUF)) return ISB_OK;   // a real error: the caller reports it
+    const int64_t n_sites = (int64_t)ctx->h_counters[2], n_listed = (int64_t)ctx->h_counters[3];
+    if (n_sites > ctx->sites_cap) {
+        ctx->sites_cap = n_sites + n_sites / 8 + 1024;
+        *again = true;
+    }
+    if (e & ISB_DEV_ERR_ROWBUF) {
+        const size_t need = (size_t)ctx->sites_cap * ISB_K3_ROW_SLOT + (size_t)ctx->h_counters[4];
+        int rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * (need + need / 8 + 1024));
+        if (rc) return rc;
+        *again = true;
+    }
+    const int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
+    if (n_listed > cap_pairs) {
+        int rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(n_listed + n_listed / 8 + 1024));
+        if (rc) return rc;
+        *again = true;
+    }
+    if (*again) {
+        cudaError_t ce = cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned int), ctx->stream);
+        if (ce != cudaSuccess) return isb_fail(ctx, ISB_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    return ISB_OK;
+}

@@ -26,6 +26,7 @@
 #include "isb_common.cuh"
 #include "isb_bitslice.cuh"
 #include <climits>
+#include <cstdlib>
 
 #define K1R_THREADS (K1R_TILE / 8)     // one thread per 8 positions (one word of nibbles)
 #define K1R_MAXLEN 256                 // hard cap of max_seg_len
@@ -337,6 +338,10 @@ int isb_k1r_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_mm, int6
 {
     cudaStream_t st = ctx->stream;
     if (L <= 0) return ISB_OK;
+    // default: the circular-schedule kernel of isb_k1f_fused.cu (no word staging, conflict-free); ISB_K1R_LEGACY=1 keeps
+    // the first K1r (TMA-staged words, free-running per-thread candidate loops) for A/B runs
+    static const int legacy = getenv("ISB_K1R_LEGACY") ? atoi(getenv("ISB_K1R_LEGACY")) : 0;
+    if (!legacy) return isb_k1f_pileup_launch(ctx, rd, pair_mm, n_pairs, start, L, M, counts, nmask);
     if (rd->max_seg_len < 1 || rd->max_seg_len > K1R_MAXLEN)
         return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: max_seg_len must be in [1, 256]");
     if (M > 1 && !pair_mm) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: pair_mm is required when M > 1");

@@ -16,11 +16,12 @@
 // overlap quirk can produce) are handled by a slow exact path.
 #include "isb_common.cuh"
 #include "isb_scan.cuh"
+#include "isb_k3_dev.cuh"
 #include <math_constants.h>
 #include <cstdlib>
 
 #define K3_THREADS 256
-#define K3_ROW_SCRATCH 64            // words of per-warp shared scratch for assembling a site's bit rows
+#define K3_ROW_SCRATCH ISB_K3_ROW_SLOT // words of per-warp shared scratch for assembling a site's bit rows (= the fixed row slot)
 
 struct k3_args {
     // events
@@ -54,6 +55,12 @@ struct k3_args {
     int tile_tp;
     int32_t *pair_i, *pair_j;      // linked site pairs (site indices), filled by k3_enum_pairs
     int64_t pair_cap;
+    // per-tile site slots (fused read-major path, isb_k1f_fused.cu): sites are not globally ordered, a tile's are
+    int n_tiles;
+    const int32_t *tile_first, *tile_cnt;
+    int64_t sites_cap;
+    const int4 *site_counts;       // counts per site slot (M = 1) instead of counts[p]
+    const unsigned long long *n_sites_dev;   // device-side site / listed-pair counts (no host round trip)
     // output
     isb_ld_row *out;
     int64_t cap;
@@ -85,17 +92,9 @@ __device__ __forceinline__ bool k3_qualifies(const k3_args &a, int64_t e, unsign
     return a.qual[e] >= a.min_qual && b < 4 && ((bases >> b) & 1u);
 }
 
-// split = last split whose start <= abs_pos, if abs_pos <= its end (else -1)
 __device__ __forceinline__ int k3_site_split(const k3_args &a, int64_t abs_pos)
 {
-    int s_lo = 0, s_hi = a.n_splits;
-    while (s_lo < s_hi) {
-        const int mid = (s_lo + s_hi) >> 1;
-        if ((int64_t)a.splits[2 * mid] <= abs_pos) s_lo = mid + 1; else s_hi = mid;
-    }
-    int split = s_lo - 1;
-    if (split >= 0 && abs_pos > (int64_t)a.splits[2 * split + 1]) split = -1;
-    return split;
+    return isb_site_split(a.splits, a.n_splits, abs_pos);
 }
 
 // ---- per-site event range, split --------------------------------------------------------------------------------
@@ -138,21 +137,6 @@ __global__ void __launch_bounds__(256) k3r_site_cand(k3_args a, isb_reads_dev rd
     cand_lo[k] = lo;
     n_cand[k] = (int32_t)(hi - lo);
     a.meta[k].split = k3_site_split(a, abs_pos);
-}
-
-// One candidate of a site: is position abs_pos covered by segment g with a passing A/C/T/G base?
-__device__ __forceinline__ bool k3r_candidate(const isb_reads_dev &rd, int64_t g, int64_t abs_pos, int &b, int &id)
-{
-    const int32_t s = __ldg(rd.seg_start + g);
-    const int j = (int)(abs_pos - (int64_t)s);
-    if (j < 0 || j >= (int)__ldg(rd.seg_len + g)) return false;
-    const int jn = j + (s & 7);                                       // position-aligned stream: nibble index in the segment's words
-    const uint32_t w = __ldg(rd.words + __ldg(rd.seg_word + g) + (jn >> 3));
-    const uint32_t code = (w >> ((jn & 7) << 2)) & 15u;
-    if (!code) return false;
-    b = __ffs((int)code) - 1;                                       // one-hot A,C,T,G
-    id = __ldg(rd.seg_pair + g);
-    return true;
 }
 
 // ---- column-word front end (isb_cols_batch): the entries of a site are ONE nibble of every word of its column list ----
@@ -228,21 +212,6 @@ __global__ void __launch_bounds__(256) k3c_site_prep(k3_args a, isb_cols_dev cd,
     r.pad[0] = r.pad[1] = 0;
     recs[k] = r;
     a.meta[k].split = r.split;
-}
-
-__device__ __forceinline__ bool k3_row_set(uint32_t *any, const isb_site_meta &m, int na, unsigned bases, int b, int id,
-                                           unsigned int *d_err)
-{
-    const int w = (id >> 5) - m.wlo;
-    const uint32_t bit = 1u << (id & 31);
-    const int r = __popc(bases & ((1u << b) - 1u));
-    const bool dbl = atomicOr(any + w, bit) & bit;                    // second entry of this pair on this site
-    uint32_t *ge1 = any + (size_t)(1 + r) * m.nw;
-    if (atomicOr(ge1 + w, bit) & bit) {
-        uint32_t *ge2 = any + (size_t)(1 + na + r) * m.nw;
-        if (atomicOr(ge2 + w, bit) & bit) atomicOr(d_err, ISB_DEV_ERR_MULT);
-    }
-    return dbl;
 }
 
 // Fused read-major front end (warp per site): gather the site's qualifying (pair id, base) entries from its candidate
@@ -588,6 +557,13 @@ __device__ __forceinline__ int k3_pair_count(const k3_site &si, int ra, const k3
     return c;
 }
 
+// exact-mm counts of a site at level m: per site slot (fused read-major path, M = 1) or from the dense counts array
+__device__ __forceinline__ int4 k3_site_counts(const k3_args &a, int64_t k, int32_t p, int m)
+{
+    if (a.site_counts) return __ldg(a.site_counts + k);
+    return __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)p * a.M + m);
+}
+
 __device__ __forceinline__ bool k3_level_present(const k3_args &a, int32_t p, int m, const int4 &E)
 {
     if (E.x + E.y + E.z + E.w > 0) return true;
@@ -679,11 +655,28 @@ __global__ void __launch_bounds__(256) k3_enum_pairs_t(k3_args a)
 #ifndef K3_STATS_MINB
 #define K3_STATS_MINB 4              // 64 registers: 4 blocks of 256 threads per SM (measured: K3 stage 0.394 -> 0.367 ms per 2e7 positions)
 #endif
+__device__ __forceinline__ void k3_pair_stats_one(const k3_args &a, int64_t t);
+
 __global__ void __launch_bounds__(256, K3_STATS_MINB) k3_pair_stats(k3_args a, int64_t n_pairs_listed)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs_listed) return;
-    const k3_site si = k3_load_site(a, a.pair_i[t]), sj = k3_load_site(a, a.pair_j[t]);
+    k3_pair_stats_one(a, t);
+}
+
+// the same over a device-side pair count (grid-stride): no host round trip between enumeration and statistics
+__global__ void __launch_bounds__(256, K3_STATS_MINB) k3_pair_stats_dev(k3_args a)
+{
+    const unsigned long long listed = *a.n_site_pairs;
+    const int64_t n = (int64_t)(listed < (unsigned long long)a.pair_cap ? listed : (unsigned long long)a.pair_cap);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) k3_pair_stats_one(a, t);
+}
+
+__device__ __forceinline__ void k3_pair_stats_one(const k3_args &a, int64_t t)
+{
+    const int64_t ki = a.pair_i[t], kj = a.pair_j[t];
+    const k3_site si = k3_load_site(a, ki), sj = k3_load_site(a, kj);
     const int lo = max(si.wlo, sj.wlo), hi = min(si.wlo + si.nw, sj.wlo + sj.nw);
     unsigned long long pm = 1ull;                                      // mm levels having >= 1 linking pair
     if (a.M > 1) {
@@ -702,8 +695,8 @@ __global__ void __launch_bounds__(256, K3_STATS_MINB) k3_pair_stats(k3_args a, i
     int C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0};
     const int m_last = 63 - __clzll(pm);
     for (int m = 0; m <= m_last; ++m) {
-        const int4 E1 = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)si.p * a.M + m);
-        const int4 E2 = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)sj.p * a.M + m);
+        const int4 E1 = k3_site_counts(a, ki, si.p, m);
+        const int4 E2 = k3_site_counts(a, kj, sj.p, m);
         C1[0] += E1.x; C1[1] += E1.y; C1[2] += E1.z; C1[3] += E1.w;
         C2[0] += E2.x; C2[1] += E2.y; C2[2] += E2.z; C2[3] += E2.w;
         if (!((pm >> m) & 1ull)) continue;
@@ -728,12 +721,17 @@ __global__ void __launch_bounds__(256, K3_STATS_MINB) k3_pair_stats(k3_args a, i
 // Self edges: a pair with two entries (first, second in column order) on ONE site gives the combo
 // "b_first:b_second" on the edge (p, p) (itertools.combinations over the pair's entry list).  Rare: one thread per
 // flagged site, exact and slow.
-template <int kMode>   // 0 = position-major events, 1 = read-major segments, 2 = column words
+template <int kMode>   // 0 = position-major events, 1 = read-major segments, 2 = column words, 3 = read-major, per-tile site slots
 __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd, isb_cols_dev cd,
                                                      const int64_t *__restrict__ cand_lo, const int32_t *__restrict__ n_cand)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.S; k += stride) {
+    int64_t S = a.S;
+    if (kMode == 3) {
+        const unsigned long long ns = *a.n_sites_dev;
+        S = (int64_t)(ns < (unsigned long long)a.sites_cap ? ns : (unsigned long long)a.sites_cap);
+    }
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < S; k += stride) {
         if (!a.has2[k] || a.meta[k].split < 0) continue;
         const int32_t p = a.site_pos[k];
         const int64_t abs_pos = (int64_t)p + a.start;
@@ -742,11 +740,16 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
         // slots of the site's column list (column words)
         k3c_column col = {0, 0, 0};
         if (kMode == 2) col = k3c_site_column(cd, p + a.col_shift);
-        const int64_t lo = kMode == 2 ? 0 : (kMode == 1 ? cand_lo[k] : a.site_ev[2 * k]);
-        const int64_t hi = kMode == 2 ? col.depth : (kMode == 1 ? lo + n_cand[k] : a.site_ev[2 * k + 1]);
+        int64_t lo = kMode == 2 ? 0 : (kMode == 1 ? cand_lo[k] : (kMode == 0 ? a.site_ev[2 * k] : 0));
+        int64_t hi = kMode == 2 ? col.depth : (kMode == 1 ? lo + n_cand[k] : (kMode == 0 ? a.site_ev[2 * k + 1] : 0));
+        if (kMode == 3) {                                          // candidate segments inside the site's tile range
+            const int tl = p / K1R_TILE;
+            lo = isb_lower_bound(rd.seg_start, rd.tile_lo[tl], rd.tile_hi[tl], abs_pos - rd.max_seg_len + 1);
+            hi = isb_lower_bound(rd.seg_start, lo, rd.tile_hi[tl], abs_pos + 1);
+        }
         auto entry = [&](int64_t e, int &b, int &rid) -> bool {
             if (kMode == 2) return k3c_candidate(cd, col, (int)e, a.n_pairs, b, rid) && ((bases >> b) & 1u);
-            if (kMode == 1) return k3r_candidate(rd, e, abs_pos, b, rid) && ((bases >> b) & 1u);
+            if (kMode == 1 || kMode == 3) return k3r_candidate(rd, e, abs_pos, b, rid) && ((bases >> b) & 1u);
             if (!k3_qualifies(a, e, bases)) return false;
             b = a.base[e];
             rid = a.read_id[e];
@@ -756,7 +759,7 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
         for (int i = 0; i < 16; ++i) K[i] = 0;
         int C[4] = {0, 0, 0, 0};
         for (int m = 0; m < a.M; ++m) {
-            const int4 E = __ldg(reinterpret_cast<const int4 *>(a.counts) + (size_t)p * a.M + m);
+            const int4 E = k3_site_counts(a, k, p, m);
             C[0] += E.x; C[1] += E.y; C[2] += E.z; C[3] += E.w;
             bool added = false;
             for (int64_t e2 = lo; e2 < hi; ++e2) {
@@ -781,6 +784,94 @@ __global__ void __launch_bounds__(128) k3_self_edges(k3_args a, isb_reads_dev rd
             k3_emit(a, p, p, m, A, al, A, al, K[A * 4 + A], K[A * 4 + al], K[al * 4 + A], K[al * 4 + al]);
         }
     }
+}
+
+
+// Enumeration over PER-TILE site slots (fused read-major path): the sites of a tile of K1R_TILE positions occupy the
+// contiguous, position-ordered slots [tile_first, tile_first + tile_cnt); tiles got their slots in completion order, so
+// the partners of a site are the later slots of its own tile, then the slots of the following tiles up to the end of
+// the site's split.  Grid-stride over the device-side site count.
+__global__ void __launch_bounds__(256) k3_enum_pairs_tiles(k3_args a)
+{
+    const unsigned long long ns = *a.n_sites_dev;
+    const int64_t S = (int64_t)(ns < (unsigned long long)a.sites_cap ? ns : (unsigned long long)a.sites_cap);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < S * K3_ENUM_LANES; t += stride) {
+        const int64_t k = t / K3_ENUM_LANES;
+        const int sub = (int)(t % K3_ENUM_LANES);
+        const isb_site_meta mi = a.meta[k];
+        if (mi.split < 0 || mi.nw == 0) continue;
+        const uint32_t *any_i = a.rows + a.row_off[k] - mi.wlo;
+        const int i_hi = mi.wlo + mi.nw;
+        const int32_t p_i = a.site_pos[k];
+        int tl = p_i / K1R_TILE;
+        const int64_t split_end = (int64_t)__ldg(a.splits + 2 * mi.split + 1) - a.start;   // relative, inclusive
+        int last_tile = (int)(split_end / K1R_TILE);
+        if (last_tile > a.n_tiles - 1) last_tile = a.n_tiles - 1;
+        int64_t j_lo = k + 1, j_hi = (int64_t)a.tile_first[tl] + a.tile_cnt[tl];
+        for (;;) {
+            if (j_hi > S) j_hi = S;
+            for (int64_t j = j_lo + sub; j < j_hi; j += K3_ENUM_LANES) {
+                const isb_site_meta mj = a.meta[j];
+                if (mj.split != mi.split) continue;
+                const int lo = max(mi.wlo, mj.wlo), hi = min(i_hi, mj.wlo + mj.nw);
+                bool linked = false;
+                if (lo < hi) {
+                    const uint32_t *any_j = a.rows + a.row_off[j] - mj.wlo;
+                    for (int w = lo; w < hi; ++w)
+                        if (any_i[w] & any_j[w]) { linked = true; break; }
+                }
+                if (linked) {
+                    const unsigned act = __activemask();
+                    const int leader = __ffs(act) - 1, lane = threadIdx.x & 31;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(a.n_site_pairs, (unsigned long long)__popc(act));
+                    base = __shfl_sync(act, base, leader);
+                    const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
+                    if ((int64_t)slot < a.pair_cap) { a.pair_i[slot] = (int32_t)k; a.pair_j[slot] = (int32_t)j; }
+                }
+            }
+            if (++tl > last_tile) break;
+            j_lo = a.tile_first[tl];
+            j_hi = j_lo + a.tile_cnt[tl];
+        }
+    }
+}
+
+// Linkage back end of the fused read-major path (M = 1): enumeration, statistics and self edges on the site slots K1f
+// filled.  Site and pair counts stay on the device; the caller checks the capacities afterwards (isb_k1f_grow).
+int isb_k3_backend_tiles(isb_ctx *ctx, const isb_reads_dev *rd, const isb_k3_tiles *ts, int64_t n_pairs, int32_t start, int32_t L,
+                         const unsigned long long *nmask, const uint8_t *site_flags, int32_t n_splits, const int32_t *splits,
+                         int min_snp, isb_ld_row *rows, int64_t cap)
+{
+    cudaStream_t st = ctx->stream;
+    int rc;
+    int64_t cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
+    if (cap_pairs < 6 * ts->sites_cap) {
+        if ((rc = isb_ensure(ctx, SL_PAIRS, 2 * sizeof(int32_t) * (size_t)(6 * ts->sites_cap)))) return rc;
+        cap_pairs = (int64_t)(ctx->buf[SL_PAIRS].cap / (2 * sizeof(int32_t)));
+    }
+    k3_args a;
+    memset(&a, 0, sizeof(a));
+    a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = 1; a.min_snp = min_snp;
+    a.nmask = nmask; a.site_flags = site_flags; a.n_splits = n_splits; a.splits = splits;
+    a.site_pos = ts->site_pos; a.meta = ts->meta; a.row_off = ts->row_off; a.has2 = ts->has2; a.rows = ts->rows;
+    a.site_counts = ts->site_counts; a.n_tiles = ts->n_tiles; a.tile_first = ts->tile_first; a.tile_cnt = ts->tile_cnt;
+    a.sites_cap = ts->sites_cap; a.n_sites_dev = ctx->d_counters + 2;
+    a.pair_cap = cap_pairs;
+    a.pair_i = (int32_t *)ctx->buf[SL_PAIRS].p;
+    a.pair_j = a.pair_i + cap_pairs;
+    a.out = rows; a.cap = cap;
+    a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
+    const int grid = ctx->sm_count * 8;
+    k3_enum_pairs_tiles<<<grid, 256, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    k3_pair_stats_dev<<<grid, 256, 0, st>>>(a);
+    ISB_LAUNCH_CHECK();
+    const isb_cols_dev cd_none = {};
+    k3_self_edges<3><<<ctx->sm_count * 2, 128, 0, st>>>(a, *rd, cd_none, nullptr, nullptr);
+    ISB_LAUNCH_CHECK();
+    return ISB_OK;
 }
 
 static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd, int64_t n, const int32_t *ref_pos, const uint8_t *base,

@@ -267,3 +267,144 @@ def test_row_storage_regrow(null_lut):
     env = dict(os.environ, ISB_K3_ROWS_INIT="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- the fused read-major kernel (K1f: pileup + SNV call + linkage site rows in one launch; M = 1, no raw counts asked) ----
+
+def check_fused(eng, batch, null_lut, tol=1e-9, rd=None, nmask=False, **kw):
+    okw = {k: v for k, v in kw.items() if k != "skip_linkage"}
+    exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"],
+                                 do_linkage=not kw.get("skip_linkage", False), **okw)
+    assert exp["counts"].shape[1] == 1
+    if rd is None:
+        rd = reads.events_to_reads(batch, kw.get("min_qual", 30))
+    want = ("covT", "clonT", "site_flags", "snv", "ld") + (("nmask",) if nmask else ())
+    n0 = eng.launch_count
+    got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=rd, want=want, **kw)
+    launches = eng.launch_count - n0
+    assert np.array_equal(got["covT"], exp["covT"])
+    ok = ~np.isnan(exp["clonT"])
+    assert np.array_equal(np.isnan(got["clonT"]), ~ok)
+    assert np.array_equal(got["clonT"][ok].view(np.uint32), exp["clonT"][ok].view(np.uint32))
+    assert np.array_equal(got["site_flags"], exp["site_flags"])
+    if nmask:
+        assert np.array_equal(got["nmask"], exp["nmask"])
+    assert_snv_equal(got["snv"], exp["snv"])
+    if not kw.get("skip_linkage"):
+        assert_ld_equal(got["ld"], exp["ld"], tol=tol)
+        assert got["n_sites"] == int((exp["site_flags"] & 0x10).astype(bool).sum())
+    return got, exp, launches
+
+
+@pytest.mark.parametrize("L,cov,dens,nsc,n_frac,seed,max_len", [
+    (30000, 50, 0.01, 1, 0.0, 20260102, 256),
+    (12000, 100, 0.05, 1, 0.002, 20260105, 256),     # non-ACGT read bases
+    (700, 30, 0.02, 3, 0.0, 7, 256),                 # tiny scaffolds: tiles across scaffold / split boundaries
+    (25000, 8, 0.01, 1, 0.0, 11, 256),               # coverage around min_cov
+    (9000, 400, 0.01, 1, 0.0, 3, 150),               # > 255 candidates per position: plane flushes into the tile
+    (12000, 500, 0.05, 1, 0.0, 20260105, 256),       # BASELINE configs[4] shaped: wide bit rows (overflow region)
+    (20001, 60, 0.02, 2, 0.0, 5, 37),                # L not a multiple of 8, many short pieces
+    (3000, 2500, 0.02, 1, 0.0, 9, 256),              # several staging chunks per tile: global candidate search for the sites
+])
+def test_fused_parity(eng, null_lut, L, cov, dens, nsc, n_frac, seed, max_len):
+    batch = synth.make_batch(L, cov, dens, seed, n_scaffolds=nsc, skip_mm=True, n_frac=n_frac)
+    rd = reads.events_to_reads(batch, max_len=max_len, odd_blocks=max_len != 256)
+    _, _, launches = check_fused(eng, batch, null_lut, rd=rd, nmask=n_frac > 0)
+    assert launches <= 8                            # tile bounds, K1f, enumeration, statistics, self edges (+ N events, threshold table)
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+def test_fused_golden_reads_set_mode(eng, which, null_lut):
+    """The bundled BAM's reads (indels, overlap-quirk double entries -> self edges) with every pair at level 0."""
+    batch, _ = load_batch(which)
+    batch = dict(batch)
+    batch["pair_mm"] = np.zeros_like(batch["pair_mm"])
+    check_fused(eng, batch, null_lut)
+
+
+def test_fused_other_settings(eng, null_lut):
+    batch = synth.make_batch(20000, 40, 0.03, 21, skip_mm=True)
+    for kw in (dict(min_cov=1, min_freq=0.10, min_snp=5), dict(min_cov=10, min_freq=0.02, min_snp=40),
+               dict(min_cov=0), dict(skip_linkage=True)):
+        check_fused(eng, batch, null_lut, **kw)
+
+
+def test_fused_short_and_split_segments(eng, null_lut):
+    rng = np.random.default_rng(4)
+    L = 5000
+    starts, lens, pairs, codes = [], [], [], []
+    for i in range(3000):
+        n = int(rng.integers(1, 41)) if i % 7 else int(rng.integers(257, 700))
+        s = int(rng.integers(0, L - n))
+        starts.append(s); lens.append(n); pairs.append(i // 2)
+        c = rng.integers(0, 5, n).astype(np.uint8)
+        c[rng.random(n) < 0.2] = reads.NO_EVENT
+        codes.append(c)
+    rd = reads.build_reads(starts, lens, pairs, np.concatenate(codes))
+    ev = reads.reads_to_events(rd)
+    ev["pair_mm"] = np.zeros(1500, np.uint8)
+    ev["ref_codes"] = rng.integers(0, 4, L).astype(np.uint8)
+    ev["splits"] = np.array([[0, 1999], [2000, L - 1]], dtype=np.int32)
+    check_fused(eng, ev, null_lut, rd=rd, nmask=True)
+
+
+def test_fused_empty_and_errors(eng, null_lut):
+    from instrain_b200 import _cabi
+    L = 3000
+    ref = np.zeros(L, np.uint8)
+    rd = reads.build_reads([], [], [], [])
+    got = eng.profile_batch(dict(pair_mm=np.zeros(0, np.uint8)), ref, np.array([[0, L - 1]], np.int32), M=1, reads=rd)
+    assert got["covT"].sum() == 0 and got["n_snv"] == 0 and got["n_ld"] == 0 and got["n_sites"] == 0
+    batch = synth.make_batch(20000, 30, 0.01, 1, skip_mm=True)
+    rd = reads.events_to_reads(batch)
+    bad = dict(rd); bad["seg_start"] = rd["seg_start"].copy(); bad["seg_start"][100:900] = bad["seg_start"][100:900][::-1]
+    with pytest.raises(_cabi.IsbError) as ei:
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=bad)
+    assert ei.value.code == _cabi.ISB_ERR_ORDER
+    bad = dict(rd); bad["seg_word"] = rd["seg_word"].copy(); bad["seg_word"][50:] += 1 << 30
+    with pytest.raises(_cabi.IsbError):
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=bad)
+    bad = dict(rd); bad["seg_pair"] = rd["seg_pair"].copy(); bad["seg_pair"][::3] = 1 << 29      # pair ids beyond n_pairs
+    with pytest.raises(_cabi.IsbError):
+        eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=bad)
+    check_fused(eng, batch, null_lut, rd=rd)                                   # the context is usable afterwards
+
+
+def test_fused_equals_unfused_larger(eng, null_lut):
+    """Fused kernel against K1 -> K2 -> K3 on event columns at a size the oracle would take minutes for, through the
+    device generator's segments (uniform 150-base reads) and through the transfer formats."""
+    batch = synth.make_batch(600000, 80, 0.01, 99, n_scaffolds=2, skip_mm=True)
+    rd = reads.events_to_reads(batch, max_len=150, odd_blocks=True)
+    want = ("covT", "clonT", "site_flags", "snv", "ld")
+    a = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, want=want)
+    for fmt in (rd, reads.delta_reads(rd, batch["ref_codes"]), reads.compact_reads(rd)):
+        b = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, want=want, reads=fmt)
+        for k in ("covT", "site_flags"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["clonT"].view(np.uint32), b["clonT"].view(np.uint32))
+        assert_snv_equal(a["snv"], b["snv"])
+        assert_ld_equal(a["ld"], b["ld"], tol=0.0)
+        assert a["n_sites"] == b["n_sites"] and a["n_site_pairs"] == b["n_site_pairs"]
+
+
+def test_fused_scratch_regrow(null_lut):
+    """Site slots, bit-row storage and the pair list start from a forced tiny guess and are regrown from the counted need
+    (separate process: the guess is read once per process)."""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from conftest import load_lut, assert_ld_equal, assert_snv_equal\n"
+            "from oracle import restate, synth\n"
+            "from instrain_b200 import reads\n"
+            "from instrain_b200.engine import Engine\n"
+            "lut = load_lut(); b = synth.make_batch(12000, 500, 0.05, 20260105, skip_mm=True)\n"
+            "exp = restate.profile_events(b, b['ref_codes'], lut[0], lut[1], b['splits'])\n"
+            "e = Engine(0, lut[0], lut[1])\n"
+            "for _ in range(2):\n"
+            "    got = e.profile_batch(b, b['ref_codes'], b['splits'], M=1, reads=reads.events_to_reads(b), want=('snv', 'ld'))\n"
+            "    assert_snv_equal(got['snv'], exp['snv']); assert_ld_equal(got['ld'], exp['ld'], tol=1e-9)\n"
+            "print('regrow ok', len(got['ld']))\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                      os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ISB_K1F_SITES_INIT="16")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
