@@ -71,6 +71,7 @@ struct k1f_args {
     int32_t n_splits;
     const int32_t *splits;
     int32_t *tile_first, *tile_cnt;
+    const int32_t *tile_split;
     int64_t sites_cap;
     int32_t *site_pos;
     isb_site_meta *meta;
@@ -82,10 +83,13 @@ struct k1f_args {
     unsigned long long *n_sites, *row_words_total;
 };
 
-// tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range
+// tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range, and (linkage) the index of
+// the last split that starts at or before the tile's first position (-1: none) -- the per-site split lookup of the fused
+// kernel walks forward from there instead of searching the whole table (a dependent chain of ~13 L2 round trips per site)
 __global__ void __launch_bounds__(256)
 k1f_tile_bounds(const int32_t *__restrict__ seg_start, int64_t n_segs, int32_t start, int n_tiles, int max_seg_len,
-                int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi)
+                int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi, const int32_t *__restrict__ splits, int n_splits,
+                int32_t *__restrict__ tile_split)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
@@ -93,6 +97,14 @@ k1f_tile_bounds(const int32_t *__restrict__ seg_start, int64_t n_segs, int32_t s
     const int64_t lo = isb_lower_bound(seg_start, 0, n_segs, first - max_seg_len + 1);
     tile_lo[t] = lo;
     tile_hi[t] = isb_lower_bound(seg_start, lo, n_segs, first + K1F_TILE);
+    if (tile_split) {
+        int s_lo = 0, s_hi = n_splits;
+        while (s_lo < s_hi) {
+            const int mid = (s_lo + s_hi) >> 1;
+            if ((int64_t)__ldg(splits + 2 * mid) <= first) s_lo = mid + 1; else s_hi = mid;
+        }
+        tile_split[t] = s_lo - 1;
+    }
 }
 
 __device__ __forceinline__ int k1f_warp_max(int v)
@@ -161,9 +173,11 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     // one packed word per staged segment: bits 11.. = index (relative to the chunk's word base wb) of the word that covers
     // tile column 0, + 160; bits 0..10 = tile-relative end + 256
     uint32_t *s_meta = reinterpret_cast<uint32_t *>(k1f_smem);
+    const uint32_t s_meta_sa = isb_smem_u32(s_meta);                      // its shared-space byte address
     int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);   // start relative to a.start (sorted): the search key
     uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);     // M > 1 only
-    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kM1 ? 8 : 9)) + 15) & ~(size_t)15);
+    int32_t *s_pair = s_start + a.seg_cap;                                // fused: pair id per staged segment (linkage sites)
+    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kFuse ? 12 : (kM1 ? 8 : 9))) + 15) & ~(size_t)15);
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_x);                  // M > 1: [Mg * 8][K1F_THREADS]
     // fused epilogue scratch
     int4 *s_tile = reinterpret_cast<int4 *>(s_x);                         // [K1F_WARPS][K1F_TILE4]
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                     r_n[k] = __ldg(a.rd.seg_len + g);
                     r_w[k] = __ldg(a.rd.seg_word + g);
                     if (g > 0) r_prev[k] = __ldg(a.rd.seg_start + g - 1);
-                    if (!kM1) r_pid[k] = __ldg(a.rd.seg_pair + g);
+                    if (!kM1 || (kFuse && a.do_ld)) r_pid[k] = __ldg(a.rd.seg_pair + g);
                 }
             }
             int r_mm[K1F_STAGE_IT];
@@ -254,6 +268,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 const int s_rel = min(max(s - T0, -255), K1F_TILE - 1);   // candidates start in (T0 - 256, T0 + 1024)
                 s_meta[i] = ((uint32_t)(wl_c - (s_rel >> 3) + 160) << 11) | (uint32_t)(s_rel + n_c + 256);
                 s_start[i] = s;
+                if (kFuse) s_pair[i] = r_pid[k];
                 if (!kM1) {
                     if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
                     s_mm[i] = (uint8_t)r_mm[k];
@@ -289,46 +304,59 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         // the 8 one-hot nibbles of segment i at the thread's positions (0 where the segment does not reach).  The stream
         // is position-aligned: the thread's column is ONE word of the segment, no shift.
         const uint32_t *wsrc = a.rd.words + wb + (t - 160);
-        auto meta_at = [&](int &jj) -> uint32_t {
-            const uint32_t md = jj < ch ? s_meta[jj] : 0u;        // 0: end field 0, never covers
-            jj = (jj + 1 == wrap) ? cl : jj + 1;
+        asm volatile("" : "+l"(wsrc));                            // keep the pointer in registers (ptxas re-derived it per load: 5 instructions)
+        // the schedule runs on shared-memory BYTE addresses of the table words (explicit ld.shared: through a generic
+        // pointer every predicated load re-derived the shared window base, 4 extra instructions each)
+        const uint32_t ja_cl = s_meta_sa + 4u * (uint32_t)cl, ja_ch = s_meta_sa + 4u * (uint32_t)ch, ja_wrap = s_meta_sa + 4u * (uint32_t)wrap;
+        uint32_t ja = s_meta_sa + 4u * (uint32_t)j;
+        // table word of the lane's current segment; bit 31 (unused: the index field holds < 2^20) = "beyond the lane's range"
+        auto meta_at = [&](uint32_t &jj) -> uint32_t {            // jj may run past ch (into the start column): flagged
+            uint32_t md;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(md) : "r"(jj));
+            md |= jj < ja_ch ? 0u : 0x80000000u;
+            jj = (jj + 4u == ja_wrap) ? ja_cl : jj + 4u;
             return md;
         };
         auto word_of = [&](uint32_t md) -> uint32_t {
-            return P_end < (int)(md & 0x7ffu) ? __ldg(wsrc + (md >> 11)) : 0u;
+            const bool ok = (int)md >= 0 && P_end < (int)(md & 0x7ffu);
+            return ok ? __ldg(wsrc + (md >> 11)) : 0u;              // ok => bit 31 clear: the shift leaves the index only
         };
         if (kM1) {
-            int s = 0;
-            for (; s + 16 <= Pm; s += 16) {                       // two Harley-Seal blocks per trip: 16 loads in flight
-                uint32_t x[8], y[8];
+            // Software pipeline: the 8 loads of block b + 1 are issued before the carry-save adds of block b, so a warp
+            // always has 8 .. 16 word loads in flight (the words come from HBM: ~1 us; with the loads of one block at a
+            // time the kernel ran at a third of its issue rate).
+            auto load8 = [&](uint32_t (&x)[8]) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = meta_at(j);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) y[u] = meta_at(j);
+                for (int u = 0; u < 8; ++u) x[u] = meta_at(ja);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) y[u] = word_of(y[u]);
+            };
+            auto flush_if = [&](int added) {
+                n8 += added;
+                if (n8 > 239) {                                    // the next 16 could overflow 255
+                    k1f_flush_planes(tile_lane, pl);
+                    n8 = 0;
+                }
+            };
+            const int nb = Pm >> 3;                                // Pm is a multiple of 8
+            uint32_t x[8], y[8];
+            load8(x);                                              // block 0
+            int b = 1;
+            for (; b + 1 < nb; b += 2) {                           // invariant: x holds block b - 1, not yet added
+                load8(y);
+                k1r_add8(pl, x);
+                load8(x);
+                k1r_add8(pl, y);
+                flush_if(16);
+            }
+            if (b < nb) {
+                load8(y);
                 k1r_add8(pl, x);
                 k1r_add8(pl, y);
-                n8 += 16;
-                if (n8 > 239) {                                    // the next trip could overflow 255
-                    k1f_flush_planes(tile_lane, pl);
-                    n8 = 0;
-                }
-            }
-            if (s < Pm) {                                          // Pm is a multiple of 8
-                uint32_t x[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = meta_at(j);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
+                flush_if(16);
+            } else {
                 k1r_add8(pl, x);
-                n8 += 8;
-                if (n8 > 239) {
-                    k1f_flush_planes(tile_lane, pl);
-                    n8 = 0;
-                }
+                flush_if(8);
             }
         } else {
             for (int s = 0; s < Pm; s += 8) {
@@ -336,8 +364,9 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 int lv[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    lv[u] = j < ch ? (int)s_mm[j] - m_base : -1;
-                    x[u] = meta_at(j);
+                    const int jcur = (int)((ja - s_meta_sa) >> 2);
+                    lv[u] = jcur < ch ? (int)s_mm[jcur] - m_base : -1;
+                    x[u] = meta_at(ja);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = word_of(x[u]);
@@ -504,31 +533,65 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
             glo = isb_lower_bound(a.rd.seg_start, lo, hi, abs_pos - maxlen + 1);
             ch_ = (int)(isb_lower_bound(a.rd.seg_start, glo, hi, abs_pos + 1) - glo);
         }
-        auto cand = [&](int i, int &b, int &id) -> bool {
-            bool ok;
-            if (single) {
-                const uint32_t md = s_meta[i];
-                if (!(pt + 256 < (int)(md & 0x7ffu)) || s_start[i] > p) return false;
-                const uint32_t code = (__ldg(wsrc0 + (md >> 11) + tcol) >> sh) & 15u;
-                if (!code) return false;
-                b = __ffs((int)code) - 1;
-                id = __ldg(a.rd.seg_pair + lo + i);
-                ok = true;
-            } else {
-                ok = k3r_candidate(a.rd, glo + i, abs_pos, b, id);
-            }
-            if (ok && (id < 0 || (int64_t)id >= a.n_pairs)) { atomicOr(a.d_err, ISB_DEV_ERR_SEG); ok = false; }
-            return ok && ((bases >> b) & 1u);
+        // Candidates in groups of 4 x 32: the word loads of a whole group are issued before the first is decoded (one
+        // L2 round trip per group instead of one per 32 candidates); group 0 -- all of them up to ~120x coverage -- stays
+        // decoded in registers for the second pass.
+        auto decode = [&](bool cov, uint32_t w, int pid, int &b, int &id) -> bool {
+            const uint32_t code = (w >> sh) & 15u;
+            if (!cov || !code) return false;
+            b = __ffs((int)code) - 1;
+            id = pid;
+            if (id < 0 || (int64_t)id >= a.n_pairs) { atomicOr(a.d_err, ISB_DEV_ERR_SEG); return false; }
+            return ((bases >> b) & 1u) != 0u;
         };
+        auto group = [&](int g0, int (&b4)[4], int (&id4)[4]) {    // candidates g0 .. g0 + 127 -> (base, id), base -1 = no entry
+            if (single) {
+                uint32_t w4[4];
+                bool cov[4];
+                int pid[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = g0 + u * 32 + lane;
+                    cov[u] = false; w4[u] = 0u; pid[u] = 0;
+                    if (i < ch_) {
+                        const uint32_t md = s_meta[i];
+                        cov[u] = (pt + 256 < (int)(md & 0x7ffu)) && s_start[i] <= p;
+                        if (cov[u]) { w4[u] = __ldg(wsrc0 + (md >> 11) + tcol); pid[u] = s_pair[i]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { b4[u] = -1; id4[u] = 0; if (!decode(cov[u], w4[u], pid[u], b4[u], id4[u])) b4[u] = -1; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = g0 + u * 32 + lane;
+                    b4[u] = -1; id4[u] = 0;
+                    int b = 0, id = 0;
+                    if (i < ch_ && k3r_candidate(a.rd, glo + i, abs_pos, b, id) && id >= 0 && (int64_t)id < a.n_pairs && ((bases >> b) & 1u)) {
+                        b4[u] = b; id4[u] = id;
+                    }
+                }
+            }
+        };
+        int gb[4], gid[4];                                         // group 0
+        group(cl_, gb, gid);
         int idmin = INT_MAX, idmax = -1;
-        for (int i0 = cl_; i0 < ch_; i0 += 32) {
-            int b = 0, id = 0;
-            if (i0 + lane < ch_ && cand(i0 + lane, b, id)) { idmin = min(idmin, id); idmax = max(idmax, id); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (gb[u] >= 0) { idmin = min(idmin, gid[u]); idmax = max(idmax, gid[u]); }
+        for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {            // deep coverage: further groups
+            int b4[4], id4[4];
+            group(g0, b4, id4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (b4[u] >= 0) { idmin = min(idmin, id4[u]); idmax = max(idmax, id4[u]); }
         }
         idmin = k1f_warp_min(idmin);
         idmax = k1f_warp_max(idmax);
         isb_site_meta m;
-        m.split = isb_site_split(a.splits, a.n_splits, abs_pos);
+        {                                                          // split of the site: walk forward from the tile's
+            int sp = a.tile_split[tile];
+            while (sp + 1 < a.n_splits && (int64_t)__ldg(a.splits + 2 * (sp + 1)) <= abs_pos) ++sp;
+            m.split = (sp >= 0 && abs_pos <= (int64_t)__ldg(a.splits + 2 * sp + 1)) ? sp : -1;
+        }
         m.ev_lo_rel = 0;
         m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
         m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
@@ -560,12 +623,11 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
             // bits of 32 candidates at a time, word by word: ballot the lanes whose pair id falls into the word, OR their
             // bits with REDUX, one lane updates the (warp-private) row word.  A pair seen twice on the site (htslib's
             // overlap quirk) shows up as fewer bits than lanes, or as a bit that is already set: exact slow path below.
-            for (int i0 = cl_; i0 < ch_; i0 += 32) {
-                int b = 0, id = 0;
-                const bool ok = i0 + lane < ch_ && cand(i0 + lane, b, id);
+            auto add32 = [&](int b, int id) {                      // b < 0: this lane has no entry
+                const bool ok = b >= 0;
                 const int w = ok ? (id >> 5) - m.wlo : -1;
                 const uint32_t bit = 1u << (id & 31);
-                const int r = __popc(bases & ((1u << b) - 1u));
+                const int r = ok ? __popc(bases & ((1u << b) - 1u)) : -1;
                 unsigned live = __ballot_sync(ISB_FULL, ok);
                 while (live) {
                     const int src = __ffs((int)live) - 1;
@@ -591,13 +653,29 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                     }
                     __syncwarp();
                 }
+            };
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cl_ + u * 32 < ch_) add32(gb[u], gid[u]);      // warp-uniform condition
+            for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
+                int b4[4], id4[4];
+                group(g0, b4, id4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (g0 + u * 32 < ch_) add32(b4[u], id4[u]);
             }
             if (dup) {                                             // exact path with the multiplicity planes
                 for (int i = lane; i < n_words; i += 32) any[i] = 0u;
                 __syncwarp();
-                for (int i0 = cl_; i0 < ch_; i0 += 32) {
-                    int b = 0, id = 0;
-                    if (i0 + lane < ch_ && cand(i0 + lane, b, id)) k3_row_set(any, m, na, bases, b, id, a.d_err);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (gb[u] >= 0) k3_row_set(any, m, na, bases, gb[u], gid[u], a.d_err);
+                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
+                    int b4[4], id4[4];
+                    group(g0, b4, id4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (b4[u] >= 0) k3_row_set(any, m, na, bases, b4[u], id4[u], a.d_err);
                 }
                 __syncwarp();
             }
@@ -614,7 +692,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
 
 static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
 {
-    size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
+    size_t b = (((size_t)seg_cap * (fuse ? 12 : (m1 ? 8 : 9))) + 15) & ~(size_t)15;
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
     if (fuse)
@@ -623,7 +701,8 @@ static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
 }
 
 // tile bounds + staging capacity of a batch
-static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L, int *seg_cap)
+static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L, int *seg_cap, const int32_t *splits = nullptr,
+                       int n_splits = 0, int32_t **tile_split_out = nullptr)
 {
     cudaStream_t st = ctx->stream;
     if (rd->max_seg_len < 1 || rd->max_seg_len > K1F_MAXLEN)
@@ -634,8 +713,11 @@ static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L
     int rc;
     if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 4 * (size_t)n_tiles))) return rc;
     int64_t *tile_lo = (int64_t *)ctx->buf[SL_RD_BOUNDS].p, *tile_hi = tile_lo + n_tiles;
-    k1f_tile_bounds<<<(n_tiles + 255) / 256, 256, 0, st>>>(rd->seg_start, rd->n_segs, start, n_tiles, rd->max_seg_len, tile_lo, tile_hi);
+    int32_t *tile_split = tile_split_out ? (int32_t *)(tile_hi + n_tiles) : nullptr;
+    k1f_tile_bounds<<<(n_tiles + 255) / 256, 256, 0, st>>>(rd->seg_start, rd->n_segs, start, n_tiles, rd->max_seg_len, tile_lo, tile_hi,
+                                                           splits, n_splits, tile_split);
     ISB_LAUNCH_CHECK();
+    if (tile_split_out) *tile_split_out = tile_split;
     rd->n_tiles = n_tiles;
     rd->tile_lo = tile_lo;
     rd->tile_hi = tile_hi;
@@ -691,7 +773,8 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
     int rc, seg_cap = 0;
     ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), st));
     if (L <= 0) return ISB_OK;
-    if ((rc = k1f_prepare(ctx, rd, start, L, &seg_cap))) return rc;
+    int32_t *tile_split = nullptr;
+    if ((rc = k1f_prepare(ctx, rd, start, L, &seg_cap, ld ? ld->splits : nullptr, ld ? ld->n_splits : 0, ld ? &tile_split : nullptr))) return rc;
     if ((rc = isb_k2_prepare(ctx, fuse->min_freq))) return rc;
     if (nmask) {                                                  // N events only make level 0 a key of MMcounts
         ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
@@ -725,6 +808,7 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         a.n_splits = ld->n_splits; a.splits = ld->splits;
         a.tile_first = (int32_t *)ctx->buf[SL_TILE_SITES].p;
         a.tile_cnt = a.tile_first + n_tiles;
+        a.tile_split = tile_split;
         a.sites_cap = cap;
         a.site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
         a.meta = (isb_site_meta *)ctx->buf[SL_SITE_META].p;

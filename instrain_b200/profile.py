@@ -258,9 +258,11 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
 def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     """Drop-in for inStrain.profile.profile_bam (profile/__init__.py:7-18).  Writes the SNVprofile directory at ISP_loc
-    (instrain_b200/store.py: attributes.tsv, csv.gz tables, covT / clonT .hd5) and returns the ProfileResult, whose
-    `.store` is the on-disk object (same store / get interface as inStrain.SNVprofile.SNVprofile); `.get(name)` serves
-    the in-memory tables."""
+    (instrain_b200/store.py: attributes.tsv, csv.gz tables, covT / clonT .hd5) and returns the on-disk object the
+    reference's ProfileController keeps using as `self.ISP` (`.generate / .get / .store / .get_location`): inStrain's own
+    SNVprofile when importable, else instrain_b200.store.ProfileStore.  The in-memory tables of the run are its `.result`
+    (a ProfileResult; its attributes are also reachable directly on a ProfileStore).  With store=False (or ISP_loc None)
+    the bare ProfileResult is returned."""
     s2s = kwargs.pop("s2s", None)
     report = None
     if s2s is None:
@@ -286,9 +288,28 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
     # the SNVprofile directory at ISP_loc (gen_snv_profile, profile_utilities.py:670-706), written natively:
     # inStrain.SNVprofile.SNVprofile(ISP_loc) of the reference opens it unchanged
-    if ISP_loc is not None and kwargs.get("store", True):
-        from .store import store_profile
-        fdef = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)    # this shim's filter defaults
-        res.store = store_profile(ISP_loc, bam, res, mapping_info=report,
-                                  **{k: kwargs.get(k, v) for k, v in fdef.items()})
-    return res
+    if ISP_loc is None or not kwargs.get("store", True):
+        return res
+    from .store import store_profile
+    fdef = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)    # this shim's filter defaults
+    S = store_profile(ISP_loc, bam, res, mapping_info=report, **{k: kwargs.get(k, v) for k, v in fdef.items()})
+    res.store = S
+    return _as_snvprofile(S, res)
+
+
+def _as_snvprofile(S, res):
+    """The object handed back to ProfileController.run_profile (controller.py:341-350), which goes on to call
+    `.generate(...)`, `.get(...)`, `.store(...)` and `.get_location(...)` on it: the reference's own
+    inStrain.SNVprofile.SNVprofile opened on the directory just written when that class can be imported (it needs h5py),
+    otherwise this package's ProfileStore (same methods, same directory).  Either way the in-memory ProfileResult rides
+    along as `.result`."""
+    if os.environ.get("ISB_NATIVE_STORE", "0") != "1":
+        try:
+            import h5py  # noqa: F401 - the reference's SNVprofile cannot load covT / clonT without it
+            from inStrain.SNVprofile import SNVprofile
+            isp = SNVprofile(S.location)
+            isp.result = res
+            return isp
+        except Exception:                                                # noqa: BLE001 - any import problem: native store
+            pass
+    return S

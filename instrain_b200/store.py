@@ -163,6 +163,16 @@ class SNVprofileStore:
                     f.write("# {0}\n".format(" ".join("{0}:{1}".format(k, v) for k, v in values.items())))
                     db.to_csv(f, index=False, sep="\t")
             return db if return_table else None
+        if name == "gene_info":                                          # SNVprofile.py:247-257: nothing to write without a gene file
+            if self.get("genes_table") is None:
+                logging.info("Cannot generate genes_table, no genes were profiled")
+            else:                                                         # GeneProfile (out of this path's scope) stored one
+                logging.info("gene_info is written by inStrain's own SNVprofile.generate; open this directory with it")
+            return None
+        if name == "genome_info":                                        # produced by genomeUtilities, downstream of the path
+            if self.get("genome_level_info") is None:
+                logging.info("Cannot generate genome_info, no genome-level profile was stored")
+            return None
         if name not in self._OUTPUTS:
             raise KeyError("generate(%r): only %s come out of the profile hot path" % (name, sorted(self._OUTPUTS) + ["mapping_info"]))
         source, subset, order = self._OUTPUTS[name]
@@ -211,11 +221,28 @@ class SNVprofileStore:
         Adb.to_csv(self._attributes_loc(), sep="\t", index_label="name")
 
 
+class ProfileStore(SNVprofileStore):
+    """What profile_bam returns when inStrain's own SNVprofile class is not importable: the on-disk object (store / get /
+    generate / get_location, the interface ProfileController uses on `self.ISP`, controller.py:341-360) with the run's
+    in-memory ProfileResult attached; attribute names the store does not have (scaffold_list, raw_snp_table, scaffolds,
+    failures, timing ...) are answered by that result."""
+
+    def __init__(self, location, result=None):
+        super().__init__(location)
+        self.result = result
+
+    def __getattr__(self, name):                                        # only called when normal lookup fails
+        res = self.__dict__.get("result")
+        if res is not None and not name.startswith("__") and hasattr(res, name):
+            return getattr(res, name)
+        raise AttributeError(name)
+
+
 def store_profile(ISP_loc, bam, res, mapping_info=None, **kwargs):
     """What gen_snv_profile stores for a profile run (profile_utilities.py:670-706), from a ProfileResult; plus the read
     filter's report when profile_bam ran the filter itself (ProfileController.load_paired_reads stores it,
     controller.py:301-304).  kwargs: the filter settings for the header of output/*_mapping_info.tsv."""
-    S = SNVprofileStore(ISP_loc)
+    S = ProfileStore(ISP_loc, res)
     if mapping_info is not None:
         S.store("mapping_info", mapping_info, "pandas", "Report on reads")
     S.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
