@@ -447,7 +447,11 @@ int isb_bam_n_refs(void *bam);
 const char *isb_bam_ref_name(void *bam, int tid);
 int64_t isb_bam_ref_len(void *bam, int tid);
 const char *isb_bam_error(void *bam);
-int isb_bam_peek_tid(void *bam);                           /* next record's tid; -1 unmapped tail; -2 end of file */
+/* next record's tid; -1 unmapped tail; -2 clean end of file; -3 read error: a corrupt or truncated file (bad BGZF block,
+ * CRC mismatch, record cut short, missing BGZF end-of-file block) -- pysam / htslib raise there, so must the caller
+ * (isb_bam_error has the reason).  isb_pack_scaffold* return NULL and isb_filter_open returns NULL in that case. */
+int isb_bam_peek_tid(void *bam);
+const char *isb_host_last_error(void);                     /* reason of the last failed isb_filter_open on this thread */
 /* Reposition at a BGZF virtual offset taken from the BAM's .bai index (first alignment of a scaffold): several readers of
  * one BAM, one per host thread, can then pack different scaffolds concurrently.  0 on success. */
 int isb_bam_seek(void *bam, uint64_t voffset);

@@ -37,6 +37,8 @@ struct Bam {
     std::vector<uint8_t> buf;     // decompressed bytes not yet consumed
     size_t off = 0;
     bool eof = false;
+    bool saw_eof_marker = false;  // the last block read was BGZF's empty end-of-file block
+    bool bad = false;             // a block or record could not be read completely: `err` says why
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     char err[256] = "";
@@ -51,44 +53,69 @@ struct Events {
     int64_t n_reads_seen = 0, n_reads_packed = 0;
 };
 
+static bool bam_fail(Bam *b, const char *msg)
+{
+    if (!b->err[0]) snprintf(b->err, sizeof(b->err), "%s", msg);
+    b->bad = true;
+    b->eof = true;
+    return false;
+}
+
 bool read_block(Bam *b)
 {
     uint8_t h[18];
     size_t got = fread(h, 1, 18, b->fp);
-    if (got == 0) { b->eof = true; return false; }
-    if (got != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
-        snprintf(b->err, sizeof(b->err), "not a BGZF block");
+    if (got == 0) {                                // end of the file: htslib expects the empty BGZF block right before it
         b->eof = true;
+        if (!b->saw_eof_marker && !getenv("ISB_ALLOW_NO_BGZF_EOF"))
+            return bam_fail(b, "no BGZF end-of-file block: the BAM is truncated (set ISB_ALLOW_NO_BGZF_EOF=1 to read it anyway)");
         return false;
     }
+    if (got != 18) return bam_fail(b, "truncated BGZF block header");
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return bam_fail(b, "not a BGZF block (corrupt file?)");
     const int xlen = h[10] | (h[11] << 8);
+    if (xlen < 6) return bam_fail(b, "BGZF block without BC field");
     std::vector<uint8_t> extra(xlen);
-    memcpy(extra.data(), h + 12, xlen < 6 ? xlen : 6);
-    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, b->fp) != (size_t)(xlen - 6)) { b->eof = true; return false; }
+    memcpy(extra.data(), h + 12, 6);
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, b->fp) != (size_t)(xlen - 6)) return bam_fail(b, "truncated BGZF block header");
     int bsize = -1;
     for (int i = 0; i + 4 <= xlen;) {
         const int slen = extra[i + 2] | (extra[i + 3] << 8);
-        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = extra[i + 4] | (extra[i + 5] << 8);
         i += 4 + slen;
     }
-    if (bsize < 0) { snprintf(b->err, sizeof(b->err), "BGZF block without BC field"); b->eof = true; return false; }
+    if (bsize < 0) return bam_fail(b, "BGZF block without BC field");
     const int clen = bsize - xlen - 19;           // compressed payload
+    if (clen < 0) return bam_fail(b, "corrupt BGZF block size");
     std::vector<uint8_t> comp(clen + 8);
-    if (fread(comp.data(), 1, clen + 8, b->fp) != (size_t)(clen + 8)) { b->eof = true; return false; }
+    if (fread(comp.data(), 1, clen + 8, b->fp) != (size_t)(clen + 8)) return bam_fail(b, "truncated BGZF block");
     const uint32_t isize = comp[clen + 4] | (comp[clen + 5] << 8) | (comp[clen + 6] << 16) | ((uint32_t)comp[clen + 7] << 24);
+    b->saw_eof_marker = isize == 0;
     if (isize == 0) return true;                  // empty block (EOF marker)
+    if (isize > (1u << 16)) return bam_fail(b, "corrupt BGZF block (uncompressed size > 64 KiB)");
     // compact the buffer before appending
     if (b->off > (1u << 20)) { b->buf.erase(b->buf.begin(), b->buf.begin() + b->off); b->off = 0; }
     const size_t old = b->buf.size();
     b->buf.resize(old + isize);
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) { b->eof = true; return false; }
+    if (inflateInit2(&zs, -15) != Z_OK) return bam_fail(b, "inflateInit2 failed");
     zs.next_in = comp.data(); zs.avail_in = clen;
     zs.next_out = b->buf.data() + old; zs.avail_out = isize;
     const int rc = inflate(&zs, Z_FINISH);
+    const bool full = zs.avail_out == 0;
     inflateEnd(&zs);
-    if (rc != Z_STREAM_END) { snprintf(b->err, sizeof(b->err), "inflate failed (%d)", rc); b->eof = true; return false; }
+    if (rc != Z_STREAM_END || !full) {
+        b->buf.resize(old);
+        char msg[96];
+        snprintf(msg, sizeof(msg), "inflate failed (%d): corrupt BGZF block", rc);
+        return bam_fail(b, msg);
+    }
+    const uint32_t crc_stored = comp[clen] | (comp[clen + 1] << 8) | (comp[clen + 2] << 16) | ((uint32_t)comp[clen + 3] << 24);
+    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), b->buf.data() + old, isize) != crc_stored) {
+        b->buf.resize(old);
+        return bam_fail(b, "BGZF block CRC mismatch: corrupt file");
+    }
     return true;
 }
 
@@ -254,6 +281,9 @@ int isb_bam_seek(void *h, uint64_t voffset)
     b->buf.clear();
     b->off = 0;
     b->eof = false;
+    b->bad = false;
+    b->err[0] = 0;
+    b->saw_eof_marker = false;
     b->has_pending = false;
     b->pending.clear();
     const size_t u = (size_t)(voffset & 0xffff);
@@ -269,15 +299,31 @@ const char *isb_bam_ref_name(void *h, int tid) { return ((Bam *)h)->ref_names[ti
 int64_t isb_bam_ref_len(void *h, int tid) { return ((Bam *)h)->ref_lens[tid]; }
 const char *isb_bam_error(void *h) { return ((Bam *)h)->err; }
 
-// tid of the next alignment record in the (coordinate-sorted) file: >= 0, -1 = unmapped tail, -2 = end of file
+// tid of the next alignment record in the (coordinate-sorted) file: >= 0, -1 = unmapped tail, -2 = clean end of file,
+// -3 = read error (corrupt or truncated file; isb_bam_error has the reason -- pysam / htslib raise in this case)
 int isb_bam_peek_tid(void *h)
 {
     Bam *b = (Bam *)h;
+    if (b->bad) return -3;
     if (!b->has_pending) {
         int32_t block_size = 0;
-        if (!read_exact(b, &block_size, 4)) return -2;
+        if (!read_exact(b, &block_size, 4)) {
+            if (b->bad) return -3;
+            if (b->buf.size() != b->off) { bam_fail(b, "truncated alignment record"); return -3; }
+            return -2;
+        }
+        if (block_size < 32 || block_size > (1 << 28)) { bam_fail(b, "corrupt alignment record (block_size)"); return -3; }
         b->pending.resize(block_size);
-        if (!read_exact(b, b->pending.data(), block_size)) return -2;
+        if (!read_exact(b, b->pending.data(), block_size)) { bam_fail(b, "truncated alignment record"); return -3; }
+        int32_t core[8];
+        memcpy(core, b->pending.data(), 32);
+        const int l_read_name = (uint32_t)core[2] & 0xff;
+        const int64_t n_cig = (uint32_t)core[3] & 0xffff, l_seq = core[4];
+        if (core[0] >= (int32_t)b->ref_names.size() || l_seq < 0 ||
+            32 + l_read_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq > (int64_t)block_size) {
+            bam_fail(b, "corrupt alignment record (field sizes)");
+            return -3;
+        }
         b->has_pending = true;
     }
     int32_t tid;
@@ -363,6 +409,7 @@ void *isb_pack_scaffold(void *h, int tid, int64_t n_names, const char *names_blo
     Bam *b = (Bam *)h;
     Loaded ld;
     load_scaffold(b, tid, n_names, names_blob, name_off, ld);
+    if (b->bad) return nullptr;                                   // corrupt / truncated BAM: isb_bam_error() has the reason
     std::vector<BamRec> &recs = ld.recs;
     std::vector<uint32_t> &cigs = ld.cigs;
     std::vector<uint8_t> &seq = ld.seq, &qual = ld.qual;
@@ -455,6 +502,7 @@ void *isb_pack_scaffold_reads(void *h, int tid, int64_t n_names, const char *nam
     Bam *b = (Bam *)h;
     Loaded ld;
     load_scaffold(b, tid, n_names, names_blob, name_off, ld);
+    if (b->bad) return nullptr;                                   // corrupt / truncated BAM: isb_bam_error() has the reason
     ReadsOut *out = new ReadsOut();
     out->n_reads_seen = ld.n_reads_seen;
     const int64_t L = tid >= 0 && tid < (int)b->ref_lens.size() ? b->ref_lens[tid] : 0;
@@ -614,11 +662,15 @@ int nm_tag(const uint8_t *p, const uint8_t *end)
 
 extern "C" {
 
-// Pass over the whole BAM; returns a filter handle (NULL on failure).
+static thread_local char g_host_err[320] = "";
+const char *isb_host_last_error(void) { return g_host_err; }
+
+// Pass over the whole BAM; returns a filter handle (NULL on failure: isb_host_last_error() says why).
 void *isb_filter_open(const char *bam_path)
 {
+    g_host_err[0] = 0;
     Bam *b = (Bam *)isb_bam_open(bam_path);
-    if (!b) return nullptr;
+    if (!b) { snprintf(g_host_err, sizeof(g_host_err), "cannot open BAM %s", bam_path); return nullptr; }
     Filter *f = new Filter();
     f->ref_names = b->ref_names;
     f->sc.resize(b->ref_names.size());
@@ -668,6 +720,12 @@ void *isb_filter_open(const char *bam_path)
             else pi.insert = -1;
             pi.first = pi.last = 0;
         }
+    }
+    if (b->bad) {                                                 // a partial pass must not look like a complete one
+        snprintf(g_host_err, sizeof(g_host_err), "%s: %s", bam_path, b->err);
+        isb_bam_close(b);
+        delete f;
+        return nullptr;
     }
     isb_bam_close(b);
     return f;

@@ -46,6 +46,7 @@
 #define K1F_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
 #define K1F_STAGE_IT 9                 // segment-table elements per thread per chunk: seg_cap <= 9 * 128
 #define K1F_TILE4 (256 + 32)           // count quads of a warp's 256 positions + one pad quad per 8 positions
+#define K1F_CODE_IDS 1024              // pair-id window (ids) of a site the ballot row builder handles; wider ones: atomics
 #ifndef K1F_MINB
 #define K1F_MINB 5                     // __launch_bounds__ min blocks per SM of the fused kernel (<= 102 registers)
 #endif
@@ -111,6 +112,12 @@ __device__ __forceinline__ int k1f_warp_max(int v)
 {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(ISB_FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ int k1f_warp_sum(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ISB_FULL, v, d);
     return v;
 }
 __device__ __forceinline__ int k1f_warp_min(int v)
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: sites per warp, offsets, slot base
     uint16_t *s_site = reinterpret_cast<uint16_t *>(s_misc + 16);         // [K1F_WARPS][256]: position in the warp | bases << 8
     uint8_t *s_q = reinterpret_cast<uint8_t *>(s_site + K1F_WARPS * 256); // [K1F_WARPS][256]: positions for the general path
+    uint8_t *s_code = s_q + K1F_WARPS * 256;                              // [K1F_WARPS][K1F_CODE_IDS]: pair id -> allele code of a site
 
     const int t = threadIdx.x;
     const int lane = t & 31, wib = t >> 5;
@@ -215,6 +223,15 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     int64_t wb = 0;                                               // word base of the (last) chunk
     const int P_end = t * 8 + 256;
 
+    // The words of the tile are one contiguous piece of the stream: ask the TMA engine to pull it into L2 now, while the
+    // block stages its segment table -- the main loop's loads then find L2 hits (~300 cycles) instead of HBM (~1 us).
+    if (t == 0 && hi > lo) {
+        const int64_t w_first = __ldg(a.rd.seg_word + lo), w_last = __ldg(a.rd.seg_word + hi - 1) + (K1F_MAXLEN / 8 + 2);
+        const int64_t b0 = max((int64_t)0, w_first - 1) & ~(int64_t)3;
+        const int64_t b1 = min(a.rd.n_words, w_last) & ~(int64_t)3;
+        if (b1 > b0 && b1 - b0 < (1 << 24))
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rd.words + b0), "r"((unsigned)((b1 - b0) * 4)) : "memory");
+    }
     for (int64_t c0 = lo; c0 < hi; c0 += a.seg_cap) {
         const int nc = (int)min((int64_t)a.seg_cap, hi - c0);
         __syncthreads();                                          // previous chunk consumed
@@ -234,6 +251,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 const int i = t + k * K1F_THREADS;
                 const int64_t g = c0 + i;
                 r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1; r_pid[k] = 0;
+                if (k * K1F_THREADS >= nc) break;                  // block-uniform
                 if (i < nc) {
                     r_s[k] = __ldg(a.rd.seg_start + g);
                     r_n[k] = __ldg(a.rd.seg_len + g);
@@ -615,73 +633,82 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         }
         bool dup = false;
         if (m.nw > 0) {
-            const bool in_smem = n_words <= ISB_K3_ROW_SLOT;
             uint32_t *g_any = a.rows + off;
-            uint32_t *any = in_smem ? s_rows + wib * ISB_K3_ROW_SLOT : g_any;
-            for (int i = lane; i < n_words; i += 32) any[i] = 0u;
-            __syncwarp();
-            // bits of 32 candidates at a time, word by word: ballot the lanes whose pair id falls into the word, OR their
-            // bits with REDUX, one lane updates the (warp-private) row word.  A pair seen twice on the site (htslib's
-            // overlap quirk) shows up as fewer bits than lanes, or as a bit that is already set: exact slow path below.
-            auto add32 = [&](int b, int id) {                      // b < 0: this lane has no entry
-                const bool ok = b >= 0;
-                const int w = ok ? (id >> 5) - m.wlo : -1;
-                const uint32_t bit = 1u << (id & 31);
-                const int r = ok ? __popc(bases & ((1u << b) - 1u)) : -1;
-                unsigned live = __ballot_sync(ISB_FULL, ok);
-                while (live) {
-                    const int src = __ffs((int)live) - 1;
-                    const int wv = __shfl_sync(ISB_FULL, w, src);
-                    const bool mine = ok && w == wv;
-                    const unsigned m_any = __ballot_sync(ISB_FULL, mine);
-                    live &= ~m_any;
-                    uint32_t bits_any = 0u;
-                    if (mine) bits_any = __reduce_or_sync(m_any, bit);
-                    bits_any = __shfl_sync(ISB_FULL, bits_any, src);
-                    const uint32_t old = any[wv];
-                    if (__popc(m_any) != __popc(bits_any) || (old & bits_any)) dup = true;
-                    __syncwarp();
-                    if (lane == 0) any[wv] = old | bits_any;
-                    for (int rr = 0; rr < na; ++rr) {
-                        const bool mr = mine && r == rr;
-                        const unsigned m_r = __ballot_sync(ISB_FULL, mr);
-                        if (!m_r) continue;
-                        uint32_t bits = 0u;
-                        if (mr) bits = __reduce_or_sync(m_r, bit);
-                        bits = __shfl_sync(ISB_FULL, bits, __ffs((int)m_r) - 1);
-                        if (lane == 0) any[(size_t)(1 + rr) * m.nw + wv] |= bits;
-                    }
-                    __syncwarp();
-                }
-            };
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (cl_ + u * 32 < ch_) add32(gb[u], gid[u]);      // warp-uniform condition
-            for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
-                int b4[4], id4[4];
-                group(g0, b4, id4);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (g0 + u * 32 < ch_) add32(b4[u], id4[u]);
-            }
-            if (dup) {                                             // exact path with the multiplicity planes
-                for (int i = lane; i < n_words; i += 32) any[i] = 0u;
+            auto slow_rows = [&]() {                               // exact path with the multiplicity planes (atomics)
+                for (int i = lane; i < n_words; i += 32) g_any[i] = 0u;
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (gb[u] >= 0) k3_row_set(any, m, na, bases, gb[u], gid[u], a.d_err);
+                    if (gb[u] >= 0) k3_row_set(g_any, m, na, bases, gb[u], gid[u], a.d_err);
                 for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
                     int b4[4], id4[4];
                     group(g0, b4, id4);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (b4[u] >= 0) k3_row_set(any, m, na, bases, b4[u], id4[u], a.d_err);
+                        if (b4[u] >= 0) k3_row_set(g_any, m, na, bases, b4[u], id4[u], a.d_err);
                 }
                 __syncwarp();
-            }
-            if (in_smem) {
-                for (int i = lane; i < n_words; i += 32) g_any[i] = any[i];
+            };
+            if (m.nw * 32 <= K1F_CODE_IDS) {
+                // Bit rows by BALLOT.  The site's entries are scattered into a byte map "pair id -> allele code" (ids are
+                // distinct unless a pair entered the site twice: plain stores); then lane l owns bit l of every row word:
+                // word w of the `any` row is ballot(code[32 w + l] != 0), word w of allele row r is ballot(code == r's
+                // base).  ~20 instructions per row word instead of a REDUX / shuffle round per (word, allele) and 32
+                // candidates.  A pair seen twice (htslib's overlap quirk) shows up as fewer set bits than entries: then the
+                // exact slow path rebuilds the rows with the multiplicity planes.
+                uint8_t *code = s_code + wib * K1F_CODE_IDS;
+                uint32_t *code4 = reinterpret_cast<uint32_t *>(code);
+                for (int i = lane; i < m.nw * 8; i += 32) code4[i] = 0u;
                 __syncwarp();
+                const int id0 = m.wlo << 5;
+                int n_ent = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (gb[u] >= 0) { code[gid[u] - id0] = (uint8_t)(gb[u] + 1); ++n_ent; }
+                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
+                    int b4[4], id4[4];
+                    group(g0, b4, id4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (b4[u] >= 0) { code[id4[u] - id0] = (uint8_t)(b4[u] + 1); ++n_ent; }
+                }
+                __syncwarp();
+                int b_of[4] = {0, 0, 0, 0};                        // base (+ 1) of allele row r
+                {
+                    int r = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((bases >> b) & 1u) b_of[r++] = b + 1;
+                }
+                int n_bits = 0;
+                for (int w = 0; w < m.nw; ++w) {
+                    const int c = code[w * 32 + lane];
+                    const unsigned any_w = __ballot_sync(ISB_FULL, c != 0);
+                    unsigned row_w[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) row_w[r] = __ballot_sync(ISB_FULL, c != 0 && c == b_of[r]);
+                    n_bits += __popc(any_w);
+                    if (lane == 0) g_any[w] = any_w;
+                    if (lane >= 1 && lane <= na) g_any[(size_t)lane * m.nw + w] = row_w[lane - 1 < 4 ? lane - 1 : 3];
+                    if (lane > na && lane <= 2 * na) g_any[(size_t)lane * m.nw + w] = 0u;     // multiplicity planes: empty
+                }
+                n_ent = k1f_warp_sum(n_ent);
+                dup = n_bits != n_ent;
+                if (dup) slow_rows();
+            } else {
+                slow_rows();
+                // a pair with two entries sets a bit of `any` that is already set: detect it by counting
+                int n_ent = 0, n_bits = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) n_ent += gb[u] >= 0;
+                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
+                    int b4[4], id4[4];
+                    group(g0, b4, id4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) n_ent += b4[u] >= 0;
+                }
+                for (int i = lane; i < m.nw; i += 32) n_bits += __popc(g_any[i]);
+                dup = k1f_warp_sum(n_bits) != k1f_warp_sum(n_ent);
             }
         }
         if (lane == 0) a.has2[slot] = dup ? 1 : 0;
@@ -696,7 +723,8 @@ static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
     if (fuse)
-        b += 4 * K1F_WARPS * ISB_K3_ROW_SLOT + 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256;
+        b += 4 * K1F_WARPS * ISB_K3_ROW_SLOT + 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 +
+             K1F_WARPS * K1F_CODE_IDS;
     return b;
 }
 

@@ -80,8 +80,29 @@ class BamPacker:
             raise IOError("isb_bam_seek failed")
 
     def peek_tid(self):
-        """tid of the next record: >= 0; -1 unmapped tail; -2 end of file."""
-        return int(self.lib.isb_bam_peek_tid(self.h))
+        """tid of the next record: >= 0; -1 unmapped tail; -2 end of file.  A corrupt or truncated BAM (the C side's -3)
+        raises IOError, as pysam / htslib do: a partial pass must never look like a complete one."""
+        t = int(self.lib.isb_bam_peek_tid(self.h))
+        if t == -3:
+            raise IOError("error reading BAM: " + self.lib.isb_bam_error(self.h).decode())
+        return t
+
+    @staticmethod
+    def _mm_levels(values):
+        """R2M values -> uint8 levels.  The reference keys its tables by any mm (dicts); the device keeps M <= ISB_MAX_MM
+        dense levels, so mismatch counts beyond the last level are folded into it (with a warning): such pairs -- summed
+        NM >= 64 on a read pair -- keep being counted instead of aborting the run."""
+        mm = np.asarray(values, dtype=np.int64)
+        if len(mm) and mm.min() < 0:
+            raise ValueError("R2M mismatch count < 0")
+        top = _cabi.ISB_MAX_MM - 1
+        n_over = int((mm > top).sum()) if len(mm) else 0
+        if n_over:
+            import logging
+            logging.warning("instrain_b200: %d read pairs with more than %d mismatches are profiled at mm level %d",
+                            n_over, top, top)
+            mm = np.minimum(mm, top)
+        return mm.astype(np.uint8)
 
     @staticmethod
     def _names(r2m):
@@ -91,10 +112,7 @@ class BamPacker:
         if enc:
             off[1:] = np.cumsum([len(b) for b in enc])
         if isinstance(r2m, dict):
-            mm = np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names))
-            if len(mm) and (mm.min() < 0 or mm.max() >= _cabi.ISB_MAX_MM):
-                raise ValueError("R2M mismatch count outside [0, %d)" % _cabi.ISB_MAX_MM)
-            mm = mm.astype(np.uint8)
+            mm = BamPacker._mm_levels(np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names)))
         else:
             mm = np.zeros(len(names), dtype=np.uint8)
         return len(names), b"".join(enc), off, mm
@@ -132,10 +150,7 @@ class BamPacker:
             off[1:] = np.cumsum([len(b) for b in enc])
         blob = b"".join(enc)
         if isinstance(r2m, dict):
-            mm = np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names))
-            if len(mm) and (mm.min() < 0 or mm.max() >= _cabi.ISB_MAX_MM):
-                raise ValueError("R2M mismatch count outside [0, %d)" % _cabi.ISB_MAX_MM)
-            mm = mm.astype(np.uint8)
+            mm = BamPacker._mm_levels(np.fromiter((r2m[k] for k in names), dtype=np.int64, count=len(names)))
         else:
             mm = np.zeros(len(names), dtype=np.uint8)
         e = self.lib.isb_pack_scaffold(self.h, tid, len(names), blob, off.ctypes.data, mm.ctypes.data, pos_offset,

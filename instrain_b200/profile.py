@@ -61,16 +61,45 @@ class ProfileResult:
         return getattr(self, name)
 
 
+class _SplitTable:
+    """Split table per scaffold: from the reference's Fdb (fasta.py:30-52) when given -- grouped ONCE (a filter per
+    scaffold is quadratic in the number of scaffolds, and a metagenome assembly has 1e5 .. 1e6 of them) -- else the same
+    geometry computed from the length."""
+
+    def __init__(self, Fdb, window_length):
+        self.window_length = window_length
+        self.by_scaffold = None
+        if Fdb is not None:
+            db = Fdb.sort_values(["scaffold", "start"], kind="stable")
+            names = db["scaffold"].values
+            starts, ends = db["start"].values.astype(np.int64), db["end"].values.astype(np.int64)
+            cut = np.nonzero(names[1:] != names[:-1])[0] + 1 if len(names) else np.zeros(0, np.int64)
+            lo = np.concatenate([[0], cut]).astype(np.int64)
+            hi = np.concatenate([cut, [len(names)]]).astype(np.int64)
+            self.by_scaffold = {names[a]: (starts[a:b], ends[a:b]) for a, b in zip(lo, hi) if b > a}
+
+    def __call__(self, scaffold, length):
+        if self.by_scaffold is not None:
+            st, en = self.by_scaffold.get(scaffold, ((), ()))
+            return [(int(a), int(b)) for a, b in zip(st, en)]
+        return iterate_splits(length, self.window_length)
+
+
 def _fdb_splits(Fdb, scaffold, length, window_length):
-    """Split table of one scaffold: from the reference's Fdb (fasta.py:30-52) when given, else the same geometry."""
-    if Fdb is not None:
-        db = Fdb[Fdb["scaffold"] == scaffold].sort_values("start")
-        return [(int(s), int(e)) for s, e in zip(db["start"], db["end"])]
-    return iterate_splits(length, window_length)
+    """Split table of one scaffold (one-off lookups; the batch stream uses _SplitTable)."""
+    return _SplitTable(Fdb if Fdb is None else Fdb[Fdb["scaffold"] == scaffold], window_length)(scaffold, length)
+
+
+def _r2m_levels(r2m):
+    """mm levels a scaffold's R2M needs on the device (1 in set mode)."""
+    if isinstance(r2m, dict) and r2m:
+        return min(int(max(r2m.values())), 63) + 1
+    return 1
 
 
 def _new_batch():
-    return dict(names=[], off=[], ref=[], splits=[], parts=[], pair_mm=[], n_events=0, L=0, n_pairs=0)
+    return dict(names=[], off=[], ref=[], splits=[], n_splits=[], parts=[], pair_mm=[], pair_off=[], n_events=0, L=0,
+                n_pairs=0, M=1)
 
 
 def _add_to_batch(batch, name, seq, ev, splits):
@@ -78,16 +107,55 @@ def _add_to_batch(batch, name, seq, ev, splits):
     L = len(seq)
     batch["names"].append(name)
     batch["off"].append(batch["L"])
+    batch["pair_off"].append(batch["n_pairs"])
     batch["ref"].append(encode_reference(seq))
     batch["splits"].extend((s + batch["L"], e + batch["L"]) for s, e in splits)
+    batch["n_splits"].append(len(splits))
     batch["parts"].append(ev)
     batch["pair_mm"].append(ev["pair_mm"])
     batch["n_events"] += ev["n_events"]
     batch["L"] += L
     batch["n_pairs"] += len(ev["pair_mm"])
+    if len(ev["pair_mm"]):
+        batch["M"] = max(batch["M"], int(ev["pair_mm"].max()) + 1)
 
 
-def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events=400_000_000, packer_threads=1, debug=False):
+def _sub_batch(batch, i0, i1):
+    """Scaffolds [i0, i1) of a batch as a batch of their own (coordinates, pair ids and splits re-based to 0): what a
+    failed batch is bisected into, so that one bad scaffold does not take its neighbours down."""
+    sub = _new_batch()
+    d_pos, d_pair = batch["off"][i0], batch["pair_off"][i0]
+    s0 = sum(batch["n_splits"][:i0])
+    for k in range(i0, i1):
+        ev = dict(batch["parts"][k])
+        for key, d in (("seg_start", d_pos), ("nev_pos", d_pos), ("seg_pair", d_pair), ("nev_pair", d_pair)):
+            ev[key] = ev[key] - np.int32(d) if d else ev[key]
+        n_sp = batch["n_splits"][k]
+        splits = [(s - batch["off"][k], e - batch["off"][k]) for s, e in batch["splits"][s0:s0 + n_sp]]
+        s0 += n_sp
+        sub["names"].append(batch["names"][k])
+        sub["off"].append(sub["L"])
+        sub["pair_off"].append(sub["n_pairs"])
+        sub["ref"].append(batch["ref"][k])
+        sub["splits"].extend((s + sub["L"], e + sub["L"]) for s, e in splits)
+        sub["n_splits"].append(n_sp)
+        sub["parts"].append(ev)
+        sub["pair_mm"].append(ev["pair_mm"])
+        sub["n_events"] += ev["n_events"]
+        sub["L"] += len(batch["ref"][k])
+        sub["n_pairs"] += len(ev["pair_mm"])
+        if len(ev["pair_mm"]):
+            sub["M"] = max(sub["M"], int(ev["pair_mm"].max()) + 1)
+    return sub
+
+
+# Dense per-position outputs cost 24 bytes per (position, mm level) on the device (counts + covT + clonT, isb_api.cu) and
+# 8 on the host; a batch is closed before L * M exceeds this many cells (8e8 cells = 19 GB of HBM, 6.4 GB of host memory)
+MAX_BATCH_CELLS = 800_000_000
+
+
+def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events=400_000_000, packer_threads=1, debug=False,
+                 max_batch_cells=MAX_BATCH_CELLS):
     """Stream the BAM through the host packer and yield ("batch", batch dict) for every batch of scaffolds (one int32
     coordinate space each) and ("failure", scaffold) for the reference's fault-injection scaffold
     (profile_utilities.py:137-139, test_profile_17).
@@ -96,6 +164,13 @@ def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events
     packer_threads > 1 : scaffolds are packed concurrently by that many host threads, each seeking through the .bai
     index (instrain_b200.packer.pack_scaffolds_parallel); batches are planned up front from the scaffold lengths and the
     R2M sizes (300 aligned bases assumed per read pair).  Both give the same batches whenever everything fits one."""
+    split_table = _SplitTable(Fdb, window_length)
+
+    def full(b_L, b_M, b_events, L, M):
+        """Would adding a scaffold of L positions / M levels overflow the coordinate space, the event or the cell budget?"""
+        return b_events > 0 and (b_L + L >= 2 ** 31 - 1 or b_events > max_batch_events or
+                                 (b_L + L) * max(b_M, M) > max_batch_cells)
+
     if packer_threads <= 1:
         batch = _new_batch()
         with BamPacker(bam) as bp:
@@ -112,11 +187,11 @@ def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events
                     yield "failure", name
                     continue
                 L = len(s2s[name])
-                if batch["n_events"] and (batch["L"] + L >= 2 ** 31 - 1 or batch["n_events"] > max_batch_events):
+                if full(batch["L"], batch["M"], batch["n_events"], L, _r2m_levels(sR2M[name])):
                     yield "batch", batch
                     batch = _new_batch()
                 ev = bp.pack_scaffold_reads(tid, sR2M[name], pos_offset=batch["L"], pair_id_offset=batch["n_pairs"])
-                _add_to_batch(batch, name, s2s[name], ev, _fdb_splits(Fdb, name, L, window_length))
+                _add_to_batch(batch, name, s2s[name], ev, split_table(name, L))
         if batch["names"]:
             yield "batch", batch
         return
@@ -127,7 +202,7 @@ def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events
     bai = find_bai(bam)
     first = read_bai(bai) if bai is not None else scan_scaffold_offsets(bam)
     # plan: scaffolds in file (= tid) order, batch index and position offset of each
-    plan, b_idx, b_L, b_est = [], 0, 0, 0
+    plan, b_idx, b_L, b_est, b_M = [], 0, 0, 0, 1
     for tid, name in enumerate(ref_names):
         if first[tid] is None or name not in sR2M or name not in s2s:
             continue
@@ -135,10 +210,12 @@ def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events
             plan.append((tid, name, None, None))
             continue
         L = len(s2s[name])
-        if b_est and (b_L + L >= 2 ** 31 - 1 or b_est > max_batch_events):
-            b_idx, b_L, b_est = b_idx + 1, 0, 0
+        M_sc = _r2m_levels(sR2M[name])
+        if full(b_L, b_M, b_est, L, M_sc):
+            b_idx, b_L, b_est, b_M = b_idx + 1, 0, 0, 1
         plan.append((tid, name, b_idx, b_L))
         b_L += L
+        b_M = max(b_M, M_sc)
         b_est += 300 * len(sR2M[name])
     jobs = [(tid, sR2M[name], off) for tid, name, bi, off in plan if bi is not None]
     packed = pack_scaffolds_parallel(bam, jobs, packer_threads)
@@ -156,7 +233,7 @@ def iter_batches(bam, sR2M, s2s, Fdb=None, window_length=10000, max_batch_events
         if batch["n_pairs"]:                                                   # pair ids were numbered from 0 per scaffold
             ev["seg_pair"] = ev["seg_pair"] + np.int32(batch["n_pairs"])
             ev["nev_pair"] = ev["nev_pair"] + np.int32(batch["n_pairs"])
-        _add_to_batch(batch, name, s2s[name], ev, _fdb_splits(Fdb, name, len(s2s[name]), window_length))
+        _add_to_batch(batch, name, s2s[name], ev, split_table(name, len(s2s[name])))
     if batch["names"]:
         yield "batch", batch
 
@@ -191,11 +268,20 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         try:
             _flush(batch)
         except Exception as e:                                            # noqa: BLE001 - mirror of the reference's catch-all
+            # The reference loses ONE split to an exception (SplitException, profile_utilities.py:104-111).  A batch holds
+            # many scaffolds, so a failing batch is bisected until the offending scaffold stands alone: an input outside
+            # the device envelope (ISB_ERR_UNSUPPORTED), an out-of-memory condition or a bad scaffold costs that
+            # scaffold only.
+            n = len(batch["names"])
+            if n > 1:
+                logging.warning("instrain_b200: batch of %d scaffolds failed (%s); retrying in halves", n, e)
+                flush(_sub_batch(batch, 0, n // 2))
+                flush(_sub_batch(batch, n // 2, n))
+                return
             t = time.strftime("%m-%d %H:%M")
-            for name in batch["names"]:
-                msg = "\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(name, t, 0)
-                logging.error(msg + str(e))
-                res.failures.append(name)
+            msg = "\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(batch["names"][0], t, 0)
+            logging.error(msg + str(e))
+            res.failures.append(batch["names"][0])
 
     def _flush(batch):
         cat = np.concatenate
@@ -222,7 +308,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
         sum_tabs.append(summary.summary_table(k4, out["snv"], batch["names"], offs, out["M"]))
         seqs = {n: s2s[n] for n in batch["names"]}
-        snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs))
+        snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs, ref_codes=ref_codes))
         ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
         for name, off in zip(batch["names"], offs):
             sp = ScaffoldProfile(name, len(s2s[name]))
@@ -235,7 +321,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
     for kind, payload in iter_batches(bam, sR2M, s2s, Fdb=Fdb, window_length=window_length,
                                       max_batch_events=max_batch_events, packer_threads=int(kwargs.get("packer_threads", 1) or 1),
-                                      debug=kwargs.get("debug", False)):
+                                      debug=kwargs.get("debug", False),
+                                      max_batch_cells=int(kwargs.get("max_batch_cells", MAX_BATCH_CELLS))):
         if kind == "failure":
             logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(payload, time.strftime("%m-%d %H:%M"), 1))
             res.failures.append(payload)
@@ -246,9 +333,12 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     res.cumulative_snv_table = tables.cumulative_snv_table(res.raw_snp_table)
     res.cumulative_scaffold_table = (pd.concat(sum_tabs, ignore_index=True) if sum_tabs
                                      else pd.DataFrame(columns=summary.COLUMNS))
+    empty_snp, empty_ld = res.raw_snp_table.iloc[0:0], res.raw_linkage_table.iloc[0:0]
+    by_snp = {k: v for k, v in res.raw_snp_table.groupby("scaffold", sort=False)}       # grouped once, not filtered per scaffold
+    by_ld = {k: v for k, v in res.raw_linkage_table.groupby("scaffold", sort=False)}
     for name, sp in res.scaffolds.items():
-        sp.raw_snp_table = res.raw_snp_table[res.raw_snp_table["scaffold"] == name]
-        sp.raw_linkage_table = res.raw_linkage_table[res.raw_linkage_table["scaffold"] == name]
+        sp.raw_snp_table = by_snp.get(name, empty_snp)
+        sp.raw_linkage_table = by_ld.get(name, empty_ld)
     res.timing["profile_scaffolds_s"] = time.time() - t0
     logging.debug("instrain_b200: profiled %d scaffolds in %.2fs", len(res.scaffold_list), res.timing["profile_scaffolds_s"])
     if own:

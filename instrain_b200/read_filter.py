@@ -20,6 +20,8 @@ def _lib():
         vp, i64 = C.c_void_p, C.c_int64
         L.isb_filter_open.restype = vp
         L.isb_filter_open.argtypes = [C.c_char_p]
+        L.isb_host_last_error.restype = C.c_char_p
+        L.isb_host_last_error.argtypes = []
         L.isb_filter_apply.restype = i64
         L.isb_filter_apply.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int]
         L.isb_filter_apply2.restype = i64
@@ -68,7 +70,7 @@ def filter_reads(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_rela
     lib = _lib()
     h = lib.isb_filter_open(bam.encode())
     if not h:
-        raise IOError("cannot read BAM %s" % bam)
+        raise IOError("error reading BAM: " + lib.isb_host_last_error().decode())
     try:
         priority_reads = list(priority_reads)
         _apply(lib, h, min_read_ani, min_mapq, max_insert_relative, min_insert, pairing_filter, priority_reads)
@@ -124,7 +126,7 @@ def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_rela
     lib = _lib()
     h = lib.isb_filter_open(bam.encode())
     if not h:
-        raise IOError("cannot read BAM %s" % bam)
+        raise IOError("error reading BAM: " + lib.isb_host_last_error().decode())
     try:
         priority_reads = list(priority_reads)
         if pairing_filter != "paired_only" or priority_reads:

@@ -24,16 +24,29 @@ def _locate(pos, scaffold_off):
     return idx, pos - np.asarray(scaffold_off)[idx]
 
 
-def snv_table(rows, scaffold_names, scaffold_off, seqs):
-    """isb_snv_row[] -> raw_snp_table DataFrame (sorted by scaffold order, position, mm)."""
+_REF_CHARS = np.array(list("ACTGN"), dtype=object)
+
+
+def snv_table(rows, scaffold_names, scaffold_off, seqs, ref_codes=None):
+    """isb_snv_row[] -> raw_snp_table DataFrame (sorted by scaffold order, position, mm).  ref_base is the reference
+    character at the position: from the batch's reference codes when given (one gather for the whole batch; only
+    positions whose code is "not A/C/G/T" look their letter up in the sequence), else per scaffold from `seqs`."""
     rows = rows[np.lexsort((rows["mm"], rows["pos"]))]
     names = np.asarray(scaffold_names, dtype=object)
     sidx, rel = _locate(rows["pos"].astype(np.int64), scaffold_off)
-    ref_base = np.empty(len(rows), dtype=object)
-    for i in np.unique(sidx):
-        m = sidx == i
-        seq = np.frombuffer(seqs[names[i]].encode(), dtype="S1")
-        ref_base[m] = seq[rel[m]].astype(str)
+    if ref_codes is not None:
+        codes = np.asarray(ref_codes)[rows["pos"].astype(np.int64)]
+        ref_base = _REF_CHARS[np.minimum(codes, 4)]
+        for k in np.nonzero(codes > 3)[0]:                               # rare: N or another IUPAC letter
+            ref_base[k] = seqs[names[sidx[k]]][rel[k]]
+    else:
+        ref_base = np.empty(len(rows), dtype=object)
+        order = np.argsort(sidx, kind="stable")
+        bounds = np.searchsorted(sidx[order], np.arange(len(names) + 1))
+        for i in np.nonzero(np.diff(bounds))[0]:
+            m = order[bounds[i]:bounds[i + 1]]
+            seq = np.frombuffer(seqs[names[i]].encode(), dtype="S1")
+            ref_base[m] = seq[rel[m]].astype(str)
     cnt = rows["cnt"].astype(np.int64)
     return pd.DataFrame({
         "scaffold": names[sidx], "position": rel.astype(np.int64), "ref_base": ref_base,

@@ -382,3 +382,83 @@ def test_iter_batches_honours_fdb_splits():
         exp_fdb += [(cuts[i] + off, cuts[i + 1] - 1 + off) for i in range(3)]
         exp_plain += [(s + off, e + off) for s, e in iterate_splits(L, 500)]
     assert with_fdb["splits"] == exp_fdb and plain["splits"] == exp_plain and len(exp_plain) > len(exp_fdb)
+
+
+# ---- corrupt / truncated input: a partial pass must raise, never return a partial profile (pysam / htslib raise) ----------
+
+def _damaged_copies(tmp_path):
+    src = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    raw = open(src, "rb").read()
+    out = {}
+    cut = tmp_path / "cut_half.bam"
+    cut.write_bytes(raw[:len(raw) // 2])                                  # cut inside a BGZF block
+    out["cut"] = str(cut)
+    # cut exactly at a BGZF block boundary, in the middle of the file: only the missing end-of-file block gives it away
+    o, bounds = 0, []
+    while o + 18 <= len(raw):
+        bsize = (raw[o + 16] | (raw[o + 17] << 8)) + 1
+        o += bsize
+        bounds.append(o)
+    edge = tmp_path / "cut_at_block.bam"
+    edge.write_bytes(raw[:bounds[len(bounds) // 2]])
+    out["edge"] = str(edge)
+    bad = bytearray(raw)
+    mid = len(raw) // 2
+    rng = np.random.default_rng(1)
+    bad[mid:mid + 2000] = rng.integers(0, 256, 2000, dtype=np.uint8).tobytes()
+    cor = tmp_path / "corrupt.bam"
+    cor.write_bytes(bytes(bad))
+    out["corrupt"] = str(cor)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["cut", "edge", "corrupt"])
+def test_damaged_bam_raises_everywhere(tmp_path, kind):
+    import json
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.profile import iter_batches
+    from instrain_b200.read_filter import filter_reads, mapping_info
+    path = _damaged_copies(tmp_path)[kind]
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    with BamPacker(path) as bp:
+        names = bp.ref_names                                              # the header is intact in all three
+    with pytest.raises(IOError):
+        list(iter_batches(path, rdic, seqs))
+    with pytest.raises(IOError):
+        filter_reads(path, names)
+    with pytest.raises(IOError):
+        mapping_info(path, names)
+
+
+def test_intact_bam_still_reads(tmp_path):
+    """Control for the test above: the undamaged file gives its batch, and a BAM without the end-of-file block is readable
+    on request (ISB_ALLOW_NO_BGZF_EOF), as `samtools` merely warns about it."""
+    import json
+    from instrain_b200.profile import iter_batches
+    src = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    full = [b for k, b in iter_batches(src, rdic, seqs) if k == "batch"]
+    assert len(full) == 1 and full[0]["n_events"] > 100000
+    raw = open(src, "rb").read()
+    assert raw[-28:-26] == b"\x1f\x8b" and raw[-4:] == b"\0\0\0\0"         # the 28-byte empty block
+    noeof = tmp_path / "noeof.bam"
+    noeof.write_bytes(raw[:-28])
+    with pytest.raises(IOError):
+        list(iter_batches(str(noeof), rdic, seqs))
+    os.environ["ISB_ALLOW_NO_BGZF_EOF"] = "1"
+    try:
+        again = [b for k, b in iter_batches(str(noeof), rdic, seqs) if k == "batch"]
+    finally:
+        del os.environ["ISB_ALLOW_NO_BGZF_EOF"]
+    assert again[0]["n_events"] == full[0]["n_events"]
+
+
+def test_mm_levels_beyond_the_device_limit_are_folded():
+    from instrain_b200 import _cabi
+    from instrain_b200.packer import BamPacker
+    mm = BamPacker._mm_levels([0, 3, 63, 64, 300])
+    assert mm.dtype == np.uint8 and mm.tolist() == [0, 3, 63, _cabi.ISB_MAX_MM - 1, _cabi.ISB_MAX_MM - 1]
+    with pytest.raises(ValueError):
+        BamPacker._mm_levels([-1])
