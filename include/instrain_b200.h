@@ -509,6 +509,9 @@ void isb_filter_tally(void *filter, int tid, int64_t tally[6]);
  * mean_mistmaches, mean_insert_distance, mean_mapq_score, mean_pair_length, mean_PID, median_insert (over the pairs that
  * pass the pairing filter; NaN when there are none), and that number of pairs. */
 void isb_filter_stats(void *filter, int tid, double stats[10]);
+/* The same for any pairing filter: the means / median run over the entries the last isb_filter_apply2 selected (singletons,
+ * priority reads and pairs merged over two scaffolds included when the mode keeps them; filter_reads.py:262-276). */
+void isb_filter_stats2(void *filter, int tid, double stats[10]);
 int64_t isb_filter_n_pairs(void *filter, int tid);
 int64_t isb_filter_names_bytes(void *filter, int tid);
 void isb_filter_copy(void *filter, int tid, char *names_blob, int64_t *name_off, int32_t *mm);

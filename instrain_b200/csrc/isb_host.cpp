@@ -886,6 +886,37 @@ void isb_filter_stats(void *h, int tid, double out[10])
     out[6] = pairs ? s_len / pairs : nan; out[7] = pairs ? s_pid / pairs : nan; out[8] = median; out[9] = pairs;
 }
 
+// The same columns for ANY pairing filter: means / median over the entries the last isb_filter_apply2 selected (the
+// scaffold's pair2info after paired_read_filter: singletons and priority reads included when the mode keeps them, values
+// merged over scaffolds in all_reads mode), as filter_scaff2pair2info takes them (filter_reads.py:262-276).
+void isb_filter_stats2(void *h, int tid, double out[10])
+{
+    const ScaffoldPairs &sp = ((Filter *)h)->sc[tid];
+    double reads = 0, pairs = 0, singles = 0, n = 0, s_nm = 0, s_ins = 0, s_mapq = 0, s_len = 0, s_pid = 0;
+    std::vector<int64_t> ins;
+    for (const PairInfo &pi : sp.info) {
+        reads += pi.reads;
+        if (pi.reads == 1) singles += 1;
+        if (pi.reads == 2) pairs += 1;
+        if (!pi.sel) continue;
+        n += 1;
+        s_nm += (double)pi.e_nm; s_ins += (double)pi.e_insert; s_mapq += (double)pi.e_mapq; s_len += (double)pi.e_length;
+        s_pid += 1.0 - (double)pi.e_nm / (double)pi.e_length;
+        ins.push_back(pi.e_insert);
+    }
+    double median = 0.0 / 0.0;
+    if (!ins.empty()) {
+        const size_t m = ins.size(), k = m / 2;
+        std::nth_element(ins.begin(), ins.begin() + k, ins.end());
+        median = (double)ins[k];
+        if (m % 2 == 0) median = ((double)*std::max_element(ins.begin(), ins.begin() + k) + (double)ins[k]) / 2.0;
+    }
+    const double nan = 0.0 / 0.0;
+    out[0] = reads; out[1] = pairs; out[2] = singles;
+    out[3] = n ? s_nm / n : nan; out[4] = n ? s_ins / n : nan; out[5] = n ? s_mapq / n : nan;
+    out[6] = n ? s_len / n : nan; out[7] = n ? s_pid / n : nan; out[8] = median; out[9] = n;
+}
+
 int isb_filter_n_refs(void *h) { return (int)((Filter *)h)->sc.size(); }
 double isb_filter_max_insert(void *h) { return ((Filter *)h)->max_insert; }
 void isb_filter_tally(void *h, int tid, int64_t out[6]) { memcpy(out, ((Filter *)h)->sc[tid].tally, sizeof(int64_t) * 6); }

@@ -99,7 +99,7 @@ def _r2m_levels(r2m):
 
 def _new_batch():
     return dict(names=[], off=[], ref=[], splits=[], n_splits=[], parts=[], pair_mm=[], pair_off=[], n_events=0, L=0,
-                n_pairs=0, M=1)
+                n_pairs=0, M=1, pad=0)
 
 
 def _add_to_batch(batch, name, seq, ev, splits):
@@ -124,7 +124,11 @@ def _sub_batch(batch, i0, i1):
     """Scaffolds [i0, i1) of a batch as a batch of their own (coordinates, pair ids and splits re-based to 0): what a
     failed batch is bisected into, so that one bad scaffold does not take its neighbours down."""
     sub = _new_batch()
-    d_pos, d_pair = batch["off"][i0], batch["pair_off"][i0]
+    d_pair = batch["pair_off"][i0]
+    # the packed nibble words are aligned to 8-position columns of the BATCH coordinates: coordinates may only be shifted
+    # by a multiple of 8, so the sub-batch starts with up to 7 unused positions (`pad`: no reads, reference code "other")
+    sub["pad"] = sub["L"] = batch["off"][i0] & 7
+    d_pos = batch["off"][i0] - sub["pad"]
     s0 = sum(batch["n_splits"][:i0])
     for k in range(i0, i1):
         ev = dict(batch["parts"][k])
@@ -259,6 +263,10 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     res = ProfileResult()
     t0 = time.time()
     snp_tabs, ld_tabs, sum_tabs = [], [], []
+    # keep_rows = {scaffold: global index}: also keep the raw row arrays with scaffold-relative positions, the global
+    # scaffold index and the reference character per row -- what a rank sends to rank 0 (profile_bam_distributed)
+    keep_rows = kwargs.get("keep_rows")
+    res.rows = dict(snv=[], snv_sidx=[], snv_ref=[], ld=[], ld_sidx=[]) if keep_rows is not None else None
 
     def flush(batch):
         """Profile one batch; a failing batch is logged in the reference's format and skipped, the run continues
@@ -285,7 +293,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
     def _flush(batch):
         cat = np.concatenate
-        ref_codes = cat(batch["ref"])
+        pad = batch.get("pad", 0)
+        ref_codes = cat(([np.full(pad, 4, np.uint8)] if pad else []) + batch["ref"])
         offs = np.array(batch["off"], dtype=np.int64)
         # host -> device as read-major aligned segments (4 bits per aligned base); K1r transposes on the device.
         # Opt-in (kwargs["b200_transfer"] / ISB_TRANSFER): "delta" sends the reference-delta transfer format (about a
@@ -305,11 +314,31 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
                                    want=("covT", "clonT", "nmask", "snv", "ld"), **fmt)
         # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
         bounds = np.append(offs, len(ref_codes)).astype(np.int32)
+        if pad:                                                           # the unused leading positions: a dummy segment
+            bounds = np.concatenate([[0], bounds]).astype(np.int32)
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
+        if pad:
+            k4 = k4[out["M"]:]
         sum_tabs.append(summary.summary_table(k4, out["snv"], batch["names"], offs, out["M"]))
         seqs = {n: s2s[n] for n in batch["names"]}
         snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs, ref_codes=ref_codes))
         ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
+        if keep_rows is not None:
+            gidx = np.array([keep_rows[n] for n in batch["names"]], dtype=np.int32)
+            names_arr = np.asarray(batch["names"], dtype=object)
+            r = out["snv"].copy()
+            sidx, rel = tables._locate(r["pos"].astype(np.int64), offs)
+            ref_ch = tables.snv_ref_chars(r, sidx, rel, names_arr, seqs, ref_codes)
+            r["pos"] = rel
+            res.rows["snv"].append(r)
+            res.rows["snv_sidx"].append(gidx[sidx])
+            res.rows["snv_ref"].append(np.array([ord(c) for c in ref_ch], dtype=np.uint8))
+            q = out["ld"].copy()
+            sidx, rel_a = tables._locate(q["pos_a"].astype(np.int64), offs)
+            q["pos_b"] = q["pos_b"].astype(np.int64) - offs[sidx]
+            q["pos_a"] = rel_a
+            res.rows["ld"].append(q)
+            res.rows["ld_sidx"].append(gidx[sidx])
         for name, off in zip(batch["names"], offs):
             sp = ScaffoldProfile(name, len(s2s[name]))
             sl = slice(int(off), int(off) + len(s2s[name]))
@@ -403,3 +432,76 @@ def _as_snvprofile(S, res):
         except Exception:                                                # noqa: BLE001 - any import problem: native store
             pass
     return S
+
+
+def profile_bam_distributed(bam, Fdb, sR2M, ISP_loc, **kwargs):
+    """profile_bam over several GPUs of one node: one process per GPU (torchrun; torch.distributed initialised by the
+    caller, NCCL on GPUs / gloo in the CPU tests).  The reference farms (scaffold, split) tasks of ONE input to worker
+    processes, heaviest scaffolds first (profile_controller.py:243-271, fasta.py:103-105); here the scaffolds of the one
+    BAM are partitioned over the ranks by longest-processing-time packing on their filtered pairs
+    (instrain_b200.shard.lpt_partition), every rank profiles its share on its own GPU -- no collective on the data path --
+    and the final tables travel to rank 0 (instrain_b200.shard.gather_rows for the row tables; the per-scaffold coverage /
+    clonality series as pickled objects).  Rank 0 writes the SNVprofile directory and returns what profile_bam returns;
+    the other ranks return None."""
+    import torch.distributed as dist
+    from . import _cabi
+    from .shard import gather_rows, lpt_partition
+    rank, world = dist.get_rank(), dist.get_world_size()
+    s2s = kwargs.get("s2s")
+    if s2s is None or sR2M is None:
+        raise ValueError("profile_bam_distributed needs sR2M and kwargs['s2s'] (run the read filter once, on rank 0 or on every rank)")
+    order = list(sR2M)                                                    # the same on every rank
+    mine = lpt_partition([float(len(sR2M[s])) for s in order], world)[rank]
+    sub = {order[i]: sR2M[order[i]] for i in mine}
+    kw = dict(kwargs)
+    kw.pop("s2s")
+    kw["keep_rows"] = {s: i for i, s in enumerate(order)}
+    kw.setdefault("packer_threads", 2)                                    # > 1: seek through the .bai instead of reading the whole BAM
+    device = kw.pop("device", None)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    gdev = None
+    if dist.get_backend() == "nccl":
+        import torch
+        gdev = torch.device("cuda", device)
+    res = profile_scaffolds(bam, sub, s2s, Fdb=Fdb, device=device, **kw)
+    cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dtype=dt)
+    snv = gather_rows(cat(res.rows["snv"], _cabi.SNV_DT), device=gdev)
+    snv_sidx = gather_rows(cat(res.rows["snv_sidx"], np.int32), device=gdev)
+    snv_ref = gather_rows(cat(res.rows["snv_ref"], np.uint8), device=gdev)
+    ld = gather_rows(cat(res.rows["ld"], _cabi.LD_DT), device=gdev)
+    ld_sidx = gather_rows(cat(res.rows["ld_sidx"], np.int32), device=gdev)
+    small = dict(scaffold_list=res.scaffold_list, scaffolds=res.scaffolds, failures=res.failures,
+                 summary=res.cumulative_scaffold_table, seconds=res.timing.get("profile_scaffolds_s"))
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(small, parts, dst=0)
+    if rank != 0:
+        return None
+    out = ProfileResult()
+    names = np.asarray(order, dtype=object)
+    o = np.lexsort((snv["mm"], snv["pos"], snv_sidx))
+    snv, snv_sidx, snv_ref = snv[o], snv_sidx[o], snv_ref[o]
+    out.raw_snp_table = tables.snv_frame(snv, names[snv_sidx], snv["pos"].astype(np.int64),
+                                         np.array([chr(c) for c in snv_ref], dtype=object))
+    o = np.lexsort((ld["mm"], ld["pos_b"], ld["pos_a"], ld_sidx))
+    ld, ld_sidx = ld[o], ld_sidx[o]
+    out.raw_linkage_table = tables.linkage_frame(ld, names[ld_sidx], ld["pos_a"].astype(np.int64), ld["pos_b"].astype(np.int64))
+    out.cumulative_snv_table = tables.cumulative_snv_table(out.raw_snp_table)
+    sums = [p["summary"] for p in parts if p["summary"] is not None and len(p["summary"])]
+    out.cumulative_scaffold_table = pd.concat(sums, ignore_index=True) if sums else pd.DataFrame(columns=summary.COLUMNS)
+    for r, p in enumerate(parts):
+        out.scaffold_list.extend(p["scaffold_list"])
+        out.scaffolds.update(p["scaffolds"])
+        out.failures.extend(p["failures"])
+        out.timing["rank%d_profile_scaffolds_s" % r] = p["seconds"]
+    by_snp = {k: v for k, v in out.raw_snp_table.groupby("scaffold", sort=False)}
+    by_ld = {k: v for k, v in out.raw_linkage_table.groupby("scaffold", sort=False)}
+    for name, sp in out.scaffolds.items():
+        sp.raw_snp_table = by_snp.get(name, out.raw_snp_table.iloc[0:0])
+        sp.raw_linkage_table = by_ld.get(name, out.raw_linkage_table.iloc[0:0])
+    if ISP_loc is None or not kwargs.get("store", True):
+        return out
+    from .store import store_profile
+    S = store_profile(ISP_loc, bam, out)
+    out.store = S
+    return _as_snvprofile(S, out)

@@ -33,6 +33,7 @@ def _lib():
         L.isb_filter_max_insert.argtypes = [vp]
         L.isb_filter_tally.argtypes = [vp, C.c_int, vp]
         L.isb_filter_stats.argtypes = [vp, C.c_int, vp]
+        L.isb_filter_stats2.argtypes = [vp, C.c_int, vp]
         L.isb_filter_n_pairs.restype = i64
         L.isb_filter_n_pairs.argtypes = [vp, C.c_int]
         L.isb_filter_names_bytes.restype = i64
@@ -120,8 +121,8 @@ MAPPING_INFO_COLUMNS = ["scaffold", "unfiltered_reads", "unfiltered_pairs", "unf
 def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50,
                  pairing_filter="paired_only", priority_reads=(), **_):
     """The reference's `mapping_info` table (the read report of filter_scaff2pair2info, filter_reads.py:230-298, with the
-    pairing tallies of paired_read_filter, :484-502) for the default pairing filter: one row per scaffold with reads,
-    preceded by the `all_scaffolds` row (sums; means weighted by pass_pairing_filter)."""
+    pairing tallies of paired_read_filter, :484-502) for every pairing filter and with priority reads: one row per
+    scaffold with reads, preceded by the `all_scaffolds` row (sums; means weighted by pass_pairing_filter)."""
     import pandas as pd
     lib = _lib()
     h = lib.isb_filter_open(bam.encode())
@@ -129,20 +130,23 @@ def mapping_info(bam, ref_names, min_read_ani=0.95, min_mapq=-1, max_insert_rela
         raise IOError("error reading BAM: " + lib.isb_host_last_error().decode())
     try:
         priority_reads = list(priority_reads)
-        if pairing_filter != "paired_only" or priority_reads:
-            raise NotImplementedError("mapping_info: the means are taken over the paired_only selection; other pairing filters "
-                                      "are served by filter_reads (sR2M + tallies)")
+        general = pairing_filter != "paired_only" or bool(priority_reads)
         _apply(lib, h, min_read_ani, min_mapq, max_insert_relative, min_insert, pairing_filter, priority_reads)
         rows = []
         for tid in range(lib.isb_filter_n_refs(h)):
             t = np.zeros(6, dtype=np.int64)
+            t2 = np.zeros(3, dtype=np.int64)
             s = np.zeros(10, dtype=np.float64)
             lib.isb_filter_tally(h, tid, t.ctypes.data)
-            lib.isb_filter_stats(h, tid, s.ctypes.data)
+            if general:                                            # means over what the pairing filter selected
+                lib.isb_filter_stats2(h, tid, s.ctypes.data)
+                lib.isb_filter_tally2(h, tid, t2.ctypes.data)
+            else:
+                lib.isb_filter_stats(h, tid, s.ctypes.data)
             if s[0] == 0:
                 continue                                           # no read of this scaffold in the BAM
-            rows.append([ref_names[tid], int(s[0]), int(s[1]), int(s[2]), 0, int(t[0]), int(t[1]), int(t[2]), int(t[3]),
-                         int(t[4]), int(t[5]), 0, 0, s[3], s[4], s[5], s[6], s[7], s[8]])
+            rows.append([ref_names[tid], int(s[0]), int(s[1]), int(s[2]), int(t2[0]), int(t[0]), int(t[1]), int(t[2]), int(t[3]),
+                         int(t[4]), int(t[5]), int(t2[1]), int(t2[2]), s[3], s[4], s[5], s[6], s[7], s[8]])
     finally:
         lib.isb_filter_free(h)
     Adb = pd.DataFrame(rows, columns=MAPPING_INFO_COLUMNS)

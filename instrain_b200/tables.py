@@ -27,33 +27,42 @@ def _locate(pos, scaffold_off):
 _REF_CHARS = np.array(list("ACTGN"), dtype=object)
 
 
-def snv_table(rows, scaffold_names, scaffold_off, seqs, ref_codes=None):
-    """isb_snv_row[] -> raw_snp_table DataFrame (sorted by scaffold order, position, mm).  ref_base is the reference
-    character at the position: from the batch's reference codes when given (one gather for the whole batch; only
-    positions whose code is "not A/C/G/T" look their letter up in the sequence), else per scaffold from `seqs`."""
-    rows = rows[np.lexsort((rows["mm"], rows["pos"]))]
-    names = np.asarray(scaffold_names, dtype=object)
-    sidx, rel = _locate(rows["pos"].astype(np.int64), scaffold_off)
+def snv_ref_chars(rows, sidx, rel, names, seqs, ref_codes=None):
+    """Reference character of every SNV row: from the batch's reference codes when given (one gather for the whole batch;
+    only positions whose code is "not A/C/G/T" look their letter up in the sequence), else per scaffold from `seqs`."""
     if ref_codes is not None:
         codes = np.asarray(ref_codes)[rows["pos"].astype(np.int64)]
         ref_base = _REF_CHARS[np.minimum(codes, 4)]
         for k in np.nonzero(codes > 3)[0]:                               # rare: N or another IUPAC letter
             ref_base[k] = seqs[names[sidx[k]]][rel[k]]
-    else:
-        ref_base = np.empty(len(rows), dtype=object)
-        order = np.argsort(sidx, kind="stable")
-        bounds = np.searchsorted(sidx[order], np.arange(len(names) + 1))
-        for i in np.nonzero(np.diff(bounds))[0]:
-            m = order[bounds[i]:bounds[i + 1]]
-            seq = np.frombuffer(seqs[names[i]].encode(), dtype="S1")
-            ref_base[m] = seq[rel[m]].astype(str)
+        return ref_base
+    ref_base = np.empty(len(rows), dtype=object)
+    order = np.argsort(sidx, kind="stable")
+    bounds = np.searchsorted(sidx[order], np.arange(len(names) + 1))
+    for i in np.nonzero(np.diff(bounds))[0]:
+        m = order[bounds[i]:bounds[i + 1]]
+        seq = np.frombuffer(seqs[names[i]].encode(), dtype="S1")
+        ref_base[m] = seq[rel[m]].astype(str)
+    return ref_base
+
+
+def snv_frame(rows, scaffold_of_row, rel, ref_base):
+    """isb_snv_row[] + (scaffold name, scaffold-relative position, reference character) per row -> raw_snp_table."""
     cnt = rows["cnt"].astype(np.int64)
     return pd.DataFrame({
-        "scaffold": names[sidx], "position": rel.astype(np.int64), "ref_base": ref_base,
+        "scaffold": scaffold_of_row, "position": np.asarray(rel, dtype=np.int64), "ref_base": ref_base,
         "A": cnt[:, 0], "C": cnt[:, 1], "T": cnt[:, 2], "G": cnt[:, 3],
         "con_base": BASES[rows["con"]], "var_base": BASES[rows["var"]], "mm": rows["mm"].astype(np.int64),
         "allele_count": rows["allele_count"].astype(np.int64), "class": np.array(CLASS_NAMES, dtype=object)[rows["cls"]],
         "cryptic": rows["cryptic"].astype(bool), "position_coverage": cnt.sum(1)}, columns=SNV_COLUMNS)
+
+
+def snv_table(rows, scaffold_names, scaffold_off, seqs, ref_codes=None):
+    """isb_snv_row[] (batch coordinates) -> raw_snp_table DataFrame (sorted by scaffold order, position, mm)."""
+    rows = rows[np.lexsort((rows["mm"], rows["pos"]))]
+    names = np.asarray(scaffold_names, dtype=object)
+    sidx, rel = _locate(rows["pos"].astype(np.int64), scaffold_off)
+    return snv_frame(rows, names[sidx], rel, snv_ref_chars(rows, sidx, rel, names, seqs, ref_codes))
 
 
 def cumulative_snv_table(raw):
@@ -74,11 +83,7 @@ def cumulative_snv_table(raw):
     return out
 
 
-def linkage_table(rows, scaffold_names, scaffold_off):
-    rows = rows[np.lexsort((rows["mm"], rows["pos_b"], rows["pos_a"]))]
-    names = np.asarray(scaffold_names, dtype=object)
-    sidx, rel_a = _locate(rows["pos_a"].astype(np.int64), scaffold_off)
-    rel_b = rows["pos_b"].astype(np.int64) - np.asarray(scaffold_off)[sidx]
+def linkage_frame(rows, scaffold_of_row, rel_a, rel_b):
     c = [rows[k].astype(np.int64) for k in ("c_AB", "c_Ab", "c_aB", "c_ab")]
     nan = np.full(len(rows), np.nan)
     return pd.DataFrame({
@@ -86,7 +91,15 @@ def linkage_table(rows, scaffold_names, scaffold_off):
         "total": c[0] + c[1] + c[2] + c[3], "countAB": c[0], "countAb": c[1], "countaB": c[2], "countab": c[3],
         "allele_A": BASES[rows["allele_A"]], "allele_a": BASES[rows["allele_a"]], "allele_B": BASES[rows["allele_B"]],
         "allele_b": BASES[rows["allele_b"]], "distance": rel_b - rel_a, "position_A": rel_a, "position_B": rel_b,
-        "mm": rows["mm"].astype(np.int64), "scaffold": names[sidx]}, columns=LD_COLUMNS)
+        "mm": rows["mm"].astype(np.int64), "scaffold": scaffold_of_row}, columns=LD_COLUMNS)
+
+
+def linkage_table(rows, scaffold_names, scaffold_off):
+    rows = rows[np.lexsort((rows["mm"], rows["pos_b"], rows["pos_a"]))]
+    names = np.asarray(scaffold_names, dtype=object)
+    sidx, rel_a = _locate(rows["pos_a"].astype(np.int64), scaffold_off)
+    rel_b = rows["pos_b"].astype(np.int64) - np.asarray(scaffold_off)[sidx]
+    return linkage_frame(rows, names[sidx], rel_a, rel_b)
 
 
 def present_levels(covT, nmask):

@@ -332,7 +332,8 @@ def test_profile_scaffolds_host_loop_without_gpu():
         eng = StubEngine()
         res = profile_scaffolds(bam, rdic, seqs, engine=eng, b200_transfer=transfer, packer_threads=threads)
         assert sorted(res.failures) == sorted(rdic) and res.scaffold_list == [] and len(res.raw_snp_table) == 0
-        (n_pairs, L, n_splits, keys, fmt), = eng.calls
+        n_pairs, L, n_splits, keys, fmt = eng.calls[0]              # the whole batch; then it is bisected down to
+        assert len(eng.calls) == 2 * len(rdic) - 1                    # single scaffolds: 2 n - 1 calls
         assert L == sum(len(seqs[s]) for s in rdic) and n_pairs == sum(len(v) for v in rdic.values())
         seen[transfer] = fmt
     rd = seen["segments"]["reads"]
@@ -343,6 +344,65 @@ def test_profile_scaffolds_host_loop_without_gpu():
     assert int(words.sum()) > 0
     assert seen["cols"]["cols"]["n_chunks"] > 0 and int((seen["cols"]["cols"]["ids"] >= 0).sum()) == int(
         (((rd["seg_start"].astype(np.int64) & 7) + rd["seg_len"].astype(np.int64) + 7) // 8).sum())
+
+
+def test_failed_batch_is_bisected_to_the_offending_scaffold():
+    """One scaffold the engine cannot take (the device's envelope, memory ...) costs that scaffold only: the batch is
+    retried in halves and every other scaffold comes out exactly as in an undisturbed run (the reference loses one split to
+    an exception, profile_utilities.py:104-111)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_profile_host_cpu import OracleEngine
+    from instrain_b200.profile import profile_scaffolds
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    good = profile_scaffolds(bam, rdic, seqs, engine=OracleEngine())
+    victim = sorted(rdic, key=lambda s: len(rdic[s]))[len(rdic) // 2]
+    L_victim = len(seqs[victim])
+
+    class Picky(OracleEngine):
+        def profile_batch(self, ev, ref_codes, splits, **kw):
+            # the victim is recognised by its reference sequence sitting somewhere in the batch
+            from instrain_b200.profile import encode_reference
+            v = encode_reference(seqs[victim])
+            ref = np.asarray(ref_codes)
+            for off in range(0, len(ref) - L_victim + 1):
+                if ref[off] == v[0] and np.array_equal(ref[off:off + L_victim], v):
+                    raise RuntimeError("ISB_ERR_UNSUPPORTED (simulated)")
+            return super().profile_batch(ev, ref_codes, splits, **kw)
+
+    res = profile_scaffolds(bam, rdic, seqs, engine=Picky())
+    assert res.failures == [victim] and sorted(res.scaffold_list) == sorted(s for s in rdic if s != victim)
+    key = ["scaffold", "position", "mm"]
+    a = res.raw_snp_table.sort_values(key).reset_index(drop=True)
+    b = good.raw_snp_table[good.raw_snp_table["scaffold"] != victim].sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) > 500 and a.equals(b)
+    key = ["scaffold", "position_A", "position_B", "mm"]
+    a = res.raw_linkage_table.sort_values(key).reset_index(drop=True)
+    b = good.raw_linkage_table[good.raw_linkage_table["scaffold"] != victim].sort_values(key).reset_index(drop=True)
+    assert len(a) == len(b) > 500
+    for c in key + ["countAB", "countab", "total"]:
+        assert (a[c].values == b[c].values).all(), c
+    for s in res.scaffold_list:
+        for mm, ser in good.scaffolds[s].covT.items():
+            assert ser.equals(res.scaffolds[s].covT[mm])
+
+
+def test_batches_close_on_the_cell_budget():
+    """L x M cells bound a batch (dense per-position outputs: 24 B per cell on the device): a small budget splits the
+    stream into several batches whose union is the single batch."""
+    from instrain_b200.profile import iter_batches
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    one = [b for k, b in iter_batches(bam, rdic, seqs) if k == "batch"]
+    assert len(one) == 1
+    Lmax = max(len(seqs[s]) for s in rdic)
+    for threads in (1, 2):
+        many = [b for k, b in iter_batches(bam, rdic, seqs, max_batch_cells=Lmax * 16, packer_threads=threads) if k == "batch"]
+        assert len(many) > 1 and [n for b in many for n in b["names"]] == one[0]["names"]
+        assert sum(b["n_events"] for b in many) == one[0]["n_events"] and all(b["L"] * b["M"] <= Lmax * 16 or len(b["names"]) == 1 for b in many)
 
 
 def test_priority_read_files(tmp_path):

@@ -138,6 +138,14 @@ def test_read_filter_modes_against_reference_functions(pairing_filter, use_prior
     for s, t in cpp_tal.items():
         for c, v in t.items():
             assert int(R.loc[s, c]) == int(v), (s, c)
+    # the whole read report (mapping_info) of this mode: every column of every row, the weighted all_scaffolds row included
+    from instrain_b200.read_filter import MAPPING_INFO_COLUMNS, mapping_info
+    mi = mapping_info(BAM, names, pairing_filter=pairing_filter, priority_reads=priority, **thr).set_index("scaffold")
+    Rall = Rdb.set_index("scaffold")
+    assert sorted(mi.index) == sorted(Rall.index) and "all_scaffolds" in mi.index
+    for c in MAPPING_INFO_COLUMNS[1:]:
+        a, b = mi.loc[Rall.index, c].values.astype(float), Rall[c].values.astype(float)
+        assert np.allclose(a, b, rtol=0, atol=1e-9, equal_nan=True), c
 
 
 def test_hot_path_with_singletons_in_r2m_against_reference_functions():

@@ -61,3 +61,87 @@ def test_gather_tables_gloo_world2():
     exp = sorted(1000 * i + j for i, w in enumerate(weights) for j in range(w))
     assert sorted(pos) == exp and len(mm) == sum(weights)
     assert r2 == [1.5, 1.5, 1.5]
+
+
+def _profile_worker(rank, world, port, q, isp):
+    """profile_bam_distributed on the bundled BAM subset, world size 2 over gloo; the CUDA engine answered by the oracle
+    (test stub: no GPU here -- the kernels have their own parity tests)."""
+    import json
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import instrain_b200.profile as P
+    from conftest import GOLDEN
+    from test_profile_host_cpu import OracleEngine
+
+    class E(OracleEngine):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def close(self):
+            pass
+
+    P.Engine = E
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["ISB_NATIVE_STORE"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    out = P.profile_bam_distributed(bam, None, rdic, isp if rank == 0 else None, s2s=seqs, device=0)
+    if rank == 0:
+        r = out.result
+        q.put((sorted(r.scaffold_list), r.failures, len(r.raw_snp_table), len(r.raw_linkage_table), len(r.cumulative_scaffold_table),
+               r.raw_snp_table.to_json(), r.raw_linkage_table[["scaffold", "position_A", "position_B", "mm", "countAB", "total"]].to_json(),
+               sorted(r.timing)))
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_profile_bam_distributed_gloo_world2(tmp_path):
+    """One BAM, two ranks: the scaffolds are LPT-partitioned, every rank profiles its share, rank 0 ends up with exactly the
+    tables (and the SNVprofile directory) of a single-process run."""
+    import io
+    import json
+    import pandas as pd
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import GOLDEN
+    from test_profile_host_cpu import OracleEngine
+    from instrain_b200.profile import profile_scaffolds
+    from instrain_b200.store import SNVprofileStore
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    isp = str(tmp_path / "dist.IS")
+    procs = [ctx.Process(target=_profile_worker, args=(r, 2, port, q, isp)) for r in range(2)]
+    for p in procs:
+        p.start()
+    names, failures, n_snv, n_ld, n_sum, snv_json, ld_json, timing = q.get(timeout=280)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    one = profile_scaffolds(os.path.join(GOLDEN, "c1_G1_subset.bam"), rdic, seqs, engine=OracleEngine())
+    assert names == sorted(rdic) and failures == [] and timing == ["rank0_profile_scaffolds_s", "rank1_profile_scaffolds_s"]
+    assert (n_snv, n_ld, n_sum) == (len(one.raw_snp_table), len(one.raw_linkage_table), len(one.cumulative_scaffold_table))
+    key = ["scaffold", "position", "mm"]
+    a = pd.read_json(io.StringIO(snv_json)).sort_values(key).reset_index(drop=True)
+    b = one.raw_snp_table.sort_values(key).reset_index(drop=True)
+    for c in ["scaffold", "position", "mm", "ref_base", "A", "C", "T", "G", "con_base", "var_base", "allele_count", "class", "cryptic"]:
+        assert (a[c].values == b[c].values).all(), c
+    key = ["scaffold", "position_A", "position_B", "mm"]
+    a = pd.read_json(io.StringIO(ld_json)).sort_values(key).reset_index(drop=True)
+    b = one.raw_linkage_table.sort_values(key).reset_index(drop=True)
+    for c in key + ["countAB", "total"]:
+        assert (a[c].values == b[c].values).all(), c
+    S = SNVprofileStore(isp)
+    assert sorted(S.get("scaffold_list")) == sorted(rdic) and len(S.get("raw_linkage_table")) == n_ld
+    covT = S.get("covT")
+    for s, sp in one.scaffolds.items():
+        assert set(covT[s]) == set(sp.covT)

@@ -9,7 +9,8 @@ echo "pytest exit $?" >> $out/${tag}_pytest.log
 tail -5 $out/${tag}_pytest.log
 ARGS="--scaffolds 20 --steps 5 --warmup 3 --also-events 0 --no-cpu-baseline --e2e-scaffolds 1"
 i=0
-for spec in "--layout reads" "ISB_K1F=0 --layout reads" ${EXTRA_SPECS}; do
+IFS=';' read -ra SPECS <<< "--layout reads;ISB_K1F=0 --layout reads${EXTRA_SPECS:+;$EXTRA_SPECS}"
+for spec in "${SPECS[@]}"; do
   envs=""; extra=""
   for tok in $spec; do case $tok in *=*) envs="$envs $tok";; *) extra="$extra $tok";; esac; done
   env $envs timeout 600 python bench.py $ARGS $extra > $out/${tag}_$i.json 2> $out/${tag}_$i.err
