@@ -44,11 +44,14 @@
 #define K1F_WARPS (K1F_THREADS / 32)
 #define K1F_MAXLEN 256                 // hard cap of max_seg_len
 #define K1F_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
-#define K1F_STAGE_IT 9                 // segment-table elements per thread per chunk: seg_cap <= 9 * 128
+#ifndef K1F_STAGE_IT
+#define K1F_STAGE_IT 4                 // segment-table elements per thread and staging pass
+#endif
+#define K1F_SEG_CAP_MAX 1536           // segments staged per chunk at most (12 B each in the fused kernel)
 #define K1F_TILE4 (256 + 32)           // count quads of a warp's 256 positions + one pad quad per 8 positions
-#define K1F_CODE_IDS 1024              // pair-id window (ids) of a site the ballot row builder handles; wider ones: atomics
+#define K1F_CODE_IDS 512               // pair-id window (ids) of a site the ballot row builder handles; wider ones: atomics
 #ifndef K1F_MINB
-#define K1F_MINB 5                     // __launch_bounds__ min blocks per SM of the fused kernel (<= 102 registers)
+#define K1F_MINB 7                     // __launch_bounds__ min blocks per SM of the M = 1 kernels (<= 73 registers; ~32 KB shared)
 #endif
 static_assert(K1F_WARPS == 4, "the site bookkeeping of the fused epilogue assumes 4 warps per tile");
 
@@ -183,13 +186,11 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     const uint32_t s_meta_sa = isb_smem_u32(s_meta);                      // its shared-space byte address
     int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);   // start relative to a.start (sorted): the search key
     uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);     // M > 1 only
-    int32_t *s_pair = s_start + a.seg_cap;                                // fused: pair id per staged segment (linkage sites)
-    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kFuse ? 12 : (kM1 ? 8 : 9))) + 15) & ~(size_t)15);
+    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kM1 ? 8 : 9)) + 15) & ~(size_t)15);
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_x);                  // M > 1: [Mg * 8][K1F_THREADS]
     // fused epilogue scratch
     int4 *s_tile = reinterpret_cast<int4 *>(s_x);                         // [K1F_WARPS][K1F_TILE4]
-    uint32_t *s_rows = reinterpret_cast<uint32_t *>(s_tile + K1F_WARPS * K1F_TILE4);   // [K1F_WARPS][ISB_K3_ROW_SLOT]
-    int32_t *s_cl = reinterpret_cast<int32_t *>(s_rows + K1F_WARPS * ISB_K3_ROW_SLOT); // [K1F_THREADS] candidate range per column
+    int32_t *s_cl = reinterpret_cast<int32_t *>(s_tile + K1F_WARPS * K1F_TILE4);       // [K1F_THREADS] candidate range per column
     int32_t *s_ch = s_cl + K1F_THREADS;
     int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: sites per warp, offsets, slot base
     uint16_t *s_site = reinterpret_cast<uint16_t *>(s_misc + 16);         // [K1F_WARPS][256]: position in the warp | bases << 8
@@ -240,24 +241,25 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
             err |= ISB_DEV_ERR_SEG;
             continue;
         }
-        // Segment table of the chunk -> shared memory.  All global loads of the (up to K1F_STAGE_IT) elements a thread
-        // handles are issued before the first is used: the block pays ONE memory latency here.
-        {
+        // Segment table of the chunk -> shared memory, K1F_STAGE_IT * 128 segments per pass.  All global loads of the
+        // elements a thread handles in a pass are issued before the first is used: one memory latency per pass (the other
+        // resident blocks cover it); fewer elements in flight = fewer registers = one more resident block.
+        for (int pb = 0; pb < nc; pb += K1F_STAGE_IT * K1F_THREADS) {
             int32_t r_s[K1F_STAGE_IT], r_prev[K1F_STAGE_IT], r_pid[K1F_STAGE_IT];
             int r_n[K1F_STAGE_IT];
             int64_t r_w[K1F_STAGE_IT];
 #pragma unroll
             for (int k = 0; k < K1F_STAGE_IT; ++k) {
-                const int i = t + k * K1F_THREADS;
+                const int i = pb + t + k * K1F_THREADS;
                 const int64_t g = c0 + i;
                 r_s[k] = 0; r_prev[k] = INT_MIN; r_n[k] = 1; r_w[k] = wb + 1; r_pid[k] = 0;
-                if (k * K1F_THREADS >= nc) break;                  // block-uniform
+                if (pb + k * K1F_THREADS >= nc) break;             // block-uniform
                 if (i < nc) {
                     r_s[k] = __ldg(a.rd.seg_start + g);
                     r_n[k] = __ldg(a.rd.seg_len + g);
                     r_w[k] = __ldg(a.rd.seg_word + g);
                     if (g > 0) r_prev[k] = __ldg(a.rd.seg_start + g - 1);
-                    if (!kM1 || (kFuse && a.do_ld)) r_pid[k] = __ldg(a.rd.seg_pair + g);
+                    if (!kM1) r_pid[k] = __ldg(a.rd.seg_pair + g);
                 }
             }
             int r_mm[K1F_STAGE_IT];
@@ -265,13 +267,13 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
 #pragma unroll
                 for (int k = 0; k < K1F_STAGE_IT; ++k) {
                     r_mm[k] = 255;
-                    if (t + k * K1F_THREADS < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
+                    if (pb + t + k * K1F_THREADS < nc && r_pid[k] >= 0 && (int64_t)r_pid[k] < a.n_pairs)
                         r_mm[k] = __ldg(a.pair_mm + r_pid[k]);
                 }
             }
 #pragma unroll
             for (int k = 0; k < K1F_STAGE_IT; ++k) {
-                const int i = t + k * K1F_THREADS;
+                const int i = pb + t + k * K1F_THREADS;
                 if (i >= nc) break;
                 const int64_t s64 = (int64_t)r_s[k] - a.start;
                 const int n = r_n[k];
@@ -286,7 +288,6 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 const int s_rel = min(max(s - T0, -255), K1F_TILE - 1);   // candidates start in (T0 - 256, T0 + 1024)
                 s_meta[i] = ((uint32_t)(wl_c - (s_rel >> 3) + 160) << 11) | (uint32_t)(s_rel + n_c + 256);
                 s_start[i] = s;
-                if (kFuse) s_pair[i] = r_pid[k];
                 if (!kM1) {
                     if (r_mm[k] >= a.M) { err |= ISB_DEV_ERR_MM; r_mm[k] = 255; }
                     s_mm[i] = (uint8_t)r_mm[k];
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                     if (i < ch_) {
                         const uint32_t md = s_meta[i];
                         cov[u] = (pt + 256 < (int)(md & 0x7ffu)) && s_start[i] <= p;
-                        if (cov[u]) { w4[u] = __ldg(wsrc0 + (md >> 11) + tcol); pid[u] = s_pair[i]; }
+                        if (cov[u]) { w4[u] = __ldg(wsrc0 + (md >> 11) + tcol); pid[u] = __ldg(a.rd.seg_pair + lo + i); }
                     }
                 }
 #pragma unroll
@@ -719,12 +720,11 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
 
 static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
 {
-    size_t b = (((size_t)seg_cap * (fuse ? 12 : (m1 ? 8 : 9))) + 15) & ~(size_t)15;
+    size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
     if (fuse)
-        b += 4 * K1F_WARPS * ISB_K3_ROW_SLOT + 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 +
-             K1F_WARPS * K1F_CODE_IDS;
+        b += 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 + K1F_WARPS * K1F_CODE_IDS;
     return b;
 }
 
@@ -751,9 +751,9 @@ static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L
     rd->tile_hi = tile_hi;
     rd->tile_wlo = rd->tile_whi = nullptr;
     // staging capacity: what a tile holds on average + 15 % + 48 (the Poisson spread of ~800 segments is 3.5 %), capped
-    int64_t cap = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1F_TILE + rd->max_seg_len) * 1.15) + 48 : 64;
+    int64_t cap = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1F_TILE + rd->max_seg_len) * 1.12) + 40 : 64;
     if (cap < 64) cap = 64;
-    if (cap > K1F_STAGE_IT * K1F_THREADS) cap = K1F_STAGE_IT * K1F_THREADS;
+    if (cap > K1F_SEG_CAP_MAX) cap = K1F_SEG_CAP_MAX;
     *seg_cap = (int)((cap + 3) & ~(int64_t)3);
     return ISB_OK;
 }
