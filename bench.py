@@ -199,6 +199,7 @@ class Job:
         self.nmask = None if self.lean else torch.empty(L_, dtype=torch.int64, device=dev)
         self.covT = torch.empty((L_, M_), dtype=torch.int32, device=dev)
         self.clonT = torch.empty((L_, M_), dtype=torch.float32, device=dev)
+        self.clonTR = torch.empty((L_, M_), dtype=torch.float32, device=dev)   # rarefied clonality: part of the reference's output
         self.flags = torch.empty(L_, dtype=torch.uint8, device=dev)
         self.snv_cap = max(1 << 16, (L_ // 16) * (1 if M_ == 1 else 4))
         self.ld_cap = max(1 << 18, (L_ // 2) * (1 if M_ == 1 else 4))
@@ -222,7 +223,7 @@ class Job:
             self.batch = _cabi.IsbBatch(int(d["n_events"]), p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), self.npairs,
                                         p(d["pair_mm"]), 0, L_, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M_)
             self.entry = eng.lib.isb_profile_batch
-        self.prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05)
+        self.prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05, 50, 0, SEED)
         self.step_no, self.res = 0, None
 
     def _alloc_rows(self):
@@ -231,9 +232,9 @@ class Job:
         self.sets = []
         for _ in range(self.n_sets):
             s_ = torch.empty(self.snv_cap * 32, dtype=torch.uint8, device=self.dev)
-            l_ = torch.empty(self.ld_cap * 48, dtype=torch.uint8, device=self.dev)
+            l_ = torch.empty(self.ld_cap * 64, dtype=torch.uint8, device=self.dev)
             r_ = self._cabi.IsbResult(p(self.counts), p(self.nmask), p(self.covT), p(self.clonT), p(self.flags), p(s_), self.snv_cap,
-                                      p(l_), self.ld_cap, 0, 0, 0, 0)
+                                      p(l_), self.ld_cap, 0, 0, 0, 0, p(self.clonTR))
             self.sets.append((s_, l_, r_))
 
     def step(self):
@@ -276,7 +277,7 @@ class Gather:
         mine = torch.tensor([int(r_.n_snv), int(r_.n_ld)], dtype=torch.int64, device=self.dev)
         dist.all_reduce(mine, op=dist.ReduceOp.MAX)
         mx = mine.tolist()
-        self.slab = [min((mx[0] + 4095) // 4096 * 4096, self.job.snv_cap) * 32, min((mx[1] + 4095) // 4096 * 4096, self.job.ld_cap) * 48]
+        self.slab = [min((mx[0] + 4095) // 4096 * 4096, self.job.snv_cap) * 32, min((mx[1] + 4095) // 4096 * 4096, self.job.ld_cap) * 64]
         if self.rank == 0:
             self.recv = [[torch.empty(self.slab[t], dtype=torch.uint8, device=self.dev) for _ in range(self.world)] for t in range(2)]
         self.bytes_per_step = sum(self.slab) * (self.world - 1)
@@ -489,10 +490,10 @@ def main():
         in_bytes = int(rd["n_words"]) * 4 + int(rd["n_segs"]) * 14              # nibble stream + (start i32, len u16, word i64) per segment
         if fused:
             n_sites = max(0, int(res.n_sites))
-            out_bytes = Ltot * (1 + 4 + 4 + 1) + int(res.n_snv) * 32 + n_sites * 49
+            out_bytes = Ltot * (1 + 4 + 4 + 4 + 1) + int(res.n_snv) * 32 + n_sites * 49
             roofline = rl("k1f_pileup<M=1, fused SNV call + linkage site rows>", in_bytes + out_bytes, k1_ms, "K1f_fused_M1", Ltot,
                           "4 bits per aligned base (nibble stream incl. separators) + 14 B per segment + 1 B reference per position in; "
-                          "covT 4 + clonT 4 + site_flags 1 B per position, 32 B per SNV row, 49 B per linkage site (slot record + counts; "
+                          "covT 4 + clonT 4 + clonTR 4 + site_flags 1 B per position, 32 B per SNV row, 49 B per linkage site (slot record + counts; "
                           "its bit rows not counted) out",
                           achieved_survey_def=(10.0 * n_ev + (8 * M + 1) * Ltot) / k1_ms / 1e6,
                           survey_def="SURVEY 8(d): 10 B per aligned base (ref_pos, base, qual, read_id columns) + 8 M + 1 B per position, "
@@ -604,14 +605,15 @@ def main():
         def host_result():
             o = dict(covT=torch.empty((Ls, Ms), dtype=torch.int32).pin_memory(),
                      clonT=torch.empty((Ls, Ms), dtype=torch.float32).pin_memory(),
+                     clonTR=torch.empty((Ls, Ms), dtype=torch.float32).pin_memory(),
                      flags=torch.empty(Ls, dtype=torch.uint8).pin_memory(),
                      snv=torch.empty(max(1 << 16, (Ls // 16) * (1 if Ms == 1 else 16)) * 32, dtype=torch.uint8).pin_memory(),
-                     ld=torch.empty(max(1 << 18, (Ls // 2) * (1 if Ms == 1 else 8)) * 48, dtype=torch.uint8).pin_memory())
+                     ld=torch.empty(max(1 << 18, (Ls // 2) * (1 if Ms == 1 else 8)) * 64, dtype=torch.uint8).pin_memory())
             return o, _cabi.IsbResult(None, None, p(o["covT"]), p(o["clonT"]), p(o["flags"]), p(o["snv"]), o["snv"].numel() // 32,
-                                      p(o["ld"]), o["ld"].numel() // 48, 0, 0, 0, 0)
+                                      p(o["ld"]), o["ld"].numel() // 64, 0, 0, 0, 0, p(o["clonTR"]))
 
         o1, hres = host_result()
-        prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05)
+        prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05, 50, 0, SEED)
         fn = eng.lib.isb_profile_reads_delta
 
         def call(ctx_, res_):
@@ -670,7 +672,7 @@ def main():
         best = min(dt, dt_pipe) if dt_pipe else dt
         common = len(hs["pair_mm"]) + Ls + hs["splits"].nbytes
         h2d = hd["n_units"] + len(hd["mis_word"]) * 5 + hr["n_segs"] * (4 + 2 + 4) + common
-        d2h = Ls * Ms * 8 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 48
+        d2h = Ls * Ms * 12 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 64
         tot = torch.tensor([Ls / best, Ls / dt, Ls / dt_pipe if dt_pipe else 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ISB_ABI_VERSION 1
+#define ISB_ABI_VERSION 2
 
 #define ISB_OK 0
 #define ISB_ERR_CUDA (-1)        /* CUDA runtime error (message has the cudaError string) */
@@ -68,14 +68,17 @@ typedef struct {
     uint8_t pad[2];
 } isb_snv_row;
 
-/* One row of the reference's raw_linkage_table (_calc_ld_single, linkage.py:138-240; without the two
- * unseeded-random "normalized" columns).  48 bytes. */
+/* One row of the reference's raw_linkage_table (_calc_ld_single, linkage.py:138-240).  64 bytes.
+ * r2_normalized / d_prime_normalized (linkage.py:200-228) are the same statistics on min_snp haplotypes re-drawn from the
+ * four observed frequencies.  The reference draws them with an UNSEEDED np.random.choice; here the draws come from a
+ * counter-based generator keyed by (isb_params.seed, pos_a, pos_b, mm): reproducible, same distribution. */
 typedef struct {
     int32_t pos_a, pos_b; /* batch coordinates, pos_a <= pos_b */
     int32_t mm;
     int32_t c_AB, c_Ab, c_aB, c_ab;
     uint8_t allele_A, allele_a, allele_B, allele_b;
     double r2, d_prime;   /* NaN where the reference yields np.nan */
+    double r2_normalized, d_prime_normalized;
 } isb_ld_row;
 
 typedef struct isb_ctx isb_ctx;
@@ -109,14 +112,14 @@ int isb_pileup_counts(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, co
  * calculate_clonality (snv_utilities.py:40-231) and is_present (readComparer.py:307-316) for L positions.
  *   covT[p][m]   = exact-mm coverage (int32)           clonT[p][m] = clonality of cumulative counts (float32, NaN = unset)
  *   site_flags[p] see ISB_SITE_ANYSNP                   rows: unordered; *n_rows = number produced (also when > cap)
- * clonTR (rarefied, unseeded RNG in the reference, snv_utilities.py:233-247) is not produced. */
+ * clonTR (rarefied clonality) comes out of the whole-path entry points only (isb_result.clonTR). */
 int isb_call_snvs(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const uint64_t *nmask, const uint8_t *ref,
                   int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT, uint8_t *site_flags,
                   isb_snv_row *rows, int64_t cap, int64_t *n_rows);
 
 /* ---- stage K3: linkage --------------------------------------------------------------------------------------- */
 /* Replaces update_linked_reads, calc_mm_SNV_linkage_network, calculate_ld, _iterator_ld_sites,
- * major_minor_allele and the deterministic part of _calc_ld_single (linkage.py:14-198, 254-283).
+ * major_minor_allele and _calc_ld_single (linkage.py:14-240, 254-283; the normalized columns with seed 0).
  * Needs the position-major events again plus K1/K2 outputs.  rows unordered; *n_rows as above. */
 int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
                 const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
@@ -146,6 +149,10 @@ typedef struct {
     int32_t min_qual;         /* min_base_quality=30     (profile_utilities.py:152) */
     uint32_t flags;           /* ISB_SKIP_LINKAGE ... */
     double min_freq;          /* -f/--min_freq 0.05      (argumentParser.py:109) */
+    int32_t rarefied_cov;     /* --rarefied_coverage 50  (argumentParser.py:168): clonTR is computed where the cumulative
+                               * coverage reaches it; 0 = no rarefied clonality */
+    int32_t pad;
+    uint64_t seed;            /* key of the counter-based generator behind clonTR and the normalized linkage columns */
 } isb_params;
 #define ISB_SKIP_LINKAGE 0x2   /* K1+K2 only (BASELINE config 2) */
 #define ISB_NO_SYNC 0x4        /* all-device buffers only: enqueue and return; row counts valid after isb_synchronize */
@@ -171,6 +178,10 @@ typedef struct {
     int64_t n_ld;
     int64_t n_sites;          /* linkage-eligible (anySNP) sites */
     int64_t n_site_pairs;     /* site pairs evaluated by the linkage kernel */
+    /* rarefied clonality [L][M] (calculate_rarefied_clonality, snv_utilities.py:233-247: the clonality of rarefied_cov bases
+     * re-drawn from the site's base frequencies; NaN below rarefied_cov).  Unseeded in the reference; here keyed by
+     * (isb_params.seed, position, mm).  NULL or rarefied_cov == 0: not computed. */
+    float *clonTR;
 } isb_result;
 
 int isb_profile_batch(isb_ctx *ctx, const isb_batch *in, const isb_params *prm, isb_result *out);

@@ -23,8 +23,9 @@ SNV_DT = np.dtype([("pos", "<i4"), ("cnt", "<i4", (4,)), ("mm", "<i4"), ("ref", 
                    ("var", "u1"), ("allele_count", "u1"), ("cls", "u1"), ("cryptic", "u1"), ("pad", "u1", (2,))])
 LD_DT = np.dtype([("pos_a", "<i4"), ("pos_b", "<i4"), ("mm", "<i4"), ("c_AB", "<i4"), ("c_Ab", "<i4"),
                   ("c_aB", "<i4"), ("c_ab", "<i4"), ("allele_A", "u1"), ("allele_a", "u1"), ("allele_B", "u1"),
-                  ("allele_b", "u1"), ("r2", "<f8"), ("d_prime", "<f8")])
-assert SNV_DT.itemsize == 32 and LD_DT.itemsize == 48
+                  ("allele_b", "u1"), ("r2", "<f8"), ("d_prime", "<f8"), ("r2_normalized", "<f8"),
+                  ("d_prime_normalized", "<f8")])
+assert SNV_DT.itemsize == 32 and LD_DT.itemsize == 64
 
 SUMMARY_DT = np.dtype([("length", "<i8"), ("nonzero", "<i8"), ("sum_cov", "<i8"), ("sum_cov2", "<u8"), ("counted", "<i8"),
                        ("sum_clon", "<f8"), ("cov_med_lo", "<i4"), ("cov_med_hi", "<i4"), ("clon_med_lo", "<f4"),
@@ -101,14 +102,14 @@ class IsbColsBatch(C.Structure):
 
 class IsbParams(C.Structure):
     _fields_ = [("min_cov", C.c_int32), ("min_snp", C.c_int32), ("min_qual", C.c_int32), ("flags", C.c_uint32),
-                ("min_freq", C.c_double)]
+                ("min_freq", C.c_double), ("rarefied_cov", C.c_int32), ("pad", C.c_int32), ("seed", C.c_uint64)]
 
 
 class IsbResult(C.Structure):
     _fields_ = [("counts", C.c_void_p), ("nmask", C.c_void_p), ("covT", C.c_void_p), ("clonT", C.c_void_p),
                 ("site_flags", C.c_void_p), ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("ld", C.c_void_p),
                 ("ld_cap", C.c_int64), ("n_snv", C.c_int64), ("n_ld", C.c_int64), ("n_sites", C.c_int64),
-                ("n_site_pairs", C.c_int64)]
+                ("n_site_pairs", C.c_int64), ("clonTR", C.c_void_p)]
 
 
 class IsbError(RuntimeError):

@@ -334,6 +334,7 @@ int isb_linkage(isb_ctx *ctx, int64_t n_events, const int32_t *ref_pos, const ui
     if ((rc = stage_in(ctx, SL_FLAGS, site_flags, (size_t)L, &d_flags))) return rc;
     if ((rc = stage_in(ctx, SL_SPLITS, splits, (size_t)n_splits * 2, &d_splits))) return rc;
     isb_ld_row *d_rows;
+    ctx->seed = 0;
     if ((rc = stage_out(ctx, SL_LD, rows, (size_t)(cap > 0 ? cap : 1), &d_rows))) return rc;
     if ((rc = isb_k3_launch(ctx, n_events, d_pos, d_base, d_qual, d_rid, n_pairs, d_mm, start, L, M, min_qual, d_counts,
                             (const unsigned long long *)d_nmask, d_flags, n_splits, d_splits, min_snp, d_rows, cap))) return rc;
@@ -389,6 +390,11 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     if ((rc = stage_out(ctx, SL_COVT, out->covT, (size_t)L * M, &d_covT))) return rc;
     if ((rc = stage_out(ctx, SL_CLONT, out->clonT, (size_t)L * M, &d_clonT))) return rc;
     if ((rc = stage_out(ctx, SL_FLAGS, out->site_flags, (size_t)L, &d_flags))) return rc;
+    // rarefied clonality: only when the caller wants it (isb_result.clonTR) and gives a rarefied coverage
+    float *d_clonTR = nullptr;
+    const int cov_r = out->clonTR && prm->rarefied_cov > 0 ? prm->rarefied_cov : 0;
+    if (out->clonTR && (rc = stage_out(ctx, SL_CLONTR, out->clonTR, (size_t)L * M, &d_clonTR))) return rc;
+    ctx->seed = prm->seed;
     const int64_t snv_cap = out->snv ? out->snv_cap : 0, ld_cap = out->ld ? out->ld_cap : 0;
     if ((rc = stage_out(ctx, SL_SNV, out->snv, (size_t)(snv_cap > 0 ? snv_cap : 1), &d_snv))) return rc;
     if ((rc = stage_out(ctx, SL_LD, out->ld, (size_t)(ld_cap > 0 ? ld_cap : 1), &d_ld))) return rc;
@@ -421,7 +427,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     }
     static const int fuse_env = getenv("ISB_K1C_FUSE") ? atoi(getenv("ISB_K1C_FUSE")) : 1;
     if (fused_reads) {
-        isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, 0};
+        isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, 0, d_clonTR, cov_r, prm->seed};
         isb_k1f_linkage lk = {n_splits, d_splits, prm->min_snp, d_ld, ld_cap};
         for (int attempt = 0;; ++attempt) {
             if ((rc = isb_k1f_profile_launch(ctx, rd, n_pairs, start, L, (unsigned long long *)d_nmask, &fz, do_ld ? &lk : nullptr))) return rc;
@@ -468,7 +474,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
                 cdk.grp_off = cd->grp_off + off / ISB_COLS_GROUP;
                 cdk.n_groups = (len + ISB_COLS_GROUP - 1) / ISB_COLS_GROUP;
                 isb_k2_fuse fz = {d_ref + off, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off, d_snv,
-                                  snv_cap, fuse_env == 2 ? 1 : 0};
+                                  snv_cap, fuse_env == 2 ? 1 : 0, d_clonTR ? d_clonTR + off * M : nullptr, cov_r, prm->seed};
                 rc = isb_k1c_launch(ctx, &cdk, d_mm, n_pairs, (int32_t)a[c], (int32_t)len, M, d_counts + off * M * 4,
                                     d_nmask ? (unsigned long long *)d_nmask + off : nullptr, fused ? &fz : nullptr, false);
             }
@@ -486,7 +492,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
                 int t2 = isb_time_begin(ctx, 1);
                 rc = isb_k2_launch(ctx, c_len, M, d_counts + off * M * 4, d_nmask ? (const unsigned long long *)d_nmask + off : nullptr,
                                    d_ref + off, c_lo, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off,
-                                   d_snv, snv_cap);
+                                   d_snv, snv_cap, d_clonTR ? d_clonTR + off * M : nullptr, cov_r, prm->seed);
                 isb_time_end(ctx, t2);
             }
             if (rc == ISB_OK) {
@@ -533,7 +539,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
             int t2 = isb_time_begin(ctx, 1);
             rc = isb_k2_launch(ctx, c_len, M, d_counts + off * M * 4, (const unsigned long long *)d_nmask + off, d_ref + off,
                                c_lo, prm->min_cov, prm->min_freq, d_covT + off * M, d_clonT + off * M, d_flags + off,
-                               d_snv, snv_cap);
+                               d_snv, snv_cap, d_clonTR ? d_clonTR + off * M : nullptr, cov_r, prm->seed);
             isb_time_end(ctx, t2);
             if (rc == ISB_OK && do_ld) {
                 int t3 = isb_time_begin(ctx, 2);
@@ -560,7 +566,8 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
         if (fused && cd->n_nev == 0) d_nmask = nullptr;
         int ts = isb_time_begin(ctx, 0);
         if (cd) {
-            isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, fuse_env == 2 ? 1 : 0};
+            isb_k2_fuse fz = {d_ref, prm->min_cov, prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, fuse_env == 2 ? 1 : 0,
+                              d_clonTR, cov_r, prm->seed};
             rc = isb_k1c_launch(ctx, cd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask, fused ? &fz : nullptr);
         } else if (rd) rc = isb_k1r_launch(ctx, rd, d_mm, n_pairs, start, L, M, d_counts, (unsigned long long *)d_nmask);
         else rc = isb_k1_launch(ctx, n, d_pos, d_base, d_qual, d_rid, d_mm, start, L, M, prm->min_qual, 0, d_counts,
@@ -570,7 +577,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
         if (!fused) {
             ts = isb_time_begin(ctx, 1);
             if ((rc = isb_k2_launch(ctx, L, M, d_counts, (const unsigned long long *)d_nmask, d_ref, start, prm->min_cov,
-                                    prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap))) return rc;
+                                    prm->min_freq, d_covT, d_clonT, d_flags, d_snv, snv_cap, d_clonTR, cov_r, prm->seed))) return rc;
             isb_time_end(ctx, ts);
         }
         ISB_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -589,6 +596,7 @@ static int profile_device(isb_ctx *ctx, isb_reads_dev *rd, isb_cols_dev *cd, int
     if (d_nmask && (rc = finish_out(ctx, out->nmask, d_nmask, (size_t)L))) return rc;
     if ((rc = finish_out(ctx, out->covT, d_covT, (size_t)L * M))) return rc;
     if ((rc = finish_out(ctx, out->clonT, d_clonT, (size_t)L * M))) return rc;
+    if (d_clonTR && (rc = finish_out(ctx, out->clonTR, d_clonTR, (size_t)L * M))) return rc;
     if ((rc = finish_out(ctx, out->site_flags, d_flags, (size_t)L))) return rc;
     if (prm->flags & ISB_NO_SYNC) {
         out->n_snv = out->n_ld = out->n_sites = out->n_site_pairs = -1;

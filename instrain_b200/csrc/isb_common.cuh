@@ -22,7 +22,7 @@
 
 enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_REF_POS = 0, SL_BASE, SL_QUAL, SL_READ_ID, SL_PAIR_MM, SL_REF, SL_SPLITS,   // staged inputs
-    SL_COUNTS, SL_NMASK, SL_COVT, SL_CLONT, SL_FLAGS, SL_SNV, SL_LD,              // staged outputs
+    SL_COUNTS, SL_NMASK, SL_COVT, SL_CLONT, SL_CLONTR, SL_FLAGS, SL_SNV, SL_LD,              // staged outputs
     SL_TILE_OFF,                                                                   // K1 tile event offsets
     SL_PK_OFF, SL_PK_IDBASE, SL_PK_BQD, SL_PK_ESC_EVT, SL_PK_ESC_ID,                  // packed transfer format (K0 inputs)
     SL_K3_TILE_OFF, SL_PAIRS,
@@ -61,6 +61,7 @@ struct isb_ctx {
     int64_t sites_cap;                // fused read-major path: linkage-site slots allocated so far (grow-only)
     isb_devbuf buf[SL_COUNT];
     char err[512];
+    uint64_t seed;                    // isb_params.seed of the running call (linkage: normalized columns)
     // optional per-stage device timing (isb_enable_timing): CUDA events recorded on ctx->stream around K1 / K2 / K3
     int timing;
     int n_tev;
@@ -111,7 +112,8 @@ int isb_k1_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t
                   uint32_t flags, int32_t *counts, unsigned long long *nmask);
 int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                   const uint8_t *ref, int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT,
-                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap);
+                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap, float *clonTR = nullptr, int cov_r = 0,
+                  uint64_t seed = 0);
 int isb_k3_launch(isb_ctx *ctx, int64_t n, const int32_t *ref_pos, const uint8_t *base, const uint8_t *qual,
                   const int32_t *read_id, int64_t n_pairs, const uint8_t *pair_mm, int32_t start, int32_t L, int M,
                   int min_qual, const int32_t *counts, const unsigned long long *nmask, const uint8_t *site_flags,
@@ -200,6 +202,9 @@ struct isb_k2_fuse {
     isb_snv_row *rows;
     int64_t cap;
     int full_counts;                  // 1: write counts of every position; 0: only of flagged sites (what K3 reads)
+    float *clonTR;                    // rarefied clonality (NULL: not computed)
+    int cov_r;                        // rarefied_coverage
+    uint64_t seed;
 };
 // init_nmask = false: nmask (when given) already holds the N-event bits of the range (chunked calls set it once per batch)
 int isb_k1c_launch(isb_ctx *ctx, const isb_cols_dev *cd, const uint8_t *pair_mm, int64_t n_pairs, int32_t start, int32_t L,

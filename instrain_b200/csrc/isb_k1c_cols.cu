@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MINB) k1c_pileup_m1(k1c_args 
         a.k2.covT[p] = s.T;
         a.k2.clonT[p] = s.clon;
         a.k2.site_flags[p] = (uint8_t)s.flags;
+        if (a.k2.clonTR)
+            a.k2.clonTR[p] = (a.k2.cov_r > 0 && s.T >= a.k2.cov_r) ? k2_rarefied_clon(C, s.T, a.k2.cov_r, a.k2.seed, (int64_t)p + a.start, 0)
+                                                                 : CUDART_NAN_F;
         if (a.write_counts || s.flags) counts4[p] = E;            // K3 reads counts at flagged sites only
         rowmask |= (s.is_row ? 1u : 0u) << rd;
     }

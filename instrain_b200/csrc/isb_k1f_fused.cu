@@ -111,24 +111,10 @@ k1f_tile_bounds(const int32_t *__restrict__ seg_start, int64_t n_segs, int32_t s
     }
 }
 
-__device__ __forceinline__ int k1f_warp_max(int v)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(ISB_FULL, v, d));
-    return v;
-}
-__device__ __forceinline__ int k1f_warp_sum(int v)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ISB_FULL, v, d);
-    return v;
-}
-__device__ __forceinline__ int k1f_warp_min(int v)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(ISB_FULL, v, d));
-    return v;
-}
+// warp reductions of 32-bit integers: one REDUX instruction each (sm_80+), not a 5-step shuffle ladder
+__device__ __forceinline__ int k1f_warp_max(int v) { return __reduce_max_sync(ISB_FULL, v); }
+__device__ __forceinline__ int k1f_warp_sum(int v) { return __reduce_add_sync(ISB_FULL, v); }
+__device__ __forceinline__ int k1f_warp_min(int v) { return __reduce_min_sync(ISB_FULL, v); }
 
 // M > 1: write (or add, once counts hold a partial sum) the thread's shared 8-bit counters to its cells of `counts`
 __device__ __forceinline__ void k1f_flush_levels(const k1f_args &a, uint32_t *s_acc, int t, int Mg, int m_base, int32_t P,
@@ -440,6 +426,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     uint16_t *site_list = s_site + wib * 256;
     int nq = 0;                                                   // positions waiting for the general path (warp-uniform)
     const bool all_general = a.k2.min_cov < 1;                    // then "below min_cov" is not a simple case
+    const int cov_r = a.k2.clonTR ? a.k2.cov_r : 0;               // rarefied clonality wanted where the coverage reaches it
 #pragma unroll 2
     for (int rd = 0; rd < 8; ++rd) {
         const int q = rd * 32 + lane;
@@ -449,7 +436,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         const int T = E.x + E.y + E.z + E.w;
         const int mx = max(max(E.x, E.y), max(E.z, E.w));
         bool simple = false;
-        float clon = CUDART_NAN_F;
+        float clon = CUDART_NAN_F, clonr = CUDART_NAN_F;
         if (in && !all_general) {
             if (T < a.k2.min_cov) {
                 simple = true;                                    // call_snv_site -> (None, 0): coverage only
@@ -457,12 +444,16 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 const int con = E.x == T ? 0 : (E.y == T ? 1 : (E.z == T ? 2 : 3));   // reference base and passes the threshold
                 if (T >= __ldg(a.thr2 + T) && con == (int)a.k2.ref[p]) { simple = true; clon = 1.0f; }
             }
+            if (simple && cov_r > 0 && T >= cov_r) {              // rarefied clonality: 1 with one base only, else drawn (general path)
+                if (mx == T) clonr = 1.0f; else simple = false;
+            }
         }
         if (in) {
             a.k2.covT[p] = T;
             if (simple) {
                 a.k2.clonT[p] = clon;
                 a.k2.site_flags[p] = 0;
+                if (a.k2.clonTR) a.k2.clonTR[p] = clonr;
                 if (full_counts) counts4[p] = E;
             }
         }
@@ -490,6 +481,8 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
             s = k2_site_m1(C, r, nm0, thr_T, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
             a.k2.clonT[p] = s.clon;
             a.k2.site_flags[p] = (uint8_t)s.flags;
+            if (a.k2.clonTR)
+                a.k2.clonTR[p] = (cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(C, T, cov_r, a.k2.seed, (int64_t)p + a.start, 0) : CUDART_NAN_F;
             if (full_counts) counts4[p] = E;
         }
         const bool row = on && s.is_row;
@@ -685,13 +678,15 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 for (int w = 0; w < m.nw; ++w) {
                     const int c = code[w * 32 + lane];
                     const unsigned any_w = __ballot_sync(ISB_FULL, c != 0);
-                    unsigned row_w[4];
+                    unsigned mine = lane == 0 ? any_w : 0u;        // lane r + 1 keeps allele row r's word; lanes na + 1 .. 2 na: 0
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) row_w[r] = __ballot_sync(ISB_FULL, c != 0 && c == b_of[r]);
+                    for (int r = 0; r < 4; ++r) {
+                        if (r >= na) break;                        // warp-uniform
+                        const unsigned row_w = __ballot_sync(ISB_FULL, c == b_of[r]);     // b_of > 0: empty ids never match
+                        if (lane == r + 1) mine = row_w;
+                    }
                     n_bits += __popc(any_w);
-                    if (lane == 0) g_any[w] = any_w;
-                    if (lane >= 1 && lane <= na) g_any[(size_t)lane * m.nw + w] = row_w[lane - 1 < 4 ? lane - 1 : 3];
-                    if (lane > na && lane <= 2 * na) g_any[(size_t)lane * m.nw + w] = 0u;     // multiplicity planes: empty
+                    if (lane <= 2 * na) g_any[(size_t)lane * m.nw + w] = mine;
                 }
                 n_ent = k1f_warp_sum(n_ent);
                 dup = n_bits != n_ent;

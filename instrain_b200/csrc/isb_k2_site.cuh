@@ -18,6 +18,51 @@ __device__ __forceinline__ double k2_quot(double c, double s, double rcp)
     return __fma_rn(e, rcp, q);
 }
 
+// ---- counter-based random numbers for the two resampled outputs (clonTR, normalized linkage) -----------------------------
+// The reference draws them with an unseeded np.random.choice (snv_utilities.py:241, linkage.py:200), so its own tests drop
+// those columns before comparing.  Here every draw is a pure function of (seed, stream tag, site key, draw index): word k
+// of a site = mix64(mix64(seed + tag) ^ a * K1 ^ b * K2 ^ k * K3) (splitmix64's finaliser), two 32-bit draws per word, a
+// draw u picks the category of index floor(u * total / 2^32) of the cumulative counts.  Reproducible, identical in every
+// input layout, restated in numpy by the test oracle for bit-exact parity tests; same distribution as the reference's.
+#define ISB_RNG_TAG_CLONR 0x636c6f6e54520001ull
+#define ISB_RNG_TAG_LD 0x6c646e6f726d0002ull
+__host__ __device__ __forceinline__ uint64_t isb_mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t isb_rand64(uint64_t seed, uint64_t tag, uint64_t a, uint64_t b, uint64_t k)
+{
+    return isb_mix64(isb_mix64(seed + tag) ^ (a * 0x9e3779b97f4a7c15ull) ^ (b * 0xd1b54a32d192ed03ull) ^ (k * 0x8cb92ba72f3d8dd7ull));
+}
+
+// calculate_rarefied_clonality (snv_utilities.py:233-247): n bases drawn with replacement from the frequencies C / T, then
+// the clonality of the drawn counts (double, A,C,T,G order, as calculate_clonality).  pos = batch coordinate.
+__device__ __forceinline__ float k2_rarefied_clon(const int (&C)[4], int T, int n, uint64_t seed, int64_t pos, int mm)
+{
+    const int mx = max(max(C[0], C[1]), max(C[2], C[3]));
+    if (mx == T) return 1.0f;                                         // every draw lands on the one base: (n/n)^2 + 0 + 0 + 0
+    const uint32_t c0 = (uint32_t)C[0], c01 = c0 + (uint32_t)C[1], c012 = c01 + (uint32_t)C[2];
+    int r0 = 0, r01 = 0, r012 = 0;                                    // draws below each cumulative bound
+    for (int i = 0; i < n; i += 2) {
+        const uint64_t h = isb_rand64(seed, ISB_RNG_TAG_CLONR, (uint64_t)pos, (uint64_t)mm, (uint64_t)(i >> 1));
+        uint32_t idx = __umulhi((uint32_t)h, (uint32_t)T);
+        r0 += idx < c0; r01 += idx < c01; r012 += idx < c012;
+        if (i + 1 < n) {
+            idx = __umulhi((uint32_t)(h >> 32), (uint32_t)T);
+            r0 += idx < c0; r01 += idx < c01; r012 += idx < c012;
+        }
+    }
+    const double s = (double)n;
+    const double f0 = __ddiv_rn((double)r0, s), f1 = __ddiv_rn((double)(r01 - r0), s);
+    const double f2 = __ddiv_rn((double)(r012 - r01), s), f3 = __ddiv_rn((double)(n - r012), s);
+    double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
+    prob = __dadd_rn(prob, __dmul_rn(f2, f2));
+    prob = __dadd_rn(prob, __dmul_rn(f3, f3));
+    return __double2float_rn(prob);
+}
+
 __device__ __forceinline__ int k2_argmax4(const int *c)
 {
     int b = 0, v = c[0];                                  // np.argmax: first maximum (value tracked: no dynamic indexing)

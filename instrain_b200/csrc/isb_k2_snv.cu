@@ -62,7 +62,7 @@ __device__ __forceinline__ void
 k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, unsigned long long nm, int ref,
                const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
                int32_t *cov_row, float *clon_row, isb_snv_row *__restrict__ rows, int64_t slot, int64_t cap,
-               int cryptic_final)
+               int cryptic_final, float *clonr_row = nullptr, int cov_r = 0, uint64_t seed = 0)
 {
     int *C = st.C;
     for (int j = 0; j < mc; ++j) {
@@ -94,6 +94,9 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
             clon = __double2float_rn(prob);
         }
         if (!kWrite) clon_row[j] = clon;
+        if (!kWrite && clonr_row)                                     // clonTR[mm][pos]: set where the coverage reaches cov_r
+            clonr_row[m] = (present && cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(st.C, T, cov_r, seed, (int64_t)p + start, m)
+                                                                : CUDART_NAN_F;
         if (!counted) continue;                                       // call_snv_site -> (None, 0)
         int thr, i = 0;
         if (T < n_lut) {                                              // integer form of the two-part presence test
@@ -177,7 +180,7 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
              const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
              int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
              uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
-             unsigned long long *__restrict__ n_rows)
+             unsigned long long *__restrict__ n_rows, float *__restrict__ clonTR, int cov_r, uint64_t seed)
 {
     const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
     const bool active = p < L;
@@ -189,7 +192,7 @@ k2_call_snvs(int32_t L, int M, const int32_t *__restrict__ counts, const unsigne
         r = ref[p];
         k2_site_levels<false>(st, p, 0, M, reinterpret_cast<const int4 *>(counts) + (size_t)p * M, nm, r, thr2, n_lut,
                               lut_default, start, min_cov, min_freq, covT + (size_t)p * M, clonT + (size_t)p * M, nullptr,
-                              0, 0, 0);
+                              0, 0, 0, clonTR ? clonTR + (size_t)p * M : nullptr, cov_r, seed);
         site_flags[p] = (uint8_t)(st.bases | (st.any_snp ? ISB_SITE_ANYSNP : 0));
     }
     k2_emit_rows(st, p, M, counts, nm, r, thr2, n_lut, lut_default, start, min_cov, min_freq, rows, cap, n_rows);
@@ -205,7 +208,7 @@ k2_call_snvs_m1(int32_t L, const int32_t *__restrict__ counts, const unsigned lo
                 const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
                 int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
                 uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
-                unsigned long long *__restrict__ n_rows)
+                unsigned long long *__restrict__ n_rows, float *__restrict__ clonTR, int cov_r, uint64_t seed)
 {
     const int32_t p = blockIdx.x * K2_THREADS + threadIdx.x;
     const bool active = p < L;
@@ -223,6 +226,7 @@ k2_call_snvs_m1(int32_t L, const int32_t *__restrict__ counts, const unsigned lo
         covT[p] = s.T;
         clonT[p] = s.clon;
         site_flags[p] = (uint8_t)s.flags;
+        if (clonTR) clonTR[p] = (cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(C, T, cov_r, seed, (int64_t)p + start, 0) : CUDART_NAN_F;
     }
     const unsigned mask = __ballot_sync(ISB_FULL, s.is_row);
     if (!mask) return;
@@ -249,7 +253,7 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
                     const uint8_t *__restrict__ ref, const int32_t *__restrict__ thr2, int n_lut, int lut_default,
                     int32_t start, int min_cov, double min_freq, int32_t *__restrict__ covT, float *__restrict__ clonT,
                     uint8_t *__restrict__ site_flags, isb_snv_row *__restrict__ rows, int64_t cap,
-                    unsigned long long *__restrict__ n_rows)
+                    unsigned long long *__restrict__ n_rows, float *__restrict__ clonTR, int cov_r, uint64_t seed)
 {
     extern __shared__ __align__(128) unsigned char k2_smem[];
     const bool whole = M <= K2S_MC;                                   // one chunk: rows keep the global (unpadded) layout
@@ -286,7 +290,8 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
         isb_mbar_wait(bar, 0);
         if (active)
             k2_site_levels<false>(st, p, 0, M, s_in + (size_t)t * M, nm, r, thr2, n_lut, lut_default, start, min_cov,
-                                  min_freq, s_cov + (size_t)t * M, s_clon + (size_t)t * M, nullptr, 0, 0, 0);
+                                  min_freq, s_cov + (size_t)t * M, s_clon + (size_t)t * M, nullptr, 0, 0, 0,
+                                  clonTR ? clonTR + (size_t)p * M : nullptr, cov_r, seed);
         __syncthreads();
         const int n_out = npos * M;                                   // words; the block's output run starts 16-byte aligned
         const size_t g0 = (size_t)p0 * M;
@@ -316,7 +321,7 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
             if (active)
                 k2_site_levels<false>(st, p, m0, mc, s_in + (size_t)t * sin, nm, r, thr2, n_lut, lut_default, start,
                                       min_cov, min_freq, s_cov + (size_t)t * sout, s_clon + (size_t)t * sout, nullptr, 0,
-                                      0, 0);
+                                      0, 0, clonTR ? clonTR + (size_t)p * M : nullptr, cov_r, seed);
             __syncthreads();
             // two rows per warp pass: 16 lanes per row (mc <= 16), no integer division
             for (int q = (t >> 4); q < npos; q += K2S_THREADS / 16) {
@@ -357,7 +362,7 @@ int isb_k2_prepare(isb_ctx *ctx, double min_freq)
 
 int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const unsigned long long *nmask,
                   const uint8_t *ref, int32_t start, int min_cov, double min_freq, int32_t *covT, float *clonT,
-                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap)
+                  uint8_t *site_flags, isb_snv_row *rows, int64_t cap, float *clonTR, int cov_r, uint64_t seed)
 {
     cudaStream_t st = ctx->stream;
     int rc = isb_k2_prepare(ctx, min_freq);
@@ -373,15 +378,15 @@ int isb_k2_launch(isb_ctx *ctx, int32_t L, int M, const int32_t *counts, const u
         }
         k2_call_snvs_staged<<<(L + K2S_THREADS - 1) / K2S_THREADS, K2S_THREADS, smem, st>>>(
             L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
-            site_flags, rows, cap, ctx->d_counters + 0);
+            site_flags, rows, cap, ctx->d_counters + 0, clonTR, cov_r, seed);
     } else if (M == 1 && variant != 0) {
         k2_call_snvs_m1<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
             L, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
-            site_flags, rows, cap, ctx->d_counters + 0);
+            site_flags, rows, cap, ctx->d_counters + 0, clonTR, cov_r, seed);
     } else {
         k2_call_snvs<<<(L + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, st>>>(
             L, M, counts, nmask, ref, ctx->d_thr2, ctx->n_lut, ctx->lut_default, start, min_cov, min_freq, covT, clonT,
-            site_flags, rows, cap, ctx->d_counters + 0);
+            site_flags, rows, cap, ctx->d_counters + 0, clonTR, cov_r, seed);
     }
     ISB_LAUNCH_CHECK();
     return ISB_OK;

@@ -17,6 +17,7 @@
 #include "isb_common.cuh"
 #include "isb_scan.cuh"
 #include "isb_k3_dev.cuh"
+#include "isb_k2_site.cuh"
 #include <math_constants.h>
 #include <cstdlib>
 
@@ -61,6 +62,7 @@ struct k3_args {
     int64_t sites_cap;
     const int4 *site_counts;       // counts per site slot (M = 1) instead of counts[p]
     const unsigned long long *n_sites_dev;   // device-side site / listed-pair counts (no host round trip)
+    uint64_t seed;                 // key of the re-drawn ("normalized") linkage columns
     // output
     isb_ld_row *out;
     int64_t cap;
@@ -495,6 +497,37 @@ __device__ __forceinline__ void k3_emit(const k3_args &a, int32_t p1, int32_t p2
         const double d1 = __dmul_rn(fA, fb), d2 = __dmul_rn(fa, fB);
         dp = __ddiv_rn(linkd, d1 < d2 ? d1 : d2);
     }
+    // r2_normalized / d_prime_normalized (linkage.py:200-228): the same statistics on min_snp haplotypes re-drawn from
+    // the four observed frequencies (counter-based draws keyed by the row, isb_k2_site.cuh)
+    double r2n = CUDART_NAN, dpn = CUDART_NAN;
+    if (a.min_snp >= 1) {
+        const uint32_t b1 = (uint32_t)cAB, b2 = b1 + (uint32_t)cAb, b3 = b2 + (uint32_t)caB;
+        const uint64_t key = ((uint64_t)(uint32_t)(p1 + a.start) << 32) | (uint64_t)(uint32_t)(p2 + a.start);
+        int n1 = 0, n2 = 0, n3 = 0;
+        for (int i = 0; i < a.min_snp; i += 2) {
+            const uint64_t h = isb_rand64(a.seed, ISB_RNG_TAG_LD, key, (uint64_t)m, (uint64_t)(i >> 1));
+            uint32_t idx = __umulhi((uint32_t)h, (uint32_t)total);
+            n1 += idx < b1; n2 += idx < b2; n3 += idx < b3;
+            if (i + 1 < a.min_snp) {
+                idx = __umulhi((uint32_t)(h >> 32), (uint32_t)total);
+                n1 += idx < b1; n2 += idx < b2; n3 += idx < b3;
+            }
+        }
+        const double ns = (double)a.min_snp;
+        const double gAB = __ddiv_rn((double)n1, ns), gAb = __ddiv_rn((double)(n2 - n1), ns);
+        const double gaB = __ddiv_rn((double)(n3 - n2), ns), gab = __ddiv_rn((double)(a.min_snp - n3), ns);
+        const double gA = __dadd_rn(gAB, gAb), ga = __dadd_rn(gab, gaB), gB = __dadd_rn(gAB, gaB), gb = __dadd_rn(gab, gAb);
+        const double ldn = __dsub_rn(gab, __dmul_rn(ga, gb));
+        if (!(ga == 0.0 || gA == 0.0 || gB == 0.0 || gb == 0.0))
+            r2n = __ddiv_rn(__dmul_rn(ldn, ldn), __dmul_rn(__dmul_rn(__dmul_rn(gA, ga), gB), gb));
+        if (ldn < 0.0) {
+            const double d1 = __dmul_rn(-gA, gB), d2 = __dmul_rn(-ga, gb);
+            dpn = __ddiv_rn(ldn, d1 > d2 ? d1 : d2);
+        } else if (ldn > 0.0) {
+            const double d1 = __dmul_rn(gA, gb), d2 = __dmul_rn(ga, gB);
+            dpn = __ddiv_rn(ldn, d1 < d2 ? d1 : d2);
+        }
+    }
     const unsigned long long slot = atomicAdd(a.n_ld, 1ull);
     if ((int64_t)slot < a.cap) {
         isb_ld_row r;
@@ -502,6 +535,7 @@ __device__ __forceinline__ void k3_emit(const k3_args &a, int32_t p1, int32_t p2
         r.c_AB = cAB; r.c_Ab = cAb; r.c_aB = caB; r.c_ab = cab;
         r.allele_A = (uint8_t)A; r.allele_a = (uint8_t)al; r.allele_B = (uint8_t)B; r.allele_b = (uint8_t)bl;
         r.r2 = r2; r.d_prime = dp;
+        r.r2_normalized = r2n; r.d_prime_normalized = dpn;
         a.out[slot] = r;
     }
 }
@@ -863,6 +897,7 @@ int isb_k3_backend_tiles(isb_ctx *ctx, const isb_reads_dev *rd, const isb_k3_til
     a.pair_j = a.pair_i + cap_pairs;
     a.out = rows; a.cap = cap;
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
+    a.seed = ctx->seed;
     const int grid = ctx->sm_count * 8;
     k3_enum_pairs_tiles<<<grid, 256, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
@@ -925,6 +960,7 @@ static int k3_run(isb_ctx *ctx, const isb_reads_dev *rd, const isb_cols_dev *cd,
     a.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;
     a.out = rows; a.cap = cap;
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
+    a.seed = ctx->seed;
 
     // 2.-5. bit rows of the sites, then linked pairs
     const int64_t site_warps_blocks = (S * 32 + K3_THREADS - 1) / K3_THREADS;

@@ -196,10 +196,13 @@ class Engine:
     # ---- whole path --------------------------------------------------------------------------------------------
     def profile_batch(self, ev, ref_codes, splits, start=0, M=None, min_cov=5, min_freq=0.05, min_snp=20,
                       min_qual=30, skip_linkage=False, want=("covT", "clonT", "site_flags", "snv", "ld"),
-                      snv_cap=None, ld_cap=None, packed=None, pipeline=False, reads=None, cols=None):
+                      snv_cap=None, ld_cap=None, packed=None, pipeline=False, reads=None, cols=None, rarefied_coverage=50,
+                      seed=0):
         """Run K1 -> K2 -> K3 on one batch with HOST (numpy) or CUDA-tensor inputs; numpy outputs.
 
-        `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld").
+        `want` selects which outputs are copied back ("counts", "nmask", "covT", "clonT", "clonTR", "site_flags", "snv",
+        "ld").  "clonTR" = rarefied clonality at `rarefied_coverage` (--rarefied_coverage, argumentParser.py:168); it and
+        the normalized linkage columns are drawn from a counter-based generator keyed by `seed` (reproducible).
         """
         L = len(ref_codes)
         pair_mm = _pair_mm_u8(ev["pair_mm"])
@@ -241,7 +244,8 @@ class Engine:
                                    len(pair_mm), p(pair_mm), start, L, p(ref_codes), len(splits), p(splits), M)
             entry = self.lib.isb_profile_batch
         prm = _cabi.IsbParams(min_cov, min_snp, min_qual, (_cabi.ISB_SKIP_LINKAGE if skip_linkage else 0) |
-                              (_cabi.ISB_PIPELINE if pipeline else 0), float(min_freq))
+                              (_cabi.ISB_PIPELINE if pipeline else 0), float(min_freq),
+                              int(rarefied_coverage) if "clonTR" in want else 0, 0, int(seed) & 0xFFFFFFFFFFFFFFFF)
         out = {}
         if "counts" in want:
             out["counts"] = np.empty((L, M, 4), dtype=np.int32)
@@ -253,6 +257,8 @@ class Engine:
             out["clonT"] = np.empty((L, M), dtype=np.float32)
         if "site_flags" in want:
             out["site_flags"] = np.empty(L, dtype=np.uint8)
+        if "clonTR" in want:
+            out["clonTR"] = np.empty((L, M), dtype=np.float32)
         snv_cap = max(1024, L // 8) if snv_cap is None else snv_cap
         ld_cap = (1 << 16) if ld_cap is None else ld_cap
         while True:
@@ -260,7 +266,7 @@ class Engine:
             ld = np.empty(ld_cap, dtype=_cabi.LD_DT) if ("ld" in want and not skip_linkage) else None
             res = _cabi.IsbResult(p(out.get("counts")), p(out.get("nmask")), p(out.get("covT")), p(out.get("clonT")),
                                   p(out.get("site_flags")), p(snv), snv_cap if snv is not None else 0, p(ld),
-                                  ld_cap if ld is not None else 0, 0, 0, 0, 0)
+                                  ld_cap if ld is not None else 0, 0, 0, 0, 0, p(out.get("clonTR")))
             rc = self._check(entry(self.ctx, C.byref(batch), C.byref(prm), C.byref(res)),
                              allow=(_cabi.ISB_ERR_CAPACITY,))
             if rc == 0:

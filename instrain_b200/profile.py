@@ -37,7 +37,8 @@ def encode_reference(seq):
 
 class ScaffoldProfile:
     """What the reference's merged ScaffoldSplitObject carries for one scaffold (profile_utilities.py:719-820):
-    raw_snp_table, raw_linkage_table, covT, clonT (+ length).  clonTR is not produced (unseeded RNG in the reference)."""
+    raw_snp_table, raw_linkage_table, covT, clonT, clonTR (+ length).  clonTR and the normalized linkage columns are
+    re-drawn quantities: unseeded in the reference, keyed by kwargs["seed"] here."""
 
     def __init__(self, scaffold, length):
         self.scaffold, self.length = scaffold, length
@@ -254,6 +255,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     min_snp = int(kwargs.get("min_snp", 20))
     window_length = int(kwargs.get("window_length", 10000))
     fdr = float(kwargs.get("fdr", 1e-6)) or 1e-6                      # 0 -> 1e-6 (controller.py:207-208)
+    rarefied_coverage = int(kwargs.get("rarefied_coverage", 50))      # argumentParser.py:168
+    seed = int(kwargs.get("seed", 0) or 0)                            # own keyword: key of the re-drawn outputs (clonTR, normalized LD)
     transfer = kwargs.get("b200_transfer") or os.environ.get("ISB_TRANSFER", "segments")
     if transfer not in ("segments", "delta", "cols"):
         raise ValueError("b200_transfer must be 'segments', 'delta' or 'cols'")
@@ -311,15 +314,18 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             fmt["reads"] = rd
         out = engine.profile_batch(dict(pair_mm=cat(batch["pair_mm"])), ref_codes, np.array(batch["splits"], np.int32),
                                    min_cov=min_cov, min_freq=min_freq, min_snp=min_snp,
-                                   want=("covT", "clonT", "nmask", "snv", "ld"), **fmt)
+                                   want=("covT", "clonT", "clonTR", "nmask", "snv", "ld"), rarefied_coverage=rarefied_coverage,
+                                   seed=seed, **fmt)
         # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
         bounds = np.append(offs, len(ref_codes)).astype(np.int32)
         if pad:                                                           # the unused leading positions: a dummy segment
             bounds = np.concatenate([[0], bounds]).astype(np.int32)
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
+        k4r = engine.scaffold_summary(out["covT"], out["clonTR"], out["nmask"], bounds) if "clonTR" in out else None
         if pad:
             k4 = k4[out["M"]:]
-        sum_tabs.append(summary.summary_table(k4, out["snv"], batch["names"], offs, out["M"]))
+            k4r = k4r[out["M"]:] if k4r is not None else None
+        sum_tabs.append(summary.summary_table(k4, out["snv"], batch["names"], offs, out["M"], rows_rarefied=k4r))
         seqs = {n: s2s[n] for n in batch["names"]}
         snp_tabs.append(tables.snv_table(out["snv"], batch["names"], offs, seqs, ref_codes=ref_codes))
         ld_tabs.append(tables.linkage_table(out["ld"], batch["names"], offs))
@@ -345,6 +351,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             levels = tables.present_levels(out["covT"][sl], out["nmask"][sl])
             sp.covT = tables.basewise(out["covT"][sl], "coverage", levels)
             sp.clonT = tables.basewise(out["clonT"][sl], "clonality", levels)
+            if "clonTR" in out:
+                sp.clonTR = tables.basewise(out["clonTR"][sl], "clonality", levels)
             res.scaffolds[name] = sp
             res.scaffold_list.append(name)
 

@@ -256,6 +256,8 @@ def store_profile(ISP_loc, bam, res, mapping_info=None, **kwargs):
     S.store("scaffold_2_mm_2_read_2_snvs", {}, "pickle", "crazy nonsense needed for linkage")
     S.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
     S.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
+    if any(p.clonTR for p in res.scaffolds.values()):
+        S.store("clonTR", {s: p.clonTR for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> rarefied position based clonality")
     for name in ("SNVs", "scaffold_info", "linkage"):                     # ProfileController.write_output (controller.py:352-360)
         S.generate(name)
     if mapping_info is not None:

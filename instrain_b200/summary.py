@@ -1,7 +1,7 @@
 """cumulative_scaffold_table from K4's exact reductions (host glue; replaces the pandas side of make_coverage_table,
 inStrain/profile/profile_utilities.py:425-506, and calc_snps, inStrain/profile/snv_utilities.py:249-272).
 
-Random columns of the reference (nucl_diversity_rarefied*, breadth_rarefied: clonTR, unseeded RNG) are emitted as NaN / 0.
+The rarefied columns (nucl_diversity_rarefied*, breadth_rarefied) come from a second K4 pass over clonTR.
 """
 import math
 
@@ -31,10 +31,13 @@ def snv_level_counts(snv, scaffold_off, n_scaffolds, M):
     return np.cumsum(out, axis=1)[:, :M]                          # ... integrated
 
 
-def summary_table(rows, snv, scaffold_names, scaffold_off, M):
-    """K4 rows (SUMMARY_DT[n_scaffolds*M]) + SNV rows -> DataFrame shaped like the reference's cumulative_scaffold_table."""
+def summary_table(rows, snv, scaffold_names, scaffold_off, M, rows_rarefied=None):
+    """K4 rows (SUMMARY_DT[n_scaffolds*M]) + SNV rows -> DataFrame shaped like the reference's cumulative_scaffold_table.
+    rows_rarefied = the K4 rows of the same scaffolds computed on clonTR instead of clonT: nucl_diversity_rarefied,
+    nucl_diversity_rarefied_median, breadth_rarefied (make_coverage_table, profile_utilities.py:474-487); NaN / 0 without."""
     n_sc = len(scaffold_names)
     rows = rows.reshape(n_sc, M)
+    rare = rows_rarefied.reshape(n_sc, M) if rows_rarefied is not None else None
     counts = snv_level_counts(snv, np.asarray(scaffold_off), n_sc, M)
     table = []
     for s in range(n_sc):
@@ -50,11 +53,14 @@ def summary_table(rows, snv, scaffold_names, scaffold_off, M):
             sem = math.sqrt(var_num / (L * (L - 1))) / math.sqrt(L) if L > 1 else float("nan")
             counted = int(r["counted"])
             sns, snvc, div, con, pop = (int(x) for x in counts[s, m])
+            n_r = int(rare[s, m]["counted"]) if rare is not None else 0
+            nd_r = 1 - float(rare[s, m]["sum_clon"]) / n_r if n_r else float("nan")
+            nd_rm = 1 - (float(rare[s, m]["clon_med_lo"]) + float(rare[s, m]["clon_med_hi"])) / 2 if n_r else float("nan")
             table.append((
                 scaffold_names[s], L, int(r["nonzero"]) / L, mean, int((int(r["cov_med_lo"]) + int(r["cov_med_hi"])) / 2.0),
                 std, sem,
                 1 - float(r["sum_clon"]) / counted if counted else float("nan"),
                 1 - (float(r["clon_med_lo"]) + float(r["clon_med_hi"])) / 2 if counted else float("nan"),
-                float("nan"), float("nan"), counted / L, 0.0, -math.exp(-0.883 * mean) + 1, div, sns, snvc, con, pop,
+                nd_r, nd_rm, counted / L, n_r / L, -math.exp(-0.883 * mean) + 1, div, sns, snvc, con, pop,
                 (counted - con) / counted if counted else 0, (counted - pop) / counted if counted else 0, m))
     return pd.DataFrame(table, columns=COLUMNS)

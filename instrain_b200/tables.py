@@ -4,7 +4,8 @@ Column names / order follow what the reference stores:
   raw_snp_table      generate_snp_table              inStrain/profile/snv_utilities.py:274-290 (+ position shift :181)
   raw_linkage_table  _calc_ld_single / _update_r2    inStrain/profile/linkage.py:138-252
   covT / clonT       shrink_basewise                 inStrain/profile/profile_utilities.py:337-350
-The reference's unseeded-random columns (r2_normalized, d_prime_normalized, clonTR) are emitted as NaN / omitted.
+The reference's resampled columns (r2_normalized, d_prime_normalized, clonTR) come from the device's counter-based
+generator (seeded: reproducible; same distribution as the reference's unseeded np.random.choice).
 """
 import numpy as np
 import pandas as pd
@@ -85,9 +86,9 @@ def cumulative_snv_table(raw):
 
 def linkage_frame(rows, scaffold_of_row, rel_a, rel_b):
     c = [rows[k].astype(np.int64) for k in ("c_AB", "c_Ab", "c_aB", "c_ab")]
-    nan = np.full(len(rows), np.nan)
     return pd.DataFrame({
-        "r2": rows["r2"], "d_prime": rows["d_prime"], "r2_normalized": nan, "d_prime_normalized": nan,
+        "r2": rows["r2"], "d_prime": rows["d_prime"], "r2_normalized": rows["r2_normalized"],
+        "d_prime_normalized": rows["d_prime_normalized"],
         "total": c[0] + c[1] + c[2] + c[3], "countAB": c[0], "countAb": c[1], "countaB": c[2], "countab": c[3],
         "allele_A": BASES[rows["allele_A"]], "allele_a": BASES[rows["allele_a"]], "allele_B": BASES[rows["allele_B"]],
         "allele_b": BASES[rows["allele_b"]], "distance": rel_b - rel_a, "position_A": rel_a, "position_B": rel_b,

@@ -17,6 +17,9 @@ LD_DT = np.dtype([("pos_a", "<i4"), ("pos_b", "<i4"), ("mm", "<i4"), ("c_AB", "<
                   ("c_aB", "<i4"), ("c_ab", "<i4"), ("allele_A", "u1"), ("allele_a", "u1"), ("allele_B", "u1"),
                   ("allele_b", "u1"), ("r2", "<f8"), ("d_prime", "<f8")])
 assert SNV_DT.itemsize == 32 and LD_DT.itemsize == 48
+# rows as the CUDA library returns them: + the two re-drawn columns (oracle/rarefied.py)
+LD_DT_FULL = np.dtype(LD_DT.descr + [("r2_normalized", "<f8"), ("d_prime_normalized", "<f8")])
+assert LD_DT_FULL.itemsize == 64
 
 CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "pop_SNV"]
 BASES = "ACTG"
@@ -133,12 +136,19 @@ def profile_mt(ev, ref_codes, lut, lut_default, splits, M=None, ref_start=0, min
 
 
 def profile_events(ev, ref_codes, lut, lut_default, splits, start=0, M=None, min_cov=5, min_freq=0.05,
-                   min_snp=20, min_qual=30, do_linkage=True):
-    """Whole hot path on one coordinate space. `ev` must be position-major (see sort_events)."""
+                   min_snp=20, min_qual=30, do_linkage=True, rarefied_coverage=50, seed=0):
+    """Whole hot path on one coordinate space. `ev` must be position-major (see sort_events).  The re-drawn outputs
+    (clonTR, r2_normalized / d_prime_normalized of the LD rows) come from oracle/rarefied.py with the given seed."""
+    from . import rarefied
     L = len(ref_codes)
     if M is None:
         M = int(ev["pair_mm"].max()) + 1 if len(ev["pair_mm"]) else 1
     counts, nmask = pileup_counts(ev, start, L, M, min_qual)
     covT, clonT, flags, snv = call_snvs(counts, nmask, ref_codes, lut, lut_default, start, min_cov, min_freq)
     ld = linkage(ev, counts, nmask, flags, splits, start, min_snp, min_qual) if do_linkage else np.zeros(0, LD_DT)
-    return dict(counts=counts, nmask=nmask, covT=covT, clonT=clonT, site_flags=flags, snv=snv, ld=ld)
+    full = np.zeros(len(ld), dtype=LD_DT_FULL)
+    for k in LD_DT.names:
+        full[k] = ld[k]
+    full["r2_normalized"], full["d_prime_normalized"] = rarefied.normalized_ld(ld, min_snp, seed)
+    return dict(counts=counts, nmask=nmask, covT=covT, clonT=clonT, site_flags=flags, snv=snv, ld=full,
+                clonTR=rarefied.clonTR(counts, nmask, rarefied_coverage, seed, start))

@@ -52,9 +52,19 @@ def assert_ld_equal(a, b, tol=1e-6):
     assert len(a) == len(b), (len(a), len(b))
     for f in ("pos_a", "pos_b", "mm", "c_AB", "c_Ab", "c_aB", "c_ab", "allele_A", "allele_a", "allele_B", "allele_b"):
         assert np.array_equal(a[f], b[f]), f
-    for f in ("r2", "d_prime"):
+    fields = ("r2", "d_prime")
+    if "r2_normalized" in (a.dtype.names or ()) and "r2_normalized" in (b.dtype.names or ()):
+        fields += ("r2_normalized", "d_prime_normalized")     # re-drawn columns: same counter-based draws on both sides
+    for f in fields:
         assert np.array_equal(np.isnan(a[f]), np.isnan(b[f])), f
         assert np.allclose(a[f], b[f], rtol=0, atol=tol, equal_nan=True), f
+
+
+def assert_clontr_equal(got, exp):
+    """Rarefied clonality (float32, NaN = unset): bit-identical to the oracle's restatement of the same draws."""
+    ok = ~np.isnan(exp)
+    assert np.array_equal(np.isnan(got), ~ok)
+    assert np.array_equal(got[ok].view(np.uint32), exp[ok].view(np.uint32))
 
 
 def basewise_digest(values, index):

@@ -61,7 +61,7 @@ def main():
     clonT = torch.empty((L, M), dtype=torch.float32, device=dev)
     flags = torch.empty(L, dtype=torch.uint8, device=dev)
     snv = torch.empty(max(1024, L // 4) * 32, dtype=torch.uint8, device=dev)
-    ld = torch.empty(max(1 << 16, L // 2) * 48, dtype=torch.uint8, device=dev)
+    ld = torch.empty(max(1 << 16, L // 2) * 64, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ev = dict(ref_pos=pos, base=base, qual=qual, read_id=rid, pair_mm=mm)
     p = _cabi.ptr
@@ -97,7 +97,7 @@ def main():
 
     def k3():
         rc = lib.isb_linkage(ctx, n, p(pos), p(base), p(qual), p(rid), npairs, p(mm), 0, L, M, 30, p(counts), p(nmask),
-                             p(flags), splits.shape[0], p(splits), 20, p(ld), ld.numel() // 48, C.byref(nrows))
+                             p(flags), splits.shape[0], p(splits), 20, p(ld), ld.numel() // 64, C.byref(nrows))
         assert rc == 0, lib.isb_last_error(ctx)
 
     ev_bytes = (10 if M > 1 else 6) * n
@@ -136,7 +136,7 @@ def main():
               flush=True)
         prm_r = _cabi.IsbParams(5, 20, 30, 0, 0.05)
         res_r = _cabi.IsbResult(p(counts_r), p(nmask_r), p(covT), p(clonT), p(flags), p(snv), snv.numel() // 32, p(ld),
-                                ld.numel() // 48, 0, 0, 0, 0)
+                                ld.numel() // 64, 0, 0, 0, 0)
 
         def full_r():
             rc = lib.isb_profile_reads(ctx, C.byref(rb), C.byref(prm_r), C.byref(res_r))
@@ -152,7 +152,7 @@ def main():
     batch = _cabi.IsbBatch(n, p(pos), p(base), p(qual), p(rid), npairs, p(mm), 0, L, p(ref), splits.shape[0], p(splits), M)
     prm = _cabi.IsbParams(5, 20, 30, 0, 0.05)
     res = _cabi.IsbResult(p(counts), p(nmask), p(covT), p(clonT), p(flags), p(snv), snv.numel() // 32, p(ld),
-                          ld.numel() // 48, 0, 0, 0, 0)
+                          ld.numel() // 64, 0, 0, 0, 0)
 
     def full():
         rc = lib.isb_profile_batch(ctx, C.byref(batch), C.byref(prm), C.byref(res))

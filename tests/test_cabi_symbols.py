@@ -37,10 +37,10 @@ def test_header_symbols_exported(lib):
 def test_abi_version_and_row_layouts(lib):
     from instrain_b200 import _cabi
     from oracle import restate
-    assert lib.isb_abi_version() == 1
-    assert _cabi.SNV_DT == restate.SNV_DT and _cabi.LD_DT == restate.LD_DT
-    assert ctypes.sizeof(_cabi.IsbBatch) == 96 and ctypes.sizeof(_cabi.IsbParams) == 24
-    assert ctypes.sizeof(_cabi.IsbResult) == 104
+    assert lib.isb_abi_version() == 2                                     # 2: + clonTR, normalized LD columns, seed
+    assert _cabi.SNV_DT == restate.SNV_DT and _cabi.LD_DT == restate.LD_DT_FULL and _cabi.LD_DT.itemsize == 64
+    assert ctypes.sizeof(_cabi.IsbBatch) == 96 and ctypes.sizeof(_cabi.IsbParams) == 40
+    assert ctypes.sizeof(_cabi.IsbResult) == 112
 
 
 def test_no_cpu_fallback_without_gpu():

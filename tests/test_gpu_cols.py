@@ -4,14 +4,14 @@ the read-major CUDA path; plus the device-side layout conversion against the hos
 import numpy as np
 import pytest
 
-from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from conftest import assert_clontr_equal, assert_ld_equal, assert_snv_equal, load_batch
 from oracle import restate, synth
 from instrain_b200 import cols, reads
 
 pytestmark = pytest.mark.gpu
 
-FULL = ("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld")
-LEAN = ("covT", "clonT", "site_flags", "snv", "ld")            # no counts / nmask: the fused kernel at M = 1
+FULL = ("counts", "nmask", "covT", "clonT", "clonTR", "site_flags", "snv", "ld")
+LEAN = ("covT", "clonT", "clonTR", "site_flags", "snv", "ld")  # no counts / nmask: the fused kernel at M = 1
 
 
 @pytest.fixture(scope="module")
@@ -40,6 +40,7 @@ def check_cols(eng, batch, null_lut, tol=1e-9, rd=None, cd=None, wants=(FULL, LE
         assert np.array_equal(np.isnan(got["clonT"]), ~ok)
         assert np.array_equal(got["clonT"][ok].view(np.uint32), exp["clonT"][ok].view(np.uint32))
         assert np.array_equal(got["site_flags"], exp["site_flags"])
+        assert_clontr_equal(got["clonTR"], exp["clonTR"])
         assert_snv_equal(got["snv"], exp["snv"])
         assert_ld_equal(got["ld"], exp["ld"], tol=tol)
     return got, exp

@@ -7,7 +7,7 @@ Bar (BASELINE.json north_star): per-position counts and SNV calls bit-exact; r2 
 import numpy as np
 import pytest
 
-from conftest import assert_basewise_matches_digest, assert_ld_equal, assert_snv_equal, load_batch
+from conftest import assert_basewise_matches_digest, assert_clontr_equal, assert_ld_equal, assert_snv_equal, load_batch
 from oracle import restate, synth
 
 pytestmark = pytest.mark.gpu
@@ -29,10 +29,11 @@ def check_batch(eng, batch, null_lut, tol=1e-9, **kw):
     exp = oracle_all(batch, null_lut, **kw)
     M = exp["counts"].shape[1]
     got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M,
-                            want=("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld"), **kw)
+                            want=("counts", "nmask", "covT", "clonT", "clonTR", "site_flags", "snv", "ld"), **kw)
     assert np.array_equal(got["counts"], exp["counts"])
     assert np.array_equal(got["nmask"], exp["nmask"])
     assert np.array_equal(got["covT"], exp["covT"])
+    assert_clontr_equal(got["clonTR"], exp["clonTR"])
     # clonality: float32 bit patterns identical (NaN = unset)
     assert np.array_equal(got["clonT"].view(np.uint32) == 0x7FC00000, np.isnan(exp["clonT"])) or \
         np.array_equal(np.isnan(got["clonT"]), np.isnan(exp["clonT"]))

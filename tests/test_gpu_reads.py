@@ -4,7 +4,7 @@ tables, and against the position-major CUDA path."""
 import numpy as np
 import pytest
 
-from conftest import assert_ld_equal, assert_snv_equal, load_batch
+from conftest import assert_clontr_equal, assert_ld_equal, assert_snv_equal, load_batch
 from oracle import restate, synth
 from instrain_b200 import reads
 
@@ -25,7 +25,8 @@ def check_reads(eng, batch, null_lut, tol=1e-9, rd=None, **kw):
     if rd is None:
         rd = reads.events_to_reads(batch, kw.get("min_qual", 30))
     got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, reads=rd,
-                            want=("counts", "nmask", "covT", "clonT", "site_flags", "snv", "ld"), **kw)
+                            want=("counts", "nmask", "covT", "clonT", "clonTR", "site_flags", "snv", "ld"), **kw)
+    assert_clontr_equal(got["clonTR"], exp["clonTR"])
     assert np.array_equal(got["counts"], exp["counts"])
     assert np.array_equal(got["nmask"], exp["nmask"])
     assert np.array_equal(got["covT"], exp["covT"])
@@ -278,10 +279,11 @@ def check_fused(eng, batch, null_lut, tol=1e-9, rd=None, nmask=False, **kw):
     assert exp["counts"].shape[1] == 1
     if rd is None:
         rd = reads.events_to_reads(batch, kw.get("min_qual", 30))
-    want = ("covT", "clonT", "site_flags", "snv", "ld") + (("nmask",) if nmask else ())
+    want = ("covT", "clonT", "clonTR", "site_flags", "snv", "ld") + (("nmask",) if nmask else ())
     n0 = eng.launch_count
     got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=1, reads=rd, want=want, **kw)
     launches = eng.launch_count - n0
+    assert_clontr_equal(got["clonTR"], exp["clonTR"])
     assert np.array_equal(got["covT"], exp["covT"])
     ok = ~np.isnan(exp["clonT"])
     assert np.array_equal(np.isnan(got["clonT"]), ~ok)
@@ -408,3 +410,33 @@ def test_fused_scratch_regrow(null_lut):
     env = dict(os.environ, ISB_K1F_SITES_INIT="16")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("skip_mm", [True, False])
+def test_redrawn_outputs_all_layouts(eng, null_lut, skip_mm):
+    """clonTR and the normalized linkage columns (re-drawn quantities: unseeded in the reference, counter-based here) with a
+    non-default seed and rarefied coverage: bit-exact against the oracle's restatement of the same draws in every input
+    layout, reproducible, and different under another seed."""
+    from instrain_b200 import cols
+    batch = synth.make_batch(30000, 70, 0.03, 31, skip_mm=skip_mm)
+    rd = reads.events_to_reads(batch)
+    cd = cols.reads_to_cols(rd, len(batch["ref_codes"]))
+    M = int(batch["pair_mm"].max()) + 1
+    exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"], rarefied_coverage=30,
+                                 seed=20260103, min_snp=12)
+    assert (~np.isnan(exp["clonTR"])).sum() > 20000 and ((exp["clonTR"] < 1) & ~np.isnan(exp["clonTR"])).sum() > 1000
+    assert (~np.isnan(exp["ld"]["r2_normalized"])).sum() > 100
+    want = ("covT", "clonT", "clonTR", "snv", "ld")
+    outs = []
+    for layout in (dict(reads=rd), dict(cols=cd), {}, dict(reads=reads.delta_reads(rd, batch["ref_codes"]))):
+        got = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want, rarefied_coverage=30, seed=20260103,
+                                min_snp=12, **layout)
+        assert_clontr_equal(got["clonTR"], exp["clonTR"])
+        assert_ld_equal(got["ld"], exp["ld"], tol=1e-12)
+        outs.append(got)
+    other = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want, rarefied_coverage=30, seed=1, min_snp=12, reads=rd)
+    drawn = ~np.isnan(exp["clonTR"]) & (exp["clonTR"] < 1)
+    assert (other["clonTR"][drawn] != exp["clonTR"][drawn]).mean() > 0.3
+    assert np.array_equal(np.isnan(other["clonTR"]), np.isnan(exp["clonTR"]))
+    none = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want, rarefied_coverage=0, reads=rd)
+    assert np.isnan(none["clonTR"]).all()

@@ -17,7 +17,7 @@ import pandas as pd
 import pytest
 
 from conftest import load_lut
-from oracle import bamio, restate, summary
+from oracle import bamio, ref_harness, restate, summary
 
 TD = "/root/reference/test/test_data/"
 BAM = TD + "N5_271_010G1_scaffold_min1000.fa-vs-N5_271_010G1.sorted.bam"
@@ -249,3 +249,67 @@ def test_oracle_equals_reference_functions_on_random_inputs(seed, cov, dens, n_f
     for mm, arr in out["clonT"].items():
         mine = got["clonT"][:, mm]
         assert np.array_equal(np.isnan(mine), np.isnan(arr)) and np.array_equal(mine[~np.isnan(arr)], arr[~np.isnan(arr)].astype(np.float32)), mm
+
+
+# ---- the re-drawn outputs: same DISTRIBUTION as the reference's own (unseeded) functions ----------------------------------
+
+def _mean_ci_overlap(a, b, z=5.0):
+    """|mean(a) - mean(b)| within z standard errors of the difference."""
+    se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+    return abs(a.mean() - b.mean()) <= z * se + 1e-12
+
+
+@pytest.mark.parametrize("counts,n", [((96, 3, 1, 0), 50), ((40, 35, 20, 5), 50), ((0, 7, 0, 3), 10), ((500, 0, 12, 0), 50),
+                                      ((25, 25, 25, 25), 30)])
+def test_rarefied_clonality_has_the_reference_distribution(counts, n):
+    """calculate_rarefied_clonality (snv_utilities.py:233-247) draws with an unseeded np.random.choice; the restatement
+    of the CUDA path's counter-based draws (oracle/rarefied.py, bit-exact with the kernels: tests/test_gpu_*.py) must have
+    the same distribution: mean and variance over 20000 sites of the same counts, and the same support."""
+    from oracle import rarefied
+    _, su, _ = ref_harness.load_reference()
+    N = 20000
+    rng_state = np.random.get_state()
+    np.random.seed(12345)
+    try:
+        ref = np.array([su.calculate_rarefied_clonality(list(counts), rarefied_coverage=n) for _ in range(N)])
+    finally:
+        np.random.set_state(rng_state)
+    c = np.zeros((N, 1, 4), np.int32)
+    c[:, 0, :] = counts
+    own = rarefied.clonTR(c, np.zeros(N, np.uint64), rarefied_coverage=n, seed=99)[:, 0].astype(np.float64)
+    assert not np.isnan(own).any()
+    assert _mean_ci_overlap(own, ref), (own.mean(), ref.mean())
+    assert _mean_ci_overlap((own - own.mean()) ** 2, (ref - ref.mean()) ** 2), (own.var(), ref.var())
+    support = lambda x: set(np.round(x * n * n).astype(np.int64))          # clonality * n^2 = sum of squared counts: integers
+    assert support(own) <= support(ref) | support(own) and len(support(own) ^ support(ref)) <= 0.2 * len(support(ref)) + 2
+    below = rarefied.clonTR(c, np.zeros(N, np.uint64), rarefied_coverage=sum(counts) + 1, seed=99)
+    assert np.isnan(below).all()                                           # set only where the coverage reaches it
+
+
+@pytest.mark.parametrize("AB,Ab,aB,ab", [(30, 5, 4, 25), (50, 0, 0, 14), (10, 10, 10, 10), (200, 3, 2, 1)])
+def test_normalized_linkage_has_the_reference_distribution(AB, Ab, aB, ab):
+    """r2_normalized / d_prime_normalized of _calc_ld_single (linkage.py:200-228: min_snp haplotypes re-drawn from the four
+    frequencies, unseeded) against the restatement of the CUDA path's draws: NaN rate, mean and variance over 20000 rows."""
+    from oracle import rarefied, restate
+    _, _, lk = ref_harness.load_reference()
+    N, min_snp = 20000, 20
+    total = AB + Ab + aB + ab
+    rng_state = np.random.get_state()
+    np.random.seed(54321)
+    try:
+        ref = [lk._calc_ld_single(min_snp, A="A", a="C", B="G", b="T", AB=AB, Ab=Ab, aB=aB, ab=ab, total=total) for _ in range(N)]
+    finally:
+        np.random.set_state(rng_state)
+    rows = np.zeros(N, dtype=restate.LD_DT)
+    rows["pos_a"] = np.arange(N)
+    rows["pos_b"] = np.arange(N) + 7
+    rows["c_AB"], rows["c_Ab"], rows["c_aB"], rows["c_ab"] = AB, Ab, aB, ab
+    r2n, dpn = rarefied.normalized_ld(rows, min_snp, seed=5)
+    for name, own in (("r2_normalized", r2n), ("d_prime_normalized", dpn)):
+        rf = np.array([r[name] for r in ref], dtype=np.float64)
+        nan_o, nan_r = np.isnan(own).mean(), np.isnan(rf).mean()
+        assert abs(nan_o - nan_r) <= 5 * np.sqrt(max(nan_r * (1 - nan_r), 1e-4) * 2 / N) + 1e-3, (name, nan_o, nan_r)
+        o, r = own[~np.isnan(own)], rf[~np.isnan(rf)]
+        if len(o) > 100 and len(r) > 100:
+            assert _mean_ci_overlap(o, r), (name, o.mean(), r.mean())
+            assert _mean_ci_overlap((o - o.mean()) ** 2, (r - r.mean()) ** 2), (name, o.var(), r.var())
