@@ -67,6 +67,10 @@ def parse():
                     help="ask for the full counts / nmask arrays (M = 1: disables the fused pileup + SNV kernels)")
     ap.add_argument("--also-layouts", type=int, default=10,
                     help="also time the column-word and event-column layouts on this many scaffolds (0 = skip; N = 1 only)")
+    ap.add_argument("--from-bam-scaffolds", type=int, default=8,
+                    help="scaffolds of the from-BAM leg (a real BAM of the workload's shape is written, then profile_bam runs on it; "
+                         "0 = skip; N = 1 only)")
+    ap.add_argument("--from-bam-L", type=int, default=250000, help="scaffold length of the from-BAM leg")
     ap.add_argument("--seg-words", type=int, default=None, help="words per segment block of the generated read-major batch (21 or 22)")
     return ap.parse_args()
 
@@ -688,6 +692,85 @@ def main():
                "host_encode": {"what": "reference-delta encoding of the slice on ONE host core (isb_reads_delta_host), outside the timed "
                                        "region: the packer threads do it while the GPU works", "positions_per_s_per_core": Ls / t_enc}}
 
+    # -------------------------------------------------------------------------------- from a BAM file on disk
+    # The whole product call, file in / SNVprofile directory out: a coordinate-sorted, indexed BAM of the workload's shape
+    # (instrain_b200/synth_bam.py writes BGZF / BAM / BAI itself) -> profile_bam: C++ read filter -> C++ packer on every
+    # host core (BGZF inflate, htslib's overlap tweak, CIGAR expansion) -> H2D -> the same kernels -> tables -> .hd5 store.
+    from_bam = None
+    if rank == 0 and world == 1 and args.from_bam_scaffolds > 0 and args.layout == "reads":
+        import shutil
+        import tempfile
+        from instrain_b200 import synth_bam
+        from instrain_b200.packer import BamPacker
+        from instrain_b200.profile import iter_batches, profile_bam
+        from instrain_b200.read_filter import filter_reads
+        tmp = tempfile.mkdtemp(prefix="isb_bench_")
+        try:
+            n_sc, cores = args.from_bam_scaffolds, host_cores()
+            path = os.path.join(tmp, "synth.bam")
+            t0 = time.time()
+            Lsc = args.from_bam_L
+            info = synth_bam.write_bam(path, Lsc, n_sc, args.cov, args.dens, SEED)
+            t_write = time.time() - t0
+            Lb = n_sc * Lsc
+            kw = dict(s2s=info["seqs"], packer_threads=cores, skip_mm_profiling=not args.mm, seed=SEED)
+            profile_bam(path, None, None, os.path.join(tmp, "warm.IS"), **kw)        # warm: CUDA context, scratch, page cache
+            t0 = time.time()
+            out = profile_bam(path, None, None, os.path.join(tmp, "run.IS"), **kw)
+            t_run = time.time() - t0
+            tm = out.result.timing
+            # the packer alone on all cores: aligned bases per second and per core
+            with BamPacker(path) as bp:
+                names = bp.ref_names
+            t0 = time.time()
+            r2m, _, _ = filter_reads(path, names)
+            t_filter = time.time() - t0
+            if not args.mm:
+                r2m = {k: set(v) for k, v in r2m.items()}
+            t0 = time.time()
+            n_bases = sum(b["n_events"] for k, b in iter_batches(path, r2m, info["seqs"], packer_threads=cores) if k == "batch")
+            t_pack = time.time() - t0
+            t0 = time.time()
+            n_bases1 = sum(b["n_events"] for k, b in iter_batches(path, r2m, info["seqs"], packer_threads=1) if k == "batch")
+            t_pack1 = time.time() - t0
+            from_bam = {"value": Lb / t_run, "unit": UNIT, "seconds": t_run, "positions": Lb, "scaffolds": n_sc, "scaffold_len": Lsc,
+                        "coverage": args.cov, "bam_bytes": info["bytes"],
+                        "reads": info["n_reads"], "aligned_bases": info["aligned_bases"], "host_threads": cores,
+                        "what": "profile_bam(bam, Fdb=None, sR2M=None, ISP_loc, packer_threads=%d): file in, SNVprofile directory out "
+                                "(read filter + mapping_info, packer, engine, tables, .hd5 store)" % cores,
+                        "breakdown_s": {"read_filter_and_report": tm.get("read_filter_s"), "pack_plus_engine_plus_tables": tm.get("profile_scaffolds_s"),
+                                        "engine_calls": tm.get("engine_s"), "store": tm.get("store_s")},
+                        "gpu_idle_fraction": 1.0 - tm.get("engine_s", 0.0) / t_run,
+                        "packer": {"aligned_bases_per_s_all_threads": n_bases / t_pack, "aligned_bases_per_s_one_thread": n_bases1 / t_pack1,
+                                   "per_core_at_%d_threads" % cores: n_bases / t_pack / cores, "seconds_all_threads": t_pack,
+                                   "read_filter_s_one_thread": t_filter},
+                        "snv_rows": len(out.result.raw_snp_table), "linkage_rows": len(out.result.raw_linkage_table),
+                        "bam_write_s_not_timed": t_write}
+            if not args.no_cpu_baseline:                             # the oracle port on the same file's events (checker / baseline)
+                evs, off, npair = [], 0, 0
+                with BamPacker(path) as bp:
+                    while True:
+                        tid = bp.peek_tid()
+                        if tid < 0:
+                            break
+                        nm_ = bp.ref_names[tid]
+                        ev = bp.pack_scaffold(tid, r2m.get(nm_, {}), pos_offset=off, pair_id_offset=npair)
+                        evs.append(ev)
+                        off += Lsc
+                        npair += len(ev["pair_mm"])
+                hb = {k: np.concatenate([e[k] for e in evs]) for k in ("ref_pos", "base", "qual", "read_id", "pair_mm")}
+                from instrain_b200.profile import encode_reference
+                hb["ref_codes"] = np.concatenate([encode_reference(info["seqs"][n_]) for n_ in info["names"]])
+                hb["splits"] = synth.batch_splits(Lsc, n_sc)
+                t0 = time.time()
+                rows_c = cpu_oracle_pass(hb, lut, dflt, cores)
+                t_cpu = time.time() - t0
+                from_bam["cpu_port_same_bam"] = {"value": Lb / t_cpu, "unit": UNIT, "cores": cores, "seconds_compute_only": t_cpu,
+                                                 "rows": list(rows_c), "note": "oracle/oracle.c on the events the C++ packer makes of the same "
+                                                                               "BAM; BAM decoding not included"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
     # -------------------------------------------------------------------------------- CPU baseline (oracle port) beside
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -710,7 +793,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
             "dtype": "int32 counts / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "sustained": sustained,
-            "weak_scaling": weak, "gather_bytes_per_step": gather_bytes, "other_layouts": other, "rows": rows_out,
+            "weak_scaling": weak, "gather_bytes_per_step": gather_bytes, "from_bam": from_bam, "other_layouts": other, "rows": rows_out,
             "setup_s": round(t_gen, 1)}))
     if world > 1:
         dist.destroy_process_group()

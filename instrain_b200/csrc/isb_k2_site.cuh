@@ -32,9 +32,11 @@ __host__ __device__ __forceinline__ uint64_t isb_mix64(uint64_t z)
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
     return z ^ (z >> 31);
 }
-__host__ __device__ __forceinline__ uint64_t isb_rand64(uint64_t seed, uint64_t tag, uint64_t a, uint64_t b, uint64_t k)
+#define ISB_RNG_K3 0x8cb92ba72f3d8dd7ull
+// word k of the site keyed (a, b) = isb_mix64(isb_rng_base(seed, tag, a, b) ^ k * K3); the base is computed once per site
+__host__ __device__ __forceinline__ uint64_t isb_rng_base(uint64_t seed, uint64_t tag, uint64_t a, uint64_t b)
 {
-    return isb_mix64(isb_mix64(seed + tag) ^ (a * 0x9e3779b97f4a7c15ull) ^ (b * 0xd1b54a32d192ed03ull) ^ (k * 0x8cb92ba72f3d8dd7ull));
+    return isb_mix64(seed + tag) ^ (a * 0x9e3779b97f4a7c15ull) ^ (b * 0xd1b54a32d192ed03ull);
 }
 
 // calculate_rarefied_clonality (snv_utilities.py:233-247): n bases drawn with replacement from the frequencies C / T, then
@@ -45,8 +47,10 @@ __device__ __forceinline__ float k2_rarefied_clon(const int (&C)[4], int T, int 
     if (mx == T) return 1.0f;                                         // every draw lands on the one base: (n/n)^2 + 0 + 0 + 0
     const uint32_t c0 = (uint32_t)C[0], c01 = c0 + (uint32_t)C[1], c012 = c01 + (uint32_t)C[2];
     int r0 = 0, r01 = 0, r012 = 0;                                    // draws below each cumulative bound
-    for (int i = 0; i < n; i += 2) {
-        const uint64_t h = isb_rand64(seed, ISB_RNG_TAG_CLONR, (uint64_t)pos, (uint64_t)mm, (uint64_t)(i >> 1));
+    const uint64_t rb = isb_rng_base(seed, ISB_RNG_TAG_CLONR, (uint64_t)pos, (uint64_t)mm);
+    uint64_t kk = 0;                                                  // k * K3
+    for (int i = 0; i < n; i += 2, kk += ISB_RNG_K3) {
+        const uint64_t h = isb_mix64(rb ^ kk);
         uint32_t idx = __umulhi((uint32_t)h, (uint32_t)T);
         r0 += idx < c0; r01 += idx < c01; r012 += idx < c012;
         if (i + 1 < n) {

@@ -504,8 +504,10 @@ __device__ __forceinline__ void k3_emit(const k3_args &a, int32_t p1, int32_t p2
         const uint32_t b1 = (uint32_t)cAB, b2 = b1 + (uint32_t)cAb, b3 = b2 + (uint32_t)caB;
         const uint64_t key = ((uint64_t)(uint32_t)(p1 + a.start) << 32) | (uint64_t)(uint32_t)(p2 + a.start);
         int n1 = 0, n2 = 0, n3 = 0;
-        for (int i = 0; i < a.min_snp; i += 2) {
-            const uint64_t h = isb_rand64(a.seed, ISB_RNG_TAG_LD, key, (uint64_t)m, (uint64_t)(i >> 1));
+        const uint64_t rb = isb_rng_base(a.seed, ISB_RNG_TAG_LD, key, (uint64_t)m);
+        uint64_t kk = 0;
+        for (int i = 0; i < a.min_snp; i += 2, kk += ISB_RNG_K3) {
+            const uint64_t h = isb_mix64(rb ^ kk);
             uint32_t idx = __umulhi((uint32_t)h, (uint32_t)total);
             n1 += idx < b1; n2 += idx < b2; n3 += idx < b3;
             if (i + 1 < a.min_snp) {

@@ -312,6 +312,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             fmt["cols"] = reads_to_cols(rd, len(ref_codes))
         else:
             fmt["reads"] = rd
+        t_e = time.time()
         out = engine.profile_batch(dict(pair_mm=cat(batch["pair_mm"])), ref_codes, np.array(batch["splits"], np.int32),
                                    min_cov=min_cov, min_freq=min_freq, min_snp=min_snp,
                                    want=("covT", "clonT", "clonTR", "nmask", "snv", "ld"), rarefied_coverage=rarefied_coverage,
@@ -322,6 +323,9 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             bounds = np.concatenate([[0], bounds]).astype(np.int32)
         k4 = engine.scaffold_summary(out["covT"], out["clonT"], out["nmask"], bounds)
         k4r = engine.scaffold_summary(out["covT"], out["clonTR"], out["nmask"], bounds) if "clonTR" in out else None
+        res.timing["engine_s"] = res.timing.get("engine_s", 0.0) + time.time() - t_e      # host<->device copies + kernels
+        res.timing["positions"] = res.timing.get("positions", 0) + len(ref_codes)
+        res.timing["aligned_bases"] = res.timing.get("aligned_bases", 0) + int(batch["n_events"])
         if pad:
             k4 = k4[out["M"]:]
             k4r = k4r[out["M"]:] if k4r is not None else None
@@ -392,6 +396,7 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     the bare ProfileResult is returned."""
     s2s = kwargs.pop("s2s", None)
     report = None
+    t_start = time.time()
     if s2s is None:
         raise ValueError("profile_bam needs kwargs['s2s'] (scaffold -> sequence), as ProfileController.run_profile passes it")
     if sR2M is None:
@@ -412,14 +417,19 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
             report = _mapping_info(bam, names, **fkw)
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
+    t_filter = time.time() - t_start
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
+    res.timing["read_filter_s"] = t_filter
     # the SNVprofile directory at ISP_loc (gen_snv_profile, profile_utilities.py:670-706), written natively:
     # inStrain.SNVprofile.SNVprofile(ISP_loc) of the reference opens it unchanged
     if ISP_loc is None or not kwargs.get("store", True):
         return res
     from .store import store_profile
     fdef = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)    # this shim's filter defaults
+    t_store = time.time()
     S = store_profile(ISP_loc, bam, res, mapping_info=report, **{k: kwargs.get(k, v) for k, v in fdef.items()})
+    res.timing["store_s"] = time.time() - t_store
+    res.timing["total_s"] = time.time() - t_start
     res.store = S
     return _as_snvprofile(S, res)
 

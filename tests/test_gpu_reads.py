@@ -424,7 +424,7 @@ def test_redrawn_outputs_all_layouts(eng, null_lut, skip_mm):
     M = int(batch["pair_mm"].max()) + 1
     exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"], rarefied_coverage=30,
                                  seed=20260103, min_snp=12)
-    assert (~np.isnan(exp["clonTR"])).sum() > 20000 and ((exp["clonTR"] < 1) & ~np.isnan(exp["clonTR"])).sum() > 1000
+    assert (~np.isnan(exp["clonTR"])).sum() > 20000 and ((exp["clonTR"] < 1) & ~np.isnan(exp["clonTR"])).sum() > 500
     assert (~np.isnan(exp["ld"]["r2_normalized"])).sum() > 100
     want = ("covT", "clonT", "clonTR", "snv", "ld")
     outs = []
