@@ -58,6 +58,7 @@ def parse():
                     help="N > 1: shard the same --scaffolds over the ranks (strong) or give every rank its own (weak)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling line")
     ap.add_argument("--e2e-scaffolds", type=int, default=4, help="scaffolds in the bounded host-buffer (e2e) slice per rank")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configurations whose one scaffold is too large for a bounded slice)")
     ap.add_argument("--cpu-scaffolds", type=int, default=1, help="scaffolds in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained leg in seconds (0 = skip)")
@@ -586,7 +587,7 @@ def main():
     # format of the same BAM-order segments), isb_profile_reads_delta (H2D + K0d + the same K1f / linkage kernels + D2H of
     # every result table), pinned host tables out.  Every rank runs its own slice; the job's e2e is the sum over ranks.
     e2e = None
-    if args.layout == "reads":
+    if args.layout == "reads" and not args.no_e2e:
         from instrain_b200.reads import delta_reads_host
         n_sc = max(1, min(args.e2e_scaffolds, d["n_scaffolds"]))
         hs = synth.reads_to_host(d, 0, n_sc)

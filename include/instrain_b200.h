@@ -505,6 +505,9 @@ void isb_reads_free(void *reads);
  * order + summed NM) are what isb_pack_scaffold takes as R2M.  tally[6] = pass_pairing_filter, pass_min_read_ani,
  * pass_max_insert, pass_min_insert, pass_min_mapq, filtered_pairs (the mapping_info columns). */
 void *isb_filter_open(const char *bam_path);
+/* The same pass on n_threads host threads, one reader each, scaffolds taken from a shared counter: first_voffset[tid] = BGZF
+ * virtual offset of the scaffold's first alignment (from the .bai index; 0 = no alignments).  Identical tables. */
+void *isb_filter_open_mt(const char *bam_path, int n_threads, int n_refs, const uint64_t *first_voffset);
 int64_t isb_filter_apply(void *filter, double min_read_ani, int min_mapq, double max_insert_relative, int min_insert);
 /* All pairing filters of the reference + priority reads (paired_read_filter, filter_reads.py:471-532): pairing_mode 0 =
  * paired_only (isb_filter_apply), 1 = non_discordant, 2 = all_reads (mates on two scaffolds are merged: summed NM, insert

@@ -47,7 +47,7 @@ EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "is
            "isb_pack_scaffold_reads", "isb_reads_segs", "isb_reads_stream_words", "isb_reads_pairs", "isb_reads_n_events",
            "isb_reads_nev", "isb_reads_max_len", "isb_reads_reads_seen", "isb_reads_reads_packed", "isb_reads_copy",
            "isb_reads_free",
-           "isb_filter_open", "isb_filter_apply", "isb_filter_apply2", "isb_filter_tally2", "isb_filter_n_refs", "isb_filter_max_insert", "isb_filter_tally", "isb_filter_stats", "isb_filter_stats2",
+           "isb_filter_open", "isb_filter_open_mt", "isb_filter_apply", "isb_filter_apply2", "isb_filter_tally2", "isb_filter_n_refs", "isb_filter_max_insert", "isb_filter_tally", "isb_filter_stats", "isb_filter_stats2",
            "isb_filter_n_pairs", "isb_filter_names_bytes", "isb_filter_copy", "isb_filter_free"]
 
 

@@ -16,6 +16,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -665,6 +668,54 @@ extern "C" {
 static thread_local char g_host_err[320] = "";
 const char *isb_host_last_error(void) { return g_host_err; }
 
+// one alignment record (the reader's pending record) into its scaffold's pair table: get_paired_reads (filter_reads.py:885-956)
+static void filter_consume(Bam *b, ScaffoldPairs *spp)
+{
+    const uint8_t *p = b->pending.data();
+    const uint8_t *end = p + b->pending.size();
+    b->has_pending = false;
+    int32_t core[8];
+    memcpy(core, p, 32);
+    const int l_read_name = (uint32_t)core[2] & 0xff;
+    const int mapq = ((uint32_t)core[2] >> 8) & 0xff;
+    const int n_cigar = (uint32_t)core[3] & 0xffff, flag = (uint32_t)core[3] >> 16;
+    const int l_seq = core[4];
+    if (flag & 0x4 || n_cigar == 0) return;
+    const uint8_t *q = p + 32 + l_read_name;
+    int64_t pos = core[1], first = -1, last = -1, qlen = 0;
+    for (int c = 0; c < n_cigar; ++c) {
+        uint32_t cg; memcpy(&cg, q + 4 * c, 4);
+        const int op = cg & 0xf;
+        const int64_t len = cg >> 4;
+        if (is_match(op)) { if (first < 0) first = pos; last = pos + len - 1; pos += len; qlen += len; }
+        else if (op == OP_D || op == OP_N) pos += len;
+        else if (op == OP_I || op == OP_S) qlen += len;
+    }
+    if (first < 0) return;                                      // get_reference_positions() == []
+    const uint8_t *tags = q + 4 * n_cigar + ((l_seq + 1) >> 1) + l_seq;
+    const int nm = nm_tag(tags, end);
+    ScaffoldPairs &sp = *spp;
+    std::string name((const char *)p + 32, l_read_name > 0 ? l_read_name - 1 : 0);
+    auto it = sp.index.find(name);
+    if (it == sp.index.end()) {
+        PairInfo pi;
+        pi.nm = nm; pi.insert = -1; pi.mapq = mapq; pi.length = qlen; pi.reads = 1;
+        pi.first = (int32_t)first; pi.last = (int32_t)last;
+        sp.index.emplace(name, (int32_t)sp.info.size());
+        sp.names.push_back(std::move(name));
+        sp.info.push_back(pi);
+    } else {
+        PairInfo &pi = sp.info[it->second];
+        pi.nm += nm;
+        pi.reads += 1;
+        pi.length += qlen;
+        if (mapq > pi.mapq) pi.mapq = mapq;
+        if (pi.reads == 2) pi.insert = last > pi.first ? last - pi.first : (int64_t)pi.last - first;
+        else pi.insert = -1;
+        pi.first = pi.last = 0;
+    }
+}
+
 // Pass over the whole BAM; returns a filter handle (NULL on failure: isb_host_last_error() says why).
 void *isb_filter_open(const char *bam_path)
 {
@@ -677,49 +728,7 @@ void *isb_filter_open(const char *bam_path)
     for (;;) {
         const int t = isb_bam_peek_tid(b);
         if (t < 0) break;
-        const uint8_t *p = b->pending.data();
-        const uint8_t *end = p + b->pending.size();
-        b->has_pending = false;
-        int32_t core[8];
-        memcpy(core, p, 32);
-        const int l_read_name = (uint32_t)core[2] & 0xff;
-        const int mapq = ((uint32_t)core[2] >> 8) & 0xff;
-        const int n_cigar = (uint32_t)core[3] & 0xffff, flag = (uint32_t)core[3] >> 16;
-        const int l_seq = core[4];
-        if (flag & 0x4 || n_cigar == 0) continue;
-        const uint8_t *q = p + 32 + l_read_name;
-        int64_t pos = core[1], first = -1, last = -1, qlen = 0;
-        for (int c = 0; c < n_cigar; ++c) {
-            uint32_t cg; memcpy(&cg, q + 4 * c, 4);
-            const int op = cg & 0xf;
-            const int64_t len = cg >> 4;
-            if (is_match(op)) { if (first < 0) first = pos; last = pos + len - 1; pos += len; qlen += len; }
-            else if (op == OP_D || op == OP_N) pos += len;
-            else if (op == OP_I || op == OP_S) qlen += len;
-        }
-        if (first < 0) continue;                                      // get_reference_positions() == []
-        const uint8_t *tags = q + 4 * n_cigar + ((l_seq + 1) >> 1) + l_seq;
-        const int nm = nm_tag(tags, end);
-        ScaffoldPairs &sp = f->sc[t];
-        std::string name((const char *)p + 32, l_read_name > 0 ? l_read_name - 1 : 0);
-        auto it = sp.index.find(name);
-        if (it == sp.index.end()) {
-            PairInfo pi;
-            pi.nm = nm; pi.insert = -1; pi.mapq = mapq; pi.length = qlen; pi.reads = 1;
-            pi.first = (int32_t)first; pi.last = (int32_t)last;
-            sp.index.emplace(name, (int32_t)sp.info.size());
-            sp.names.push_back(std::move(name));
-            sp.info.push_back(pi);
-        } else {
-            PairInfo &pi = sp.info[it->second];
-            pi.nm += nm;
-            pi.reads += 1;
-            pi.length += qlen;
-            if (mapq > pi.mapq) pi.mapq = mapq;
-            if (pi.reads == 2) pi.insert = last > pi.first ? last - pi.first : (int64_t)pi.last - first;
-            else pi.insert = -1;
-            pi.first = pi.last = 0;
-        }
+        filter_consume(b, &f->sc[t]);
     }
     if (b->bad) {                                                 // a partial pass must not look like a complete one
         snprintf(g_host_err, sizeof(g_host_err), "%s: %s", bam_path, b->err);
@@ -728,6 +737,55 @@ void *isb_filter_open(const char *bam_path)
         return nullptr;
     }
     isb_bam_close(b);
+    return f;
+}
+
+// The same pass on n_threads host threads: scaffolds are independent until the thresholds are applied, so every thread
+// owns a reader, takes the next scaffold with alignments (first_voffset[tid] = BGZF virtual offset of its first record from
+// the .bai index, 0 = none) and fills that scaffold's pair table.  Identical tables to isb_filter_open.
+void *isb_filter_open_mt(const char *bam_path, int n_threads, int n_refs, const uint64_t *first_voffset)
+{
+    g_host_err[0] = 0;
+    if (n_threads <= 1 || !first_voffset) return isb_filter_open(bam_path);
+    Bam *b0 = (Bam *)isb_bam_open(bam_path);
+    if (!b0) { snprintf(g_host_err, sizeof(g_host_err), "cannot open BAM %s", bam_path); return nullptr; }
+    if ((int)b0->ref_names.size() != n_refs) {
+        snprintf(g_host_err, sizeof(g_host_err), "%s: index lists %d references, the header %d", bam_path, n_refs, (int)b0->ref_names.size());
+        isb_bam_close(b0);
+        return nullptr;
+    }
+    Filter *f = new Filter();
+    f->ref_names = b0->ref_names;
+    f->sc.resize(b0->ref_names.size());
+    isb_bam_close(b0);
+    std::atomic<int> next(0);
+    std::mutex err_mu;
+    std::string err;
+    auto work = [&]() {
+        Bam *b = (Bam *)isb_bam_open(bam_path);
+        if (!b) { std::lock_guard<std::mutex> g(err_mu); err = "cannot open BAM"; return; }
+        for (;;) {
+            const int tid = next.fetch_add(1);
+            if (tid >= n_refs) break;
+            if (!first_voffset[tid]) continue;
+            if (isb_bam_seek(b, first_voffset[tid]) != 0) { std::lock_guard<std::mutex> g(err_mu); err = "seek failed"; break; }
+            for (;;) {
+                const int t = isb_bam_peek_tid(b);
+                if (t != tid) break;                              // next scaffold, unmapped tail, end of file or an error
+                filter_consume(b, &f->sc[tid]);
+            }
+            if (b->bad) { std::lock_guard<std::mutex> g(err_mu); err = b->err; break; }
+        }
+        isb_bam_close(b);
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    if (!err.empty()) {
+        snprintf(g_host_err, sizeof(g_host_err), "%s: %s", bam_path, err.c_str());
+        delete f;
+        return nullptr;
+    }
     return f;
 }
 

@@ -47,9 +47,10 @@
 #ifndef K1F_STAGE_IT
 #define K1F_STAGE_IT 4                 // segment-table elements per thread and staging pass
 #endif
-#define K1F_SEG_CAP_MAX 1536           // segments staged per chunk at most (12 B each in the fused kernel)
+#define K1F_SEG_CAP_MAX 6144           // segments staged per chunk at most (8 B each: one chunk per tile up to ~700x coverage)
 #define K1F_TILE4 (256 + 32)           // count quads of a warp's 256 positions + one pad quad per 8 positions
-#define K1F_CODE_IDS 512               // pair-id window (ids) of a site the ballot row builder handles; wider ones: atomics
+#define K1F_CODE_IDS_MIN 512           // pair-id window (ids) of a site the ballot row builder handles at least; sized per batch
+#define K1F_CODE_IDS_MAX 4096          // from the pair density (k1f_args.code_ids); wider windows: atomics
 #ifndef K1F_MINB
 #define K1F_MINB 7                     // __launch_bounds__ min blocks per SM of the M = 1 kernels (<= 73 registers; ~32 KB shared)
 #endif
@@ -62,6 +63,7 @@ struct k1f_args {
     int32_t start, L;
     int M;
     int seg_cap;                       // segments staged per chunk
+    int code_ids;                      // ids of the per-warp "pair id -> allele" byte map (fused linkage front end)
     int32_t *counts;
     unsigned int *d_err;
     // fused SNV call (M = 1)
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: sites per warp, offsets, slot base
     uint16_t *s_site = reinterpret_cast<uint16_t *>(s_misc + 16);         // [K1F_WARPS][256]: position in the warp | bases << 8
     uint8_t *s_q = reinterpret_cast<uint8_t *>(s_site + K1F_WARPS * 256); // [K1F_WARPS][256]: positions for the general path
-    uint8_t *s_code = s_q + K1F_WARPS * 256;                              // [K1F_WARPS][K1F_CODE_IDS]: pair id -> allele code of a site
+    uint8_t *s_code = s_q + K1F_WARPS * 256;                              // [K1F_WARPS][a.code_ids]: pair id -> allele code of a site
 
     const int t = threadIdx.x;
     const int lane = t & 31, wib = t >> 5;
@@ -643,14 +645,14 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 }
                 __syncwarp();
             };
-            if (m.nw * 32 <= K1F_CODE_IDS) {
+            if (m.nw * 32 <= a.code_ids) {
                 // Bit rows by BALLOT.  The site's entries are scattered into a byte map "pair id -> allele code" (ids are
                 // distinct unless a pair entered the site twice: plain stores); then lane l owns bit l of every row word:
                 // word w of the `any` row is ballot(code[32 w + l] != 0), word w of allele row r is ballot(code == r's
                 // base).  ~20 instructions per row word instead of a REDUX / shuffle round per (word, allele) and 32
                 // candidates.  A pair seen twice (htslib's overlap quirk) shows up as fewer set bits than entries: then the
                 // exact slow path rebuilds the rows with the multiplicity planes.
-                uint8_t *code = s_code + wib * K1F_CODE_IDS;
+                uint8_t *code = s_code + wib * a.code_ids;
                 uint32_t *code4 = reinterpret_cast<uint32_t *>(code);
                 for (int i = lane; i < m.nw * 8; i += 32) code4[i] = 0u;
                 __syncwarp();
@@ -713,13 +715,13 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 
-static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
+static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg, int code_ids = 0)
 {
     size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
     if (fuse)
-        b += 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 + K1F_WARPS * K1F_CODE_IDS;
+        b += 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 + (size_t)K1F_WARPS * code_ids;
     return b;
 }
 
@@ -846,7 +848,14 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         ts.site_pos = a.site_pos; ts.meta = a.meta; ts.row_off = a.row_off; ts.has2 = a.has2; ts.site_counts = a.site_counts;
         ts.rows = a.rows;
     }
-    const size_t smem = k1f_smem_bytes(seg_cap, true, true, 0);
+    // pair-id window of a site ~ the pairs whose first mate starts within one fragment length before it: sized from the
+    // pair density with headroom, so that the ballot row builder (not the atomic fallback) serves deep coverage too
+    int64_t ids = (int64_t)((double)n_pairs / (L > 0 ? L : 1) * 700.0 * 1.5) + 64;
+    ids = (ids + 255) / 256 * 256;
+    if (ids < K1F_CODE_IDS_MIN) ids = K1F_CODE_IDS_MIN;
+    if (ids > K1F_CODE_IDS_MAX) ids = K1F_CODE_IDS_MAX;
+    a.code_ids = (int)ids;
+    const size_t smem = k1f_smem_bytes(seg_cap, true, true, 0, a.code_ids);
     static bool attr[64] = {false};
     if (!attr[ctx->device & 63])
         ISB_CUDA(cudaFuncSetAttribute(k1f_pileup<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -411,10 +411,8 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
         if pr is not None and not isinstance(pr, (set, list, tuple)):      # the CLI hands a file name (argumentParser.py:95-97)
             from .read_filter import load_priority_reads
             pr = load_priority_reads(pr)
-        sR2M, _, _ = filter_reads(bam, names, priority_reads=pr or (), **fkw)
-        if fkw.get("pairing_filter", "paired_only") == "paired_only" and not pr:
-            from .read_filter import mapping_info as _mapping_info
-            report = _mapping_info(bam, names, **fkw)
+        sR2M, _, _, report = filter_reads(bam, names, priority_reads=pr or (), with_report=True,      # one pass: sR2M + mapping_info
+                                          threads=int(kwargs.get("packer_threads", 1) or 1), **fkw)
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
     t_filter = time.time() - t_start

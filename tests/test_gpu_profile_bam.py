@@ -39,6 +39,7 @@ def test_profile_bam_matches_reference_goldens(tmp_path):
     isp = str(tmp_path / "subset.IS")
     res = profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, rdic, isp, s2s=seqs,
                       min_cov=5, min_freq=0.05, min_snp=20, window_length=10000)
+    res = getattr(res, "result", res)          # the on-disk object carries the in-memory tables as .result
     assert sorted(res.scaffold_list) == sorted(rdic)
     g_snv, g_ld = golden_tables(set(rdic))
     key = ["scaffold", "position", "mm"]
@@ -99,6 +100,7 @@ def test_profile_bam_tiny_scaffold_vs_reference_functions(tmp_path):
     name = fx["scaffold"]
     res = profile_bam(os.path.join(GOLDEN, "small_scaffold.bam"), None, {name: fx["r2m"]}, str(tmp_path / "tiny.IS"),
                       s2s={name: fx["seq"]}, min_cov=5, min_freq=0.05, min_snp=20)
+    res = getattr(res, "result", res)          # the on-disk object carries the in-memory tables as .result
     assert res.scaffold_list == [name] and not res.failures
     exp = pd.DataFrame(fx["snp"]).sort_values(["position", "mm"]).reset_index(drop=True)
     got = res.raw_snp_table.sort_values(["position", "mm"]).reset_index(drop=True)

@@ -154,6 +154,7 @@ def test_profile_bam_runs_its_own_read_filter_and_reports_it(tmp_path, monkeypat
     bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
     isp = str(tmp_path / "own_filter.IS")
     res = P.profile_bam(bam, None, None, isp, s2s=seqs, min_read_ani=0.95)
+    res = getattr(res, "result", res)          # the on-disk object carries the in-memory tables as .result
     assert not res.failures and len(res.raw_snp_table) > 1000
     S = SNVprofileStore(isp)
     mi = S.get("mapping_info")

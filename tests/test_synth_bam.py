@@ -99,3 +99,17 @@ def test_profile_bam_on_the_written_bam(bam, tmp_path, monkeypatch):
         n_ld += len(l)
     assert n_snv > 500 and n_ld > 500
     assert os.path.exists(str(tmp_path / "s.IS" / "output" / "s.IS_SNVs.tsv"))
+
+
+def test_threaded_read_filter_equals_the_sequential_pass(bam):
+    """isb_filter_open_mt (one reader per host thread, scaffolds through the .bai index) gives the same sR2M, tallies, max
+    insert and mapping_info report as the sequential pass, on the synthetic file and on the bundled BAM subset."""
+    from conftest import GOLDEN
+    from instrain_b200.packer import BamPacker
+    from instrain_b200.read_filter import filter_reads
+    for path in (bam[0], os.path.join(GOLDEN, "c1_G1_subset.bam")):
+        with BamPacker(path) as bp:
+            names = bp.ref_names
+        a = filter_reads(path, names, with_report=True)
+        b = filter_reads(path, names, with_report=True, threads=3)
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3].equals(b[3]) and len(a[0]) > 0
