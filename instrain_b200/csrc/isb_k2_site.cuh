@@ -20,23 +20,60 @@ __device__ __forceinline__ double k2_quot(double c, double s, double rcp)
 
 // ---- counter-based random numbers for the two resampled outputs (clonTR, normalized linkage) -----------------------------
 // The reference draws them with an unseeded np.random.choice (snv_utilities.py:241, linkage.py:200), so its own tests drop
-// those columns before comparing.  Here every draw is a pure function of (seed, stream tag, site key, draw index): word k
-// of a site = mix64(mix64(seed + tag) ^ a * K1 ^ b * K2 ^ k * K3) (splitmix64's finaliser), two 32-bit draws per word, a
-// draw u picks the category of index floor(u * total / 2^32) of the cumulative counts.  Reproducible, identical in every
-// input layout, restated in numpy by the test oracle for bit-exact parity tests; same distribution as the reference's.
+// those columns before comparing.  Here every random word is a pure function of (seed, stream tag, site key, word index):
+// word k of a site = mix64(mix64(seed + tag) ^ a * K1 ^ b * K2 ^ k * K3) (splitmix64's finaliser).  Reproducible, identical in
+// every input layout, restated in numpy by the test oracle for bit-exact parity tests; same distribution as the reference's.
+//
+// n draws with replacement from 4 categories with counts c[] (total T) = a multinomial, sampled BIT-SLICED: the n trials are
+// the bit lanes of one 64-bit word.  Categories are split off one after the other (category i against the rest: a
+// binomial with p = c_i / remaining total); a trial compares a lazily generated uniform with p from the most significant
+// bit down -- one random word decides that bit for all trials at once, and a trial is decided as soon as its bit differs
+// from p's (success iff p has the 1).  Half of the undecided trials are decided per word, so ~log2(n) + 1.3 words serve all
+// n trials of a stage (7 for n = 50) instead of one word per two draws; p is taken to 32 bits (the last non-empty category
+// takes what remains: exact totals).
 #define ISB_RNG_TAG_CLONR 0x636c6f6e54520001ull
 #define ISB_RNG_TAG_LD 0x6c646e6f726d0002ull
+#define ISB_RNG_K3 0x8cb92ba72f3d8dd7ull
+#define ISB_RNG_K4 0xa0761d6478bd642full
 __host__ __device__ __forceinline__ uint64_t isb_mix64(uint64_t z)
 {
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
     return z ^ (z >> 31);
 }
-#define ISB_RNG_K3 0x8cb92ba72f3d8dd7ull
 // word k of the site keyed (a, b) = isb_mix64(isb_rng_base(seed, tag, a, b) ^ k * K3); the base is computed once per site
 __host__ __device__ __forceinline__ uint64_t isb_rng_base(uint64_t seed, uint64_t tag, uint64_t a, uint64_t b)
 {
     return isb_mix64(seed + tag) ^ (a * 0x9e3779b97f4a7c15ull) ^ (b * 0xd1b54a32d192ed03ull);
+}
+
+// r[i] = number of the n draws that fall into category i (sum = n).  rb = isb_rng_base of the site.
+__device__ __forceinline__ void isb_redraw4(const int (&c)[4], int T, int n, uint64_t rb, int (&r)[4])
+{
+    r[0] = r[1] = r[2] = r[3] = 0;
+    for (int q = 0; q * 64 < n; ++q) {                                // 64 trials per chunk (n = 50, 20: one chunk)
+        const int nt = min(64, n - q * 64);
+        uint64_t left = nt == 64 ? ~0ull : ((1ull << nt) - 1ull);     // trials not yet assigned to a category
+        const uint64_t base = rb ^ ((uint64_t)q * ISB_RNG_K4);
+        uint64_t kk = 0;                                              // word index * K3
+        int rem = T;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (c[i] == 0 || left == 0ull) continue;
+            if (c[i] == rem) { r[i] += __popcll(left); left = 0ull; continue; }     // the last non-empty category: all that remain
+            const uint32_t P = (uint32_t)(unsigned long long)__dmul_rn(__ddiv_rn((double)c[i], (double)rem), 4294967296.0);
+            uint64_t und = left, hit = 0ull;
+            for (int b = 31; b >= 0 && und != 0ull; --b) {
+                const uint64_t W = isb_mix64(base ^ kk);
+                kk += ISB_RNG_K3;
+                if ((P >> b) & 1u) { hit |= ~W & und; und &= W; }    // p's bit is 1: a 0 bit of the uniform is below p
+                else und &= ~W;                                       // p's bit is 0: a 1 bit of the uniform is above p
+            }
+            r[i] += __popcll(hit);
+            left &= ~hit;
+            rem -= c[i];
+        }
+    }
 }
 
 // calculate_rarefied_clonality (snv_utilities.py:233-247): n bases drawn with replacement from the frequencies C / T, then
@@ -45,22 +82,11 @@ __device__ __forceinline__ float k2_rarefied_clon(const int (&C)[4], int T, int 
 {
     const int mx = max(max(C[0], C[1]), max(C[2], C[3]));
     if (mx == T) return 1.0f;                                         // every draw lands on the one base: (n/n)^2 + 0 + 0 + 0
-    const uint32_t c0 = (uint32_t)C[0], c01 = c0 + (uint32_t)C[1], c012 = c01 + (uint32_t)C[2];
-    int r0 = 0, r01 = 0, r012 = 0;                                    // draws below each cumulative bound
-    const uint64_t rb = isb_rng_base(seed, ISB_RNG_TAG_CLONR, (uint64_t)pos, (uint64_t)mm);
-    uint64_t kk = 0;                                                  // k * K3
-    for (int i = 0; i < n; i += 2, kk += ISB_RNG_K3) {
-        const uint64_t h = isb_mix64(rb ^ kk);
-        uint32_t idx = __umulhi((uint32_t)h, (uint32_t)T);
-        r0 += idx < c0; r01 += idx < c01; r012 += idx < c012;
-        if (i + 1 < n) {
-            idx = __umulhi((uint32_t)(h >> 32), (uint32_t)T);
-            r0 += idx < c0; r01 += idx < c01; r012 += idx < c012;
-        }
-    }
+    int r[4];
+    isb_redraw4(C, T, n, isb_rng_base(seed, ISB_RNG_TAG_CLONR, (uint64_t)pos, (uint64_t)mm), r);
     const double s = (double)n;
-    const double f0 = __ddiv_rn((double)r0, s), f1 = __ddiv_rn((double)(r01 - r0), s);
-    const double f2 = __ddiv_rn((double)(r012 - r01), s), f3 = __ddiv_rn((double)(n - r012), s);
+    const double f0 = __ddiv_rn((double)r[0], s), f1 = __ddiv_rn((double)r[1], s);
+    const double f2 = __ddiv_rn((double)r[2], s), f3 = __ddiv_rn((double)r[3], s);
     double prob = __dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1));
     prob = __dadd_rn(prob, __dmul_rn(f2, f2));
     prob = __dadd_rn(prob, __dmul_rn(f3, f3));

@@ -52,6 +52,35 @@ struct k2_site_state {
     int C[4];                                                         // cumulative A,C,T,G counts up to the current level
 };
 
+// Rarefied clonality at M > 1.  A (position, level) needs ~750 instructions of draws only when the level reaches the rarefied
+// coverage AND holds more than one base (~10 % of the cells), but a warp whose 32 lanes walk their levels in lock step
+// would run that path at almost every level for a few lanes each.  The cells that need draws are therefore queued per warp
+// in shared memory and processed DENSELY, one cell per lane, whenever 32 are waiting.
+struct k2_rq_entry { int C[4]; int32_t p; int32_t m; };
+struct k2_rq { k2_rq_entry *e; int n; };                               // e: [64] per warp; n: warp-uniform
+
+__device__ __forceinline__ void k2_rq_drain(k2_rq &q, bool all, float *__restrict__ clonTR, int M, int cov_r, uint64_t seed,
+                                            int32_t start)
+{
+    const int lane = threadIdx.x & 31;
+    while (q.n >= 32 || (all && q.n > 0)) {
+        const int take = min(q.n, 32);
+        __syncwarp();
+        if (lane < take) {
+            const k2_rq_entry e = q.e[lane];
+            const int C[4] = {e.C[0], e.C[1], e.C[2], e.C[3]};
+            clonTR[(size_t)e.p * M + e.m] = k2_rarefied_clon(C, C[0] + C[1] + C[2] + C[3], cov_r, seed, (int64_t)e.p + start, e.m);
+        }
+        const bool has = lane + 32 < q.n;
+        k2_rq_entry mv;
+        if (has) mv = q.e[lane + 32];
+        __syncwarp();
+        if (has) q.e[lane] = mv;
+        q.n -= take;
+    }
+    __syncwarp();
+}
+
 // The reference's ascending-mm loop over levels [m0, m0 + mc) of ONE site; `st` carries anySNP / bases / cryptic / the
 // cumulative counts across calls.  crow[j], cov_row[j], clon_row[j] address level m0 + j (global rows, or the block's
 // shared-memory tiles in the staged kernel).
@@ -62,12 +91,15 @@ __device__ __forceinline__ void
 k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, unsigned long long nm, int ref,
                const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
                int32_t *cov_row, float *clon_row, isb_snv_row *__restrict__ rows, int64_t slot, int64_t cap,
-               int cryptic_final, float *clonr_row = nullptr, int cov_r = 0, uint64_t seed = 0)
+               int cryptic_final, float *clonr_row = nullptr, int cov_r = 0, uint64_t seed = 0, k2_rq *rq = nullptr,
+               bool valid = true, float *clonTR = nullptr, int M = 0)
 {
+    // rq != nullptr: EVERY lane of the warp runs this loop (valid = false for lanes without a position): the queue uses
+    // full-warp ballots
     int *C = st.C;
     for (int j = 0; j < mc; ++j) {
         const int m = m0 + j;
-        const int4 E = crow[j];
+        const int4 E = valid ? crow[j] : make_int4(0, 0, 0, 0);
         const int e_sum = E.x + E.y + E.z + E.w;
         const bool present = e_sum > 0 || ((nm >> m) & 1ull);       // mm is a key of MMcounts
         if (!kWrite) cov_row[j] = e_sum;                              // update_covT: exact-mm coverage
@@ -94,9 +126,28 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
             clon = __double2float_rn(prob);
         }
         if (!kWrite) clon_row[j] = clon;
-        if (!kWrite && clonr_row)                                     // clonTR[mm][pos]: set where the coverage reaches cov_r
-            clonr_row[m] = (present && cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(st.C, T, cov_r, seed, (int64_t)p + start, m)
-                                                                : CUDART_NAN_F;
+        if (!kWrite && (clonr_row || rq)) {                           // clonTR[mm][pos]: set where the coverage reaches cov_r
+            bool need = false;
+            if (valid && clonr_row) {
+                if (present && cov_r > 0 && T >= cov_r) {
+                    if (max(max(C[0], C[1]), max(C[2], C[3])) == T) clonr_row[m] = 1.0f;      // one base only: no draws
+                    else if (rq) need = true;
+                    else clonr_row[m] = k2_rarefied_clon(st.C, T, cov_r, seed, (int64_t)p + start, m);
+                } else {
+                    clonr_row[m] = CUDART_NAN_F;
+                }
+            }
+            if (rq) {
+                const unsigned nm_ = __ballot_sync(ISB_FULL, need);
+                if (need) {
+                    k2_rq_entry e;
+                    e.C[0] = C[0]; e.C[1] = C[1]; e.C[2] = C[2]; e.C[3] = C[3]; e.p = p; e.m = m;
+                    rq->e[rq->n + __popc(nm_ & ((1u << (threadIdx.x & 31)) - 1u))] = e;
+                }
+                rq->n += __popc(nm_);
+                if (rq->n >= 32) k2_rq_drain(*rq, false, clonTR, M, cov_r, seed, start);
+            }
+        }
         if (!counted) continue;                                       // call_snv_site -> (None, 0)
         int thr, i = 0;
         if (T < n_lut) {                                              // integer form of the two-part presence test
@@ -264,6 +315,8 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
     int32_t *s_cov = reinterpret_cast<int32_t *>(s_in + (size_t)K2S_THREADS * sin);
     float *s_clon = reinterpret_cast<float *>(s_cov + (size_t)K2S_THREADS * sout);
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_clon + (size_t)K2S_THREADS * sout);   // 8-byte aligned: K2S_THREADS is even
+    k2_rq rq = {reinterpret_cast<k2_rq_entry *>(bar + 2) + (threadIdx.x >> 5) * 64, 0};   // per-warp queue of cells that need draws
+    k2_rq *rqp = (clonTR && cov_r > 0) ? &rq : nullptr;
     const int t = threadIdx.x;
     const int32_t p0 = blockIdx.x * K2S_THREADS;
     const int32_t p = p0 + t;
@@ -288,10 +341,11 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
             r = ref[p];
         }
         isb_mbar_wait(bar, 0);
-        if (active)
+        if (active || rqp)                                            // with the draw queue every lane walks the levels
             k2_site_levels<false>(st, p, 0, M, s_in + (size_t)t * M, nm, r, thr2, n_lut, lut_default, start, min_cov,
                                   min_freq, s_cov + (size_t)t * M, s_clon + (size_t)t * M, nullptr, 0, 0, 0,
-                                  clonTR ? clonTR + (size_t)p * M : nullptr, cov_r, seed);
+                                  clonTR && active ? clonTR + (size_t)p * M : nullptr, cov_r, seed, rqp, active, clonTR, M);
+        if (rqp) k2_rq_drain(rq, true, clonTR, M, cov_r, seed, start);
         __syncthreads();
         const int n_out = npos * M;                                   // words; the block's output run starts 16-byte aligned
         const size_t g0 = (size_t)p0 * M;
@@ -318,10 +372,11 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
             }
             isb_mbar_wait(bar, parity);
             parity ^= 1u;
-            if (active)
+            if (active || rqp)
                 k2_site_levels<false>(st, p, m0, mc, s_in + (size_t)t * sin, nm, r, thr2, n_lut, lut_default, start,
                                       min_cov, min_freq, s_cov + (size_t)t * sout, s_clon + (size_t)t * sout, nullptr, 0,
-                                      0, 0, clonTR ? clonTR + (size_t)p * M : nullptr, cov_r, seed);
+                                      0, 0, clonTR && active ? clonTR + (size_t)p * M : nullptr, cov_r, seed, rqp, active, clonTR, M);
+            if (rqp) k2_rq_drain(rq, true, clonTR, M, cov_r, seed, start);
             __syncthreads();
             // two rows per warp pass: 16 lanes per row (mc <= 16), no integer division
             for (int q = (t >> 4); q < npos; q += K2S_THREADS / 16) {
@@ -342,7 +397,7 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
 static size_t k2s_smem_bytes(int M)
 {
     const size_t sin = M <= K2S_MC ? (size_t)M : (size_t)(K2S_MC | 1), sout = sin;
-    return (size_t)K2S_THREADS * sin * 16 + 2 * (size_t)K2S_THREADS * sout * 4 + 16;
+    return (size_t)K2S_THREADS * sin * 16 + 2 * (size_t)K2S_THREADS * sout * 4 + 16 + (K2S_THREADS / 32) * 64 * sizeof(k2_rq_entry);
 }
 
 // Row counter reset + the merged integer threshold table of (context, min_freq); also called by the fused pileup + SNV

@@ -501,20 +501,11 @@ __device__ __forceinline__ void k3_emit(const k3_args &a, int32_t p1, int32_t p2
     // the four observed frequencies (counter-based draws keyed by the row, isb_k2_site.cuh)
     double r2n = CUDART_NAN, dpn = CUDART_NAN;
     if (a.min_snp >= 1) {
-        const uint32_t b1 = (uint32_t)cAB, b2 = b1 + (uint32_t)cAb, b3 = b2 + (uint32_t)caB;
         const uint64_t key = ((uint64_t)(uint32_t)(p1 + a.start) << 32) | (uint64_t)(uint32_t)(p2 + a.start);
-        int n1 = 0, n2 = 0, n3 = 0;
-        const uint64_t rb = isb_rng_base(a.seed, ISB_RNG_TAG_LD, key, (uint64_t)m);
-        uint64_t kk = 0;
-        for (int i = 0; i < a.min_snp; i += 2, kk += ISB_RNG_K3) {
-            const uint64_t h = isb_mix64(rb ^ kk);
-            uint32_t idx = __umulhi((uint32_t)h, (uint32_t)total);
-            n1 += idx < b1; n2 += idx < b2; n3 += idx < b3;
-            if (i + 1 < a.min_snp) {
-                idx = __umulhi((uint32_t)(h >> 32), (uint32_t)total);
-                n1 += idx < b1; n2 += idx < b2; n3 += idx < b3;
-            }
-        }
+        const int hc[4] = {cAB, cAb, caB, cab};                       // np.random.choice(['AB','Ab','aB','ab'], p=..., size=min_snp)
+        int hn[4];
+        isb_redraw4(hc, total, a.min_snp, isb_rng_base(a.seed, ISB_RNG_TAG_LD, key, (uint64_t)m), hn);
+        const int n1 = hn[0], n2 = hn[0] + hn[1], n3 = hn[0] + hn[1] + hn[2];
         const double ns = (double)a.min_snp;
         const double gAB = __ddiv_rn((double)n1, ns), gAb = __ddiv_rn((double)(n2 - n1), ns);
         const double gaB = __ddiv_rn((double)(n3 - n2), ns), gab = __ddiv_rn((double)(a.min_snp - n3), ns);

@@ -5,8 +5,8 @@
 
 The reference draws both with an UNSEEDED np.random.choice, so nothing of theirs can be pinned bit for bit (its own tests
 delete these columns before comparing: test/tests/test_profile.py:896-900).  The CUDA path draws from a counter-based
-generator instead (instrain_b200/csrc/isb_k2_site.cuh: splitmix64's finaliser over (seed, stream tag, site key, draw index);
-draw u picks the category of index floor(u * total / 2^32) of the cumulative counts).  This module restates exactly that
+generator instead (instrain_b200/csrc/isb_k2_site.cuh: splitmix64's finaliser over (seed, stream tag, site key, word index),
+the n draws sampled bit-sliced as a chain of binomials: isb_redraw4).  This module restates exactly that
 generator and the arithmetic around it, so the CUDA outputs ARE bit-exact against the oracle for a given seed; that the
 construction has the reference's distribution is checked separately against the reference's own functions
 (tests/test_reference_mirrors.py).
@@ -27,22 +27,66 @@ def mix64(z):
     return z ^ (z >> np.uint64(31))
 
 
-def rand64(seed, tag, a, b, k):
+_K4 = np.uint64(0xa0761d6478bd642f)
+
+
+def rng_base(seed, tag, a, b):
     with np.errstate(over="ignore"):
-        s = mix64(np.uint64(seed) + tag)
-        return mix64(s ^ (np.asarray(a, np.uint64) * _K1) ^ (np.asarray(b, np.uint64) * _K2) ^ (np.asarray(k, np.uint64) * _K3))
+        return mix64(np.uint64(seed) + tag) ^ (np.asarray(a, np.uint64) * _K1) ^ (np.asarray(b, np.uint64) * _K2)
 
 
-def _draw_counts(bounds, total, n, seed, tag, a, b):
-    """n draws per row: number of draws below each cumulative bound.  bounds: [rows, 3] uint64, total: [rows]."""
-    below = np.zeros(bounds.shape, dtype=np.int64)
-    total = total.astype(np.uint64)
-    for i in range(n):
-        h = rand64(seed, tag, a, b, np.uint64(i >> 1))
-        u = (h >> np.uint64(32)) if (i & 1) else (h & np.uint64(0xFFFFFFFF))
-        idx = (u * total) >> np.uint64(32)
-        below += idx[:, None] < bounds
-    return below
+def redraw4(c, T, n, rb):
+    """isb_redraw4 (instrain_b200/csrc/isb_k2_site.cuh), row-wise: n draws with replacement from 4 categories with counts
+    c[rows, 4] (totals T), bit-sliced -- the trials are the bit lanes of a 64-bit word, categories are split off one after
+    the other (a binomial with p = c_i / remaining), a random word decides one bit of the comparison "uniform < p" for all
+    trials at once.  Returns int64 r[rows, 4] (row sums = n)."""
+    c = np.asarray(c, dtype=np.int64)
+    rows = len(c)
+    r = np.zeros((rows, 4), dtype=np.int64)
+    q = 0
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        while q * 64 < n:
+            nt = min(64, n - q * 64)
+            left = np.full(rows, np.uint64(0xFFFFFFFFFFFFFFFF) if nt == 64 else np.uint64((1 << nt) - 1), dtype=np.uint64)
+            base = rb ^ (np.uint64(q) * _K4)
+            kk = np.zeros(rows, dtype=np.uint64)
+            rem = np.asarray(T, dtype=np.int64).copy()
+            for i in range(4):
+                ci = c[:, i]
+                act = (ci != 0) & (left != 0)
+                last = act & (ci == rem)
+                r[last, i] += _popc64(left[last])
+                left[last] = 0
+                go = act & ~last
+                P = np.zeros(rows, dtype=np.uint64)
+                P[go] = np.floor(ci[go].astype(np.float64) / rem[go].astype(np.float64) * 4294967296.0).astype(np.uint64)
+                und = np.where(go, left, np.uint64(0))
+                hit = np.zeros(rows, dtype=np.uint64)
+                for b in range(31, -1, -1):
+                    run = und != 0
+                    if not run.any():
+                        break
+                    W = mix64(base ^ kk)
+                    kk = np.where(run, kk + _K3, kk)
+                    one = ((P >> np.uint64(b)) & np.uint64(1)) != 0
+                    hit = np.where(run & one, hit | (~W & und), hit)
+                    und = np.where(run, np.where(one, und & W, und & ~W), und)
+                r[:, i] += np.where(go, _popc64(hit), 0)
+                left = np.where(go, left & ~hit, left)
+                rem = np.where(go, rem - ci, rem)
+            q += 1
+    return r
+
+
+def _popc64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    out = np.zeros(len(x), dtype=np.int64)
+    for sh in range(0, 64, 16):
+        out += _POP16[((x >> np.uint64(sh)) & np.uint64(0xFFFF)).astype(np.int64)]
+    return out
+
+
+_POP16 = np.array([bin(i).count("1") for i in range(1 << 16)], dtype=np.int64)
 
 
 def clonality_of(c, s):
@@ -71,10 +115,8 @@ def clonTR(counts, nmask, rarefied_coverage=50, seed=0, start=0):
     val = np.ones(len(p), dtype=np.float64)
     q = np.nonzero(~single)[0]
     if len(q):
-        b = np.cumsum(C[q, :3], axis=1).astype(np.uint64)
-        below = _draw_counts(b, Ts[q], rarefied_coverage, seed, TAG_CLONR, (p[q] + start).astype(np.uint64), m[q].astype(np.uint64))
-        r = np.stack([below[:, 0], below[:, 1] - below[:, 0], below[:, 2] - below[:, 1], rarefied_coverage - below[:, 2]], 1)
-        val[q] = clonality_of(r, rarefied_coverage)
+        rb = rng_base(seed, TAG_CLONR, (p[q] + start).astype(np.uint64), m[q].astype(np.uint64))
+        val[q] = clonality_of(redraw4(C[q], Ts[q], rarefied_coverage, rb), rarefied_coverage)
     out[p, m] = val.astype(np.float32)
     return out
 
@@ -87,11 +129,9 @@ def normalized_ld(rows, min_snp=20, seed=0):
         return r2n, dpn
     c = np.stack([rows["c_AB"], rows["c_Ab"], rows["c_aB"], rows["c_ab"]], 1).astype(np.int64)
     total = c.sum(1)
-    b = np.cumsum(c[:, :3], axis=1).astype(np.uint64)
     key = (rows["pos_a"].astype(np.int64).astype(np.uint64) & np.uint64(0xFFFFFFFF)) << np.uint64(32)
     key |= rows["pos_b"].astype(np.int64).astype(np.uint64) & np.uint64(0xFFFFFFFF)
-    below = _draw_counts(b, total, min_snp, seed, TAG_LD, key, rows["mm"].astype(np.uint64))
-    g = np.stack([below[:, 0], below[:, 1] - below[:, 0], below[:, 2] - below[:, 1], min_snp - below[:, 2]], 1) / np.float64(min_snp)
+    g = redraw4(c, total, min_snp, rng_base(seed, TAG_LD, key, rows["mm"].astype(np.uint64))) / np.float64(min_snp)
     gAB, gAb, gaB, gab = g[:, 0], g[:, 1], g[:, 2], g[:, 3]
     gA, ga, gB, gb = gAB + gAb, gab + gaB, gAB + gaB, gab + gAb
     ldn = gab - ga * gb
