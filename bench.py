@@ -204,7 +204,9 @@ class Job:
         self.nmask = None if self.lean else torch.empty(L_, dtype=torch.int64, device=dev)
         self.covT = torch.empty((L_, M_), dtype=torch.int32, device=dev)
         self.clonT = torch.empty((L_, M_), dtype=torch.float32, device=dev)
-        self.clonTR = torch.empty((L_, M_), dtype=torch.float32, device=dev)   # rarefied clonality: part of the reference's output
+        # rarefied clonality: part of the reference's output (ISB_BENCH_NO_CLONTR=1: A/B switch, not a bench configuration)
+        self.no_clontr = os.environ.get("ISB_BENCH_NO_CLONTR", "0") == "1"
+        self.clonTR = None if self.no_clontr else torch.empty((L_, M_), dtype=torch.float32, device=dev)
         self.flags = torch.empty(L_, dtype=torch.uint8, device=dev)
         self.snv_cap = max(1 << 16, (L_ // 16) * (1 if M_ == 1 else 4))
         self.ld_cap = max(1 << 18, (L_ // 2) * (1 if M_ == 1 else 4))
@@ -228,7 +230,7 @@ class Job:
             self.batch = _cabi.IsbBatch(int(d["n_events"]), p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), self.npairs,
                                         p(d["pair_mm"]), 0, L_, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M_)
             self.entry = eng.lib.isb_profile_batch
-        self.prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05, 50, 0, SEED)
+        self.prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05, 0 if self.no_clontr else 50, 0, SEED)
         self.step_no, self.res = 0, None
 
     def _alloc_rows(self):

@@ -17,6 +17,7 @@
 #define ISB_DEV_ERR_ROWBUF 0x8u       // linkage bit-row scratch too small (host grows it and re-runs K3)
 #define ISB_DEV_ERR_SEG 0x10u         // read-major batch violates its layout rules (order, range, word offsets)
 #define ISB_DEV_ERR_SITECAP 0x20u     // fused read-major path: more linkage sites than site slots (host grows them and re-runs)
+#define ISB_DEV_ERR_QCAP 0x40u        // fused read-major path: more sites for the general SNV call than queue slots (same remedy)
 
 #define ISB_K3_ROW_SLOT 64            // words of the fixed bit-row slot every linkage site owns (wider rows go to an overflow region)
 
@@ -33,6 +34,7 @@ enum {  // scratch buffer slots of a context (grow-only device allocations)
     SL_CD_OFF, SL_CD_WORDS, SL_CD_IDS, SL_CD_CNT,                                  // column-word batch (K1c inputs) + conversion scratch
     SL_SCAN_TMP, SL_SITE_POS, SL_SITE_META, SL_SITE_WORDS, SL_ROW_OFF, SL_ROWS, SL_MM_MASK, SL_HAS2,
     SL_TILE_SITES, SL_SITE_COUNTS,                                                 // fused read-major path: per-tile site slots, counts per site
+    SL_Q_TILE, SL_Q_POS, SL_Q_E, SL_Q_CAND, SL_SITE_CAND,                          // fused read-major path: queue of the sites for the general SNV call
     SL_COUNT
 };
 
@@ -59,6 +61,7 @@ struct isb_ctx {
     unsigned int *h_err;
     int64_t launches;
     int64_t sites_cap;                // fused read-major path: linkage-site slots allocated so far (grow-only)
+    int64_t queue_cap;                // fused read-major path: queue slots (sites for the general SNV call) allocated so far
     isb_devbuf buf[SL_COUNT];
     char err[512];
     uint64_t seed;                    // isb_params.seed of the running call (linkage: normalized columns)

@@ -63,31 +63,21 @@ struct k1f_args {
     int32_t start, L;
     int M;
     int seg_cap;                       // segments staged per chunk
-    int code_ids;                      // ids of the per-warp "pair id -> allele" byte map (fused linkage front end)
     int32_t *counts;
     unsigned int *d_err;
-    // fused SNV call (M = 1)
-    const unsigned long long *nmask;   // read only when min_cov <= 0 (a level without counts cannot be "counted" otherwise)
+    // fused epilogue (M = 1)
     isb_k2_fuse k2;
     const int32_t *thr2;
-    int n_lut, lut_default;
-    unsigned long long *n_rows;
-    // linkage front end
-    int do_ld;
-    int32_t n_splits;
-    const int32_t *splits;
-    int32_t *tile_first, *tile_cnt;
-    const int32_t *tile_split;
-    int64_t sites_cap;
-    int32_t *site_pos;
-    isb_site_meta *meta;
-    int64_t *row_off;
-    uint8_t *has2;
-    int4 *site_counts;
-    uint32_t *rows;
-    int64_t row_cap;
-    unsigned long long *n_sites, *row_words_total;
+    int n_lut;
+    // site queue: the sites the epilogue does not finish itself (k2q_sites does)
+    int32_t *q_first, *q_cnt;          // [n_tiles] queue slots of a tile (contiguous, position-ordered)
+    int32_t *q_pos;                    // [q_cap] relative position
+    int4 *q_E;                         // [q_cap] A,C,T,G counts
+    uint32_t *q_cand;                  // [q_cap] candidate segments of the site's column: first (relative to tile_lo) | count << 16
+    int64_t q_cap;
+    unsigned long long *n_queue;
 };
+#define K1F_NO_CAND 0xffffffffu        // q_cand: not known (tile staged in several chunks): k3f_site_rows searches
 
 // tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range, and (linkage) the index of
 // the last split that starts at or before the tile's first position (-1: none) -- the per-site split lookup of the fused
@@ -180,10 +170,8 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     int4 *s_tile = reinterpret_cast<int4 *>(s_x);                         // [K1F_WARPS][K1F_TILE4]
     int32_t *s_cl = reinterpret_cast<int32_t *>(s_tile + K1F_WARPS * K1F_TILE4);       // [K1F_THREADS] candidate range per column
     int32_t *s_ch = s_cl + K1F_THREADS;
-    int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: sites per warp, offsets, slot base
-    uint16_t *s_site = reinterpret_cast<uint16_t *>(s_misc + 16);         // [K1F_WARPS][256]: position in the warp | bases << 8
-    uint8_t *s_q = reinterpret_cast<uint8_t *>(s_site + K1F_WARPS * 256); // [K1F_WARPS][256]: positions for the general path
-    uint8_t *s_code = s_q + K1F_WARPS * 256;                              // [K1F_WARPS][a.code_ids]: pair id -> allele code of a site
+    int32_t *s_misc = s_ch + K1F_THREADS;                                 // [16]: queued sites per warp, offsets, slot base
+    uint8_t *s_q = reinterpret_cast<uint8_t *>(s_misc + 16);              // [K1F_WARPS][256]: positions for the site queue
 
     const int t = threadIdx.x;
     const int lane = t & 31, wib = t >> 5;
@@ -205,6 +193,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     if (kM1) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) tile_lane[k] = make_int4(0, 0, 0, 0);
+        if (kFuse) { s_cl[t] = 0; s_ch[t] = 0; }
     } else {
         for (int w = 0; w < Mg * 8; ++w) s_acc[w * K1F_THREADS + t] = 0u;
     }
@@ -418,15 +407,20 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         return;
     }
 
-    // ---- fused SNV call (K2 at M = 1) ------------------------------------------------------------------------------
+    // ---- fused epilogue (M = 1) ---------------------------------------------------------------------------------------
+    // Coverage of every position; sites with one base only (or below min_cov) are finished here with integer compares and
+    // coalesced stores.  The others (~12 % at 100x: a second base, usually a sequencing error) go to the tile's slots of
+    // the SITE QUEUE (position, the four counts, candidate segment range of the column) and are finished by k2q_sites.
+    // Keeping the double-precision site arithmetic, the re-drawn clonality and the linkage row builder out of this kernel
+    // keeps its code inside the instruction caches: the one-kernel version spent a third of its issue slots waiting for
+    // instruction fetches (ncu: stall_no_inst 5.2 per issue, 138 KB of SASS).
     k1f_flush_planes(tile_lane, pl);
     __syncwarp();
     const int32_t W0 = T0 + wib * 256;
     int4 *counts4 = reinterpret_cast<int4 *>(a.counts);
     const bool full_counts = a.counts != nullptr && a.k2.full_counts;
     uint8_t *q_list = s_q + wib * 256;
-    uint16_t *site_list = s_site + wib * 256;
-    int nq = 0;                                                   // positions waiting for the general path (warp-uniform)
+    int nq = 0;                                                   // positions of the warp for the queue (warp-uniform)
     const bool all_general = a.k2.min_cov < 1;                    // then "below min_cov" is not a simple case
     const int cov_r = a.k2.clonTR ? a.k2.cov_r : 0;               // rarefied clonality wanted where the coverage reaches it
 #pragma unroll 2
@@ -446,7 +440,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 const int con = E.x == T ? 0 : (E.y == T ? 1 : (E.z == T ? 2 : 3));   // reference base and passes the threshold
                 if (T >= __ldg(a.thr2 + T) && con == (int)a.k2.ref[p]) { simple = true; clon = 1.0f; }
             }
-            if (simple && cov_r > 0 && T >= cov_r) {              // rarefied clonality: 1 with one base only, else drawn (general path)
+            if (simple && cov_r > 0 && T >= cov_r) {              // rarefied clonality: 1 with one base only, else drawn (queue)
                 if (mx == T) clonr = 1.0f; else simple = false;
             }
         }
@@ -464,145 +458,280 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         if (need) q_list[nq + __popc(nm & ((1u << lane) - 1u))] = (uint8_t)q;
         nq += __popc(nm);
     }
-    __syncwarp();
-    int ns = 0;                                                   // anySNP sites of the warp (warp-uniform)
-    for (int b0 = 0; b0 < nq; b0 += 32) {                         // general path, dense: lane = one waiting position
-        const bool on = b0 + lane < nq;
-        const int q = on ? (int)q_list[b0 + lane] : 0;
-        const int32_t p = W0 + q;
-        const int4 E = tile4[q + (q >> 3)];
-        int C[4] = {E.x, E.y, E.z, E.w};
-        int r = 0;
-        k2_m1_site s;
-        s.T = 0; s.clon = CUDART_NAN_F; s.flags = 0u; s.is_row = false; s.i = 0; s.con = 0; s.thr = 0;
-        if (on) {
-            r = a.k2.ref[p];
-            const int T = E.x + E.y + E.z + E.w;
-            const int thr_T = (T >= a.k2.min_cov && T < a.n_lut) ? __ldg(a.thr2 + T) : a.lut_default;
-            const bool nm0 = T == 0 && a.nmask && (a.nmask[p] & 1ull);
-            s = k2_site_m1(C, r, nm0, thr_T, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
-            a.k2.clonT[p] = s.clon;
-            a.k2.site_flags[p] = (uint8_t)s.flags;
-            if (a.k2.clonTR)
-                a.k2.clonTR[p] = (cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(C, T, cov_r, a.k2.seed, (int64_t)p + a.start, 0) : CUDART_NAN_F;
-            if (full_counts) counts4[p] = E;
-        }
-        const bool row = on && s.is_row;
-        const unsigned rm = __ballot_sync(ISB_FULL, row);
-        if (rm) {                                                 // one row allocation per batch of 32
-            unsigned long long base_slot = 0;
-            if (lane == 0) base_slot = atomicAdd(a.n_rows, (unsigned long long)__popc(rm));
-            base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
-            const int64_t slot = (int64_t)base_slot + __popc(rm & ((1u << lane) - 1u));
-            if (row && slot < a.k2.cap) k2_write_row_m1(a.k2.rows + slot, p + a.start, C, r, s, a.n_lut, a.k2.min_freq);
-        }
-        const bool st = on && (s.flags & ISB_SITE_ANYSNP);
-        const unsigned sm = __ballot_sync(ISB_FULL, st);
-        if (st) site_list[ns + __popc(sm & ((1u << lane) - 1u))] = (uint16_t)(q | ((s.flags & 0xFu) << 8));
-        ns += __popc(sm);
-    }
-    if (!a.do_ld) return;
-
-    // ---- linkage front end: site slots of the tile, then one warp per site ---------------------------------------------
-    if (lane == 0) s_misc[wib] = ns;
+    // queue slots of the tile: contiguous and position-ordered (warp after warp), one atomic per tile
+    if (lane == 0) s_misc[wib] = nq;
     __syncthreads();
     if (t == 0) {
         int tot = 0;
         for (int w = 0; w < K1F_WARPS; ++w) { s_misc[4 + w] = tot; tot += s_misc[w]; }
         unsigned long long b0 = 0;
-        if (tot) b0 = atomicAdd(a.n_sites, (unsigned long long)tot);
-        s_misc[8] = tot;
+        if (tot) b0 = atomicAdd(a.n_queue, (unsigned long long)tot);
         s_misc[9] = (int32_t)(b0 < (unsigned long long)INT_MAX ? b0 : (unsigned long long)INT_MAX);
-        a.tile_first[tile] = s_misc[9];
-        a.tile_cnt[tile] = tot;
+        a.q_first[tile] = s_misc[9];
+        a.q_cnt[tile] = tot;
     }
     __syncthreads();
-    const int tot = s_misc[8];
-    const int64_t sbase = s_misc[9];
-    const uint32_t *wsrc0 = a.rd.words + wb - 160;                // single-chunk tiles: word index = wsrc0[(meta >> 11) + column]
-    for (int si = wib; si < tot; si += K1F_WARPS) {
-        int ow = 0;
-#pragma unroll
-        for (int w = 1; w < K1F_WARPS; ++w) if (si >= s_misc[4 + w]) ow = w;
-        const unsigned ent = s_site[ow * 256 + si - s_misc[4 + ow]];
-        const int q = ent & 0xff;
-        const unsigned bases = ent >> 8;
-        const int pt = ow * 256 + q;                               // tile-relative position
-        const int32_t p = T0 + pt;
-        const int64_t abs_pos = (int64_t)p + a.start;
-        const int64_t slot = sbase + si;
-        if (slot >= a.sites_cap) {                                 // host grows the site slots and re-runs
-            if (lane == 0) atomicOr(a.d_err, ISB_DEV_ERR_SITECAP);
-            continue;
+    const int64_t qb = (int64_t)s_misc[9] + s_misc[4 + wib];
+    for (int i = lane; i < nq; i += 32) {
+        const int64_t slot = qb + i;
+        if (slot >= a.q_cap) {                                    // host grows the queue and re-runs
+            atomicOr(a.d_err, ISB_DEV_ERR_QCAP);
+            break;
         }
+        const int q = q_list[i];
+        const int tc = wib * 32 + (q >> 3);
+        a.q_pos[slot] = W0 + q;
+        a.q_E[slot] = tile4[q + (q >> 3)];
+        // candidate segments of the site's column word, relative to the tile's first candidate (single-chunk tiles)
+        a.q_cand[slot] = single ? ((uint32_t)s_cl[tc] | ((uint32_t)(s_ch[tc] - s_cl[tc]) << 16)) : K1F_NO_CAND;
+    }
+}
+
+// ---- k2q_sites: the general SNV call on the queued sites (K2 at M = 1) + the linkage site slots -----------------------------
+// One warp per tile, lane = one queued site, batches of 32: the reference's call_snv_site / update_snp_table / clonality in
+// double precision (isb_k2_site.cuh), the re-drawn clonality, the raw_snp_table rows (one row allocation per batch).  The
+// tile's anySNP sites get contiguous, position-ordered site slots (one atomic per tile) with their counts and candidate
+// range: the input of k3f_site_rows and of the linkage back end.
+struct k2q_args {
+    int n_tiles;
+    const int32_t *q_first, *q_cnt;
+    const int32_t *q_pos;
+    const int4 *q_E;
+    const uint32_t *q_cand;
+    int64_t q_cap;
+    int32_t start, L;
+    const unsigned long long *nmask;
+    isb_k2_fuse k2;
+    const int32_t *thr2;
+    int n_lut, lut_default;
+    unsigned long long *n_rows;
+    int32_t *counts;
+    unsigned int *d_err;
+    int do_ld;
+    int32_t *tile_first, *tile_cnt;
+    int64_t sites_cap;
+    int32_t *site_pos;
+    int4 *site_counts;
+    uint32_t *site_cand;
+    unsigned long long *n_sites;
+};
+
+#define K2Q_WARPS 4
+__global__ void __launch_bounds__(K2Q_WARPS * 32) k2q_sites(k2q_args a)
+{
+    __shared__ uint16_t s_sites[K2Q_WARPS][K1F_TILE];             // index in the tile's queue range | allele set << 12
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int4 *counts4 = reinterpret_cast<int4 *>(a.counts);
+    const bool full_counts = a.counts != nullptr && a.k2.full_counts;
+    const int cov_r = a.k2.clonTR ? a.k2.cov_r : 0;
+    for (int tile = blockIdx.x * K2Q_WARPS + wib; tile < a.n_tiles; tile += gridDim.x * K2Q_WARPS) {
+        const int64_t first = a.q_first[tile];
+        int cnt = a.q_cnt[tile];
+        if (first + cnt > a.q_cap) cnt = first < a.q_cap ? (int)(a.q_cap - first) : 0;   // overflow: flagged by K1f, re-run follows
+        int ns = 0;                                               // anySNP sites of the tile (warp-uniform)
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+            const bool on = b0 + lane < cnt;
+            int4 E = make_int4(0, 0, 0, 0);
+            int32_t p = 0;
+            if (on) {
+                p = __ldg(a.q_pos + first + b0 + lane);
+                E = __ldg(a.q_E + first + b0 + lane);
+            }
+            int C[4] = {E.x, E.y, E.z, E.w};
+            int r = 0;
+            k2_m1_site s;
+            s.T = 0; s.clon = CUDART_NAN_F; s.flags = 0u; s.is_row = false; s.i = 0; s.con = 0; s.thr = 0;
+            if (on) {
+                r = a.k2.ref[p];
+                const int T = E.x + E.y + E.z + E.w;
+                const int thr_T = (T >= a.k2.min_cov && T < a.n_lut) ? __ldg(a.thr2 + T) : a.lut_default;
+                const bool nm0 = T == 0 && a.nmask && (a.nmask[p] & 1ull);
+                s = k2_site_m1(C, r, nm0, thr_T, a.n_lut, a.lut_default, a.k2.min_cov, a.k2.min_freq);
+                a.k2.clonT[p] = s.clon;
+                a.k2.site_flags[p] = (uint8_t)s.flags;
+                if (a.k2.clonTR)
+                    a.k2.clonTR[p] = (cov_r > 0 && T >= cov_r) ? k2_rarefied_clon(C, T, cov_r, a.k2.seed, (int64_t)p + a.start, 0) : CUDART_NAN_F;
+                if (full_counts) counts4[p] = E;
+            }
+            const bool row = on && s.is_row;
+            const unsigned rm = __ballot_sync(ISB_FULL, row);
+            if (rm) {                                             // one row allocation per batch of 32
+                unsigned long long base_slot = 0;
+                if (lane == 0) base_slot = atomicAdd(a.n_rows, (unsigned long long)__popc(rm));
+                base_slot = __shfl_sync(ISB_FULL, base_slot, 0);
+                const int64_t slot = (int64_t)base_slot + __popc(rm & ((1u << lane) - 1u));
+                if (row && slot < a.k2.cap) k2_write_row_m1(a.k2.rows + slot, p + a.start, C, r, s, a.n_lut, a.k2.min_freq);
+            }
+            const bool st = on && (s.flags & ISB_SITE_ANYSNP);
+            const unsigned sm = __ballot_sync(ISB_FULL, st);
+            if (st) s_sites[wib][ns + __popc(sm & ((1u << lane) - 1u))] = (uint16_t)((b0 + lane) | ((s.flags & 0xFu) << 12));
+            ns += __popc(sm);
+        }
+        if (!a.do_ld) continue;
+        unsigned long long sb = 0;
+        if (lane == 0) {
+            if (ns) sb = atomicAdd(a.n_sites, (unsigned long long)ns);
+            a.tile_first[tile] = (int32_t)(sb < (unsigned long long)INT_MAX ? sb : (unsigned long long)INT_MAX);
+            a.tile_cnt[tile] = ns;
+        }
+        sb = __shfl_sync(ISB_FULL, sb, 0);
+        __syncwarp();
+        for (int i = lane; i < ns; i += 32) {
+            const int64_t slot = (int64_t)sb + i;
+            if (slot >= a.sites_cap) {                            // host grows the site slots and re-runs
+                atomicOr(a.d_err, ISB_DEV_ERR_SITECAP);
+                break;
+            }
+            const int64_t idx = first + (s_sites[wib][i] & 0x3ffu);
+            a.site_pos[slot] = __ldg(a.q_pos + idx);
+            a.site_counts[slot] = __ldg(a.q_E + idx);
+            a.site_cand[slot] = __ldg(a.q_cand + idx);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- k3f_site_rows: linkage front end, one warp per site slot ---------------------------------------------------------------
+// update_linked_reads (inStrain/profile/linkage.py:254-283): the (pair id, base) entries of a site, gathered from its
+// candidate segments (table entries are contiguous: coalesced; one 32-byte sector of the stream per covering segment) and
+// turned into the bit rows  any | ge1[b] | ge2[b]  over the site's pair-id window.
+struct k3f_args {
+    isb_reads_dev rd;
+    int64_t n_pairs;
+    int32_t start, L;
+    const uint8_t *site_flags;
+    int32_t n_splits;
+    const int32_t *splits;
+    const int32_t *tile_split;
+    int64_t sites_cap;
+    const int32_t *site_pos;
+    const uint32_t *site_cand;
+    isb_site_meta *meta;
+    int64_t *row_off;
+    uint8_t *has2;
+    uint32_t *rows;
+    int64_t row_cap;
+    const unsigned long long *n_sites;
+    unsigned long long *row_words_total;
+    int code_ids;                      // ids of the per-warp "pair id -> allele" byte map
+    unsigned int *d_err;
+};
+
+// The exact row builder with the multiplicity planes (atomics on the row words): windows wider than the byte map, and
+// sites where a pair has two entries (htslib's overlap quirk).  Rare: kept out of line.
+__device__ __noinline__ void k3f_slow_rows(const int32_t *__restrict__ seg_start, const uint16_t *__restrict__ seg_len,
+                                           const int64_t *__restrict__ seg_word, const int32_t *__restrict__ seg_pair,
+                                           const uint32_t *__restrict__ words, int64_t n_words_stream, int64_t n_pairs,
+                                           unsigned int *d_err, uint32_t *g_any, int wlo, int nw, int na, unsigned bases,
+                                           int64_t glo, int nc, int64_t abs_pos, int lane)
+{
+    isb_site_meta m;
+    m.ev_lo_rel = 0; m.wlo = wlo; m.nw = nw; m.split = 0;
+    const int n_words = (1 + 2 * na) * nw;
+    for (int i = lane; i < n_words; i += 32) g_any[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < nc; i += 32) {
+        const int64_t g = glo + i;
+        const int32_t s = __ldg(seg_start + g);
+        const int64_t j = abs_pos - (int64_t)s;
+        if (j < 0 || j >= (int64_t)__ldg(seg_len + g)) continue;
+        const int jn = (int)j + (s & 7);
+        const int64_t wi = __ldg(seg_word + g) + (jn >> 3);
+        if (wi < 0 || wi >= n_words_stream) continue;
+        const uint32_t c = (__ldg(words + wi) >> ((jn & 7) << 2)) & 15u;
+        if (!c) continue;
+        const int b = __ffs((int)c) - 1, id = __ldg(seg_pair + g);
+        if (id >= 0 && (int64_t)id < n_pairs && ((bases >> b) & 1u)) k3_row_set(g_any, m, na, bases, b, id, d_err);
+    }
+    __syncwarp();
+}
+
+#define K3F_WARPS 8
+__global__ void __launch_bounds__(K3F_WARPS * 32) k3f_site_rows(k3f_args a)
+{
+    extern __shared__ __align__(16) unsigned char k3f_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint8_t *code = k3f_smem + (size_t)wib * a.code_ids;          // pair id -> allele code of the warp's site
+    uint32_t *code4 = reinterpret_cast<uint32_t *>(code);
+    const unsigned long long ns_dev = *a.n_sites;
+    const int64_t S = (int64_t)(ns_dev < (unsigned long long)a.sites_cap ? ns_dev : (unsigned long long)a.sites_cap);
+    const int maxlen = a.rd.max_seg_len;
+    for (int64_t k = (int64_t)blockIdx.x * K3F_WARPS + wib; k < S; k += (int64_t)gridDim.x * K3F_WARPS) {
+        const int32_t p = __ldg(a.site_pos + k);
+        const uint32_t cand = __ldg(a.site_cand + k);
+        const int64_t abs_pos = (int64_t)p + a.start;
+        const unsigned bases = a.site_flags[p] & 0xFu;
         const int na = __popc(bases);
-        const int tcol = pt >> 3, sh = (pt & 7) << 2;
-        // candidate segments of the site: staged table (single-chunk tile) or the global table
-        int cl_ = 0, ch_ = 0;
-        int64_t glo = 0;
-        if (single) {
-            cl_ = s_cl[tcol];
-            ch_ = s_ch[tcol];
+        const int tile = p / K1F_TILE;
+        const int64_t lo = __ldg(a.rd.tile_lo + tile), hi = __ldg(a.rd.tile_hi + tile);
+        int64_t glo;
+        int nc;
+        if (cand != K1F_NO_CAND) {
+            glo = lo + (int64_t)(cand & 0xffffu);
+            nc = (int)(cand >> 16);
+            if (glo + nc > hi) nc = glo < hi ? (int)(hi - glo) : 0;
         } else {
             glo = isb_lower_bound(a.rd.seg_start, lo, hi, abs_pos - maxlen + 1);
-            ch_ = (int)(isb_lower_bound(a.rd.seg_start, glo, hi, abs_pos + 1) - glo);
+            nc = (int)(isb_lower_bound(a.rd.seg_start, glo, hi, abs_pos + 1) - glo);
         }
-        // Candidates in groups of 4 x 32: the word loads of a whole group are issued before the first is decoded (one
-        // L2 round trip per group instead of one per 32 candidates); group 0 -- all of them up to ~120x coverage -- stays
-        // decoded in registers for the second pass.
-        auto decode = [&](bool cov, uint32_t w, int pid, int &b, int &id) -> bool {
-            const uint32_t code = (w >> sh) & 15u;
-            if (!cov || !code) return false;
-            b = __ffs((int)code) - 1;
-            id = pid;
-            if (id < 0 || (int64_t)id >= a.n_pairs) { atomicOr(a.d_err, ISB_DEV_ERR_SEG); return false; }
-            return ((bases >> b) & 1u) != 0u;
-        };
-        auto group = [&](int g0, int (&b4)[4], int (&id4)[4]) {    // candidates g0 .. g0 + 127 -> (base, id), base -1 = no entry
-            if (single) {
-                uint32_t w4[4];
-                bool cov[4];
-                int pid[4];
+        // Candidates in groups of 4 x 32: the table loads of a whole group are issued together, then its word loads (two
+        // memory latencies per group instead of three per 32 candidates); group 0 -- all of them up to ~120x coverage --
+        // stays decoded in registers for the second pass.
+        auto group = [&](int g0, int (&b4)[4], int (&id4)[4]) {
+            int32_t s4[4], n4[4], pid[4];
+            int64_t w4[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = g0 + u * 32 + lane;
-                    cov[u] = false; w4[u] = 0u; pid[u] = 0;
-                    if (i < ch_) {
-                        const uint32_t md = s_meta[i];
-                        cov[u] = (pt + 256 < (int)(md & 0x7ffu)) && s_start[i] <= p;
-                        if (cov[u]) { w4[u] = __ldg(wsrc0 + (md >> 11) + tcol); pid[u] = __ldg(a.rd.seg_pair + lo + i); }
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const int i = g0 + u * 32 + lane;
+                s4[u] = 0; n4[u] = 0; pid[u] = -1; w4[u] = 0;
+                if (i < nc) {
+                    const int64_t g = glo + i;
+                    s4[u] = __ldg(a.rd.seg_start + g);
+                    n4[u] = (int)__ldg(a.rd.seg_len + g);
+                    w4[u] = __ldg(a.rd.seg_word + g);
+                    pid[u] = __ldg(a.rd.seg_pair + g);
                 }
+            }
+            uint32_t wd[4];
+            int sh[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { b4[u] = -1; id4[u] = 0; if (!decode(cov[u], w4[u], pid[u], b4[u], id4[u])) b4[u] = -1; }
-            } else {
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = abs_pos - (int64_t)s4[u];
+                wd[u] = 0u; sh[u] = 0;
+                if (j >= 0 && j < (int64_t)n4[u]) {
+                    const int jn = (int)j + (s4[u] & 7);              // position-aligned stream: nibble index in the segment's words
+                    const int64_t wi = w4[u] + (jn >> 3);
+                    if (wi >= 0 && wi < a.rd.n_words) wd[u] = __ldg(a.rd.words + wi);
+                    sh[u] = (jn & 7) << 2;
+                }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = g0 + u * 32 + lane;
-                    b4[u] = -1; id4[u] = 0;
-                    int b = 0, id = 0;
-                    if (i < ch_ && k3r_candidate(a.rd, glo + i, abs_pos, b, id) && id >= 0 && (int64_t)id < a.n_pairs && ((bases >> b) & 1u)) {
-                        b4[u] = b; id4[u] = id;
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t c = (wd[u] >> sh[u]) & 15u;
+                b4[u] = -1; id4[u] = 0;
+                if (c) {
+                    const int b = __ffs((int)c) - 1;                   // one-hot A,C,T,G
+                    if (pid[u] < 0 || (int64_t)pid[u] >= a.n_pairs) atomicOr(a.d_err, ISB_DEV_ERR_SEG);
+                    else if ((bases >> b) & 1u) { b4[u] = b; id4[u] = pid[u]; }
                 }
             }
         };
         int gb[4], gid[4];                                         // group 0
-        group(cl_, gb, gid);
-        int idmin = INT_MAX, idmax = -1;
+        group(0, gb, gid);
+        int idmin = INT_MAX, idmax = -1, n_ent = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (gb[u] >= 0) { idmin = min(idmin, gid[u]); idmax = max(idmax, gid[u]); }
-        for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {            // deep coverage: further groups
+        for (int u = 0; u < 4; ++u) if (gb[u] >= 0) { idmin = min(idmin, gid[u]); idmax = max(idmax, gid[u]); ++n_ent; }
+        for (int g0 = 128; g0 < nc; g0 += 128) {                   // deep coverage: further groups
             int b4[4], id4[4];
             group(g0, b4, id4);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (b4[u] >= 0) { idmin = min(idmin, id4[u]); idmax = max(idmax, id4[u]); }
+            for (int u = 0; u < 4; ++u) if (b4[u] >= 0) { idmin = min(idmin, id4[u]); idmax = max(idmax, id4[u]); ++n_ent; }
         }
         idmin = k1f_warp_min(idmin);
         idmax = k1f_warp_max(idmax);
         isb_site_meta m;
         {                                                          // split of the site: walk forward from the tile's
-            int sp = a.tile_split[tile];
+            int sp = __ldg(a.tile_split + tile);
             while (sp + 1 < a.n_splits && (int64_t)__ldg(a.splits + 2 * (sp + 1)) <= abs_pos) ++sp;
             m.split = (sp >= 0 && abs_pos <= (int64_t)__ldg(a.splits + 2 * sp + 1)) ? sp : -1;
         }
@@ -612,7 +741,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         const int n_words = (1 + 2 * na) * m.nw;
         // Row storage: slot k owns the fixed region [k * ROW_SLOT, + ROW_SLOT); only rows wider than that (deep coverage)
         // are allocated with an atomic behind the sites_cap fixed regions.
-        unsigned long long off = (unsigned long long)slot * ISB_K3_ROW_SLOT;
+        unsigned long long off = (unsigned long long)k * ISB_K3_ROW_SLOT;
         if (n_words > ISB_K3_ROW_SLOT) {
             if (lane == 0) off = (unsigned long long)a.sites_cap * ISB_K3_ROW_SLOT + atomicAdd(a.row_words_total, (unsigned long long)n_words);
             off = __shfl_sync(ISB_FULL, off, 0);
@@ -622,51 +751,32 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
             m.nw = 0;
         }
         if (lane == 0) {
-            a.meta[slot] = m;
-            a.row_off[slot] = (int64_t)off;
-            a.site_pos[slot] = p;
-            a.site_counts[slot] = s_tile[ow * K1F_TILE4 + q + (q >> 3)];
+            a.meta[k] = m;
+            a.row_off[k] = (int64_t)off;
         }
         bool dup = false;
         if (m.nw > 0) {
             uint32_t *g_any = a.rows + off;
-            auto slow_rows = [&]() {                               // exact path with the multiplicity planes (atomics)
-                for (int i = lane; i < n_words; i += 32) g_any[i] = 0u;
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (gb[u] >= 0) k3_row_set(g_any, m, na, bases, gb[u], gid[u], a.d_err);
-                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
-                    int b4[4], id4[4];
-                    group(g0, b4, id4);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (b4[u] >= 0) k3_row_set(g_any, m, na, bases, b4[u], id4[u], a.d_err);
-                }
-                __syncwarp();
-            };
+            n_ent = k1f_warp_sum(n_ent);
+            int n_bits = 0;
             if (m.nw * 32 <= a.code_ids) {
                 // Bit rows by BALLOT.  The site's entries are scattered into a byte map "pair id -> allele code" (ids are
                 // distinct unless a pair entered the site twice: plain stores); then lane l owns bit l of every row word:
                 // word w of the `any` row is ballot(code[32 w + l] != 0), word w of allele row r is ballot(code == r's
-                // base).  ~20 instructions per row word instead of a REDUX / shuffle round per (word, allele) and 32
-                // candidates.  A pair seen twice (htslib's overlap quirk) shows up as fewer set bits than entries: then the
+                // base).  A pair seen twice (htslib's overlap quirk) shows up as fewer set bits than entries: then the
                 // exact slow path rebuilds the rows with the multiplicity planes.
-                uint8_t *code = s_code + wib * a.code_ids;
-                uint32_t *code4 = reinterpret_cast<uint32_t *>(code);
                 for (int i = lane; i < m.nw * 8; i += 32) code4[i] = 0u;
                 __syncwarp();
                 const int id0 = m.wlo << 5;
-                int n_ent = 0;
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (gb[u] >= 0) { code[gid[u] - id0] = (uint8_t)(gb[u] + 1); ++n_ent; }
-                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
+                    if (gb[u] >= 0) code[gid[u] - id0] = (uint8_t)(gb[u] + 1);
+                for (int g0 = 128; g0 < nc; g0 += 128) {
                     int b4[4], id4[4];
                     group(g0, b4, id4);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (b4[u] >= 0) { code[id4[u] - id0] = (uint8_t)(b4[u] + 1); ++n_ent; }
+                        if (b4[u] >= 0) code[id4[u] - id0] = (uint8_t)(b4[u] + 1);
                 }
                 __syncwarp();
                 int b_of[4] = {0, 0, 0, 0};                        // base (+ 1) of allele row r
@@ -676,7 +786,6 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                     for (int b = 0; b < 4; ++b)
                         if ((bases >> b) & 1u) b_of[r++] = b + 1;
                 }
-                int n_bits = 0;
                 for (int w = 0; w < m.nw; ++w) {
                     const int c = code[w * 32 + lane];
                     const unsigned any_w = __ballot_sync(ISB_FULL, c != 0);
@@ -690,38 +799,31 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                     n_bits += __popc(any_w);
                     if (lane <= 2 * na) g_any[(size_t)lane * m.nw + w] = mine;
                 }
-                n_ent = k1f_warp_sum(n_ent);
+                __syncwarp();
                 dup = n_bits != n_ent;
-                if (dup) slow_rows();
+                if (dup)
+                    k3f_slow_rows(a.rd.seg_start, a.rd.seg_len, a.rd.seg_word, a.rd.seg_pair, a.rd.words, a.rd.n_words, a.n_pairs, a.d_err,
+                                  g_any, m.wlo, m.nw, na, bases, glo, nc, abs_pos, lane);
             } else {
-                slow_rows();
+                k3f_slow_rows(a.rd.seg_start, a.rd.seg_len, a.rd.seg_word, a.rd.seg_pair, a.rd.words, a.rd.n_words, a.n_pairs, a.d_err,
+                              g_any, m.wlo, m.nw, na, bases, glo, nc, abs_pos, lane);
                 // a pair with two entries sets a bit of `any` that is already set: detect it by counting
-                int n_ent = 0, n_bits = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) n_ent += gb[u] >= 0;
-                for (int g0 = cl_ + 128; g0 < ch_; g0 += 128) {
-                    int b4[4], id4[4];
-                    group(g0, b4, id4);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) n_ent += b4[u] >= 0;
-                }
                 for (int i = lane; i < m.nw; i += 32) n_bits += __popc(g_any[i]);
-                dup = k1f_warp_sum(n_bits) != k1f_warp_sum(n_ent);
+                dup = k1f_warp_sum(n_bits) != n_ent;
             }
         }
-        if (lane == 0) a.has2[slot] = dup ? 1 : 0;
+        if (lane == 0) a.has2[k] = dup ? 1 : 0;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 
-static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg, int code_ids = 0)
+static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
 {
     size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
-    if (fuse)
-        b += 4 * 2 * K1F_THREADS + 4 * 16 + 2 * K1F_WARPS * 256 + K1F_WARPS * 256 + (size_t)K1F_WARPS * code_ids;
+    if (fuse) b += 4 * 2 * K1F_THREADS + 4 * 16 + K1F_WARPS * 256;
     return b;
 }
 
@@ -789,14 +891,14 @@ int isb_k1f_pileup_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_m
     return ISB_OK;
 }
 
-// Fused path: K1f<fused> (+ the linkage back end when `ld` is given).  Counters: [0] SNV rows, [1] LD rows, [2] sites,
-// [3] linked site pairs, [4] overflow row words; nothing is read back here.
+// Fused path: K1f<fused> -> k2q_sites (-> k3f_site_rows -> the linkage back end when `ld` is given).  Counters: [0] SNV
+// rows, [1] LD rows, [2] sites, [3] linked site pairs, [4] overflow row words, [5] queued sites; nothing is read back here.
 int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int32_t start, int32_t L,
                            unsigned long long *nmask, const isb_k2_fuse *fuse, const isb_k1f_linkage *ld)
 {
     cudaStream_t st = ctx->stream;
     int rc, seg_cap = 0;
-    ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), st));
+    ISB_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 6 * sizeof(unsigned long long), st));
     if (L <= 0) return ISB_OK;
     int32_t *tile_split = nullptr;
     if ((rc = k1f_prepare(ctx, rd, start, L, &seg_cap, ld ? ld->splits : nullptr, ld ? ld->n_splits : 0, ld ? &tile_split : nullptr))) return rc;
@@ -805,17 +907,48 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         ISB_CUDA(cudaMemsetAsync(nmask, 0, sizeof(unsigned long long) * (size_t)L, st));
         if ((rc = isb_k1r_n_events_launch(ctx, rd->n_nev, rd->nev_pos, rd->nev_pair, nullptr, n_pairs, start, L, 1, nmask))) return rc;
     }
+    const int n_tiles = rd->n_tiles;
+    // Site queue: sites with a second base (mostly sequencing errors: their share grows with the coverage) and, with
+    // min_cov < 1, every position.  First guess from the mean coverage, grown on demand (isb_k1f_grow);
+    // ISB_K1F_QUEUE_INIT forces a small first guess (tests of the re-run path).
+    static const int64_t queue_init = getenv("ISB_K1F_QUEUE_INIT") ? atoll(getenv("ISB_K1F_QUEUE_INIT")) : 0;
+    {
+        const double cov = (double)rd->n_words * 8.0 / (double)L;
+        double share = fuse->min_cov < 1 ? 1.0 : 0.10 + cov / 400.0;
+        if (share > 1.0) share = 1.0;
+        int64_t want = queue_init > 0 ? queue_init : (int64_t)((double)L * share) + 4096;
+        if (want > (int64_t)L + 32) want = (int64_t)L + 32;
+        if (ctx->queue_cap < want) ctx->queue_cap = want;
+    }
+    const int64_t qcap = ctx->queue_cap;
+    if ((rc = isb_ensure(ctx, SL_Q_TILE, sizeof(int32_t) * 2 * (size_t)n_tiles))) return rc;
+    if ((rc = isb_ensure(ctx, SL_Q_POS, sizeof(int32_t) * (size_t)qcap))) return rc;
+    if ((rc = isb_ensure(ctx, SL_Q_E, sizeof(int4) * (size_t)qcap))) return rc;
+    if ((rc = isb_ensure(ctx, SL_Q_CAND, sizeof(uint32_t) * (size_t)qcap))) return rc;
     k1f_args a;
     memset(&a, 0, sizeof(a));
     a.rd = *rd; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = 1; a.d_err = ctx->d_err; a.seg_cap = seg_cap;
-    a.nmask = nmask;
     a.k2 = *fuse;
-    a.thr2 = ctx->d_thr2; a.n_lut = ctx->n_lut; a.lut_default = ctx->lut_default;
-    a.n_rows = ctx->d_counters + 0;
+    a.thr2 = ctx->d_thr2; a.n_lut = ctx->n_lut;
+    a.q_first = (int32_t *)ctx->buf[SL_Q_TILE].p;
+    a.q_cnt = a.q_first + n_tiles;
+    a.q_pos = (int32_t *)ctx->buf[SL_Q_POS].p;
+    a.q_E = (int4 *)ctx->buf[SL_Q_E].p;
+    a.q_cand = (uint32_t *)ctx->buf[SL_Q_CAND].p;
+    a.q_cap = qcap;
+    a.n_queue = ctx->d_counters + 5;
+
+    k2q_args b;
+    memset(&b, 0, sizeof(b));
+    b.n_tiles = n_tiles; b.q_first = a.q_first; b.q_cnt = a.q_cnt; b.q_pos = a.q_pos; b.q_E = a.q_E; b.q_cand = a.q_cand; b.q_cap = qcap;
+    b.start = start; b.L = L; b.nmask = nmask; b.k2 = *fuse; b.thr2 = ctx->d_thr2; b.n_lut = ctx->n_lut; b.lut_default = ctx->lut_default;
+    b.n_rows = ctx->d_counters + 0; b.counts = nullptr; b.d_err = ctx->d_err;
+
+    k3f_args c;
+    memset(&c, 0, sizeof(c));
     isb_k3_tiles ts;
     memset(&ts, 0, sizeof(ts));
     if (ld) {
-        const int n_tiles = rd->n_tiles;
         // site slots: 1 % SNV sites with headroom, grown on demand (isb_k1f_grow); ISB_K1F_SITES_INIT forces a small
         // first guess (tests of the re-run path)
         static const int64_t sites_init = getenv("ISB_K1F_SITES_INIT") ? atoll(getenv("ISB_K1F_SITES_INIT")) : 0;
@@ -824,48 +957,62 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         const int64_t cap = ctx->sites_cap;
         if ((rc = isb_ensure(ctx, SL_TILE_SITES, sizeof(int32_t) * 2 * (size_t)n_tiles))) return rc;
         if ((rc = isb_ensure(ctx, SL_SITE_POS, sizeof(int32_t) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_SITE_CAND, sizeof(uint32_t) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_SITE_META, sizeof(isb_site_meta) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_ROW_OFF, sizeof(int64_t) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_HAS2, (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_SITE_COUNTS, sizeof(int4) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_ROWS, sizeof(uint32_t) * ((size_t)cap * (ISB_K3_ROW_SLOT + 8) + 64)))) return rc;
-        a.do_ld = 1;
-        a.n_splits = ld->n_splits; a.splits = ld->splits;
-        a.tile_first = (int32_t *)ctx->buf[SL_TILE_SITES].p;
-        a.tile_cnt = a.tile_first + n_tiles;
-        a.tile_split = tile_split;
-        a.sites_cap = cap;
-        a.site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
-        a.meta = (isb_site_meta *)ctx->buf[SL_SITE_META].p;
-        a.row_off = (int64_t *)ctx->buf[SL_ROW_OFF].p;
-        a.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;
-        a.site_counts = (int4 *)ctx->buf[SL_SITE_COUNTS].p;
-        a.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
-        a.row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
-        a.n_sites = ctx->d_counters + 2;
-        a.row_words_total = ctx->d_counters + 4;
-        ts.n_tiles = n_tiles; ts.tile_first = a.tile_first; ts.tile_cnt = a.tile_cnt; ts.sites_cap = cap;
-        ts.site_pos = a.site_pos; ts.meta = a.meta; ts.row_off = a.row_off; ts.has2 = a.has2; ts.site_counts = a.site_counts;
-        ts.rows = a.rows;
+        b.do_ld = 1;
+        b.tile_first = (int32_t *)ctx->buf[SL_TILE_SITES].p;
+        b.tile_cnt = b.tile_first + n_tiles;
+        b.sites_cap = cap;
+        b.site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
+        b.site_counts = (int4 *)ctx->buf[SL_SITE_COUNTS].p;
+        b.site_cand = (uint32_t *)ctx->buf[SL_SITE_CAND].p;
+        b.n_sites = ctx->d_counters + 2;
+        c.rd = *rd; c.n_pairs = n_pairs; c.start = start; c.L = L; c.site_flags = fuse->site_flags;
+        c.n_splits = ld->n_splits; c.splits = ld->splits; c.tile_split = tile_split;
+        c.sites_cap = cap; c.site_pos = b.site_pos; c.site_cand = b.site_cand;
+        c.meta = (isb_site_meta *)ctx->buf[SL_SITE_META].p;
+        c.row_off = (int64_t *)ctx->buf[SL_ROW_OFF].p;
+        c.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;
+        c.rows = (uint32_t *)ctx->buf[SL_ROWS].p;
+        c.row_cap = (int64_t)(ctx->buf[SL_ROWS].cap / sizeof(uint32_t));
+        c.n_sites = ctx->d_counters + 2;
+        c.row_words_total = ctx->d_counters + 4;
+        c.d_err = ctx->d_err;
+        // pair-id window of a site ~ the pairs whose first mate starts within one fragment length before it: sized from the
+        // pair density with headroom, so that the ballot row builder (not the atomic fallback) serves deep coverage too
+        int64_t ids = (int64_t)((double)n_pairs / (L > 0 ? L : 1) * 700.0 * 1.5) + 64;
+        ids = (ids + 255) / 256 * 256;
+        if (ids < K1F_CODE_IDS_MIN) ids = K1F_CODE_IDS_MIN;
+        if (ids > K1F_CODE_IDS_MAX) ids = K1F_CODE_IDS_MAX;
+        c.code_ids = (int)ids;
+        ts.n_tiles = n_tiles; ts.tile_first = b.tile_first; ts.tile_cnt = b.tile_cnt; ts.sites_cap = cap;
+        ts.site_pos = b.site_pos; ts.meta = c.meta; ts.row_off = c.row_off; ts.has2 = c.has2; ts.site_counts = b.site_counts;
+        ts.rows = c.rows;
     }
-    // pair-id window of a site ~ the pairs whose first mate starts within one fragment length before it: sized from the
-    // pair density with headroom, so that the ballot row builder (not the atomic fallback) serves deep coverage too
-    int64_t ids = (int64_t)((double)n_pairs / (L > 0 ? L : 1) * 700.0 * 1.5) + 64;
-    ids = (ids + 255) / 256 * 256;
-    if (ids < K1F_CODE_IDS_MIN) ids = K1F_CODE_IDS_MIN;
-    if (ids > K1F_CODE_IDS_MAX) ids = K1F_CODE_IDS_MAX;
-    a.code_ids = (int)ids;
-    const size_t smem = k1f_smem_bytes(seg_cap, true, true, 0, a.code_ids);
+    const size_t smem = k1f_smem_bytes(seg_cap, true, true, 0);
     static bool attr[64] = {false};
     if (!attr[ctx->device & 63])
         ISB_CUDA(cudaFuncSetAttribute(k1f_pileup<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr[ctx->device & 63] = true;
     int ts0 = isb_time_begin(ctx, 0);
-    k1f_pileup<true, true><<<rd->n_tiles, K1F_THREADS, smem, st>>>(a);
+    k1f_pileup<true, true><<<n_tiles, K1F_THREADS, smem, st>>>(a);
     ISB_LAUNCH_CHECK();
     isb_time_end(ctx, ts0);
+    int ts1 = isb_time_begin(ctx, 1);
+    {
+        const int want = (n_tiles + K2Q_WARPS - 1) / K2Q_WARPS, most = ctx->sm_count * 16;
+        k2q_sites<<<want < most ? want : most, K2Q_WARPS * 32, 0, st>>>(b);
+        ISB_LAUNCH_CHECK();
+    }
+    isb_time_end(ctx, ts1);
     if (ld) {
         int ts2 = isb_time_begin(ctx, 2);
+        k3f_site_rows<<<ctx->sm_count * 8, K3F_WARPS * 32, (size_t)K3F_WARPS * c.code_ids, st>>>(c);
+        ISB_LAUNCH_CHECK();
         rc = isb_k3_backend_tiles(ctx, rd, &ts, n_pairs, start, L, nmask, fuse->site_flags, ld->n_splits, ld->splits, ld->min_snp,
                                   ld->rows, ld->cap);
         isb_time_end(ctx, ts2);
@@ -879,8 +1026,12 @@ int isb_k1f_grow(isb_ctx *ctx, bool *again)
 {
     *again = false;
     const unsigned e = *ctx->h_err;
-    if (e & ~(ISB_DEV_ERR_SITECAP | ISB_DEV_ERR_ROWBUF)) return ISB_OK;   // a real error: the caller reports it
-    const int64_t n_sites = (int64_t)ctx->h_counters[2], n_listed = (int64_t)ctx->h_counters[3];
+    if (e & ~(ISB_DEV_ERR_SITECAP | ISB_DEV_ERR_ROWBUF | ISB_DEV_ERR_QCAP)) return ISB_OK;   // a real error: the caller reports it
+    const int64_t n_sites = (int64_t)ctx->h_counters[2], n_listed = (int64_t)ctx->h_counters[3], n_queue = (int64_t)ctx->h_counters[5];
+    if (n_queue > ctx->queue_cap) {
+        ctx->queue_cap = n_queue + n_queue / 8 + 1024;
+        *again = true;
+    }
     if (n_sites > ctx->sites_cap) {
         ctx->sites_cap = n_sites + n_sites / 8 + 1024;
         *again = true;

@@ -407,7 +407,7 @@ def test_fused_scratch_regrow(null_lut):
             "    assert_snv_equal(got['snv'], exp['snv']); assert_ld_equal(got['ld'], exp['ld'], tol=1e-9)\n"
             "print('regrow ok', len(got['ld']))\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                       os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, ISB_K1F_SITES_INIT="16")
+    env = dict(os.environ, ISB_K1F_SITES_INIT="16", ISB_K1F_QUEUE_INIT="64")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "regrow ok" in r.stdout, r.stdout + r.stderr
 
