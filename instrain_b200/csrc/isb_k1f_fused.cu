@@ -52,7 +52,7 @@
 #define K1F_CODE_IDS_MIN 512           // pair-id window (ids) of a site the ballot row builder handles at least; sized per batch
 #define K1F_CODE_IDS_MAX 4096          // from the pair density (k1f_args.code_ids); wider windows: atomics
 #ifndef K1F_MINB
-#define K1F_MINB 7                     // __launch_bounds__ min blocks per SM of the M = 1 kernels (<= 73 registers; ~32 KB shared)
+#define K1F_MINB 8                     // __launch_bounds__ min blocks per SM of the M = 1 kernels (64 registers; ~28 KB shared)
 #endif
 static_assert(K1F_WARPS == 4, "the site bookkeeping of the fused epilogue assumes 4 warps per tile");
 
@@ -63,6 +63,7 @@ struct k1f_args {
     int32_t start, L;
     int M;
     int seg_cap;                       // segments staged per chunk
+    int pf_ahead;                      // L2 prefetch distance in tiles (0: own tile only)
     int32_t *counts;
     unsigned int *d_err;
     // fused epilogue (M = 1)
@@ -79,27 +80,59 @@ struct k1f_args {
 };
 #define K1F_NO_CAND 0xffffffffu        // q_cand: not known (tile staged in several chunks): k3f_site_rows searches
 
-// tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range, and (linkage) the index of
-// the last split that starts at or before the tile's first position (-1: none) -- the per-site split lookup of the fused
-// kernel walks forward from there instead of searching the whole table (a dependent chain of ~13 L2 round trips per site)
+// First index in [lo, hi) with a[idx * stride] >= key, searched by a whole WARP: 32 probes per round (a 32-ary search: 5
+// dependent memory round trips over 1e7 entries instead of 24).  All lanes return the result.
+__device__ __forceinline__ int64_t k1f_warp_lower_bound(const int32_t *__restrict__ a, int stride, int64_t lo, int64_t hi, int64_t key,
+                                                        int lane)
+{
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) >> 5;
+        int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
+        if (idx > hi - 1) idx = hi - 1;
+        const bool below = (int64_t)__ldg(a + idx * stride) < key;
+        const int c = __popc(__ballot_sync(ISB_FULL, below));     // probes are ascending: the first c are below the key
+        int64_t i_c = lo + (int64_t)(c + 1) * step - 1;           // first probe at or above the key (if c < 32)
+        if (i_c > hi - 1) i_c = hi - 1;
+        int64_t i_p = lo + (int64_t)c * step - 1;                 // last probe below it (if c > 0)
+        if (i_p > hi - 1) i_p = hi - 1;
+        if (c < 32) hi = i_c;
+        if (c > 0) lo = i_p + 1;
+    }
+    const bool below = lo + lane < hi && (int64_t)__ldg(a + (lo + lane) * stride) < key;
+    return lo + __popc(__ballot_sync(ISB_FULL, below));
+}
+
+// tile t covers relative positions [t * TILE, (t + 1) * TILE): its candidate segment range, the piece of the word stream
+// those segments occupy (16-byte aligned: what K1f prefetches into L2), and (linkage) the index of the last split that
+// starts at or before the tile's first position (-1: none) -- the per-site split lookup walks forward from there instead
+// of searching the whole table.  One warp per tile.
 __global__ void __launch_bounds__(256)
-k1f_tile_bounds(const int32_t *__restrict__ seg_start, int64_t n_segs, int32_t start, int n_tiles, int max_seg_len,
-                int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi, const int32_t *__restrict__ splits, int n_splits,
+k1f_tile_bounds(const int32_t *__restrict__ seg_start, const int64_t *__restrict__ seg_word, int64_t n_segs, int64_t n_words,
+                int32_t start, int n_tiles, int max_seg_len, int64_t *__restrict__ tile_lo, int64_t *__restrict__ tile_hi,
+                int64_t *__restrict__ tile_wlo, int64_t *__restrict__ tile_whi, const int32_t *__restrict__ splits, int n_splits,
                 int32_t *__restrict__ tile_split)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (t >= n_tiles) return;                                     // warp-uniform
     const int64_t first = (int64_t)start + (int64_t)t * K1F_TILE;
-    const int64_t lo = isb_lower_bound(seg_start, 0, n_segs, first - max_seg_len + 1);
-    tile_lo[t] = lo;
-    tile_hi[t] = isb_lower_bound(seg_start, lo, n_segs, first + K1F_TILE);
-    if (tile_split) {
-        int s_lo = 0, s_hi = n_splits;
-        while (s_lo < s_hi) {
-            const int mid = (s_lo + s_hi) >> 1;
-            if ((int64_t)__ldg(splits + 2 * mid) <= first) s_lo = mid + 1; else s_hi = mid;
+    const int64_t lo = k1f_warp_lower_bound(seg_start, 1, 0, n_segs, first - max_seg_len + 1, lane);
+    const int64_t hi = k1f_warp_lower_bound(seg_start, 1, lo, n_segs, first + K1F_TILE, lane);
+    int sp = -1;
+    if (tile_split) sp = (int)k1f_warp_lower_bound(splits, 2, 0, n_splits, first + 1, lane) - 1;   // last split with start <= first
+    if (lane == 0) {
+        tile_lo[t] = lo;
+        tile_hi[t] = hi;
+        int64_t b0 = 0, b1 = 0;
+        if (hi > lo) {
+            const int64_t w_first = __ldg(seg_word + lo), w_last = __ldg(seg_word + hi - 1) + (K1F_MAXLEN / 8 + 2);
+            b0 = (w_first - 1 > 0 ? w_first - 1 : 0) & ~(int64_t)3;
+            b1 = (w_last < n_words ? w_last : n_words) & ~(int64_t)3;
+            if (b1 < b0 || b0 > n_words) b0 = b1 = 0;             // a table that breaks the layout rules: K1f reports it
         }
-        tile_split[t] = s_lo - 1;
+        tile_wlo[t] = b0;
+        tile_whi[t] = b1;
+        if (tile_split) tile_split[t] = sp;
     }
 }
 
@@ -164,7 +197,8 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     const uint32_t s_meta_sa = isb_smem_u32(s_meta);                      // its shared-space byte address
     int32_t *s_start = reinterpret_cast<int32_t *>(s_meta + a.seg_cap);   // start relative to a.start (sorted): the search key
     uint8_t *s_mm = reinterpret_cast<uint8_t *>(s_start + a.seg_cap);     // M > 1 only
-    unsigned char *s_x = k1f_smem + ((((size_t)a.seg_cap * (kM1 ? 8 : 9)) + 15) & ~(size_t)15);
+    uint32_t *s_zero = reinterpret_cast<uint32_t *>(k1f_smem + ((((size_t)a.seg_cap * (kM1 ? 8 : 9)) + 15) & ~(size_t)15));   // one zero table word
+    unsigned char *s_x = reinterpret_cast<unsigned char *>(s_zero) + 16;
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_x);                  // M > 1: [Mg * 8][K1F_THREADS]
     // fused epilogue scratch
     int4 *s_tile = reinterpret_cast<int4 *>(s_x);                         // [K1F_WARPS][K1F_TILE4]
@@ -197,18 +231,37 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     } else {
         for (int w = 0; w < Mg * 8; ++w) s_acc[w * K1F_THREADS + t] = 0u;
     }
+    if (t == 0) *s_zero = 0u;                                     // visible after the first barrier of the staging loop
+    const uint32_t zero_sa = isb_smem_u32(s_zero);
     unsigned err = 0;
     int64_t wb = 0;                                               // word base of the (last) chunk
     const int P_end = t * 8 + 256;
 
-    // The words of the tile are one contiguous piece of the stream: ask the TMA engine to pull it into L2 now, while the
-    // block stages its segment table -- the main loop's loads then find L2 hits (~300 cycles) instead of HBM (~1 us).
-    if (t == 0 && hi > lo) {
-        const int64_t w_first = __ldg(a.rd.seg_word + lo), w_last = __ldg(a.rd.seg_word + hi - 1) + (K1F_MAXLEN / 8 + 2);
-        const int64_t b0 = max((int64_t)0, w_first - 1) & ~(int64_t)3;
-        const int64_t b1 = min(a.rd.n_words, w_last) & ~(int64_t)3;
-        if (b1 > b0 && b1 - b0 < (1 << 24))
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.rd.words + b0), "r"((unsigned)((b1 - b0) * 4)) : "memory");
+    // The words of a tile are one contiguous piece of the stream: the TMA engine pulls it into L2 ahead of the loads.  Each
+    // block asks for the tile that starts `pf_ahead` tiles later (blocks start in index order: ~1/8 of a block's lifetime
+    // ahead = several microseconds, many DRAM latencies; ~12 % more data resident in L2) together with its piece of the
+    // segment table, and for its own words in case nobody did (the first tiles of the grid).
+    if (t == 0) {
+        auto pf = [](const void *ptr, int64_t bytes) {
+            const uintptr_t a0 = (uintptr_t)ptr & ~(uintptr_t)15, a1 = ((uintptr_t)ptr + (uintptr_t)bytes + 15) & ~(uintptr_t)15;
+            if (bytes > 0 && a1 - a0 < (1u << 24))
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+        };
+        const int t2 = tile + a.pf_ahead;
+        int64_t w0 = __ldg(a.rd.tile_wlo + tile), w1 = __ldg(a.rd.tile_whi + tile);
+        int64_t lo2 = 0, hi2 = 0, v0 = 0, v1 = 0;
+        if (a.pf_ahead > 0 && t2 < a.rd.n_tiles) {
+            lo2 = __ldg(a.rd.tile_lo + t2); hi2 = __ldg(a.rd.tile_hi + t2);
+            v0 = __ldg(a.rd.tile_wlo + t2); v1 = __ldg(a.rd.tile_whi + t2);
+        }
+        if (tile < a.pf_ahead || a.pf_ahead <= 0) pf(a.rd.words + w0, (w1 - w0) * 4);
+        if (hi2 > lo2) {
+            pf(a.rd.words + v0, (v1 - v0) * 4);
+            pf(a.rd.seg_start + lo2, (hi2 - lo2) * 4);
+            pf(a.rd.seg_len + lo2, (hi2 - lo2) * 2);
+            pf(a.rd.seg_word + lo2, (hi2 - lo2) * 8);
+            if (!kM1) pf(a.rd.seg_pair + lo2, (hi2 - lo2) * 4);
+        }
     }
     for (int64_t c0 = lo; c0 < hi; c0 += a.seg_cap) {
         const int nc = (int)min((int64_t)a.seg_cap, hi - c0);
@@ -305,17 +358,18 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
         // pointer every predicated load re-derived the shared window base, 4 extra instructions each)
         const uint32_t ja_cl = s_meta_sa + 4u * (uint32_t)cl, ja_ch = s_meta_sa + 4u * (uint32_t)ch, ja_wrap = s_meta_sa + 4u * (uint32_t)wrap;
         uint32_t ja = s_meta_sa + 4u * (uint32_t)j;
-        // table word of the lane's current segment; bit 31 (unused: the index field holds < 2^20) = "beyond the lane's range"
-        auto meta_at = [&](uint32_t &jj) -> uint32_t {            // jj may run past ch (into the start column): flagged
+        // table word of the lane's current segment; a step beyond the lane's range (jj may run past ch, into the start
+        // column) reads the zero word instead: end field 0 = "covers nothing"
+        auto meta_at = [&](uint32_t &jj) -> uint32_t {
             uint32_t md;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(md) : "r"(jj));
-            md |= jj < ja_ch ? 0u : 0x80000000u;
+            const uint32_t src = jj < ja_ch ? jj : zero_sa;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(md) : "r"(src));
             jj = (jj + 4u == ja_wrap) ? ja_cl : jj + 4u;
             return md;
         };
         auto word_of = [&](uint32_t md) -> uint32_t {
-            const bool ok = (int)md >= 0 && P_end < (int)(md & 0x7ffu);
-            return ok ? __ldg(wsrc + (md >> 11)) : 0u;              // ok => bit 31 clear: the shift leaves the index only
+            const bool ok = P_end < (int)(md & 0x7ffu);
+            return ok ? __ldg(wsrc + (md >> 11)) : 0u;
         };
         if (kM1) {
             // Software pipeline: the 8 loads of block b + 1 are issued before the carry-save adds of block b, so a warp
@@ -414,9 +468,15 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
     // Keeping the double-precision site arithmetic, the re-drawn clonality and the linkage row builder out of this kernel
     // keeps its code inside the instruction caches: the one-kernel version spent a third of its issue slots waiting for
     // instruction fetches (ncu: stall_no_inst 5.2 per issue, 138 KB of SASS).
+    const int32_t W0 = T0 + wib * 256;
+    unsigned long long ref8 = 0ull;                               // reference bases of the lane's 8 epilogue positions: requested
+#pragma unroll                                                    // now, used after the flush (the loads were the longest stall)
+    for (int rd = 0; rd < 8; ++rd) {
+        const int32_t p = W0 + rd * 32 + lane;
+        if (p < a.L) ref8 |= (unsigned long long)__ldg(a.k2.ref + p) << (8 * rd);
+    }
     k1f_flush_planes(tile_lane, pl);
     __syncwarp();
-    const int32_t W0 = T0 + wib * 256;
     int4 *counts4 = reinterpret_cast<int4 *>(a.counts);
     const bool full_counts = a.counts != nullptr && a.k2.full_counts;
     uint8_t *q_list = s_q + wib * 256;
@@ -438,7 +498,7 @@ __global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1
                 simple = true;                                    // call_snv_site -> (None, 0): coverage only
             } else if (mx == T && T < a.n_lut) {                  // one base only: clonality exactly 1; a row unless it is the
                 const int con = E.x == T ? 0 : (E.y == T ? 1 : (E.z == T ? 2 : 3));   // reference base and passes the threshold
-                if (T >= __ldg(a.thr2 + T) && con == (int)a.k2.ref[p]) { simple = true; clon = 1.0f; }
+                if (T >= __ldg(a.thr2 + T) && con == (int)((ref8 >> (8 * rd)) & 0xffull)) { simple = true; clon = 1.0f; }
             }
             if (simple && cov_r > 0 && T >= cov_r) {              // rarefied clonality: 1 with one base only, else drawn (queue)
                 if (mx == T) clonr = 1.0f; else simple = false;
@@ -512,7 +572,11 @@ struct k2q_args {
     int64_t sites_cap;
     int32_t *site_pos;
     int4 *site_counts;
-    uint32_t *site_cand;
+    int4 *site_rec;                    // position, candidate range, allele set, split: all k3f_site_rows needs, one load
+    int32_t n_splits;
+    const int32_t *splits;
+    const int32_t *tile_split;
+    const int64_t *tile_lo;
     unsigned long long *n_sites;
 };
 
@@ -582,10 +646,25 @@ __global__ void __launch_bounds__(K2Q_WARPS * 32) k2q_sites(k2q_args a)
                 atomicOr(a.d_err, ISB_DEV_ERR_SITECAP);
                 break;
             }
-            const int64_t idx = first + (s_sites[wib][i] & 0x3ffu);
-            a.site_pos[slot] = __ldg(a.q_pos + idx);
+            const unsigned ent = s_sites[wib][i];
+            const int64_t idx = first + (ent & 0x3ffu);
+            const int32_t p = __ldg(a.q_pos + idx);
+            const int64_t abs_pos = (int64_t)p + a.start;
+            int sp = __ldg(a.tile_split + tile);                  // split of the site: walk forward from the tile's
+            while (sp + 1 < a.n_splits && (int64_t)__ldg(a.splits + 2 * (sp + 1)) <= abs_pos) ++sp;
+            if (!(sp >= 0 && abs_pos <= (int64_t)__ldg(a.splits + 2 * sp + 1))) sp = -1;
+            a.site_pos[slot] = p;
             a.site_counts[slot] = __ldg(a.q_E + idx);
-            a.site_cand[slot] = __ldg(a.q_cand + idx);
+            // record: position | first candidate segment (low 32 bits) | its bits 32..39, allele set << 8, candidates << 12
+            // (bit 31: range not known, search) | split
+            const uint32_t cand = __ldg(a.q_cand + idx);
+            int4 rec = make_int4(p, 0, (int)(0x80000000u | ((ent >> 12) << 8)), sp);
+            if (cand != K1F_NO_CAND) {
+                const int64_t glo = __ldg(a.tile_lo + tile) + (int64_t)(cand & 0xffffu);
+                rec.y = (int)(uint32_t)(glo & 0xffffffffll);
+                rec.z = (int)((uint32_t)((glo >> 32) & 0xff) | ((ent >> 12) << 8) | ((cand >> 16) << 12));
+            }
+            a.site_rec[slot] = rec;
         }
         __syncwarp();
     }
@@ -599,13 +678,8 @@ struct k3f_args {
     isb_reads_dev rd;
     int64_t n_pairs;
     int32_t start, L;
-    const uint8_t *site_flags;
-    int32_t n_splits;
-    const int32_t *splits;
-    const int32_t *tile_split;
     int64_t sites_cap;
-    const int32_t *site_pos;
-    const uint32_t *site_cand;
+    const int4 *site_rec;              // position, candidate range (K1F_NO_CAND: search), allele set, split
     isb_site_meta *meta;
     int64_t *row_off;
     uint8_t *has2;
@@ -647,7 +721,10 @@ __device__ __noinline__ void k3f_slow_rows(const int32_t *__restrict__ seg_start
 }
 
 #define K3F_WARPS 8
-__global__ void __launch_bounds__(K3F_WARPS * 32) k3f_site_rows(k3f_args a)
+#ifndef K3F_MINB
+#define K3F_MINB 4                    // resident blocks of 256 threads per SM the register budget is set for
+#endif
+__global__ void __launch_bounds__(K3F_WARPS * 32, K3F_MINB) k3f_site_rows(k3f_args a)
 {
     extern __shared__ __align__(16) unsigned char k3f_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -656,24 +733,25 @@ __global__ void __launch_bounds__(K3F_WARPS * 32) k3f_site_rows(k3f_args a)
     const unsigned long long ns_dev = *a.n_sites;
     const int64_t S = (int64_t)(ns_dev < (unsigned long long)a.sites_cap ? ns_dev : (unsigned long long)a.sites_cap);
     const int maxlen = a.rd.max_seg_len;
-    for (int64_t k = (int64_t)blockIdx.x * K3F_WARPS + wib; k < S; k += (int64_t)gridDim.x * K3F_WARPS) {
-        const int32_t p = __ldg(a.site_pos + k);
-        const uint32_t cand = __ldg(a.site_cand + k);
+    const int64_t k0 = (int64_t)blockIdx.x * K3F_WARPS + wib, k_step = (int64_t)gridDim.x * K3F_WARPS;
+    int4 rec_next = k0 < S ? __ldg(a.site_rec + k0) : make_int4(0, 0, 0, 0);
+    for (int64_t k = k0; k < S; k += k_step) {
+        const int4 rec = rec_next;
+        if (k + k_step < S) rec_next = __ldg(a.site_rec + k + k_step);   // the next site's record travels while this one is built
+        const int32_t p = rec.x;
+        const uint32_t rz = (uint32_t)rec.z;
         const int64_t abs_pos = (int64_t)p + a.start;
-        const unsigned bases = a.site_flags[p] & 0xFu;
+        const unsigned bases = (rz >> 8) & 0xFu;
         const int na = __popc(bases);
-        const int tile = p / K1F_TILE;
-        const int64_t lo = __ldg(a.rd.tile_lo + tile), hi = __ldg(a.rd.tile_hi + tile);
-        int64_t glo;
-        int nc;
-        if (cand != K1F_NO_CAND) {
-            glo = lo + (int64_t)(cand & 0xffffu);
-            nc = (int)(cand >> 16);
-            if (glo + nc > hi) nc = glo < hi ? (int)(hi - glo) : 0;
-        } else {
+        int64_t glo = (int64_t)(uint32_t)rec.y | ((int64_t)(rz & 0xffu) << 32);
+        int nc = (int)((rz >> 12) & 0x1fffu);
+        if (rz & 0x80000000u) {                                    // tile staged in several chunks (deep coverage): search
+            const int tile = p / K1F_TILE;
+            const int64_t lo = __ldg(a.rd.tile_lo + tile), hi = __ldg(a.rd.tile_hi + tile);
             glo = isb_lower_bound(a.rd.seg_start, lo, hi, abs_pos - maxlen + 1);
             nc = (int)(isb_lower_bound(a.rd.seg_start, glo, hi, abs_pos + 1) - glo);
         }
+        if (glo < 0 || glo + nc > a.rd.n_segs) nc = 0;
         // Candidates in groups of 4 x 32: the table loads of a whole group are issued together, then its word loads (two
         // memory latencies per group instead of three per 32 candidates); group 0 -- all of them up to ~120x coverage --
         // stays decoded in registers for the second pass.
@@ -730,11 +808,7 @@ __global__ void __launch_bounds__(K3F_WARPS * 32) k3f_site_rows(k3f_args a)
         idmin = k1f_warp_min(idmin);
         idmax = k1f_warp_max(idmax);
         isb_site_meta m;
-        {                                                          // split of the site: walk forward from the tile's
-            int sp = __ldg(a.tile_split + tile);
-            while (sp + 1 < a.n_splits && (int64_t)__ldg(a.splits + 2 * (sp + 1)) <= abs_pos) ++sp;
-            m.split = (sp >= 0 && abs_pos <= (int64_t)__ldg(a.splits + 2 * sp + 1)) ? sp : -1;
-        }
+        m.split = rec.w;
         m.ev_lo_rel = 0;
         m.wlo = idmax >= 0 ? (idmin >> 5) : 0;
         m.nw = idmax >= 0 ? (idmax >> 5) - (idmin >> 5) + 1 : 0;
@@ -820,11 +894,20 @@ __global__ void __launch_bounds__(K3F_WARPS * 32) k3f_site_rows(k3f_args a)
 
 static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
 {
-    size_t b = (((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15;
+    size_t b = ((((size_t)seg_cap * (m1 ? 8 : 9)) + 15) & ~(size_t)15) + 16;   // staged table + the zero word
     if (!m1) b += (size_t)Mg * 8 * K1F_THREADS * 4;
     else b += sizeof(int4) * K1F_WARPS * K1F_TILE4;                // the count quads of the tile
     if (fuse) b += 4 * 2 * K1F_THREADS + 4 * 16 + K1F_WARPS * 256;
     return b;
+}
+
+// L2 prefetch distance: half a tile per SM ahead (ISB_K1F_PF overrides it; 0 = every block prefetches its own tile only).
+// Measured (B200, 2e7 positions at 100x): 0 -> 0.428 ms, 74 -> 0.424, 148 -> 0.438, 296 -> 0.468: the loads are not
+// waiting for DRAM any more; further ahead only displaces data that is still needed.
+static int k1f_pf_ahead(const isb_ctx *ctx)
+{
+    static const int env = getenv("ISB_K1F_PF") ? atoi(getenv("ISB_K1F_PF")) : -1;
+    return env >= 0 ? env : ctx->sm_count / 2;
 }
 
 // tile bounds + staging capacity of a batch
@@ -838,17 +921,19 @@ static int k1f_prepare(isb_ctx *ctx, isb_reads_dev *rd, int32_t start, int32_t L
     if (start & 7) return isb_fail(ctx, ISB_ERR_ARG, "read-major batch: start must be a multiple of 8 (the stream is position-aligned)");
     const int n_tiles = (L + K1F_TILE - 1) / K1F_TILE;
     int rc;
-    if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 4 * (size_t)n_tiles))) return rc;
+    if ((rc = isb_ensure(ctx, SL_RD_BOUNDS, sizeof(int64_t) * 5 * (size_t)n_tiles))) return rc;
     int64_t *tile_lo = (int64_t *)ctx->buf[SL_RD_BOUNDS].p, *tile_hi = tile_lo + n_tiles;
-    int32_t *tile_split = tile_split_out ? (int32_t *)(tile_hi + n_tiles) : nullptr;
-    k1f_tile_bounds<<<(n_tiles + 255) / 256, 256, 0, st>>>(rd->seg_start, rd->n_segs, start, n_tiles, rd->max_seg_len, tile_lo, tile_hi,
-                                                           splits, n_splits, tile_split);
+    int64_t *tile_wlo = tile_hi + n_tiles, *tile_whi = tile_wlo + n_tiles;
+    int32_t *tile_split = tile_split_out ? (int32_t *)(tile_whi + n_tiles) : nullptr;
+    k1f_tile_bounds<<<(n_tiles + 7) / 8, 256, 0, st>>>(rd->seg_start, rd->seg_word, rd->n_segs, rd->n_words, start, n_tiles,
+                                                       rd->max_seg_len, tile_lo, tile_hi, tile_wlo, tile_whi, splits, n_splits, tile_split);
     ISB_LAUNCH_CHECK();
     if (tile_split_out) *tile_split_out = tile_split;
     rd->n_tiles = n_tiles;
     rd->tile_lo = tile_lo;
     rd->tile_hi = tile_hi;
-    rd->tile_wlo = rd->tile_whi = nullptr;
+    rd->tile_wlo = tile_wlo;
+    rd->tile_whi = tile_whi;
     // staging capacity: what a tile holds on average + 15 % + 48 (the Poisson spread of ~800 segments is 3.5 %), capped
     int64_t cap = rd->n_segs > 0 ? (int64_t)((double)rd->n_segs / L * (K1F_TILE + rd->max_seg_len) * 1.12) + 40 : 64;
     if (cap < 64) cap = 64;
@@ -868,7 +953,7 @@ int isb_k1f_pileup_launch(isb_ctx *ctx, isb_reads_dev *rd, const uint8_t *pair_m
     k1f_args a;
     memset(&a, 0, sizeof(a));
     a.rd = *rd; a.pair_mm = pair_mm; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = M; a.counts = counts;
-    a.d_err = ctx->d_err; a.seg_cap = seg_cap;
+    a.d_err = ctx->d_err; a.seg_cap = seg_cap; a.pf_ahead = k1f_pf_ahead(ctx);
     const int groups = M == 1 ? 1 : (M + K1F_LEVELS - 1) / K1F_LEVELS;
     const int Mg = M == 1 ? 0 : (M < K1F_LEVELS ? M : K1F_LEVELS);
     const size_t smem = k1f_smem_bytes(seg_cap, M == 1, false, Mg);
@@ -927,7 +1012,7 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
     if ((rc = isb_ensure(ctx, SL_Q_CAND, sizeof(uint32_t) * (size_t)qcap))) return rc;
     k1f_args a;
     memset(&a, 0, sizeof(a));
-    a.rd = *rd; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = 1; a.d_err = ctx->d_err; a.seg_cap = seg_cap;
+    a.rd = *rd; a.n_pairs = n_pairs; a.start = start; a.L = L; a.M = 1; a.d_err = ctx->d_err; a.seg_cap = seg_cap; a.pf_ahead = k1f_pf_ahead(ctx);
     a.k2 = *fuse;
     a.thr2 = ctx->d_thr2; a.n_lut = ctx->n_lut;
     a.q_first = (int32_t *)ctx->buf[SL_Q_TILE].p;
@@ -957,7 +1042,7 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         const int64_t cap = ctx->sites_cap;
         if ((rc = isb_ensure(ctx, SL_TILE_SITES, sizeof(int32_t) * 2 * (size_t)n_tiles))) return rc;
         if ((rc = isb_ensure(ctx, SL_SITE_POS, sizeof(int32_t) * (size_t)cap))) return rc;
-        if ((rc = isb_ensure(ctx, SL_SITE_CAND, sizeof(uint32_t) * (size_t)cap))) return rc;
+        if ((rc = isb_ensure(ctx, SL_SITE_CAND, sizeof(int4) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_SITE_META, sizeof(isb_site_meta) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_ROW_OFF, sizeof(int64_t) * (size_t)cap))) return rc;
         if ((rc = isb_ensure(ctx, SL_HAS2, (size_t)cap))) return rc;
@@ -969,11 +1054,11 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
         b.sites_cap = cap;
         b.site_pos = (int32_t *)ctx->buf[SL_SITE_POS].p;
         b.site_counts = (int4 *)ctx->buf[SL_SITE_COUNTS].p;
-        b.site_cand = (uint32_t *)ctx->buf[SL_SITE_CAND].p;
+        b.site_rec = (int4 *)ctx->buf[SL_SITE_CAND].p;
+        b.n_splits = ld->n_splits; b.splits = ld->splits; b.tile_split = tile_split; b.tile_lo = rd->tile_lo;
         b.n_sites = ctx->d_counters + 2;
-        c.rd = *rd; c.n_pairs = n_pairs; c.start = start; c.L = L; c.site_flags = fuse->site_flags;
-        c.n_splits = ld->n_splits; c.splits = ld->splits; c.tile_split = tile_split;
-        c.sites_cap = cap; c.site_pos = b.site_pos; c.site_cand = b.site_cand;
+        c.rd = *rd; c.n_pairs = n_pairs; c.start = start; c.L = L;
+        c.sites_cap = cap; c.site_rec = b.site_rec;
         c.meta = (isb_site_meta *)ctx->buf[SL_SITE_META].p;
         c.row_off = (int64_t *)ctx->buf[SL_ROW_OFF].p;
         c.has2 = (uint8_t *)ctx->buf[SL_HAS2].p;

@@ -1,7 +1,7 @@
 """profile_bam with the opt-in host -> device formats (kwargs["b200_transfer"]): the reference-delta transfer format
 (C++ host encoder -> K0d -> K1r) and column words laid out on the host (C++ host conversion -> K1c) give exactly the
-tables of the default read-major path on a real BAM; so does packing the scaffolds on several host threads.  (Named to sort last: these paths were added after the last GPU
-session of round 1; their pieces are covered by test_gpu_reads.py / test_gpu_cols.py / the CPU suite.)"""
+tables of the default read-major path on a real BAM; so does packing the scaffolds on several host threads.  (Named to sort last; the pieces are covered by test_gpu_reads.py / test_gpu_cols.py / the CPU suite.  The chunk
+pipeline tests ran green on a B200 in round 2: gpurun_out/r2l_pytest_exp.log.)"""
 import json
 import os
 
@@ -11,14 +11,6 @@ import pytest
 from conftest import GOLDEN
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
-# The chunk pipeline below was written after the last GPU session of round 1 and has not run on a GPU: it runs only when
-# asked for, so that an untested kernel path can neither fail nor hang the suite.  (The transfer formats / packer threads
-# of the first test are validated end to end on the CPU with the oracle as engine, tests/test_profile_host_cpu.py, and
-# their GPU entry points by tests/test_gpu_reads.py / test_gpu_cols.py.)
-experimental = pytest.mark.skipif(os.environ.get("ISB_TEST_EXPERIMENTAL") != "1",
-                                  reason="not yet validated on a GPU; set ISB_TEST_EXPERIMENTAL=1")
-
-
 @pytest.mark.parametrize("transfer,threads", [("delta", 1), ("cols", 1), ("segments", 3)])
 def test_profile_bam_transfer_formats(transfer, threads):
     from instrain_b200.profile import profile_bam
@@ -46,7 +38,6 @@ def test_profile_bam_transfer_formats(transfer, threads):
             assert a.scaffolds[s].clonT[m].equals(b.scaffolds[s].clonT[m])
 
 
-@experimental
 @pytest.mark.parametrize("skip_mm,lean", [(True, True), (True, False), (False, False)])
 def test_cols_chunk_pipeline_equals_single_pass(skip_mm, lean):
     """ISB_PIPELINE on the column-word path (opt-in): K1c of all chunks back to back on the main stream, K3 (+ K2 when not
