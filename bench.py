@@ -496,16 +496,16 @@ def main():
         fused = M == 1 and job.lean and os.environ.get("ISB_K1F", "1") != "0"
         in_bytes = int(rd["n_words"]) * 4 + int(rd["n_segs"]) * 14              # nibble stream + (start i32, len u16, word i64) per segment
         if fused:
-            n_sites = max(0, int(res.n_sites))
-            out_bytes = Ltot * (1 + 4 + 4 + 4 + 1) + int(res.n_snv) * 32 + n_sites * 49
-            roofline = rl("k1f_pileup<M=1, fused SNV call + linkage site rows>", in_bytes + out_bytes, k1_ms, "K1f_fused_M1", Ltot,
+            out_bytes = Ltot * (1 + 4 + 4 + 4 + 1)
+            roofline = rl("k1f_pileup<M=1, fused: coverage + single-allele sites + site queue>", in_bytes + out_bytes, k1_ms, "K1f_fused_M1", Ltot,
                           "4 bits per aligned base (nibble stream incl. separators) + 14 B per segment + 1 B reference per position in; "
-                          "covT 4 + clonT 4 + clonTR 4 + site_flags 1 B per position, 32 B per SNV row, 49 B per linkage site (slot record + counts; "
-                          "its bit rows not counted) out",
+                          "covT 4 + clonT 4 + clonTR 4 + site_flags 1 B per position out (the ~12 % of the sites that go to the site queue "
+                          "get a 24-byte queue entry instead of the last three: not counted)",
                           achieved_survey_def=(10.0 * n_ev + (8 * M + 1) * Ltot) / k1_ms / 1e6,
                           survey_def="SURVEY 8(d): 10 B per aligned base (ref_pos, base, qual, read_id columns) + 8 M + 1 B per position, "
                                      "fused; the layout here is 16x smaller, so this figure can exceed the HBM peak",
-                          note="ONE kernel from BAM-order segments: pileup counts + per-site SNV call + bit rows of the linkage sites")
+                          note="pileup from BAM-order segments; the step's other kernels: k2q_sites (general SNV call on the queued sites, "
+                               "stage k2_snv), k3f_site_rows + k3_enum_pairs_tiles + k3_pair_stats_dev + k3_self_edges (stage k3_linkage)")
         else:
             alg = in_bytes + int(rd["n_segs"]) * (4 if M > 1 else 0) + 16 * M * Ltot + 8 * Ltot
             roofline = rl("k1f_pileup<M=1>" if M == 1 else "k1f_pileup<M>1>", alg, k1_ms, "K1r_M1" if M == 1 else "K1r_Mgt1", Ltot,
