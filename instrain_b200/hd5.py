@@ -11,7 +11,7 @@ against test/test_data/*.forRC.IS/raw_data/covT.hd5):
   root group: v1 object header with a symbol-table message -> v1 B-tree (node type 0) -> SNOD leaves + local heap
   dataset:    v1 object header {dataspace v1 (rank 2, max dims), datatype v1 (int64 LE / IEEE float64 LE),
               fill value v2, filter pipeline v1 (deflate, level 4), layout v3 chunked -> v1 B-tree (node type 1)}
-  chunks:     1 x C rows, zlib streams, edge chunks padded with the fill value (0)
+  chunks:     h5py's guess_chunk shapes (R x C), zlib streams, edge chunks padded with the fill value (0)
 
 `read_hd5` parses exactly that dialect (it reads the reference's stored files, which is how tests pin the covT / clonT
 arrays of the hot path at EVERY position, not only at SNV sites) and `write_hd5` emits it.
@@ -194,6 +194,94 @@ def read_hd5(path, names=None):
     return {n: r.dataset(a) for n, a in entries.items() if names is None or n in names}
 
 
+def describe_hd5(path, max_datasets=None):
+    """Address-free structural description of a file in this dialect: everything libhdf5 looks at before it touches data
+    -- superblock fields, the root group's header messages / B-tree / symbol nodes / local heap, and per dataset the
+    header messages with their version bytes and decoded fields (dataspace, datatype, fill value, filter pipeline, layout,
+    chunk B-tree node type / depth / key layout).  Two files that agree here are read by the same libhdf5 code paths:
+    tests/test_hd5.py compares a file written by write_hd5 with the reference's own stored covT.hd5 / clonT.hd5."""
+    with open(path, "rb") as f:
+        b = f.read()
+    r = _Reader(b)
+    sb = dict(signature=bytes(b[:8]), superblock_version=b[8], free_space_version=b[9], root_group_version=b[10],
+              shared_header_version=b[12], size_of_offsets=b[13], size_of_lengths=b[14], leaf_k=r.leaf_k, internal_k=r.internal_k,
+              file_consistency_flags=struct.unpack_from("<I", b, 20)[0], base_address=r.base,
+              free_space_address_undefined=struct.unpack_from("<Q", b, 32)[0] == UNDEF,
+              driver_info_address_undefined=struct.unpack_from("<Q", b, 48)[0] == UNDEF,
+              eof_is_file_size=r.eof == len(b), root_cache_type=struct.unpack_from("<I", b, 72)[0])
+    root_msgs = [(t, fl, len(m)) for t, fl, m in r.messages(r.root_header)]
+    if r.root_btree is None:
+        for mtype, _, m in r.messages(r.root_header):
+            if mtype == 0x11:
+                r.root_btree, r.root_heap = struct.unpack_from("<QQ", m, 0)
+    hv, = struct.unpack_from("<B", b, r.root_heap + 4)
+    heap = dict(signature=bytes(b[r.root_heap:r.root_heap + 4]), version=hv)
+    # group B-tree: depth, node signatures / types, entries per symbol node
+    depth, a, snod_versions, snod_fill = 0, r.root_btree, set(), []
+    stack = [(r.root_btree, 0)]
+    while stack:
+        a, d = stack.pop()
+        if b[a:a + 4] == b"TREE":
+            ntype, level, used = struct.unpack_from("<BBH", b, a + 4)
+            assert ntype == 0
+            depth = max(depth, level + 1)
+            for i in range(used):
+                stack.append((struct.unpack_from("<Q", b, a + 24 + 8 + i * 16)[0], d + 1))
+        else:
+            assert b[a:a + 4] == b"SNOD"
+            snod_versions.add(b[a + 4])
+            snod_fill.append(struct.unpack_from("<H", b, a + 6)[0])
+    group = dict(btree_depth=depth, snod_versions=sorted(snod_versions), max_entries_per_snod=max(snod_fill) if snod_fill else 0,
+                 snod_entries_bound=2 * r.leaf_k)
+    entries = r.group_entries(r.root_btree, r.root_heap)
+    dsets = {}
+    for name in sorted(entries)[:max_datasets]:
+        addr = entries[name]
+        version, _, nmsg, _, _ = struct.unpack_from("<BBHII", b, addr)
+        msgs, chunk_tree = [], None
+        for mtype, flags, m in r.messages(addr):
+            if mtype == 0:                                                   # NIL padding: size is layout noise
+                continue
+            d = dict(type=mtype, flags=flags)
+            if mtype == 1:
+                rank = m[1]
+                d.update(version=m[0], rank=rank, dim_flags=m[2], dims=struct.unpack_from("<%dQ" % rank, m, 8),
+                         max_dims=struct.unpack_from("<%dQ" % rank, m, 8 + 8 * rank) if m[2] & 1 else None)
+            elif mtype == 3:
+                size = struct.unpack_from("<I", m, 4)[0]
+                d.update(class_and_version=m[0], bits=bytes(m[1:4]), size=size, properties=bytes(m[8:8 + (12 if (m[0] & 15) == 1 else 4)]))
+            elif mtype == 5:
+                d.update(version=m[0], alloc_time=m[1], write_time=m[2], defined=m[3],
+                         size=struct.unpack_from("<I", m, 4)[0] if m[0] >= 2 and m[3] else None)
+            elif mtype == 0x0B:
+                nf = m[1]
+                fl, q = [], 8
+                for _ in range(nf):
+                    fid, nlen, fflags, ncv = struct.unpack_from("<HHHH", m, q)
+                    nm = bytes(m[q + 8:q + 8 + nlen]).rstrip(b"\0")
+                    q += 8 + ((nlen + 7) & ~7)
+                    fl.append(dict(id=fid, name=nm, flags=fflags, client_data=struct.unpack_from("<%dI" % ncv, m, q)))
+                    q += 4 * (ncv + (ncv & 1))
+                d.update(version=m[0], filters=fl)
+            elif mtype == 8:
+                d.update(version=m[0], layout_class=m[1])
+                if m[1] == 2:
+                    r1 = m[2]
+                    bt = struct.unpack_from("<Q", m, 3)[0]
+                    d.update(rank_plus_1=r1, chunk_dims=struct.unpack_from("<%dI" % r1, m, 11), allocated=bt != UNDEF)
+                    if bt != UNDEF:
+                        ntype, level, used = struct.unpack_from("<BBH", b, bt + 4)
+                        ch = r.chunks(bt, r1)
+                        chunk_tree = dict(signature=bytes(b[bt:bt + 4]), node_type=ntype, root_level=level, n_chunks=len(ch),
+                                          filter_masks=sorted({c[2] for c in ch}),
+                                          chunk_offsets=sorted(c[0] for c in ch))
+            else:
+                d.update(size=len(m))
+            msgs.append(d)
+        dsets[name] = dict(header_version=version, messages=msgs, chunk_tree=chunk_tree)
+    return dict(superblock=sb, root_messages=root_msgs, heap=heap, group=group, n_datasets=len(entries), datasets=dsets)
+
+
 def load_special(path, scaffolds=()):
     """Mirror of SNVprofile._load_special for covT / clonT (SNVprofile.py:750-786): scaffold -> mm -> pandas Series
     (values indexed by position; the reference rebuilds `pd.Series(data=arr[0], index=np.array(arr[1].astype('int')))`)."""
@@ -240,6 +328,27 @@ class _FileBuf:
         self.fh.seek(0, 2)
 
 
+def _guess_chunk(rows, n, typesize):
+    """h5py's chunk-shape heuristic (h5py/_hl/filters.py: guess_chunk) for a 2-D dataset without maxshape: halve the
+    dimensions in turn until a chunk is within 50 % of a target size between 8 KiB and 1 MiB that grows with the
+    dataset.  The reference stores covT / clonT through h5py's create_dataset(compression='gzip'): same chunk shapes."""
+    import math
+    base, cmin, cmax = 16 * 1024, 8 * 1024, 1024 * 1024
+    chunks = [float(rows), float(n)]
+    target = base * (2 ** math.log10(rows * n * typesize / (1024.0 * 1024.0)))
+    target = cmax if target > cmax else cmin if target < cmin else target
+    idx = 0
+    while True:
+        nbytes = chunks[0] * chunks[1] * typesize
+        if (nbytes < target or abs(nbytes - target) / target < 0.5) and nbytes < cmax:
+            break
+        if chunks[0] * chunks[1] == 1:
+            break
+        chunks[idx % 2] = math.ceil(chunks[idx % 2] / 2.0)
+        idx += 1
+    return int(chunks[0]), int(chunks[1])
+
+
 class _Writer:
     def __init__(self, fh=None):
         # superblock + root object header come first and are patched at the end
@@ -265,30 +374,38 @@ class _Writer:
         else:
             raise ValueError("dtype %s not supported" % arr.dtype)
         rows, n = arr.shape
-        # 1 x C chunks, at most 2 * CHUNK_K of them so the chunk index is a single B-tree node
-        per_row = max(1, (2 * CHUNK_K) // max(rows, 1))
-        C = max(1, -(-n // per_row)) if n else 1024    # empty dataset: no chunk index (libhdf5 does the same)
-        if rows * (-(-n // C) if n else 0) > 2 * CHUNK_K:
-            raise ValueError("too many rows for a single-node chunk index")
+        # Chunk shape: h5py's guess_chunk (what the reference's files were written with) as long as the chunk index stays
+        # a single B-tree node (<= 2 * CHUNK_K chunks); larger datasets: 1 x C chunks, 2 * CHUNK_K of them.
+        R, C = _guess_chunk(rows, n, 8) if n else (1, 1024)          # empty dataset: no chunk index (libhdf5 does the same)
+        if n and (-(-rows // R)) * (-(-n // C)) > 2 * CHUNK_K:
+            R = 1
+            per_row = max(1, (2 * CHUNK_K) // max(rows, 1))
+            C = max(1, -(-n // per_row))
+            if rows * (-(-n // C)) > 2 * CHUNK_K:
+                raise ValueError("too many rows for a single-node chunk index")
         chunks = []
-        for r in range(rows):
+        for r0 in range(0, rows if n else 0, R):
             for c0 in range(0, n, C):
-                blk = np.zeros(C, dtype=arr.dtype)
-                seg = arr[r, c0:c0 + C]
-                blk[:len(seg)] = seg
-                chunks.append(((r, c0, 0), zlib.compress(blk.tobytes(), level)))
-        return rows, n, C, dt, chunks
+                blk = np.zeros((R, C), dtype=arr.dtype)
+                seg = arr[r0:r0 + R, c0:c0 + C]
+                blk[:seg.shape[0], :seg.shape[1]] = seg
+                chunks.append(((r0, c0, 0), zlib.compress(blk.tobytes(), level)))
+        return rows, n, (R, C), dt, chunks
 
     def add_dataset(self, name, arr, level=4, prepared=None):
-        rows, n, C, dt, chunks = prepared if prepared is not None else self.prepare(arr, level)
+        rows, n, (R, C), dt, chunks = prepared if prepared is not None else self.prepare(arr, level)
         keys = [(offs, len(z), self._append(z)) for offs, z in chunks]
         btree = UNDEF
         if keys:
             node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(keys), UNDEF, UNDEF))
+            # the rightmost key as libhdf5's insertion history leaves it: a chunk at or beyond the current right key moves
+            # the key to (that chunk's offset + the chunk dimensions); a chunk below it splits a child and leaves it alone
+            right = None
             for offs, nbytes, a in keys:
                 node += struct.pack("<II3QQ", nbytes, 0, *offs, a)
-            last = keys[-1][0]
-            node += struct.pack("<II3Q", 0, 0, last[0], last[1], 8)
+                if right is None or offs >= right:
+                    right = (offs[0] + R, offs[1] + C, 8)
+            node += struct.pack("<II3Q", 0, 0, *right)
             node += b"\0" * (24 + (2 * CHUNK_K + 1) * 32 + 2 * CHUNK_K * 8 - len(node))
             self.buf += b"\0" * (-len(self.buf) % 8)
             btree = self._append(bytes(node))
@@ -297,7 +414,7 @@ class _Writer:
             _msg(3, dt, flags=1),
             _msg(5, bytes([2, 3, 0, 1]) + struct.pack("<I", 0), flags=1),
             _msg(0x0B, struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 8, 1, 1) + b"deflate\0" + struct.pack("<II", level, 0), flags=1),
-            _msg(8, struct.pack("<BBBQ3I", 3, 2, 3, btree, 1, C, 8)),
+            _msg(8, struct.pack("<BBBQ3I", 3, 2, 3, btree, R, C, 8)),
         ]
         body = b"".join(msgs)
         self.buf += b"\0" * (-len(self.buf) % 8)

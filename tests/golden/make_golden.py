@@ -186,3 +186,20 @@ if __name__ == "__main__":
         make_hd5_digests(which)
         print(which, "events", len(batch["ref_pos"]), "pairs", len(batch["pair_mm"]), "L", len(batch["ref_codes"]),
               "snv rows", len(exp["snv_pos"]), "ld rows", len(exp["ld_pos_a"]))
+
+
+def make_hd5_structure_fixture():
+    """tests/golden/hd5_structure_G1.json: hd5.describe_hd5 (address-free structure) of the reference's stored G1
+    covT.hd5 / clonT.hd5, first 60 datasets -- what tests/test_hd5.py holds the native writer against where
+    /root/reference is absent.  Run: python -c "import make_golden as m; m.make_hd5_structure_fixture()" in tests/golden."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from instrain_b200 import hd5
+    from test_hd5 import REF_RAW, _plain
+    out = {}
+    for name in ("covT", "clonT"):
+        d = hd5.describe_hd5(os.path.join(REF_RAW % "G1", name + ".hd5"))
+        d["datasets"] = {k: d["datasets"][k] for k in sorted(d["datasets"])[:60]}
+        out[name] = _plain(d)
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hd5_structure_G1.json"), "w"), indent=0, sort_keys=True)

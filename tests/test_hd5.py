@@ -128,3 +128,74 @@ def test_threaded_writer_is_byte_identical(tmp_path):
     assert sizes[0] == len(blobs[0]) and blobs[0] == blobs[1] == blobs[2]
     back = hd5.read_hd5(str(tmp_path / "t8.hd5"))
     assert set(back) == set(ds) and all(np.array_equal(back[k], ds[k].astype(back[k].dtype)) for k in ds)
+
+
+def _plain(x):
+    """describe_hd5 output -> JSON-comparable (tuples -> lists, bytes -> hex)."""
+    if isinstance(x, dict):
+        return {str(k): _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_plain(v) for v in x]
+    if isinstance(x, (bytes, bytearray)):
+        return bytes(x).hex()
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    return x
+
+
+@pytest.mark.parametrize("which", ["G1", "G2"])
+@pytest.mark.parametrize("name", ["covT", "clonT"])
+def test_writer_structure_equals_reference_files(tmp_path, which, name):
+    """The writer against libhdf5's own output, structure by structure (h5py / libhdf5 are not in this image, so no
+    library can open the written file here): the reference's stored covT.hd5 / clonT.hd5 (h5py, libver='earliest') are
+    read, the same datasets are written by write_hd5, and the address-free descriptions of the two files
+    (hd5.describe_hd5: superblock fields, root header messages, local heap, group B-tree depth and symbol-node fill,
+    and per dataset every header message with its version byte and decoded fields -- dataspace, datatype bits and
+    properties, fill value, filter pipeline with the deflate client data, chunked layout with h5py's chunk shape -- and
+    the chunk B-tree's node type, depth, filter masks and chunk offsets) must be EQUAL for all 1267 / 1429 datasets."""
+    path = os.path.join(REF_RAW % which, name + ".hd5")
+    if not os.path.exists(path):
+        pytest.skip("reference test data not present on this machine")
+    ref = hd5.describe_hd5(path)
+    ds = hd5.read_hd5(path)
+    out = str(tmp_path / "w.hd5")
+    hd5.write_hd5(out, ds, threads=2)
+    mine = hd5.describe_hd5(out)
+    assert mine["superblock"] == ref["superblock"] and mine["root_messages"] == ref["root_messages"]
+    assert mine["heap"] == ref["heap"] and mine["group"] == ref["group"] and mine["n_datasets"] == ref["n_datasets"]
+    bad = [k for k in ref["datasets"] if mine["datasets"].get(k) != ref["datasets"][k]]
+    assert not bad, (bad[:3], ref["datasets"][bad[0]], mine["datasets"].get(bad[0]))
+    back = hd5.read_hd5(out)
+    assert all(np.array_equal(ds[k], back[k]) and ds[k].dtype == back[k].dtype for k in ds)
+
+
+def test_writer_structure_equals_committed_reference_description(tmp_path):
+    """The same comparison where /root/reference is absent: tests/golden/hd5_structure_G1.json holds describe_hd5 of the
+    reference's stored G1 covT.hd5 / clonT.hd5 for the datasets of the first scaffolds (made by make_golden.py); the
+    datasets are rebuilt from the oracle's basewise tables (equal to the stored ones: test_oracle_basewise_equals_
+    reference_store) and written by write_hd5."""
+    import json
+    from instrain_b200 import tables
+    gold = json.load(open(os.path.join(GOLDEN, "hd5_structure_G1.json")))
+    lut, dflt = load_lut()
+    b, _ = load_batch("G1")
+    exp = restate.profile_events(b, b["ref_codes"], lut, dflt, b["splits"], do_linkage=False)
+    cov_ds, clon_ds = {}, {}
+    for sname, off, L in zip(b["scaffold_names"], b["scaffold_off"], b["scaffold_len"]):
+        sl = slice(int(off), int(off) + int(L))
+        lv = tables.present_levels(exp["covT"][sl], exp["nmask"][sl])
+        cov = tables.basewise(exp["covT"][sl], "coverage", lv)
+        clon = tables.basewise(exp["clonT"][sl], "clonality", lv)
+        for mm in lv:
+            cov_ds["%s::%d" % (sname, mm)] = np.array([cov[mm].values, cov[mm].index])
+            clon_ds["%s::%d" % (sname, mm)] = np.array([clon[mm].values, clon[mm].index])
+    for name, ds in (("covT", cov_ds), ("clonT", clon_ds)):
+        out = str(tmp_path / (name + ".hd5"))
+        hd5.write_hd5(out, ds)
+        mine = _plain(hd5.describe_hd5(out))
+        g = gold[name]
+        for k in ("superblock", "root_messages", "heap", "group", "n_datasets"):
+            assert mine[k] == g[k], (name, k)
+        assert len(g["datasets"]) >= 40
+        for k, v in g["datasets"].items():
+            assert mine["datasets"][k] == v, (name, k)
