@@ -3,8 +3,11 @@
 Drop-in for inStrain.polymorpher.extract_SNVS_from_bam (inStrain/polymorpher.py:275-316, used by `compare --bams` to pool
 SNVs): the reference re-runs the identical pysam pileup over [min(positions)-1, max(positions)] and sums
 get_base_counts_mm over all mm levels (get_pooling_counts, :312-316).  Here: host packer -> K1 with the mm dimension
-collapsed (M = 1) -> gather.  The mate-overlap tweak does not depend on the pileup region, so counts equal the ones of a
-full-scaffold profile.
+collapsed (M = 1) -> gather.  The reference piles up only the reads its index fetch returns for that region; under the
+pinned restatement of htslib's pileup the mate-overlap tweak gives the same counts either way (a mate can only change
+qualities inside the overlap of the two reads, and such a position inside the region makes both mates overlap it):
+tests/test_polymorpher_region.py holds the region-limited emulation against the whole-scaffold one at > 400 positions,
+single-position regions included, so packing the whole scaffold is the reference's semantics.
 """
 import numpy as np
 
