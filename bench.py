@@ -230,7 +230,12 @@ class Job:
             self.batch = _cabi.IsbBatch(int(d["n_events"]), p(d["ref_pos"]), p(d["base"]), p(d["qual"]), p(d["read_id"]), self.npairs,
                                         p(d["pair_mm"]), 0, L_, p(d["ref_codes"]), d["splits"].shape[0], p(d["splits"]), M_)
             self.entry = eng.lib.isb_profile_batch
-        self.prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0, 0.05, 0 if self.no_clontr else 50, 0, SEED)
+        flags = _cabi.ISB_SKIP_LINKAGE if args.skip_linkage else 0
+        self.prm = _cabi.IsbParams(5, 20, 30, flags, 0.05, 0 if self.no_clontr else 50, 0, SEED)
+        # the timed loops enqueue the steps without a host round trip per call (ISB_NO_SYNC: capacities are settled in the
+        # synchronous warm-up steps; errors and row counts are checked once after the loop, isb_synchronize)
+        self.prm_async = _cabi.IsbParams(5, 20, 30, flags | _cabi.ISB_NO_SYNC, 0.05, 0 if self.no_clontr else 50, 0, SEED)
+        self.counts4 = torch.zeros(4, dtype=torch.int64, device=dev)
         self.step_no, self.res = 0, None
 
     def _alloc_rows(self):
@@ -243,6 +248,29 @@ class Job:
             r_ = self._cabi.IsbResult(p(self.counts), p(self.nmask), p(self.covT), p(self.clonT), p(self.flags), p(s_), self.snv_cap,
                                       p(l_), self.ld_cap, 0, 0, 0, 0, p(self.clonTR))
             self.sets.append((s_, l_, r_))
+
+    def step_async(self):
+        """One step enqueued on the stream, no host synchronisation (row counts stay on the device)."""
+        cur = self.step_no % self.n_sets
+        rc = self.entry(self.eng.ctx, C.byref(self.batch), C.byref(self.prm_async), C.byref(self.sets[cur][2]))
+        if rc != 0:
+            raise RuntimeError(self.eng.lib.isb_last_error(self.eng.ctx).decode())
+        self.step_no += 1
+        return cur
+
+    def check_async(self):
+        """After a loop of step_async: device-side error flags, row counts of the last step (one host round trip)."""
+        rc = self.eng.lib.isb_row_counts_async(self.eng.ctx, self._cabi.ptr(self.counts4))
+        if rc == 0:
+            rc = self.eng.lib.isb_synchronize(self.eng.ctx)
+        if rc != 0:
+            raise RuntimeError(self.eng.lib.isb_last_error(self.eng.ctx).decode())
+        c = self.counts4.tolist()
+        if c[0] > self.snv_cap or c[1] > self.ld_cap:
+            raise RuntimeError("row buffers too small in the timed loop: %r" % (c,))
+        r_ = self.sets[(self.step_no - 1) % self.n_sets][2]
+        r_.n_snv, r_.n_ld, r_.n_sites, r_.n_site_pairs = c
+        self.res = r_
 
     def step(self):
         cur = self.step_no % self.n_sets
@@ -272,9 +300,8 @@ class Gather:
         self.job, self.world, self.rank, self.stream, self.dev, self.dist, self.torch = job, world, rank, stream, dev, dist, torch
         self.side = torch.cuda.Stream(device=dev)
         self.done = [None] * job.n_sets
-        self.counts_host = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(job.n_sets)]
-        self.counts_in = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.counts_all = torch.zeros(world * 2, dtype=torch.int64, device=dev)
+        self.counts_in = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(job.n_sets)]
+        self.counts_all = torch.zeros(world * 4, dtype=torch.int64, device=dev)
         self.slab, self.recv, self.bytes_per_step = None, None, 0
 
     def fix_sizes(self):
@@ -296,12 +323,13 @@ class Gather:
     def launch(self, cur):
         torch, dist = self.torch, self.dist
         s_, l_, r_ = self.job.sets[cur]
-        ch = self.counts_host[cur]
-        ch[0], ch[1] = int(r_.n_snv), int(r_.n_ld)
+        # row counts of the step: device -> device on the step's stream (isb_row_counts_async), exchanged on the side stream
+        rc = self.job.eng.lib.isb_row_counts_async(self.job.eng.ctx, self.job._cabi.ptr(self.counts_in[cur]))
+        if rc != 0:
+            raise RuntimeError(self.job.eng.lib.isb_last_error(self.job.eng.ctx).decode())
         self.side.wait_stream(self.stream)
         with torch.cuda.stream(self.side):
-            self.counts_in.copy_(ch, non_blocking=True)
-            dist.all_gather_into_tensor(self.counts_all, self.counts_in)
+            dist.all_gather_into_tensor(self.counts_all, self.counts_in[cur])
             for t, buf in enumerate((s_, l_)):
                 dist.gather(buf[:self.slab[t]], self.recv[t] if self.rank == 0 else None, dst=0)
             ev = torch.cuda.Event()
@@ -324,13 +352,14 @@ def time_steps(job, gather, steps, stream, world, dist, torch):
     for _ in range(steps):
         if gather is not None:
             gather.wait_set(job.step_no % job.n_sets)
-        cur = job.step()
+        cur = job.step_async()
         if gather is not None:
             gather.launch(cur)
     if gather is not None:
         gather.finish()                                          # the last gathers belong to the timed region
     e1.record(stream)
     torch.cuda.synchronize()
+    job.check_async()
     if world > 1:
         dist.barrier()
     w1 = time.time()
@@ -431,8 +460,8 @@ def main():
         eng = Engine(local_rank, lut, dflt)
         torch.cuda.empty_cache()
     t_gen = time.time() - t_gen
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
+    stream = torch.cuda.Stream(device=dev)                 # the steps' stream (not the legacy default stream: handle 0 would mean
+    eng.set_stream(stream.cuda_stream)                     # "the context's own stream" to isb_set_stream)
     job = Job(eng, d, args, dev, layout=args.layout, cols=cols, two_sets=world > 1)
     gather = Gather(job, world, rank, stream, dev) if world > 1 else None
     n_ev, npairs, Ltot, M = int(d["n_events"]), job.npairs, job.Ltot, job.M

@@ -93,6 +93,11 @@ int isb_abi_version(void);
 /* Run on `stream` (a cudaStream_t) instead of the context's own stream; 0 restores the own stream. */
 int isb_set_stream(isb_ctx *ctx, void *stream);
 int isb_synchronize(isb_ctx *ctx);
+/* Row counts of the last whole-path call, [n_snv, n_ld, n_sites, n_site_pairs], copied to `dst` (device or pinned host
+ * memory, 4 x int64) by an asynchronous copy on the context's stream: with ISB_NO_SYNC a multi-GPU caller exchanges the
+ * counts on the device and trims the gathered row slabs without ever waiting for the host (bench.py's table gather, the
+ * counterpart of the result queue of the reference's task farm, profile_controller.py:243-271). */
+int isb_row_counts_async(isb_ctx *ctx, int64_t *dst);
 
 /* ---- stage K1: pileup counts ------------------------------------------------------------------------------- */
 /* Replaces pysam's column iteration + get_base_counts_mm (profile_utilities.py:268-286):

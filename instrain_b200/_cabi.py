@@ -35,7 +35,7 @@ assert SUMMARY_DT.itemsize == 72
 CLASS_NAMES = ["AmbiguousReference", "DivergentSite", "SNS", "SNV", "con_SNV", "pop_SNV"]
 
 # every symbol include/instrain_b200.h declares (tests/test_cabi_symbols.py checks the list against the header)
-EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize",
+EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "isb_set_stream", "isb_synchronize", "isb_row_counts_async",
            "isb_pileup_counts", "isb_call_snvs", "isb_linkage", "isb_profile_batch", "isb_profile_batch_packed",
            "isb_pileup_reads", "isb_profile_reads", "isb_profile_reads_compact", "isb_profile_reads_delta", "isb_reads_delta_host",
            "isb_cols_from_reads", "isb_cols_from_reads_host", "isb_pileup_cols", "isb_profile_cols",
@@ -143,6 +143,8 @@ def load():
     L.isb_set_stream.argtypes = [vp, vp]
     L.isb_synchronize.restype = C.c_int
     L.isb_synchronize.argtypes = [vp]
+    L.isb_row_counts_async.restype = C.c_int
+    L.isb_row_counts_async.argtypes = [vp, vp]
     L.isb_launch_count.restype = i64
     L.isb_launch_count.argtypes = [vp]
     L.isb_pileup_counts.restype = C.c_int

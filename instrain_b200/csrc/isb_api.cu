@@ -205,6 +205,14 @@ int isb_synchronize(isb_ctx *ctx)
     return check_dev_err(ctx);
 }
 
+int isb_row_counts_async(isb_ctx *ctx, int64_t *dst)
+{
+    if (!ctx || !dst) return ISB_ERR_ARG;
+    ISB_CUDA(cudaSetDevice(ctx->device));
+    ISB_CUDA(cudaMemcpyAsync(dst, ctx->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDefault, ctx->stream));
+    return ISB_OK;
+}
+
 int64_t isb_launch_count(const isb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int64_t isb_selftest_division(isb_ctx *ctx, int s_lo, int s_hi)

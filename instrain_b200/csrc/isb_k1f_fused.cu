@@ -901,13 +901,15 @@ static size_t k1f_smem_bytes(int seg_cap, bool m1, bool fuse, int Mg)
     return b;
 }
 
-// L2 prefetch distance: half a tile per SM ahead (ISB_K1F_PF overrides it; 0 = every block prefetches its own tile only).
-// Measured (B200, 2e7 positions at 100x): 0 -> 0.428 ms, 74 -> 0.424, 148 -> 0.438, 296 -> 0.468: the loads are not
-// waiting for DRAM any more; further ahead only displaces data that is still needed.
+// L2 prefetch distance in tiles: 0 = every block prefetches its own tile only (the default); ISB_K1F_PF = n > 0 makes a block
+// also ask for the words and the table of the tile n later.  Measured (B200, 2e7 positions at 100x): M = 1: 0 -> 0.428 ms,
+// 74 -> 0.424, 148 -> 0.438, 296 -> 0.468; M = 15: 0 -> 3.76 ms, 74 -> 4.49.  The loads are not waiting for DRAM any more;
+// data fetched further ahead only displaces data that is still needed.
 static int k1f_pf_ahead(const isb_ctx *ctx)
 {
     static const int env = getenv("ISB_K1F_PF") ? atoi(getenv("ISB_K1F_PF")) : -1;
-    return env >= 0 ? env : ctx->sm_count / 2;
+    (void)ctx;
+    return env >= 0 ? env : 0;
 }
 
 // tile bounds + staging capacity of a batch

@@ -838,24 +838,37 @@ __global__ void __launch_bounds__(256) k3_enum_pairs_tiles(k3_args a)
         int64_t j_lo = k + 1, j_hi = (int64_t)a.tile_first[tl] + a.tile_cnt[tl];
         for (;;) {
             if (j_hi > S) j_hi = S;
-            for (int64_t j = j_lo + sub; j < j_hi; j += K3_ENUM_LANES) {
-                const isb_site_meta mj = a.meta[j];
-                if (mj.split != mi.split) continue;
-                const int lo = max(mi.wlo, mj.wlo), hi = min(i_hi, mj.wlo + mj.nw);
-                bool linked = false;
-                if (lo < hi) {
-                    const uint32_t *any_j = a.rows + a.row_off[j] - mj.wlo;
-                    for (int w = lo; w < hi; ++w)
-                        if (any_i[w] & any_j[w]) { linked = true; break; }
+            // partners in batches of 4 per thread: their records are requested together (the scan is a chain of dependent
+            // loads; one record per trip left the kernel at 24 % issue-active)
+            for (int64_t j0 = j_lo + sub; j0 < j_hi; j0 += 4 * K3_ENUM_LANES) {
+                int4 rec[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t j = j0 + (int64_t)u * K3_ENUM_LANES;
+                    rec[u] = make_int4(0, 0, 0, -2);
+                    if (j < j_hi) rec[u] = __ldg(reinterpret_cast<const int4 *>(a.meta + j));
                 }
-                if (linked) {
-                    const unsigned act = __activemask();
-                    const int leader = __ffs(act) - 1, lane = threadIdx.x & 31;
-                    unsigned long long base = 0;
-                    if (lane == leader) base = atomicAdd(a.n_site_pairs, (unsigned long long)__popc(act));
-                    base = __shfl_sync(act, base, leader);
-                    const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
-                    if ((int64_t)slot < a.pair_cap) { a.pair_i[slot] = (int32_t)k; a.pair_j[slot] = (int32_t)j; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t j = j0 + (int64_t)u * K3_ENUM_LANES;
+                    const int wlo_j = rec[u].y, nw_j = rec[u].z;                 // isb_site_meta: ev_lo_rel, wlo, nw, split
+                    if (j >= j_hi || rec[u].w != mi.split) continue;
+                    const int lo = max(mi.wlo, wlo_j), hi = min(i_hi, wlo_j + nw_j);
+                    bool linked = false;
+                    if (lo < hi) {
+                        const uint32_t *any_j = a.rows + a.row_off[j] - wlo_j;
+                        for (int w = lo; w < hi; ++w)
+                            if (any_i[w] & any_j[w]) { linked = true; break; }
+                    }
+                    if (linked) {
+                        const unsigned act = __activemask();
+                        const int leader = __ffs(act) - 1, lane = threadIdx.x & 31;
+                        unsigned long long base = 0;
+                        if (lane == leader) base = atomicAdd(a.n_site_pairs, (unsigned long long)__popc(act));
+                        base = __shfl_sync(act, base, leader);
+                        const unsigned long long slot = base + __popc(act & ((1u << lane) - 1u));
+                        if ((int64_t)slot < a.pair_cap) { a.pair_i[slot] = (int32_t)k; a.pair_j[slot] = (int32_t)j; }
+                    }
                 }
             }
             if (++tl > last_tile) break;
