@@ -109,7 +109,9 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
         }
         const int T = C[0] + C[1] + C[2] + C[3];
         const bool counted = present && T >= min_cov;
-        if (counted && !kWrite) {                                     // calculate_clonality, double, A,C,T,G order
+        if (counted && !kWrite && max(max(C[0], C[1]), max(C[2], C[3])) == T && T > 0) {
+            clon = 1.0f;                                              // one base only: (T/T)^2 + 0 + 0 + 0 is exactly 1 (most cells)
+        } else if (counted && !kWrite) {                              // calculate_clonality, double, A,C,T,G order
             const double s = (double)T;
             double f0, f1, f2, f3;
             if (T <= K2_FAST_DIV_MAX) {                               // one reciprocal, four 3-op quotients (bit-exact)

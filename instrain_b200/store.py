@@ -78,6 +78,46 @@ class SNVprofileStore:
             Adb = pd.concat([Adb, pd.DataFrame({"value": stored, "type": type, "description": description}, index=[name])])
         self._write_attributes(Adb)
 
+    def store_many(self, items, threads=4):
+        """`store` for several (name, value, type, description) at once: the files are written concurrently (deflate of
+        the csv.gz tables and of the .hd5 chunks releases the GIL), the attribute table is updated afterwards, in order.
+        Same files, same attributes.tsv as the one-by-one calls."""
+        from concurrent.futures import ThreadPoolExecutor
+        plan = []
+        for name, value, typ, description in items:
+            if typ == "value":
+                plan.append((name, value, typ, description, None, None))
+                continue
+            if typ not in _EXT:
+                logging.error("I dont know how to save a {0} type, so Im just going to pickle it".format(typ))
+                typ = "pickle"
+            save_as = typ
+            if typ == "special" and name not in _HD5_NAMES:
+                logging.error("I dont know how to store {0}! Ill just pickle it".format(name))
+                stored, save_as = self._fileloc(name) + ".pickle", "pickle"
+            else:
+                stored = self._fileloc(name) + _EXT[typ]
+            plan.append((name, stored, typ, description, save_as, value))
+        jobs = [e for e in plan if e[4] is not None]
+        if threads > 1 and len(jobs) > 1:
+            with ThreadPoolExecutor(max_workers=min(threads, len(jobs))) as ex:
+                for f in [ex.submit(self._save, e[4], e[5], e[1]) for e in jobs]:
+                    f.result()
+        else:
+            for e in jobs:
+                self._save(e[4], e[5], e[1])
+        Adb = self._read_attributes()
+        for name, stored, typ, description, _, _ in plan:
+            if name in Adb.index:
+                clash = [t for t, new in (("type", typ), ("description", description)) if Adb.loc[name, t] != new]
+                if clash:
+                    logging.error("WILL NOT OVERWRITE {0}; {1} arent the same".format(name, clash[0]))
+                    continue
+                Adb.at[name, "value"] = stored
+            else:
+                Adb = pd.concat([Adb, pd.DataFrame({"value": stored, "type": typ, "description": description}, index=[name])])
+        self._write_attributes(Adb)
+
     def get(self, name, **kwargs):
         Adb = self._read_attributes()
         if name not in Adb.index:
@@ -201,7 +241,8 @@ class SNVprofileStore:
         elif typ == "pandas":
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                value.to_csv(loc)
+                # gzip level 4 instead of pandas' 9: 3 % larger files, half the time (the reference's reader is pd.read_csv)
+                value.to_csv(loc, compression={"method": "gzip", "compresslevel": 4} if loc.endswith(".gz") else "infer")
         elif typ == "special":
             hd5.store_special(loc, value)
         else:
@@ -245,19 +286,21 @@ def store_profile(ISP_loc, bam, res, mapping_info=None, **kwargs):
     S = ProfileStore(ISP_loc, res)
     if mapping_info is not None:
         S.store("mapping_info", mapping_info, "pandas", "Report on reads")
-    S.store("object_type", "profile", "value", "Type of SNVprofile (profile or compare)")
-    S.store("bam_loc", bam, "value", "Location of .bam file")
-    S.store("scaffold_list", list(res.scaffold_list), "list", "1d list of scaffolds that were profiled")
-    S.store("raw_linkage_table", res.raw_linkage_table, "pandas", "Raw table of linkage information")
-    S.store("raw_snp_table", res.cumulative_snv_table, "pandas", "Contains raw SNP information on a mm level")
-    S.store("cumulative_scaffold_table", res.cumulative_scaffold_table, "pandas",
-            "Cumulative coverage on mm level. Formerly scaffoldTable.csv")
-    S.store("cumulative_snv_table", res.cumulative_snv_table, "pandas", "Cumulative SNP on mm level. Formerly snpLocations.pickle")
-    S.store("scaffold_2_mm_2_read_2_snvs", {}, "pickle", "crazy nonsense needed for linkage")
-    S.store("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage")
-    S.store("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")
+    items = [("object_type", "profile", "value", "Type of SNVprofile (profile or compare)"),
+             ("bam_loc", bam, "value", "Location of .bam file"),
+             ("scaffold_list", list(res.scaffold_list), "list", "1d list of scaffolds that were profiled"),
+             ("raw_linkage_table", res.raw_linkage_table, "pandas", "Raw table of linkage information"),
+             ("raw_snp_table", res.cumulative_snv_table, "pandas", "Contains raw SNP information on a mm level"),
+             ("cumulative_scaffold_table", res.cumulative_scaffold_table, "pandas",
+              "Cumulative coverage on mm level. Formerly scaffoldTable.csv"),
+             ("cumulative_snv_table", res.cumulative_snv_table, "pandas", "Cumulative SNP on mm level. Formerly snpLocations.pickle"),
+             ("scaffold_2_mm_2_read_2_snvs", {}, "pickle", "crazy nonsense needed for linkage"),
+             ("covT", {s: p.covT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based coverage"),
+             ("clonT", {s: p.clonT for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> position based clonality")]
     if any(p.clonTR for p in res.scaffolds.values()):
-        S.store("clonTR", {s: p.clonTR for s, p in res.scaffolds.items()}, "special", "Scaffold -> mm -> rarefied position based clonality")
+        items.append(("clonTR", {s: p.clonTR for s, p in res.scaffolds.items()}, "special",
+                      "Scaffold -> mm -> rarefied position based clonality"))
+    S.store_many(items, threads=int(kwargs.pop("store_threads", 0) or min(8, os.cpu_count() or 1)))
     for name in ("SNVs", "scaffold_info", "linkage"):                     # ProfileController.write_output (controller.py:352-360)
         S.generate(name)
     if mapping_info is not None:
