@@ -43,7 +43,9 @@
 #define K1F_THREADS (K1F_TILE / 8)     // one thread per column word
 #define K1F_WARPS (K1F_THREADS / 32)
 #define K1F_MAXLEN 256                 // hard cap of max_seg_len
+#ifndef K1F_LEVELS
 #define K1F_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
+#endif
 #ifndef K1F_STAGE_IT
 #define K1F_STAGE_IT 4                 // segment-table elements per thread and staging pass
 #endif
@@ -53,6 +55,9 @@
 #define K1F_CODE_IDS_MAX 4096          // from the pair density (k1f_args.code_ids); wider windows: atomics
 #ifndef K1F_MINB
 #define K1F_MINB 8                     // __launch_bounds__ min blocks per SM of the M = 1 kernels (64 registers; ~28 KB shared)
+#endif
+#ifndef K1F_MM_MINB
+#define K1F_MM_MINB 1                  // the same for the M > 1 kernel (shared-memory accumulators bound its occupancy, not registers)
 #endif
 static_assert(K1F_WARPS == 4, "the site bookkeeping of the fused epilogue assumes 4 warps per tile");
 
@@ -187,7 +192,7 @@ __device__ __forceinline__ void k1f_flush_planes(int4 *tile_lane, uint32_t (&pl)
 }
 
 template <bool kM1, bool kFuse>
-__global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : 1) k1f_pileup(k1f_args a)
+__global__ void __launch_bounds__(K1F_THREADS, kM1 ? K1F_MINB : K1F_MM_MINB) k1f_pileup(k1f_args a)
 {
     static_assert(kM1 || !kFuse, "the fused epilogue is the M = 1 SNV call");
     extern __shared__ __align__(16) unsigned char k1f_smem[];

@@ -59,8 +59,8 @@ struct k2_site_state {
 struct k2_rq_entry { int C[4]; int32_t p; int32_t m; };
 struct k2_rq { k2_rq_entry *e; int n; };                               // e: [64] per warp; n: warp-uniform
 
-__device__ __forceinline__ void k2_rq_drain(k2_rq &q, bool all, float *__restrict__ clonTR, int M, int cov_r, uint64_t seed,
-                                            int32_t start)
+__device__ __forceinline__ void k2_rq_drain(k2_rq &q, bool all, float *clonTR, int M, int cov_r, uint64_t seed,
+                                            int32_t start, int cstride = 1)
 {
     const int lane = threadIdx.x & 31;
     while (q.n >= 32 || (all && q.n > 0)) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void k2_rq_drain(k2_rq &q, bool all, float *__restric
         if (lane < take) {
             const k2_rq_entry e = q.e[lane];
             const int C[4] = {e.C[0], e.C[1], e.C[2], e.C[3]};
-            clonTR[(size_t)e.p * M + e.m] = k2_rarefied_clon(C, C[0] + C[1] + C[2] + C[3], cov_r, seed, (int64_t)e.p + start, e.m);
+            clonTR[((int64_t)e.p * M + e.m) * cstride] = k2_rarefied_clon(C, C[0] + C[1] + C[2] + C[3], cov_r, seed, (int64_t)e.p + start, e.m);
         }
         const bool has = lane + 32 < q.n;
         k2_rq_entry mv;
@@ -92,7 +92,7 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
                const int32_t *__restrict__ thr2, int n_lut, int lut_default, int32_t start, int min_cov, double min_freq,
                int32_t *cov_row, float *clon_row, isb_snv_row *__restrict__ rows, int64_t slot, int64_t cap,
                int cryptic_final, float *clonr_row = nullptr, int cov_r = 0, uint64_t seed = 0, k2_rq *rq = nullptr,
-               bool valid = true, float *clonTR = nullptr, int M = 0)
+               bool valid = true, float *clonTR = nullptr, int M = 0, int cstride = 1)
 {
     // rq != nullptr: EVERY lane of the warp runs this loop (valid = false for lanes without a position): the queue uses
     // full-warp ballots
@@ -132,11 +132,11 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
             bool need = false;
             if (valid && clonr_row) {
                 if (present && cov_r > 0 && T >= cov_r) {
-                    if (max(max(C[0], C[1]), max(C[2], C[3])) == T) clonr_row[m] = 1.0f;      // one base only: no draws
+                    if (max(max(C[0], C[1]), max(C[2], C[3])) == T) clonr_row[m * cstride] = 1.0f;      // one base only: no draws
                     else if (rq) need = true;
-                    else clonr_row[m] = k2_rarefied_clon(st.C, T, cov_r, seed, (int64_t)p + start, m);
+                    else clonr_row[m * cstride] = k2_rarefied_clon(st.C, T, cov_r, seed, (int64_t)p + start, m);
                 } else {
-                    clonr_row[m] = CUDART_NAN_F;
+                    clonr_row[m * cstride] = CUDART_NAN_F;
                 }
             }
             if (rq) {
@@ -147,7 +147,7 @@ k2_site_levels(k2_site_state &st, int32_t p, int m0, int mc, const int4 *crow, u
                     rq->e[rq->n + __popc(nm_ & ((1u << (threadIdx.x & 31)) - 1u))] = e;
                 }
                 rq->n += __popc(nm_);
-                if (rq->n >= 32) k2_rq_drain(*rq, false, clonTR, M, cov_r, seed, start);
+                if (rq->n >= 32) k2_rq_drain(*rq, false, clonTR, M, cov_r, seed, start, cstride);
             }
         }
         if (!counted) continue;                                       // call_snv_site -> (None, 0)
@@ -344,10 +344,14 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
         }
         isb_mbar_wait(bar, 0);
         if (active || rqp)                                            // with the draw queue every lane walks the levels
+            // clonTR of cell (position, level) is parked in the first word of the cell's (already consumed) input quad and
+            // written out coalesced below: a row per thread at stride M straight to global memory was one 32-byte sector
+            // per 4-byte store.  Cells are queued for draws only after their quad has been read.
             k2_site_levels<false>(st, p, 0, M, s_in + (size_t)t * M, nm, r, thr2, n_lut, lut_default, start, min_cov,
                                   min_freq, s_cov + (size_t)t * M, s_clon + (size_t)t * M, nullptr, 0, 0, 0,
-                                  clonTR && active ? clonTR + (size_t)p * M : nullptr, cov_r, seed, rqp, active, clonTR, M);
-        if (rqp) k2_rq_drain(rq, true, clonTR, M, cov_r, seed, start);
+                                  clonTR && active ? reinterpret_cast<float *>(s_in + (size_t)t * M) : nullptr, cov_r, seed, rqp,
+                                  active, reinterpret_cast<float *>(s_in) - (int64_t)p0 * M * 4, M, 4);
+        if (rqp) k2_rq_drain(rq, true, reinterpret_cast<float *>(s_in) - (int64_t)p0 * M * 4, M, cov_r, seed, start, 4);
         __syncthreads();
         const int n_out = npos * M;                                   // words; the block's output run starts 16-byte aligned
         const size_t g0 = (size_t)p0 * M;
@@ -357,6 +361,10 @@ k2_call_snvs_staged(int32_t L, int M, const int32_t *__restrict__ counts, const 
         const int4 *sc = reinterpret_cast<const int4 *>(s_cov), *sl = reinterpret_cast<const int4 *>(s_clon);
         for (int e = t; e < n4; e += K2S_THREADS) { gc[e] = sc[e]; gl[e] = sl[e]; }
         for (int e = (n4 << 2) + t; e < n_out; e += K2S_THREADS) { covT[g0 + e] = s_cov[e]; clonT[g0 + e] = s_clon[e]; }
+        if (clonTR) {
+            const float *sr = reinterpret_cast<const float *>(s_in);
+            for (int e = t; e < n_out; e += K2S_THREADS) clonTR[g0 + e] = sr[(size_t)e * 4];
+        }
     } else {
         if (active) {
             nm = nmask ? nmask[p] : 0ull;
