@@ -440,3 +440,51 @@ def test_redrawn_outputs_all_layouts(eng, null_lut, skip_mm):
     assert np.array_equal(np.isnan(other["clonTR"]), np.isnan(exp["clonTR"]))
     none = eng.profile_batch(batch, batch["ref_codes"], batch["splits"], M=M, want=want, rarefied_coverage=0, reads=rd)
     assert np.isnan(none["clonTR"]).all()
+
+
+def test_async_steps_on_device_buffers(eng, null_lut):
+    """The streaming mode bench.py's timed loops use: inputs and outputs resident on the device, three steps enqueued with
+    ISB_NO_SYNC (no host round trip per call), the row counts fetched through isb_row_counts_async, one isb_synchronize at the
+    end -- tables identical to the synchronous call and to the oracle."""
+    import ctypes as C
+    import torch
+    from instrain_b200 import _cabi
+    batch = synth.make_batch(40000, 60, 0.02, 4242, skip_mm=True)
+    exp = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"])
+    rd = reads.events_to_reads(batch)
+    L = len(batch["ref_codes"])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = {k: t(rd[k]) for k in ("seg_start", "seg_len", "seg_pair", "seg_word", "words")}
+    d["seg_len"] = t(np.asarray(rd["seg_len"]).view(np.int16))
+    pair_mm, ref, splits = t(np.zeros(len(batch["pair_mm"]), np.uint8)), t(batch["ref_codes"]), t(batch["splits"].astype(np.int32))
+    p = _cabi.ptr
+    bt = _cabi.IsbReadsBatch(int(rd["n_segs"]), p(d["seg_start"]), p(d["seg_len"]), p(d["seg_pair"]), p(d["seg_word"]),
+                             int(rd["n_words"]), p(d["words"]), int(rd["max_seg_len"]), 0, 0, None, None, pair_mm.numel(), p(pair_mm),
+                             0, L, p(ref), len(batch["splits"]), p(splits), 1, 0)
+    snv_cap, ld_cap = len(exp["snv"]) + 64, len(exp["ld"]) + 64
+    out = dict(covT=torch.empty((L, 1), dtype=torch.int32, device=dev), clonT=torch.empty((L, 1), dtype=torch.float32, device=dev),
+               flags=torch.empty(L, dtype=torch.uint8, device=dev), snv=torch.zeros(snv_cap * 32, dtype=torch.uint8, device=dev),
+               ld=torch.zeros(ld_cap * 64, dtype=torch.uint8, device=dev))
+    res = _cabi.IsbResult(None, None, p(out["covT"]), p(out["clonT"]), p(out["flags"]), p(out["snv"]), snv_cap, p(out["ld"]), ld_cap,
+                          0, 0, 0, 0, None)
+    counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    lib, ctx = eng.lib, eng.ctx
+    sync_prm = _cabi.IsbParams(5, 20, 30, 0, 0.05, 0, 0, 0)
+    assert lib.isb_profile_reads(ctx, C.byref(bt), C.byref(sync_prm), C.byref(res)) == 0      # warm-up: scratch sized, synchronous
+    n_sync = (int(res.n_snv), int(res.n_ld), int(res.n_sites), int(res.n_site_pairs))
+    assert n_sync[:2] == (len(exp["snv"]), len(exp["ld"]))
+    out["snv"].zero_(); out["ld"].zero_(); out["covT"].zero_()
+    torch.cuda.synchronize()
+    prm = _cabi.IsbParams(5, 20, 30, _cabi.ISB_NO_SYNC, 0.05, 0, 0, 0)
+    for _ in range(3):
+        assert lib.isb_profile_reads(ctx, C.byref(bt), C.byref(prm), C.byref(res)) == 0
+        assert int(res.n_snv) == -1                                                            # not known without a round trip
+    assert lib.isb_row_counts_async(ctx, p(counts)) == 0
+    assert lib.isb_synchronize(ctx) == 0
+    assert tuple(counts.tolist()) == n_sync
+    snv = out["snv"].cpu().numpy().view(_cabi.SNV_DT)[:n_sync[0]]
+    ld = out["ld"].cpu().numpy().view(_cabi.LD_DT)[:n_sync[1]]
+    assert_snv_equal(snv.copy(), exp["snv"])
+    assert_ld_equal(ld.copy(), exp["ld"], tol=1e-9)
+    assert np.array_equal(out["covT"].cpu().numpy(), exp["covT"]) and np.array_equal(out["flags"].cpu().numpy(), exp["site_flags"])
