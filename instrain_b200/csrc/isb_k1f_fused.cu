@@ -1096,8 +1096,9 @@ int isb_k1f_profile_launch(isb_ctx *ctx, isb_reads_dev *rd, int64_t n_pairs, int
     isb_time_end(ctx, ts0);
     int ts1 = isb_time_begin(ctx, 1);
     {
-        const int want = (n_tiles + K2Q_WARPS - 1) / K2Q_WARPS, most = ctx->sm_count * 16;
-        k2q_sites<<<want < most ? want : most, K2Q_WARPS * 32, 0, st>>>(b);
+        // one warp per tile, no grid-stride cap: with ~1.3 waves of capped blocks the last wave left half the SMs idle on
+        // small batches (the per-rank share of a strong-scaling run)
+        k2q_sites<<<(n_tiles + K2Q_WARPS - 1) / K2Q_WARPS, K2Q_WARPS * 32, 0, st>>>(b);
         ISB_LAUNCH_CHECK();
     }
     isb_time_end(ctx, ts1);

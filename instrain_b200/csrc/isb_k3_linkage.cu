@@ -905,7 +905,10 @@ int isb_k3_backend_tiles(isb_ctx *ctx, const isb_reads_dev *rd, const isb_k3_til
     a.n_ld = ctx->d_counters + 1; a.n_site_pairs = ctx->d_counters + 3; a.d_err = ctx->d_err;
     a.seed = ctx->seed;
     const int grid = ctx->sm_count * 8;
-    k3_enum_pairs_tiles<<<grid, 256, 0, st>>>(a);
+    // enumeration: one thread per (site, lane) over the site SLOTS (the site count stays on the device; unused slots exit at
+    // once) instead of a fixed grid-stride grid: with 1 - 2 trips per thread the last trip left the SMs half empty
+    const int64_t enum_blocks = (ts->sites_cap * K3_ENUM_LANES + 255) / 256;
+    k3_enum_pairs_tiles<<<(unsigned)(enum_blocks > grid ? (enum_blocks < (1 << 30) ? enum_blocks : (1 << 30)) : grid), 256, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
     k3_pair_stats_dev<<<grid, 256, 0, st>>>(a);
     ISB_LAUNCH_CHECK();
