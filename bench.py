@@ -675,12 +675,11 @@ def main():
         torch.cuda.synchronize()
         dt = ev0.elapsed_time(ev1) / 1e3 / n_calls
 
-        # Two contexts on two host threads (each call is still host buffers -> C-ABI -> host tables): the H2D copy of one
-        # call overlaps the kernels and the D2H copy of the other, which is how a host pipeline feeds the GPU.
-        dt_pipe = None
+        # Two (and three) contexts on as many host threads (each call is still host buffers -> C-ABI -> host tables): the H2D
+        # copy of one call overlaps the kernels and the D2H copy of the others, which is how a host pipeline feeds the GPU.
+        dt_pipe, dt_pipe3 = None, None
         try:
-            eng2 = Engine(local_rank, lut, dflt)
-            o2, hres2 = host_result()
+            extra = [(Engine(local_rank, lut, dflt),) + host_result() for _ in range(2)]     # (engine, host tables, isb_result)
             errs = []
 
             def worker(c, r, n):
@@ -690,37 +689,45 @@ def main():
                 except Exception as ex:                      # noqa: BLE001
                     errs.append(str(ex))
 
-            for n_it in (4, max(25, n_calls // 2)):         # the first repetition warms the second context's scratch buffers
-                torch.cuda.synchronize()
-                t_a = time.time()
-                ths = [threading.Thread(target=worker, args=(eng.ctx, hres, n_it)),
-                       threading.Thread(target=worker, args=(eng2.ctx, hres2, n_it))]
-                [t.start() for t in ths]
-                [t.join() for t in ths]
-                torch.cuda.synchronize()
-                dt_pipe = (time.time() - t_a) / (2 * n_it)
+            for n_ctx in (2, 3):
+                ctxs = [(eng.ctx, hres)] + [(e_[0].ctx, e_[2]) for e_ in extra[:n_ctx - 1]]
+                for n_it in (4, max(25, n_calls // 2)):     # the first repetition warms the extra contexts' scratch buffers
+                    torch.cuda.synchronize()
+                    t_a = time.time()
+                    ths = [threading.Thread(target=worker, args=(c_, r_, n_it)) for c_, r_ in ctxs]
+                    [t.start() for t in ths]
+                    [t.join() for t in ths]
+                    torch.cuda.synchronize()
+                    d_ = (time.time() - t_a) / (n_ctx * n_it)
+                if n_ctx == 2:
+                    dt_pipe = d_
+                else:
+                    dt_pipe3 = d_
             if errs:
                 raise RuntimeError(errs[0])
-            eng2.close()
-        except Exception as ex:                              # noqa: BLE001 - the pipelined figure is optional
-            dt_pipe = None
+            for e_ in extra:
+                e_[0].close()
+        except Exception as ex:                              # noqa: BLE001 - the pipelined figures are optional
+            dt_pipe = dt_pipe3 = None
             print("e2e pipelined leg skipped: %r" % (ex,), file=sys.stderr)
-        best = min(dt, dt_pipe) if dt_pipe else dt
+        best = min([d_ for d_ in (dt, dt_pipe, dt_pipe3) if d_])
         common = len(hs["pair_mm"]) + Ls + hs["splits"].nbytes
         h2d = hd["n_units"] + len(hd["mis_word"]) * 5 + hr["n_segs"] * (4 + 2 + 4) + common
         d2h = Ls * Ms * 12 + Ls + int(hres.n_snv) * 32 + int(hres.n_ld) * 64
-        tot = torch.tensor([Ls / best, Ls / dt, Ls / dt_pipe if dt_pipe else 0.0], dtype=torch.float64, device=dev)
+        tot = torch.tensor([Ls / best, Ls / dt, Ls / dt_pipe if dt_pipe else 0.0, Ls / dt_pipe3 if dt_pipe3 else 0.0],
+                           dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         tot = tot.tolist()
         e2e = {"value": tot[0], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": best * 1e3, "calls_timed": n_calls,
-               "timer": "CUDA events on the context stream around %d back-to-back calls (single context); wall clock around the two-thread leg" % n_calls,
+               "timer": "CUDA events on the context stream around %d back-to-back calls (single context); wall clock around the multi-context legs" % n_calls,
                "api": "isb_profile_reads_delta: BAM-order segments in the reference-delta transfer format (event bits + one entry per base "
                       "that differs from the reference) -> K0d -> the same K1f / linkage kernels as `value` -> host tables",
                "ranks": world, "per_rank_slice": "%d scaffolds (%d positions) per call, pinned host buffers -> C-ABI -> pinned host result tables" % (n_sc, Ls),
                "single_context": {"value": tot[1], "ms_per_step": dt * 1e3},
                "two_contexts_pipelined": ({"value": tot[2], "ms_per_step": dt_pipe * 1e3} if dt_pipe else None),
+               "three_contexts_pipelined": ({"value": tot[3], "ms_per_step": dt_pipe3 * 1e3} if dt_pipe3 else None),
                "host_encode": {"what": "reference-delta encoding of the slice on ONE host core (isb_reads_delta_host), outside the timed "
                                        "region: the packer threads do it while the GPU works", "positions_per_s_per_core": Ls / t_enc}}
 
