@@ -185,6 +185,55 @@ def build_dataset(synth, device, ids, args):
     return d
 
 
+def clip_dataset_to_run(d, lo, hi):
+    """Split-run sharding of ONE scaffold: keep the part of a device-resident read-major data set that lies
+    in [lo, hi) -- the device-side twin of instrain_b200.reads.clip_reads.  The segments that overlap the range are a
+    contiguous slice of the start-sorted table; the few that stick out (coverage many at each border) are cut in place:
+    start / length / first word moved, the nibbles outside the range zeroed.  The batch is then profiled with start =
+    lo & ~7 and L = hi - start; coordinates, pair ids and the keys of the re-drawn outputs stay those of the whole."""
+    import torch
+    rd = d["reads"]
+    s = rd["seg_start"].to(torch.int64)
+    n = rd["seg_len"].to(torch.int64) & 0xffff
+    keep = torch.nonzero((s < hi) & (s + n > lo)).flatten()
+    i0, i1 = (int(keep[0]), int(keep[-1]) + 1) if keep.numel() else (0, 0)
+    origin = lo & ~7
+    words = rd["words"].clone()
+    seg_start, seg_len = rd["seg_start"][i0:i1].clone(), rd["seg_len"][i0:i1].clone()
+    seg_pair, seg_word = rd["seg_pair"][i0:i1].clone(), rd["seg_word"][i0:i1].clone()
+    s, n = s[i0:i1], n[i0:i1]
+    cut = torch.nonzero((s < lo) | (s + n > hi)).flatten()
+    if cut.numel():                                         # the border segments, fixed on the host (a few hundred)
+        cs, cn, cw = s[cut].cpu().numpy(), n[cut].cpu().numpy(), seg_word[cut].cpu().numpy()
+        nw_old = ((cs & 7) + cn + 7) >> 3
+        idx = np.concatenate([w0 + np.arange(k) for w0, k in zip(cw, nw_old)])
+        old = words[torch.from_numpy(idx).to(words.device)].cpu().numpy().astype(np.uint32).astype(np.uint64)
+        s2, e2 = np.maximum(cs, lo), np.minimum(cs + cn, hi)
+        c_first, c_last = (s2 >> 3) - (cs >> 3), ((e2 - 1) >> 3) - (cs >> 3)
+        new = np.zeros_like(old)
+        off = np.concatenate([[0], np.cumsum(nw_old)])
+        for j in range(len(cs)):
+            w = old[off[j]:off[j + 1]].copy()
+            w[:c_first[j]] = 0
+            w[c_last[j] + 1:] = 0
+            w[c_first[j]] &= ~((np.uint64(1) << np.uint64(4 * (s2[j] & 7))) - np.uint64(1))
+            w[c_last[j]] &= (np.uint64(1) << np.uint64(4 * (((e2[j] - 1) & 7) + 1))) - np.uint64(1)
+            new[off[j]:off[j + 1]] = w
+        words[torch.from_numpy(idx).to(words.device)] = torch.from_numpy((new & np.uint64(0xffffffff)).astype(np.uint32).view(np.int32)).to(words.device)
+        dev = seg_start.device
+        seg_start[cut] = torch.from_numpy(s2.astype(np.int32)).to(dev)
+        seg_len[cut] = torch.from_numpy((e2 - s2).astype(np.int16)).to(dev)
+        seg_word[cut] = torch.from_numpy((cw + c_first).astype(np.int64)).to(dev)
+    out = dict(d)
+    out["reads"] = dict(rd, n_segs=i1 - i0, seg_start=seg_start, seg_len=seg_len, seg_pair=seg_pair, seg_word=seg_word, words=words)
+    sp = d["splits"]
+    out["splits"] = sp[(sp[:, 0] >= lo) & (sp[:, 1] < hi)].contiguous()
+    out["ref_codes"] = d["ref_codes"][origin:hi].contiguous()
+    out["start"], out["L_run"] = origin, hi - origin
+    out["n_events"] = int((seg_len.to(torch.int64) & 0xffff).sum().item())
+    return out
+
+
 class Job:
     """One rank's share of the workload resident in HBM + the result buffers; step() = one pass of the hot path."""
 
@@ -194,7 +243,8 @@ class Job:
         self.eng, self.d, self.args, self.dev, self.layout = eng, d, args, dev, layout
         self._cabi = _cabi
         p = _cabi.ptr
-        self.Ltot = d["L"] * d["n_scaffolds"]
+        self.Ltot = d.get("L_run", d["L"] * d["n_scaffolds"])   # a run of splits of one scaffold: its own start / length
+        start_ = int(d.get("start", 0))
         self.npairs = d["pair_mm"].numel()
         self.M = int(d["pair_mm"].max().item()) + 1 if self.npairs else 1
         L_, M_ = self.Ltot, self.M
@@ -217,7 +267,7 @@ class Job:
             rd = d["reads"]
             self.batch = _cabi.IsbReadsBatch(int(rd["n_segs"]), p(rd["seg_start"]), p(rd["seg_len"]), p(rd["seg_pair"]),
                                              p(rd["seg_word"]), int(rd["n_words"]), p(rd["words"]), int(rd["max_seg_len"]), 0,
-                                             0, None, None, self.npairs, p(d["pair_mm"]), 0, L_, p(d["ref_codes"]),
+                                             0, None, None, self.npairs, p(d["pair_mm"]), start_, L_, p(d["ref_codes"]),
                                              len(d["splits"]), p(d["splits"]), M_, 0)
             self.entry = eng.lib.isb_profile_reads
         elif layout == "cols":
@@ -397,8 +447,11 @@ def main():
     per_gpu = args.scaffolds / (n_ranks if strong else 1)
     config = {"workload": workload, "scaffolds": args.scaffolds, "scaffold_len": args.L, "coverage": args.cov,
               "snv_density": args.dens, "min_cov": 5, "min_freq": 0.05, "min_snp": 20, "window_length": 10000,
-              "sharding": (("the same %d scaffolds LPT-partitioned over %d ranks (strong scaling), NCCL gather of SNV/linkage rows to rank 0"
-                            % (args.scaffolds, n_ranks)) if strong else
+              "sharding": ((("the same %d scaffold(s) cut into contiguous runs of splits, one run per rank (strong scaling; reads that reach "
+                             "into a run are cut at its borders), NCCL gather of SNV/linkage rows to rank 0" % args.scaffolds)
+                            if args.scaffolds < n_ranks else
+                            ("the same %d scaffolds LPT-partitioned over %d ranks (strong scaling), NCCL gather of SNV/linkage rows to rank 0"
+                             % (args.scaffolds, n_ranks))) if strong else
                            ("%d scaffolds per rank (weak scaling), NCCL gather of SNV/linkage rows to rank 0" % args.scaffolds))
               if n_ranks > 1 else "single GPU",
               "layout": {"reads": "BAM-order aligned segments (4-bit one-hot code per aligned base, stored once per read: what the host packer emits)",
@@ -437,13 +490,29 @@ def main():
     # ------------------------------------------------------------------------------------------------ B200 arm
     from instrain_b200.engine import Engine
     t_gen = time.time()
-    if world > 1 and strong:
+    run = None
+    if world > 1 and strong and args.scaffolds < world:
+        # fewer scaffolds than GPUs (BASELINE config 5: one 10 Mb scaffold): every scaffold is cut into contiguous runs of
+        # splits, one run per rank of its group (instrain_b200.shard.split_runs); a rank profiles its run from the reads
+        # that overlap it (read halo, cut at the run's borders)
+        from instrain_b200.shard import split_runs
+        from instrain_b200.synth import iterate_splits
+        per = world // args.scaffolds                                   # ranks per scaffold (the last group takes the rest)
+        sc = min(rank // per, args.scaffolds - 1)
+        grp = list(range(sc * per, world if sc == args.scaffolds - 1 else (sc + 1) * per))
+        sp = iterate_splits(args.L, 10000)
+        a_, b_ = split_runs(sp, [e - s_ + 1 for s_, e in sp], len(grp))[grp.index(rank)]
+        run = (sp[a_][0], sp[b_ - 1][1] + 1)
+        my_ids = [sc]
+    elif world > 1 and strong:
         # LPT over aligned bases (all scaffolds of the synthetic set weigh the same: contiguous blocks come out)
         my_ids = lpt_partition([float(args.L) * args.cov] * args.scaffolds, world)[rank]
     else:
         my_ids = list(range(rank * args.scaffolds, (rank + 1) * args.scaffolds))
     if args.layout == "reads":
         d = build_dataset(synth, local_rank, my_ids, args)
+        if run is not None:
+            d = clip_dataset_to_run(d, run[0], run[1])
     else:                                                # the older layouts: one generator call, N = 1 or weak scaling only
         if world > 1 and strong:
             raise SystemExit("--layout %s is timed with --scaling weak only" % args.layout)
@@ -561,7 +630,7 @@ def main():
 
     # -------------------------------------------------------------------------------- weak scaling beside (N > 1)
     weak = None
-    if world > 1 and strong and not args.no_weak and args.layout == "reads":
+    if world > 1 and strong and not args.no_weak and args.layout == "reads" and run is None:
         del job, gather, d
         torch.cuda.empty_cache()
         dw = build_dataset(synth, local_rank, list(range(rank * args.scaffolds, (rank + 1) * args.scaffolds)), args)
@@ -618,7 +687,7 @@ def main():
     # format of the same BAM-order segments), isb_profile_reads_delta (H2D + K0d + the same K1f / linkage kernels + D2H of
     # every result table), pinned host tables out.  Every rank runs its own slice; the job's e2e is the sum over ranks.
     e2e = None
-    if args.layout == "reads" and not args.no_e2e:
+    if args.layout == "reads" and not args.no_e2e and run is None:    # (a run of splits: no bounded host slice is cut)
         from instrain_b200.reads import delta_reads_host
         n_sc = max(1, min(args.e2e_scaffolds, d["n_scaffolds"]))
         hs = synth.reads_to_host(d, 0, n_sc)

@@ -254,3 +254,48 @@ def concat_streams(parts):
                 seg_word=np.concatenate(seg_word) if seg_word else np.zeros(0, np.int64), n_words=n_words, words=words,
                 max_seg_len=max([p["max_seg_len"] for p in parts] + [1]), nev_pos=cat("nev_pos", np.int32),
                 nev_pair=cat("nev_pair", np.int32))
+
+
+def clip_reads(rd, lo, hi):
+    """The part of a read-major batch that lies in the coordinates [lo, hi): every segment that overlaps the range, cut to
+    it (first / last word masked), re-laid-out as a batch of its own.  Coordinates and pair ids are KEPT; the batch is to be
+    profiled with `start = origin = lo & ~7` and `L = hi - origin` (a batch must start on an 8-position column; the up to 7
+    positions in front of `lo` carry no events), so rows, and the keys of the re-drawn outputs, come out in the
+    coordinates of the whole.  Returns (batch, origin).
+
+    This is the read halo of SURVEY 8(e): a contiguous run of splits of ONE large scaffold becomes a batch of its own --
+    the reads that reach into the run from outside are cut at its borders, exactly what a position of the run sees of them
+    -- so the runs of a scaffold can be profiled on different GPUs (linkage never crosses a split,
+    inStrain/profile/profile_utilities.py:165,184-185; the mate-overlap tweak is already in the codes)."""
+    lo, hi = int(lo), int(hi)
+    origin = lo & ~7
+    s = rd["seg_start"].astype(np.int64)
+    n = rd["seg_len"].astype(np.int64)
+    keep = (s < hi) & (s + n > lo)
+    s, n = s[keep], n[keep]
+    sw = np.asarray(rd["seg_word"], dtype=np.int64)[keep]
+    s2, e2 = np.maximum(s, lo), np.minimum(s + n, hi)
+    c_first, c_last = (s2 >> 3) - (s >> 3), ((e2 - 1) >> 3) - (s >> 3)       # word range inside the original segment
+    nw = c_last - c_first + 1
+    m = len(s)
+    seg_word = np.ones(m, dtype=np.int64)
+    if m:
+        seg_word[1:] = 1 + np.cumsum(nw[:-1] + 1)
+    n_words = int(seg_word[-1] + nw[-1] + 1) if m else 1
+    n_words = (n_words + 3) // 4 * 4
+    words = np.zeros(n_words, dtype=np.uint32)
+    k = np.arange(int(nw.sum()), dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
+    w = rd["words"][np.repeat(sw + c_first, nw) + k].astype(np.uint64)
+    first = k == 0
+    last = k == np.repeat(nw, nw) - 1
+    lo_nib = np.repeat(s2 & 7, nw)                                            # nibbles below s2 in the first word: cut
+    hi_nib = np.repeat(((e2 - 1) & 7) + 1, nw)                                # nibbles kept in the last word
+    w = np.where(first, w & ~((np.uint64(1) << (4 * lo_nib).astype(np.uint64)) - np.uint64(1)), w)
+    w = np.where(last, w & ((np.uint64(1) << (4 * hi_nib).astype(np.uint64)) - np.uint64(1)), w)
+    words[np.repeat(seg_word, nw) + k] = (w & np.uint64(0xffffffff)).astype(np.uint32)
+    nk = (rd["nev_pos"] >= lo) & (rd["nev_pos"] < hi)
+    out = dict(n_segs=m, seg_start=s2.astype(np.int32), seg_len=(e2 - s2).astype(np.uint16),
+               seg_pair=np.asarray(rd["seg_pair"])[keep].astype(np.int32), seg_word=seg_word, n_words=n_words, words=words,
+               max_seg_len=int(rd["max_seg_len"]), nev_pos=rd["nev_pos"][nk].astype(np.int32),
+               nev_pair=rd["nev_pair"][nk].astype(np.int32))
+    return out, origin

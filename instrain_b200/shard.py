@@ -45,3 +45,25 @@ def gather_rows(rows, dst=0, group=None, device=None):
         return None
     parts = [np.frombuffer(b.cpu().numpy().tobytes()[:c * item], dtype=rows.dtype) for b, c in zip(bufs, counts)]
     return np.concatenate(parts) if parts else rows[:0]
+
+
+def split_runs(splits, weights, n_ranks):
+    """Contiguous runs of the splits of ONE scaffold, one per rank, of about equal weight (a scaffold too large
+    for a balanced scaffold-wise partition is sharded by runs of splits; every run is profiled from the reads that overlap
+    it, instrain_b200.reads.clip_reads).  splits: [(start, end)] in order; weights: per-split cost (aligned bases, or
+    positions).  Returns [(first split, one past the last)] -- at most one run per split."""
+    import numpy as np
+    n = len(splits)
+    k = max(1, min(int(n_ranks), n))
+    w = np.asarray(weights, dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, k):
+        target = cum[-1] * r / k
+        i = int(np.searchsorted(cum, target, side="left"))
+        if i > 0 and abs(cum[i - 1] - target) <= abs(cum[min(i, n)] - target):
+            i -= 1
+        i = max(cuts[-1] + 1, min(i, n - (k - r)))
+        cuts.append(i)
+    cuts.append(n)
+    return [(a, b) for a, b in zip(cuts, cuts[1:])]

@@ -1,0 +1,131 @@
+"""a single large scaffold is sharded by contiguous runs of splits with a read halo.  instrain_b200.reads.
+clip_reads cuts a read-major batch to the positions of a run; instrain_b200.shard.split_runs partitions the splits of one
+scaffold into runs of about equal weight.  CPU tests: the clipped batch encodes exactly the events of the run, and the
+oracle on the runs, put back together, equals the oracle on the whole scaffold -- SNV rows, linkage rows (none crosses a
+split), coverage and clonality at every position."""
+import numpy as np
+
+from conftest import assert_ld_equal, assert_snv_equal, load_lut
+from instrain_b200 import reads
+from instrain_b200.shard import split_runs
+from oracle import restate, synth
+
+
+def _run_batch(batch, rd, lo, hi, run_splits):
+    sub, origin = reads.clip_reads(rd, lo, hi)
+    ev = reads.reads_to_events(sub)
+    ev["pair_mm"] = batch["pair_mm"]
+    ref = batch["ref_codes"][origin:hi]
+    splits = np.asarray(run_splits, dtype=np.int32)
+    return sub, origin, ev, ref, splits
+
+
+def test_split_runs_cover_and_balance():
+    splits = synth.batch_splits(95000, 1, 10000) if hasattr(synth, "batch_splits") else None
+    from instrain_b200.synth import iterate_splits
+    sp = iterate_splits(95000, 10000)
+    w = np.ones(len(sp))
+    runs = split_runs(sp, w, 3)
+    assert runs[0][0] == 0 and runs[-1][1] == len(sp) and all(a[1] == b[0] for a, b in zip(runs, runs[1:]))
+    sizes = [b - a for a, b in runs]
+    assert max(sizes) - min(sizes) <= 1 and len(runs) == 3
+    assert split_runs(sp[:2], np.ones(2), 8) == [(0, 1), (1, 2)]          # never more runs than splits
+
+
+def test_clipped_runs_equal_the_whole_scaffold():
+    lut, dflt = load_lut()
+    batch = synth.make_batch(42000, 60, 0.03, 20260501, skip_mm=False, n_frac=0.002)
+    rd = reads.events_to_reads(batch)
+    whole = restate.profile_events(batch, batch["ref_codes"], lut, dflt, batch["splits"])
+    sp = [tuple(int(v) for v in r) for r in batch["splits"]]
+    assert len(sp) >= 4
+    runs = split_runs(sp, np.ones(len(sp)), 3)
+    snv, ld = [], []
+    covT = np.zeros_like(whole["covT"])
+    clonT = np.full_like(whole["clonT"], np.nan)
+    M = whole["covT"].shape[1]
+    for a, b in runs:
+        lo, hi = sp[a][0], sp[b - 1][1] + 1
+        sub, origin, ev, ref, splits = _run_batch(batch, rd, lo, hi, sp[a:b])
+        # the clipped batch holds exactly the passing events of the run
+        full_ev = reads.reads_to_events(rd)
+        sel = (full_ev["ref_pos"] >= lo) & (full_ev["ref_pos"] < hi)
+        for k in ("ref_pos", "base", "read_id"):
+            assert np.array_equal(ev[k], full_ev[k][sel]), k
+        assert sub["seg_start"].min() >= lo and (sub["seg_start"].astype(np.int64) + sub["seg_len"]).max() <= hi
+        got = restate.profile_events(ev, ref, lut, dflt, splits, start=origin, M=M)     # rows come back in whole-batch coordinates
+        snv.append(got["snv"]); ld.append(got["ld"])
+        covT[lo:hi] = got["covT"][lo - origin:]
+        clonT[lo:hi] = got["clonT"][lo - origin:]
+        assert not got["covT"][:lo - origin].any()                          # the alignment pad in front of the run: no events
+    assert_snv_equal(np.concatenate(snv), whole["snv"])
+    assert_ld_equal(np.concatenate(ld), whole["ld"], tol=0.0)
+    assert np.array_equal(covT, whole["covT"])
+    assert np.array_equal(np.isnan(clonT), np.isnan(whole["clonT"]))
+    ok = ~np.isnan(clonT)
+    assert np.array_equal(clonT[ok].view(np.uint32), whole["clonT"][ok].view(np.uint32))
+
+
+# ---- on the device --------------------------------------------------------------------------------------------------------
+import pytest
+
+
+@pytest.fixture(scope="module")
+def eng(null_lut):
+    from instrain_b200.engine import Engine
+    e = Engine(0, null_lut[0], null_lut[1])
+    yield e
+    e.close()
+
+
+@pytest.mark.gpu
+def test_gpu_runs_equal_the_whole_scaffold(eng, null_lut):
+    """The CUDA path on the clipped runs (start = the run's origin) against the oracle on the whole scaffold."""
+    batch = synth.make_batch(52000, 70, 0.03, 20260502, skip_mm=True)
+    rd = reads.events_to_reads(batch)
+    whole = restate.profile_events(batch, batch["ref_codes"], null_lut[0], null_lut[1], batch["splits"])
+    sp = [tuple(int(v) for v in r) for r in batch["splits"]]
+    snv, ld = [], []
+    covT = np.zeros_like(whole["covT"])
+    for a, b in split_runs(sp, np.ones(len(sp)), 4):
+        lo, hi = sp[a][0], sp[b - 1][1] + 1
+        sub, origin = reads.clip_reads(rd, lo, hi)
+        got = eng.profile_batch(batch, batch["ref_codes"][origin:hi], np.asarray(sp[a:b], np.int32), start=origin, M=1, reads=sub,
+                                want=("covT", "clonT", "clonTR", "snv", "ld"))
+        snv.append(got["snv"]); ld.append(got["ld"])
+        covT[lo:hi] = got["covT"][lo - origin:]
+    assert_snv_equal(np.concatenate(snv), whole["snv"])
+    assert_ld_equal(np.concatenate(ld), whole["ld"], tol=1e-9)
+    assert np.array_equal(covT, whole["covT"])
+
+
+@pytest.mark.gpu
+def test_gpu_bench_run_clipping_equals_the_whole_scaffold(eng):
+    """bench.py's device-side twin (clip_dataset_to_run) on the generator's data: the runs of one scaffold, profiled one by
+    one, give the rows of the whole scaffold."""
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from instrain_b200 import synth as dsynth
+    args = types.SimpleNamespace(L=80000, cov=60, dens=0.03, mm=False, seg_words=None)
+    d = bench.build_dataset(dsynth, 0, [0], args)
+    npf = lambda t: t.cpu().numpy()
+    ev = dict(pair_mm=npf(d["pair_mm"]))
+    want = ("covT", "snv", "ld")
+    whole = eng.profile_batch(ev, npf(d["ref_codes"]), npf(d["splits"]), M=1, reads=d["reads"], want=want)
+    assert len(whole["snv"]) > 500 and len(whole["ld"]) > 500
+    sp = [tuple(int(v) for v in r) for r in npf(d["splits"])]
+    snv, ld = [], []
+    covT = np.zeros_like(whole["covT"])
+    for a, b in split_runs(sp, np.ones(len(sp)), 3):
+        lo, hi = sp[a][0], sp[b - 1][1] + 1
+        dd = bench.clip_dataset_to_run(d, lo, hi)
+        assert dd["start"] == lo & ~7 and dd["L_run"] == hi - dd["start"] and len(dd["splits"]) == b - a
+        got = eng.profile_batch(ev, npf(dd["ref_codes"]), npf(dd["splits"]), start=dd["start"], M=1, reads=dd["reads"], want=want)
+        snv.append(got["snv"]); ld.append(got["ld"])
+        covT[lo:hi] = got["covT"][lo - dd["start"]:]
+    assert_snv_equal(np.concatenate(snv), whole["snv"])
+    assert_ld_equal(np.concatenate(ld), whole["ld"], tol=0.0)
+    assert np.array_equal(covT, whole["covT"])
