@@ -14,7 +14,7 @@ import json
 try:
     d = json.loads([l for l in open("$out/${tag}_n$NG.json") if l.startswith("{")][-1])
     print("N=%d value %.3e ms/step %.3f scaling %s" % (d["n_gpus"], d["value"], d["ms_per_step"], d["scaling"]), d["roofline"]["stage_ms_per_step"])
-    print("weak", d["weak_scaling"]); print("e2e %.3e" % d["e2e"]["value"], d["e2e"]["single_context"], d["e2e"]["two_contexts_pipelined"])
+    print("weak", d["weak_scaling"]); print("e2e", d["e2e"] and ("%.3e" % d["e2e"]["value"], d["e2e"]["single_context"], d["e2e"]["two_contexts_pipelined"]))
     print("gather bytes/step", d["gather_bytes_per_step"], "sustained", d["sustained"])
 except Exception as ex:
     print("failed", ex)
