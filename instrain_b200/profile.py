@@ -387,6 +387,51 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     return res
 
 
+def profile_scaffold_run(bam, name, r2m, seq, run_splits, engine, **kwargs):
+    """One contiguous run of splits of ONE scaffold (a scaffold too large for a balanced scaffold-wise
+    partition is sharded by runs of splits): the scaffold is packed, the reads that overlap the run are cut at its borders
+    (instrain_b200.reads.clip_reads) and the run is profiled as a batch of its own with start = its origin, so rows come
+    back in scaffold coordinates.  run_splits: [(start, end)] of the run, in order.  Returns dict(snv, ld: row arrays;
+    lo, hi; covT, clonT, clonTR, nmask: dense arrays of the positions [lo, hi); M)."""
+    from .packer import find_bai, read_bai
+    lo, hi = int(run_splits[0][0]), int(run_splits[-1][1]) + 1
+    with BamPacker(bam) as bp:
+        tid = bp.ref_names.index(name)
+        bai = find_bai(bam)
+        if bai is not None:
+            first = read_bai(bai)[tid]
+            if first is not None:
+                bp.seek(first)
+        while True:
+            t = bp.peek_tid()
+            if t < 0 or t >= tid:
+                break
+            bp.pack_scaffold_reads(t, {})                                  # no index: skip the earlier scaffolds
+        part = bp.pack_scaffold_reads(tid, r2m) if bp.peek_tid() == tid else None
+    L_run = hi - (lo & ~7)
+    if part is None or len(part["seg_start"]) == 0:
+        M = _r2m_levels(r2m)
+        return dict(snv=np.zeros(0, _cabi_mod().SNV_DT), ld=np.zeros(0, _cabi_mod().LD_DT), lo=lo, hi=hi, M=M,
+                    covT=np.zeros((hi - lo, M), np.int32), clonT=np.full((hi - lo, M), np.nan, np.float32),
+                    clonTR=np.full((hi - lo, M), np.nan, np.float32), nmask=np.zeros(hi - lo, np.uint64))
+    sub, origin = reads_mod.clip_reads(reads_mod.concat_streams([part]), lo, hi)
+    ref_codes = encode_reference(seq)[origin:hi]
+    out = engine.profile_batch(dict(pair_mm=part["pair_mm"]), ref_codes, np.asarray(run_splits, np.int32), start=origin,
+                               min_cov=int(kwargs.get("min_cov", 5)), min_freq=float(kwargs.get("min_freq", 0.05)),
+                               min_snp=int(kwargs.get("min_snp", 20)), want=("covT", "clonT", "clonTR", "nmask", "snv", "ld"),
+                               rarefied_coverage=int(kwargs.get("rarefied_coverage", 50)), seed=int(kwargs.get("seed", 0) or 0),
+                               reads=sub)
+    assert len(ref_codes) == L_run
+    d = lo - origin
+    return dict(snv=out["snv"], ld=out["ld"], lo=lo, hi=hi, M=int(out["M"]), covT=out["covT"][d:], clonT=out["clonT"][d:],
+                clonTR=out["clonTR"][d:] if "clonTR" in out else None, nmask=out["nmask"][d:])
+
+
+def _cabi_mod():
+    from . import _cabi
+    return _cabi
+
+
 def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     """Drop-in for inStrain.profile.profile_bam (profile/__init__.py:7-18).  Writes the SNVprofile directory at ISP_loc
     (instrain_b200/store.py: attributes.tsv, csv.gz tables, covT / clonT .hd5) and returns the on-disk object the
@@ -467,7 +512,28 @@ def profile_bam_distributed(bam, Fdb, sR2M, ISP_loc, **kwargs):
     if s2s is None or sR2M is None:
         raise ValueError("profile_bam_distributed needs sR2M and kwargs['s2s'] (run the read filter once, on rank 0 or on every rank)")
     order = list(sR2M)                                                    # the same on every rank
-    mine = lpt_partition([float(len(sR2M[s])) for s in order], world)[rank]
+    weights = [float(len(sR2M[s])) for s in order]
+    # A scaffold heavier than a rank's fair share cannot be balanced scaffold-wise: it is cut into contiguous runs of its
+    # splits (one unit each, weight by length), profiled from the reads that overlap the run (profile_scaffold_run) and
+    # put back together on rank 0.  kwargs["split_runs"] = False keeps every scaffold whole.
+    units, heavy = [], {}                                                 # unit = (scaffold index, run index or None, weight)
+    fair = sum(weights) / world if world > 1 else float("inf")
+    st = _SplitTable(Fdb, int(kwargs.get("window_length", 10000)))
+    for i, name in enumerate(order):
+        k = int(np.ceil(weights[i] / fair)) if (kwargs.get("split_runs", True) and weights[i] > 1.25 * fair) else 1
+        sp = st(name, len(s2s[name])) if k > 1 and name in s2s else None
+        if sp is not None and len(sp) > 1:
+            from .shard import split_runs
+            runs = split_runs(sp, [e - a + 1 for a, e in sp], min(k, world))
+            heavy[i] = (sp, runs)
+            tot_len = float(sum(e - a + 1 for a, e in sp))
+            for r_, (a_, b_) in enumerate(runs):
+                units.append((i, r_, weights[i] * sum(e - a + 1 for a, e in sp[a_:b_]) / tot_len))
+        else:
+            units.append((i, None, weights[i]))
+    mine_u = [units[j] for j in lpt_partition([u[2] for u in units], world)[rank]]
+    mine = [u[0] for u in mine_u if u[1] is None]
+    my_runs = [(u[0], u[1]) for u in mine_u if u[1] is not None]
     sub = {order[i]: sR2M[order[i]] for i in mine}
     kw = dict(kwargs)
     kw.pop("s2s")
@@ -480,7 +546,28 @@ def profile_bam_distributed(bam, Fdb, sR2M, ISP_loc, **kwargs):
     if dist.get_backend() == "nccl":
         import torch
         gdev = torch.device("cuda", device)
+    run_engine = None
+    if my_runs or (rank == 0 and heavy):                                  # runs, and their merge on rank 0, need an engine of their own
+        run_engine = Engine(device, model_file=kwargs.get("model_file"), fdr=float(kwargs.get("fdr", 1e-6)) or 1e-6)
     res = profile_scaffolds(bam, sub, s2s, Fdb=Fdb, device=device, **kw)
+    run_parts = []
+    for i, r_ in my_runs:
+        sp, runs = heavy[i]
+        a_, b_ = runs[r_]
+        try:
+            rr = profile_scaffold_run(bam, order[i], sR2M[order[i]], s2s[order[i]], sp[a_:b_], run_engine, **kwargs)
+        except Exception as e:                                           # noqa: BLE001 - the reference's per-split catch-all
+            logging.error("\n{1} DEBUG FAILURE SplitException {0} {2}\n".format(order[i], time.strftime("%m-%d %H:%M"), r_) + str(e))
+            res.failures.append(order[i])
+            continue
+        seq = s2s[order[i]]
+        res.rows["snv"].append(rr["snv"])
+        res.rows["snv_sidx"].append(np.full(len(rr["snv"]), i, np.int32))
+        res.rows["snv_ref"].append(np.array([ord(seq[int(p_)]) for p_ in rr["snv"]["pos"]], dtype=np.uint8))
+        res.rows["ld"].append(rr["ld"])
+        res.rows["ld_sidx"].append(np.full(len(rr["ld"]), i, np.int32))
+        run_parts.append(dict(sidx=i, run=r_, lo=rr["lo"], hi=rr["hi"], M=rr["M"], covT=rr["covT"], clonT=rr["clonT"],
+                              clonTR=rr["clonTR"], nmask=rr["nmask"]))
     cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dtype=dt)
     snv = gather_rows(cat(res.rows["snv"], _cabi.SNV_DT), device=gdev)
     snv_sidx = gather_rows(cat(res.rows["snv_sidx"], np.int32), device=gdev)
@@ -488,10 +575,12 @@ def profile_bam_distributed(bam, Fdb, sR2M, ISP_loc, **kwargs):
     ld = gather_rows(cat(res.rows["ld"], _cabi.LD_DT), device=gdev)
     ld_sidx = gather_rows(cat(res.rows["ld_sidx"], np.int32), device=gdev)
     small = dict(scaffold_list=res.scaffold_list, scaffolds=res.scaffolds, failures=res.failures,
-                 summary=res.cumulative_scaffold_table, seconds=res.timing.get("profile_scaffolds_s"))
+                 summary=res.cumulative_scaffold_table, seconds=res.timing.get("profile_scaffolds_s"), runs=run_parts)
     parts = [None] * world if rank == 0 else None
     dist.gather_object(small, parts, dst=0)
     if rank != 0:
+        if run_engine is not None:
+            run_engine.close()
         return None
     out = ProfileResult()
     names = np.asarray(order, dtype=object)
@@ -510,6 +599,42 @@ def profile_bam_distributed(bam, Fdb, sR2M, ISP_loc, **kwargs):
         out.scaffolds.update(p["scaffolds"])
         out.failures.extend(p["failures"])
         out.timing["rank%d_profile_scaffolds_s" % r] = p["seconds"]
+    # the scaffolds that were profiled by runs: dense series put back together, basewise tables and the merge-stage
+    # summary (K4) computed on rank 0
+    for i, (sp, runs) in sorted(heavy.items()):
+        name = order[i]
+        pieces = sorted((q for p in parts for q in p["runs"] if q["sidx"] == i), key=lambda q: q["lo"])
+        if len(pieces) != len(runs) or name in out.failures:
+            if name not in out.failures:
+                out.failures.append(name)
+            continue
+        Ls, Ms = len(s2s[name]), max(q["M"] for q in pieces)
+        covT = np.zeros((Ls, Ms), np.int32)
+        clonT = np.full((Ls, Ms), np.nan, np.float32)
+        clonTR = np.full((Ls, Ms), np.nan, np.float32)
+        nmask = np.zeros(Ls, np.uint64)
+        for q in pieces:
+            sl = slice(q["lo"], q["hi"])
+            covT[sl, :q["M"]] = q["covT"]
+            clonT[sl, :q["M"]] = q["clonT"]
+            if q["clonTR"] is not None:
+                clonTR[sl, :q["M"]] = q["clonTR"]
+            nmask[sl] = q["nmask"]
+        bounds = np.array([0, Ls], dtype=np.int32)
+        k4 = run_engine.scaffold_summary(covT, clonT, nmask, bounds)
+        k4r = run_engine.scaffold_summary(covT, clonTR, nmask, bounds)
+        sel = snv[snv_sidx == i]
+        sums.append(summary.summary_table(k4, sel, [name], np.array([0]), Ms, rows_rarefied=k4r))
+        spf = ScaffoldProfile(name, Ls)
+        levels = tables.present_levels(covT, nmask)
+        spf.covT = tables.basewise(covT, "coverage", levels)
+        spf.clonT = tables.basewise(clonT, "clonality", levels)
+        spf.clonTR = tables.basewise(clonTR, "clonality", levels)
+        out.scaffolds[name] = spf
+        out.scaffold_list.append(name)
+    if run_engine is not None:
+        run_engine.close()
+    out.cumulative_scaffold_table = pd.concat(sums, ignore_index=True) if sums else pd.DataFrame(columns=summary.COLUMNS)
     by_snp = {k: v for k, v in out.raw_snp_table.groupby("scaffold", sort=False)}
     by_ld = {k: v for k, v in out.raw_linkage_table.groupby("scaffold", sort=False)}
     for name, sp in out.scaffolds.items():

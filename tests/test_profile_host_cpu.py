@@ -35,8 +35,9 @@ class OracleEngine:
             self.formats.append("segments")
             events = reads_mod.reads_to_events(reads)
         events["pair_mm"] = np.asarray(ev["pair_mm"])
-        out = restate.profile_events(events, ref_codes, self.lut, self.dflt, splits, min_cov=min_cov, min_freq=min_freq,
-                                     min_snp=min_snp)
+        out = restate.profile_events(events, ref_codes, self.lut, self.dflt, splits, start=int(kw.get("start", 0)), min_cov=min_cov,
+                                     min_freq=min_freq, min_snp=min_snp, rarefied_coverage=int(kw.get("rarefied_coverage", 50)),
+                                     seed=int(kw.get("seed", 0)))
         out["M"] = out["counts"].shape[1]
         for k in ("n_snv", "n_ld"):
             out[k] = len(out[k[2:]])
