@@ -155,3 +155,40 @@ def test_polymorpher_extract_snvs_from_bam(null_lut):
             n_chk += 1
     assert n_chk > 20
     assert extract_SNVS_from_bam(bam, rdic[name], [], name) == {}
+
+
+def test_profile_scaffold_run_equals_whole_scaffold(null_lut):
+    """SURVEY 8(e) on the device: the largest scaffold of the bundled BAM profiled by two contiguous runs of its splits
+    (profile_scaffold_run: packer -> clip_reads -> CUDA path with start = the run's origin) gives the rows and the
+    per-position coverage of profiling it whole."""
+    import json
+    from instrain_b200.engine import Engine
+    from instrain_b200.profile import _SplitTable, profile_scaffold_run, profile_scaffolds
+    from instrain_b200.shard import split_runs
+    name = "N5_271_010G1_scaffold_963"
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    bam = os.path.join(GOLDEN, "c1_G1_subset.bam")
+    eng = Engine(0, null_lut[0], null_lut[1])
+    try:
+        whole = profile_scaffolds(bam, {name: rdic[name]}, seqs, engine=eng, window_length=300)
+        sp = _SplitTable(None, 300)(name, len(seqs[name]))
+        assert len(sp) >= 2
+        snv_pos, ld_keys = [], []
+        cov = {}
+        for a, b in split_runs(sp, [e - s + 1 for s, e in sp], 2):
+            rr = profile_scaffold_run(bam, name, rdic[name], seqs[name], sp[a:b], eng)
+            snv_pos += [(int(p), int(m)) for p, m in zip(rr["snv"]["pos"], rr["snv"]["mm"])]
+            ld_keys += [(int(x), int(y), int(m), int(c)) for x, y, m, c in zip(rr["ld"]["pos_a"], rr["ld"]["pos_b"], rr["ld"]["mm"], rr["ld"]["c_AB"])]
+            for m in range(rr["M"]):
+                nz = np.nonzero(rr["covT"][:, m])[0]
+                cov.setdefault(m, []).extend(zip((nz + rr["lo"]).tolist(), rr["covT"][nz, m].tolist()))
+        t = whole.raw_snp_table
+        assert sorted(snv_pos) == sorted(zip(t["position"].astype(int), t["mm"].astype(int))) and len(t) > 100
+        l = whole.raw_linkage_table
+        assert sorted(ld_keys) == sorted(zip(l["position_A"].astype(int), l["position_B"].astype(int), l["mm"].astype(int),
+                                            l["countAB"].astype(int))) and len(l) > 100
+        for m, s in whole.scaffolds[name].covT.items():
+            assert sorted(cov.get(int(m), [])) == list(zip(s.index.tolist(), s.values.tolist())), m
+    finally:
+        eng.close()
