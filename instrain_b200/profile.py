@@ -91,6 +91,29 @@ def _fdb_splits(Fdb, scaffold, length, window_length):
     return _SplitTable(Fdb if Fdb is None else Fdb[Fdb["scaffold"] == scaffold], window_length)(scaffold, length)
 
 
+def _rss():
+    try:
+        import psutil
+        return psutil.Process(os.getpid()).memory_info().rss
+    except Exception:                                                     # noqa: BLE001 - psutil is optional here
+        return 0
+
+
+def worker_log(worker_type, unit, status, t=None):
+    """A line of the reference's run log (inStrain/logUtils.py:940-975, get_worker_log): "WorkerLog worker_type unit status
+    RAM time PID" -- what its log parser (logUtils.py:167, 401-470) turns into the per-split / per-scaffold run report.
+    Emitted for every (scaffold, split) of a batch (SplitProfile, profile_utilities.py:135,213) and every scaffold
+    (MergeProfile, :756-802) with the batch's start / end times: a batch is the unit of work here."""
+    assert status in ("start", "end")
+    return "\nWorkerLog {0} {1} {2} {3} {4} {5}".format(worker_type, unit, status, _rss(), time.time() if t is None else t, os.getpid())
+
+
+def log_checkpoint(log_class, name, status):
+    """"Checkpoint class task status RAM" (inStrain/logUtils.py:903-937)."""
+    assert status in ("start", "end") and len(name.split()) == 1
+    logging.debug("Checkpoint {0} {1} {2} {3}".format(log_class, name, status, _rss()))
+
+
 def _r2m_levels(r2m):
     """mm levels a scaffold's R2M needs on the device (1 in set mode)."""
     if isinstance(r2m, dict) and r2m:
@@ -296,6 +319,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
 
     def _flush(batch):
         cat = np.concatenate
+        t_batch = time.time()
         pad = batch.get("pad", 0)
         ref_codes = cat(([np.full(pad, 4, np.uint8)] if pad else []) + batch["ref"])
         offs = np.array(batch["off"], dtype=np.int64)
@@ -349,6 +373,15 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             q["pos_a"] = rel_a
             res.rows["ld"].append(q)
             res.rows["ld_sidx"].append(gidx[sidx])
+        if logging.getLogger().isEnabledFor(logging.DEBUG):                # the reference's per-split / per-scaffold log lines
+            t_end, msg = time.time(), []
+            for name, n_sp in zip(batch["names"], batch["n_splits"]):
+                for k in range(n_sp):
+                    msg.append(worker_log("SplitProfile", "{0}.{1}".format(name, k), "start", t_batch))
+                    msg.append(worker_log("SplitProfile", "{0}.{1}".format(name, k), "end", t_end))
+                msg.append(worker_log("MergeProfile", name, "start", t_end))
+                msg.append(worker_log("MergeProfile", name, "end", t_end))
+            logging.debug("".join(msg))
         for name, off in zip(batch["names"], offs):
             sp = ScaffoldProfile(name, len(s2s[name]))
             sl = slice(int(off), int(off) + len(s2s[name]))
@@ -461,7 +494,9 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
         if kwargs.get("skip_mm_profiling"):
             sR2M = {s: set(d) for s, d in sR2M.items()}
     t_filter = time.time() - t_start
+    log_checkpoint("Profile", "B200_profile_scaffolds", "start")
     res = profile_scaffolds(bam, sR2M, s2s, Fdb=Fdb, **kwargs)
+    log_checkpoint("Profile", "B200_profile_scaffolds", "end")
     res.timing["read_filter_s"] = t_filter
     # the SNVprofile directory at ISP_loc (gen_snv_profile, profile_utilities.py:670-706), written natively:
     # inStrain.SNVprofile.SNVprofile(ISP_loc) of the reference opens it unchanged
@@ -470,7 +505,9 @@ def profile_bam(bam, Fdb, sR2M, ISP_loc, **kwargs):
     from .store import store_profile
     fdef = dict(min_read_ani=0.95, min_mapq=-1, max_insert_relative=3, min_insert=50)    # this shim's filter defaults
     t_store = time.time()
+    log_checkpoint("Profile", "B200_store", "start")
     S = store_profile(ISP_loc, bam, res, mapping_info=report, **{k: kwargs.get(k, v) for k, v in fdef.items()})
+    log_checkpoint("Profile", "B200_store", "end")
     res.timing["store_s"] = time.time() - t_store
     res.timing["total_s"] = time.time() - t_start
     res.store = S

@@ -169,3 +169,36 @@ def test_profile_bam_runs_its_own_read_filter_and_reports_it(tmp_path, monkeypat
     assert lines[1].split("\t")[:3] == ["scaffold", "pass_pairing_filter", "filtered_pairs"]
     snvs = pd.read_csv(os.path.join(out, base + "SNVs.tsv"), sep="\t")
     assert not snvs.duplicated(["scaffold", "position"]).any() and list(snvs.columns[:4]) == ["scaffold", "position", "position_coverage", "allele_count"]
+
+
+def test_run_log_lines_follow_the_reference_format(tmp_path, monkeypatch, caplog):
+    """profile_bam emits the reference's run-log lines at DEBUG level: "WorkerLog SplitProfile <scaffold>.<split> start|end
+    RAM time PID" for every split, "WorkerLog MergeProfile <scaffold> ..." for every scaffold (inStrain/logUtils.py:940-975;
+    parsed at :167 by splitting on whitespace) and "Checkpoint Profile <task> start|end RAM" (:903-937)."""
+    import logging
+    import instrain_b200.profile as P
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+
+    class E(OracleEngine):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(P, "Engine", E)
+    monkeypatch.setenv("ISB_NATIVE_STORE", "1")
+    name = "N5_271_010G1_scaffold_963"
+    with caplog.at_level(logging.DEBUG):
+        P.profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, {name: rdic[name]}, str(tmp_path / "l.IS"), s2s=seqs,
+                      window_length=300)
+    lines = [l for r in caplog.records for l in r.getMessage().split("\n") if l.startswith(("WorkerLog", "Checkpoint"))]
+    wl = [l.split() for l in lines if l.startswith("WorkerLog")]
+    assert all(len(w) == 7 and w[3] in ("start", "end") and float(w[5]) > 0 and int(w[6]) == os.getpid() for w in wl)
+    splits = sorted({w[2] for w in wl if w[1] == "SplitProfile"})
+    assert splits == ["%s.%d" % (name, k) for k in range(len(splits))] and len(splits) >= 3
+    assert [w[2] for w in wl if w[1] == "MergeProfile"] == [name, name]
+    cp = [l.split() for l in lines if l.startswith("Checkpoint")]
+    assert [(c[1], c[2], c[3]) for c in cp] == [("Profile", "B200_profile_scaffolds", "start"), ("Profile", "B200_profile_scaffolds", "end"),
+                                                ("Profile", "B200_store", "start"), ("Profile", "B200_store", "end")]
