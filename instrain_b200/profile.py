@@ -44,6 +44,7 @@ class ScaffoldProfile:
         self.scaffold, self.length = scaffold, length
         self.raw_snp_table = self.raw_linkage_table = None
         self.covT, self.clonT, self.clonTR = {}, {}, {}
+        self.pileup_counts = None       # [length, 4] A,C,T,G counts over all mm levels, with kwargs["store_everything"] only
 
 
 class ProfileResult:
@@ -291,6 +292,7 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
     snp_tabs, ld_tabs, sum_tabs = [], [], []
     # keep_rows = {scaffold: global index}: also keep the raw row arrays with scaffold-relative positions, the global
     # scaffold index and the reference character per row -- what a rank sends to rank 0 (profile_bam_distributed)
+    store_everything = bool(kwargs.get("store_everything", False))     # --store_everything: keep the raw pileup counts
     keep_rows = kwargs.get("keep_rows")
     res.rows = dict(snv=[], snv_sidx=[], snv_ref=[], ld=[], ld_sidx=[]) if keep_rows is not None else None
 
@@ -339,8 +341,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
         t_e = time.time()
         out = engine.profile_batch(dict(pair_mm=cat(batch["pair_mm"])), ref_codes, np.array(batch["splits"], np.int32),
                                    min_cov=min_cov, min_freq=min_freq, min_snp=min_snp,
-                                   want=("covT", "clonT", "clonTR", "nmask", "snv", "ld"), rarefied_coverage=rarefied_coverage,
-                                   seed=seed, **fmt)
+                                   want=("covT", "clonT", "clonTR", "nmask", "snv", "ld") + (("counts",) if store_everything else ()),
+                                   rarefied_coverage=rarefied_coverage, seed=seed, **fmt)
         # merge-stage summary (K4): cumulative_scaffold_table rows of this batch
         bounds = np.append(offs, len(ref_codes)).astype(np.int32)
         if pad:                                                           # the unused leading positions: a dummy segment
@@ -390,6 +392,8 @@ def profile_scaffolds(bam, sR2M, s2s, Fdb=None, engine=None, device=0, max_batch
             sp.clonT = tables.basewise(out["clonT"][sl], "clonality", levels)
             if "clonTR" in out:
                 sp.clonTR = tables.basewise(out["clonTR"][sl], "clonality", levels)
+            if store_everything:                                          # pileup_counts[RelPosition] = total counts (profile_utilities.py:167-168,258-259)
+                sp.pileup_counts = out["counts"][sl].sum(axis=1).astype(np.int64)
             res.scaffolds[name] = sp
             res.scaffold_list.append(name)
 

@@ -300,6 +300,9 @@ def store_profile(ISP_loc, bam, res, mapping_info=None, **kwargs):
     if any(p.clonTR for p in res.scaffolds.values()):
         items.append(("clonTR", {s: p.clonTR for s, p in res.scaffolds.items()}, "special",
                       "Scaffold -> mm -> rarefied position based clonality"))
+    if any(p.pileup_counts is not None for p in res.scaffolds.values()):   # --store_everything (profile_utilities.py:709-715)
+        items.append(("counts_table", [res.scaffolds[s].pileup_counts for s in res.scaffold_list if s in res.scaffolds], "pickle",
+                      "1d numpy array of 2D counts tables for each scaffold"))
     S.store_many(items, threads=int(kwargs.pop("store_threads", 0) or min(8, os.cpu_count() or 1)))
     for name in ("SNVs", "scaffold_info", "linkage"):                     # ProfileController.write_output (controller.py:352-360)
         S.generate(name)

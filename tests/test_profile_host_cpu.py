@@ -202,3 +202,35 @@ def test_run_log_lines_follow_the_reference_format(tmp_path, monkeypatch, caplog
     cp = [l.split() for l in lines if l.startswith("Checkpoint")]
     assert [(c[1], c[2], c[3]) for c in cp] == [("Profile", "B200_profile_scaffolds", "start"), ("Profile", "B200_profile_scaffolds", "end"),
                                                 ("Profile", "B200_store", "start"), ("Profile", "B200_store", "end")]
+
+
+def test_store_everything_keeps_the_pileup_counts(tmp_path, monkeypatch):
+    """--store_everything: the SNVprofile gets `counts_table`, one [length, 4] array of A,C,T,G counts over all mm levels per
+    scaffold (profile_utilities.py:167-168, 258-259, 709-715)."""
+    import instrain_b200.profile as P
+    from instrain_b200.store import SNVprofileStore
+    seqs = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_seqs.json")))
+    rdic = json.load(open(os.path.join(GOLDEN, "c1_G1_subset_r2m.json")))
+
+    class E(OracleEngine):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(P, "Engine", E)
+    monkeypatch.setenv("ISB_NATIVE_STORE", "1")
+    names = ["N5_271_010G1_scaffold_963", "N5_271_010G1_scaffold_62"]
+    out = P.profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, {n: rdic[n] for n in names}, str(tmp_path / "e.IS"), s2s=seqs,
+                        store_everything=True)
+    tab = SNVprofileStore(str(tmp_path / "e.IS")).get("counts_table")
+    res = out.result
+    assert len(tab) == 2 and [t.shape for t in tab] == [(len(seqs[n]), 4) for n in res.scaffold_list]
+    for n, t in zip(res.scaffold_list, tab):
+        cov = np.zeros(len(seqs[n]), dtype=np.int64)
+        for mm, ser in res.scaffolds[n].covT.items():
+            cov[ser.index.values] += ser.values
+        assert np.array_equal(t.sum(axis=1), cov) and t.sum() > 1000      # total counts = coverage summed over the levels
+    plain = P.profile_bam(os.path.join(GOLDEN, "c1_G1_subset.bam"), None, {n: rdic[n] for n in names}, str(tmp_path / "p.IS"), s2s=seqs)
+    assert SNVprofileStore(str(tmp_path / "p.IS")).get("counts_table") is None and plain.result.scaffolds[names[0]].pileup_counts is None
