@@ -66,6 +66,36 @@ def test_clipped_runs_equal_the_whole_scaffold():
     assert np.array_equal(clonT[ok].view(np.uint32), whole["clonT"][ok].view(np.uint32))
 
 
+def test_clip_reads_property_random_ranges():
+    """clip_reads on ragged segments (short pieces, odd block sizes, non-ACGT events) and arbitrary, unaligned ranges --
+    empty ones included: the clipped batch obeys the layout rules and encodes exactly the events of the range."""
+    rng = np.random.default_rng(20260503)
+    batch = synth.make_batch(9000, 25, 0.05, 77, n_scaffolds=2, skip_mm=True, n_frac=0.004)
+    rd = reads.events_to_reads(batch, max_len=37, odd_blocks=True)
+    full = reads.reads_to_events(rd)
+    L = len(batch["ref_codes"])
+    ranges = [(0, L), (0, 1), (L - 1, L), (4321, 4322), (17, 17 + 8)] + [tuple(sorted(rng.integers(0, L, 2))) for _ in range(40)]
+    for lo, hi in ranges:
+        lo, hi = int(lo), int(hi)
+        if hi <= lo:
+            hi = lo + 1
+        sub, origin = reads.clip_reads(rd, lo, hi)
+        assert origin == lo & ~7
+        ev = reads.reads_to_events(sub)
+        sel = (full["ref_pos"] >= lo) & (full["ref_pos"] < hi)
+        for k in ("ref_pos", "base", "read_id"):
+            assert np.array_equal(ev[k], full[k][sel]), (k, lo, hi)
+        s, n, w = sub["seg_start"].astype(np.int64), sub["seg_len"].astype(np.int64), sub["seg_word"]
+        assert (np.diff(s) >= 0).all() and (n >= 1).all() and (s >= lo).all() and (s + n <= hi).all()
+        nw = ((s & 7) + n + 7) // 8
+        assert (w[1:] == w[:-1] + nw[:-1] + 1).all() and (len(w) == 0 or w[0] == 1)
+        assert sub["n_words"] % 4 == 0 and (len(w) == 0 or w[-1] + nw[-1] + 1 <= sub["n_words"])
+        sep = np.ones(sub["n_words"], dtype=bool)                      # every word outside the segments' data words is zero
+        for a, b in zip(w, nw):
+            sep[a:a + b] = False
+        assert not sub["words"][sep].any()
+
+
 # ---- on the device --------------------------------------------------------------------------------------------------------
 import pytest
 
