@@ -47,7 +47,7 @@
 #define K1F_LEVELS 32                  // mm levels per pass of the M > 1 kernel (shared-memory accumulators)
 #endif
 #ifndef K1F_STAGE_IT
-#define K1F_STAGE_IT 4                 // segment-table elements per thread and staging pass
+#define K1F_STAGE_IT 2                 // segment-table elements per thread and staging pass (measured 1 / 2 / 4 / 8: K1f 0.432 / 0.411 / 0.427 / 0.478 ms per 2e7 positions)
 #endif
 #define K1F_SEG_CAP_MAX 6144           // segments staged per chunk at most (8 B each: one chunk per tile up to ~700x coverage)
 #define K1F_TILE4 (256 + 32)           // count quads of a warp's 256 positions + one pad quad per 8 positions
