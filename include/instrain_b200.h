@@ -226,7 +226,7 @@ int isb_profile_batch_packed(isb_ctx *ctx, const isb_packed_batch *in, const isb
  * is not an event at all) or when it is not A/C/T/G.  Passing non-ACGT bases -- which only make their pair's mm level a
  * key of the position's MMcounts (the nmask bit) -- are listed separately (nev_pos / nev_pair; usually empty).
  * 4 bits per aligned base + ~22 bytes per segment instead of 10 bytes per event: 16x less HBM traffic for the pileup
- * and ~1.8x less PCIe traffic than the packed format.  The pileup kernel (K1r, isb_k1r_reads.cu) transposes on the fly:
+ * and ~1.8x less PCIe traffic than the packed format.  The pileup kernel (K1f, isb_k1f_fused.cu) transposes on the fly:
  * every thread owns 8 consecutive positions and counts the codes of the segments that cover them with bit-sliced
  * (vertical, carry-save) counters -- no atomics.
  *
@@ -266,9 +266,11 @@ typedef struct {
     int32_t pad2;
 } isb_reads_batch;
 
-/* stage K1r alone: counts[L][M][4] (+ nmask[L], may be NULL) from a read-major batch */
+/* the pileup stage alone (K1f, unfused): counts[L][M][4] (+ nmask[L], may be NULL) from a read-major batch */
 int isb_pileup_reads(isb_ctx *ctx, const isb_reads_batch *in, int32_t *counts, uint64_t *nmask);
-/* K1r -> K2 -> K3 (site events materialised from the segments) on a read-major batch; same results as
+/* The whole path on a read-major batch -- the default path.  M = 1 and no raw counts asked: K1f (pileup + single-allele
+ * sites) -> k2q_sites (general SNV call on the site queue) -> k3f_site_rows -> linkage back end; otherwise K1f (counts) ->
+ * K2 -> K3 (site events materialised from the segments).  Same results as
  * isb_profile_batch on the event columns of the same reads.  isb_params.min_qual is not used (the codes carry it). */
 int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params *prm, isb_result *out);
 
@@ -281,7 +283,7 @@ int isb_profile_reads(isb_ctx *ctx, const isb_reads_batch *in, const isb_params 
  * order, profile_utilities.py:34-35) in bits 2j..2j+1 of base2, event bit j of pass (1 = the base survives htslib's
  * base-quality filter after the mate-overlap tweak and is A/C/T/G).  Passing non-ACGT bases go to nev_pos / nev_pair as
  * in isb_reads_batch.  K0r (isb_k0r_expand.cu) rebuilds seg_word and the canonical nibble stream in device memory, then
- * K1r -> K2 -> K3 run as in isb_profile_reads: results are identical.  Same ordering / range rules for the segments. */
+ * the kernels of isb_profile_reads run: results are identical.  Same ordering / range rules for the segments. */
 typedef struct {
     int64_t n_segs;
     const int32_t *seg_start;   /* [n_segs] ascending */
@@ -317,7 +319,7 @@ int isb_profile_reads_compact(isb_ctx *ctx, const isb_reads_compact *in, const i
  * position in the word, bits 0-3 the XOR of the one-hot codes of the reference base (0 if not A/C/T/G) and of the read
  * base.  ~1.1 bits per aligned base + 5 bytes per mismatch instead of 3 bits per base: about half the bytes of
  * isb_reads_compact at 1 % divergence.  K0d (isb_k0r_expand.cu) rebuilds the nibble stream on the device (reference
- * codes masked by the event bits, then the listed nibbles flipped), then K1r -> K2 -> K3 run as in isb_profile_reads:
+ * codes masked by the event bits, then the listed nibbles flipped), then the kernels of isb_profile_reads run:
  * results are identical. */
 typedef struct {
     int64_t n_segs;
