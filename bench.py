@@ -748,7 +748,7 @@ def main():
         # copy of one call overlaps the kernels and the D2H copy of the others, which is how a host pipeline feeds the GPU.
         dt_pipe, dt_pipe3 = None, None
         try:
-            extra = [(Engine(local_rank, lut, dflt),) + host_result() for _ in range(2)]     # (engine, host tables, isb_result)
+            extra = [(Engine(local_rank, lut, dflt),) + host_result() for _ in range(2 if world == 1 else 1)]     # (engine, host tables, isb_result)
             errs = []
 
             def worker(c, r, n):
@@ -758,7 +758,7 @@ def main():
                 except Exception as ex:                      # noqa: BLE001
                     errs.append(str(ex))
 
-            for n_ctx in (2, 3):
+            for n_ctx in ((2, 3) if world == 1 else (2,)):          # N > 1: the ranks already share the host's cores and PCIe root
                 ctxs = [(eng.ctx, hres)] + [(e_[0].ctx, e_[2]) for e_ in extra[:n_ctx - 1]]
                 for n_it in (4, max(25, n_calls // 2)):     # the first repetition warms the extra contexts' scratch buffers
                     torch.cuda.synchronize()
