@@ -492,6 +492,13 @@ void isb_events_free(void *events);
  * 4 words, and isb_reads_copy() rebases seg_word to word_base = the index where this scaffold's stream is placed. */
 void *isb_pack_scaffold_reads(void *bam, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
                               const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual);
+/* The same for the reads that overlap the scaffold positions [lo, hi) only (hi <= lo: the whole scaffold): what an index
+ * fetch of that region hands htslib's pileup (inStrain/polymorpher.py:287-293).  Reading stops at the first record that
+ * starts at or behind hi, so the reader is left inside the scaffold: seek (isb_bam_seek) or close it afterwards.  Used to
+ * profile ONE large scaffold by contiguous runs of its splits on several GPUs (instrain_b200.profile.profile_scaffold_run). */
+void *isb_pack_scaffold_reads_region(void *bam, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                                     const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual,
+                                     int64_t lo, int64_t hi);
 int64_t isb_reads_segs(void *reads);
 int64_t isb_reads_stream_words(void *reads);
 int64_t isb_reads_pairs(void *reads);

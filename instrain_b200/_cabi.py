@@ -44,7 +44,7 @@ EXPORTS = ["isb_create", "isb_destroy", "isb_last_error", "isb_abi_version", "is
            "isb_bam_open", "isb_bam_close", "isb_bam_n_refs", "isb_bam_ref_name", "isb_bam_ref_len", "isb_bam_error",
            "isb_bam_peek_tid", "isb_host_last_error", "isb_bam_seek", "isb_pack_scaffold", "isb_events_count", "isb_events_pairs", "isb_events_reads_seen",
            "isb_events_reads_packed", "isb_events_copy", "isb_events_free",
-           "isb_pack_scaffold_reads", "isb_reads_segs", "isb_reads_stream_words", "isb_reads_pairs", "isb_reads_n_events",
+           "isb_pack_scaffold_reads", "isb_pack_scaffold_reads_region", "isb_reads_segs", "isb_reads_stream_words", "isb_reads_pairs", "isb_reads_n_events",
            "isb_reads_nev", "isb_reads_max_len", "isb_reads_reads_seen", "isb_reads_reads_packed", "isb_reads_copy",
            "isb_reads_free",
            "isb_filter_open", "isb_filter_open_mt", "isb_filter_apply", "isb_filter_apply2", "isb_filter_tally2", "isb_filter_n_refs", "isb_filter_max_insert", "isb_filter_tally", "isb_filter_stats", "isb_filter_stats2",

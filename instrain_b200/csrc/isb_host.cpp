@@ -343,7 +343,11 @@ struct Loaded {
 
 // Consume every record of scaffold `tid` (the file is coordinate-sorted, so they are contiguous), keep the reads whose
 // name is in the list and apply the mate-overlap quality tweak in file order (bam_plp overlap_push, ignore_overlaps=True).
-static void load_scaffold(Bam *b, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off, Loaded &ld)
+// Region form (lo < hi): only the reads that overlap the scaffold positions [lo, hi) are kept -- what an index fetch of that
+// region hands htslib's pileup (inStrain/polymorpher.py:287-293; the split-run sharding of one large scaffold) -- and
+// reading stops at the first record that starts at or behind hi (the reader is then left INSIDE the scaffold).
+static void load_scaffold(Bam *b, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off, Loaded &ld,
+                          int64_t lo = 0, int64_t hi = -1)
 {
     std::unordered_map<std::string, int32_t> name2idx;
     name2idx.reserve((size_t)n_names * 2 + 16);
@@ -356,10 +360,11 @@ static void load_scaffold(Bam *b, int tid, int64_t n_names, const char *names_bl
         const int t = isb_bam_peek_tid(b);
         if (t != tid) break;
         const uint8_t *p = b->pending.data();
-        b->has_pending = false;
-        ld.n_reads_seen++;
         int32_t core[8];
         memcpy(core, p, 32);
+        if (hi > lo && (int64_t)core[1] >= hi) break;                // sorted by position: nothing further overlaps the region
+        b->has_pending = false;
+        ld.n_reads_seen++;
         BamRec r;
         r.tid = core[0]; r.pos = core[1];
         const uint32_t bmq = (uint32_t)core[2];
@@ -373,6 +378,16 @@ static void load_scaffold(Bam *b, int tid, int64_t n_names, const char *names_bl
         if (it == name2idx.end()) continue;                          // not in R2M: can never be counted
         r.name_idx = it->second;
         const uint8_t *q = p + 32 + l_read_name;
+        if (hi > lo) {                                               // ends in front of the region: not fetched
+            uint32_t cg[64];
+            int64_t rl = 0;
+            for (uint32_t c0 = 0; c0 < r.n_cigar; c0 += 64) {
+                const int nc = (int)std::min<uint32_t>(64, r.n_cigar - c0);
+                memcpy(cg, q + 4u * c0, 4u * nc);
+                rl += ref_len_of(cg, nc);
+            }
+            if ((int64_t)r.pos + rl <= lo) continue;
+        }
         r.cig_off = (uint32_t)cigs.size();
         cigs.resize(cigs.size() + r.n_cigar);
         memcpy(cigs.data() + r.cig_off, q, 4u * r.n_cigar);
@@ -499,12 +514,23 @@ struct ReadsOut {
     int max_len = 1;
 };
 
+void *isb_pack_scaffold_reads_region(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                                     const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual,
+                                     int64_t lo, int64_t hi);
+
 void *isb_pack_scaffold_reads(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
                               const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual)
 {
+    return isb_pack_scaffold_reads_region(h, tid, n_names, names_blob, name_off, name_mm, pos_offset, pair_id_offset, min_qual, 0, -1);
+}
+
+void *isb_pack_scaffold_reads_region(void *h, int tid, int64_t n_names, const char *names_blob, const int64_t *name_off,
+                                     const uint8_t *name_mm, int32_t pos_offset, int32_t pair_id_offset, int min_qual,
+                                     int64_t lo, int64_t hi)
+{
     Bam *b = (Bam *)h;
     Loaded ld;
-    load_scaffold(b, tid, n_names, names_blob, name_off, ld);
+    load_scaffold(b, tid, n_names, names_blob, name_off, ld, lo, hi);
     if (b->bad) return nullptr;                                   // corrupt / truncated BAM: isb_bam_error() has the reason
     ReadsOut *out = new ReadsOut();
     out->n_reads_seen = ld.n_reads_seen;

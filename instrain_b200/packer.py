@@ -39,6 +39,8 @@ def _lib():
         L.isb_events_free.argtypes = [vp]
         L.isb_pack_scaffold_reads.restype = vp
         L.isb_pack_scaffold_reads.argtypes = [vp, C.c_int, i64, C.c_char_p, vp, vp, i32, i32, C.c_int]
+        L.isb_pack_scaffold_reads_region.restype = vp
+        L.isb_pack_scaffold_reads_region.argtypes = [vp, C.c_int, i64, C.c_char_p, vp, vp, i32, i32, C.c_int, i64, i64]
         for f in ("isb_reads_segs", "isb_reads_stream_words", "isb_reads_pairs", "isb_reads_n_events", "isb_reads_nev",
                   "isb_reads_reads_seen", "isb_reads_reads_packed"):
             getattr(L, f).restype = i64
@@ -117,12 +119,15 @@ class BamPacker:
             mm = np.zeros(len(names), dtype=np.uint8)
         return len(names), b"".join(enc), off, mm
 
-    def pack_scaffold_reads(self, tid, r2m, pos_offset=0, pair_id_offset=0, min_qual=30):
+    def pack_scaffold_reads(self, tid, r2m, pos_offset=0, pair_id_offset=0, min_qual=30, region=None):
         """Consume the records of scaffold `tid` as READ-MAJOR aligned segments (instrain_b200/reads.py layout, the
-        scaffold's own word stream: `stream` = [data words + one zero word] per segment, seg_word relative to it)."""
+        scaffold's own word stream: `stream` = [data words + one zero word] per segment, seg_word relative to it).
+        region = (lo, hi): only the reads that overlap the scaffold positions [lo, hi) (an index fetch of that region);
+        reading stops behind it, the reader is left inside the scaffold."""
         n_names, blob, off, mm = self._names(r2m)
-        r = self.lib.isb_pack_scaffold_reads(self.h, tid, n_names, blob, off.ctypes.data, mm.ctypes.data, pos_offset,
-                                             pair_id_offset, min_qual)
+        lo, hi = (int(region[0]), int(region[1])) if region is not None else (0, -1)
+        r = self.lib.isb_pack_scaffold_reads_region(self.h, tid, n_names, blob, off.ctypes.data, mm.ctypes.data, pos_offset,
+                                                    pair_id_offset, min_qual, lo, hi)
         if not r:
             raise IOError("isb_pack_scaffold_reads failed: " + self.lib.isb_bam_error(self.h).decode())
         try:
@@ -196,6 +201,39 @@ def read_bai(path):
         o += 4 + 8 * n_intv
         out.append(first)
     return out
+
+
+def read_bai_linear(path):
+    """The linear index of a .bai (SAM spec 5.2): per reference the virtual offset of the first alignment that overlaps each
+    16 kb window (0 = no entry).  seek_offset(ioffset, first, lo) below picks where a region fetch starts reading."""
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"BAI\1":
+        raise IOError("not a BAI index: %s" % path)
+    n_ref, = struct.unpack_from("<i", data, 4)
+    o, out = 8, []
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", data, o)
+        o += 4
+        for _ in range(n_bin):
+            _, n_chunk = struct.unpack_from("<Ii", data, o)
+            o += 8 + 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", data, o)
+        out.append(np.frombuffer(data, dtype="<u8", count=n_intv, offset=o + 4).copy())
+        o += 4 + 8 * n_intv
+    return out
+
+
+def seek_offset(ioffset, first, lo):
+    """Virtual offset a fetch of positions >= lo starts at: the linear-index entry of lo's 16 kb window (every read that
+    overlaps lo overlaps that window), falling back to earlier windows and to the reference's first alignment."""
+    k = min(int(lo) >> 14, len(ioffset) - 1)
+    while k >= 0:
+        if ioffset[k]:
+            return int(ioffset[k])
+        k -= 1
+    return first
 
 
 def scan_scaffold_offsets(bam):

@@ -430,21 +430,22 @@ def profile_scaffold_run(bam, name, r2m, seq, run_splits, engine, **kwargs):
     (instrain_b200.reads.clip_reads) and the run is profiled as a batch of its own with start = its origin, so rows come
     back in scaffold coordinates.  run_splits: [(start, end)] of the run, in order.  Returns dict(snv, ld: row arrays;
     lo, hi; covT, clonT, clonTR, nmask: dense arrays of the positions [lo, hi); M)."""
-    from .packer import find_bai, read_bai
+    from .packer import find_bai, read_bai, read_bai_linear, seek_offset
     lo, hi = int(run_splits[0][0]), int(run_splits[-1][1]) + 1
     with BamPacker(bam) as bp:
         tid = bp.ref_names.index(name)
         bai = find_bai(bam)
-        if bai is not None:
+        if bai is not None:                                               # straight to the first read that can overlap the run
             first = read_bai(bai)[tid]
             if first is not None:
-                bp.seek(first)
+                bp.seek(seek_offset(read_bai_linear(bai)[tid], first, lo))
         while True:
             t = bp.peek_tid()
             if t < 0 or t >= tid:
                 break
             bp.pack_scaffold_reads(t, {})                                  # no index: skip the earlier scaffolds
-        part = bp.pack_scaffold_reads(tid, r2m) if bp.peek_tid() == tid else None
+        # only the reads that overlap the run are read and packed (the read halo); reading stops behind the run
+        part = bp.pack_scaffold_reads(tid, r2m, region=(lo, hi)) if bp.peek_tid() == tid else None
     L_run = hi - (lo & ~7)
     if part is None or len(part["seg_start"]) == 0:
         M = _r2m_levels(r2m)

@@ -152,21 +152,28 @@ def write_bam(path, L, n_scaffolds, coverage, snv_density, seed, level=1, name_p
     for nm in names:
         hdr += struct.pack("<i", len(nm) + 1) + nm.encode() + b"\0" + struct.pack("<i", L)
     w.write(bytes(hdr))
-    seqs, spans, n_reads, name_off = {}, [], 0, 0
+    seqs, spans, linear, n_reads, name_off = {}, [], [], 0, 0
     letters = np.frombuffer(b"ACTG", dtype=np.uint8)
     for tid, nm in enumerate(names):
         ref, rd = _scaffold_reads(rng, L, coverage, snv_density)
         seqs[nm] = letters[ref].tobytes().decode()
         rec = _records(tid, rd, name_off)
         beg = w.tell()
-        w.write(rec.reshape(-1))
+        # linear index: for every 16 kb window the first record that overlaps it (records are sorted, all READLEN long)
+        n_win = (L + 16383) >> 14
+        first_rec = np.searchsorted(rd["pos"] + READLEN, np.arange(n_win) * 16384, side="right")
+        has = first_rec < len(rec)
+        voffs = w.write(rec.reshape(-1), boundaries=(first_rec[has] * REC).tolist())
+        lin = np.zeros(n_win, dtype="<u8")
+        lin[has] = voffs
+        linear.append(lin)
         spans.append((beg, w.tell()))
         n_reads += len(rec)
         name_off += rd["n_pairs"]
     w.close()
-    with open(path + ".bai", "wb") as f:                            # one bin with one chunk per reference: enough to seek to it
+    with open(path + ".bai", "wb") as f:                            # one bin with one chunk per reference
         f.write(b"BAI\1" + struct.pack("<i", n_scaffolds))
-        for beg, end in spans:
-            f.write(struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", beg, end) + struct.pack("<i", 0))
+        for (beg, end), lin in zip(spans, linear):                   # + the linear index (16 kb windows) for region fetches
+            f.write(struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", beg, end) + struct.pack("<i", len(lin)) + lin.tobytes())
     return dict(seqs=seqs, names=names, n_reads=n_reads, n_pairs=name_off, aligned_bases=n_reads * READLEN,
                 bytes=os.path.getsize(path))

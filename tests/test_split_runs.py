@@ -159,3 +159,52 @@ def test_gpu_bench_run_clipping_equals_the_whole_scaffold(eng):
     assert_snv_equal(np.concatenate(snv), whole["snv"])
     assert_ld_equal(np.concatenate(ld), whole["ld"], tol=0.0)
     assert np.array_equal(covT, whole["covT"])
+
+
+def test_region_packing_equals_clipping_the_whole_scaffold(tmp_path):
+    """The host side of a run: BamPacker.pack_scaffold_reads(region=...) after a seek through the .bai LINEAR index reads and
+    packs only the reads that overlap the run; cut to the run it encodes the same events as the whole scaffold's pack cut to
+    the run (the mate-overlap tweak only needs the reads a region fetch returns: tests/test_polymorpher_region.py)."""
+    from instrain_b200 import synth_bam
+    from instrain_b200.packer import BamPacker, find_bai, read_bai, read_bai_linear, seek_offset
+    from instrain_b200.read_filter import filter_reads
+    from instrain_b200.synth import iterate_splits
+    bam = str(tmp_path / "r.bam")
+    info = synth_bam.write_bam(bam, 70000, 2, 25, 0.02, seed=31)
+    r2m, _, _ = filter_reads(bam, info["names"])
+    first, linear = read_bai(find_bai(bam)), read_bai_linear(find_bai(bam))
+    assert all(len(l) == 5 and l.all() for l in linear)                    # 70 kb = 5 windows of 16 kb, all covered
+    for tid, name in enumerate(info["names"]):
+        with BamPacker(bam) as bp:
+            bp.seek(first[tid])
+            whole = reads.concat_streams([bp.pack_scaffold_reads(tid, r2m[name])])
+        sp = iterate_splits(70000, 10000)
+        seen = 0
+        for a, b in split_runs(sp, [e - s + 1 for s, e in sp], 3):
+            lo, hi = sp[a][0], sp[b - 1][1] + 1
+            with BamPacker(bam) as bp:
+                bp.seek(seek_offset(linear[tid], first[tid], lo))
+                part = bp.pack_scaffold_reads(tid, r2m[name], region=(lo, hi))
+            assert part["reads_seen"] < 0.6 * (info["n_reads"] // 2)        # a third of the scaffold (+ halo), not all of it
+            seen += part["reads_seen"]
+            got = reads.reads_to_events(reads.clip_reads(reads.concat_streams([part]), lo, hi)[0])
+            exp = reads.reads_to_events(reads.clip_reads(whole, lo, hi)[0])
+            assert len(exp["ref_pos"]) > 100000
+            # pair ids are numbered per pack (order inside a position differs): compare (position, base, mm of the pair) sets
+            wmm = whole_pair_mm(bam, tid, r2m[name])
+            ga = np.stack([got["ref_pos"], got["base"], part["pair_mm"][got["read_id"]]], axis=1)
+            ea = np.stack([exp["ref_pos"], exp["base"], wmm[exp["read_id"]]], axis=1)
+            ga, ea = ga[np.lexsort(ga.T[::-1])], ea[np.lexsort(ea.T[::-1])]
+            assert np.array_equal(ga, ea), (name, lo)
+            # and the pairing itself: events of one pair in the region pack are events of one pair in the whole pack
+            gk = np.unique(np.stack([got["read_id"], got["ref_pos"]], axis=1), axis=0)
+            ek = np.unique(np.stack([exp["read_id"], exp["ref_pos"]], axis=1), axis=0)
+            assert len(gk) == len(ek) and len(np.unique(gk[:, 0])) == len(np.unique(ek[:, 0]))
+        assert seen < 1.5 * (info["n_reads"] // 2)                         # the seek lands on a 16 kb window start: some reads read twice
+
+
+def whole_pair_mm(bam, tid, r2m):
+    from instrain_b200.packer import BamPacker, find_bai, read_bai
+    with BamPacker(bam) as bp:
+        bp.seek(read_bai(find_bai(bam))[tid])
+        return bp.pack_scaffold_reads(tid, r2m)["pair_mm"]
